@@ -1,0 +1,340 @@
+// dune-gdt_b200/csrc/assemble_q1_gather.cu -- owner-computes-rows ("row gather") assembly for
+// continuous-Lagrange Q1 spaces on axis-aligned structured grids.
+//
+// Replaces, for element forms whose integrands are sums of LocalLaplaceIntegrand / LocalElementProductIntegrand
+// with element-wise constant coefficients, the whole chain
+//   LocalElementBilinearFormAssembler::apply_local  (local/assembler/bilinear-form-assemblers.hh:110-128)
+//   LocalElementIntegralBilinearForm::apply2        (local/bilinear-forms/integrals.hh:97-134)
+//   LocalLaplaceIntegrand / LocalElementProductIntegrand::evaluate (laplace.hh:81-102, product.hh:104-130)
+//   MatrixType::add_to_entry [EXT]
+// and the matching functional chain (functional-assemblers.hh:77-86, local/functionals/integrals.hh:72-98).
+//
+// Formulation.  On an axis-aligned cell with an element-constant coefficient c_e the local matrix is
+// c_e * Lref, where Lref ("reference tensor") is the quadrature sum evaluated once for the cell shape with
+// the form's own Gauss rule (host side, capi.cu).  Instead of scattering 8x8 local matrices (read-modify-write,
+// 2^d colour passes, 5x the compulsory traffic -- SURVEY.md section 8d) every CSR row is produced exactly once by
+// the thread that owns its vertex: A[v][v+delta] = sum_{o in {0,1}^d} c_{e(v,o)} * Lref[i(o)][j(o,delta)],
+// i.e. at most 2^d * 2^d = 64 FMAs per row in 3D.  The CSR position of every entry is a closed form of the
+// vertex coordinates (tensor-product stencil), so neither rowptr nor colidx is read.
+//
+// Data movement.  One work item = one x-line chunk of vertices; its CSR values form ONE contiguous segment.
+// Rows are staged in shared memory in CSR order and leave the SM as a single TMA bulk store
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP) -- HBM sees only full-line sequential writes.  The kernel is
+// persistent-strided over work items with several CTAs per SM so that one CTA's store drains while the
+// others compute.  Deterministic (no atomics, fixed summation order).
+#include "common.cuh"
+#include "kernels.hpp"
+
+namespace gdtb {
+
+namespace {
+
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void bulk_store_s2g(double* gdst, const double* ssrc, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit()
+{
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void bulk_wait_read0()
+{
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void bulk_wait0()
+{
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// number of stencil columns before vertex index i along one axis with N cells: sum_{i' < i} n(i'),
+// n(i') = 2 at the two ends, 3 inside
+__device__ __forceinline__ long long S_axis(long long i, long long N)
+{
+  return i == 0 ? 0 : (i > N ? 3 * N + 1 : 3 * i - 1);
+}
+
+template <int D>
+struct P3
+{
+  static constexpr int value = D == 1 ? 3 : (D == 2 ? 9 : 27);
+};
+
+template <int D, bool ACCUMULATE>
+__global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values,
+                            double* __restrict__ rhs, int chunk, int nchunks, long long nitems)
+{
+  constexpr int NO = 1 << D;        // elements around a vertex
+  constexpr int ND = P3<D>::value;  // stencil size
+  extern __shared__ __align__(16) double smem[];
+  const GridDev& g = p.g;
+  const int last = D - 1;
+  const long long Nx = g.n[0], Ny = D > 1 ? g.n[1] : 1, Nz = D > 2 ? g.n[2] : 1;
+  const long long Wx = 3 * Nx + 1, Wy = D > 1 ? 3 * Ny + 1 : 1;
+  // vertex rows handled by this process along the last axis: [layer_lo, layer_hi]
+  const long long lines_y = D == 3 ? Ny + 1 : (D == 2 ? g.layer_hi - g.layer_lo + 1 : 1);
+
+  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const long long line = item / nchunks;
+    const int ch = int(item % nchunks);
+    long long iv[3] = {0, 0, 0};
+    if (D == 3) {
+      iv[1] = line % lines_y;
+      iv[2] = g.layer_lo + line / lines_y;
+    } else if (D == 2) {
+      iv[1] = g.layer_lo + line;
+    }
+    const long long x_lo = D == 1 ? g.layer_lo : 0, x_hi = D == 1 ? g.layer_hi + 1 : Nx + 1; // vertex range in x
+    const long long x0 = x_lo + (long long)ch * chunk;
+    const long long x1 = min(x0 + chunk, x_hi);
+
+    // stencil extents of this line in y and z
+    const int ny = D > 1 ? ((iv[1] == 0 || iv[1] == Ny) ? 2 : 3) : 1;
+    const int nz = D > 2 ? ((iv[2] == 0 || iv[2] == Nz) ? 2 : 3) : 1;
+    const int c = ny * nz;
+    // global CSR position of the first entry of the chunk
+    long long start;
+    if (D == 3)
+      start = S_axis(iv[2], Nz) * Wy * Wx + nz * (S_axis(iv[1], Ny) * Wx + ny * S_axis(x0, Nx));
+    else if (D == 2)
+      start = S_axis(iv[1], Ny) * Wx + ny * S_axis(x0, Nx);
+    else
+      start = S_axis(x0, Nx);
+    const long long seg = (long long)c * (S_axis(x1, Nx) - S_axis(x0, Nx));
+    start -= p.value_offset;
+    // keep the shared-memory and global 16-byte phases equal for the bulk copy
+    const int phase = values ? int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL) : 0;
+    double* stage = smem + phase;
+
+    const long long ix = x0 + threadIdx.x;
+    if (ix < x1) {
+      iv[0] = ix;
+      // element validity per axis and offset: e_k = i_k - 1 + o_k inside the grid and inside this process' layers
+      bool ok[3][2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const long long elo = (k == last) ? g.layer_lo : 0;
+        const long long ehi = (k == last) ? g.layer_hi : (k < D ? g.n[k] : 1);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const long long e = iv[k] - 1 + o;
+          ok[k][o] = k < D ? (e >= elo && e < ehi) : (o == 1);
+        }
+      }
+      double acc[ND];
+#pragma unroll
+      for (int dlt = 0; dlt < ND; ++dlt)
+        acc[dlt] = 0.;
+      double b = 0.;
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        const int ox = o & 1, oy = (o >> 1) & 1, oz = (o >> 2) & 1;
+        const bool valid = ok[0][ox] && (D < 2 || ok[1][oy]) && (D < 3 || ok[2][oz]);
+        const long long e = (ix - 1 + ox) + Nx * ((D > 1 ? iv[1] - 1 + oy : 0) + Ny * (D > 2 ? iv[2] - 1 + oz : 0));
+        if (p.has_const) {
+          const double m = valid ? 1. : 0.;
+#pragma unroll
+          for (int s = 0; s < NO; ++s) {
+            const int dx = ox - 1 + (s & 1), dy = D > 1 ? oy - 1 + ((s >> 1) & 1) : 0,
+                      dz = D > 2 ? oz - 1 + ((s >> 2) & 1) : 0;
+            const int dlt = (dx + 1) + (D > 1 ? 3 * (dy + 1) : 0) + (D > 2 ? 9 * (dz + 1) : 0);
+            acc[dlt] = fma(m, p.T_const[o][s], acc[dlt]);
+          }
+        }
+        for (int chn = 0; chn < p.n_elem; ++chn) {
+          const double cf = valid ? __ldg(p.coef[chn] + e) : 0.;
+#pragma unroll
+          for (int s = 0; s < NO; ++s) {
+            const int dx = ox - 1 + (s & 1), dy = D > 1 ? oy - 1 + ((s >> 1) & 1) : 0,
+                      dz = D > 2 ? oz - 1 + ((s >> 2) & 1) : 0;
+            const int dlt = (dx + 1) + (D > 1 ? 3 * (dy + 1) : 0) + (D > 2 ? 9 * (dz + 1) : 0);
+            acc[dlt] = fma(cf, p.T_elem[chn][o][s], acc[dlt]);
+          }
+        }
+        if (p.has_rhs) {
+          if (p.rhs_has_const && valid)
+            b += p.rhs_const;
+          if (p.rhs_has_elem && valid)
+            b = fma(p.rhs_elem_scale, __ldg(p.rhs_elem + e), b);
+        }
+      }
+      // rows in CSR order: (dz, dy, dx) ascending over the columns that exist
+      if (values) {
+        const int nx = (ix == 0 || ix == Nx) ? 2 : 3;
+        int pos = int((long long)c * (S_axis(ix, Nx) - S_axis(x0, Nx)));
+#pragma unroll
+        for (int dz = -1; dz <= 1; ++dz) {
+          if (D < 3 && dz != 0)
+            continue;
+          if (D == 3 && (iv[2] + dz < 0 || iv[2] + dz > Nz))
+            continue;
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            if (D < 2 && dy != 0)
+              continue;
+            if (D >= 2 && (iv[1] + dy < 0 || iv[1] + dy > Ny))
+              continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              if (ix + dx < 0 || ix + dx > Nx)
+                continue;
+              const int dlt = (dx + 1) + (D > 1 ? 3 * (dy + 1) : 0) + (D > 2 ? 9 * (dz + 1) : 0);
+              stage[pos++] = acc[dlt];
+            }
+          }
+        }
+        (void)nx;
+      }
+      if (p.has_rhs && rhs) {
+        if (p.rhs_has_sep) {
+          double t = p.rhs_sep_scale;
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+            t *= __ldg(p.rhs_sep_tab + k * p.rhs_sep_stride + iv[k]);
+          b += t;
+        }
+        long long row = ix;
+        if (D > 1)
+          row += (Nx + 1) * iv[1];
+        if (D > 2)
+          row += (Nx + 1) * (Ny + 1) * iv[2];
+        row -= p.row_offset;
+        if (ACCUMULATE)
+          rhs[row] += b;
+        else
+          rhs[row] = b;
+      }
+    }
+
+    if (values) {
+      if (ACCUMULATE) {
+        __syncthreads();
+        for (long long i = threadIdx.x; i < seg; i += blockDim.x)
+          values[start + i] += stage[i];
+        __syncthreads();
+      } else {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          // 16-byte aligned middle part by one bulk copy, at most one odd double at either end by plain stores
+          long long head = phase; // start odd -> first double is not 16B aligned
+          long long body = (seg - head) & ~1LL;
+          if (head)
+            values[start] = stage[0];
+          if (body > 0)
+            bulk_store_s2g(values + start + head, stage + head, (unsigned)(body * sizeof(double)));
+          if (head + body < seg)
+            values[start + head + body] = stage[head + body];
+          bulk_commit();
+          bulk_wait_read0();
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (!ACCUMULATE && values && threadIdx.x == 0)
+    bulk_wait0();
+}
+
+// Separable right-hand side tables: for f(x) = p0 * prod_k F_k(x_k),
+//   B_k[i] = sum over the (valid) cells e in {i-1, i} of  sum_q w_q phi_a(xi_q) F_k(lower_e + xi_q * ext_e),
+// a = local index of vertex i in cell e.  One block, strided over (axis, vertex).
+__global__ void k_q1_rhs_tables(const GridDev g, const FnDev f, int m, const double* __restrict__ qx,
+                                const double* __restrict__ qw, const double* __restrict__ phi,
+                                double* __restrict__ tab, long long stride)
+{
+  const int last = g.d - 1;
+  for (int k = 0; k < g.d; ++k) {
+    const long long elo = (k == last) ? g.layer_lo : 0;
+    const long long ehi = (k == last) ? g.layer_hi : g.n[k];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i <= g.n[k];
+         i += (long long)gridDim.x * blockDim.x) {
+      double s = 0.;
+      for (int o = 0; o < 2; ++o) {
+        const long long e = i - 1 + o;
+        if (e < elo || e >= ehi)
+          continue;
+        const int a = 1 - o;
+        const double lower = g.lo[k] + double(e) * g.h[k];
+        const double upper = g.lo[k] + double(e + 1) * g.h[k];
+        const double ext = upper - lower;
+        for (int q = 0; q < m; ++q) {
+          const double x = lower + qx[q] * ext;
+          double F = 1.;
+          if (f.builtin == GDTB_BUILTIN_COS_PRODUCT)
+            F = cos(f.p[1] * x);
+          else if (f.builtin == GDTB_BUILTIN_GAUSSIAN && k == 0) {
+            const double t = x - f.p[0];
+            F = exp(-(t * t) / (2. * (f.p[1] * f.p[1])));
+          } else if (f.builtin == GDTB_BUILTIN_INDICATOR && k == 0)
+            F = (f.p[0] <= x && x <= f.p[1]) ? 1. : 0.;
+          s += qw[q] * phi[q * 2 + a] * F;
+        }
+      }
+      tab[k * stride + i] = s;
+    }
+  }
+}
+
+} // namespace
+
+int launch_q1_rhs_tables(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx, const double* qw,
+                         const double* phi, double* tab, long long stride)
+{
+  k_q1_rhs_tables<<<8, 256, 0, L.stream>>>(g, f, m, qx, qw, phi, tab, stride);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+template <int D>
+static int launch_q1_gather_d(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
+{
+  const GridDev& g = p.g;
+  const long long nvx = D == 1 ? g.layer_hi - g.layer_lo + 1 : g.n[0] + 1;
+  const int max_chunk = 512;
+  const int nchunks = int((nvx + max_chunk - 1) / max_chunk);
+  const int chunk = int((nvx + nchunks - 1) / nchunks);
+  const int threads = ((chunk + 31) / 32) * 32;
+  long long nlines = 1;
+  if (D == 3)
+    nlines = (g.n[1] + 1) * (g.layer_hi - g.layer_lo + 1);
+  else if (D == 2)
+    nlines = g.layer_hi - g.layer_lo + 1;
+  const long long nitems = nlines * nchunks;
+  const size_t smem = values ? (size_t)(chunk * P3<D>::value + 2) * sizeof(double) : 16;
+  auto kern = accumulate ? k_q1_gather<D, true> : k_q1_gather<D, false>;
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1)
+    return fail(GDTB_ERR_CUDA, "q1_gather: kernel does not fit on an SM");
+  long long grid = (long long)per_sm * L.sm_count;
+  if (grid > nitems)
+    grid = nitems;
+  kern<<<(unsigned)grid, threads, smem, L.stream>>>(p, values, rhs, chunk, nchunks, nitems);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
+{
+  switch (p.g.d) {
+    case 1: return launch_q1_gather_d<1>(L, p, values, rhs, accumulate);
+    case 2: return launch_q1_gather_d<2>(L, p, values, rhs, accumulate);
+    case 3: return launch_q1_gather_d<3>(L, p, values, rhs, accumulate);
+    default: return fail(GDTB_ERR_INVALID_ARGUMENT, "q1_gather: dimension must be 1, 2 or 3");
+  }
+}
+
+} // namespace gdtb

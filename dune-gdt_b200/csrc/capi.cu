@@ -1,0 +1,1423 @@
+// dune-gdt_b200/csrc/capi.cu -- the C ABI of libgdtb (include/gdtb.h): handles, lowering of the appended local
+// forms to kernel descriptors, kernel selection, and the host<->device plumbing.  No CPU compute path exists:
+// every gdtb_assemble / gdtb_fvop_* call ends in the CUDA kernels of this directory or fails.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.hpp"
+
+namespace gdtb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg)
+{
+  g_last_error = msg;
+}
+
+int fail(int code, const std::string& msg)
+{
+  g_last_error = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side numerics needed for lowering: Gauss-Legendre rules on [0,1] and 1D Lagrange tables
+// ([EXT] dune-geometry QuadratureRules / dune-localfunctions Lagrange basis)
+// ------------------------------------------------------------------------------------------------
+static int gauss_points_for_order(int order)
+{
+  return std::max(order, 0) / 2 + 1;
+}
+
+static void gauss_legendre_01(int m, double* x, double* w)
+{
+  // Newton iteration on the Legendre polynomial P_m, extended precision, roots ascending
+  for (int i = 0; i < m; ++i) {
+    long double z = cosl(3.14159265358979323846264338327950288L * (i + 0.75L) / (m + 0.5L));
+    long double dp = 1.0L;
+    for (int it = 0; it < 100; ++it) {
+      long double p0 = 1.0L, p1 = z; // P_0, P_1
+      for (int j = 2; j <= m; ++j) {
+        const long double pj = ((2.0L * j - 1.0L) * z * p1 - (j - 1.0L) * p0) / j;
+        p0 = p1;
+        p1 = pj;
+      }
+      if (m == 0)
+        p1 = 1.0L;
+      dp = m * (z * p1 - p0) / (z * z - 1.0L);
+      const long double dz = p1 / dp;
+      z -= dz;
+      if (fabsl(dz) < 1e-19L)
+        break;
+    }
+    x[m - 1 - i] = (double)((1.0L + z) / 2.0L);
+    w[m - 1 - i] = (double)(1.0L / ((1.0L - z * z) * dp * dp));
+  }
+}
+
+static void lagrange_1d(int K, double x, double* v, double* dv)
+{
+  if (K == 0) {
+    v[0] = 1.;
+    dv[0] = 0.;
+    return;
+  }
+  for (int a = 0; a <= K; ++a) {
+    const double ta = double(a) / K;
+    double val = 1.;
+    for (int b = 0; b <= K; ++b)
+      if (b != a)
+        val *= (x - double(b) / K) / (ta - double(b) / K);
+    double der = 0.;
+    for (int c = 0; c <= K; ++c) {
+      if (c == a)
+        continue;
+      double t = 1. / (ta - double(c) / K);
+      for (int b = 0; b <= K; ++b)
+        if (b != a && b != c)
+          t *= (x - double(b) / K) / (ta - double(b) / K);
+      der += t;
+    }
+    v[a] = val;
+    dv[a] = der;
+  }
+}
+
+} // namespace gdtb
+
+using namespace gdtb;
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct gdtb_ctx
+{
+  int device;
+  cudaStream_t own_stream;
+  Launch launch;
+  int* d_error_flag;
+};
+
+struct gdtb_grid
+{
+  gdtb_ctx* ctx;
+  gdtb_grid_desc desc;
+  GridDev dev;
+};
+
+struct gdtb_space
+{
+  gdtb_ctx* ctx;
+  GridDev grid;
+  SpaceDev dev;
+};
+
+struct gdtb_pattern
+{
+  gdtb_ctx* ctx;
+  GridDev grid;
+  SpaceDev test, ansatz;
+  int stencil;
+  long long rows, cols, nnz;
+  long long* d_rowptr;
+  int* d_colidx;
+};
+
+namespace {
+
+struct LoweredForm
+{
+  gdtb_form form;                // cloned descriptor (data pointers replaced by device pointers)
+  std::vector<double*> owned;    // device arrays cloned from host data
+  int filter;
+};
+
+void free_form(LoweredForm& f)
+{
+  for (double* p : f.owned)
+    cudaFree(p);
+  f.owned.clear();
+}
+
+} // namespace
+
+struct gdtb_matop
+{
+  gdtb_ctx* ctx;
+  GridDev grid;
+  SpaceDev test, ansatz;
+  const gdtb_pattern* pattern;
+  double* d_values;
+  bool owns_values;
+  std::vector<LoweredForm> element_forms, coupling_forms, boundary_forms;
+  std::string plan;
+};
+
+struct gdtb_vecfun
+{
+  gdtb_ctx* ctx;
+  GridDev grid;
+  SpaceDev space;
+  double* d_vec;
+  bool owns_vec;
+  std::vector<LoweredForm> forms;
+  double* d_sep_tab; // separable right-hand-side tables for the gather kernel
+  double* d_rule;    // qx | qw | phi for the table kernel
+};
+
+struct gdtb_fvop
+{
+  gdtb_ctx* ctx;
+  GridDev grid;
+  SpaceDev space;
+  gdtb_flux flux;
+  bool ghosted;
+  double* d_tmp; // ping-pong buffer for the Euler loop
+  double* d_src; // staging for the *_host entry points
+  double* d_dst;
+};
+
+namespace {
+
+int check_ctx(gdtb_ctx* ctx)
+{
+  if (!ctx)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "context is NULL");
+  GDTB_CUDA(cudaSetDevice(ctx->device));
+  return GDTB_OK;
+}
+
+long long function_data_size(const gdtb_function& f, const GridDev& g)
+{
+  if (f.kind == GDTB_FN_ELEM_SCALAR)
+    return g.ne;
+  if (f.kind == GDTB_FN_ELEM_TENSOR)
+    return g.ne * g.d * g.d;
+  return 0;
+}
+
+int validate_function(const gdtb_function& f, const char* what)
+{
+  if (f.kind < GDTB_FN_CONST_SCALAR || f.kind > GDTB_FN_BUILTIN)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": unknown function kind");
+  if (f.kind == GDTB_FN_BUILTIN && (f.builtin < GDTB_BUILTIN_COS_PRODUCT || f.builtin > GDTB_BUILTIN_QUADRATIC))
+    return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": unknown built-in function id");
+  if ((f.kind == GDTB_FN_ELEM_SCALAR || f.kind == GDTB_FN_ELEM_TENSOR) && !f.data)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": per-element function without data");
+  if (f.order < 0)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": negative polynomial order");
+  return GDTB_OK;
+}
+
+// clone-on-append of a grid function: host arrays are copied to the device
+int lower_function(gdtb_ctx* ctx, const GridDev& g, gdtb_function& f, LoweredForm& owner)
+{
+  const long long n = function_data_size(f, g);
+  if (n > 0 && !f.data_on_device) {
+    double* d = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * (size_t)n) != cudaSuccess)
+      return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory while cloning a per-element function");
+    owner.owned.push_back(d);
+    GDTB_CUDA(cudaMemcpyAsync(d, f.data, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->launch.stream));
+    GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+    f.data = d;
+    f.data_on_device = 1;
+  }
+  return GDTB_OK;
+}
+
+int lower_form(gdtb_ctx* ctx, const GridDev& g, const gdtb_form* form, int filter, LoweredForm& out)
+{
+  if (!form)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "form is NULL");
+  if (form->n_terms < 1 || form->n_terms > GDTB_MAX_TERMS)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "form: n_terms must be in [1, GDTB_MAX_TERMS]");
+  out.form = *form;
+  out.filter = filter;
+  for (int t = 0; t < form->n_terms; ++t) {
+    GDTB_TRY(validate_function(out.form.terms[t].diffusion, "integrand.diffusion"));
+    GDTB_TRY(validate_function(out.form.terms[t].weight, "integrand.weight"));
+    int st = lower_function(ctx, g, out.form.terms[t].diffusion, out);
+    if (st == GDTB_OK)
+      st = lower_function(ctx, g, out.form.terms[t].weight, out);
+    if (st != GDTB_OK) {
+      free_form(out);
+      return st;
+    }
+  }
+  return GDTB_OK;
+}
+
+FnDev to_dev(const gdtb_function& f)
+{
+  FnDev d;
+  d.kind = f.kind;
+  d.order = f.order;
+  d.builtin = f.builtin;
+  d.pad = 0;
+  std::memcpy(d.c, f.c, sizeof(d.c));
+  std::memcpy(d.p, f.p, sizeof(d.p));
+  d.data = f.data;
+  return d;
+}
+
+enum FormRole
+{
+  ROLE_ELEMENT,
+  ROLE_RHS,
+  ROLE_COUPLING,
+  ROLE_BOUNDARY
+};
+
+// quadrature order of a form exactly as the reference derives it
+int form_quadrature_order(const gdtb_form& f, int K, FormRole role)
+{
+  int order = 0;
+  for (int t = 0; t < f.n_terms; ++t) {
+    const gdtb_integrand& in = f.terms[t];
+    int o = 0;
+    switch (role) {
+      case ROLE_ELEMENT: // laplace.hh:74-79, product.hh:89-100
+        o = in.diffusion.order + K + K;
+        break;
+      case ROLE_RHS: // conversion.hh:92 -> product.hh:99
+        o = in.diffusion.order + K + in.weight.order;
+        break;
+      case ROLE_COUPLING: // laplace-ipdg.hh:95-105, ipdg.hh:100-111
+        o = (in.kind == GDTB_INT_IPDG_INNER_COUPLING ? in.diffusion.order : 0) + in.weight.order + K + K;
+        break;
+      case ROLE_BOUNDARY: // laplace-ipdg.hh:331-338, ipdg.hh:245-252
+        o = (in.kind == GDTB_INT_IPDG_DIRICHLET_COUPLING ? in.diffusion.order : in.weight.order) + K + K;
+        break;
+    }
+    order = std::max(order, o); // combined.hh:293-299
+  }
+  return order + f.over_integrate;
+}
+
+int make_form_dev(const gdtb_form& f, int K, FormRole role, FormDev& out)
+{
+  std::memset(&out, 0, sizeof(out));
+  out.n_terms = f.n_terms;
+  out.scaling = f.scaling;
+  out.m = gauss_points_for_order(form_quadrature_order(f, K, role));
+  if (out.m > MAX_Q1D)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "quadrature order too high (more than 8 Gauss points per direction)");
+  gauss_legendre_01(out.m, out.qx, out.qw);
+  for (int q = 0; q < out.m; ++q)
+    lagrange_1d(K, out.qx[q], out.phi[q], out.dphi[q]);
+  lagrange_1d(K, 0., out.phi_end[0], out.dphi_end[0]);
+  lagrange_1d(K, 1., out.phi_end[1], out.dphi_end[1]);
+  for (int t = 0; t < f.n_terms; ++t) {
+    IntegrandDev& d = out.terms[t];
+    d.kind = f.terms[t].kind;
+    d.hI_kind = f.terms[t].hI_kind;
+    d.prefactor = f.terms[t].prefactor;
+    d.diffusion = to_dev(f.terms[t].diffusion);
+    d.weight = to_dev(f.terms[t].weight);
+  }
+  return GDTB_OK;
+}
+
+// ---- CG-Q1 gather eligibility and lowering ------------------------------------------------------
+bool fn_is_const(const gdtb_function& f)
+{
+  return f.kind == GDTB_FN_CONST_SCALAR || f.kind == GDTB_FN_CONST_TENSOR;
+}
+
+bool q1_space(const SpaceDev& sp)
+{
+  return sp.kind == GDTB_SPACE_CG && sp.K == 1;
+}
+
+bool matop_q1_eligible(const gdtb_matop* op)
+{
+  if (!q1_space(op->test) || !q1_space(op->ansatz) || op->grid.periodic)
+    return false;
+  if (op->pattern->stencil != GDTB_STENCIL_ELEMENT || !q1_space(op->pattern->test) || !q1_space(op->pattern->ansatz))
+    return false;
+  if (!op->coupling_forms.empty() || !op->boundary_forms.empty() || op->element_forms.empty())
+    return false;
+  int n_elem = 0;
+  for (const auto& lf : op->element_forms)
+    for (int t = 0; t < lf.form.n_terms; ++t) {
+      const gdtb_integrand& in = lf.form.terms[t];
+      if (in.kind == GDTB_INT_LAPLACE) {
+        if (in.diffusion.kind == GDTB_FN_ELEM_SCALAR)
+          ++n_elem;
+        else if (!fn_is_const(in.diffusion))
+          return false;
+      } else if (in.kind == GDTB_INT_PRODUCT) {
+        if (in.diffusion.kind == GDTB_FN_ELEM_SCALAR)
+          ++n_elem;
+        else if (in.diffusion.kind != GDTB_FN_CONST_SCALAR)
+          return false;
+      } else
+        return false;
+    }
+  return n_elem <= Q1G_MAX_ELEM_CHANNELS;
+}
+
+bool builtin_is_separable(int id)
+{
+  return id == GDTB_BUILTIN_COS_PRODUCT || id == GDTB_BUILTIN_GAUSSIAN || id == GDTB_BUILTIN_INDICATOR;
+}
+
+bool vecfun_q1_eligible(const gdtb_vecfun* fun)
+{
+  if (!q1_space(fun->space) || fun->grid.periodic || fun->forms.empty())
+    return false;
+  int n_elem = 0, n_sep = 0;
+  for (const auto& lf : fun->forms) {
+    if (lf.form.n_terms != 1)
+      return false;
+    const gdtb_integrand& in = lf.form.terms[0];
+    if (in.kind != GDTB_INT_PRODUCT || in.diffusion.kind != GDTB_FN_CONST_SCALAR)
+      return false;
+    if (in.weight.kind == GDTB_FN_ELEM_SCALAR)
+      ++n_elem;
+    else if (in.weight.kind == GDTB_FN_BUILTIN && builtin_is_separable(in.weight.builtin))
+      ++n_sep;
+    else if (in.weight.kind != GDTB_FN_CONST_SCALAR)
+      return false;
+  }
+  return n_elem <= 1 && n_sep <= 1;
+}
+
+// 1D integrals of the Q1 shape functions with an m-point Gauss rule:
+// G[ta][tb][a][b] = sum_q w_q D^ta phi_a(x_q) D^tb phi_b(x_q), s1[a] = sum_q w_q phi_a(x_q)
+struct Q1Tables
+{
+  double G[2][2][2][2];
+  double s1[2];
+  int m;
+  double qx[MAX_Q1D], qw[MAX_Q1D], phi[MAX_Q1D][2];
+};
+
+void q1_tables(int order, Q1Tables& t)
+{
+  std::memset(&t, 0, sizeof(t));
+  t.m = gauss_points_for_order(order);
+  gauss_legendre_01(t.m, t.qx, t.qw);
+  for (int q = 0; q < t.m; ++q) {
+    double v[2], dv[2];
+    lagrange_1d(1, t.qx[q], v, dv);
+    t.phi[q][0] = v[0];
+    t.phi[q][1] = v[1];
+    const double* D[2] = {v, dv};
+    for (int ta = 0; ta < 2; ++ta)
+      for (int tb = 0; tb < 2; ++tb)
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b)
+            t.G[ta][tb][a][b] += t.qw[q] * D[ta][a] * D[tb][b];
+    t.s1[0] += t.qw[q] * v[0];
+    t.s1[1] += t.qw[q] * v[1];
+  }
+}
+
+// reference tensor of one integrand with unit (or the given constant) coefficient on a cell with extents h:
+// Lref[i][j], i = test, j = ansatz, local index bits = (a_0, a_1, a_2)
+void q1_reference_tensor(const gdtb_integrand& in, int d, const double* h, const Q1Tables& tab, bool unit_coefficient,
+                         double Lref[8][8])
+{
+  const int n = 1 << d;
+  double ie = 1.;
+  for (int k = 0; k < d; ++k)
+    ie *= h[k];
+  double kap[3][3] = {{0}};
+  if (in.kind == GDTB_INT_LAPLACE) {
+    if (!unit_coefficient && in.diffusion.kind == GDTB_FN_CONST_TENSOR) {
+      for (int r = 0; r < d; ++r)
+        for (int c = 0; c < d; ++c)
+          kap[r][c] = in.diffusion.c[r * d + c];
+    } else {
+      const double s = unit_coefficient ? 1. : in.diffusion.c[0];
+      for (int r = 0; r < d; ++r)
+        kap[r][r] = s;
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double v = 0.;
+      if (in.kind == GDTB_INT_LAPLACE) {
+        // v_ij = sum_{r,s} kappa_rs d_s phi_j d_r phi_i (laplace.hh:101), gradients scaled by 1/h (default.hh:167-174)
+        for (int r = 0; r < d; ++r)
+          for (int s = 0; s < d; ++s) {
+            if (kap[r][s] == 0.)
+              continue;
+            double prod = kap[r][s] * ie / (h[r] * h[s]);
+            for (int k = 0; k < d; ++k)
+              prod *= tab.G[k == r ? 1 : 0][k == s ? 1 : 0][(i >> k) & 1][(j >> k) & 1];
+            v += prod;
+          }
+      } else {
+        double prod = (unit_coefficient ? 1. : in.diffusion.c[0]) * ie;
+        for (int k = 0; k < d; ++k)
+          prod *= tab.G[0][0][(i >> k) & 1][(j >> k) & 1];
+        v = prod;
+      }
+      Lref[i][j] = v;
+    }
+}
+
+void add_to_T(double T[8][8], const double Lref[8][8], double scale, int d)
+{
+  const int n = 1 << d;
+  for (int o = 0; o < n; ++o) {
+    const int i = (n - 1) ^ o; // a_k = 1 - o_k
+    for (int s = 0; s < n; ++s)
+      T[o][s] += scale * Lref[i][s];
+  }
+}
+
+int build_q1_params(gdtb_matop* op, gdtb_vecfun* fun, Q1GatherParams& p)
+{
+  std::memset(&p, 0, sizeof(p));
+  const GridDev& g = op ? op->grid : fun->grid;
+  p.g = g;
+  const int d = g.d;
+  if (op) {
+    for (const auto& lf : op->element_forms) {
+      Q1Tables tab;
+      q1_tables(form_quadrature_order(lf.form, 1, ROLE_ELEMENT), tab);
+      for (int t = 0; t < lf.form.n_terms; ++t) {
+        const gdtb_integrand& in = lf.form.terms[t];
+        double Lref[8][8];
+        if (in.diffusion.kind == GDTB_FN_ELEM_SCALAR) {
+          q1_reference_tensor(in, d, g.h, tab, true, Lref);
+          add_to_T(p.T_elem[p.n_elem], Lref, lf.form.scaling, d);
+          p.coef[p.n_elem] = in.diffusion.data;
+          p.n_elem++;
+        } else {
+          q1_reference_tensor(in, d, g.h, tab, false, Lref);
+          add_to_T(p.T_const, Lref, lf.form.scaling, d);
+          p.has_const = 1;
+        }
+      }
+    }
+  }
+  return GDTB_OK;
+}
+
+} // namespace
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+extern "C" {
+
+const char* gdtb_last_error(void)
+{
+  return g_last_error.c_str();
+}
+
+int gdtb_version(void)
+{
+  return GDTB_VERSION;
+}
+
+int gdtb_ctx_create(int device, gdtb_ctx** out)
+{
+  if (!out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "ctx out pointer is NULL");
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0)
+    return fail(GDTB_ERR_CUDA,
+                std::string("no usable CUDA device (libgdtb has no CPU fallback): ") + cudaGetErrorString(err));
+  if (device < 0 || device >= count)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "device index out of range");
+  GDTB_CUDA(cudaSetDevice(device));
+  auto ctx = new gdtb_ctx();
+  ctx->device = device;
+  ctx->d_error_flag = nullptr;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return fail(GDTB_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  ctx->launch.stream = ctx->own_stream;
+  ctx->launch.count = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return fail(GDTB_ERR_CUDA, "cudaGetDeviceProperties failed");
+  }
+  ctx->launch.sm_count = prop.multiProcessorCount;
+  if (cudaMalloc(&ctx->d_error_flag, sizeof(int)) != cudaSuccess
+      || cudaMemset(ctx->d_error_flag, 0, sizeof(int)) != cudaSuccess) {
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return fail(GDTB_ERR_CUDA, "cudaMalloc failed");
+  }
+  *out = ctx;
+  return GDTB_OK;
+}
+
+int gdtb_ctx_destroy(gdtb_ctx* ctx)
+{
+  if (!ctx)
+    return GDTB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->launch.stream);
+  cudaFree(ctx->d_error_flag);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return GDTB_OK;
+}
+
+int gdtb_ctx_set_stream(gdtb_ctx* ctx, void* cuda_stream)
+{
+  GDTB_TRY(check_ctx(ctx));
+  ctx->launch.stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return GDTB_OK;
+}
+
+int gdtb_ctx_synchronize(gdtb_ctx* ctx)
+{
+  GDTB_TRY(check_ctx(ctx));
+  GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int64_t gdtb_ctx_launch_count(const gdtb_ctx* ctx)
+{
+  return ctx ? ctx->launch.count : 0;
+}
+
+// ---- grid / spaces ---------------------------------------------------------------------------
+int gdtb_grid_create_cube(gdtb_ctx* ctx, const gdtb_grid_desc* desc, gdtb_grid** out)
+{
+  if (!ctx || !desc || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_grid_create_cube: NULL argument");
+  if (desc->dim < 1 || desc->dim > 3)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "grid dimension must be 1, 2 or 3");
+  auto g = new gdtb_grid();
+  g->ctx = ctx;
+  g->desc = *desc;
+  GridDev& d = g->dev;
+  std::memset(&d, 0, sizeof(d));
+  d.d = desc->dim;
+  d.periodic = desc->periodic & ((1 << desc->dim) - 1);
+  d.ne = 1;
+  for (int k = 0; k < 3; ++k) {
+    if (k < desc->dim) {
+      if (desc->n[k] < 1 || !(desc->upper[k] > desc->lower[k])) {
+        delete g;
+        return fail(GDTB_ERR_INVALID_ARGUMENT, "grid needs n >= 1 and upper > lower in every direction");
+      }
+      d.lo[k] = desc->lower[k];
+      d.n[k] = desc->n[k];
+      d.h[k] = (desc->upper[k] - desc->lower[k]) / double(desc->n[k]);
+    } else {
+      d.lo[k] = 0.;
+      d.n[k] = 1;
+      d.h[k] = 1.;
+    }
+    d.ne *= d.n[k];
+  }
+  d.layer_lo = 0;
+  d.layer_hi = d.n[d.d - 1];
+  *out = g;
+  return GDTB_OK;
+}
+
+int gdtb_grid_destroy(gdtb_grid* grid)
+{
+  delete grid;
+  return GDTB_OK;
+}
+
+int64_t gdtb_grid_num_elements(const gdtb_grid* grid)
+{
+  return grid ? grid->dev.ne : 0;
+}
+
+int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order, gdtb_space** out)
+{
+  if (!ctx || !grid || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_space_create: NULL argument");
+  if (kind < GDTB_SPACE_CG || kind > GDTB_SPACE_FV)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown space kind");
+  const int d = grid->dev.d;
+  int K = order;
+  if (kind == GDTB_SPACE_FV)
+    K = 0;
+  else if (kind == GDTB_SPACE_CG && order < 1)
+    return fail(GDTB_ERR_SPACE, "continuous Lagrange spaces need order >= 1");
+  else if (order < 0)
+    return fail(GDTB_ERR_SPACE, "negative polynomial order");
+  if (K > MAX_K || (d == 3 && K > 2))
+    return fail(GDTB_ERR_FINITE_ELEMENT, "Lagrange order not supported (max 3 in 1d/2d, 2 in 3d)");
+  if (kind == GDTB_SPACE_CG && grid->dev.periodic)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "continuous Lagrange spaces on periodic grid views are not supported");
+  auto s = new gdtb_space();
+  s->ctx = ctx;
+  s->grid = grid->dev;
+  SpaceDev& sp = s->dev;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.kind = kind;
+  sp.K = K;
+  sp.d = d;
+  sp.nloc = ipow(K + 1, d);
+  if (kind == GDTB_SPACE_CG) {
+    // MCMGMapper offsets: codim 0..d, YaspGrid sub-entity groups by shift bitset (common.cuh)
+    long long running = 0;
+    for (int c = 0; c <= d; ++c) {
+      long long b = 1;
+      for (int j = 0; j < d - c; ++j)
+        b *= (K - 1);
+      sp.cg.block[c] = b;
+      sp.cg.codim_offset[c] = running;
+      long long entities = 0;
+      for (int sh = 0; sh < (1 << d); ++sh) {
+        int pc = 0;
+        for (int k = 0; k < d; ++k)
+          pc += (sh >> k) & 1;
+        if (pc != d - c)
+          continue;
+        sp.cg.group_offset[sh] = entities;
+        long long cnt = 1;
+        for (int k = 0; k < d; ++k)
+          cnt *= ((sh >> k) & 1) ? grid->dev.n[k] : grid->dev.n[k] + 1;
+        entities += cnt;
+      }
+      running += entities * b;
+    }
+    sp.size = running;
+  } else
+    sp.size = grid->dev.ne * sp.nloc;
+  *out = s;
+  return GDTB_OK;
+}
+
+int gdtb_space_destroy(gdtb_space* space)
+{
+  delete space;
+  return GDTB_OK;
+}
+
+int64_t gdtb_space_size(const gdtb_space* space)
+{
+  return space ? space->dev.size : 0;
+}
+
+int32_t gdtb_space_max_local_size(const gdtb_space* space)
+{
+  return space ? space->dev.nloc : 0;
+}
+
+int gdtb_space_global_indices(const gdtb_space* space, int64_t element, int64_t* out)
+{
+  if (!space || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_space_global_indices: NULL argument");
+  if (element < 0 || element >= space->grid.ne)
+    return fail(GDTB_ERR_SPACE, "element index out of range"); // Exceptions::mapper_error
+  long long idx[3];
+  elem_coords(space->grid, element, idx);
+  for (int i = 0; i < space->dev.nloc; ++i)
+    out[i] = global_index(space->grid, space->dev, idx, i);
+  return GDTB_OK;
+}
+
+// ---- sparsity pattern --------------------------------------------------------------------------
+int gdtb_pattern_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* ansatz, int stencil, int method,
+                        gdtb_pattern** out)
+{
+  if (!test || !ansatz || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_pattern_create: NULL argument");
+  GDTB_TRY(check_ctx(ctx));
+  if (stencil < GDTB_STENCIL_ELEMENT || stencil > GDTB_STENCIL_ELEMENT_AND_INTERSECTION)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "Unknown Stencil encountered"); // sparsity-pattern.hh:174-177
+  if (std::memcmp(&test->grid, &ansatz->grid, sizeof(GridDev)) != 0)
+    return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "test and ansatz space live on different grids");
+  const bool structured_ok =
+      stencil == GDTB_STENCIL_ELEMENT && q1_space(test->dev) && q1_space(ansatz->dev) && !test->grid.periodic;
+  if (method == GDTB_PATTERN_STRUCTURED && !structured_ok)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "structured pattern generator only covers the CG Q1 element stencil");
+  auto p = std::make_unique<gdtb_pattern>();
+  p->ctx = ctx;
+  p->grid = test->grid;
+  p->test = test->dev;
+  p->ansatz = ansatz->dev;
+  p->stencil = stencil;
+  p->rows = test->dev.size;
+  p->cols = ansatz->dev.size;
+  p->d_rowptr = nullptr;
+  p->d_colidx = nullptr;
+  const bool use_structured = method == GDTB_PATTERN_STRUCTURED || (method == GDTB_PATTERN_AUTO && structured_ok);
+  if (use_structured)
+    GDTB_TRY(pattern_structured_cg_q1(ctx->launch, p->grid, p->test, &p->d_rowptr, &p->d_colidx, &p->nnz));
+  else
+    GDTB_TRY(
+        pattern_sort_unique(ctx->launch, p->grid, p->test, p->ansatz, stencil, &p->d_rowptr, &p->d_colidx, &p->nnz));
+  *out = p.release();
+  return GDTB_OK;
+}
+
+int gdtb_pattern_destroy(gdtb_pattern* p)
+{
+  if (!p)
+    return GDTB_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaFree(p->d_rowptr);
+  cudaFree(p->d_colidx);
+  delete p;
+  return GDTB_OK;
+}
+
+int64_t gdtb_pattern_rows(const gdtb_pattern* p)
+{
+  return p ? p->rows : 0;
+}
+int64_t gdtb_pattern_cols(const gdtb_pattern* p)
+{
+  return p ? p->cols : 0;
+}
+int64_t gdtb_pattern_nnz(const gdtb_pattern* p)
+{
+  return p ? p->nnz : 0;
+}
+
+int gdtb_pattern_download(const gdtb_pattern* p, int64_t* rowptr, int32_t* colidx)
+{
+  if (!p)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "pattern is NULL");
+  GDTB_TRY(check_ctx(p->ctx));
+  if (rowptr)
+    GDTB_CUDA(cudaMemcpy(rowptr, p->d_rowptr, sizeof(int64_t) * (size_t)(p->rows + 1), cudaMemcpyDeviceToHost));
+  if (colidx)
+    GDTB_CUDA(cudaMemcpy(colidx, p->d_colidx, sizeof(int32_t) * (size_t)p->nnz, cudaMemcpyDeviceToHost));
+  return GDTB_OK;
+}
+
+int gdtb_pattern_device(const gdtb_pattern* p, const int64_t** d_rowptr, const int32_t** d_colidx)
+{
+  if (!p)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "pattern is NULL");
+  if (d_rowptr)
+    *d_rowptr = (const int64_t*)p->d_rowptr;
+  if (d_colidx)
+    *d_colidx = p->d_colidx;
+  return GDTB_OK;
+}
+
+// ---- MatrixOperator ----------------------------------------------------------------------------
+int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* ansatz, const gdtb_pattern* pattern,
+                      gdtb_matop** out)
+{
+  if (!test || !ansatz || !pattern || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_create: NULL argument");
+  GDTB_TRY(check_ctx(ctx));
+  // matrix-based.hh:73-80: matrix.rows() == range_space.mapper().size(), cols == source_space.mapper().size()
+  if (pattern->rows != test->dev.size || pattern->cols != ansatz->dev.size)
+    return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "pattern shape does not match the spaces (rows = test, cols = ansatz)");
+  if (std::memcmp(&test->grid, &ansatz->grid, sizeof(GridDev)) != 0)
+    return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "test and ansatz space live on different grids");
+  if (std::memcmp(&test->dev, &ansatz->dev, sizeof(SpaceDev)) != 0)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "rectangular operators (test space != ansatz space) are not supported yet");
+  auto op = std::make_unique<gdtb_matop>();
+  op->ctx = ctx;
+  op->grid = test->grid;
+  op->test = test->dev;
+  op->ansatz = ansatz->dev;
+  op->pattern = pattern;
+  op->d_values = nullptr;
+  op->owns_values = true;
+  if (cudaMalloc(&op->d_values, sizeof(double) * (size_t)std::max<long long>(pattern->nnz, 1)) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the matrix values");
+  GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pattern->nnz, ctx->launch.stream));
+  *out = op.release();
+  return GDTB_OK;
+}
+
+int gdtb_matop_clear_forms(gdtb_matop* op)
+{
+  if (!op)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  cudaSetDevice(op->ctx->device);
+  cudaStreamSynchronize(op->ctx->launch.stream);
+  for (auto* v : {&op->element_forms, &op->coupling_forms, &op->boundary_forms}) {
+    for (auto& f : *v)
+      free_form(f);
+    v->clear();
+  }
+  return GDTB_OK;
+}
+
+int gdtb_matop_destroy(gdtb_matop* op)
+{
+  if (!op)
+    return GDTB_OK;
+  gdtb_matop_clear_forms(op);
+  if (op->owns_values)
+    cudaFree(op->d_values);
+  delete op;
+  return GDTB_OK;
+}
+
+int gdtb_matop_append_element(gdtb_matop* op, const gdtb_form* form)
+{
+  if (!op)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  GDTB_TRY(check_ctx(op->ctx));
+  if (form)
+    for (int t = 0; t < form->n_terms && t < GDTB_MAX_TERMS; ++t)
+      if (form->terms[t].kind != GDTB_INT_LAPLACE && form->terms[t].kind != GDTB_INT_PRODUCT)
+        return fail(GDTB_ERR_INTEGRAND, "element bilinear forms take Laplace / product integrands");
+  LoweredForm lf;
+  GDTB_TRY(lower_form(op->ctx, op->grid, form, 0, lf));
+  op->element_forms.push_back(std::move(lf));
+  return GDTB_OK;
+}
+
+int gdtb_matop_append_coupling(gdtb_matop* op, const gdtb_form* form, int filter)
+{
+  if (!op)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  GDTB_TRY(check_ctx(op->ctx));
+  if (filter != GDTB_FILTER_INNER_ONCE && filter != GDTB_FILTER_INNER_AND_PERIODIC_ONCE)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "coupling forms need an inner-intersections-once filter");
+  if (op->test.kind == GDTB_SPACE_CG)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "intersection forms are implemented for DG / FV spaces only");
+  if (form)
+    for (int t = 0; t < form->n_terms && t < GDTB_MAX_TERMS; ++t)
+      if (form->terms[t].kind != GDTB_INT_IPDG_INNER_COUPLING && form->terms[t].kind != GDTB_INT_IPDG_INNER_PENALTY)
+        return fail(GDTB_ERR_INTEGRAND, "This integrand cannot be used on an inner intersection!");
+  LoweredForm lf;
+  GDTB_TRY(lower_form(op->ctx, op->grid, form, filter, lf));
+  op->coupling_forms.push_back(std::move(lf));
+  return GDTB_OK;
+}
+
+int gdtb_matop_append_boundary(gdtb_matop* op, const gdtb_form* form, int filter)
+{
+  if (!op)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  GDTB_TRY(check_ctx(op->ctx));
+  if (filter != GDTB_FILTER_ALL_BOUNDARY)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "boundary forms need a boundary filter");
+  if (op->test.kind == GDTB_SPACE_CG)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "intersection forms are implemented for DG / FV spaces only");
+  if (form)
+    for (int t = 0; t < form->n_terms && t < GDTB_MAX_TERMS; ++t)
+      if (form->terms[t].kind != GDTB_INT_IPDG_DIRICHLET_COUPLING
+          && form->terms[t].kind != GDTB_INT_IPDG_BOUNDARY_PENALTY)
+        return fail(GDTB_ERR_INTEGRAND, "This integrand cannot be used on a boundary intersection!"); // ipdg.hh:93-94
+  LoweredForm lf;
+  GDTB_TRY(lower_form(op->ctx, op->grid, form, filter, lf));
+  op->boundary_forms.push_back(std::move(lf));
+  return GDTB_OK;
+}
+
+int gdtb_matop_num_forms(const gdtb_matop* op)
+{
+  return op ? int(op->element_forms.size() + op->coupling_forms.size() + op->boundary_forms.size()) : 0;
+}
+
+const char* gdtb_matop_plan(gdtb_matop* op)
+{
+  if (!op)
+    return "";
+  op->plan = matop_q1_eligible(op) ? "q1_gather" : "generic_coloured";
+  return op->plan.c_str();
+}
+
+int gdtb_matop_set_zero(gdtb_matop* op)
+{
+  if (!op)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  GDTB_TRY(check_ctx(op->ctx));
+  GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)op->pattern->nnz, op->ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(op->ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int gdtb_matop_values_download(const gdtb_matop* op, double* values)
+{
+  if (!op || !values)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_values_download: NULL argument");
+  GDTB_TRY(check_ctx(op->ctx));
+  GDTB_CUDA(cudaMemcpyAsync(values, op->d_values, sizeof(double) * (size_t)op->pattern->nnz, cudaMemcpyDeviceToHost,
+                            op->ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(op->ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int gdtb_matop_values_upload(gdtb_matop* op, const double* values)
+{
+  if (!op || !values)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_values_upload: NULL argument");
+  GDTB_TRY(check_ctx(op->ctx));
+  GDTB_CUDA(cudaMemcpyAsync(op->d_values, values, sizeof(double) * (size_t)op->pattern->nnz, cudaMemcpyHostToDevice,
+                            op->ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(op->ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int gdtb_matop_values_device(const gdtb_matop* op, double** d_values)
+{
+  if (!op || !d_values)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_values_device: NULL argument");
+  *d_values = op->d_values;
+  return GDTB_OK;
+}
+
+int gdtb_matop_set_values_device(gdtb_matop* op, double* d_values)
+{
+  if (!op || !d_values)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_set_values_device: NULL argument");
+  if (op->owns_values)
+    cudaFree(op->d_values);
+  op->d_values = d_values;
+  op->owns_values = false;
+  return GDTB_OK;
+}
+
+int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end)
+{
+  if (!op)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  const long long n_last = op->grid.n[op->grid.d - 1];
+  if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
+  op->grid.layer_lo = layer_begin;
+  op->grid.layer_hi = layer_end;
+  return GDTB_OK;
+}
+
+// ---- VectorBasedFunctional ---------------------------------------------------------------------
+int gdtb_vecfun_create(gdtb_ctx* ctx, const gdtb_space* space, gdtb_vecfun** out)
+{
+  if (!space || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_create: NULL argument");
+  GDTB_TRY(check_ctx(ctx));
+  auto f = std::make_unique<gdtb_vecfun>();
+  f->ctx = ctx;
+  f->grid = space->grid;
+  f->space = space->dev;
+  f->d_vec = nullptr;
+  f->owns_vec = true;
+  f->d_sep_tab = nullptr;
+  f->d_rule = nullptr;
+  if (cudaMalloc(&f->d_vec, sizeof(double) * (size_t)std::max<long long>(space->dev.size, 1)) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the vector");
+  GDTB_CUDA(cudaMemsetAsync(f->d_vec, 0, sizeof(double) * (size_t)space->dev.size, ctx->launch.stream));
+  *out = f.release();
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_clear_forms(gdtb_vecfun* fun)
+{
+  if (!fun)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "functional is NULL");
+  cudaSetDevice(fun->ctx->device);
+  cudaStreamSynchronize(fun->ctx->launch.stream);
+  for (auto& f : fun->forms)
+    free_form(f);
+  fun->forms.clear();
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_destroy(gdtb_vecfun* fun)
+{
+  if (!fun)
+    return GDTB_OK;
+  gdtb_vecfun_clear_forms(fun);
+  if (fun->owns_vec)
+    cudaFree(fun->d_vec);
+  cudaFree(fun->d_sep_tab);
+  cudaFree(fun->d_rule);
+  delete fun;
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_append_element(gdtb_vecfun* fun, const gdtb_form* form)
+{
+  if (!fun)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "functional is NULL");
+  GDTB_TRY(check_ctx(fun->ctx));
+  if (form && (form->n_terms != 1 || form->terms[0].kind != GDTB_INT_PRODUCT))
+    return fail(GDTB_ERR_INTEGRAND, "element functionals take LocalProductIntegrand(w).with_ansatz(f) (one term)");
+  LoweredForm lf;
+  GDTB_TRY(lower_form(fun->ctx, fun->grid, form, 0, lf));
+  fun->forms.push_back(std::move(lf));
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_set_zero(gdtb_vecfun* fun)
+{
+  if (!fun)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "functional is NULL");
+  GDTB_TRY(check_ctx(fun->ctx));
+  GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)fun->space.size, fun->ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(fun->ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_download(const gdtb_vecfun* fun, double* vector)
+{
+  if (!fun || !vector)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_download: NULL argument");
+  GDTB_TRY(check_ctx(fun->ctx));
+  GDTB_CUDA(cudaMemcpyAsync(vector, fun->d_vec, sizeof(double) * (size_t)fun->space.size, cudaMemcpyDeviceToHost,
+                            fun->ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(fun->ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_device(const gdtb_vecfun* fun, double** d_vector)
+{
+  if (!fun || !d_vector)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_device: NULL argument");
+  *d_vector = fun->d_vec;
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_set_device(gdtb_vecfun* fun, double* d_vector)
+{
+  if (!fun || !d_vector)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_set_device: NULL argument");
+  if (fun->owns_vec)
+    cudaFree(fun->d_vec);
+  fun->d_vec = d_vector;
+  fun->owns_vec = false;
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end)
+{
+  if (!fun)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "functional is NULL");
+  const long long n_last = fun->grid.n[fun->grid.d - 1];
+  if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
+  fun->grid.layer_lo = layer_begin;
+  fun->grid.layer_hi = layer_end;
+  return GDTB_OK;
+}
+
+// ---- the grid walk -----------------------------------------------------------------------------
+static int q1_rhs_params(gdtb_vecfun* fun, Q1GatherParams& p)
+{
+  const GridDev& g = fun->grid;
+  const int d = g.d;
+  double ie = 1.;
+  for (int k = 0; k < d; ++k)
+    ie *= g.h[k];
+  p.has_rhs = 1;
+  for (const auto& lf : fun->forms) {
+    const gdtb_integrand& in = lf.form.terms[0];
+    Q1Tables tab;
+    q1_tables(form_quadrature_order(lf.form, 1, ROLE_RHS), tab);
+    const double w = in.diffusion.c[0];
+    double s = 1.;
+    for (int k = 0; k < d; ++k)
+      s *= tab.s1[0]; // = 1/2 for either local index by symmetry of the rule
+    if (in.weight.kind == GDTB_FN_CONST_SCALAR) {
+      p.rhs_has_const = 1;
+      p.rhs_const += w * in.weight.c[0] * ie * s;
+    } else if (in.weight.kind == GDTB_FN_ELEM_SCALAR) {
+      p.rhs_has_elem = 1;
+      p.rhs_elem_scale = w * ie * s;
+      p.rhs_elem = in.weight.data;
+    } else {
+      // separable built-in: 1D tables on the device
+      const long long stride = std::max(std::max(g.n[0], g.n[1]), g.n[2]) + 1;
+      gdtb_ctx* ctx = fun->ctx;
+      if (!fun->d_sep_tab)
+        if (cudaMalloc(&fun->d_sep_tab, sizeof(double) * 3 * (size_t)stride) != cudaSuccess)
+          return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the right-hand-side tables");
+      if (!fun->d_rule)
+        if (cudaMalloc(&fun->d_rule, sizeof(double) * 4 * MAX_Q1D) != cudaSuccess)
+          return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the quadrature rule");
+      double host[4 * MAX_Q1D];
+      for (int q = 0; q < MAX_Q1D; ++q) {
+        host[q] = tab.qx[q];
+        host[MAX_Q1D + q] = tab.qw[q];
+        host[2 * MAX_Q1D + 2 * q] = tab.phi[q][0];
+        host[2 * MAX_Q1D + 2 * q + 1] = tab.phi[q][1];
+      }
+      GDTB_CUDA(cudaMemcpyAsync(fun->d_rule, host, sizeof(host), cudaMemcpyHostToDevice, ctx->launch.stream));
+      GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream)); // `host` is a stack buffer
+      GDTB_TRY(launch_q1_rhs_tables(ctx->launch, g, to_dev(in.weight), tab.m, fun->d_rule, fun->d_rule + MAX_Q1D,
+                                    fun->d_rule + 2 * MAX_Q1D, fun->d_sep_tab, stride));
+      p.rhs_has_sep = 1;
+      p.rhs_sep_scale = w * (in.weight.builtin == GDTB_BUILTIN_COS_PRODUCT ? in.weight.p[0] : 1.) * ie;
+      p.rhs_sep_tab = fun->d_sep_tab;
+      p.rhs_sep_stride = stride;
+    }
+  }
+  return GDTB_OK;
+}
+
+int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode)
+{
+  if (!op && !fun)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_assemble: nothing to assemble");
+  if (mode != GDTB_ASSEMBLE_OVERWRITE && mode != GDTB_ASSEMBLE_ACCUMULATE)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_assemble: unknown mode");
+  gdtb_ctx* ctx = op ? op->ctx : fun->ctx;
+  GDTB_TRY(check_ctx(ctx));
+  if (op && fun && std::memcmp(&op->grid, &fun->grid, sizeof(GridDev)) != 0)
+    return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "operator and functional live on different grids / slabs");
+  Launch& L = ctx->launch;
+  const bool accumulate = mode == GDTB_ASSEMBLE_ACCUMULATE;
+  const bool op_fast = op && matop_q1_eligible(op);
+  const bool fun_fast = fun && vecfun_q1_eligible(fun);
+
+  // --- CG-Q1 row-gather path: matrix and right-hand side in ONE pass over the vertices ---------
+  if (op_fast || fun_fast) {
+    Q1GatherParams p;
+    GDTB_TRY(build_q1_params(op_fast ? op : nullptr, fun_fast ? fun : nullptr, p));
+    if (fun_fast)
+      GDTB_TRY(q1_rhs_params(fun, p));
+    GDTB_TRY(launch_q1_gather(L, p, op_fast ? op->d_values : nullptr, fun_fast ? fun->d_vec : nullptr, accumulate));
+  }
+
+  // --- generic path --------------------------------------------------------------------------
+  if (op && !op_fast) {
+    const gdtb_pattern* pat = op->pattern;
+    if (!accumulate)
+      GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pat->nnz, L.stream));
+    GDTB_CUDA(cudaMemsetAsync(ctx->d_error_flag, 0, sizeof(int), L.stream));
+    for (const auto& lf : op->element_forms) {
+      FormDev fd;
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_ELEMENT, fd));
+      GDTB_TRY(launch_element_matrix(L, op->grid, op->test, fd, pat->d_rowptr, pat->d_colidx, op->d_values,
+                                     ctx->d_error_flag));
+    }
+    for (const auto& lf : op->coupling_forms) {
+      FormDev fd;
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_COUPLING, fd));
+      GDTB_TRY(launch_coupling_matrix(L, op->grid, op->test, fd, lf.filter, pat->d_rowptr, pat->d_colidx,
+                                      op->d_values, ctx->d_error_flag));
+    }
+    for (const auto& lf : op->boundary_forms) {
+      FormDev fd;
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_BOUNDARY, fd));
+      GDTB_TRY(launch_boundary_matrix(L, op->grid, op->test, fd, pat->d_rowptr, pat->d_colidx, op->d_values,
+                                      ctx->d_error_flag));
+    }
+    int flag = 0;
+    GDTB_CUDA(cudaMemcpyAsync(&flag, ctx->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+    GDTB_CUDA(cudaStreamSynchronize(L.stream));
+    if (flag)
+      return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH,
+                  "add_to_entry: a local entry is not part of the sparsity pattern (wrong stencil for the appended forms?)");
+  }
+  if (fun && !fun_fast) {
+    if (!accumulate)
+      GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)fun->space.size, L.stream));
+    for (const auto& lf : fun->forms) {
+      FormDev fd;
+      GDTB_TRY(make_form_dev(lf.form, fun->space.K, ROLE_RHS, fd));
+      GDTB_TRY(launch_element_vector(L, fun->grid, fun->space, fd, fun->d_vec));
+    }
+  }
+  GDTB_CUDA(cudaStreamSynchronize(L.stream));
+  return GDTB_OK;
+}
+
+int gdtb_assemble_host(gdtb_matop* op, gdtb_vecfun* fun, double* values, double* vector)
+{
+  GDTB_TRY(gdtb_assemble(op, fun, GDTB_ASSEMBLE_OVERWRITE));
+  if (op && values)
+    GDTB_TRY(gdtb_matop_values_download(op, values));
+  if (fun && vector)
+    GDTB_TRY(gdtb_vecfun_download(fun, vector));
+  return GDTB_OK;
+}
+
+// ---- AdvectionFvOperator -----------------------------------------------------------------------
+int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* flux, gdtb_fvop** out)
+{
+  if (!space || !flux || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_create: NULL argument");
+  GDTB_TRY(check_ctx(ctx));
+  if (space->dev.kind != GDTB_SPACE_FV)
+    return fail(GDTB_ERR_OPERATOR, "Use LocalAdvectionDgCouplingOperator instead!"); // local/operators/advection-fv.hh:131-134
+  if (flux->kind != GDTB_FLUX_LINEAR && flux->kind != GDTB_FLUX_BURGERS)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown flux function");
+  if (flux->numflux != GDTB_NUMFLUX_UPWIND && flux->numflux != GDTB_NUMFLUX_LAX_FRIEDRICHS)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown numerical flux");
+  auto L = new gdtb_fvop();
+  L->ctx = ctx;
+  L->grid = space->grid;
+  L->space = space->dev;
+  L->flux = *flux;
+  L->ghosted = false;
+  L->d_tmp = L->d_src = L->d_dst = nullptr;
+  *out = L;
+  return GDTB_OK;
+}
+
+int gdtb_fvop_destroy(gdtb_fvop* L)
+{
+  if (!L)
+    return GDTB_OK;
+  cudaSetDevice(L->ctx->device);
+  cudaFree(L->d_tmp);
+  cudaFree(L->d_src);
+  cudaFree(L->d_dst);
+  delete L;
+  return GDTB_OK;
+}
+
+int64_t gdtb_fvop_ghost_layer_size(const gdtb_fvop* L)
+{
+  if (!L)
+    return 0;
+  long long plane = 1;
+  for (int k = 0; k < L->grid.d - 1; ++k)
+    plane *= L->grid.n[k];
+  return plane;
+}
+
+static long long fv_local_size(const gdtb_fvop* L)
+{
+  const long long plane = gdtb_fvop_ghost_layer_size(L);
+  return plane * (L->grid.layer_hi - L->grid.layer_lo + (L->ghosted ? 2 : 0));
+}
+
+int gdtb_fvop_set_slab(gdtb_fvop* L, int64_t layer_begin, int64_t layer_end)
+{
+  if (!L)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  const long long n_last = L->grid.n[L->grid.d - 1];
+  if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
+  L->grid.layer_lo = layer_begin;
+  L->grid.layer_hi = layer_end;
+  L->ghosted = true;
+  cudaFree(L->d_tmp);
+  L->d_tmp = nullptr;
+  return GDTB_OK;
+}
+
+int gdtb_fvop_apply(gdtb_fvop* L, const double* d_source, double* d_range)
+{
+  if (!L || !d_source || !d_range)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_apply: NULL argument");
+  GDTB_TRY(check_ctx(L->ctx));
+  FvParams p;
+  p.g = L->grid;
+  p.flux = L->flux;
+  p.ghosted = L->ghosted ? 1 : 0;
+  p.euler = 0;
+  p.dt = 0.;
+  GDTB_TRY(launch_fv_apply(L->ctx->launch, p, d_source, d_range));
+  GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
+  return GDTB_OK;
+}
+
+static int fv_stage(gdtb_fvop* L)
+{
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  if (!L->d_src && cudaMalloc(&L->d_src, bytes) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (fv staging)");
+  if (!L->d_dst && cudaMalloc(&L->d_dst, bytes) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (fv staging)");
+  return GDTB_OK;
+}
+
+int gdtb_fvop_apply_host(gdtb_fvop* L, const double* source, double* range)
+{
+  if (!L || !source || !range)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_apply_host: NULL argument");
+  GDTB_TRY(check_ctx(L->ctx));
+  GDTB_TRY(fv_stage(L));
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  cudaStream_t s = L->ctx->launch.stream;
+  GDTB_CUDA(cudaMemcpyAsync(L->d_src, source, bytes, cudaMemcpyHostToDevice, s));
+  GDTB_TRY(gdtb_fvop_apply(L, L->d_src, L->d_dst));
+  GDTB_CUDA(cudaMemcpyAsync(range, L->d_dst, bytes, cudaMemcpyDeviceToHost, s));
+  GDTB_CUDA(cudaStreamSynchronize(s));
+  return GDTB_OK;
+}
+
+int gdtb_fvop_euler(gdtb_fvop* L, double* d_u, double dt, int64_t n_steps)
+{
+  if (!L || !d_u)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_euler: NULL argument");
+  if (n_steps < 0)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_euler: negative step count");
+  GDTB_TRY(check_ctx(L->ctx));
+  if (L->ghosted && n_steps > 1)
+    return fail(GDTB_ERR_INVALID_ARGUMENT,
+                "gdtb_fvop_euler: on a slab the ghost layers must be exchanged between steps (n_steps <= 1)");
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  if (!L->d_tmp && cudaMalloc(&L->d_tmp, bytes) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (fv euler buffer)");
+  FvParams p;
+  p.g = L->grid;
+  p.flux = L->flux;
+  p.ghosted = L->ghosted ? 1 : 0;
+  p.euler = 1;
+  p.dt = dt;
+  double* a = d_u;
+  double* b = L->d_tmp;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    GDTB_TRY(launch_fv_apply(L->ctx->launch, p, a, b));
+    std::swap(a, b);
+  }
+  if (a != d_u) // odd number of steps: result sits in the internal buffer
+    GDTB_CUDA(cudaMemcpyAsync(d_u, a, bytes, cudaMemcpyDeviceToDevice, L->ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int gdtb_fvop_euler_host(gdtb_fvop* L, double* u, double dt, int64_t n_steps)
+{
+  if (!L || !u)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_euler_host: NULL argument");
+  GDTB_TRY(check_ctx(L->ctx));
+  GDTB_TRY(fv_stage(L));
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  cudaStream_t s = L->ctx->launch.stream;
+  GDTB_CUDA(cudaMemcpyAsync(L->d_src, u, bytes, cudaMemcpyHostToDevice, s));
+  GDTB_TRY(gdtb_fvop_euler(L, L->d_src, dt, n_steps));
+  GDTB_CUDA(cudaMemcpyAsync(u, L->d_src, bytes, cudaMemcpyDeviceToHost, s));
+  GDTB_CUDA(cudaStreamSynchronize(s));
+  return GDTB_OK;
+}
+
+int gdtb_fv_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* d_u)
+{
+  if (!space || !f || !d_u)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fv_interpolate: NULL argument");
+  GDTB_TRY(check_ctx(ctx));
+  if (space->dev.kind != GDTB_SPACE_FV)
+    return fail(GDTB_ERR_SPACE, "gdtb_fv_interpolate needs a finite volume space");
+  GDTB_TRY(validate_function(*f, "function"));
+  if ((f->kind == GDTB_FN_ELEM_SCALAR || f->kind == GDTB_FN_ELEM_TENSOR) && !f->data_on_device)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fv_interpolate: per-element data must live on the device");
+  const int m = gauss_points_for_order(f->order);
+  if (m > MAX_Q1D)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "quadrature order too high");
+  double host[2 * MAX_Q1D] = {0};
+  gauss_legendre_01(m, host, host + MAX_Q1D);
+  double* d_rule = nullptr;
+  if (cudaMalloc(&d_rule, sizeof(host)) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory");
+  cudaError_t err = cudaMemcpy(d_rule, host, sizeof(host), cudaMemcpyHostToDevice);
+  int st = GDTB_OK;
+  if (err == cudaSuccess)
+    st = launch_fv_interpolate(ctx->launch, space->grid, to_dev(*f), m, d_rule, d_rule + MAX_Q1D, d_u);
+  if (st == GDTB_OK)
+    err = cudaStreamSynchronize(ctx->launch.stream);
+  cudaFree(d_rule);
+  if (st != GDTB_OK)
+    return st;
+  if (err != cudaSuccess)
+    return fail(GDTB_ERR_CUDA, std::string("gdtb_fv_interpolate: ") + cudaGetErrorString(err));
+  return GDTB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,317 @@
+/*
+ * include/gdtb.h -- C ABI of libgdtb.so: the B200 (sm_100a) implementation of dune-gdt's assembly and
+ * finite-volume operator-apply hot path.
+ *
+ * dune-gdt is a header-only C++ template library: it has no FFI of its own.  The boundary a maintainer
+ * binds is therefore the set of calls the C++ facade (dune-gdt_b200/include/dune/gdt/...) makes from
+ * MatrixOperator::assemble / VectorBasedFunctional::assemble / AdvectionFvOperator::apply.  Every entry
+ * point below names the reference interface it replaces (paths relative to the dune-gdt checkout).
+ *
+ * Conventions
+ *   - plain C: opaque handles, POD descriptors, pointers and sizes only; no C++/torch types.
+ *   - every function returns an int status: 0 = ok, otherwise one of the GDTB_ERR_* codes that mirror the
+ *     reference's exception classes (dune/gdt/exceptions.hh:24-75); gdtb_last_error() returns the
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - ownership: descriptors (forms, integrands, functions, fluxes) are CLONED at append/create time, like
+ *     copy()/copy_as_*_integrand() in the reference (operators/matrix-based.hh:346-408), including any
+ *     host array a gdtb_function points to; handles are owned by the caller until the matching *_destroy.
+ *     Device buffers are owned by the library unless a *_set_*_device call lends one.
+ *   - "host" entry points take host pointers and copy; "device" entry points take/return device pointers
+ *     valid on the context's device.
+ *   - all work is issued on the context's CUDA stream; calls block until complete unless documented
+ *     otherwise (*_async).  A handle must not be used from two threads at once (the reference's
+ *     operators are not re-entrant either).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *     GDTB_ERR_CUDA.
+ *
+ * Canonical matrix format (XT::LA::IstlRowMajorSparseMatrix / EigenRowMajorSparseMatrix compatible CSR):
+ * rowptr int64[rows+1], colidx int32[nnz] (ascending, unique per row), values double[nnz].
+ */
+#ifndef GDTB_H
+#define GDTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDTB_VERSION 1
+
+/* ---- status codes --------------------------------------------------------------------------- */
+enum
+{
+  GDTB_OK = 0,
+  GDTB_ERR_INVALID_ARGUMENT = 1, /* XT::Common::Exceptions::wrong_input_given                         */
+  GDTB_ERR_SHAPES_DO_NOT_MATCH = 2, /* XT::Common::Exceptions::shapes_do_not_match (matrix-based.hh:73-80) */
+  GDTB_ERR_INTEGRAND = 3,        /* Exceptions::integrand_error (ipdg.hh:93-94)                       */
+  GDTB_ERR_FINITE_ELEMENT = 4,   /* Exceptions::finite_element_error (lagrange.hh:107-136)            */
+  GDTB_ERR_SPACE = 5,            /* Exceptions::space_error / mapper_error                            */
+  GDTB_ERR_OPERATOR = 6,         /* Exceptions::operator_error                                        */
+  GDTB_ERR_NOT_IMPLEMENTED = 7,  /* Dune::NotImplemented                                              */
+  GDTB_ERR_CUDA = 8,             /* CUDA runtime failure / no device                                  */
+  GDTB_ERR_OUT_OF_MEMORY = 9
+};
+
+/* ---- descriptors ---------------------------------------------------------------------------- */
+
+/* XT::Grid::make_cube_grid<YaspGrid<d, EquidistantOffsetCoordinates<double,d>>>(lower, upper, n)
+ * (examples/stationary-heat-equation.cc:87) [+ make_periodic_grid_view, examples/mpi_2019_02...cc:261].
+ * slab_begin/slab_end select the element layers [begin, end) along the LAST direction that this
+ * process owns (multi-GPU element-block partition); 0/0 means the whole grid. */
+typedef struct gdtb_grid_desc
+{
+  int32_t dim;      /* 1, 2 or 3 */
+  int32_t periodic; /* bit k: periodic in direction k */
+  double lower[3];
+  double upper[3];
+  int64_t n[3];
+} gdtb_grid_desc;
+
+enum
+{
+  GDTB_SPACE_CG = 0, /* make_continuous_lagrange_space    (spaces/h1/continuous-lagrange.hh:189-203)     */
+  GDTB_SPACE_DG = 1, /* make_discontinuous_lagrange_space (spaces/l2/discontinuous-lagrange.hh:191-205)  */
+  GDTB_SPACE_FV = 2  /* make_finite_volume_space          (spaces/l2/finite-volume.hh:208-230)           */
+};
+
+/* Dune::GDT::Stencil (type_traits.hh:55-60) */
+enum
+{
+  GDTB_STENCIL_ELEMENT = 0,
+  GDTB_STENCIL_INTERSECTION = 1,
+  GDTB_STENCIL_ELEMENT_AND_INTERSECTION = 2
+};
+
+/* XT::Functions::GridFunction<E, r, rC> stand-ins.  User lambdas cannot cross a C ABI as code, so a
+ * grid function is a constant, a per-element array or one of a few analytic built-ins evaluated at the
+ * global coordinate.  `order` is what GridFunction::order() would return: it enters the quadrature
+ * order exactly like in the reference (laplace.hh:74-79, product.hh:89-100, conversion.hh:92). */
+enum
+{
+  GDTB_FN_CONST_SCALAR = 0, /* c[0]; used as a d x d function it means c[0] * I (laplace.hh:41) */
+  GDTB_FN_CONST_TENSOR = 1, /* c[0 .. d*d) row-major                                             */
+  GDTB_FN_ELEM_SCALAR = 2,  /* data[e], e = element index of the grid view                        */
+  GDTB_FN_ELEM_TENSOR = 3,  /* data[e*d*d + r*d + c]                                              */
+  GDTB_FN_BUILTIN = 4       /* see GDTB_BUILTIN_*                                                 */
+};
+
+enum
+{
+  GDTB_BUILTIN_COS_PRODUCT = 1, /* p0 * prod_i cos(p1 * x_i)  (heat-equation source, ESV2007 force) */
+  GDTB_BUILTIN_AFFINE = 2,      /* p0 + sum_i p[1+i] * x_i                                           */
+  GDTB_BUILTIN_GAUSSIAN = 3,    /* exp(-(x_0 - p0)^2 / (2 p1^2))  (examples/mpi...cc:321-326)        */
+  GDTB_BUILTIN_INDICATOR = 4,   /* p0 <= x_0 <= p1 ? 1 : 0        (examples/mpi...cc:275-283)        */
+  GDTB_BUILTIN_QUADRATIC = 5    /* p0 + p1 * sum_i x_i^2                                             */
+};
+
+typedef struct gdtb_function
+{
+  int32_t kind;
+  int32_t order;
+  int32_t builtin;
+  int32_t data_on_device; /* 0: `data` is a host array (cloned at append); 1: device array (borrowed) */
+  double c[9];
+  double p[8];
+  const double* data;
+} gdtb_function;
+
+enum
+{
+  GDTB_INT_LAPLACE = 0,                 /* LocalLaplaceIntegrand(diffusion)                   laplace.hh:40-48     */
+  GDTB_INT_PRODUCT = 1,                 /* LocalElementProductIntegrand(weight = diffusion)   product.hh:56-65     */
+  GDTB_INT_IPDG_INNER_COUPLING = 2,     /* LocalLaplaceIPDGIntegrands::InnerCoupling          laplace-ipdg.hh:47-61 */
+  GDTB_INT_IPDG_INNER_PENALTY = 3,      /* LocalIPDGIntegrands::InnerPenalty                  ipdg.hh:59-72        */
+  GDTB_INT_IPDG_DIRICHLET_COUPLING = 4, /* LocalLaplaceIPDGIntegrands::DirichletCoupling      laplace-ipdg.hh:237-252 */
+  GDTB_INT_IPDG_BOUNDARY_PENALTY = 5    /* LocalIPDGIntegrands::BoundaryPenalty               ipdg.hh:201-213      */
+};
+
+enum
+{
+  GDTB_HI_DIAMETER = 0, /* internal::default_intersection_diameter (ipdg.hh:27-38)          */
+  GDTB_HI_VOLUME = 1    /* intersection.geometry().volume() (test/.../ESV2007.hh:108-112)   */
+};
+
+typedef struct gdtb_integrand
+{
+  int32_t kind;
+  int32_t hI_kind;
+  double prefactor;        /* symmetry_prefactor (couplings) or penalty (penalties) */
+  gdtb_function diffusion; /* kappa; for GDTB_INT_PRODUCT: the weight */
+  gdtb_function weight;    /* omega of the IPDG integrands; for a functional: the function f of with_ansatz(f) */
+} gdtb_integrand;
+
+#define GDTB_MAX_TERMS 4
+
+/* Local*IntegralBilinearForm / LocalElementIntegralFunctional (integrand, over_integrate)
+ * (local/bilinear-forms/integrals.hh:52-63,169-180,305-316; local/functionals/integrals.hh:41-52);
+ * n_terms > 1 is integrand_a + integrand_b (local/integrands/combined.hh). */
+typedef struct gdtb_form
+{
+  int32_t n_terms;
+  int32_t over_integrate;
+  double scaling; /* MatrixOperator::scaling at append time (matrix-based.hh:342,365) */
+  gdtb_integrand terms[GDTB_MAX_TERMS];
+} gdtb_form;
+
+/* intersection filters [XT::Grid::ApplyOn], used at matrix-based.hh:371-408 */
+enum
+{
+  GDTB_FILTER_INNER_ONCE = 0,              /* ApplyOn::InnerIntersectionsOnce                        */
+  GDTB_FILTER_INNER_AND_PERIODIC_ONCE = 1, /* ... || PeriodicBoundaryIntersectionsOnce               */
+  GDTB_FILTER_ALL_BOUNDARY = 2             /* CustomBoundaryIntersections(AllDirichletBoundaryInfo, DirichletBoundary) */
+};
+
+enum
+{
+  GDTB_FLUX_LINEAR = 0, /* f(u) = a u, a = p[0..d)  (test/linear-transport/base.hh:50-57) */
+  GDTB_FLUX_BURGERS = 1 /* f(u) = u^2/2 (1,...,1)   (test/burgers/base.hh:38-44)          */
+};
+
+enum
+{
+  GDTB_NUMFLUX_UPWIND = 0,        /* NumericalUpwindFlux<I,d,1>      upwind.hh:44-73         */
+  GDTB_NUMFLUX_LAX_FRIEDRICHS = 1 /* NumericalLaxFriedrichsFlux      lax-friedrichs.hh:60-88 */
+};
+
+typedef struct gdtb_flux
+{
+  int32_t kind;
+  int32_t numflux;
+  double p[4];
+} gdtb_flux;
+
+enum
+{
+  GDTB_ASSEMBLE_OVERWRITE = 0, /* matrix/vector are known to be zero (fresh containers): values = assembled */
+  GDTB_ASSEMBLE_ACCUMULATE = 1 /* values += assembled (add_to_entry into existing content)                  */
+};
+
+typedef struct gdtb_ctx gdtb_ctx;
+typedef struct gdtb_grid gdtb_grid;
+typedef struct gdtb_space gdtb_space;
+typedef struct gdtb_pattern gdtb_pattern;
+typedef struct gdtb_matop gdtb_matop;
+typedef struct gdtb_vecfun gdtb_vecfun;
+typedef struct gdtb_fvop gdtb_fvop;
+
+/* ---- context -------------------------------------------------------------------------------- */
+const char* gdtb_last_error(void);
+int gdtb_version(void);
+/* one context per process and GPU; creates its own non-blocking stream */
+int gdtb_ctx_create(int device, gdtb_ctx** ctx);
+int gdtb_ctx_destroy(gdtb_ctx* ctx);
+/* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL restores the own stream */
+int gdtb_ctx_set_stream(gdtb_ctx* ctx, void* cuda_stream);
+int gdtb_ctx_synchronize(gdtb_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t gdtb_ctx_launch_count(const gdtb_ctx* ctx);
+
+/* ---- grid / spaces -------------------------------------------------------------------------- */
+/* replaces XT::Grid::make_cube_grid + leaf_view (examples/stationary-heat-equation.cc:87-88) */
+int gdtb_grid_create_cube(gdtb_ctx* ctx, const gdtb_grid_desc* desc, gdtb_grid** grid);
+int gdtb_grid_destroy(gdtb_grid* grid);
+int64_t gdtb_grid_num_elements(const gdtb_grid* grid);
+
+/* replaces make_{continuous_lagrange,discontinuous_lagrange,finite_volume}_space */
+int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order, gdtb_space** space);
+int gdtb_space_destroy(gdtb_space* space);
+/* MapperInterface::size / max_local_size / global_indices (spaces/mapper/interfaces.hh) */
+int64_t gdtb_space_size(const gdtb_space* space);
+int32_t gdtb_space_max_local_size(const gdtb_space* space);
+int gdtb_space_global_indices(const gdtb_space* space, int64_t element, int64_t* out);
+
+/* ---- sparsity pattern ----------------------------------------------------------------------- */
+enum
+{
+  GDTB_PATTERN_AUTO = 0,        /* structured closed form when available, else sort-unique */
+  GDTB_PATTERN_SORT_UNIQUE = 1, /* emit (row,col) keys per element/intersection, radix sort, unique, CSR */
+  GDTB_PATTERN_STRUCTURED = 2   /* closed-form tensor-product stencil generator */
+};
+/* replaces make_sparsity_pattern(test, ansatz, view, stencil) (tools/sparsity-pattern.hh:163-178) */
+int gdtb_pattern_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* ansatz, int stencil, int method,
+                        gdtb_pattern** pattern);
+int gdtb_pattern_destroy(gdtb_pattern* pattern);
+int64_t gdtb_pattern_rows(const gdtb_pattern* pattern);
+int64_t gdtb_pattern_cols(const gdtb_pattern* pattern);
+int64_t gdtb_pattern_nnz(const gdtb_pattern* pattern);
+int gdtb_pattern_download(const gdtb_pattern* pattern, int64_t* rowptr, int32_t* colidx);
+int gdtb_pattern_device(const gdtb_pattern* pattern, const int64_t** d_rowptr, const int32_t** d_colidx);
+
+/* ---- MatrixOperator (operators/matrix-based.hh:245-508) -------------------------------------- */
+/* make_matrix_operator<M>(view, source_space, range_space, pattern) (matrix-based.hh:514-598):
+ * rows = range/test space, cols = source/ansatz space. */
+int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* ansatz, const gdtb_pattern* pattern,
+                      gdtb_matop** op);
+int gdtb_matop_destroy(gdtb_matop* op);
+/* MatrixOperator::append(LocalElementBilinearFormInterface) (matrix-based.hh:346-369), filter AllElements */
+int gdtb_matop_append_element(gdtb_matop* op, const gdtb_form* form);
+/* MatrixOperator::append(LocalCouplingIntersectionBilinearFormInterface, param, filter) (matrix-based.hh:371-393) */
+int gdtb_matop_append_coupling(gdtb_matop* op, const gdtb_form* form, int filter);
+/* MatrixOperator::append(LocalIntersectionBilinearFormInterface, param, filter) (matrix-based.hh:395-408) */
+int gdtb_matop_append_boundary(gdtb_matop* op, const gdtb_form* form, int filter);
+/* drops all appended forms (dune-xt's walker clears its functors after each walk) */
+int gdtb_matop_clear_forms(gdtb_matop* op);
+int gdtb_matop_num_forms(const gdtb_matop* op);
+/* name of the kernel family the next assemble will use: "q1_gather", "generic_coloured", ... (diagnostics) */
+const char* gdtb_matop_plan(gdtb_matop* op);
+int gdtb_matop_set_zero(gdtb_matop* op);
+int gdtb_matop_values_download(const gdtb_matop* op, double* values);
+int gdtb_matop_values_upload(gdtb_matop* op, const double* values);
+int gdtb_matop_values_device(const gdtb_matop* op, double** d_values);
+/* lend a device buffer of nnz doubles (MatrixOperator's "borrow a caller matrix" ctor, matrix-based.hh:280-293) */
+int gdtb_matop_set_values_device(gdtb_matop* op, double* d_values);
+
+/* ---- VectorBasedFunctional (functionals/vector-based.hh:133-286) ------------------------------ */
+int gdtb_vecfun_create(gdtb_ctx* ctx, const gdtb_space* space, gdtb_vecfun** fun);
+int gdtb_vecfun_destroy(gdtb_vecfun* fun);
+/* append(LocalElementIntegralFunctional(LocalProductIntegrand(w).with_ansatz(f))) (vector-based.hh:214-222):
+ * form->terms[0].kind = GDTB_INT_PRODUCT, .diffusion = w, .weight = f */
+int gdtb_vecfun_append_element(gdtb_vecfun* fun, const gdtb_form* form);
+int gdtb_vecfun_clear_forms(gdtb_vecfun* fun);
+int gdtb_vecfun_set_zero(gdtb_vecfun* fun);
+int gdtb_vecfun_download(const gdtb_vecfun* fun, double* vector);
+int gdtb_vecfun_device(const gdtb_vecfun* fun, double** d_vector);
+int gdtb_vecfun_set_device(gdtb_vecfun* fun, double* d_vector);
+
+/* ---- the grid walk --------------------------------------------------------------------------- */
+/* MatrixOperator::assemble / VectorBasedFunctional::assemble / walker.walk() with both appended
+ * (matrix-based.hh:496-500, vector-based.hh:276-279, examples/stationary-heat-equation.cc:102-106):
+ * one pass over the grid for everything appended to `op` and `fun` (either may be NULL). */
+int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode);
+/* convenience for host-side callers: assemble (overwrite) and copy values / vector to host buffers (may be NULL) */
+int gdtb_assemble_host(gdtb_matop* op, gdtb_vecfun* fun, double* values, double* vector);
+
+/* ---- AdvectionFvOperator (operators/advection-fv.hh:44-141) ----------------------------------- */
+/* make_advection_fv_operator<M>(view, numerical_flux, source_space, range_space) */
+int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* flux, gdtb_fvop** L);
+int gdtb_fvop_destroy(gdtb_fvop* L);
+/* LocalizableOperator::apply(source, range) (operators/localizable-operator.hh:352-387): range = L(source).
+ * Device pointers, each gdtb_space_size doubles. */
+int gdtb_fvop_apply(gdtb_fvop* L, const double* d_source, double* d_range);
+int gdtb_fvop_apply_host(gdtb_fvop* L, const double* source, double* range);
+/* explicit Euler u <- u - L(u) dt (examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:152-157), fused
+ * apply + axpy, n_steps times, ping-ponging between d_u and an internal buffer; result ends in d_u. */
+int gdtb_fvop_euler(gdtb_fvop* L, double* d_u, double dt, int64_t n_steps);
+int gdtb_fvop_euler_host(gdtb_fvop* L, double* u, double dt, int64_t n_steps);
+/* Multi-GPU (slab partition along the last direction): the local vector carries one ghost layer below
+ * and above the owned cells: layout [ghost_lo | owned | ghost_hi], each ghost layer = n[0]*..*n[dim-2]
+ * cells.  The caller fills the ghost layers (NCCL send/recv of the neighbours' boundary layers,
+ * tools/timestepper/explicit-rungekutta.hh:252-257) before calling apply. */
+int gdtb_fvop_set_slab(gdtb_fvop* L, int64_t layer_begin, int64_t layer_end);
+int64_t gdtb_fvop_ghost_layer_size(const gdtb_fvop* L);
+
+/* default_interpolation(order, f, fv_space) (interpolations/default.hh:76-83, spaces/basis/finite-volume.hh:244-252) */
+int gdtb_fv_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* d_u);
+
+/* ---- multi-GPU assembly ----------------------------------------------------------------------- */
+/* Restrict a matrix operator / functional to the element layers [begin, end) along the last direction
+ * (element-block partition).  Rows touched by elements of other slabs hold partial sums that the caller
+ * completes with the interface-row halo (see dune-gdt_b200/python/gdtb/distributed.py). */
+int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end);
+int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDTB_H */

@@ -1,0 +1,153 @@
+"""Python loader of the CPU restatement oracle (oracle/oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing in dune-gdt_b200/ (the product) imports this package.
+Descriptor layouts are shared with include/gdtb.h, so the ctypes classes of dune_gdt_b200.descriptors are reused.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle.h", "Makefile")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        from dune_gdt_b200.descriptors import Flux, Form, Function, GridDesc
+
+        if not os.path.exists(LIB_PATH):
+            build()
+        h = C.CDLL(LIB_PATH)
+        P, DP = C.c_void_p, C.POINTER(C.c_double)
+        I64P, I32P = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+        G = C.POINTER(GridDesc)
+        protos = {
+            "orc_num_elements": (C.c_int64, [G]),
+            "orc_space_size": (C.c_int64, [G, C.c_int, C.c_int]),
+            "orc_space_local_size": (C.c_int32, [G, C.c_int, C.c_int]),
+            "orc_space_global_indices": (None, [G, C.c_int, C.c_int, C.c_int64, I64P]),
+            "orc_gauss_rule": (C.c_int32, [C.c_int, DP, DP]),
+            "orc_shape_values": (None, [C.c_int, C.c_int, DP, DP]),
+            "orc_shape_gradients": (None, [C.c_int, C.c_int, DP, DP]),
+            "orc_pattern_create": (P, [G, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+            "orc_pattern_rows": (C.c_int64, [P]),
+            "orc_pattern_nnz": (C.c_int64, [P]),
+            "orc_pattern_copy": (None, [P, I64P, I32P]),
+            "orc_pattern_free": (None, [P]),
+            "orc_assemble": (
+                C.c_int,
+                [G, C.c_int, C.c_int, I64P, I32P, DP, C.c_int, C.POINTER(Form), C.c_int, C.POINTER(Form), C.c_int,
+                 C.POINTER(Form), C.c_int, C.POINTER(Form), DP, C.c_int],
+            ),
+            "orc_local_element_matrix": (None, [G, C.c_int, C.c_int, C.POINTER(Form), C.c_int64, DP]),
+            "orc_fv_apply": (C.c_int, [G, C.POINTER(Flux), DP, DP, C.c_int]),
+            "orc_fv_euler": (C.c_int, [G, C.POINTER(Flux), DP, C.c_double, C.c_int64, C.c_int]),
+            "orc_fv_interpolate": (None, [G, C.POINTER(Function), DP]),
+            "orc_function_eval": (C.c_double, [C.POINTER(Function), C.c_int, DP, C.c_int64]),
+            "orc_last_error": (C.c_char_p, []),
+        }
+        for name, (res, args) in protos.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def space_size(grid, kind, order):
+    return lib().orc_space_size(C.byref(grid), kind, order)
+
+
+def local_size(grid, kind, order):
+    return lib().orc_space_local_size(C.byref(grid), kind, order)
+
+
+def global_indices(grid, kind, order, element):
+    out = np.zeros(local_size(grid, kind, order), dtype=np.int64)
+    lib().orc_space_global_indices(C.byref(grid), kind, order, element, out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out
+
+
+def gauss_rule(order):
+    x, w = np.zeros(8), np.zeros(8)
+    m = lib().orc_gauss_rule(order, _dp(x), _dp(w))
+    return x[:m], w[:m]
+
+
+def pattern(grid, test=(0, 1), ansatz=None, stencil=0):
+    """returns (rowptr int64, colidx int32); test/ansatz = (kind, order)"""
+    ansatz = ansatz or test
+    p = lib().orc_pattern_create(C.byref(grid), test[0], test[1], ansatz[0], ansatz[1], stencil)
+    rows, nnz = lib().orc_pattern_rows(p), lib().orc_pattern_nnz(p)
+    rowptr, colidx = np.empty(rows + 1, dtype=np.int64), np.empty(nnz, dtype=np.int32)
+    lib().orc_pattern_copy(p, rowptr.ctypes.data_as(C.POINTER(C.c_int64)), colidx.ctypes.data_as(C.POINTER(C.c_int32)))
+    lib().orc_pattern_free(p)
+    return rowptr, colidx
+
+
+def _forms(forms):
+    from dune_gdt_b200.descriptors import Form
+
+    forms = list(forms or [])
+    arr = (Form * max(len(forms), 1))()
+    for i, f in enumerate(forms):
+        C.memmove(C.byref(arr[i]), C.byref(f), C.sizeof(Form))
+    arr._refs = forms
+    return len(forms), arr
+
+
+def assemble(grid, kind, order, rowptr, colidx, element_forms=(), coupling_forms=(), boundary_forms=(), rhs_forms=(),
+             num_threads=1):
+    """one grid walk; returns (values[nnz], rhs[ndof])"""
+    values = np.zeros(len(colidx), dtype=np.float64)
+    rhs = np.zeros(len(rowptr) - 1, dtype=np.float64)
+    ne, ef = _forms(element_forms)
+    nc, cf = _forms(coupling_forms)
+    nb, bf = _forms(boundary_forms)
+    nr, rf = _forms(rhs_forms)
+    st = lib().orc_assemble(
+        C.byref(grid), kind, order, rowptr.ctypes.data_as(C.POINTER(C.c_int64)),
+        colidx.ctypes.data_as(C.POINTER(C.c_int32)), _dp(values), ne, ef, nc, cf, nb, bf, nr, rf, _dp(rhs), num_threads)
+    if st != 0:
+        raise RuntimeError(lib().orc_last_error().decode())
+    return values, rhs
+
+
+def local_element_matrix(grid, kind, order, form, element):
+    n = local_size(grid, kind, order)
+    out = np.zeros((n, n))
+    lib().orc_local_element_matrix(C.byref(grid), kind, order, C.byref(form), element, _dp(out))
+    return out
+
+
+def fv_apply(grid, flux, u, num_threads=1):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty_like(u)
+    lib().orc_fv_apply(C.byref(grid), C.byref(flux), _dp(u), _dp(out), num_threads)
+    return out
+
+
+def fv_euler(grid, flux, u, dt, n_steps, num_threads=1):
+    u = np.array(u, dtype=np.float64, copy=True)
+    lib().orc_fv_euler(C.byref(grid), C.byref(flux), _dp(u), dt, n_steps, num_threads)
+    return u
+
+
+def fv_interpolate(grid, function):
+    u = np.empty(lib().orc_num_elements(C.byref(grid)), dtype=np.float64)
+    lib().orc_fv_interpolate(C.byref(grid), C.byref(function), _dp(u))
+    return u
