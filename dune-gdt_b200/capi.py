@@ -81,6 +81,8 @@ PROTOTYPES = {
     "gdtb_ctx_set_stream": (C.c_int, [_P, _P]),
     "gdtb_ctx_synchronize": (C.c_int, [_P]),
     "gdtb_ctx_launch_count": (C.c_int64, [_P]),
+    "gdtb_ctx_enable_timing": (C.c_int, [_P, C.c_int]),
+    "gdtb_ctx_kernel_time": (C.c_int, [_P, C.c_char_p, _DP, _I64P]),
     "gdtb_grid_create_cube": (C.c_int, [_P, C.POINTER(GridDesc), _PP]),
     "gdtb_grid_destroy": (C.c_int, [_P]),
     "gdtb_grid_num_elements": (C.c_int64, [_P]),
@@ -120,6 +122,9 @@ PROTOTYPES = {
     "gdtb_vecfun_set_device": (C.c_int, [_P, _P]),
     "gdtb_vecfun_set_slab": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gdtb_assemble": (C.c_int, [_P, _P, C.c_int]),
+    "gdtb_assemble_async": (C.c_int, [_P, _P, C.c_int]),
+    "gdtb_matop_local_nnz": (C.c_int64, [_P]),
+    "gdtb_matop_local_rows": (C.c_int, [_P, _I64P, _I64P, _I64P]),
     "gdtb_assemble_host": (C.c_int, [_P, _P, _DP, _DP]),
     "gdtb_fvop_create": (C.c_int, [_P, _P, C.POINTER(Flux), _PP]),
     "gdtb_fvop_destroy": (C.c_int, [_P]),

@@ -638,6 +638,7 @@ struct ElementMatrixLauncher
   static int run(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, const long long* rowptr,
                  const int* colidx, double* values, int* error_flag)
   {
+    time_begin(L, KF_ELEMENT_MATRIX);
     const bool coloured = sp.kind == GDTB_SPACE_CG;
     const int ncol = coloured ? (1 << g.d) : 1;
     for (int c = 0; c < ncol; ++c) {
@@ -649,6 +650,7 @@ struct ElementMatrixLauncher
                                                                              error_flag);
       L.count++;
     }
+    time_end(L, KF_ELEMENT_MATRIX);
     GDTB_CUDA(cudaGetLastError());
     return GDTB_OK;
   }
@@ -659,6 +661,7 @@ struct ElementVectorLauncher
 {
   static int run(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, double* vec)
   {
+    time_begin(L, KF_ELEMENT_VECTOR);
     const bool coloured = sp.kind == GDTB_SPACE_CG;
     const int ncol = coloured ? (1 << g.d) : 1;
     for (int c = 0; c < ncol; ++c) {
@@ -669,6 +672,7 @@ struct ElementVectorLauncher
       k_element_vector<D, K><<<blocks_for(threads, 128), 128, 0, L.stream>>>(g, sp, f, r, vec);
       L.count++;
     }
+    time_end(L, KF_ELEMENT_VECTOR);
     GDTB_CUDA(cudaGetLastError());
     return GDTB_OK;
   }
@@ -680,6 +684,7 @@ struct CouplingLauncher
   static int run(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, int filter,
                  const long long* rowptr, const int* colidx, double* values, int* error_flag)
   {
+    time_begin(L, KF_COUPLING_MATRIX);
     // classes per direction: inner faces with even / odd lower element, then the periodic wrap faces
     for (int k = 0; k < g.d; ++k)
       for (int cls = 0; cls < 3; ++cls) {
@@ -707,6 +712,7 @@ struct CouplingLauncher
                                                                                 colidx, values, error_flag);
         L.count++;
       }
+    time_end(L, KF_COUPLING_MATRIX);
     GDTB_CUDA(cudaGetLastError());
     return GDTB_OK;
   }
@@ -718,6 +724,7 @@ struct BoundaryLauncher
   static int run(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, const long long* rowptr,
                  const int* colidx, double* values, int* error_flag)
   {
+    time_begin(L, KF_BOUNDARY_MATRIX);
     for (int k = 0; k < g.d; ++k) {
       if (g.periodic & (1 << k))
         continue; // periodic intersections have a neighbour
@@ -735,6 +742,7 @@ struct BoundaryLauncher
         L.count++;
       }
     }
+    time_end(L, KF_BOUNDARY_MATRIX);
     GDTB_CUDA(cudaGetLastError());
     return GDTB_OK;
   }

@@ -80,8 +80,8 @@ __global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __
   const int last = D - 1;
   const long long Nx = g.n[0], Ny = D > 1 ? g.n[1] : 1, Nz = D > 2 ? g.n[2] : 1;
   const long long Wx = 3 * Nx + 1, Wy = D > 1 ? 3 * Ny + 1 : 1;
-  // vertex rows handled by this process along the last axis: [layer_lo, layer_hi]
-  const long long lines_y = D == 3 ? Ny + 1 : (D == 2 ? g.layer_hi - g.layer_lo + 1 : 1);
+  // vertex rows handled by this process along the last axis: [row_lo, row_hi)
+  const long long lines_y = D == 3 ? Ny + 1 : (D == 2 ? p.row_hi - p.row_lo : 1);
 
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const long long line = item / nchunks;
@@ -89,11 +89,11 @@ __global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __
     long long iv[3] = {0, 0, 0};
     if (D == 3) {
       iv[1] = line % lines_y;
-      iv[2] = g.layer_lo + line / lines_y;
+      iv[2] = p.row_lo + line / lines_y;
     } else if (D == 2) {
-      iv[1] = g.layer_lo + line;
+      iv[1] = p.row_lo + line;
     }
-    const long long x_lo = D == 1 ? g.layer_lo : 0, x_hi = D == 1 ? g.layer_hi + 1 : Nx + 1; // vertex range in x
+    const long long x_lo = D == 1 ? p.row_lo : 0, x_hi = D == 1 ? p.row_hi : Nx + 1; // vertex range in x
     const long long x0 = x_lo + (long long)ch * chunk;
     const long long x1 = min(x0 + chunk, x_hi);
 
@@ -122,8 +122,8 @@ __global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __
       bool ok[3][2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const long long elo = (k == last) ? g.layer_lo : 0;
-        const long long ehi = (k == last) ? g.layer_hi : (k < D ? g.n[k] : 1);
+        const long long elo = (k == last) ? p.elem_lo : 0;
+        const long long ehi = (k == last) ? p.elem_hi : (k < D ? g.n[k] : 1);
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           const long long e = iv[k] - 1 + o;
@@ -248,14 +248,15 @@ __global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __
 // Separable right-hand side tables: for f(x) = p0 * prod_k F_k(x_k),
 //   B_k[i] = sum over the (valid) cells e in {i-1, i} of  sum_q w_q phi_a(xi_q) F_k(lower_e + xi_q * ext_e),
 // a = local index of vertex i in cell e.  One block, strided over (axis, vertex).
-__global__ void k_q1_rhs_tables(const GridDev g, const FnDev f, int m, const double* __restrict__ qx,
+__global__ void k_q1_rhs_tables(const GridDev g, long long elem_lo, long long elem_hi, const FnDev f, int m,
+                                const double* __restrict__ qx,
                                 const double* __restrict__ qw, const double* __restrict__ phi,
                                 double* __restrict__ tab, long long stride)
 {
   const int last = g.d - 1;
   for (int k = 0; k < g.d; ++k) {
-    const long long elo = (k == last) ? g.layer_lo : 0;
-    const long long ehi = (k == last) ? g.layer_hi : g.n[k];
+    const long long elo = (k == last) ? elem_lo : 0;
+    const long long ehi = (k == last) ? elem_hi : g.n[k];
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i <= g.n[k];
          i += (long long)gridDim.x * blockDim.x) {
       double s = 0.;
@@ -287,10 +288,10 @@ __global__ void k_q1_rhs_tables(const GridDev g, const FnDev f, int m, const dou
 
 } // namespace
 
-int launch_q1_rhs_tables(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx, const double* qw,
-                         const double* phi, double* tab, long long stride)
+int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long long elem_hi, const FnDev& f, int m,
+                         const double* qx, const double* qw, const double* phi, double* tab, long long stride)
 {
-  k_q1_rhs_tables<<<8, 256, 0, L.stream>>>(g, f, m, qx, qw, phi, tab, stride);
+  k_q1_rhs_tables<<<8, 256, 0, L.stream>>>(g, elem_lo, elem_hi, f, m, qx, qw, phi, tab, stride);
   L.count++;
   GDTB_CUDA(cudaGetLastError());
   return GDTB_OK;
@@ -300,16 +301,16 @@ template <int D>
 static int launch_q1_gather_d(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
 {
   const GridDev& g = p.g;
-  const long long nvx = D == 1 ? g.layer_hi - g.layer_lo + 1 : g.n[0] + 1;
+  const long long nvx = D == 1 ? p.row_hi - p.row_lo : g.n[0] + 1;
   const int max_chunk = 512;
   const int nchunks = int((nvx + max_chunk - 1) / max_chunk);
   const int chunk = int((nvx + nchunks - 1) / nchunks);
   const int threads = ((chunk + 31) / 32) * 32;
   long long nlines = 1;
   if (D == 3)
-    nlines = (g.n[1] + 1) * (g.layer_hi - g.layer_lo + 1);
+    nlines = (g.n[1] + 1) * (p.row_hi - p.row_lo);
   else if (D == 2)
-    nlines = g.layer_hi - g.layer_lo + 1;
+    nlines = p.row_hi - p.row_lo;
   const long long nitems = nlines * nchunks;
   const size_t smem = values ? (size_t)(chunk * P3<D>::value + 2) * sizeof(double) : 16;
   auto kern = accumulate ? k_q1_gather<D, true> : k_q1_gather<D, false>;
@@ -321,7 +322,9 @@ static int launch_q1_gather_d(Launch& L, const Q1GatherParams& p, double* values
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)
     grid = nitems;
+  time_begin(L, KF_Q1_GATHER);
   kern<<<(unsigned)grid, threads, smem, L.stream>>>(p, values, rhs, chunk, nchunks, nitems);
+  time_end(L, KF_Q1_GATHER);
   L.count++;
   GDTB_CUDA(cudaGetLastError());
   return GDTB_OK;

@@ -101,7 +101,9 @@ struct gdtb_ctx
   int device;
   cudaStream_t own_stream;
   Launch launch;
+  Timing timing;
   int* d_error_flag;
+  bool error_flag_pending; // an asynchronous generic assemble has not been checked yet
 };
 
 struct gdtb_grid
@@ -157,6 +159,11 @@ struct gdtb_matop
   bool owns_values;
   std::vector<LoweredForm> element_forms, coupling_forms, boundary_forms;
   std::string plan;
+  // owner-computes-rows slab (multi-GPU): only the rows [row_begin, row_end) live in d_values
+  bool slab;
+  long long row_begin, row_end;   // global row range held by this process
+  long long value_offset, nnz_local;
+  long long row_lo, row_hi, elem_lo, elem_hi; // vertex / element layers along the last direction
 };
 
 struct gdtb_vecfun
@@ -169,6 +176,11 @@ struct gdtb_vecfun
   std::vector<LoweredForm> forms;
   double* d_sep_tab; // separable right-hand-side tables for the gather kernel
   double* d_rule;    // qx | qw | phi for the table kernel
+  bool slab;
+  long long row_begin, row_end;
+  long long row_lo, row_hi, elem_lo, elem_hi;
+  double h_rule[4 * MAX_Q1D];
+  bool rule_uploaded;
 };
 
 struct gdtb_fvop
@@ -340,7 +352,9 @@ bool matop_q1_eligible(const gdtb_matop* op)
 {
   if (!q1_space(op->test) || !q1_space(op->ansatz) || op->grid.periodic)
     return false;
-  if (op->pattern->stencil != GDTB_STENCIL_ELEMENT || !q1_space(op->pattern->test) || !q1_space(op->pattern->ansatz))
+  if (op->pattern
+      && (op->pattern->stencil != GDTB_STENCIL_ELEMENT || !q1_space(op->pattern->test)
+          || !q1_space(op->pattern->ansatz)))
     return false;
   if (!op->coupling_forms.empty() || !op->boundary_forms.empty() || op->element_forms.empty())
     return false;
@@ -476,12 +490,53 @@ void add_to_T(double T[8][8], const double Lref[8][8], double scale, int d)
   }
 }
 
+// closed-form CSR row pointer of the CG-Q1 element stencil (same formula as the kernels)
+long long q1_S(long long i, long long N)
+{
+  return i == 0 ? 0 : (i > N ? 3 * N + 1 : 3 * i - 1);
+}
+
+// global CSR position of the first entry of vertex layer `layer` along the last direction
+long long q1_layer_rowptr(const GridDev& g, long long layer)
+{
+  long long w = 1;
+  for (int k = 0; k < g.d - 1; ++k)
+    w *= 3 * g.n[k] + 1;
+  return q1_S(layer, g.n[g.d - 1]) * w;
+}
+
+long long q1_layer_rows(const GridDev& g)
+{
+  long long v = 1;
+  for (int k = 0; k < g.d - 1; ++k)
+    v *= g.n[k] + 1;
+  return v;
+}
+
+// owner-computes-rows ranges of the slab [begin, end) of element layers: vertex layers [begin, end) plus the top
+// layer on the last slab, produced from the element layers [begin - 1, end)
+void q1_slab_ranges(const GridDev& g, long long begin, long long end, long long& row_lo, long long& row_hi,
+                    long long& elem_lo, long long& elem_hi)
+{
+  const long long n_last = g.n[g.d - 1];
+  row_lo = begin;
+  row_hi = end == n_last ? n_last + 1 : end;
+  elem_lo = std::max<long long>(begin - 1, 0);
+  elem_hi = end;
+}
+
 int build_q1_params(gdtb_matop* op, gdtb_vecfun* fun, Q1GatherParams& p)
 {
   std::memset(&p, 0, sizeof(p));
   const GridDev& g = op ? op->grid : fun->grid;
   p.g = g;
   const int d = g.d;
+  p.row_lo = op ? op->row_lo : fun->row_lo;
+  p.row_hi = op ? op->row_hi : fun->row_hi;
+  p.elem_lo = op ? op->elem_lo : fun->elem_lo;
+  p.elem_hi = op ? op->elem_hi : fun->elem_hi;
+  p.value_offset = q1_layer_rowptr(g, p.row_lo);
+  p.row_offset = p.row_lo * q1_layer_rows(g);
   if (op) {
     for (const auto& lf : op->element_forms) {
       Q1Tables tab;
@@ -543,6 +598,8 @@ int gdtb_ctx_create(int device, gdtb_ctx** out)
   }
   ctx->launch.stream = ctx->own_stream;
   ctx->launch.count = 0;
+  ctx->launch.timing = &ctx->timing;
+  ctx->error_flag_pending = false;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
     cudaStreamDestroy(ctx->own_stream);
@@ -582,7 +639,62 @@ int gdtb_ctx_set_stream(gdtb_ctx* ctx, void* cuda_stream)
 int gdtb_ctx_synchronize(gdtb_ctx* ctx)
 {
   GDTB_TRY(check_ctx(ctx));
+  if (ctx->error_flag_pending) {
+    // scatter kernels flag local entries that are missing from the pattern (the reference's add_to_entry throws)
+    int flag = 0;
+    GDTB_CUDA(cudaMemcpyAsync(&flag, ctx->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->launch.stream));
+    GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+    ctx->error_flag_pending = false;
+    if (flag) {
+      GDTB_CUDA(cudaMemset(ctx->d_error_flag, 0, sizeof(int)));
+      return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH,
+                  "add_to_entry: a local entry is not part of the sparsity pattern (wrong stencil for the appended "
+                  "forms?)");
+    }
+    return GDTB_OK;
+  }
   GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int gdtb_ctx_enable_timing(gdtb_ctx* ctx, int enabled)
+{
+  GDTB_TRY(check_ctx(ctx));
+  ctx->timing.enabled = enabled != 0;
+  return GDTB_OK;
+}
+
+int gdtb_ctx_kernel_time(gdtb_ctx* ctx, const char* family, double* total_ms, int64_t* launches)
+{
+  GDTB_TRY(check_ctx(ctx));
+  static const char* names[KF_COUNT] = {"q1_gather",      "fv_apply",        "element_matrix",
+                                        "element_vector", "coupling_matrix", "boundary_matrix"};
+  int fam = -1;
+  for (int i = 0; i < KF_COUNT; ++i)
+    if (family && std::strcmp(family, names[i]) == 0)
+      fam = i;
+  if (fam < 0)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown kernel family");
+  GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+  auto& st = ctx->timing.start[fam];
+  auto& en = ctx->timing.stop[fam];
+  double total = 0.;
+  const size_t n = std::min(st.size(), en.size());
+  for (size_t i = 0; i < n; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, st[i], en[i]);
+    total += ms;
+  }
+  for (auto e : st)
+    cudaEventDestroy(e);
+  for (auto e : en)
+    cudaEventDestroy(e);
+  st.clear();
+  en.clear();
+  if (total_ms)
+    *total_ms = total;
+  if (launches)
+    *launches = (int64_t)n;
   return GDTB_OK;
 }
 
@@ -812,11 +924,14 @@ int gdtb_pattern_device(const gdtb_pattern* p, const int64_t** d_rowptr, const i
 int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* ansatz, const gdtb_pattern* pattern,
                       gdtb_matop** out)
 {
-  if (!test || !ansatz || !pattern || !out)
+  if (!test || !ansatz || !out)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_create: NULL argument");
   GDTB_TRY(check_ctx(ctx));
+  if (!pattern && !(q1_space(test->dev) && q1_space(ansatz->dev) && !test->grid.periodic))
+    return fail(GDTB_ERR_INVALID_ARGUMENT,
+                "gdtb_matop_create: a pattern is required (only the CG Q1 element stencil has a closed form)");
   // matrix-based.hh:73-80: matrix.rows() == range_space.mapper().size(), cols == source_space.mapper().size()
-  if (pattern->rows != test->dev.size || pattern->cols != ansatz->dev.size)
+  if (pattern && (pattern->rows != test->dev.size || pattern->cols != ansatz->dev.size))
     return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "pattern shape does not match the spaces (rows = test, cols = ansatz)");
   if (std::memcmp(&test->grid, &ansatz->grid, sizeof(GridDev)) != 0)
     return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "test and ansatz space live on different grids");
@@ -830,9 +945,26 @@ int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* a
   op->pattern = pattern;
   op->d_values = nullptr;
   op->owns_values = true;
-  if (cudaMalloc(&op->d_values, sizeof(double) * (size_t)std::max<long long>(pattern->nnz, 1)) != cudaSuccess)
-    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the matrix values");
-  GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pattern->nnz, ctx->launch.stream));
+  op->slab = false;
+  op->row_begin = 0;
+  op->row_end = test->dev.size;
+  op->value_offset = 0;
+  if (pattern)
+    op->nnz_local = pattern->nnz;
+  else {
+    op->nnz_local = 1;
+    for (int k = 0; k < op->grid.d; ++k)
+      op->nnz_local *= 3 * op->grid.n[k] + 1;
+  }
+  op->row_lo = 0;
+  op->row_hi = op->grid.n[op->grid.d - 1] + 1;
+  op->elem_lo = 0;
+  op->elem_hi = op->grid.n[op->grid.d - 1];
+  if (pattern || true) {
+    if (cudaMalloc(&op->d_values, sizeof(double) * (size_t)std::max<long long>(op->nnz_local, 1)) != cudaSuccess)
+      return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the matrix values");
+    GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)op->nnz_local, ctx->launch.stream));
+  }
   *out = op.release();
   return GDTB_OK;
 }
@@ -934,7 +1066,7 @@ int gdtb_matop_set_zero(gdtb_matop* op)
   if (!op)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
   GDTB_TRY(check_ctx(op->ctx));
-  GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)op->pattern->nnz, op->ctx->launch.stream));
+  GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)op->nnz_local, op->ctx->launch.stream));
   GDTB_CUDA(cudaStreamSynchronize(op->ctx->launch.stream));
   return GDTB_OK;
 }
@@ -944,7 +1076,7 @@ int gdtb_matop_values_download(const gdtb_matop* op, double* values)
   if (!op || !values)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_values_download: NULL argument");
   GDTB_TRY(check_ctx(op->ctx));
-  GDTB_CUDA(cudaMemcpyAsync(values, op->d_values, sizeof(double) * (size_t)op->pattern->nnz, cudaMemcpyDeviceToHost,
+  GDTB_CUDA(cudaMemcpyAsync(values, op->d_values, sizeof(double) * (size_t)op->nnz_local, cudaMemcpyDeviceToHost,
                             op->ctx->launch.stream));
   GDTB_CUDA(cudaStreamSynchronize(op->ctx->launch.stream));
   return GDTB_OK;
@@ -955,7 +1087,7 @@ int gdtb_matop_values_upload(gdtb_matop* op, const double* values)
   if (!op || !values)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_values_upload: NULL argument");
   GDTB_TRY(check_ctx(op->ctx));
-  GDTB_CUDA(cudaMemcpyAsync(op->d_values, values, sizeof(double) * (size_t)op->pattern->nnz, cudaMemcpyHostToDevice,
+  GDTB_CUDA(cudaMemcpyAsync(op->d_values, values, sizeof(double) * (size_t)op->nnz_local, cudaMemcpyHostToDevice,
                             op->ctx->launch.stream));
   GDTB_CUDA(cudaStreamSynchronize(op->ctx->launch.stream));
   return GDTB_OK;
@@ -984,11 +1116,45 @@ int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end)
 {
   if (!op)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  GDTB_TRY(check_ctx(op->ctx));
   const long long n_last = op->grid.n[op->grid.d - 1];
   if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
+  if (!q1_space(op->test) || !q1_space(op->ansatz))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab-partitioned assembly is implemented for CG Q1 spaces");
+  if (!op->owns_values)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_set_slab must be called before lending a value buffer");
   op->grid.layer_lo = layer_begin;
   op->grid.layer_hi = layer_end;
+  op->slab = true;
+  q1_slab_ranges(op->grid, layer_begin, layer_end, op->row_lo, op->row_hi, op->elem_lo, op->elem_hi);
+  op->row_begin = op->row_lo * q1_layer_rows(op->grid);
+  op->row_end = op->row_hi * q1_layer_rows(op->grid);
+  op->value_offset = q1_layer_rowptr(op->grid, op->row_lo);
+  op->nnz_local = q1_layer_rowptr(op->grid, op->row_hi) - op->value_offset;
+  cudaFree(op->d_values);
+  op->d_values = nullptr;
+  if (cudaMalloc(&op->d_values, sizeof(double) * (size_t)op->nnz_local) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the matrix values of the slab");
+  GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)op->nnz_local, op->ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int64_t gdtb_matop_local_nnz(const gdtb_matop* op)
+{
+  return op ? op->nnz_local : 0;
+}
+
+int gdtb_matop_local_rows(const gdtb_matop* op, int64_t* row_begin, int64_t* row_end, int64_t* value_offset)
+{
+  if (!op)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  if (row_begin)
+    *row_begin = op->row_begin;
+  if (row_end)
+    *row_end = op->row_end;
+  if (value_offset)
+    *value_offset = op->value_offset;
   return GDTB_OK;
 }
 
@@ -1006,6 +1172,14 @@ int gdtb_vecfun_create(gdtb_ctx* ctx, const gdtb_space* space, gdtb_vecfun** out
   f->owns_vec = true;
   f->d_sep_tab = nullptr;
   f->d_rule = nullptr;
+  f->slab = false;
+  f->rule_uploaded = false;
+  f->row_begin = 0;
+  f->row_end = space->dev.size;
+  f->row_lo = 0;
+  f->row_hi = space->grid.n[space->grid.d - 1] + 1;
+  f->elem_lo = 0;
+  f->elem_hi = space->grid.n[space->grid.d - 1];
   if (cudaMalloc(&f->d_vec, sizeof(double) * (size_t)std::max<long long>(space->dev.size, 1)) != cudaSuccess)
     return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the vector");
   GDTB_CUDA(cudaMemsetAsync(f->d_vec, 0, sizeof(double) * (size_t)space->dev.size, ctx->launch.stream));
@@ -1056,7 +1230,8 @@ int gdtb_vecfun_set_zero(gdtb_vecfun* fun)
   if (!fun)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "functional is NULL");
   GDTB_TRY(check_ctx(fun->ctx));
-  GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)fun->space.size, fun->ctx->launch.stream));
+  GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)(fun->row_end - fun->row_begin),
+                            fun->ctx->launch.stream));
   GDTB_CUDA(cudaStreamSynchronize(fun->ctx->launch.stream));
   return GDTB_OK;
 }
@@ -1066,8 +1241,8 @@ int gdtb_vecfun_download(const gdtb_vecfun* fun, double* vector)
   if (!fun || !vector)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_download: NULL argument");
   GDTB_TRY(check_ctx(fun->ctx));
-  GDTB_CUDA(cudaMemcpyAsync(vector, fun->d_vec, sizeof(double) * (size_t)fun->space.size, cudaMemcpyDeviceToHost,
-                            fun->ctx->launch.stream));
+  GDTB_CUDA(cudaMemcpyAsync(vector, fun->d_vec, sizeof(double) * (size_t)(fun->row_end - fun->row_begin),
+                            cudaMemcpyDeviceToHost, fun->ctx->launch.stream));
   GDTB_CUDA(cudaStreamSynchronize(fun->ctx->launch.stream));
   return GDTB_OK;
 }
@@ -1095,11 +1270,26 @@ int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_en
 {
   if (!fun)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "functional is NULL");
+  GDTB_TRY(check_ctx(fun->ctx));
   const long long n_last = fun->grid.n[fun->grid.d - 1];
   if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
+  if (!q1_space(fun->space))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab-partitioned assembly is implemented for CG Q1 spaces");
+  if (!fun->owns_vec)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_set_slab must be called before lending a vector buffer");
   fun->grid.layer_lo = layer_begin;
   fun->grid.layer_hi = layer_end;
+  fun->slab = true;
+  q1_slab_ranges(fun->grid, layer_begin, layer_end, fun->row_lo, fun->row_hi, fun->elem_lo, fun->elem_hi);
+  fun->row_begin = fun->row_lo * q1_layer_rows(fun->grid);
+  fun->row_end = fun->row_hi * q1_layer_rows(fun->grid);
+  cudaFree(fun->d_vec);
+  fun->d_vec = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)(fun->row_end - fun->row_begin);
+  if (cudaMalloc(&fun->d_vec, bytes) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the vector of the slab");
+  GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, bytes, fun->ctx->launch.stream));
   return GDTB_OK;
 }
 
@@ -1144,10 +1334,14 @@ static int q1_rhs_params(gdtb_vecfun* fun, Q1GatherParams& p)
         host[2 * MAX_Q1D + 2 * q] = tab.phi[q][0];
         host[2 * MAX_Q1D + 2 * q + 1] = tab.phi[q][1];
       }
-      GDTB_CUDA(cudaMemcpyAsync(fun->d_rule, host, sizeof(host), cudaMemcpyHostToDevice, ctx->launch.stream));
-      GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream)); // `host` is a stack buffer
-      GDTB_TRY(launch_q1_rhs_tables(ctx->launch, g, to_dev(in.weight), tab.m, fun->d_rule, fun->d_rule + MAX_Q1D,
-                                    fun->d_rule + 2 * MAX_Q1D, fun->d_sep_tab, stride));
+      if (!fun->rule_uploaded || std::memcmp(host, fun->h_rule, sizeof(host)) != 0) {
+        std::memcpy(fun->h_rule, host, sizeof(host));
+        GDTB_CUDA(cudaMemcpyAsync(fun->d_rule, fun->h_rule, sizeof(host), cudaMemcpyHostToDevice, ctx->launch.stream));
+        GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+        fun->rule_uploaded = true;
+      }
+      GDTB_TRY(launch_q1_rhs_tables(ctx->launch, g, fun->elem_lo, fun->elem_hi, to_dev(in.weight), tab.m, fun->d_rule,
+                                    fun->d_rule + MAX_Q1D, fun->d_rule + 2 * MAX_Q1D, fun->d_sep_tab, stride));
       p.rhs_has_sep = 1;
       p.rhs_sep_scale = w * (in.weight.builtin == GDTB_BUILTIN_COS_PRODUCT ? in.weight.p[0] : 1.) * ie;
       p.rhs_sep_tab = fun->d_sep_tab;
@@ -1157,7 +1351,7 @@ static int q1_rhs_params(gdtb_vecfun* fun, Q1GatherParams& p)
   return GDTB_OK;
 }
 
-int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode)
+static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchronize)
 {
   if (!op && !fun)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_assemble: nothing to assemble");
@@ -1171,6 +1365,12 @@ int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode)
   const bool accumulate = mode == GDTB_ASSEMBLE_ACCUMULATE;
   const bool op_fast = op && matop_q1_eligible(op);
   const bool fun_fast = fun && vecfun_q1_eligible(fun);
+  if (op && !op_fast && (op->slab || !op->pattern))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED,
+                "slab-partitioned / pattern-free operators only support forms the CG Q1 row-gather kernel covers");
+  if (fun && !fun_fast && fun->slab)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED,
+                "slab-partitioned functionals only support sources the CG Q1 row-gather kernel covers");
 
   // --- CG-Q1 row-gather path: matrix and right-hand side in ONE pass over the vertices ---------
   if (op_fast || fun_fast) {
@@ -1186,7 +1386,6 @@ int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode)
     const gdtb_pattern* pat = op->pattern;
     if (!accumulate)
       GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pat->nnz, L.stream));
-    GDTB_CUDA(cudaMemsetAsync(ctx->d_error_flag, 0, sizeof(int), L.stream));
     for (const auto& lf : op->element_forms) {
       FormDev fd;
       GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_ELEMENT, fd));
@@ -1205,12 +1404,7 @@ int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode)
       GDTB_TRY(launch_boundary_matrix(L, op->grid, op->test, fd, pat->d_rowptr, pat->d_colidx, op->d_values,
                                       ctx->d_error_flag));
     }
-    int flag = 0;
-    GDTB_CUDA(cudaMemcpyAsync(&flag, ctx->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
-    GDTB_CUDA(cudaStreamSynchronize(L.stream));
-    if (flag)
-      return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH,
-                  "add_to_entry: a local entry is not part of the sparsity pattern (wrong stencil for the appended forms?)");
+    ctx->error_flag_pending = true;
   }
   if (fun && !fun_fast) {
     if (!accumulate)
@@ -1221,8 +1415,19 @@ int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode)
       GDTB_TRY(launch_element_vector(L, fun->grid, fun->space, fd, fun->d_vec));
     }
   }
-  GDTB_CUDA(cudaStreamSynchronize(L.stream));
+  if (synchronize)
+    return gdtb_ctx_synchronize(ctx);
   return GDTB_OK;
+}
+
+int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode)
+{
+  return assemble_impl(op, fun, mode, true);
+}
+
+int gdtb_assemble_async(gdtb_matop* op, gdtb_vecfun* fun, int mode)
+{
+  return assemble_impl(op, fun, mode, false);
 }
 
 int gdtb_assemble_host(gdtb_matop* op, gdtb_vecfun* fun, double* values, double* vector)

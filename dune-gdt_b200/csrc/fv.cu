@@ -11,6 +11,8 @@
 // HBM traffic: u in, L(u) out).  To stay bit-identical to the face-once walk, each face flux is evaluated with
 // the reference's roles (inside = the element with the smaller index, its outer normal) and the per-cell sum
 // runs in the order in which the walker would have touched the cell; FMA contraction is disabled explicitly.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.hpp"
 
@@ -269,12 +271,14 @@ int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
   const int block = 256;
   long long want = (owned + block - 1) / block;
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)L.sm_count * 16));
+  time_begin(L, KF_FV_APPLY);
   switch (g.d) {
     case 1: k_fv_apply<1><<<grid, block, 0, L.stream>>>(p, u, out); break;
     case 2: k_fv_apply<2><<<grid, block, 0, L.stream>>>(p, u, out); break;
     case 3: k_fv_apply<3><<<grid, block, 0, L.stream>>>(p, u, out); break;
     default: return fail(GDTB_ERR_INVALID_ARGUMENT, "fv: dimension must be 1, 2 or 3");
   }
+  time_end(L, KF_FV_APPLY);
   L.count++;
   GDTB_CUDA(cudaGetLastError());
   return GDTB_OK;

@@ -1,16 +1,58 @@
 // dune-gdt_b200/csrc/kernels.hpp -- host-callable launchers of the CUDA kernels (internal).
 #pragma once
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace gdtb {
+
+// kernel families for the optional per-kernel CUDA-event timing (gdtb_ctx_enable_timing)
+enum KernelFamily
+{
+  KF_Q1_GATHER = 0,
+  KF_FV_APPLY,
+  KF_ELEMENT_MATRIX,
+  KF_ELEMENT_VECTOR,
+  KF_COUPLING_MATRIX,
+  KF_BOUNDARY_MATRIX,
+  KF_COUNT
+};
+
+struct Timing
+{
+  bool enabled = false;
+  std::vector<cudaEvent_t> start[KF_COUNT], stop[KF_COUNT];
+};
 
 struct Launch
 {
   cudaStream_t stream;
   long long count; // kernels launched through this object
   int sm_count;
+  Timing* timing;
 };
+
+// CUDA events on the launching stream, directly around the kernel launch(es) of one family
+inline void time_begin(Launch& L, int family)
+{
+  if (L.timing && L.timing->enabled) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, L.stream);
+    L.timing->start[family].push_back(e);
+  }
+}
+
+inline void time_end(Launch& L, int family)
+{
+  if (L.timing && L.timing->enabled) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, L.stream);
+    L.timing->stop[family].push_back(e);
+  }
+}
 
 // ---- generic, quadrature-faithful kernels (assemble_generic.cu) -----------------------------------
 int launch_element_matrix(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, const long long* rowptr,
@@ -49,13 +91,18 @@ struct Q1GatherParams
   long long rhs_sep_stride;
   long long value_offset; // global CSR position of this process' first row (values points at it)
   long long row_offset;   // first vertex row of this process
+  // owner-computes-rows slab along the last direction: vertex layers [row_lo, row_hi) are produced here from the
+  // element layers [elem_lo, elem_hi) (the owned ones plus the ghost layer below)
+  long long row_lo, row_hi;
+  long long elem_lo, elem_hi;
 };
 
 int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate);
 
 // builds the separable right-hand-side tables B_k[i_k] for a product-separable built-in source
-int launch_q1_rhs_tables(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx, const double* qw,
-                         const double* phi /* [m][2] */, double* tab, long long stride);
+int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long long elem_hi, const FnDev& f, int m,
+                         const double* qx, const double* qw, const double* phi /* [m][2] */, double* tab,
+                         long long stride);
 
 // ---- sparsity pattern (pattern.cu) ----------------------------------------------------------------
 int pattern_sort_unique(Launch& L, const GridDev& g, const SpaceDev& test, const SpaceDev& ansatz, int stencil,

@@ -206,6 +206,12 @@ int gdtb_ctx_set_stream(gdtb_ctx* ctx, void* cuda_stream);
 int gdtb_ctx_synchronize(gdtb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t gdtb_ctx_launch_count(const gdtb_ctx* ctx);
+/* optional per-kernel timing: CUDA events on the launching stream directly around the launches of one kernel family
+ * ("q1_gather", "fv_apply", "element_matrix", "element_vector", "coupling_matrix", "boundary_matrix").
+ * gdtb_ctx_kernel_time synchronises, returns the summed device time and launch count since the last query and
+ * resets them. */
+int gdtb_ctx_enable_timing(gdtb_ctx* ctx, int enabled);
+int gdtb_ctx_kernel_time(gdtb_ctx* ctx, const char* family, double* total_ms, int64_t* launches);
 
 /* ---- grid / spaces -------------------------------------------------------------------------- */
 /* replaces XT::Grid::make_cube_grid + leaf_view (examples/stationary-heat-equation.cc:87-88) */
@@ -240,7 +246,8 @@ int gdtb_pattern_device(const gdtb_pattern* pattern, const int64_t** d_rowptr, c
 
 /* ---- MatrixOperator (operators/matrix-based.hh:245-508) -------------------------------------- */
 /* make_matrix_operator<M>(view, source_space, range_space, pattern) (matrix-based.hh:514-598):
- * rows = range/test space, cols = source/ansatz space. */
+ * rows = range/test space, cols = source/ansatz space.  `pattern` may be NULL for continuous Q1 spaces: their
+ * element stencil has a closed form, the values then follow the layout gdtb_pattern_create would produce. */
 int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* ansatz, const gdtb_pattern* pattern,
                       gdtb_matop** op);
 int gdtb_matop_destroy(gdtb_matop* op);
@@ -279,6 +286,9 @@ int gdtb_vecfun_set_device(gdtb_vecfun* fun, double* d_vector);
  * (matrix-based.hh:496-500, vector-based.hh:276-279, examples/stationary-heat-equation.cc:102-106):
  * one pass over the grid for everything appended to `op` and `fun` (either may be NULL). */
 int gdtb_assemble(gdtb_matop* op, gdtb_vecfun* fun, int mode);
+/* same, but only enqueues the kernels on the context's stream; errors detected on the device (entries outside the
+ * pattern) surface at the next gdtb_ctx_synchronize */
+int gdtb_assemble_async(gdtb_matop* op, gdtb_vecfun* fun, int mode);
 /* convenience for host-side callers: assemble (overwrite) and copy values / vector to host buffers (may be NULL) */
 int gdtb_assemble_host(gdtb_matop* op, gdtb_vecfun* fun, double* values, double* vector);
 
@@ -305,11 +315,16 @@ int64_t gdtb_fvop_ghost_layer_size(const gdtb_fvop* L);
 int gdtb_fv_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* d_u);
 
 /* ---- multi-GPU assembly ----------------------------------------------------------------------- */
-/* Restrict a matrix operator / functional to the element layers [begin, end) along the last direction
- * (element-block partition).  Rows touched by elements of other slabs hold partial sums that the caller
- * completes with the interface-row halo (see dune-gdt_b200/python/gdtb/distributed.py). */
+/* Element-block partition: this process owns the element layers [begin, end) along the last direction and, owner-
+ * computes-rows, the DoF rows of the vertex layers [begin, end) (the last slab also owns the top layer).  Owned
+ * rows are complete: the one ghost element layer below the slab is recomputed locally (what the reference does
+ * with YaspGrid's overlap), so assembly needs no communication; per-element coefficient arrays stay indexed by
+ * the global element index.  After this call the value / vector buffers hold the owned rows only
+ * (gdtb_matop_local_rows gives the global row range and the global CSR offset of the first owned value). */
 int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end);
 int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end);
+int64_t gdtb_matop_local_nnz(const gdtb_matop* op);
+int gdtb_matop_local_rows(const gdtb_matop* op, int64_t* row_begin, int64_t* row_end, int64_t* value_offset);
 
 #ifdef __cplusplus
 }
