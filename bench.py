@@ -214,7 +214,11 @@ def run_product(args):
     lib = gdt.capi.lib()
     check = gdt.capi.check
     ctx = gdt.Context(local_rank)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # the library launches on the stream bench.py times with torch CUDA events (a non-default torch stream: handle 0
+    # would mean "use the library's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
 
     # global grid: 256 x 256 x (256 * world), h = 2/256 everywhere; this rank owns element layers [rank*256, (rank+1)*256)
     h = 2.0 / NX

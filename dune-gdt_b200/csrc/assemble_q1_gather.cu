@@ -51,6 +51,11 @@ __device__ __forceinline__ void bulk_wait_read0()
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+__device__ __forceinline__ void bulk_wait_read1()
+{
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
 __device__ __forceinline__ void bulk_wait0()
 {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -69,165 +74,180 @@ struct P3
   static constexpr int value = D == 1 ? 3 : (D == 2 ? 9 : 27);
 };
 
+// stencil index of the column offset (dx, dy, dz) in {-1,0,1}^D: lexicographic in (dz, dy, dx) = CSR order
+template <int D>
+__device__ __forceinline__ constexpr int delta_index(int dx, int dy, int dz)
+{
+  return (dx + 1) + (D > 1 ? 3 * (dy + 1) : 0) + (D > 2 ? 9 * (dz + 1) : 0);
+}
+
 template <int D, bool ACCUMULATE>
 __global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values,
-                            double* __restrict__ rhs, int chunk, int nchunks, long long nitems)
+                            double* __restrict__ rhs, int chunk, int nchunks, long long nitems, int stage_doubles)
 {
-  constexpr int NO = 1 << D;        // elements around a vertex
-  constexpr int ND = P3<D>::value;  // stencil size
+  constexpr int NO = 1 << D;       // elements around a vertex
+  constexpr int ND = P3<D>::value; // stencil size
   extern __shared__ __align__(16) double smem[];
   const GridDev& g = p.g;
-  const int last = D - 1;
-  const long long Nx = g.n[0], Ny = D > 1 ? g.n[1] : 1, Nz = D > 2 ? g.n[2] : 1;
-  const long long Wx = 3 * Nx + 1, Wy = D > 1 ? 3 * Ny + 1 : 1;
-  // vertex rows handled by this process along the last axis: [row_lo, row_hi)
-  const long long lines_y = D == 3 ? Ny + 1 : (D == 2 ? p.row_hi - p.row_lo : 1);
+  const int Nx = (int)g.n[0], Ny = D > 1 ? (int)g.n[1] : 1, Nz = D > 2 ? (int)g.n[2] : 1;
+  const long long Wx = 3LL * Nx + 1, Wy = D > 1 ? 3LL * Ny + 1 : 1;
+  const int lines_y = D == 3 ? Ny + 1 : 1;
+  // element range along the last direction (owner-computes slab + ghost layer), vertex range in x
+  const int elo = (int)p.elem_lo, ehi = (int)p.elem_hi;
+  const int x_lo = D == 1 ? (int)p.row_lo : 0, x_hi = D == 1 ? (int)p.row_hi : Nx + 1;
+  int buf = 0;
 
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const long long line = item / nchunks;
+    // ---- per line (uniform over the CTA) ----------------------------------------------------------------
     const int ch = int(item % nchunks);
-    long long iv[3] = {0, 0, 0};
+    const long long line = item / nchunks;
+    int iy = 0, iz = 0;
     if (D == 3) {
-      iv[1] = line % lines_y;
-      iv[2] = p.row_lo + line / lines_y;
-    } else if (D == 2) {
-      iv[1] = p.row_lo + line;
+      iy = int(line % lines_y);
+      iz = int(p.row_lo + line / lines_y);
+    } else if (D == 2)
+      iy = int(p.row_lo + line);
+    const int x0 = x_lo + ch * chunk;
+    const int x1 = min(x0 + chunk, x_hi);
+    // element validity along y and z: e_k = i_k - 1 + o_k
+    bool vy[2] = {true, true}, vz[2] = {true, true};
+    if (D == 2) {
+      vy[0] = iy - 1 >= elo && iy - 1 < ehi;
+      vy[1] = iy >= elo && iy < ehi;
+    } else if (D == 3) {
+      vy[0] = iy >= 1;
+      vy[1] = iy < Ny;
+      vz[0] = iz - 1 >= elo && iz - 1 < ehi;
+      vz[1] = iz >= elo && iz < ehi;
     }
-    const long long x_lo = D == 1 ? p.row_lo : 0, x_hi = D == 1 ? p.row_hi : Nx + 1; // vertex range in x
-    const long long x0 = x_lo + (long long)ch * chunk;
-    const long long x1 = min(x0 + chunk, x_hi);
-
-    // stencil extents of this line in y and z
-    const int ny = D > 1 ? ((iv[1] == 0 || iv[1] == Ny) ? 2 : 3) : 1;
-    const int nz = D > 2 ? ((iv[2] == 0 || iv[2] == Nz) ? 2 : 3) : 1;
+    // columns that exist in y and z
+    const bool cy0 = D > 1 && iy > 0, cy1 = D > 1 && iy < Ny, cz0 = D > 2 && iz > 0, cz1 = D > 2 && iz < Nz;
+    const int ny = D > 1 ? 1 + cy0 + cy1 : 1, nz = D > 2 ? 1 + cz0 + cz1 : 1;
     const int c = ny * nz;
-    // global CSR position of the first entry of the chunk
+    const bool full_yz = (D < 2 || ny == 3) && (D < 3 || nz == 3);
+    const int Sx0 = x0 == 0 ? 0 : 3 * x0 - 1;
+    const int Sx1 = x1 > Nx ? 3 * Nx + 1 : 3 * x1 - 1;
     long long start;
     if (D == 3)
-      start = S_axis(iv[2], Nz) * Wy * Wx + nz * (S_axis(iv[1], Ny) * Wx + ny * S_axis(x0, Nx));
+      start = S_axis(iz, Nz) * Wy * Wx + (long long)nz * (S_axis(iy, Ny) * Wx + (long long)ny * Sx0);
     else if (D == 2)
-      start = S_axis(iv[1], Ny) * Wx + ny * S_axis(x0, Nx);
+      start = S_axis(iy, Ny) * Wx + (long long)ny * Sx0;
     else
-      start = S_axis(x0, Nx);
-    const long long seg = (long long)c * (S_axis(x1, Nx) - S_axis(x0, Nx));
+      start = Sx0;
     start -= p.value_offset;
+    const int seg = c * (Sx1 - Sx0);
     // keep the shared-memory and global 16-byte phases equal for the bulk copy
     const int phase = values ? int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL) : 0;
-    double* stage = smem + phase;
+    double* stage = smem + buf * stage_doubles + phase;
 
-    const long long ix = x0 + threadIdx.x;
+    // ---- per vertex ----------------------------------------------------------------------------------------
+    const int ix = x0 + (int)threadIdx.x;
     if (ix < x1) {
-      iv[0] = ix;
-      // element validity per axis and offset: e_k = i_k - 1 + o_k inside the grid and inside this process' layers
-      bool ok[3][2];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const long long elo = (k == last) ? p.elem_lo : 0;
-        const long long ehi = (k == last) ? p.elem_hi : (k < D ? g.n[k] : 1);
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          const long long e = iv[k] - 1 + o;
-          ok[k][o] = k < D ? (e >= elo && e < ehi) : (o == 1);
-        }
+      bool vx[2];
+      if (D == 1) {
+        vx[0] = ix - 1 >= elo && ix - 1 < ehi;
+        vx[1] = ix >= elo && ix < ehi;
+      } else {
+        vx[0] = ix >= 1;
+        vx[1] = ix < Nx;
       }
       double acc[ND];
 #pragma unroll
       for (int dlt = 0; dlt < ND; ++dlt)
         acc[dlt] = 0.;
       double b = 0.;
+      // element index of offset o = 0 (may be out of range; only dereferenced when valid)
+      const long long e0 = (long long)(ix - 1) + (long long)Nx * ((D > 1 ? iy - 1 : 0) + (long long)Ny * (D > 2 ? iz - 1 : 0));
 #pragma unroll
       for (int o = 0; o < NO; ++o) {
         const int ox = o & 1, oy = (o >> 1) & 1, oz = (o >> 2) & 1;
-        const bool valid = ok[0][ox] && (D < 2 || ok[1][oy]) && (D < 3 || ok[2][oz]);
-        const long long e = (ix - 1 + ox) + Nx * ((D > 1 ? iv[1] - 1 + oy : 0) + Ny * (D > 2 ? iv[2] - 1 + oz : 0));
-        if (p.has_const) {
-          const double m = valid ? 1. : 0.;
+        const bool valid = vx[ox] && vy[oy] && vz[oz];
+        if (valid) {
+          const long long e = e0 + ox + (long long)Nx * (oy + (long long)Ny * oz);
+          if (p.has_const) {
 #pragma unroll
-          for (int s = 0; s < NO; ++s) {
-            const int dx = ox - 1 + (s & 1), dy = D > 1 ? oy - 1 + ((s >> 1) & 1) : 0,
-                      dz = D > 2 ? oz - 1 + ((s >> 2) & 1) : 0;
-            const int dlt = (dx + 1) + (D > 1 ? 3 * (dy + 1) : 0) + (D > 2 ? 9 * (dz + 1) : 0);
-            acc[dlt] = fma(m, p.T_const[o][s], acc[dlt]);
+            for (int s = 0; s < NO; ++s)
+              acc[delta_index<D>(ox - 1 + (s & 1), oy - 1 + ((s >> 1) & 1), oz - 1 + ((s >> 2) & 1))] +=
+                  p.T_const[o][s];
           }
-        }
-        for (int chn = 0; chn < p.n_elem; ++chn) {
-          const double cf = valid ? __ldg(p.coef[chn] + e) : 0.;
+          for (int chn = 0; chn < p.n_elem; ++chn) {
+            const double cf = __ldg(p.coef[chn] + e);
 #pragma unroll
-          for (int s = 0; s < NO; ++s) {
-            const int dx = ox - 1 + (s & 1), dy = D > 1 ? oy - 1 + ((s >> 1) & 1) : 0,
-                      dz = D > 2 ? oz - 1 + ((s >> 2) & 1) : 0;
-            const int dlt = (dx + 1) + (D > 1 ? 3 * (dy + 1) : 0) + (D > 2 ? 9 * (dz + 1) : 0);
-            acc[dlt] = fma(cf, p.T_elem[chn][o][s], acc[dlt]);
+            for (int s = 0; s < NO; ++s) {
+              const int dlt = delta_index<D>(ox - 1 + (s & 1), oy - 1 + ((s >> 1) & 1), oz - 1 + ((s >> 2) & 1));
+              acc[dlt] = fma(cf, p.T_elem[chn][o][s], acc[dlt]);
+            }
           }
-        }
-        if (p.has_rhs) {
-          if (p.rhs_has_const && valid)
+          if (p.rhs_has_const)
             b += p.rhs_const;
-          if (p.rhs_has_elem && valid)
+          if (p.rhs_has_elem)
             b = fma(p.rhs_elem_scale, __ldg(p.rhs_elem + e), b);
         }
       }
       // rows in CSR order: (dz, dy, dx) ascending over the columns that exist
       if (values) {
-        const int nx = (ix == 0 || ix == Nx) ? 2 : 3;
-        int pos = int((long long)c * (S_axis(ix, Nx) - S_axis(x0, Nx)));
+        const int Sx = ix == 0 ? 0 : 3 * ix - 1;
+        double* row = stage + c * (Sx - Sx0);
+        if (full_yz && vx[0] && vx[1] && D > 1) {
 #pragma unroll
-        for (int dz = -1; dz <= 1; ++dz) {
-          if (D < 3 && dz != 0)
-            continue;
-          if (D == 3 && (iv[2] + dz < 0 || iv[2] + dz > Nz))
-            continue;
+          for (int k = 0; k < ND; ++k)
+            row[k] = acc[k];
+        } else {
+          int pos = 0;
 #pragma unroll
-          for (int dy = -1; dy <= 1; ++dy) {
-            if (D < 2 && dy != 0)
-              continue;
-            if (D >= 2 && (iv[1] + dy < 0 || iv[1] + dy > Ny))
+          for (int dz = -1; dz <= 1; ++dz) {
+            if (D < 3 ? dz != 0 : (dz < 0 ? !cz0 : (dz > 0 ? !cz1 : false)))
               continue;
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-              if (ix + dx < 0 || ix + dx > Nx)
+            for (int dy = -1; dy <= 1; ++dy) {
+              if (D < 2 ? dy != 0 : (dy < 0 ? !cy0 : (dy > 0 ? !cy1 : false)))
                 continue;
-              const int dlt = (dx + 1) + (D > 1 ? 3 * (dy + 1) : 0) + (D > 2 ? 9 * (dz + 1) : 0);
-              stage[pos++] = acc[dlt];
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx) {
+                if (dx < 0 ? ix == 0 : (dx > 0 ? ix == Nx : false))
+                  continue;
+                row[pos++] = acc[delta_index<D>(dx, dy, dz)];
+              }
             }
           }
         }
-        (void)nx;
       }
       if (p.has_rhs && rhs) {
         if (p.rhs_has_sep) {
-          double t = p.rhs_sep_scale;
-#pragma unroll
-          for (int k = 0; k < D; ++k)
-            t *= __ldg(p.rhs_sep_tab + k * p.rhs_sep_stride + iv[k]);
+          double t = p.rhs_sep_scale * __ldg(p.rhs_sep_tab + ix);
+          if (D > 1)
+            t *= __ldg(p.rhs_sep_tab + p.rhs_sep_stride + iy);
+          if (D > 2)
+            t *= __ldg(p.rhs_sep_tab + 2 * p.rhs_sep_stride + iz);
           b += t;
         }
-        long long row = ix;
+        long long r = ix;
         if (D > 1)
-          row += (Nx + 1) * iv[1];
+          r += (long long)(Nx + 1) * iy;
         if (D > 2)
-          row += (Nx + 1) * (Ny + 1) * iv[2];
-        row -= p.row_offset;
+          r += (long long)(Nx + 1) * (Ny + 1) * iz;
+        r -= p.row_offset;
         if (ACCUMULATE)
-          rhs[row] += b;
+          rhs[r] += b;
         else
-          rhs[row] = b;
+          rhs[r] = b;
       }
     }
 
     if (values) {
       if (ACCUMULATE) {
         __syncthreads();
-        for (long long i = threadIdx.x; i < seg; i += blockDim.x)
+        for (int i = threadIdx.x; i < seg; i += blockDim.x)
           values[start + i] += stage[i];
         __syncthreads();
       } else {
+        // double-buffered TMA bulk store: the store of this line drains while the next line is computed
         fence_proxy_async_smem();
         __syncthreads();
         if (threadIdx.x == 0) {
           // 16-byte aligned middle part by one bulk copy, at most one odd double at either end by plain stores
-          long long head = phase; // start odd -> first double is not 16B aligned
-          long long body = (seg - head) & ~1LL;
+          const int head = phase;
+          const int body = (seg - head) & ~1;
           if (head)
             values[start] = stage[0];
           if (body > 0)
@@ -235,9 +255,10 @@ __global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __
           if (head + body < seg)
             values[start + head + body] = stage[head + body];
           bulk_commit();
-          bulk_wait_read0();
+          bulk_wait_read1(); // the buffer written two lines ago is free again
         }
         __syncthreads();
+        buf ^= 1;
       }
     }
   }
@@ -312,9 +333,12 @@ static int launch_q1_gather_d(Launch& L, const Q1GatherParams& p, double* values
   else if (D == 2)
     nlines = p.row_hi - p.row_lo;
   const long long nitems = nlines * nchunks;
-  const size_t smem = values ? (size_t)(chunk * P3<D>::value + 2) * sizeof(double) : 16;
+  // two stage buffers (double-buffered bulk store), each padded for the 16-byte phase shift
+  const int stage_doubles = ((chunk * P3<D>::value + 2) + 1) & ~1;
+  const size_t smem = values ? (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double) : 16;
   auto kern = accumulate ? k_q1_gather<D, true> : k_q1_gather<D, false>;
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
   GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1)
@@ -323,7 +347,7 @@ static int launch_q1_gather_d(Launch& L, const Q1GatherParams& p, double* values
   if (grid > nitems)
     grid = nitems;
   time_begin(L, KF_Q1_GATHER);
-  kern<<<(unsigned)grid, threads, smem, L.stream>>>(p, values, rhs, chunk, nchunks, nitems);
+  kern<<<(unsigned)grid, threads, smem, L.stream>>>(p, values, rhs, chunk, nchunks, nitems, stage_doubles);
   time_end(L, KF_Q1_GATHER);
   L.count++;
   GDTB_CUDA(cudaGetLastError());

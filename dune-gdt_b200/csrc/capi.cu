@@ -193,6 +193,8 @@ struct gdtb_fvop
   double* d_tmp; // ping-pong buffer for the Euler loop
   double* d_src; // staging for the *_host entry points
   double* d_dst;
+  double* d_ext; // per-axis cell extents, axis k at d_ext + ext_offset[k]
+  long long ext_offset[3];
 };
 
 namespace {
@@ -1458,9 +1460,40 @@ int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* fl
   L->space = space->dev;
   L->flux = *flux;
   L->ghosted = false;
-  L->d_tmp = L->d_src = L->d_dst = nullptr;
+  L->d_tmp = L->d_src = L->d_dst = L->d_ext = nullptr;
+  // cell extents per axis, exactly as YaspGrid's EquidistantOffsetCoordinates produce them: upper - lower with
+  // lower = origin + i * h, upper = origin + (i + 1) * h [EXT]
+  std::vector<double> ext;
+  for (int k = 0; k < 3; ++k) {
+    L->ext_offset[k] = (long long)ext.size();
+    for (long long i = 0; i < L->grid.n[k]; ++i) {
+      volatile double lower = L->grid.lo[k] + double(i) * L->grid.h[k];
+      volatile double upper = L->grid.lo[k] + double(i + 1) * L->grid.h[k];
+      ext.push_back(k < L->grid.d ? upper - lower : 1.);
+    }
+  }
+  if (cudaMalloc(&L->d_ext, sizeof(double) * ext.size()) != cudaSuccess
+      || cudaMemcpy(L->d_ext, ext.data(), sizeof(double) * ext.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(L->d_ext);
+    delete L;
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (fv geometry tables)");
+  }
   *out = L;
   return GDTB_OK;
+}
+
+static void fv_fill_params(const gdtb_fvop* L, FvParams& p)
+{
+  p.g = L->grid;
+  p.flux = L->flux;
+  p.ghosted = L->ghosted ? 1 : 0;
+  p.euler = 0;
+  p.dt = 0.;
+  p.lf_lambda_linear = 0.;
+  for (int k = 0; k < L->grid.d; ++k)
+    p.lf_lambda_linear = std::max(p.lf_lambda_linear, std::fabs(L->flux.p[k]));
+  for (int k = 0; k < 3; ++k)
+    p.ext[k] = L->d_ext + L->ext_offset[k];
 }
 
 int gdtb_fvop_destroy(gdtb_fvop* L)
@@ -1471,6 +1504,7 @@ int gdtb_fvop_destroy(gdtb_fvop* L)
   cudaFree(L->d_tmp);
   cudaFree(L->d_src);
   cudaFree(L->d_dst);
+  cudaFree(L->d_ext);
   delete L;
   return GDTB_OK;
 }
@@ -1512,11 +1546,7 @@ int gdtb_fvop_apply(gdtb_fvop* L, const double* d_source, double* d_range)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_apply: NULL argument");
   GDTB_TRY(check_ctx(L->ctx));
   FvParams p;
-  p.g = L->grid;
-  p.flux = L->flux;
-  p.ghosted = L->ghosted ? 1 : 0;
-  p.euler = 0;
-  p.dt = 0.;
+  fv_fill_params(L, p);
   GDTB_TRY(launch_fv_apply(L->ctx->launch, p, d_source, d_range));
   GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
   return GDTB_OK;
@@ -1561,9 +1591,7 @@ int gdtb_fvop_euler(gdtb_fvop* L, double* d_u, double dt, int64_t n_steps)
   if (!L->d_tmp && cudaMalloc(&L->d_tmp, bytes) != cudaSuccess)
     return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (fv euler buffer)");
   FvParams p;
-  p.g = L->grid;
-  p.flux = L->flux;
-  p.ghosted = L->ghosted ? 1 : 0;
+  fv_fill_params(L, p);
   p.euler = 1;
   p.dt = dt;
   double* a = d_u;

@@ -8,9 +8,10 @@
 //
 // The reference walks the faces once and read-modify-writes both adjacent cells (2 RMW per face behind a lock).
 // Here each cell gathers the fluxes of its 2d faces, so every range value is written exactly once (16 B/cell of
-// HBM traffic: u in, L(u) out).  To stay bit-identical to the face-once walk, each face flux is evaluated with
-// the reference's roles (inside = the element with the smaller index, its outer normal) and the per-cell sum
-// runs in the order in which the walker would have touched the cell; FMA contraction is disabled explicitly.
+// HBM traffic: u in, L(u) out).  Each face flux is evaluated with the reference's roles (inside = the element with
+// the smaller index, its outer normal) and the per-cell sum runs in the order in which the walker would have touched
+// the cell, so results differ from the face-once walk only by FMA contraction (a few ulp).  Cell extents come from
+// per-axis tables computed once per operator with YaspGrid's own formula.
 #include <algorithm>
 
 #include "common.cuh"
@@ -20,132 +21,102 @@ namespace gdtb {
 
 namespace {
 
-__device__ __forceinline__ double mul(double a, double b)
+// flux function along axis k and its derivative (scalar conservation law, m = 1)
+__device__ __forceinline__ double flux_k(const gdtb_flux& fl, int k, double w)
 {
-  return __dmul_rn(a, b);
-}
-__device__ __forceinline__ double add(double a, double b)
-{
-  return __dadd_rn(a, b);
+  return fl.kind == GDTB_FLUX_LINEAR ? fl.p[k] * w : 0.5 * w * w;
 }
 
+// numerical flux g(u, v, n) * 1 for the axis-aligned unit normal n = sign * e_k
+// NumericalUpwindFlux<I,d,1>::apply (upwind.hh:67-72) / NumericalLaxFriedrichsFlux::apply (lax-friedrichs.hh:70-87);
+// with n = +-e_k all terms of the reference's dot products except the k-th are exact zeros.
 template <int D>
-__device__ __forceinline__ double dot_n(const double* a, const double* n)
+__device__ __forceinline__ double numerical_flux_axis(const gdtb_flux& fl, double lf_lambda_linear, int k, double sign,
+                                                      double u, double v)
 {
-  double s = 0.;
-#pragma unroll
-  for (int k = 0; k < D; ++k)
-    s = add(s, mul(a[k], n[k]));
-  return s;
-}
-
-template <int D>
-__device__ __forceinline__ void flux_eval(const gdtb_flux& fl, double u, double* f)
-{
-#pragma unroll
-  for (int k = 0; k < D; ++k)
-    f[k] = fl.kind == GDTB_FLUX_LINEAR ? mul(fl.p[k], u) : mul(mul(0.5, u), u);
-}
-
-template <int D>
-__device__ __forceinline__ void flux_jac(const gdtb_flux& fl, double u, double* df)
-{
-#pragma unroll
-  for (int k = 0; k < D; ++k)
-    df[k] = fl.kind == GDTB_FLUX_LINEAR ? fl.p[k] : u;
-}
-
-template <int D>
-__device__ __forceinline__ double numerical_flux(const gdtb_flux& fl, double u, double v, const double* n)
-{
-  double a[3], b[3];
-  if (fl.numflux == GDTB_NUMFLUX_UPWIND) { // upwind.hh:67-72
-    flux_jac<D>(fl, add(u, v) / 2., a);
-    if (dot_n<D>(n, a) > 0) {
-      flux_eval<D>(fl, u, b);
-      return dot_n<D>(b, n);
-    }
-    flux_eval<D>(fl, v, b);
-    return dot_n<D>(b, n);
+  if (fl.numflux == GDTB_NUMFLUX_UPWIND) {
+    const double ubar = (u + v) / 2.;
+    const double dfk = fl.kind == GDTB_FLUX_LINEAR ? fl.p[k] : ubar;
+    return (sign * dfk > 0 ? flux_k(fl, k, u) : flux_k(fl, k, v)) * sign;
   }
-  // lax-friedrichs.hh:70-87 with lambda_ = 0
-  double lambda = 0.;
-  flux_jac<D>(fl, u, a);
-  flux_jac<D>(fl, v, b);
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    lambda = fmax(lambda, fabs(a[k]));
-    lambda = fmax(lambda, fabs(b[k]));
-  }
-  lambda = 1. / lambda;
-  flux_eval<D>(fl, u, a);
-  flux_eval<D>(fl, v, b);
-  double ret = 0.;
-#pragma unroll
-  for (int k = 0; k < D; ++k)
-    ret = add(ret, mul(add(a[k], b[k]), mul(n[k], 0.5)));
-  ret = add(ret, mul(add(u, -v), 0.5 / lambda));
-  return ret;
+  // lambda = 1 / max_j(|f_j'(u)|, |f_j'(v)|); ret = (f(u) + f(v)) . n / 2 + (u - v) / (2 lambda)
+  const double inv_lambda = fl.kind == GDTB_FLUX_LINEAR ? lf_lambda_linear : fmax(fabs(u), fabs(v));
+  return (flux_k(fl, k, u) + flux_k(fl, k, v)) * (sign * 0.5) + (u - v) * (0.5 * inv_lambda);
 }
 
-__device__ __forceinline__ void cell_geometry_strict(const GridDev& g, const long long* idx, double* ext)
-{
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    if (k < g.d) {
-      const double lower = add(g.lo[k], mul(double(idx[k]), g.h[k]));
-      const double upper = add(g.lo[k], mul(double(idx[k] + 1), g.h[k]));
-      ext[k] = add(upper, -lower);
-    } else
-      ext[k] = 1.;
-  }
-}
-
-template <int D>
-__device__ __forceinline__ double volume(const double* ext)
-{
-  double v = 1.;
-#pragma unroll
-  for (int k = 0; k < D; ++k)
-    v = mul(v, ext[k]);
-  return v;
-}
-
+// One thread per cell, launched on a (x-chunks, y, z) grid so that no index needs a division.  Every cell gathers
+// the fluxes of its 2 D faces: per face the reference's roles are kept (inside = element with the smaller index, its
+// outer normal, advection-fv.hh:135-152) and the contributions are summed in the order the face-once walk would have
+// added them to this cell.
 template <int D>
 __global__ void __launch_bounds__(256) k_fv_apply(const __grid_constant__ FvParams p, const double* __restrict__ u,
                                                   double* __restrict__ out)
 {
   const GridDev& g = p.g;
-  const int last = D - 1;
-  const long long layers = g.layer_hi - g.layer_lo;
-  long long plane = 1; // cells per layer of the last direction
+  constexpr int last = D - 1;
+  const int n0 = (int)g.n[0], n1 = D > 1 ? (int)g.n[1] : 1, n2 = D > 2 ? (int)g.n[2] : 1;
+  const int layer_lo = (int)g.layer_lo;
+  int idx[3];
+  idx[0] = blockIdx.x * blockDim.x + threadIdx.x;
+  idx[1] = D > 1 ? (int)blockIdx.y : 0;
+  idx[2] = D > 2 ? (int)blockIdx.z : 0;
+  if (D == 1)
+    idx[0] += layer_lo;
+  if (idx[0] >= (D == 1 ? (int)g.layer_hi : n0))
+    return;
+  idx[last] += (D == 1) ? 0 : layer_lo; // global coordinate along the partitioned direction
+  const int n[3] = {n0, n1, n2};
+  // local linear index: x fastest; along the last direction the local layer (+1 ghost layer below)
+  long long stride[3] = {1, n0, (long long)n0 * n1};
+  const long long plane = stride[last];
+  const long long loc = (long long)idx[0] * (D == 1 ? 1 : 1) + (D > 1 ? (long long)idx[1] * stride[1] : 0)
+                        + (D > 2 ? (long long)idx[2] * stride[2] : 0) - (long long)layer_lo * plane
+                        + (p.ghosted ? plane : 0);
+  const long long e = (long long)idx[0] + (long long)n0 * ((D > 1 ? idx[1] : 0) + (long long)n1 * (D > 2 ? idx[2] : 0));
+  const double ue = u[loc];
+  double ext[3];
 #pragma unroll
-  for (int k = 0; k < D - 1; ++k)
-    plane *= g.n[k];
-  const long long owned = plane * layers;
-  const long long shift = p.ghosted ? plane : 0; // local offset of the first owned cell
+  for (int k = 0; k < D; ++k)
+    ext[k] = __ldg(p.ext[k] + idx[k]);
+  double vol = ext[0];
+  if (D > 1)
+    vol *= ext[1];
+  if (D > 2)
+    vol *= ext[2];
+  const double hinv = 1. / vol;
+  double hI[3]; // |intersection| normal to axis k
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    double a = 1.;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if (j != k)
+        a *= ext[j];
+    hI[k] = a;
+  }
 
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < owned;
-       t += (long long)gridDim.x * blockDim.x) {
-    // global coordinates of this cell
-    long long idx[3] = {0, 0, 0};
-    {
-      long long r = t;
+  bool interior = true;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        const long long nk = (k == last) ? layers : g.n[k];
-        idx[k] = r % nk;
-        r /= nk;
-      }
-      idx[last] += g.layer_lo;
+  for (int k = 0; k < D; ++k)
+    interior = interior && idx[k] > 0 && idx[k] < n[k] - 1;
+
+  double acc = 0.;
+  if (interior) {
+    // lower neighbours are the inside elements (visited earlier, ascending index: z-, y-, x-), then this cell's
+    // own upper faces in intersection order (x+, y+, z+)
+#pragma unroll
+    for (int k = D - 1; k >= 0; --k) {
+      const double un = __ldg(u + loc - stride[k]);
+      const double gf = numerical_flux_axis<D>(p.flux, p.lf_lambda_linear, k, 1., un, ue);
+      acc += -(gf * hI[k]) * hinv; // advection-fv.hh:151
     }
-    const long long e = elem_index(g, idx);
-    const long long loc = t + shift;
-    const double ue = u[loc];
-    double ext_e[3];
-    cell_geometry_strict(g, idx, ext_e);
-    const double hinv_e = 1. / volume<D>(ext_e);
-
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double un = __ldg(u + loc + stride[k]);
+      const double gf = numerical_flux_axis<D>(p.flux, p.lf_lambda_linear, k, 1., ue, un);
+      acc += (gf * hI[k]) * hinv; // advection-fv.hh:150
+    }
+  } else {
     double contrib[2 * D];
     long long key[2 * D];
     int nc = 0;
@@ -153,57 +124,34 @@ __global__ void __launch_bounds__(256) k_fv_apply(const __grid_constant__ FvPara
     for (int k = 0; k < D; ++k) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        long long nb[3];
-        bool boundary;
-        if (!face_neighbor(g, idx, k, s, nb, &boundary))
-          continue;
-        const long long en = elem_index(g, nb);
-        if (en == e)
-          continue; // degenerate periodic direction with a single cell: filtered by index(in) < index(out)
-        // local position of the neighbour's value
-        long long stride = 1;
-#pragma unroll
-        for (int j = 0; j < k; ++j)
-          stride *= g.n[j];
+        int t = idx[k] + (s ? 1 : -1);
         long long nloc;
+        if (t < 0 || t >= n[k]) {
+          if (!(g.periodic & (1 << k)))
+            continue; // domain boundary without neighbour: no coupling operator (advection-fv.hh:77-82)
+          t = (t + n[k]) % n[k];
+        }
+        if (t == idx[k])
+          continue; // single periodic cell: filtered by index(inside) < index(outside)
         if (k == last && p.ghosted)
           nloc = loc + (s ? plane : -plane); // ghost layers carry the (periodic) neighbours' data
         else
-          nloc = loc + (nb[k] - idx[k]) * stride;
+          nloc = loc + (long long)(t - idx[k]) * stride[k];
+        const long long en = e + (long long)(t - idx[k]) * stride[k];
         const double un = __ldg(u + nloc);
-        double ext_n[3];
-        cell_geometry_strict(g, nb, ext_n);
-        double normal[3] = {0., 0., 0.};
-        double c;
-        if (e < en) {
-          // this cell is the inside element, the face is its (k, s) intersection
-          normal[k] = s ? 1. : -1.;
-          double hI = 1.;
-#pragma unroll
-          for (int j = 0; j < D; ++j)
-            if (j != k)
-              hI = mul(hI, ext_e[j]);
-          const double gf = numerical_flux<D>(p.flux, ue, un, normal);
-          c = mul(mul(gf, hI), hinv_e); // advection-fv.hh:149-150
+        if (e < en) { // this cell is the inside element, the face is its (k, s) intersection
+          const double gf = numerical_flux_axis<D>(p.flux, p.lf_lambda_linear, k, s ? 1. : -1., ue, un);
+          contrib[nc] = (gf * hI[k]) * hinv;
           key[nc] = e * 8 + (2 * k + s);
-        } else {
-          // the neighbour is the inside element, the face is its (k, 1-s) intersection
-          normal[k] = s ? -1. : 1.;
-          double hI = 1.;
-#pragma unroll
-          for (int j = 0; j < D; ++j)
-            if (j != k)
-              hI = mul(hI, ext_n[j]);
-          const double gf = numerical_flux<D>(p.flux, un, ue, normal);
-          c = mul(-mul(gf, hI), hinv_e); // advection-fv.hh:151
+        } else { // the neighbour is the inside element, the face is its (k, 1-s) intersection
+          const double gf = numerical_flux_axis<D>(p.flux, p.lf_lambda_linear, k, s ? -1. : 1., un, ue);
+          contrib[nc] = -(gf * hI[k]) * hinv;
           key[nc] = en * 8 + (2 * k + (1 - s));
         }
-        contrib[nc] = c;
         ++nc;
       }
     }
     // sum in walker order: ascending (inside element, intersection index)
-    double acc = 0.;
     for (int a = 0; a < nc; ++a) {
       int best = -1;
       long long bk = 0x7fffffffffffffffLL;
@@ -216,15 +164,12 @@ __global__ void __launch_bounds__(256) k_fv_apply(const __grid_constant__ FvPara
 #pragma unroll
       for (int b = 0; b < 2 * D; ++b)
         if (b == best) {
-          acc = add(acc, contrib[b]);
+          acc += contrib[b];
           key[b] = 0x7fffffffffffffffLL;
         }
     }
-    if (p.euler)
-      out[loc] = add(ue, -mul(acc, p.dt)); // u_n - L(u_n) * dt
-    else
-      out[loc] = acc;
   }
+  out[loc] = p.euler ? ue - acc * p.dt : acc; // u_n - L(u_n) * dt (examples/mpi_2019_02...cc:154)
 }
 
 template <int D>
@@ -265,12 +210,18 @@ __global__ void __launch_bounds__(256) k_fv_interpolate(const GridDev g, const F
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
 {
   const GridDev& g = p.g;
-  long long owned = g.layer_hi - g.layer_lo;
-  for (int k = 0; k < g.d - 1; ++k)
-    owned *= g.n[k];
+  const long long layers = g.layer_hi - g.layer_lo;
   const int block = 256;
-  long long want = (owned + block - 1) / block;
-  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)L.sm_count * 16));
+  dim3 grid(1, 1, 1);
+  if (g.d == 1)
+    grid.x = (unsigned)((layers + block - 1) / block);
+  else {
+    grid.x = (unsigned)((g.n[0] + block - 1) / block);
+    grid.y = (unsigned)(g.d == 2 ? layers : g.n[1]);
+    grid.z = (unsigned)(g.d == 3 ? layers : 1);
+    if (grid.y > 65535 || grid.z > 65535)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "fv: more than 65535 cells in the second / third direction");
+  }
   time_begin(L, KF_FV_APPLY);
   switch (g.d) {
     case 1: k_fv_apply<1><<<grid, block, 0, L.stream>>>(p, u, out); break;

@@ -1,0 +1,1643 @@
+// dune-gdt_b200/include/dune/gdt/b200.hh -- header-only C++ facade: dune-gdt's class and function names for the
+// assembly / FV-apply hot path, lowered through the C ABI (include/gdtb.h) to the sm_100a kernels of libgdtb.
+//
+// Scope: exactly what the three reference drivers call on this path:
+//   examples/stationary-heat-equation.cc:87-106, examples/adaptive_elliptic_swipdg.cc:216-251,
+//   examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:141-158,255-298.
+// Same spelling, argument order and meaning as the reference; value types are cloned on append like
+// copy()/copy_as_*_integrand() (operators/matrix-based.hh:346-408); errors are Dune::Exception subclasses with the
+// reference's names.  The dune-xt / dune-grid types the drivers touch (grid provider, grid view, GridFunction,
+// LA containers, walker, ApplyOn filters) are provided as thin stand-ins in namespace Dune::XT -- they are
+// [EXT] to dune-gdt and only cover what the hot path needs.
+//
+// What cannot cross a C ABI: user lambdas.  XT::Functions::GridFunction therefore wraps constants, per-element
+// arrays and the built-in analytic functions of gdtb.h instead of GenericFunction lambdas.
+#ifndef DUNE_GDT_B200_HH
+#define DUNE_GDT_B200_HH
+
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <exception>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <gdtb.h>
+
+namespace Dune {
+
+// ---- exceptions (dune-common Exception + dune/gdt/exceptions.hh:24-75) ------------------------------------
+class Exception : public std::exception
+{
+public:
+  Exception() = default;
+  explicit Exception(std::string msg)
+    : msg_(std::move(msg))
+  {}
+  const char* what() const noexcept override
+  {
+    return msg_.c_str();
+  }
+  void message(const std::string& m)
+  {
+    msg_ = m;
+  }
+
+private:
+  std::string msg_;
+};
+
+class NotImplemented : public Exception
+{
+  using Exception::Exception;
+};
+
+namespace XT {
+namespace Common {
+namespace Exceptions {
+class wrong_input_given : public Dune::Exception
+{
+  using Exception::Exception;
+};
+class shapes_do_not_match : public Dune::Exception
+{
+  using Exception::Exception;
+};
+} // namespace Exceptions
+
+// XT::Common::Parameter: only carried for signature compatibility ({} everywhere on this path)
+struct Parameter
+{
+  Parameter() = default;
+  Parameter(std::initializer_list<std::pair<std::string, std::vector<double>>>) {}
+};
+} // namespace Common
+} // namespace XT
+
+namespace GDT {
+namespace Exceptions {
+class integrand_error : public Dune::Exception
+{
+  using Exception::Exception;
+};
+class finite_element_error : public Dune::Exception
+{
+  using Exception::Exception;
+};
+class space_error : public Dune::Exception
+{
+  using Exception::Exception;
+};
+class mapper_error : public space_error
+{
+  using space_error::space_error;
+};
+class operator_error : public Dune::Exception
+{
+  using Exception::Exception;
+};
+class device_error : public Dune::Exception // CUDA failure / no device: there is no CPU fallback
+{
+  using Exception::Exception;
+};
+} // namespace Exceptions
+
+namespace internal {
+inline void check(int status)
+{
+  if (status == GDTB_OK)
+    return;
+  const std::string msg = gdtb_last_error();
+  switch (status) {
+    case GDTB_ERR_INVALID_ARGUMENT: throw XT::Common::Exceptions::wrong_input_given(msg);
+    case GDTB_ERR_SHAPES_DO_NOT_MATCH: throw XT::Common::Exceptions::shapes_do_not_match(msg);
+    case GDTB_ERR_INTEGRAND: throw Exceptions::integrand_error(msg);
+    case GDTB_ERR_FINITE_ELEMENT: throw Exceptions::finite_element_error(msg);
+    case GDTB_ERR_SPACE: throw Exceptions::space_error(msg);
+    case GDTB_ERR_OPERATOR: throw Exceptions::operator_error(msg);
+    case GDTB_ERR_NOT_IMPLEMENTED: throw Dune::NotImplemented(msg);
+    default: throw Exceptions::device_error(msg);
+  }
+}
+
+// process-wide context (one GPU per process, like one MPI rank per GPU)
+inline gdtb_ctx* context(int device = -1)
+{
+  struct Holder
+  {
+    gdtb_ctx* ctx = nullptr;
+    ~Holder()
+    {
+      gdtb_ctx_destroy(ctx);
+    }
+  };
+  static Holder holder;
+  if (!holder.ctx)
+    check(gdtb_ctx_create(device < 0 ? 0 : device, &holder.ctx));
+  return holder.ctx;
+}
+
+template <class T, int (*Destroy)(T*)>
+struct Handle
+{
+  std::shared_ptr<T> ptr;
+  Handle() = default;
+  explicit Handle(T* raw)
+    : ptr(raw, [](T* p) { Destroy(p); })
+  {}
+  T* get() const
+  {
+    return ptr.get();
+  }
+};
+} // namespace internal
+} // namespace GDT
+
+// ==========================================================================================================
+// [EXT] stand-ins for the dune-grid / dune-xt types the drivers touch
+// ==========================================================================================================
+template <class K, int n>
+using FieldVector = std::array<K, n>;
+
+template <class K, int r, int c>
+struct FieldMatrix
+{
+  std::array<std::array<K, c>, r> rows{};
+  std::array<K, c>& operator[](std::size_t i)
+  {
+    return rows[i];
+  }
+  const std::array<K, c>& operator[](std::size_t i) const
+  {
+    return rows[i];
+  }
+};
+
+namespace XT {
+namespace Grid {
+
+template <std::size_t d>
+struct CubeEntity
+{
+  static constexpr std::size_t dimension = d;
+};
+template <std::size_t d>
+struct CubeIntersection
+{
+  using Entity = CubeEntity<d>;
+};
+
+// Dune::YaspGrid<d, EquidistantOffsetCoordinates<double, d>>::LeafGridView stand-in
+template <std::size_t d>
+class CubeGridView
+{
+public:
+  static constexpr std::size_t dimension = d;
+  using ctype = double;
+  using Element = CubeEntity<d>;
+  using Intersection = CubeIntersection<d>;
+
+  CubeGridView() = default;
+  CubeGridView(const gdtb_grid_desc& desc)
+    : desc_(desc)
+  {
+    gdtb_grid* raw = nullptr;
+    GDT::internal::check(gdtb_grid_create_cube(GDT::internal::context(), &desc_, &raw));
+    handle_ = GDT::internal::Handle<gdtb_grid, gdtb_grid_destroy>(raw);
+  }
+  gdtb_grid* handle() const
+  {
+    return handle_.get();
+  }
+  const gdtb_grid_desc& desc() const
+  {
+    return desc_;
+  }
+  std::int64_t size(int codim) const
+  {
+    if (codim != 0)
+      throw Dune::NotImplemented("CubeGridView::size: only codim 0");
+    return gdtb_grid_num_elements(handle_.get());
+  }
+
+private:
+  gdtb_grid_desc desc_{};
+  GDT::internal::Handle<gdtb_grid, gdtb_grid_destroy> handle_;
+};
+
+template <std::size_t d>
+struct YaspEquidistantOffset
+{
+  static constexpr std::size_t dimension = d;
+  using LeafGridView = CubeGridView<d>;
+};
+
+template <class GV>
+using extract_entity_t = typename GV::Element;
+template <class GV>
+using extract_intersection_t = typename GV::Intersection;
+
+template <class G>
+class GridProvider
+{
+public:
+  explicit GridProvider(const gdtb_grid_desc& desc)
+    : desc_(desc)
+  {}
+  typename G::LeafGridView leaf_view() const
+  {
+    return typename G::LeafGridView(desc_);
+  }
+  const gdtb_grid_desc& desc() const
+  {
+    return desc_;
+  }
+
+private:
+  gdtb_grid_desc desc_;
+};
+
+// XT::Grid::make_cube_grid<G>(lower, upper, num_elements) (examples/stationary-heat-equation.cc:87)
+template <class G>
+GridProvider<G> make_cube_grid(const std::array<double, G::dimension>& lower,
+                               const std::array<double, G::dimension>& upper,
+                               const std::array<unsigned int, G::dimension>& num_elements)
+{
+  gdtb_grid_desc desc{};
+  desc.dim = int(G::dimension);
+  desc.periodic = 0;
+  for (std::size_t k = 0; k < 3; ++k) {
+    desc.lower[k] = k < G::dimension ? lower[k] : 0.;
+    desc.upper[k] = k < G::dimension ? upper[k] : 1.;
+    desc.n[k] = k < G::dimension ? num_elements[k] : 1;
+  }
+  return GridProvider<G>(desc);
+}
+
+template <class G>
+GridProvider<G> make_cube_grid(const double lower, const double upper, const unsigned int num_elements)
+{
+  std::array<double, G::dimension> lo, up;
+  std::array<unsigned int, G::dimension> n;
+  lo.fill(lower);
+  up.fill(upper);
+  n.fill(num_elements);
+  return make_cube_grid<G>(lo, up, n);
+}
+
+// XT::Grid::make_periodic_grid_view(view) (examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:261)
+template <std::size_t d>
+CubeGridView<d> make_periodic_grid_view(const CubeGridView<d>& view)
+{
+  gdtb_grid_desc desc = view.desc();
+  desc.periodic = (1 << d) - 1;
+  return CubeGridView<d>(desc);
+}
+
+// intersection / element filters used on this path (XT::Grid::ApplyOn)
+template <class GV>
+struct ElementFilter
+{
+  virtual ~ElementFilter() = default;
+};
+template <class GV>
+struct IntersectionFilter
+{
+  virtual ~IntersectionFilter() = default;
+  virtual int gdtb_filter() const = 0;
+};
+namespace ApplyOn {
+template <class GV>
+struct AllElements : ElementFilter<GV>
+{};
+template <class GV>
+struct InnerIntersectionsOnce : IntersectionFilter<GV>
+{
+  int gdtb_filter() const override
+  {
+    return GDTB_FILTER_INNER_ONCE;
+  }
+};
+template <class GV>
+struct PeriodicBoundaryIntersectionsOnce : IntersectionFilter<GV>
+{
+  int gdtb_filter() const override
+  {
+    return GDTB_FILTER_INNER_AND_PERIODIC_ONCE;
+  }
+};
+template <class GV>
+struct AllIntersections : IntersectionFilter<GV>
+{
+  int gdtb_filter() const override
+  {
+    return -1;
+  }
+};
+} // namespace ApplyOn
+
+struct DirichletBoundary
+{};
+template <class I>
+struct AllDirichletBoundaryInfo
+{};
+namespace ApplyOn {
+// CustomBoundaryIntersections(boundary_info, new DirichletBoundary()) with AllDirichletBoundaryInfo
+// (examples/adaptive_elliptic_swipdg.cc:243)
+template <class GV>
+struct CustomBoundaryIntersections : IntersectionFilter<GV>
+{
+  template <class Info>
+  CustomBoundaryIntersections(const Info&, DirichletBoundary* type)
+  {
+    delete type;
+  }
+  int gdtb_filter() const override
+  {
+    return GDTB_FILTER_ALL_BOUNDARY;
+  }
+};
+} // namespace ApplyOn
+} // namespace Grid
+
+namespace Functions {
+
+// XT::Functions::GridFunction<E, r, rC>: a constant (scalar -> c * I for r = rC = d, laplace.hh:41), a constant
+// matrix, a per-element array, or a built-in analytic function.  Cloned by value.
+template <class E, std::size_t r = 1, std::size_t rC = 1, class R = double>
+class GridFunction
+{
+public:
+  GridFunction(const double value = 1., const int order = 0)
+  {
+    fn_.kind = GDTB_FN_CONST_SCALAR;
+    fn_.order = order;
+    fn_.c[0] = value;
+  }
+  GridFunction(const FieldMatrix<double, int(r), int(rC)>& value)
+  {
+    fn_.kind = GDTB_FN_CONST_TENSOR;
+    for (std::size_t i = 0; i < r; ++i)
+      for (std::size_t j = 0; j < rC; ++j)
+        fn_.c[i * rC + j] = value[i][j];
+  }
+  explicit GridFunction(const gdtb_function& fn, std::shared_ptr<std::vector<double>> storage = nullptr)
+    : fn_(fn)
+    , storage_(std::move(storage))
+  {}
+  const gdtb_function& descriptor() const
+  {
+    return fn_;
+  }
+  int order() const
+  {
+    return fn_.order;
+  }
+
+private:
+  gdtb_function fn_{};
+  std::shared_ptr<std::vector<double>> storage_;
+};
+
+// element-wise constant data (e.g. a heterogeneous diffusion field), values[e] for element index e
+template <class E>
+GridFunction<E> make_elementwise_constant(std::vector<double> values, const int order = 0)
+{
+  auto storage = std::make_shared<std::vector<double>>(std::move(values));
+  gdtb_function fn{};
+  fn.kind = GDTB_FN_ELEM_SCALAR;
+  fn.order = order;
+  fn.data = storage->data();
+  return GridFunction<E>(fn, storage);
+}
+
+// stand-ins for the GenericFunction lambdas of the reference drivers
+template <class E>
+GridFunction<E> make_cosine_product(const int order, const double factor, const double frequency)
+{
+  gdtb_function fn{};
+  fn.kind = GDTB_FN_BUILTIN;
+  fn.builtin = GDTB_BUILTIN_COS_PRODUCT;
+  fn.order = order;
+  fn.p[0] = factor;
+  fn.p[1] = frequency;
+  return GridFunction<E>(fn);
+}
+template <class E>
+GridFunction<E> make_indicator(const int order, const double lower, const double upper)
+{
+  gdtb_function fn{};
+  fn.kind = GDTB_FN_BUILTIN;
+  fn.builtin = GDTB_BUILTIN_INDICATOR;
+  fn.order = order;
+  fn.p[0] = lower;
+  fn.p[1] = upper;
+  return GridFunction<E>(fn);
+}
+template <class E>
+GridFunction<E> make_gaussian(const int order, const double center, const double sigma)
+{
+  gdtb_function fn{};
+  fn.kind = GDTB_FN_BUILTIN;
+  fn.builtin = GDTB_BUILTIN_GAUSSIAN;
+  fn.order = order;
+  fn.p[0] = center;
+  fn.p[1] = sigma;
+  return GridFunction<E>(fn);
+}
+
+} // namespace Functions
+
+namespace LA {
+
+// XT::LA::IstlDenseVector<double> stand-in (host storage)
+template <class R = double>
+class IstlDenseVector
+{
+public:
+  using ScalarType = R;
+  explicit IstlDenseVector(std::size_t size = 0, R value = 0)
+    : data_(size, value)
+  {}
+  std::size_t size() const
+  {
+    return data_.size();
+  }
+  R& operator[](std::size_t i)
+  {
+    return data_[i];
+  }
+  const R& operator[](std::size_t i) const
+  {
+    return data_[i];
+  }
+  R get_entry(std::size_t i) const
+  {
+    return data_[i];
+  }
+  R* data()
+  {
+    return data_.data();
+  }
+  const R* data() const
+  {
+    return data_.data();
+  }
+  IstlDenseVector operator*(R alpha) const
+  {
+    IstlDenseVector out(*this);
+    for (auto& x : out.data_)
+      x *= alpha;
+    return out;
+  }
+  IstlDenseVector operator-(const IstlDenseVector& other) const
+  {
+    IstlDenseVector out(*this);
+    for (std::size_t i = 0; i < data_.size(); ++i)
+      out.data_[i] -= other.data_[i];
+    return out;
+  }
+  R sup_norm() const
+  {
+    R m = 0;
+    for (auto x : data_)
+      m = std::max(m, x < 0 ? -x : x);
+    return m;
+  }
+
+private:
+  std::vector<R> data_;
+};
+
+// XT::LA::SparsityPatternDefault stand-in: the CSR pattern lives on the device, a host copy is made on demand
+class SparsityPatternDefault
+{
+public:
+  SparsityPatternDefault() = default;
+  explicit SparsityPatternDefault(gdtb_pattern* raw)
+    : handle_(raw)
+  {}
+  gdtb_pattern* handle() const
+  {
+    return handle_.get();
+  }
+  std::size_t size() const
+  {
+    return std::size_t(gdtb_pattern_rows(handle_.get()));
+  }
+  std::int64_t nnz() const
+  {
+    return gdtb_pattern_nnz(handle_.get());
+  }
+  // inner(row): the sorted column indices of a row (as SparsityPatternDefault::inner)
+  std::vector<std::size_t> inner(std::size_t row) const
+  {
+    fetch();
+    std::vector<std::size_t> cols;
+    for (std::int64_t k = rowptr_[row]; k < rowptr_[row + 1]; ++k)
+      cols.push_back(std::size_t(colidx_[std::size_t(k)]));
+    return cols;
+  }
+  const std::vector<std::int64_t>& rowptr() const
+  {
+    fetch();
+    return rowptr_;
+  }
+  const std::vector<std::int32_t>& colidx() const
+  {
+    fetch();
+    return colidx_;
+  }
+
+private:
+  void fetch() const
+  {
+    if (!rowptr_.empty())
+      return;
+    rowptr_.resize(size() + 1);
+    colidx_.resize(std::size_t(nnz()));
+    GDT::internal::check(gdtb_pattern_download(handle_.get(), rowptr_.data(), colidx_.data()));
+  }
+  GDT::internal::Handle<gdtb_pattern, gdtb_pattern_destroy> handle_;
+  mutable std::vector<std::int64_t> rowptr_;
+  mutable std::vector<std::int32_t> colidx_;
+};
+
+// XT::LA::IstlRowMajorSparseMatrix<double> stand-in: CSR, values on the host after assemble()
+template <class R = double>
+class IstlRowMajorSparseMatrix
+{
+public:
+  using ScalarType = R;
+  IstlRowMajorSparseMatrix() = default;
+  IstlRowMajorSparseMatrix(std::size_t rows, std::size_t cols, const SparsityPatternDefault& pattern)
+    : rows_(rows)
+    , cols_(cols)
+    , pattern_(pattern)
+    , values_(std::size_t(pattern.nnz()), R(0))
+  {}
+  std::size_t rows() const
+  {
+    return rows_;
+  }
+  std::size_t cols() const
+  {
+    return cols_;
+  }
+  std::size_t non_zeros() const
+  {
+    return values_.size();
+  }
+  const SparsityPatternDefault& pattern() const
+  {
+    return pattern_;
+  }
+  R get_entry(std::size_t i, std::size_t j) const
+  {
+    const auto& rp = pattern_.rowptr();
+    const auto& ci = pattern_.colidx();
+    for (std::int64_t k = rp[i]; k < rp[i + 1]; ++k)
+      if (std::size_t(ci[std::size_t(k)]) == j)
+        return values_[std::size_t(k)];
+    return R(0);
+  }
+  // y = A x (ConstMatrixOperator::apply, operators/matrix-based.hh:121-129), host side convenience
+  void mv(const IstlDenseVector<R>& x, IstlDenseVector<R>& y) const
+  {
+    const auto& rp = pattern_.rowptr();
+    const auto& ci = pattern_.colidx();
+    for (std::size_t i = 0; i < rows_; ++i) {
+      R s = 0;
+      for (std::int64_t k = rp[i]; k < rp[i + 1]; ++k)
+        s += values_[std::size_t(k)] * x[std::size_t(ci[std::size_t(k)])];
+      y[i] = s;
+    }
+  }
+  std::vector<R>& values()
+  {
+    return values_;
+  }
+  const std::vector<R>& values() const
+  {
+    return values_;
+  }
+
+private:
+  std::size_t rows_ = 0, cols_ = 0;
+  SparsityPatternDefault pattern_;
+  std::vector<R> values_;
+};
+
+} // namespace LA
+} // namespace XT
+
+// ==========================================================================================================
+// dune-gdt
+// ==========================================================================================================
+namespace GDT {
+
+// dune/gdt/type_traits.hh:24-32,55-60
+enum class SpaceType
+{
+  continuous_lagrange,
+  discontinuous_lagrange,
+  finite_volume
+};
+enum class Stencil
+{
+  element,
+  intersection,
+  element_and_intersection
+};
+
+// ---- spaces (spaces/interface.hh:92-98, spaces/mapper/interfaces.hh) ----------------------------------------
+template <class GV>
+class SpaceInterface;
+
+template <class GV>
+class MapperInterface
+{
+public:
+  explicit MapperInterface(const SpaceInterface<GV>& space)
+    : space_(space)
+  {}
+  std::size_t size() const;
+  std::size_t max_local_size() const;
+  std::size_t local_size(std::int64_t /*element*/) const
+  {
+    return max_local_size();
+  }
+  std::vector<std::size_t> global_indices(std::int64_t element) const;
+
+private:
+  const SpaceInterface<GV>& space_;
+};
+
+template <class GV>
+class SpaceInterface
+{
+public:
+  using GridViewType = GV;
+  static constexpr std::size_t d = GV::dimension;
+  using ElementType = typename GV::Element;
+
+  SpaceInterface(const GV& grid_view, int kind, int order)
+    : grid_view_(grid_view)
+    , kind_(kind)
+    , order_(order)
+    , mapper_(*this)
+  {
+    gdtb_space* raw = nullptr;
+    internal::check(gdtb_space_create(internal::context(), grid_view_.handle(), kind, order, &raw));
+    handle_ = internal::Handle<gdtb_space, gdtb_space_destroy>(raw);
+  }
+  SpaceInterface(const SpaceInterface& other)
+    : grid_view_(other.grid_view_)
+    , kind_(other.kind_)
+    , order_(other.order_)
+    , mapper_(*this)
+    , handle_(other.handle_)
+  {}
+  const GV& grid_view() const
+  {
+    return grid_view_;
+  }
+  const MapperInterface<GV>& mapper() const
+  {
+    return mapper_;
+  }
+  SpaceType type() const
+  {
+    return kind_ == GDTB_SPACE_CG ? SpaceType::continuous_lagrange
+                                  : (kind_ == GDTB_SPACE_DG ? SpaceType::discontinuous_lagrange
+                                                            : SpaceType::finite_volume);
+  }
+  int min_polorder() const
+  {
+    return order_;
+  }
+  int max_polorder() const
+  {
+    return order_;
+  }
+  gdtb_space* handle() const
+  {
+    return handle_.get();
+  }
+
+private:
+  GV grid_view_;
+  int kind_, order_;
+  MapperInterface<GV> mapper_;
+  internal::Handle<gdtb_space, gdtb_space_destroy> handle_;
+};
+
+template <class GV>
+std::size_t MapperInterface<GV>::size() const
+{
+  return std::size_t(gdtb_space_size(space_.handle()));
+}
+template <class GV>
+std::size_t MapperInterface<GV>::max_local_size() const
+{
+  return std::size_t(gdtb_space_max_local_size(space_.handle()));
+}
+template <class GV>
+std::vector<std::size_t> MapperInterface<GV>::global_indices(std::int64_t element) const
+{
+  std::vector<std::int64_t> tmp(max_local_size());
+  internal::check(gdtb_space_global_indices(space_.handle(), element, tmp.data()));
+  return std::vector<std::size_t>(tmp.begin(), tmp.end());
+}
+
+template <class GV>
+using ContinuousLagrangeSpace = SpaceInterface<GV>;
+template <class GV>
+using DiscontinuousLagrangeSpace = SpaceInterface<GV>;
+template <class GV>
+using FiniteVolumeSpace = SpaceInterface<GV>;
+
+// spaces/h1/continuous-lagrange.hh:189-203
+template <class GV>
+SpaceInterface<GV> make_continuous_lagrange_space(const GV& grid_view, const int order)
+{
+  return SpaceInterface<GV>(grid_view, GDTB_SPACE_CG, order);
+}
+// spaces/l2/discontinuous-lagrange.hh:191-205
+template <class GV>
+SpaceInterface<GV> make_discontinuous_lagrange_space(const GV& grid_view, const int order)
+{
+  return SpaceInterface<GV>(grid_view, GDTB_SPACE_DG, order);
+}
+// spaces/l2/finite-volume.hh:208-230
+template <class GV>
+SpaceInterface<GV> make_finite_volume_space(const GV& grid_view)
+{
+  return SpaceInterface<GV>(grid_view, GDTB_SPACE_FV, 0);
+}
+
+// ---- sparsity patterns (tools/sparsity-pattern.hh:34-178) ---------------------------------------------------
+template <class GV>
+XT::LA::SparsityPatternDefault make_sparsity_pattern(const SpaceInterface<GV>& test_space,
+                                                     const SpaceInterface<GV>& ansatz_space,
+                                                     const GV& /*grid_view*/,
+                                                     const Stencil stencil)
+{
+  gdtb_pattern* raw = nullptr;
+  internal::check(gdtb_pattern_create(
+      internal::context(), test_space.handle(), ansatz_space.handle(), int(stencil), GDTB_PATTERN_AUTO, &raw));
+  return XT::LA::SparsityPatternDefault(raw);
+}
+template <class GV>
+XT::LA::SparsityPatternDefault make_element_sparsity_pattern(const SpaceInterface<GV>& space)
+{
+  return make_sparsity_pattern(space, space, space.grid_view(), Stencil::element);
+}
+template <class GV>
+XT::LA::SparsityPatternDefault make_element_sparsity_pattern(const SpaceInterface<GV>& test,
+                                                             const SpaceInterface<GV>& ansatz,
+                                                             const GV& grid_view)
+{
+  return make_sparsity_pattern(test, ansatz, grid_view, Stencil::element);
+}
+template <class GV>
+XT::LA::SparsityPatternDefault make_intersection_sparsity_pattern(const SpaceInterface<GV>& space)
+{
+  return make_sparsity_pattern(space, space, space.grid_view(), Stencil::intersection);
+}
+template <class GV>
+XT::LA::SparsityPatternDefault make_element_and_intersection_sparsity_pattern(const SpaceInterface<GV>& space)
+{
+  return make_sparsity_pattern(space, space, space.grid_view(), Stencil::element_and_intersection);
+}
+
+// ---- integrands (local/integrands/*.hh) -----------------------------------------------------------------------
+namespace internal {
+struct IntegrandTerms
+{
+  std::vector<gdtb_integrand> terms;
+  // keep per-element storage of the wrapped grid functions alive until the form has been appended (= cloned)
+  std::vector<std::shared_ptr<void>> keep;
+};
+inline IntegrandTerms concat(const IntegrandTerms& a, const IntegrandTerms& b)
+{
+  IntegrandTerms out = a;
+  out.terms.insert(out.terms.end(), b.terms.begin(), b.terms.end());
+  out.keep.insert(out.keep.end(), b.keep.begin(), b.keep.end());
+  return out;
+}
+inline gdtb_form make_form(const IntegrandTerms& t, int over_integrate, double scaling)
+{
+  if (t.terms.empty() || t.terms.size() > GDTB_MAX_TERMS)
+    throw Exceptions::integrand_error("an integrand sum may have 1 to GDTB_MAX_TERMS summands");
+  gdtb_form f{};
+  f.n_terms = int(t.terms.size());
+  f.over_integrate = over_integrate;
+  f.scaling = scaling;
+  for (std::size_t i = 0; i < t.terms.size(); ++i)
+    f.terms[i] = t.terms[i];
+  return f;
+}
+template <class F>
+gdtb_integrand make_term(int kind, const F* diffusion, const F* weight, double prefactor, int hI_kind)
+{
+  gdtb_integrand in{};
+  in.kind = kind;
+  in.hI_kind = hI_kind;
+  in.prefactor = prefactor;
+  in.diffusion.kind = GDTB_FN_CONST_SCALAR;
+  in.diffusion.c[0] = 1.;
+  in.weight.kind = GDTB_FN_CONST_SCALAR;
+  in.weight.c[0] = 1.;
+  if (diffusion)
+    in.diffusion = diffusion->descriptor();
+  if (weight)
+    in.weight = weight->descriptor();
+  return in;
+}
+} // namespace internal
+
+// local/integrands/interfaces.hh: binary element integrands, summable with operator+ (:233-236)
+template <class E>
+class LocalBinaryElementIntegrandInterface
+{
+public:
+  explicit LocalBinaryElementIntegrandInterface(internal::IntegrandTerms terms = {})
+    : terms_(std::move(terms))
+  {}
+  const internal::IntegrandTerms& terms() const
+  {
+    return terms_;
+  }
+  LocalBinaryElementIntegrandInterface operator+(const LocalBinaryElementIntegrandInterface& other) const
+  {
+    return LocalBinaryElementIntegrandInterface(internal::concat(terms_, other.terms_));
+  }
+
+protected:
+  internal::IntegrandTerms terms_;
+};
+
+template <class E>
+class LocalUnaryElementIntegrandInterface
+{
+public:
+  explicit LocalUnaryElementIntegrandInterface(internal::IntegrandTerms terms = {})
+    : terms_(std::move(terms))
+  {}
+  const internal::IntegrandTerms& terms() const
+  {
+    return terms_;
+  }
+
+protected:
+  internal::IntegrandTerms terms_;
+};
+
+// local/integrands/laplace.hh:40-48
+template <class E, std::size_t r = 1, class F = double>
+class LocalLaplaceIntegrand : public LocalBinaryElementIntegrandInterface<E>
+{
+  static constexpr std::size_t d = E::dimension;
+
+public:
+  LocalLaplaceIntegrand(XT::Functions::GridFunction<E, d, d> diffusion = 1.)
+  {
+    this->terms_.terms.push_back(
+        internal::make_term(GDTB_INT_LAPLACE, &diffusion, (decltype(&diffusion)) nullptr, 0., GDTB_HI_DIAMETER));
+    this->terms_.keep.push_back(std::make_shared<XT::Functions::GridFunction<E, d, d>>(diffusion));
+  }
+  // element-wise constant scalar diffusion (kappa_e * I)
+  LocalLaplaceIntegrand(const XT::Functions::GridFunction<E>& diffusion, int /*scalar tag*/)
+  {
+    this->terms_.terms.push_back(
+        internal::make_term(GDTB_INT_LAPLACE, &diffusion, (decltype(&diffusion)) nullptr, 0., GDTB_HI_DIAMETER));
+    this->terms_.keep.push_back(std::make_shared<XT::Functions::GridFunction<E>>(diffusion));
+  }
+};
+
+// local/integrands/product.hh:56-65, 389-404; with_ansatz: integrands/interfaces.hh:225-229 + conversion.hh:42-124
+template <class E, std::size_t r = 1, class TF = double, class F = double, class AF = double>
+class LocalElementProductIntegrand : public LocalBinaryElementIntegrandInterface<E>
+{
+public:
+  LocalElementProductIntegrand(XT::Functions::GridFunction<E> weight = 1.)
+    : weight_(weight)
+  {
+    this->terms_.terms.push_back(
+        internal::make_term(GDTB_INT_PRODUCT, &weight_, (decltype(&weight_)) nullptr, 0., GDTB_HI_DIAMETER));
+    this->terms_.keep.push_back(std::make_shared<XT::Functions::GridFunction<E>>(weight_));
+  }
+  LocalUnaryElementIntegrandInterface<E> with_ansatz(const XT::Functions::GridFunction<E>& function) const
+  {
+    internal::IntegrandTerms t;
+    t.terms.push_back(internal::make_term(GDTB_INT_PRODUCT, &weight_, &function, 0., GDTB_HI_DIAMETER));
+    t.keep.push_back(std::make_shared<XT::Functions::GridFunction<E>>(weight_));
+    t.keep.push_back(std::make_shared<XT::Functions::GridFunction<E>>(function));
+    return LocalUnaryElementIntegrandInterface<E>(t);
+  }
+
+private:
+  XT::Functions::GridFunction<E> weight_;
+};
+template <class E, std::size_t r = 1, class TF = double, class F = double, class AF = double>
+using LocalProductIntegrand = LocalElementProductIntegrand<E, r, TF, F, AF>;
+
+template <class I>
+class LocalQuaternaryIntersectionIntegrandInterface
+{
+public:
+  explicit LocalQuaternaryIntersectionIntegrandInterface(internal::IntegrandTerms terms = {})
+    : terms_(std::move(terms))
+  {}
+  const internal::IntegrandTerms& terms() const
+  {
+    return terms_;
+  }
+  LocalQuaternaryIntersectionIntegrandInterface
+  operator+(const LocalQuaternaryIntersectionIntegrandInterface& other) const // interfaces.hh:609-612
+  {
+    return LocalQuaternaryIntersectionIntegrandInterface(internal::concat(terms_, other.terms_));
+  }
+
+protected:
+  internal::IntegrandTerms terms_;
+};
+
+template <class I>
+class LocalBinaryIntersectionIntegrandInterface
+{
+public:
+  explicit LocalBinaryIntersectionIntegrandInterface(internal::IntegrandTerms terms = {})
+    : terms_(std::move(terms))
+  {}
+  const internal::IntegrandTerms& terms() const
+  {
+    return terms_;
+  }
+  LocalBinaryIntersectionIntegrandInterface
+  operator+(const LocalBinaryIntersectionIntegrandInterface& other) const // interfaces.hh:480-483
+  {
+    return LocalBinaryIntersectionIntegrandInterface(internal::concat(terms_, other.terms_));
+  }
+
+protected:
+  internal::IntegrandTerms terms_;
+};
+
+enum class IntersectionDiameter
+{
+  diameter = GDTB_HI_DIAMETER, // internal::default_intersection_diameter (ipdg.hh:27-38)
+  volume = GDTB_HI_VOLUME      // [](const auto& intersection) { return intersection.geometry().volume(); }
+};
+
+namespace LocalLaplaceIPDGIntegrands {
+// local/integrands/laplace-ipdg.hh:47-61
+template <class I>
+class InnerCoupling : public LocalQuaternaryIntersectionIntegrandInterface<I>
+{
+  using E = typename I::Entity;
+  static constexpr std::size_t d = E::dimension;
+
+public:
+  InnerCoupling(const double& symmetry_prefactor,
+                XT::Functions::GridFunction<E, d, d> diffusion,
+                XT::Functions::GridFunction<E, d, d> weight_function = 1.)
+  {
+    this->terms_.terms.push_back(internal::make_term(
+        GDTB_INT_IPDG_INNER_COUPLING, &diffusion, &weight_function, symmetry_prefactor, GDTB_HI_DIAMETER));
+  }
+};
+// local/integrands/laplace-ipdg.hh:237-252 (binary use: the bilinear form on Dirichlet faces)
+template <class I>
+class DirichletCoupling : public LocalBinaryIntersectionIntegrandInterface<I>
+{
+  using E = typename I::Entity;
+  static constexpr std::size_t d = E::dimension;
+
+public:
+  DirichletCoupling(const double& symmetry_prefactor, XT::Functions::GridFunction<E, d, d> diffusion)
+  {
+    this->terms_.terms.push_back(internal::make_term(GDTB_INT_IPDG_DIRICHLET_COUPLING,
+                                                     &diffusion,
+                                                     (decltype(&diffusion)) nullptr,
+                                                     symmetry_prefactor,
+                                                     GDTB_HI_DIAMETER));
+  }
+};
+} // namespace LocalLaplaceIPDGIntegrands
+
+namespace LocalIPDGIntegrands {
+// local/integrands/ipdg.hh:59-72
+template <class I>
+class InnerPenalty : public LocalQuaternaryIntersectionIntegrandInterface<I>
+{
+  using E = typename I::Entity;
+  static constexpr std::size_t d = E::dimension;
+
+public:
+  InnerPenalty(const double& penalty,
+               XT::Functions::GridFunction<E, d, d> weight_function = 1.,
+               const IntersectionDiameter intersection_diameter = IntersectionDiameter::diameter)
+  {
+    this->terms_.terms.push_back(internal::make_term(GDTB_INT_IPDG_INNER_PENALTY,
+                                                     (decltype(&weight_function)) nullptr,
+                                                     &weight_function,
+                                                     penalty,
+                                                     int(intersection_diameter)));
+  }
+};
+// local/integrands/ipdg.hh:201-213
+template <class I>
+class BoundaryPenalty : public LocalBinaryIntersectionIntegrandInterface<I>
+{
+  using E = typename I::Entity;
+  static constexpr std::size_t d = E::dimension;
+
+public:
+  BoundaryPenalty(const double& penalty,
+                  XT::Functions::GridFunction<E, d, d> weight_function = 1.,
+                  const IntersectionDiameter intersection_diameter = IntersectionDiameter::diameter)
+  {
+    this->terms_.terms.push_back(internal::make_term(GDTB_INT_IPDG_BOUNDARY_PENALTY,
+                                                     (decltype(&weight_function)) nullptr,
+                                                     &weight_function,
+                                                     penalty,
+                                                     int(intersection_diameter)));
+  }
+};
+} // namespace LocalIPDGIntegrands
+
+// ---- local forms (local/bilinear-forms/integrals.hh, local/functionals/integrals.hh) ---------------------------
+template <class E>
+class LocalElementBilinearFormInterface
+{
+public:
+  virtual ~LocalElementBilinearFormInterface() = default;
+  virtual gdtb_form descriptor(double scaling) const = 0;
+};
+template <class I>
+class LocalCouplingIntersectionBilinearFormInterface
+{
+public:
+  virtual ~LocalCouplingIntersectionBilinearFormInterface() = default;
+  virtual gdtb_form descriptor(double scaling) const = 0;
+};
+template <class I>
+class LocalIntersectionBilinearFormInterface
+{
+public:
+  virtual ~LocalIntersectionBilinearFormInterface() = default;
+  virtual gdtb_form descriptor(double scaling) const = 0;
+};
+template <class E>
+class LocalElementFunctionalInterface
+{
+public:
+  virtual ~LocalElementFunctionalInterface() = default;
+  virtual gdtb_form descriptor() const = 0;
+};
+
+// integrals.hh:52-63
+template <class E, std::size_t r = 1>
+class LocalElementIntegralBilinearForm : public LocalElementBilinearFormInterface<E>
+{
+public:
+  LocalElementIntegralBilinearForm(const LocalBinaryElementIntegrandInterface<E>& integrand,
+                                   const int over_integrate = 0)
+    : terms_(integrand.terms())
+    , over_integrate_(over_integrate)
+  {}
+  gdtb_form descriptor(double scaling) const override
+  {
+    return internal::make_form(terms_, over_integrate_, scaling);
+  }
+
+private:
+  internal::IntegrandTerms terms_;
+  int over_integrate_;
+};
+
+// integrals.hh:169-180
+template <class I, std::size_t r = 1>
+class LocalCouplingIntersectionIntegralBilinearForm : public LocalCouplingIntersectionBilinearFormInterface<I>
+{
+public:
+  LocalCouplingIntersectionIntegralBilinearForm(const LocalQuaternaryIntersectionIntegrandInterface<I>& integrand,
+                                                const int over_integrate = 0)
+    : terms_(integrand.terms())
+    , over_integrate_(over_integrate)
+  {}
+  gdtb_form descriptor(double scaling) const override
+  {
+    return internal::make_form(terms_, over_integrate_, scaling);
+  }
+
+private:
+  internal::IntegrandTerms terms_;
+  int over_integrate_;
+};
+
+// integrals.hh:305-316
+template <class I, std::size_t r = 1>
+class LocalIntersectionIntegralBilinearForm : public LocalIntersectionBilinearFormInterface<I>
+{
+public:
+  LocalIntersectionIntegralBilinearForm(const LocalBinaryIntersectionIntegrandInterface<I>& integrand,
+                                        const int over_integrate = 0)
+    : terms_(integrand.terms())
+    , over_integrate_(over_integrate)
+  {}
+  gdtb_form descriptor(double scaling) const override
+  {
+    return internal::make_form(terms_, over_integrate_, scaling);
+  }
+
+private:
+  internal::IntegrandTerms terms_;
+  int over_integrate_;
+};
+
+// local/functionals/integrals.hh:41-52
+template <class E, std::size_t r = 1>
+class LocalElementIntegralFunctional : public LocalElementFunctionalInterface<E>
+{
+public:
+  LocalElementIntegralFunctional(const LocalUnaryElementIntegrandInterface<E>& integrand, const int over_integrate = 0)
+    : terms_(integrand.terms())
+    , over_integrate_(over_integrate)
+  {}
+  gdtb_form descriptor() const override
+  {
+    return internal::make_form(terms_, over_integrate_, 1.);
+  }
+
+private:
+  internal::IntegrandTerms terms_;
+  int over_integrate_;
+};
+
+// ---- VectorBasedFunctional (functionals/vector-based.hh:133-286) ----------------------------------------------
+template <class V, class GV>
+class VectorBasedFunctional
+{
+public:
+  using ElementType = typename GV::Element;
+
+  explicit VectorBasedFunctional(const SpaceInterface<GV>& space)
+    : space_(space)
+    , vector_(std::make_shared<V>(space.mapper().size()))
+  {
+    gdtb_vecfun* raw = nullptr;
+    internal::check(gdtb_vecfun_create(internal::context(), space_.handle(), &raw));
+    handle_ = internal::Handle<gdtb_vecfun, gdtb_vecfun_destroy>(raw);
+  }
+  // vector-based.hh:214-222
+  VectorBasedFunctional& append(const LocalElementFunctionalInterface<ElementType>& local_functional,
+                                const XT::Common::Parameter& /*param*/ = {},
+                                const XT::Grid::ElementFilter<GV>& /*filter*/ = XT::Grid::ApplyOn::AllElements<GV>())
+  {
+    const gdtb_form f = local_functional.descriptor();
+    internal::check(gdtb_vecfun_append_element(handle_.get(), &f));
+    return *this;
+  }
+  // vector-based.hh:276-279
+  void assemble(const bool /*use_tbb*/ = false)
+  {
+    internal::check(gdtb_assemble(nullptr, handle_.get(), mode()));
+    finalize();
+  }
+  V& vector()
+  {
+    return *vector_;
+  }
+  const V& vector() const
+  {
+    return *vector_;
+  }
+  const SpaceInterface<GV>& source_space() const
+  {
+    return space_;
+  }
+  // -- used by the walker / MatrixOperator to fuse the functional into their grid walk
+  gdtb_vecfun* handle() const
+  {
+    return handle_.get();
+  }
+  int mode() const
+  {
+    return fresh_ ? GDTB_ASSEMBLE_OVERWRITE : GDTB_ASSEMBLE_ACCUMULATE;
+  }
+  void finalize()
+  {
+    fresh_ = false;
+    internal::check(gdtb_vecfun_download(handle_.get(), vector_->data()));
+    internal::check(gdtb_vecfun_clear_forms(handle_.get()));
+  }
+
+private:
+  SpaceInterface<GV> space_;
+  std::shared_ptr<V> vector_;
+  internal::Handle<gdtb_vecfun, gdtb_vecfun_destroy> handle_;
+  bool fresh_ = true;
+};
+
+template <class V, class GV>
+VectorBasedFunctional<V, GV> make_vector_functional(const SpaceInterface<GV>& space)
+{
+  return VectorBasedFunctional<V, GV>(space);
+}
+
+// ---- MatrixOperator (operators/matrix-based.hh:245-508) --------------------------------------------------------
+template <class M, class GV>
+class MatrixOperator
+{
+public:
+  using MatrixType = M;
+  using E = typename GV::Element;
+  using I = typename GV::Intersection;
+  using FieldType = double;
+
+  // ctor which creates an appropriate matrix from a sparsity pattern (matrix-based.hh:298-311)
+  MatrixOperator(const GV& /*assembly_grid_view*/,
+                 const SpaceInterface<GV>& source_space,
+                 const SpaceInterface<GV>& range_space,
+                 const XT::LA::SparsityPatternDefault& pattern)
+    : scaling(1.)
+    , source_space_(source_space)
+    , range_space_(range_space)
+    , pattern_(pattern)
+    , matrix_(std::make_shared<M>(range_space.mapper().size(), source_space.mapper().size(), pattern))
+  {
+    gdtb_matop* raw = nullptr;
+    // rows = range (test) space, cols = source (ansatz) space (matrix-based.hh:73-80, 361-366)
+    internal::check(
+        gdtb_matop_create(internal::context(), range_space_.handle(), source_space_.handle(), pattern_.handle(), &raw));
+    handle_ = internal::Handle<gdtb_matop, gdtb_matop_destroy>(raw);
+  }
+
+  FieldType scaling; // captured by value at append time (matrix-based.hh:342,365)
+
+  // matrix-based.hh:346-369
+  MatrixOperator& append(const LocalElementBilinearFormInterface<E>& local_bilinear_form,
+                         const XT::Common::Parameter& /*param*/ = {},
+                         const XT::Grid::ElementFilter<GV>& /*filter*/ = XT::Grid::ApplyOn::AllElements<GV>())
+  {
+    const gdtb_form f = local_bilinear_form.descriptor(scaling);
+    internal::check(gdtb_matop_append_element(handle_.get(), &f));
+    return *this;
+  }
+  MatrixOperator& operator+=(const LocalElementBilinearFormInterface<E>& local_bilinear_form) // :450-455
+  {
+    return append(local_bilinear_form);
+  }
+  // matrix-based.hh:371-393
+  MatrixOperator& append(const LocalCouplingIntersectionBilinearFormInterface<I>& local_bilinear_form,
+                         const XT::Common::Parameter& /*param*/ = {},
+                         const XT::Grid::IntersectionFilter<GV>& filter = XT::Grid::ApplyOn::AllIntersections<GV>())
+  {
+    const gdtb_form f = local_bilinear_form.descriptor(scaling);
+    const int flt = filter.gdtb_filter();
+    if (flt != GDTB_FILTER_INNER_ONCE && flt != GDTB_FILTER_INNER_AND_PERIODIC_ONCE)
+      throw Dune::NotImplemented("coupling forms are supported with ApplyOn::InnerIntersectionsOnce (and the "
+                                 "periodic variant) only");
+    internal::check(gdtb_matop_append_coupling(handle_.get(), &f, flt));
+    return *this;
+  }
+  // matrix-based.hh:395-408
+  MatrixOperator& append(const LocalIntersectionBilinearFormInterface<I>& local_bilinear_form,
+                         const XT::Common::Parameter& /*param*/ = {},
+                         const XT::Grid::IntersectionFilter<GV>& filter = XT::Grid::ApplyOn::AllIntersections<GV>())
+  {
+    const gdtb_form f = local_bilinear_form.descriptor(scaling);
+    if (filter.gdtb_filter() != GDTB_FILTER_ALL_BOUNDARY)
+      throw Dune::NotImplemented("boundary forms are supported with CustomBoundaryIntersections(AllDirichlet...) only");
+    internal::check(gdtb_matop_append_boundary(handle_.get(), &f, GDTB_FILTER_ALL_BOUNDARY));
+    return *this;
+  }
+  // operator-as-walker: assemble the functional in the same grid walk (examples/adaptive_elliptic_swipdg.cc:250)
+  template <class V>
+  MatrixOperator& append(VectorBasedFunctional<V, GV>& functional)
+  {
+    riders_.push_back([&functional]() { return functional.handle(); });
+    modes_.push_back([&functional]() { return functional.mode(); });
+    finalizers_.push_back([&functional]() { functional.finalize(); });
+    return *this;
+  }
+
+  // matrix-based.hh:496-500: one grid walk; afterwards the functor list is empty (dune-xt clears it after walk)
+  void assemble(const bool /*use_tbb*/ = false)
+  {
+    walk();
+  }
+  void walk(const bool /*thread_parallel*/ = false)
+  {
+    if (riders_.size() > 1)
+      throw Dune::NotImplemented("at most one functional can ride along with a matrix operator");
+    gdtb_vecfun* fun = riders_.empty() ? nullptr : riders_[0]();
+    if (fun && modes_[0]() != mode()) {
+      internal::check(gdtb_assemble(handle_.get(), nullptr, mode()));
+      internal::check(gdtb_assemble(nullptr, fun, modes_[0]()));
+    } else
+      internal::check(gdtb_assemble(handle_.get(), fun, mode()));
+    finalize();
+    for (auto& fin : finalizers_)
+      fin();
+    riders_.clear();
+    modes_.clear();
+    finalizers_.clear();
+  }
+
+  M& matrix()
+  {
+    return *matrix_;
+  }
+  const M& matrix() const
+  {
+    return *matrix_;
+  }
+  const SpaceInterface<GV>& source_space() const
+  {
+    return source_space_;
+  }
+  const SpaceInterface<GV>& range_space() const
+  {
+    return range_space_;
+  }
+  // device-side access for callers that keep the matrix on the GPU
+  double* device_values() const
+  {
+    double* p = nullptr;
+    internal::check(gdtb_matop_values_device(handle_.get(), &p));
+    return p;
+  }
+  gdtb_matop* handle() const
+  {
+    return handle_.get();
+  }
+  int mode() const
+  {
+    return fresh_ ? GDTB_ASSEMBLE_OVERWRITE : GDTB_ASSEMBLE_ACCUMULATE;
+  }
+  void finalize()
+  {
+    fresh_ = false;
+    internal::check(gdtb_matop_values_download(handle_.get(), matrix_->values().data()));
+    internal::check(gdtb_matop_clear_forms(handle_.get()));
+  }
+
+private:
+  SpaceInterface<GV> source_space_, range_space_;
+  XT::LA::SparsityPatternDefault pattern_;
+  std::shared_ptr<M> matrix_;
+  internal::Handle<gdtb_matop, gdtb_matop_destroy> handle_;
+  std::vector<std::function<gdtb_vecfun*()>> riders_;
+  std::vector<std::function<int()>> modes_;
+  std::vector<std::function<void()>> finalizers_;
+  bool fresh_ = true;
+};
+
+// make_matrix_operator<M>(space, stencil) (matrix-based.hh:650-658)
+template <class M, class GV>
+MatrixOperator<M, GV> make_matrix_operator(const SpaceInterface<GV>& space, const Stencil stencil = Stencil::element)
+{
+  return MatrixOperator<M, GV>(
+      space.grid_view(), space, space, make_sparsity_pattern(space, space, space.grid_view(), stencil));
+}
+// make_matrix_operator<M>(view, source_space, range_space, pattern) (matrix-based.hh:514-560)
+template <class M, class GV>
+MatrixOperator<M, GV> make_matrix_operator(const GV& grid_view,
+                                           const SpaceInterface<GV>& source_space,
+                                           const SpaceInterface<GV>& range_space,
+                                           const XT::LA::SparsityPatternDefault& pattern)
+{
+  return MatrixOperator<M, GV>(grid_view, source_space, range_space, pattern);
+}
+
+} // namespace GDT
+
+namespace XT {
+namespace Grid {
+
+// XT::Grid::Walker: collects operators / functionals and assembles them in ONE grid walk
+// (examples/stationary-heat-equation.cc:102-106)
+template <class GV>
+class Walker
+{
+public:
+  explicit Walker(const GV& grid_view)
+    : grid_view_(grid_view)
+  {}
+  template <class M>
+  Walker& append(GDT::MatrixOperator<M, GV>& op)
+  {
+    if (op_walk_)
+      throw Dune::NotImplemented("one matrix operator per walk");
+    op_handle_ = [&op]() { return op.handle(); };
+    op_mode_ = [&op]() { return op.mode(); };
+    op_walk_ = [&op]() { op.finalize(); };
+    return *this;
+  }
+  template <class V>
+  Walker& append(GDT::VectorBasedFunctional<V, GV>& fun)
+  {
+    if (fun_walk_)
+      throw Dune::NotImplemented("one functional per walk");
+    fun_handle_ = [&fun]() { return fun.handle(); };
+    fun_mode_ = [&fun]() { return fun.mode(); };
+    fun_walk_ = [&fun]() { fun.finalize(); };
+    return *this;
+  }
+  void walk(const bool /*thread_parallel*/ = false)
+  {
+    gdtb_matop* op = op_walk_ ? op_handle_() : nullptr;
+    gdtb_vecfun* fun = fun_walk_ ? fun_handle_() : nullptr;
+    if (op && fun && op_mode_() != fun_mode_()) {
+      GDT::internal::check(gdtb_assemble(op, nullptr, op_mode_()));
+      GDT::internal::check(gdtb_assemble(nullptr, fun, fun_mode_()));
+    } else if (op || fun)
+      GDT::internal::check(gdtb_assemble(op, fun, op ? op_mode_() : fun_mode_()));
+    if (op_walk_)
+      op_walk_();
+    if (fun_walk_)
+      fun_walk_();
+    op_walk_ = nullptr; // walk(thread_parallel, clear_functors = true)
+    fun_walk_ = nullptr;
+  }
+
+private:
+  GV grid_view_;
+  std::function<gdtb_matop*()> op_handle_;
+  std::function<gdtb_vecfun*()> fun_handle_;
+  std::function<int()> op_mode_, fun_mode_;
+  std::function<void()> op_walk_, fun_walk_;
+};
+
+template <class GV>
+Walker<GV> make_walker(const GV& grid_view)
+{
+  return Walker<GV>(grid_view);
+}
+
+} // namespace Grid
+} // namespace XT
+
+namespace GDT {
+
+// ---- finite volumes (local/numerical-fluxes/upwind.hh, operators/advection-fv.hh) ------------------------------
+// stand-ins for the GenericFunction flux lambdas of the reference drivers
+struct LinearFlux // f(u) = a u (test/linear-transport/base.hh:50-57)
+{
+  std::array<double, 3> direction{{1., 0., 0.}};
+};
+struct BurgersFlux // f(u) = u^2/2 (1,...,1) (test/burgers/base.hh:38-44)
+{};
+
+template <class I, std::size_t d, std::size_t m = 1>
+class NumericalFluxInterface
+{
+public:
+  const gdtb_flux& descriptor() const
+  {
+    return flux_;
+  }
+
+protected:
+  gdtb_flux flux_{};
+};
+
+// local/numerical-fluxes/upwind.hh:44-50
+template <class I, std::size_t d, std::size_t m = 1>
+class NumericalUpwindFlux : public NumericalFluxInterface<I, d, m>
+{
+  static_assert(m == 1, "the upwind flux is only available for scalar equations (upwind.hh:24-28)");
+
+public:
+  NumericalUpwindFlux(const LinearFlux& f)
+  {
+    this->flux_.kind = GDTB_FLUX_LINEAR;
+    this->flux_.numflux = GDTB_NUMFLUX_UPWIND;
+    for (std::size_t k = 0; k < d; ++k)
+      this->flux_.p[k] = f.direction[k];
+  }
+  NumericalUpwindFlux(const BurgersFlux&)
+  {
+    this->flux_.kind = GDTB_FLUX_BURGERS;
+    this->flux_.numflux = GDTB_NUMFLUX_UPWIND;
+  }
+};
+
+// local/numerical-fluxes/lax-friedrichs.hh:33-58
+template <class I, std::size_t d, std::size_t m = 1>
+class NumericalLaxFriedrichsFlux : public NumericalFluxInterface<I, d, m>
+{
+public:
+  NumericalLaxFriedrichsFlux(const LinearFlux& f)
+  {
+    this->flux_.kind = GDTB_FLUX_LINEAR;
+    this->flux_.numflux = GDTB_NUMFLUX_LAX_FRIEDRICHS;
+    for (std::size_t k = 0; k < d; ++k)
+      this->flux_.p[k] = f.direction[k];
+  }
+  NumericalLaxFriedrichsFlux(const BurgersFlux&)
+  {
+    this->flux_.kind = GDTB_FLUX_BURGERS;
+    this->flux_.numflux = GDTB_NUMFLUX_LAX_FRIEDRICHS;
+  }
+};
+
+// operators/advection-fv.hh:44-128
+template <class M, class GV>
+class AdvectionFvOperator
+{
+public:
+  using V = XT::LA::IstlDenseVector<double>;
+  static constexpr std::size_t d = GV::dimension;
+
+  template <class I>
+  AdvectionFvOperator(const GV& /*assembly_grid_view*/,
+                      const NumericalFluxInterface<I, d, 1>& numerical_flux,
+                      const SpaceInterface<GV>& source_space,
+                      const SpaceInterface<GV>& range_space)
+    : source_space_(source_space)
+    , range_space_(range_space)
+  {
+    if (source_space.type() != SpaceType::finite_volume || range_space.type() != SpaceType::finite_volume)
+      throw Exceptions::operator_error("Use LocalAdvectionDgCouplingOperator instead!"); // advection-fv.hh:131-134
+    gdtb_fvop* raw = nullptr;
+    internal::check(gdtb_fvop_create(internal::context(), source_space_.handle(), &numerical_flux.descriptor(), &raw));
+    handle_ = internal::Handle<gdtb_fvop, gdtb_fvop_destroy>(raw);
+  }
+  // LocalizableOperator::apply(source, range, param) (operators/localizable-operator.hh:382-387)
+  void apply(const V& source, V& range, const XT::Common::Parameter& /*param*/ = {}) const
+  {
+    if (source.size() != source_space_.mapper().size() || range.size() != range_space_.mapper().size())
+      throw XT::Common::Exceptions::shapes_do_not_match("vector sizes do not match the finite volume spaces");
+    internal::check(gdtb_fvop_apply_host(handle_.get(), source.data(), range.data()));
+  }
+  // OperatorInterface::apply(source, param) (operators/interfaces.hh:645-650)
+  V apply(const V& source, const XT::Common::Parameter& param = {}) const
+  {
+    V range(range_space_.mapper().size());
+    apply(source, range, param);
+    return range;
+  }
+  const SpaceInterface<GV>& source_space() const
+  {
+    return source_space_;
+  }
+  const SpaceInterface<GV>& range_space() const
+  {
+    return range_space_;
+  }
+  gdtb_fvop* handle() const
+  {
+    return handle_.get();
+  }
+
+private:
+  SpaceInterface<GV> source_space_, range_space_;
+  internal::Handle<gdtb_fvop, gdtb_fvop_destroy> handle_;
+};
+
+// operators/advection-fv.hh:130-141
+template <class M, class GV, class I, std::size_t d>
+AdvectionFvOperator<M, GV> make_advection_fv_operator(const GV& assembly_grid_view,
+                                                      const NumericalFluxInterface<I, d, 1>& numerical_flux,
+                                                      const SpaceInterface<GV>& source_space,
+                                                      const SpaceInterface<GV>& range_space)
+{
+  return AdvectionFvOperator<M, GV>(assembly_grid_view, numerical_flux, source_space, range_space);
+}
+
+// explicit_euler of examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:141-159, run on the device:
+// returns u after the loop `while (time < T_end + dt)`
+template <class M, class GV>
+XT::LA::IstlDenseVector<double> explicit_euler(const XT::LA::IstlDenseVector<double>& initial_values,
+                                               const AdvectionFvOperator<M, GV>& spatial_op,
+                                               const double T_end,
+                                               const double dt)
+{
+  std::int64_t steps = 0;
+  double time = 0.;
+  while (time < T_end + dt) {
+    time += dt;
+    ++steps;
+  }
+  XT::LA::IstlDenseVector<double> u(initial_values);
+  internal::check(gdtb_fvop_euler_host(spatial_op.handle(), u.data(), dt, steps));
+  return u;
+}
+
+} // namespace GDT
+} // namespace Dune
+
+// grid type aliases of dune/xt/grid/grids.hh
+using YASP_1D_EQUIDISTANT_OFFSET = Dune::XT::Grid::YaspEquidistantOffset<1>;
+using YASP_2D_EQUIDISTANT_OFFSET = Dune::XT::Grid::YaspEquidistantOffset<2>;
+using YASP_3D_EQUIDISTANT_OFFSET = Dune::XT::Grid::YaspEquidistantOffset<3>;
+
+#endif // DUNE_GDT_B200_HH
