@@ -63,9 +63,14 @@ __device__ __forceinline__ void bulk_wait0()
 
 // number of stencil columns before vertex index i along one axis with N cells: sum_{i' < i} n(i'),
 // n(i') = 2 at the two ends, 3 inside
-__device__ __forceinline__ long long S_axis(long long i, long long N)
+__device__ __forceinline__ int S_axis(int i, int N)
 {
   return i == 0 ? 0 : (i > N ? 3 * N + 1 : 3 * i - 1);
+}
+
+__device__ __forceinline__ int n_axis(int i, int N)
+{
+  return 1 + (i > 0 ? 1 : 0) + (i < N ? 1 : 0);
 }
 
 template <int D>
@@ -81,167 +86,316 @@ __device__ __forceinline__ constexpr int delta_index(int dx, int dy, int dz)
   return (dx + 1) + (D > 1 ? 3 * (dy + 1) : 0) + (D > 2 ? 9 * (dz + 1) : 0);
 }
 
-template <int D, bool ACCUMULATE>
-__global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values,
-                            double* __restrict__ rhs, int chunk, int nchunks, long long nitems, int stage_doubles)
+// closed-form CSR row pointer of vertex (ix, iy, iz) of the CG-Q1 element stencil (tensor-product pattern)
+template <int D>
+__device__ __forceinline__ long long q1_rowptr(int ix, int iy, int iz, int Nx, int Ny, int Nz)
 {
-  constexpr int NO = 1 << D;       // elements around a vertex
-  constexpr int ND = P3<D>::value; // stencil size
+  if (D == 1)
+    return S_axis(ix, Nx);
+  const long long Wx = 3LL * Nx + 1;
+  if (D == 2)
+    return S_axis(iy, Ny) * Wx + (long long)(n_axis(iy, Ny) * S_axis(ix, Nx));
+  const long long Wy = 3LL * Ny + 1;
+  return S_axis(iz, Nz) * Wy * Wx
+         + n_axis(iz, Nz) * (S_axis(iy, Ny) * Wx + (long long)(n_axis(iy, Ny) * S_axis(ix, Nx)));
+}
+
+// extent of cell i along one axis exactly as YaspGrid<EquidistantOffsetCoordinates> hands it to the geometry:
+// upper - lower with lower = origin + i * h, upper = origin + (i + 1) * h (no FMA contraction, so that the ulp
+// noise of the extents is the one of the CPU path)
+__device__ __forceinline__ double cell_extent(double lo, double h, int i)
+{
+  const double lower = __dadd_rn(lo, __dmul_rn(double(i), h));
+  const double upper = __dadd_rn(lo, __dmul_rn(double(i + 1), h));
+  return __dsub_rn(upper, lower);
+}
+
+// vertex index -> (ix, iy, iz), x fastest; one past the last vertex decodes to i_last = N_last + 1, others 0
+template <int D>
+__device__ __forceinline__ void q1_decode(unsigned v, unsigned Vx, unsigned Vy, int& ix, int& iy, int& iz)
+{
+  ix = (int)v;
+  iy = 0;
+  iz = 0;
+  if (D > 1) {
+    const unsigned t = v / Vx;
+    ix = int(v - t * Vx);
+    iy = (int)t;
+    if (D > 2) {
+      const unsigned u = t / Vy;
+      iy = int(t - u * Vy);
+      iz = (int)u;
+    }
+  }
+}
+
+constexpr int Q1G_ROWS = 256; // rows (vertices) per work item = threads per CTA
+
+// Contribution of ONE element (offset (ox, oy, oz) around the vertex) to the vertex' row: the row i = (2^D-1) ^ o of
+// its local matrix L_e = sum_g scale_g * coefficient_g(e) * sum_{r,c} (1/h_r)(1/h_c) |det J_e| M_g[r][c] is added to
+// the stencil accumulators.  P0 / P1 receive the ansatz vertices with s_last = 0 / 1 (D == 3: the two z-planes the
+// element touches, index 3 (oy + sy) + ox + sx; D < 3: both point to the full accumulator array, index delta_index).
+// a[k] = h_k(e) and b[k] = 1 / h_k(e), both zeroed for a cell outside the grid / slab: such an element contributes
+// exact zeros and no branch is needed.
+template <int D, int NG, int KIND0>
+__device__ __forceinline__ void q1_add_element(const Q1GatherParams& p, int ox, int oy, int oz, const double (&a)[3],
+                                               const double (&b)[3], bool valid, long long e, double* __restrict__ P0,
+                                               double* __restrict__ P1)
+{
+  constexpr int NO = 1 << D;
+  const int o = ox + 2 * oy + 4 * oz;
+  const double ie = a[0] * (D > 1 ? a[1] : 1.) * (D > 2 ? a[2] : 1.); // |det J_e| (integrals.hh:119)
+#pragma unroll
+  for (int gi = 0; gi < NG; ++gi) {
+    const Q1Group& G = p.group[gi];
+    const int kind = KIND0 >= 0 ? KIND0 : G.kind;
+    double cf = G.scale;
+    if (G.coef_elem && kind != Q1G_LAPLACE_TENSOR)
+      cf *= valid ? __ldg(G.coef + e) : 0.;
+    if (kind == Q1G_LAPLACE_SCALAR) {
+      // kappa = c I: L_e = c sum_r |det J| / h_r^2 M[r][r]
+      double w[3];
+      w[0] = cf * (b[0] * (D > 1 ? a[1] : 1.) * (D > 2 ? a[2] : 1.));
+      if (D > 1)
+        w[1] = cf * (a[0] * b[1] * (D > 2 ? a[2] : 1.));
+      if (D > 2)
+        w[2] = cf * (a[0] * a[1] * b[2]);
+#pragma unroll
+      for (int s = 0; s < NO; ++s) {
+        const int sx = s & 1, sy = (s >> 1) & 1, sz = (s >> 2) & 1;
+        double* P = (D == 3 ? sz : (D == 2 ? 0 : 0)) ? P1 : P0;
+        const int t = D == 3 ? 3 * (oy + sy) + ox + sx : delta_index<D>(ox - 1 + sx, oy - 1 + sy, 0);
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+          P[t] = fma(w[r], G.M[r * 3 + r][o][s], P[t]);
+      }
+    } else if (kind == Q1G_MASS) {
+      const double w = cf * ie;
+#pragma unroll
+      for (int s = 0; s < NO; ++s) {
+        const int sx = s & 1, sy = (s >> 1) & 1, sz = (s >> 2) & 1;
+        double* P = (D == 3 && sz) ? P1 : P0;
+        const int t = D == 3 ? 3 * (oy + sy) + ox + sx : delta_index<D>(ox - 1 + sx, oy - 1 + sy, 0);
+        P[t] = fma(w, G.M[0][o][s], P[t]);
+      }
+    } else {
+      double w[9];
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const double kap =
+              G.coef_elem ? (valid ? __ldg(G.coef + e * (D * D) + r * D + c) : 0.) : G.kappa[r * 3 + c];
+          w[r * 3 + c] = cf * kap * (b[r] * b[c]) * ie;
+        }
+#pragma unroll
+      for (int s = 0; s < NO; ++s) {
+        const int sx = s & 1, sy = (s >> 1) & 1, sz = (s >> 2) & 1;
+        double* P = (D == 3 && sz) ? P1 : P0;
+        const int t = D == 3 ? 3 * (oy + sy) + ox + sx : delta_index<D>(ox - 1 + sx, oy - 1 + sy, 0);
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+          for (int c = 0; c < D; ++c)
+            P[t] = fma(w[r * 3 + c], G.M[r * 3 + c][o][s], P[t]);
+      }
+    }
+  }
+}
+
+// writes the (dy, dx) entries of one z-plane (D == 3) / of the whole row (D < 3) in CSR order; returns the count
+template <int NP>
+__device__ __forceinline__ int q1_store_plane(double* __restrict__ row, const double* __restrict__ P, bool full,
+                                              bool cx0, bool cx1, bool cy0, bool cy1)
+{
+  if (full) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+      row[k] = P[k];
+    return NP;
+  }
+  int pos = 0;
+#pragma unroll
+  for (int dy = 0; dy < NP / 3; ++dy) {
+    if (NP > 3 && (dy == 0 ? !cy0 : (dy == 2 ? !cy1 : false)))
+      continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      if (dx == 0 ? !cx0 : (dx == 2 ? !cx1 : false))
+        continue;
+      row[pos++] = P[3 * dy + dx];
+    }
+  }
+  return pos;
+}
+
+// Work item = Q1G_ROWS consecutive rows (vertices in mapper order).  Consecutive rows are consecutive in CSR, so the
+// item's values form ONE contiguous segment [rowptr(r0), rowptr(r0 + Q1G_ROWS)): it is staged in shared memory in CSR
+// order and leaves the SM as one TMA bulk store.  Thread t owns row r0 + t: it evaluates the geometry of the 2^D
+// cells around its vertex, forms the row of each cell's local matrix that belongs to the vertex and sums the
+// contributions per stencil column in a fixed order (deterministic, no atomics).
+template <int D, int NG, int KIND0, bool ACCUMULATE>
+__global__ void __launch_bounds__(Q1G_ROWS, 2)
+    k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values, double* __restrict__ rhs,
+                long long nrows, int nitems, int stage_doubles)
+{
+  constexpr int NO = 1 << D; // elements around a vertex
   extern __shared__ __align__(16) double smem[];
   const GridDev& g = p.g;
   const int Nx = (int)g.n[0], Ny = D > 1 ? (int)g.n[1] : 1, Nz = D > 2 ? (int)g.n[2] : 1;
-  const long long Wx = 3LL * Nx + 1, Wy = D > 1 ? 3LL * Ny + 1 : 1;
-  const int lines_y = D == 3 ? Ny + 1 : 1;
-  // element range along the last direction (owner-computes slab + ghost layer), vertex range in x
+  const unsigned Vx = Nx + 1, Vy = D > 1 ? Ny + 1 : 1;
+  // element range along the last direction (owner-computes slab + ghost layer)
   const int elo = (int)p.elem_lo, ehi = (int)p.elem_hi;
-  const int x_lo = D == 1 ? (int)p.row_lo : 0, x_hi = D == 1 ? (int)p.row_hi : Nx + 1;
+  const bool want_values = NG > 0 && values != nullptr;
   int buf = 0;
 
-  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-    // ---- per line (uniform over the CTA) ----------------------------------------------------------------
-    const int ch = int(item % nchunks);
-    const long long line = item / nchunks;
-    int iy = 0, iz = 0;
-    if (D == 3) {
-      iy = int(line % lines_y);
-      iz = int(p.row_lo + line / lines_y);
-    } else if (D == 2)
-      iy = int(p.row_lo + line);
-    const int x0 = x_lo + ch * chunk;
-    const int x1 = min(x0 + chunk, x_hi);
-    // element validity along y and z: e_k = i_k - 1 + o_k
-    bool vy[2] = {true, true}, vz[2] = {true, true};
-    if (D == 2) {
-      vy[0] = iy - 1 >= elo && iy - 1 < ehi;
-      vy[1] = iy >= elo && iy < ehi;
-    } else if (D == 3) {
-      vy[0] = iy >= 1;
-      vy[1] = iy < Ny;
-      vz[0] = iz - 1 >= elo && iz - 1 < ehi;
-      vz[1] = iz >= elo && iz < ehi;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    // ---- per item (uniform over the CTA): the CSR segment -------------------------------------------------
+    const long long l0 = (long long)item * Q1G_ROWS; // first local row
+    const int nr = (int)min((long long)Q1G_ROWS, nrows - l0);
+    const unsigned r0 = (unsigned)(p.row_offset + l0); // first global row (= vertex index)
+    long long start = 0;
+    int seg = 0, phase = 0;
+    unsigned start32 = 0;
+    double* stage = smem;
+    if (want_values) {
+      int bx, by, bz, cx, cy, cz;
+      q1_decode<D>(r0, Vx, Vy, bx, by, bz);
+      q1_decode<D>(r0 + nr, Vx, Vy, cx, cy, cz);
+      const long long gstart = q1_rowptr<D>(bx, by, bz, Nx, Ny, Nz);
+      // one past the last vertex decodes to (0, 0, Nz + 1) [(0, Ny + 1) in 2D, Nx + 1 in 1D]: S_axis saturates
+      const long long gend = q1_rowptr<D>(cx, cy, cz, Nx, Ny, Nz);
+      seg = int(gend - gstart);
+      start = gstart - p.value_offset;
+      start32 = (unsigned)gstart;
+      // keep the shared-memory and global 16-byte phases equal for the bulk copy
+      phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
+      stage = smem + buf * stage_doubles + phase;
     }
-    // columns that exist in y and z
-    const bool cy0 = D > 1 && iy > 0, cy1 = D > 1 && iy < Ny, cz0 = D > 2 && iz > 0, cz1 = D > 2 && iz < Nz;
-    const int ny = D > 1 ? 1 + cy0 + cy1 : 1, nz = D > 2 ? 1 + cz0 + cz1 : 1;
-    const int c = ny * nz;
-    const bool full_yz = (D < 2 || ny == 3) && (D < 3 || nz == 3);
-    const int Sx0 = x0 == 0 ? 0 : 3 * x0 - 1;
-    const int Sx1 = x1 > Nx ? 3 * Nx + 1 : 3 * x1 - 1;
-    long long start;
-    if (D == 3)
-      start = S_axis(iz, Nz) * Wy * Wx + (long long)nz * (S_axis(iy, Ny) * Wx + (long long)ny * Sx0);
-    else if (D == 2)
-      start = S_axis(iy, Ny) * Wx + (long long)ny * Sx0;
-    else
-      start = Sx0;
-    start -= p.value_offset;
-    const int seg = c * (Sx1 - Sx0);
-    // keep the shared-memory and global 16-byte phases equal for the bulk copy
-    const int phase = values ? int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL) : 0;
-    double* stage = smem + buf * stage_doubles + phase;
 
-    // ---- per vertex ----------------------------------------------------------------------------------------
-    const int ix = x0 + (int)threadIdx.x;
-    if (ix < x1) {
-      bool vx[2];
-      if (D == 1) {
-        vx[0] = ix - 1 >= elo && ix - 1 < ehi;
-        vx[1] = ix >= elo && ix < ehi;
-      } else {
-        vx[0] = ix >= 1;
-        vx[1] = ix < Nx;
-      }
-      double acc[ND];
+    // ---- per vertex --------------------------------------------------------------------------------------
+    if ((int)threadIdx.x < nr) {
+      int ix, iy, iz;
+      q1_decode<D>(r0 + threadIdx.x, Vx, Vy, ix, iy, iz);
+      const int il[3] = {ix, iy, iz};
+      const int Nl[3] = {Nx, Ny, Nz};
+      // geometry of the two cells per axis around the vertex: ha[k][o] = h_k, hb[k][o] = 1 / h_k (J^{-T} = diag(1/h_k),
+      // spaces/basis/default.hh:167-174; integration element = prod h_k); zero for cells outside the grid / slab
+      double ha[3][2], hb[3][2];
+      bool vk[3][2];
 #pragma unroll
-      for (int dlt = 0; dlt < ND; ++dlt)
-        acc[dlt] = 0.;
-      double b = 0.;
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          ha[k][o] = 1.;
+          hb[k][o] = 1.;
+          vk[k][o] = o == 0;
+          if (k < D) {
+            const int lo = k == D - 1 ? elo : 0, hi = k == D - 1 ? ehi : Nl[k];
+            const int c = il[k] - 1 + o;
+            vk[k][o] = c >= lo && c < hi;
+            const double h = cell_extent(g.lo[k], g.h[k], c);
+            ha[k][o] = vk[k][o] ? h : 0.;
+            hb[k][o] = vk[k][o] ? __drcp_rn(h) : 0.;
+          }
+        }
       // element index of offset o = 0 (may be out of range; only dereferenced when valid)
-      const long long e0 = (long long)(ix - 1) + (long long)Nx * ((D > 1 ? iy - 1 : 0) + (long long)Ny * (D > 2 ? iz - 1 : 0));
+      const long long e0 =
+          (long long)(ix - 1) + (long long)Nx * ((D > 1 ? iy - 1 : 0) + (long long)Ny * (D > 2 ? iz - 1 : 0));
+      const bool cx0 = ix > 0, cx1 = ix < Nx;
+      const bool cy0 = D > 1 && iy > 0, cy1 = D > 1 && iy < Ny, cz0 = D > 2 && iz > 0, cz1 = D > 2 && iz < Nz;
+      const bool full_xy = cx0 && cx1 && (D < 2 || (cy0 && cy1));
+      // wrap-around 32-bit arithmetic is exact for the (small) difference of two row pointers
+      double* row = stage;
+      if (want_values)
+        row += (unsigned)q1_rowptr<D>(ix, iy, iz, Nx, Ny, Nz) - start32;
+      double bsum = 0.;
+
+      if (D == 3) {
+        // two passes over the element layers below / above the vertex; the z-plane of the stencil that is complete
+        // after a pass is written out at once, so only two planes (18 values) are live at any time
+        double P[3][9];
 #pragma unroll
-      for (int o = 0; o < NO; ++o) {
-        const int ox = o & 1, oy = (o >> 1) & 1, oz = (o >> 2) & 1;
-        const bool valid = vx[ox] && vy[oy] && vz[oz];
-        if (valid) {
-          const long long e = e0 + ox + (long long)Nx * (oy + (long long)Ny * oz);
-          if (p.has_const) {
+        for (int k = 0; k < 9; ++k)
+          P[0][k] = P[1][k] = P[2][k] = 0.;
 #pragma unroll
-            for (int s = 0; s < NO; ++s)
-              acc[delta_index<D>(ox - 1 + (s & 1), oy - 1 + ((s >> 1) & 1), oz - 1 + ((s >> 2) & 1))] +=
-                  p.T_const[o][s];
+        for (int oz = 0; oz < 2; ++oz) {
+#pragma unroll
+          for (int oxy = 0; oxy < 4; ++oxy) {
+            const int ox = oxy & 1, oy = oxy >> 1;
+            const double a[3] = {ha[0][ox], ha[1][oy], ha[2][oz]};
+            const double b[3] = {hb[0][ox], hb[1][oy], hb[2][oz]};
+            const bool valid = vk[0][ox] && vk[1][oy] && vk[2][oz];
+            const long long e = e0 + ox + (long long)Nx * (oy + (long long)Ny * oz);
+            if (want_values)
+              q1_add_element<D, NG, KIND0>(p, ox, oy, oz, a, b, valid, e, P[oz], P[oz + 1]);
+            const double ie = a[0] * a[1] * a[2];
+            if (p.rhs_has_const)
+              bsum = fma(ie, p.rhs_S_const[ox + 2 * oy + 4 * oz], bsum);
+            if (p.rhs_has_elem)
+              bsum = fma(ie * p.rhs_S_elem[ox + 2 * oy + 4 * oz], valid ? __ldg(p.rhs_elem + e) : 0., bsum);
           }
-          for (int chn = 0; chn < p.n_elem; ++chn) {
-            const double cf = __ldg(p.coef[chn] + e);
-#pragma unroll
-            for (int s = 0; s < NO; ++s) {
-              const int dlt = delta_index<D>(ox - 1 + (s & 1), oy - 1 + ((s >> 1) & 1), oz - 1 + ((s >> 2) & 1));
-              acc[dlt] = fma(cf, p.T_elem[chn][o][s], acc[dlt]);
+          if (want_values) {
+            if (oz == 0) {
+              if (cz0)
+                row += q1_store_plane<9>(row, P[0], full_xy, cx0, cx1, cy0, cy1);
+            } else {
+              row += q1_store_plane<9>(row, P[1], full_xy, cx0, cx1, cy0, cy1);
+              if (cz1)
+                q1_store_plane<9>(row, P[2], full_xy, cx0, cx1, cy0, cy1);
             }
           }
+        }
+      } else {
+        constexpr int ND = P3<D>::value;
+        double P[ND];
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+          P[k] = 0.;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          const int ox = o & 1, oy = (o >> 1) & 1;
+          const double a[3] = {ha[0][ox], ha[1][oy], 1.};
+          const double b[3] = {hb[0][ox], hb[1][oy], 1.};
+          const bool valid = vk[0][ox] && vk[1][oy];
+          const long long e = e0 + ox + (long long)Nx * oy;
+          if (want_values)
+            q1_add_element<D, NG, KIND0>(p, ox, oy, 0, a, b, valid, e, P, P);
+          const double ie = a[0] * a[1];
           if (p.rhs_has_const)
-            b += p.rhs_const;
+            bsum = fma(ie, p.rhs_S_const[o], bsum);
           if (p.rhs_has_elem)
-            b = fma(p.rhs_elem_scale, __ldg(p.rhs_elem + e), b);
+            bsum = fma(ie * p.rhs_S_elem[o], valid ? __ldg(p.rhs_elem + e) : 0., bsum);
         }
+        if (want_values)
+          q1_store_plane<ND>(row, P, full_xy, cx0, cx1, cy0, cy1);
       }
-      // rows in CSR order: (dz, dy, dx) ascending over the columns that exist
-      if (values) {
-        const int Sx = ix == 0 ? 0 : 3 * ix - 1;
-        double* row = stage + c * (Sx - Sx0);
-        if (full_yz && vx[0] && vx[1] && D > 1) {
-#pragma unroll
-          for (int k = 0; k < ND; ++k)
-            row[k] = acc[k];
-        } else {
-          int pos = 0;
-#pragma unroll
-          for (int dz = -1; dz <= 1; ++dz) {
-            if (D < 3 ? dz != 0 : (dz < 0 ? !cz0 : (dz > 0 ? !cz1 : false)))
-              continue;
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-              if (D < 2 ? dy != 0 : (dy < 0 ? !cy0 : (dy > 0 ? !cy1 : false)))
-                continue;
-#pragma unroll
-              for (int dx = -1; dx <= 1; ++dx) {
-                if (dx < 0 ? ix == 0 : (dx > 0 ? ix == Nx : false))
-                  continue;
-                row[pos++] = acc[delta_index<D>(dx, dy, dz)];
-              }
-            }
-          }
-        }
-      }
+
       if (p.has_rhs && rhs) {
         if (p.rhs_has_sep) {
-          double t = p.rhs_sep_scale * __ldg(p.rhs_sep_tab + ix);
+          double t2 = p.rhs_sep_scale * __ldg(p.rhs_sep_tab + ix);
           if (D > 1)
-            t *= __ldg(p.rhs_sep_tab + p.rhs_sep_stride + iy);
+            t2 *= __ldg(p.rhs_sep_tab + p.rhs_sep_stride + iy);
           if (D > 2)
-            t *= __ldg(p.rhs_sep_tab + 2 * p.rhs_sep_stride + iz);
-          b += t;
+            t2 *= __ldg(p.rhs_sep_tab + 2 * p.rhs_sep_stride + iz);
+          bsum += t2;
         }
-        long long r = ix;
-        if (D > 1)
-          r += (long long)(Nx + 1) * iy;
-        if (D > 2)
-          r += (long long)(Nx + 1) * (Ny + 1) * iz;
-        r -= p.row_offset;
+        const long long r = l0 + threadIdx.x;
         if (ACCUMULATE)
-          rhs[r] += b;
+          rhs[r] += bsum;
         else
-          rhs[r] = b;
+          rhs[r] = bsum;
       }
     }
 
-    if (values) {
+    if (want_values) {
       if (ACCUMULATE) {
         __syncthreads();
         for (int i = threadIdx.x; i < seg; i += blockDim.x)
           values[start + i] += stage[i];
         __syncthreads();
       } else {
-        // double-buffered TMA bulk store: the store of this line drains while the next line is computed
+        // double-buffered TMA bulk store: the store of this item drains while the next one is computed
         fence_proxy_async_smem();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -255,19 +409,19 @@ __global__ void k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __
           if (head + body < seg)
             values[start + head + body] = stage[head + body];
           bulk_commit();
-          bulk_wait_read1(); // the buffer written two lines ago is free again
+          bulk_wait_read1(); // the buffer written two items ago is free again
         }
         __syncthreads();
         buf ^= 1;
       }
     }
   }
-  if (!ACCUMULATE && values && threadIdx.x == 0)
+  if (!ACCUMULATE && want_values && threadIdx.x == 0)
     bulk_wait0();
 }
 
 // Separable right-hand side tables: for f(x) = p0 * prod_k F_k(x_k),
-//   B_k[i] = sum over the (valid) cells e in {i-1, i} of  sum_q w_q phi_a(xi_q) F_k(lower_e + xi_q * ext_e),
+//   B_k[i] = sum over the (valid) cells e in {i-1, i} of  ext_e * sum_q w_q phi_a(xi_q) F_k(lower_e + xi_q * ext_e),
 // a = local index of vertex i in cell e.  One block, strided over (axis, vertex).
 __global__ void k_q1_rhs_tables(const GridDev g, long long elem_lo, long long elem_hi, const FnDev f, int m,
                                 const double* __restrict__ qx,
@@ -286,9 +440,10 @@ __global__ void k_q1_rhs_tables(const GridDev g, long long elem_lo, long long el
         if (e < elo || e >= ehi)
           continue;
         const int a = 1 - o;
-        const double lower = g.lo[k] + double(e) * g.h[k];
-        const double upper = g.lo[k] + double(e + 1) * g.h[k];
-        const double ext = upper - lower;
+        const double lower = __dadd_rn(g.lo[k], __dmul_rn(double(e), g.h[k]));
+        const double upper = __dadd_rn(g.lo[k], __dmul_rn(double(e + 1), g.h[k]));
+        const double ext = __dsub_rn(upper, lower);
+        double sc = 0.;
         for (int q = 0; q < m; ++q) {
           const double x = lower + qx[q] * ext;
           double F = 1.;
@@ -299,8 +454,9 @@ __global__ void k_q1_rhs_tables(const GridDev g, long long elem_lo, long long el
             F = exp(-(t * t) / (2. * (f.p[1] * f.p[1])));
           } else if (f.builtin == GDTB_BUILTIN_INDICATOR && k == 0)
             F = (f.p[0] <= x && x <= f.p[1]) ? 1. : 0.;
-          s += qw[q] * phi[q * 2 + a] * F;
+          sc += qw[q] * phi[q * 2 + a] * F;
         }
+        s += sc * ext; // this axis' factor of the integration element prod_k ext_k (local/functionals/integrals.hh:96)
       }
       tab[k * stride + i] = s;
     }
@@ -318,40 +474,58 @@ int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long lo
   return GDTB_OK;
 }
 
-template <int D>
-static int launch_q1_gather_d(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
+template <int D, int NG, int KIND0>
+static int launch_q1_gather_dn(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
 {
   const GridDev& g = p.g;
-  const long long nvx = D == 1 ? p.row_hi - p.row_lo : g.n[0] + 1;
-  const int max_chunk = 512;
-  const int nchunks = int((nvx + max_chunk - 1) / max_chunk);
-  const int chunk = int((nvx + nchunks - 1) / nchunks);
-  const int threads = ((chunk + 31) / 32) * 32;
-  long long nlines = 1;
-  if (D == 3)
-    nlines = (g.n[1] + 1) * (p.row_hi - p.row_lo);
-  else if (D == 2)
-    nlines = p.row_hi - p.row_lo;
-  const long long nitems = nlines * nchunks;
+  long long layer_rows = 1;
+  for (int k = 0; k < D - 1; ++k)
+    layer_rows *= g.n[k] + 1;
+  long long total_rows = layer_rows * (g.n[D - 1] + 1);
+  if (total_rows >= (1LL << 31) - Q1G_ROWS)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q1_gather: more than 2^31 vertices");
+  const long long nrows = (p.row_hi - p.row_lo) * layer_rows;
+  const long long nitems = (nrows + Q1G_ROWS - 1) / Q1G_ROWS;
+  if (nitems <= 0)
+    return GDTB_OK;
   // two stage buffers (double-buffered bulk store), each padded for the 16-byte phase shift
-  const int stage_doubles = ((chunk * P3<D>::value + 2) + 1) & ~1;
-  const size_t smem = values ? (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double) : 16;
-  auto kern = accumulate ? k_q1_gather<D, true> : k_q1_gather<D, false>;
+  const int stage_doubles = ((Q1G_ROWS * P3<D>::value + 2) + 1) & ~1;
+  const bool with_values = NG > 0 && values;
+  const size_t smem = with_values ? (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double) : 16;
+  auto kern = accumulate ? k_q1_gather<D, NG, KIND0, true> : k_q1_gather<D, NG, KIND0, false>;
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Q1G_ROWS, smem));
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "q1_gather: kernel does not fit on an SM");
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)
     grid = nitems;
   time_begin(L, KF_Q1_GATHER);
-  kern<<<(unsigned)grid, threads, smem, L.stream>>>(p, values, rhs, chunk, nchunks, nitems, stage_doubles);
+  kern<<<(unsigned)grid, Q1G_ROWS, smem, L.stream>>>(p, values, rhs, nrows, (int)nitems, stage_doubles);
   time_end(L, KF_Q1_GATHER);
   L.count++;
   GDTB_CUDA(cudaGetLastError());
   return GDTB_OK;
+}
+
+template <int D>
+static int launch_q1_gather_d(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
+{
+  switch (values ? p.n_groups : 0) {
+    case 0: return launch_q1_gather_dn<D, 0, -1>(L, p, nullptr, rhs, accumulate);
+    case 1:
+      // a single integrand: its kind is a compile-time constant of the kernel
+      switch (p.group[0].kind) {
+        case Q1G_LAPLACE_SCALAR: return launch_q1_gather_dn<D, 1, Q1G_LAPLACE_SCALAR>(L, p, values, rhs, accumulate);
+        case Q1G_MASS: return launch_q1_gather_dn<D, 1, Q1G_MASS>(L, p, values, rhs, accumulate);
+        default: return launch_q1_gather_dn<D, 1, Q1G_LAPLACE_TENSOR>(L, p, values, rhs, accumulate);
+      }
+    case 2: return launch_q1_gather_dn<D, 2, -1>(L, p, values, rhs, accumulate);
+    case 3: return launch_q1_gather_dn<D, 3, -1>(L, p, values, rhs, accumulate);
+    default: return fail(GDTB_ERR_INVALID_ARGUMENT, "q1_gather: too many integrand groups");
+  }
 }
 
 int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)

@@ -360,24 +360,22 @@ bool matop_q1_eligible(const gdtb_matop* op)
     return false;
   if (!op->coupling_forms.empty() || !op->boundary_forms.empty() || op->element_forms.empty())
     return false;
-  int n_elem = 0;
+  // element-wise constant coefficients only: then the quadrature sum factorises exactly (kernels.hpp, Q1Group)
+  int n_groups = 0;
   for (const auto& lf : op->element_forms)
     for (int t = 0; t < lf.form.n_terms; ++t) {
       const gdtb_integrand& in = lf.form.terms[t];
       if (in.kind == GDTB_INT_LAPLACE) {
-        if (in.diffusion.kind == GDTB_FN_ELEM_SCALAR)
-          ++n_elem;
-        else if (!fn_is_const(in.diffusion))
+        if (in.diffusion.kind == GDTB_FN_BUILTIN)
           return false;
       } else if (in.kind == GDTB_INT_PRODUCT) {
-        if (in.diffusion.kind == GDTB_FN_ELEM_SCALAR)
-          ++n_elem;
-        else if (in.diffusion.kind != GDTB_FN_CONST_SCALAR)
+        if (in.diffusion.kind != GDTB_FN_CONST_SCALAR && in.diffusion.kind != GDTB_FN_ELEM_SCALAR)
           return false;
       } else
         return false;
+      ++n_groups;
     }
-  return n_elem <= Q1G_MAX_ELEM_CHANNELS;
+  return n_groups <= Q1G_MAX_GROUPS;
 }
 
 bool builtin_is_separable(int id)
@@ -437,58 +435,34 @@ void q1_tables(int order, Q1Tables& t)
   }
 }
 
-// reference tensor of one integrand with unit (or the given constant) coefficient on a cell with extents h:
-// Lref[i][j], i = test, j = ansatz, local index bits = (a_0, a_1, a_2)
-void q1_reference_tensor(const gdtb_integrand& in, int d, const double* h, const Q1Tables& tab, bool unit_coefficient,
-                         double Lref[8][8])
+// reference-element tensors of one integrand for the gather kernel (kernels.hpp, Q1Group):
+// M[r*3+c][o][s] = sum_q w_q d_r phihat_i(x_q) d_c phihat_j(x_q) with i = (2^d - 1) ^ o (the vertex seen from the
+// element at offset o), j = s; tensor-product rule => product of the 1D tables.  Mass: M[0][o][s] = sum_q w_q phihat_i phihat_j.
+void q1_group_tensors(int kind, int d, const Q1Tables& tab, double M[9][8][8])
 {
   const int n = 1 << d;
-  double ie = 1.;
-  for (int k = 0; k < d; ++k)
-    ie *= h[k];
-  double kap[3][3] = {{0}};
-  if (in.kind == GDTB_INT_LAPLACE) {
-    if (!unit_coefficient && in.diffusion.kind == GDTB_FN_CONST_TENSOR) {
-      for (int r = 0; r < d; ++r)
-        for (int c = 0; c < d; ++c)
-          kap[r][c] = in.diffusion.c[r * d + c];
-    } else {
-      const double s = unit_coefficient ? 1. : in.diffusion.c[0];
-      for (int r = 0; r < d; ++r)
-        kap[r][r] = s;
-    }
-  }
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < n; ++j) {
-      double v = 0.;
-      if (in.kind == GDTB_INT_LAPLACE) {
-        // v_ij = sum_{r,s} kappa_rs d_s phi_j d_r phi_i (laplace.hh:101), gradients scaled by 1/h (default.hh:167-174)
-        for (int r = 0; r < d; ++r)
-          for (int s = 0; s < d; ++s) {
-            if (kap[r][s] == 0.)
-              continue;
-            double prod = kap[r][s] * ie / (h[r] * h[s]);
-            for (int k = 0; k < d; ++k)
-              prod *= tab.G[k == r ? 1 : 0][k == s ? 1 : 0][(i >> k) & 1][(j >> k) & 1];
-            v += prod;
-          }
-      } else {
-        double prod = (unit_coefficient ? 1. : in.diffusion.c[0]) * ie;
-        for (int k = 0; k < d; ++k)
-          prod *= tab.G[0][0][(i >> k) & 1][(j >> k) & 1];
-        v = prod;
-      }
-      Lref[i][j] = v;
-    }
-}
-
-void add_to_T(double T[8][8], const double Lref[8][8], double scale, int d)
-{
-  const int n = 1 << d;
+  std::memset(M, 0, sizeof(double) * 9 * 64);
   for (int o = 0; o < n; ++o) {
     const int i = (n - 1) ^ o; // a_k = 1 - o_k
-    for (int s = 0; s < n; ++s)
-      T[o][s] += scale * Lref[i][s];
+    for (int j = 0; j < n; ++j) {
+      if (kind == Q1G_MASS) {
+        double prod = 1.;
+        for (int k = 0; k < d; ++k)
+          prod *= tab.G[0][0][(i >> k) & 1][(j >> k) & 1];
+        M[0][o][j] = prod;
+        continue;
+      }
+      // v_ij = sum_{r,c} kappa_rc d_c phi_j d_r phi_i (laplace.hh:98-101)
+      for (int r = 0; r < d; ++r)
+        for (int c = 0; c < d; ++c) {
+          if (kind == Q1G_LAPLACE_SCALAR && r != c)
+            continue;
+          double prod = 1.;
+          for (int k = 0; k < d; ++k)
+            prod *= tab.G[k == r ? 1 : 0][k == c ? 1 : 0][(i >> k) & 1][(j >> k) & 1];
+          M[r * 3 + c][o][j] = prod;
+        }
+    }
   }
 }
 
@@ -545,17 +519,23 @@ int build_q1_params(gdtb_matop* op, gdtb_vecfun* fun, Q1GatherParams& p)
       q1_tables(form_quadrature_order(lf.form, 1, ROLE_ELEMENT), tab);
       for (int t = 0; t < lf.form.n_terms; ++t) {
         const gdtb_integrand& in = lf.form.terms[t];
-        double Lref[8][8];
-        if (in.diffusion.kind == GDTB_FN_ELEM_SCALAR) {
-          q1_reference_tensor(in, d, g.h, tab, true, Lref);
-          add_to_T(p.T_elem[p.n_elem], Lref, lf.form.scaling, d);
-          p.coef[p.n_elem] = in.diffusion.data;
-          p.n_elem++;
-        } else {
-          q1_reference_tensor(in, d, g.h, tab, false, Lref);
-          add_to_T(p.T_const, Lref, lf.form.scaling, d);
-          p.has_const = 1;
-        }
+        Q1Group& G = p.group[p.n_groups++];
+        const gdtb_function& f = in.diffusion;
+        G.scale = lf.form.scaling;
+        G.coef = f.data;
+        if (in.kind == GDTB_INT_PRODUCT)
+          G.kind = Q1G_MASS;
+        else
+          G.kind = (f.kind == GDTB_FN_CONST_TENSOR || f.kind == GDTB_FN_ELEM_TENSOR) ? Q1G_LAPLACE_TENSOR
+                                                                                   : Q1G_LAPLACE_SCALAR;
+        G.coef_elem = (f.kind == GDTB_FN_ELEM_SCALAR || f.kind == GDTB_FN_ELEM_TENSOR) ? 1 : 0;
+        if (f.kind == GDTB_FN_CONST_SCALAR)
+          G.scale *= f.c[0];
+        if (f.kind == GDTB_FN_CONST_TENSOR)
+          for (int r = 0; r < d; ++r)
+            for (int c = 0; c < d; ++c)
+              G.kappa[r * 3 + c] = f.c[r * d + c];
+        q1_group_tensors(G.kind, d, tab, G.M);
       }
     }
   }
@@ -1300,27 +1280,32 @@ static int q1_rhs_params(gdtb_vecfun* fun, Q1GatherParams& p)
 {
   const GridDev& g = fun->grid;
   const int d = g.d;
-  double ie = 1.;
-  for (int k = 0; k < d; ++k)
-    ie *= g.h[k];
+  const int n = 1 << d;
   p.has_rhs = 1;
   for (const auto& lf : fun->forms) {
     const gdtb_integrand& in = lf.form.terms[0];
     Q1Tables tab;
     q1_tables(form_quadrature_order(lf.form, 1, ROLE_RHS), tab);
     const double w = in.diffusion.c[0];
-    double s = 1.;
-    for (int k = 0; k < d; ++k)
-      s *= tab.s1[0]; // = 1/2 for either local index by symmetry of the rule
+    // S[o] = prod_k sum_q w_q phihat_{a_k}(x_q), a_k = 1 - o_k: the reference-element part of
+    // l_i = sum_q (w psi_i f) |det J| w_q (conversion.hh:109-116, local/functionals/integrals.hh:95-96) for constant f
+    double S[8];
+    for (int o = 0; o < n; ++o) {
+      S[o] = 1.;
+      for (int k = 0; k < d; ++k)
+        S[o] *= tab.s1[1 - ((o >> k) & 1)];
+    }
     if (in.weight.kind == GDTB_FN_CONST_SCALAR) {
       p.rhs_has_const = 1;
-      p.rhs_const += w * in.weight.c[0] * ie * s;
+      for (int o = 0; o < n; ++o)
+        p.rhs_S_const[o] += w * in.weight.c[0] * S[o];
     } else if (in.weight.kind == GDTB_FN_ELEM_SCALAR) {
       p.rhs_has_elem = 1;
-      p.rhs_elem_scale = w * ie * s;
+      for (int o = 0; o < n; ++o)
+        p.rhs_S_elem[o] = w * S[o];
       p.rhs_elem = in.weight.data;
     } else {
-      // separable built-in: 1D tables on the device
+      // separable built-in: 1D tables on the device (they carry the cells' extents, i.e. the integration element)
       const long long stride = std::max(std::max(g.n[0], g.n[1]), g.n[2]) + 1;
       gdtb_ctx* ctx = fun->ctx;
       if (!fun->d_sep_tab)
@@ -1345,7 +1330,7 @@ static int q1_rhs_params(gdtb_vecfun* fun, Q1GatherParams& p)
       GDTB_TRY(launch_q1_rhs_tables(ctx->launch, g, fun->elem_lo, fun->elem_hi, to_dev(in.weight), tab.m, fun->d_rule,
                                     fun->d_rule + MAX_Q1D, fun->d_rule + 2 * MAX_Q1D, fun->d_sep_tab, stride));
       p.rhs_has_sep = 1;
-      p.rhs_sep_scale = w * (in.weight.builtin == GDTB_BUILTIN_COS_PRODUCT ? in.weight.p[0] : 1.) * ie;
+      p.rhs_sep_scale = w * (in.weight.builtin == GDTB_BUILTIN_COS_PRODUCT ? in.weight.p[0] : 1.);
       p.rhs_sep_tab = fun->d_sep_tab;
       p.rhs_sep_stride = stride;
     }

@@ -126,6 +126,18 @@ __host__ __device__ inline long long elem_index(const GridDev& g, const long lon
   return idx[0] + g.n[0] * (idx[1] + g.n[1] * idx[2]);
 }
 
+// origin + i * h without FMA contraction: the grid coordinates (and with them the ulp noise of the cell extents
+// upper - lower) are the ones the CPU path produces
+__host__ __device__ inline double grid_coord(double lo, double h, long long i)
+{
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(lo, __dmul_rn(double(i), h));
+#else
+  volatile double t = double(i) * h;
+  return lo + t;
+#endif
+}
+
 // AxisAlignedCubeGeometry of element idx: lower corner and extents, computed per cell from the
 // grid coordinates like YaspGrid does (upper - lower, so extents carry the same ulp noise)
 __host__ __device__ inline void cell_geometry(const GridDev& g, const long long* idx, double* lower, double* ext)
@@ -133,8 +145,8 @@ __host__ __device__ inline void cell_geometry(const GridDev& g, const long long*
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     if (k < g.d) {
-      lower[k] = g.lo[k] + double(idx[k]) * g.h[k];
-      const double upper = g.lo[k] + double(idx[k] + 1) * g.h[k];
+      lower[k] = grid_coord(g.lo[k], g.h[k], idx[k]);
+      const double upper = grid_coord(g.lo[k], g.h[k], idx[k] + 1);
       ext[k] = upper - lower[k];
     } else {
       lower[k] = 0.;

@@ -64,30 +64,48 @@ int launch_boundary_matrix(Launch& L, const GridDev& g, const SpaceDev& sp, cons
                            const int* colidx, double* values, int* error_flag);
 
 // ---- CG-Q1 row-gather assembly (assemble_q1_gather.cu) --------------------------------------------
-constexpr int Q1G_MAX_ELEM_CHANNELS = 3;
+constexpr int Q1G_MAX_GROUPS = 3;
 
-// The local matrix of an axis-aligned cell with an element-constant coefficient c is c * Lref, where Lref
-// (reference tensor) only depends on the cell's extents, the rule and the integrand.  A "channel" is one
-// such (coefficient source, Lref) pair; all constant-coefficient summands are merged into channel 0.
+enum
+{
+  Q1G_LAPLACE_SCALAR = 0, // LocalLaplaceIntegrand with kappa = c * I (constant c or one value per element)
+  Q1G_LAPLACE_TENSOR = 1, // LocalLaplaceIntegrand with a full d x d kappa (constant or one tensor per element)
+  Q1G_MASS = 2            // LocalElementProductIntegrand with a scalar weight (constant or per element)
+};
+
+// One "group" = one integrand of one appended local form.  On an affine, axis-aligned cell e with an element-wise
+// constant coefficient the quadrature sum of integrals.hh:116-132 factorises exactly into
+//   L_e[i][j] = sum_{r,c} kappa_rc(e) * (1/h_r(e)) * (1/h_c(e)) * |det J_e| * M[r][c][i][j],
+//   M[r][c][i][j] = sum_q w_q d_r phihat_i(xhat_q) d_c phihat_j(xhat_q)      (reference element, the form's own rule)
+// (mass: L_e[i][j] = w(e) * |det J_e| * sum_q w_q phihat_i phihat_j).  M is tabulated at plan time; the geometry
+// factors h_k(e), 1/h_k(e), |det J_e| and the coefficient are evaluated per element on the device, in FP64.
+struct Q1Group
+{
+  int kind;
+  int coef_elem;      // 1: coefficient array indexed by element (scalar, or d*d row-major for the tensor kind)
+  double scale;       // MatrixOperator::scaling at append time (* the constant scalar coefficient)
+  double kappa[9];    // constant tensor, row-major with leading dimension 3 (Q1G_LAPLACE_TENSOR, coef_elem == 0)
+  const double* coef; // device array
+  double M[9][8][8];  // M[r*3+c][o][s]: o = offset of the element around the vertex (test index i = (2^d-1) ^ o),
+                      // s = ansatz index; the scalar kinds only use r == c, the mass kind only M[0]
+};
+
 struct Q1GatherParams
 {
   GridDev g;
-  int has_const;                             // channel with coefficient 1
-  int n_elem;                                // channels with a per-element coefficient array
-  double T_const[8][8];                      // T[o][s] = Lref[i(o)][s], see assemble_q1_gather.cu
-  double T_elem[Q1G_MAX_ELEM_CHANNELS][8][8];
-  const double* coef[Q1G_MAX_ELEM_CHANNELS]; // device arrays indexed by element
-  // right-hand side: b[v] = rhs_const * sum_o valid(o) + sum_o rhs_elem_scale * f[e_o]
+  int n_groups;
+  Q1Group group[Q1G_MAX_GROUPS];
+  // right-hand side: b[v] = sum_o valid(o) * |det J_e| * (rhs_S_const[o] + rhs_S_elem[o] * f[e])
   //                         + rhs_sep_scale * prod_k B_k[i_k]
   int has_rhs;
   int rhs_has_const;
   int rhs_has_elem;
   int rhs_has_sep;
-  double rhs_const;          // c * ie * prod_k s1 = per (vertex, element) contribution of a constant source
-  double rhs_elem_scale;     // ie * prod_k s1
+  double rhs_S_const[8];     // sum over forms of w * c * prod_k s1[a_k(o)], s1[a] = sum_q w_q phihat_a(x_q)
+  double rhs_S_elem[8];      // w * prod_k s1[a_k(o)]
   const double* rhs_elem;    // per-element source values
-  double rhs_sep_scale;      // p0 * w * ie
-  const double* rhs_sep_tab; // 3 tables B_k[i_k], k-th table at offset k * rhs_sep_stride
+  double rhs_sep_scale;      // w * p0
+  const double* rhs_sep_tab; // 3 tables B_k[i_k] (they carry the cells' extents), k-th table at offset k * stride
   long long rhs_sep_stride;
   long long value_offset; // global CSR position of this process' first row (values points at it)
   long long row_offset;   // first vertex row of this process

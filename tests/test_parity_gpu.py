@@ -138,7 +138,7 @@ def element_cases():
             ("q1-laplace-elem+mass-elem", n, 1, [laplace(D.fn_elem(rng_elem(n))), mass(D.fn_elem(rng_elem(n, seed=7)))], "q1_gather"),
             ("q1-laplace-tensor", n, 1, [laplace(D.fn_const(kt))], "q1_gather"),
             ("q1-laplace-builtin", n, 1, [laplace(D.fn_builtin(D.BUILTIN_QUADRATIC, 2, 1.0, 0.5))], "generic_coloured"),
-            ("q1-laplace-elemtensor", n, 1, [laplace(D.fn_elem(np.tile(kt, (int(np.prod(n)), 1, 1)) * rng_elem(n)[:, None, None]))], "generic_coloured"),
+            ("q1-laplace-elemtensor", n, 1, [laplace(D.fn_elem(np.tile(kt, (int(np.prod(n)), 1, 1)) * rng_elem(n)[:, None, None]))], "q1_gather"),
             ("q2-laplace-const", n, 2, [laplace(1.0)], "generic_coloured"),
             ("q2-mass-builtin", n, 2, [mass(D.fn_builtin(D.BUILTIN_AFFINE, 1, 1.0, 0.3, 0.2, 0.1))], "generic_coloured"),
             ("q2-laplace-elem+mass", n, 2, [D.form([D.integrand(D.INT_LAPLACE, diffusion=D.fn_elem(rng_elem(n))), D.integrand(D.INT_PRODUCT, diffusion=2.0)])], "generic_coloured"),
