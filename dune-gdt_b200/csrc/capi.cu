@@ -193,8 +193,10 @@ struct gdtb_fvop
   double* d_tmp; // ping-pong buffer for the Euler loop
   double* d_src; // staging for the *_host entry points
   double* d_dst;
-  double* d_ext; // per-axis cell extents, axis k at d_ext + ext_offset[k]
+  double* d_ext; // per-axis cell extents, axis k at d_ext + ext_offset[k]; reciprocals inv_ext_shift further on
   long long ext_offset[3];
+  long long inv_ext_shift;
+  int rows_per_block; // tuning knob of the marching kernel (0 = automatic), GDTB_FV_ROWS in the environment
 };
 
 namespace {
@@ -1446,6 +1448,9 @@ int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* fl
   L->flux = *flux;
   L->ghosted = false;
   L->d_tmp = L->d_src = L->d_dst = L->d_ext = nullptr;
+  L->rows_per_block = 0;
+  if (const char* env = std::getenv("GDTB_FV_ROWS"))
+    L->rows_per_block = std::atoi(env);
   // cell extents per axis, exactly as YaspGrid's EquidistantOffsetCoordinates produce them: upper - lower with
   // lower = origin + i * h, upper = origin + (i + 1) * h [EXT]
   std::vector<double> ext;
@@ -1457,6 +1462,10 @@ int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* fl
       ext.push_back(k < L->grid.d ? upper - lower : 1.);
     }
   }
+  // ... followed by the reciprocals 1 / ext, same layout
+  L->inv_ext_shift = (long long)ext.size();
+  for (long long i = 0; i < L->inv_ext_shift; ++i)
+    ext.push_back(1. / ext[(size_t)i]);
   if (cudaMalloc(&L->d_ext, sizeof(double) * ext.size()) != cudaSuccess
       || cudaMemcpy(L->d_ext, ext.data(), sizeof(double) * ext.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaFree(L->d_ext);
@@ -1477,8 +1486,11 @@ static void fv_fill_params(const gdtb_fvop* L, FvParams& p)
   p.lf_lambda_linear = 0.;
   for (int k = 0; k < L->grid.d; ++k)
     p.lf_lambda_linear = std::max(p.lf_lambda_linear, std::fabs(L->flux.p[k]));
-  for (int k = 0; k < 3; ++k)
+  for (int k = 0; k < 3; ++k) {
     p.ext[k] = L->d_ext + L->ext_offset[k];
+    p.inv_ext[k] = L->d_ext + L->inv_ext_shift + L->ext_offset[k];
+  }
+  p.rows_per_block = L->rows_per_block;
 }
 
 int gdtb_fvop_destroy(gdtb_fvop* L)

@@ -172,6 +172,199 @@ __global__ void __launch_bounds__(256) k_fv_apply(const __grid_constant__ FvPara
   out[loc] = p.euler ? ue - acc * p.dt : acc; // u_n - L(u_n) * dt (examples/mpi_2019_02...cc:154)
 }
 
+// Flux through the face between the cells L (lower index along axis k) and U = L + 1 (or U = 0, L = n_k - 1 for a
+// periodic wrap face), measured along +e_k.  In the reference the inside element is the one with the smaller index
+// (ApplyOn::InnerIntersectionsOnce / PeriodicBoundaryIntersectionsOnce) and the flux is evaluated with its outer
+// normal: +e_k for an inner face (inside = L), -e_k for the wrap face (inside = U = cell 0).  Written out for both
+// orientations the upwind flux (upwind.hh:67-72) along +e_k is f_k(u_L) if f_k'(ubar) > 0 and f_k(u_U) if
+// f_k'(ubar) < 0 for either orientation.  Only the tie f_k'(ubar) == 0 depends on who is inside, and for the two flux
+// families here the tie does not matter: a_k == 0 makes both candidates a_k u = 0, and ubar == 0 means
+// u_L = -u_U, i.e. u_L^2 / 2 == u_U^2 / 2.  The Lax-Friedrichs flux (lax-friedrichs.hh:70-87) is orientation
+// independent.  Hence one formula serves inner and wrap faces.
+template <int NUMFLUX, int KIND>
+__device__ __forceinline__ double flux_plus(const FvParams& p, int k, double uL, double uU)
+{
+  if (NUMFLUX == GDTB_NUMFLUX_UPWIND) {
+    if (KIND == GDTB_FLUX_LINEAR) {
+      const double a = p.flux.p[k];
+      return a * (a > 0. ? uL : uU);
+    }
+    const double w = (uL + uU) > 0. ? uL : uU; // sign of ubar = (u + v) / 2
+    return 0.5 * w * w;
+  }
+  if (KIND == GDTB_FLUX_LINEAR)
+    return (p.flux.p[k] * uL + p.flux.p[k] * uU) * 0.5 + (uL - uU) * (0.5 * p.lf_lambda_linear);
+  return (0.5 * uL * uL + 0.5 * uU * uU) * 0.5 + (uL - uU) * (0.5 * fmax(fabs(uL), fabs(uU)));
+}
+
+constexpr int FV_BATCH = 4;
+
+template <int C>
+__device__ __forceinline__ void ldg_cols(const double* q, double (&v)[C])
+{
+  if (C == 2) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(q));
+    v[0] = t.x;
+    v[C - 1] = t.y;
+  } else
+    v[0] = __ldg(q);
+}
+
+template <int C>
+__device__ __forceinline__ void st_cols(double* q, const double (&v)[C])
+{
+  if (C == 2)
+    *reinterpret_cast<double2*>(q) = make_double2(v[0], v[C - 1]);
+  else
+    *q = v[0];
+}
+
+// D >= 2: the thread block covers a tile of the first D-1 axes (x: 2D, x-y: 3D) and marches along the last axis
+// over `rows` layers; a thread owns C adjacent cells in x (C = 2: 16-byte loads and stores).  The layers u[j], u[j+1]
+// of a thread's cells live in registers, so every value of u is read from L2/HBM once per tile (plus the two halo
+// layers); the neighbours along the tile axes are read through L1.  The flux through the upper face of layer j is
+// reused as the lower-face flux of layer j+1, the flux between the thread's two cells is shared.  Every cell sums
+// (G_up - G_low) / ext_k over its axes, G = flux along +e_k through the face (flux_plus); (g |I|) (1/|E|) of
+// advection-fv.hh:147-152 equals g / ext_k on axis-aligned cells up to rounding.  Faces that do not exist (domain
+// boundary without periodicity) get the coefficient 0.  Loads are issued FV_BATCH layers at a time before the first
+// flux of the batch is evaluated (memory-level parallelism).
+template <int D, int NUMFLUX, int KIND, int C>
+__global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvParams p, const double* __restrict__ u,
+                                                  double* __restrict__ out, int rows)
+{
+  static_assert(D == 2 || D == 3, "marching kernel is for 2D / 3D grids");
+  const GridDev& g = p.g;
+  constexpr int last = D - 1;
+  constexpr int R = FV_BATCH;
+  const int n0 = (int)g.n[0], n1 = (int)g.n[1], nl = (int)g.n[last];
+  const int layer_lo = (int)g.layer_lo, layer_hi = (int)g.layer_hi;
+  const int ix = (blockIdx.x * blockDim.x + threadIdx.x) * C; // first of the thread's cells
+  const int iy = D == 3 ? blockIdx.y * blockDim.y + threadIdx.y : 0;
+  if (ix >= n0 || (D == 3 && iy >= n1))
+    return;
+  const long long plane = D == 3 ? (long long)n0 * n1 : n0; // cells per layer
+  const long long col = D == 3 ? (long long)iy * n0 + ix : ix;
+  const int j0 = layer_lo + (int)(D == 3 ? blockIdx.z : blockIdx.y) * rows;
+  const int j1 = min(j0 + rows, layer_hi);
+  if (j0 >= j1)
+    return;
+  // local layer index of global layer j: j - layer_lo (+1 ghost layer below on a slab)
+  const int shift = p.ghosted ? 1 - layer_lo : -layer_lo;
+
+  // tile axes: offsets to the neighbour cells (periodic wrap, or 0 = the cell itself where there is no face) and
+  // the face coefficients 1 / ext (0 where there is no face)
+  const bool per0 = (g.periodic & 1) && n0 > 1, per1 = D == 3 && (g.periodic & 2) && n1 > 1;
+  const bool perl = (g.periodic & (1 << last)) && nl > 1;
+  const bool x_lo_edge = ix == 0, x_hi_edge = ix + C - 1 == n0 - 1;
+  const bool x_lo = !x_lo_edge || per0, x_hi = !x_hi_edge || per0;
+  const int d_xm = x_lo ? (x_lo_edge ? n0 - 1 : -1) : 0;              // relative to the first cell
+  const int d_xp = C - 1 + (x_hi ? (x_hi_edge ? 1 - n0 : 1) : 0);    // relative to the first cell
+  double rx[C];
+  ldg_cols<C>(p.inv_ext[0] + ix, rx);
+  const double cxl = x_lo ? rx[0] : 0., cxh = x_hi ? rx[C - 1] : 0.;
+  long long d_ym = 0, d_yp = 0;
+  double cyl = 0., cyh = 0.;
+  if (D == 3) {
+    const bool y_lo_edge = iy == 0, y_hi_edge = iy == n1 - 1;
+    const bool y_lo = !y_lo_edge || per1, y_hi = !y_hi_edge || per1;
+    d_ym = y_lo ? (y_lo_edge ? (long long)(n1 - 1) * n0 : -(long long)n0) : 0;
+    d_yp = y_hi ? (y_hi_edge ? -(long long)(n1 - 1) * n0 : (long long)n0) : 0;
+    const double ry = __ldg(p.inv_ext[1] + iy);
+    cyl = y_lo ? ry : 0.;
+    cyh = y_hi ? ry : 0.;
+  }
+
+  const double* pc = u + (long long)(j0 + shift) * plane + col; // own cells, layer j
+  double* po = out + (long long)(j0 + shift) * plane + col;
+  const double* prl = p.inv_ext[last] + j0;
+  double uc[C], G_low[C];
+  ldg_cols<C>(pc, uc);
+  // flux through the lower face of the first layer (on a slab the ghost layer below carries the neighbour); 0 if
+  // there is no face
+  {
+    const bool has = j0 > 0 || perl;
+    const long long off = (j0 > 0 || p.ghosted) ? -plane : (has ? (long long)(nl - 1) * plane : 0);
+    double ub[C];
+    ldg_cols<C>(pc + off, ub);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      G_low[c] = has ? flux_plus<NUMFLUX, KIND>(p, last, ub[c], uc[c]) : 0.;
+  }
+  // layers whose upper neighbour is simply the next layer in memory: all but the top layer of an unpartitioned grid
+  const int j_plain = p.ghosted ? j1 : min(j1, nl - 1);
+  int jb = j0;
+  for (; jb + R <= j_plain; jb += R) {
+    double un[R][C], xl[R], xr[R], yl[R][C], yr[R][C], rl[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double* q = pc + (long long)r * plane;
+      ldg_cols<C>(q + plane, un[r]);
+      xl[r] = __ldg(q + d_xm);
+      xr[r] = __ldg(q + d_xp);
+      if (D == 3) {
+        ldg_cols<C>(q + d_ym, yl[r]);
+        ldg_cols<C>(q + d_yp, yr[r]);
+      }
+      rl[r] = __ldg(prl + r);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double res[C], gx[C + 1];
+      gx[0] = flux_plus<NUMFLUX, KIND>(p, 0, xl[r], uc[0]);
+      if (C == 2)
+        gx[1] = flux_plus<NUMFLUX, KIND>(p, 0, uc[0], uc[C - 1]);
+      gx[C] = flux_plus<NUMFLUX, KIND>(p, 0, uc[C - 1], xr[r]);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const double G_up = flux_plus<NUMFLUX, KIND>(p, last, uc[c], un[r][c]);
+        // faces between the thread's own cells always exist; the outer ones carry the (possibly zero) coefficient
+        double acc = gx[c + 1] * (c == C - 1 ? cxh : rx[c]) - gx[c] * (c == 0 ? cxl : rx[c]);
+        if (D == 3)
+          acc += flux_plus<NUMFLUX, KIND>(p, 1, uc[c], yr[r][c]) * cyh - flux_plus<NUMFLUX, KIND>(p, 1, yl[r][c], uc[c]) * cyl;
+        acc += (G_up - G_low[c]) * rl[r];
+        res[c] = p.euler ? uc[c] - acc * p.dt : acc; // u_n - L(u_n) dt (examples/mpi...cc:154)
+        G_low[c] = G_up;
+        uc[c] = un[r][c];
+      }
+      st_cols<C>(po + (long long)r * plane, res);
+    }
+    pc += (long long)R * plane;
+    po += (long long)R * plane;
+    prl += R;
+  }
+  // remaining layers one at a time (batch tail and the top layer of the grid: periodic wrap or no upper face)
+  for (int j = jb; j < j1; ++j) {
+    const bool top = !p.ghosted && j == nl - 1;
+    const bool has_up = !top || perl;
+    double un[C], yl[C], yr[C], res[C], gx[C + 1];
+    ldg_cols<C>(pc + (top ? (has_up ? (1 - (long long)nl) * plane : 0) : plane), un);
+    gx[0] = flux_plus<NUMFLUX, KIND>(p, 0, __ldg(pc + d_xm), uc[0]);
+    if (C == 2)
+      gx[1] = flux_plus<NUMFLUX, KIND>(p, 0, uc[0], uc[C - 1]);
+    gx[C] = flux_plus<NUMFLUX, KIND>(p, 0, uc[C - 1], __ldg(pc + d_xp));
+    if (D == 3) {
+      ldg_cols<C>(pc + d_ym, yl);
+      ldg_cols<C>(pc + d_yp, yr);
+    }
+    const double rl = __ldg(prl);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const double G_up = has_up ? flux_plus<NUMFLUX, KIND>(p, last, uc[c], un[c]) : 0.;
+      double acc = gx[c + 1] * (c == C - 1 ? cxh : rx[c]) - gx[c] * (c == 0 ? cxl : rx[c]);
+      if (D == 3)
+        acc += flux_plus<NUMFLUX, KIND>(p, 1, uc[c], yr[c]) * cyh - flux_plus<NUMFLUX, KIND>(p, 1, yl[c], uc[c]) * cyl;
+      acc += (G_up - G_low[c]) * rl;
+      res[c] = p.euler ? uc[c] - acc * p.dt : acc;
+      G_low[c] = G_up;
+      uc[c] = un[c];
+    }
+    st_cols<C>(po, res);
+    pc += plane;
+    po += plane;
+    prl += 1;
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(256) k_fv_interpolate(const GridDev g, const FnDev f, int m,
                                                         const double* __restrict__ qx, const double* __restrict__ qw,
@@ -207,27 +400,68 @@ __global__ void __launch_bounds__(256) k_fv_interpolate(const GridDev g, const F
 
 } // namespace
 
+template <int D, int C>
+static void launch_fv_march(const FvParams& p, const double* u, double* out, int rows, dim3 grid, dim3 block,
+                            cudaStream_t stream)
+{
+  const int variant = (p.flux.numflux == GDTB_NUMFLUX_LAX_FRIEDRICHS ? 2 : 0) + (p.flux.kind == GDTB_FLUX_BURGERS ? 1 : 0);
+  switch (variant) {
+    case 0: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 1: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 2: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    default: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+  }
+}
+
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
 {
   const GridDev& g = p.g;
   const long long layers = g.layer_hi - g.layer_lo;
-  const int block = 256;
-  dim3 grid(1, 1, 1);
-  if (g.d == 1)
-    grid.x = (unsigned)((layers + block - 1) / block);
-  else {
-    grid.x = (unsigned)((g.n[0] + block - 1) / block);
-    grid.y = (unsigned)(g.d == 2 ? layers : g.n[1]);
-    grid.z = (unsigned)(g.d == 3 ? layers : 1);
-    if (grid.y > 65535 || grid.z > 65535)
-      return fail(GDTB_ERR_NOT_IMPLEMENTED, "fv: more than 65535 cells in the second / third direction");
-  }
   time_begin(L, KF_FV_APPLY);
-  switch (g.d) {
-    case 1: k_fv_apply<1><<<grid, block, 0, L.stream>>>(p, u, out); break;
-    case 2: k_fv_apply<2><<<grid, block, 0, L.stream>>>(p, u, out); break;
-    case 3: k_fv_apply<3><<<grid, block, 0, L.stream>>>(p, u, out); break;
-    default: return fail(GDTB_ERR_INVALID_ARGUMENT, "fv: dimension must be 1, 2 or 3");
+  if (g.d == 1) {
+    const int block = 256;
+    k_fv_apply<1><<<(unsigned)((layers + block - 1) / block), block, 0, L.stream>>>(p, u, out);
+  } else {
+    // two cells per thread (16-byte accesses) when every row starts 16-byte aligned
+    const bool two = g.n[0] % 2 == 0 && ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(out)) & 15) == 0
+                     && (reinterpret_cast<uintptr_t>(p.inv_ext[0]) & 15) == 0;
+    const long long nx = two ? g.n[0] / 2 : g.n[0]; // threads along x
+    dim3 block(1, 1, 1), grid(1, 1, 1);
+    long long tiles;
+    if (g.d == 2) {
+      block.x = (unsigned)std::min<long long>(128, ((nx + 31) / 32) * 32);
+      grid.x = (unsigned)((nx + block.x - 1) / block.x);
+      tiles = grid.x;
+    } else {
+      block.x = (unsigned)std::min<long long>(32, ((nx + 31) / 32) * 32);
+      block.y = 128 / block.x;
+      grid.x = (unsigned)((nx + block.x - 1) / block.x);
+      grid.y = (unsigned)((g.n[1] + block.y - 1) / block.y);
+      tiles = (long long)grid.x * grid.y;
+    }
+    // layers per block along the marching axis: long enough to amortise the two halo layers, short enough for a few
+    // waves of blocks over the SMs
+    int rows = p.rows_per_block;
+    if (rows <= 0) {
+      const long long want = (long long)L.sm_count * 8 * 4;
+      rows = (int)std::max<long long>(8, std::min<long long>(64, layers * tiles / want));
+    }
+    rows = (rows + FV_BATCH - 1) / FV_BATCH * FV_BATCH; // whole register batches
+    const long long chunks = (layers + rows - 1) / rows;
+    if (chunks > 65535)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "fv: too many layers along the last direction");
+    (g.d == 2 ? grid.y : grid.z) = (unsigned)chunks;
+    if (g.d == 2) {
+      if (two)
+        launch_fv_march<2, 2>(p, u, out, rows, grid, block, L.stream);
+      else
+        launch_fv_march<2, 1>(p, u, out, rows, grid, block, L.stream);
+    } else {
+      if (two)
+        launch_fv_march<3, 2>(p, u, out, rows, grid, block, L.stream);
+      else
+        launch_fv_march<3, 1>(p, u, out, rows, grid, block, L.stream);
+    }
   }
   time_end(L, KF_FV_APPLY);
   L.count++;

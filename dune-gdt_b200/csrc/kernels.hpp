@@ -137,7 +137,9 @@ struct FvParams
   int euler;    // 1: out = u - dt * L(u), 0: out = L(u)
   double dt;
   double lf_lambda_linear; // max_k |a_k| of a linear flux (1 / lambda of the Lax-Friedrichs flux)
-  const double* ext[3];    // per-axis cell extents (device)
+  const double* ext[3];     // per-axis cell extents (device)
+  const double* inv_ext[3]; // 1 / ext
+  int rows_per_block;       // marching kernel: layers per thread block (0 = choose)
 };
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out);
 int launch_fv_interpolate(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx, const double* qw,
