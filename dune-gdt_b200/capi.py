@@ -135,6 +135,7 @@ PROTOTYPES = {
     "gdtb_fvop_set_slab": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gdtb_fvop_ghost_layer_size": (C.c_int64, [_P]),
     "gdtb_fv_interpolate": (C.c_int, [_P, _P, C.POINTER(Function), _P]),
+    "gdtb_fv_interpolate_host": (C.c_int, [_P, _P, C.POINTER(Function), _DP]),
 }
 
 _lib = None

@@ -1650,4 +1650,26 @@ int gdtb_fv_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_funct
   return GDTB_OK;
 }
 
+int gdtb_fv_interpolate_host(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* u)
+{
+  if (!space || !f || !u)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fv_interpolate_host: NULL argument");
+  GDTB_TRY(check_ctx(ctx));
+  GDTB_TRY(validate_function(*f, "function"));
+  const size_t n = (size_t)space->dev.size;
+  double* d_u = nullptr;
+  if (cudaMalloc(&d_u, sizeof(double) * std::max<size_t>(n, 1)) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory");
+  LoweredForm owner; // owns the device clone of per-element host data
+  gdtb_function fd = *f;
+  int st = lower_function(ctx, space->grid, fd, owner);
+  if (st == GDTB_OK)
+    st = gdtb_fv_interpolate(ctx, space, &fd, d_u);
+  if (st == GDTB_OK && cudaMemcpy(u, d_u, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    st = fail(GDTB_ERR_CUDA, "gdtb_fv_interpolate_host: copy to host failed");
+  free_form(owner);
+  cudaFree(d_u);
+  return st;
+}
+
 } // extern "C"

@@ -19,6 +19,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <exception>
+#include <functional>
 #include <memory>
 #include <sstream>
 #include <string>
@@ -1611,6 +1612,16 @@ AdvectionFvOperator<M, GV> make_advection_fv_operator(const GV& assembly_grid_vi
                                                       const SpaceInterface<GV>& range_space)
 {
   return AdvectionFvOperator<M, GV>(assembly_grid_view, numerical_flux, source_space, range_space);
+}
+
+// default_interpolation<V>(order, f, fv_space) (interpolations/default.hh:76-83): the FV "interpolation" is the cell
+// average by a Gauss rule of the declared order (spaces/basis/finite-volume.hh:244-252); `f` carries its order
+template <class V, class GV>
+V default_interpolation(const XT::Functions::GridFunction<typename GV::Element>& f, const SpaceInterface<GV>& fv_space)
+{
+  V u(std::size_t(fv_space.mapper().size()), 0.);
+  internal::check(gdtb_fv_interpolate_host(internal::context(), fv_space.handle(), &f.descriptor(), u.data()));
+  return u;
 }
 
 // explicit_euler of examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:141-159, run on the device:

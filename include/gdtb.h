@@ -313,6 +313,8 @@ int64_t gdtb_fvop_ghost_layer_size(const gdtb_fvop* L);
 
 /* default_interpolation(order, f, fv_space) (interpolations/default.hh:76-83, spaces/basis/finite-volume.hh:244-252) */
 int gdtb_fv_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* d_u);
+/* same with a host result buffer of gdtb_space_size doubles (per-element function data may live on the host) */
+int gdtb_fv_interpolate_host(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* u);
 
 /* ---- multi-GPU assembly ----------------------------------------------------------------------- */
 /* Element-block partition: this process owns the element layers [begin, end) along the last direction and, owner-

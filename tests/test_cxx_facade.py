@@ -1,0 +1,43 @@
+"""The C++ facade (dune-gdt_b200/include/dune/gdt/b200.hh): drivers written with dune-gdt's own class / function names
+compile against the C ABI with the host compiler alone, and (on a GPU box) reproduce size-independent properties."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXAMPLES = os.path.join(ROOT, "dune-gdt_b200", "examples")
+PROGS = ["stationary-heat-equation", "linear-transport-fv"]
+
+
+def build_examples():
+    subprocess.check_call(["make", "-C", EXAMPLES], stdout=subprocess.DEVNULL)
+
+
+def test_examples_compile_against_the_c_abi(gdt):
+    build_examples()
+    for prog in PROGS:
+        path = os.path.join(EXAMPLES, prog)
+        assert os.access(path, os.X_OK)
+        needed = subprocess.check_output(["readelf", "-d", path], text=True)
+        assert "libgdtb.so" in needed  # the drivers go through the C ABI, nothing else
+
+
+def test_examples_fail_loudly_without_a_gpu(gdt):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("only meaningful on a box without a GPU")
+    build_examples()
+    r = subprocess.run([os.path.join(EXAMPLES, PROGS[0]), "8"], capture_output=True, text=True)
+    assert r.returncode != 0 and "DUNE reported error" in r.stderr  # Exceptions::device_error, no CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [["stationary-heat-equation", "128", "2"], ["stationary-heat-equation", "48", "3"],
+                                  ["linear-transport-fv", "1024"]])
+def test_examples_run(gdt, args):
+    build_examples()
+    r = subprocess.run([os.path.join(EXAMPLES, args[0])] + args[1:], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("OK")
