@@ -134,6 +134,7 @@ PROTOTYPES = {
     "gdtb_fvop_euler_host": (C.c_int, [_P, _DP, C.c_double, C.c_int64]),
     "gdtb_fvop_set_slab": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gdtb_fvop_ghost_layer_size": (C.c_int64, [_P]),
+    "gdtb_fvop_step_async": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, C.c_int64, C.c_int64]),
     "gdtb_fv_interpolate": (C.c_int, [_P, _P, C.POINTER(Function), _P]),
     "gdtb_fv_interpolate_host": (C.c_int, [_P, _P, C.POINTER(Function), _DP]),
 }

@@ -1491,6 +1491,8 @@ static void fv_fill_params(const gdtb_fvop* L, FvParams& p)
     p.inv_ext[k] = L->d_ext + L->inv_ext_shift + L->ext_offset[k];
   }
   p.rows_per_block = L->rows_per_block;
+  p.apply_lo = L->grid.layer_lo;
+  p.apply_hi = L->grid.layer_hi;
 }
 
 int gdtb_fvop_destroy(gdtb_fvop* L)
@@ -1547,6 +1549,25 @@ int gdtb_fvop_apply(gdtb_fvop* L, const double* d_source, double* d_range)
   GDTB_TRY(launch_fv_apply(L->ctx->launch, p, d_source, d_range));
   GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
   return GDTB_OK;
+}
+
+int gdtb_fvop_step_async(gdtb_fvop* L, const double* d_source, double* d_range, int euler, double dt,
+                         int64_t layer_begin, int64_t layer_end)
+{
+  if (!L || !d_source || !d_range)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_step_async: NULL argument");
+  GDTB_TRY(check_ctx(L->ctx));
+  FvParams p;
+  fv_fill_params(L, p);
+  if (layer_begin != 0 || layer_end != 0) {
+    if (layer_begin < L->grid.layer_lo || layer_end > L->grid.layer_hi || layer_begin > layer_end)
+      return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_step_async: layers must lie inside the operator's slab");
+    p.apply_lo = layer_begin;
+    p.apply_hi = layer_end;
+  }
+  p.euler = euler ? 1 : 0;
+  p.dt = dt;
+  return launch_fv_apply(L->ctx->launch, p, d_source, d_range);
 }
 
 static int fv_stage(gdtb_fvop* L)

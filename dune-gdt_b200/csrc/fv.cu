@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(256) k_fv_apply(const __grid_constant__ FvPara
   idx[1] = D > 1 ? (int)blockIdx.y : 0;
   idx[2] = D > 2 ? (int)blockIdx.z : 0;
   if (D == 1)
-    idx[0] += layer_lo;
-  if (idx[0] >= (D == 1 ? (int)g.layer_hi : n0))
+    idx[0] += (int)p.apply_lo;
+  if (idx[0] >= (D == 1 ? (int)p.apply_hi : n0))
     return;
   idx[last] += (D == 1) ? 0 : layer_lo; // global coordinate along the partitioned direction
   const int n[3] = {n0, n1, n2};
@@ -237,15 +237,15 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
   constexpr int last = D - 1;
   constexpr int R = FV_BATCH;
   const int n0 = (int)g.n[0], n1 = (int)g.n[1], nl = (int)g.n[last];
-  const int layer_lo = (int)g.layer_lo, layer_hi = (int)g.layer_hi;
+  const int layer_lo = (int)g.layer_lo;
   const int ix = (blockIdx.x * blockDim.x + threadIdx.x) * C; // first of the thread's cells
   const int iy = D == 3 ? blockIdx.y * blockDim.y + threadIdx.y : 0;
   if (ix >= n0 || (D == 3 && iy >= n1))
     return;
   const long long plane = D == 3 ? (long long)n0 * n1 : n0; // cells per layer
   const long long col = D == 3 ? (long long)iy * n0 + ix : ix;
-  const int j0 = layer_lo + (int)(D == 3 ? blockIdx.z : blockIdx.y) * rows;
-  const int j1 = min(j0 + rows, layer_hi);
+  const int j0 = (int)p.apply_lo + (int)(D == 3 ? blockIdx.z : blockIdx.y) * rows;
+  const int j1 = min(j0 + rows, (int)p.apply_hi);
   if (j0 >= j1)
     return;
   // local layer index of global layer j: j - layer_lo (+1 ghost layer below on a slab)
@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
       G_low[c] = has ? flux_plus<NUMFLUX, KIND>(p, last, ub[c], uc[c]) : 0.;
   }
   // layers whose upper neighbour is simply the next layer in memory: all but the top layer of an unpartitioned grid
-  const int j_plain = p.ghosted ? j1 : min(j1, nl - 1);
+  // (on a slab the ghost layer above carries the periodic neighbour; without periodicity the top face does not exist)
+  const int j_plain = (p.ghosted && perl) ? j1 : min(j1, nl - 1);
   int jb = j0;
   for (; jb + R <= j_plain; jb += R) {
     double un[R][C], xl[R], xr[R], yl[R][C], yr[R][C], rl[R];
@@ -334,10 +335,10 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
   }
   // remaining layers one at a time (batch tail and the top layer of the grid: periodic wrap or no upper face)
   for (int j = jb; j < j1; ++j) {
-    const bool top = !p.ghosted && j == nl - 1;
+    const bool top = j == nl - 1;
     const bool has_up = !top || perl;
     double un[C], yl[C], yr[C], res[C], gx[C + 1];
-    ldg_cols<C>(pc + (top ? (has_up ? (1 - (long long)nl) * plane : 0) : plane), un);
+    ldg_cols<C>(pc + ((top && !p.ghosted) ? (has_up ? (1 - (long long)nl) * plane : 0) : plane), un);
     gx[0] = flux_plus<NUMFLUX, KIND>(p, 0, __ldg(pc + d_xm), uc[0]);
     if (C == 2)
       gx[1] = flux_plus<NUMFLUX, KIND>(p, 0, uc[0], uc[C - 1]);
@@ -416,7 +417,9 @@ static void launch_fv_march(const FvParams& p, const double* u, double* out, int
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
 {
   const GridDev& g = p.g;
-  const long long layers = g.layer_hi - g.layer_lo;
+  const long long layers = p.apply_hi - p.apply_lo;
+  if (layers <= 0)
+    return GDTB_OK;
   time_begin(L, KF_FV_APPLY);
   if (g.d == 1) {
     const int block = 256;

@@ -140,6 +140,9 @@ struct FvParams
   const double* ext[3];     // per-axis cell extents (device)
   const double* inv_ext[3]; // 1 / ext
   int rows_per_block;       // marching kernel: layers per thread block (0 = choose)
+  // layers [apply_lo, apply_hi) of the slab [g.layer_lo, g.layer_hi) to produce in this launch (overlap of the
+  // interior with the ghost-layer exchange); the memory layout always follows the slab
+  long long apply_lo, apply_hi;
 };
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out);
 int launch_fv_interpolate(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx, const double* qw,

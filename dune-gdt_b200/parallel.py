@@ -1,0 +1,195 @@
+"""One process per GPU: element-slab partition of the structured grid and the ghost-layer exchange of the FV path.
+
+Reference: the only halo site of this path is the stage-vector exchange of the explicit Runge-Kutta stepper
+(dune/gdt/tools/timestepper/explicit-rungekutta.hh:252-257, a DUNE `communicate()` with a data handle on an overlapping
+YaspGrid).  Here the grid is cut into slabs of element layers along the LAST direction; a rank's FV vector is
+[ghost layer below | owned layers | ghost layer above] and before every operator apply the first / last owned layer
+travels to the neighbours' ghost layers (periodic wrap: rank 0 <-> rank N-1) with grouped point-to-point messages
+(`torch.distributed` P2P: NCCL send/recv over NVLink on GPUs, gloo on CPU for the host-logic tests).
+
+Assembly needs no exchange: rows are owned by the slab that owns the vertex layer, and the one element layer below a
+slab is recomputed locally (what the reference does with YaspGrid's overlap) -- see `slab_layers` / `gdtb_matop_set_slab`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from . import descriptors as D
+
+
+def slab_layers(n_last, rank, world):
+    """element layers [begin, end) of `rank`: contiguous, sizes differ by at most one (lower ranks get the extra layer)"""
+    if world < 1 or not 0 <= rank < world:
+        raise capi.WrongInputGiven("slab_layers: need 0 <= rank < world")
+    if n_last < world:
+        raise capi.WrongInputGiven(f"cannot cut {n_last} element layers into {world} non-empty slabs")
+    base, extra = divmod(n_last, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def neighbours(rank, world, periodic_last):
+    """(rank owning the layer below my first layer, rank owning the layer above my last layer); None at a domain
+    boundary without periodicity.  With world == 1 and a periodic direction both neighbours are the rank itself."""
+    lower = rank - 1 if rank > 0 else (world - 1 if periodic_last else None)
+    upper = rank + 1 if rank < world - 1 else (0 if periodic_last else None)
+    return lower, upper
+
+
+def exchange_ghost_layers(u_local, plane, rank, world, periodic_last, group=None):
+    """fills the ghost layers of `u_local` (1D torch tensor, layout [ghost | owned | ghost], `plane` cells per layer)
+    with the neighbours' boundary layers.  Returns the list of outstanding requests (call .wait() on each)."""
+    import torch.distributed as dist
+
+    lower, upper = neighbours(rank, world, periodic_last)
+    first_owned = u_local[plane:2 * plane]
+    last_owned = u_local[-2 * plane:-plane]
+    ghost_lo = u_local[:plane]
+    ghost_hi = u_local[-plane:]
+    if world == 1:
+        if periodic_last:
+            ghost_lo.copy_(last_owned)
+            ghost_hi.copy_(first_owned)
+        return []
+    ops = []
+    # tags are not supported by NCCL P2P; message order per pair is fixed instead: "upward" messages first
+    if upper is not None:
+        ops.append(dist.P2POp(dist.isend, last_owned, upper, group))
+    if lower is not None:
+        ops.append(dist.P2POp(dist.irecv, ghost_lo, lower, group))
+    if lower is not None:
+        ops.append(dist.P2POp(dist.isend, first_owned, lower, group))
+    if upper is not None:
+        ops.append(dist.P2POp(dist.irecv, ghost_hi, upper, group))
+    if world == 2 and periodic_last:
+        # both neighbours are the same rank: keep the two message pairs apart (send/recv order must match on both sides)
+        reqs = dist.batch_isend_irecv(ops[:2])
+        for r in reqs:
+            r.wait()
+        return dist.batch_isend_irecv(ops[2:])
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+class DistributedAdvectionFvOperator:
+    """AdvectionFvOperator (dune/gdt/operators/advection-fv.hh:44-141) on the slab of this rank.
+
+    `apply` / `euler_step` work on device vectors in slab layout (torch float64 CUDA tensors of `local_size` entries).
+    The interior layers are computed while the ghost layers are in flight; the first and last owned layer follow."""
+
+    def __init__(self, numerical_flux, space, rank, world, group=None):
+        from .api import AdvectionFvOperator
+
+        self.space = space
+        self.rank, self.world, self.group = rank, world, group
+        g = space.grid.desc
+        self.dim = int(g.dim)
+        self.n_last = int(g.n[self.dim - 1])
+        self.periodic_last = bool(g.periodic & (1 << (self.dim - 1))) and self.n_last > 1
+        self.begin, self.end = slab_layers(self.n_last, rank, world)
+        self.op = AdvectionFvOperator(numerical_flux, space)
+        capi.check(capi.lib().gdtb_fvop_set_slab(self.op._h, self.begin, self.end))
+        self.plane = int(capi.lib().gdtb_fvop_ghost_layer_size(self.op._h))
+        self.owned = (self.end - self.begin) * self.plane
+        self.local_size = self.owned + 2 * self.plane
+        self._comm_stream = None
+        self._compute_stream = None
+
+    # ---- layout helpers -------------------------------------------------------------------------------------
+    def scatter_from_global(self, u_global):
+        """owned part of a global host vector in slab layout (ghost layers zero)"""
+        out = np.zeros(self.local_size)
+        out[self.plane:self.plane + self.owned] = np.asarray(u_global)[self.begin * self.plane:self.end * self.plane]
+        return out
+
+    def owned_view(self, u_local):
+        return u_local[self.plane:self.plane + self.owned]
+
+    # ---- operator ---------------------------------------------------------------------------------------------
+    def _step(self, src, dst, euler, dt, lo, hi):
+        capi.check(capi.lib().gdtb_fvop_step_async(self.op._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                                   int(euler), float(dt), int(lo), int(hi)))
+
+    def _run(self, src, dst, euler, dt):
+        import torch
+
+        ctx = self.space.grid.ctx
+        caller = torch.cuda.current_stream()
+        if self._comm_stream is None:
+            # the library launches on an explicit (non-default) stream: handle 0 would select its own stream
+            self._compute_stream = torch.cuda.Stream()
+            self._comm_stream = torch.cuda.Stream()
+        compute, comm = self._compute_stream, self._comm_stream
+        ctx.set_stream(compute.cuda_stream)
+        compute.wait_stream(caller)  # src is complete on the caller's stream
+        comm.wait_stream(caller)
+        comm.wait_stream(compute)
+        with torch.cuda.stream(comm):
+            reqs = exchange_ghost_layers(src, self.plane, self.rank, self.world, self.periodic_last, self.group)
+            for r in reqs:
+                r.wait()  # stream-ordered: makes `comm` wait for the transfers, does not block the host
+        lo, hi = self.begin, self.end
+        if hi - lo > 2:
+            self._step(src, dst, euler, dt, lo + 1, hi - 1)  # interior: independent of the ghost layers
+            compute.wait_stream(comm)
+            self._step(src, dst, euler, dt, lo, lo + 1)
+            self._step(src, dst, euler, dt, hi - 1, hi)
+        else:
+            compute.wait_stream(comm)
+            self._step(src, dst, euler, dt, lo, hi)
+        caller.wait_stream(compute)
+        src.record_stream(compute)
+        dst.record_stream(compute)
+        src.record_stream(comm)
+
+    def apply(self, src, dst):
+        """dst(owned) = L(src); fills src's ghost layers first"""
+        self._run(src, dst, 0, 0.0)
+
+    def euler_step(self, src, dst, dt):
+        """dst(owned) = src - dt L(src) (examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:152-157)"""
+        self._run(src, dst, 1, dt)
+
+
+def make_distributed_advection_fv_operator(numerical_flux, space, rank, world, group=None):
+    return DistributedAdvectionFvOperator(numerical_flux, space, rank, world, group)
+
+
+class SlabAssembly:
+    """Matrix operator + functional of one rank: owner-computes-rows on the rank's element slab, no communication.
+    The global CSR matrix is the concatenation of the ranks' value arrays in rank order (`value_offset` is the
+    global position of the first local value, `row_begin/row_end` the global row range)."""
+
+    def __init__(self, space, rank, world):
+        lib = capi.lib()
+        g = space.grid.desc
+        d = int(g.dim)
+        self.begin, self.end = slab_layers(int(g.n[d - 1]), rank, world)
+        self.space = space
+        self.op_h, self.fun_h = C.c_void_p(), C.c_void_p()
+        ctx = space.grid.ctx
+        capi.check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(self.op_h)))
+        capi.check(lib.gdtb_vecfun_create(ctx._h, space._h, C.byref(self.fun_h)))
+        capi.check(lib.gdtb_matop_set_slab(self.op_h, self.begin, self.end))
+        capi.check(lib.gdtb_vecfun_set_slab(self.fun_h, self.begin, self.end))
+        rb, re_, vo = C.c_int64(), C.c_int64(), C.c_int64()
+        capi.check(lib.gdtb_matop_local_rows(self.op_h, C.byref(rb), C.byref(re_), C.byref(vo)))
+        self.row_begin, self.row_end, self.value_offset = rb.value, re_.value, vo.value
+        self.nnz_local = int(lib.gdtb_matop_local_nnz(self.op_h))
+
+    def append(self, form):
+        capi.check(capi.lib().gdtb_matop_append_element(self.op_h, C.byref(form)))
+
+    def append_rhs(self, form):
+        capi.check(capi.lib().gdtb_vecfun_append_element(self.fun_h, C.byref(form)))
+
+    def assemble(self):
+        values = np.empty(self.nnz_local)
+        vector = np.empty(self.row_end - self.row_begin)
+        capi.check(capi.lib().gdtb_assemble_host(self.op_h, self.fun_h, capi.dptr(values), capi.dptr(vector)))
+        return values, vector
+
+    def __del__(self):
+        if getattr(self, "op_h", None) and self.op_h.value:
+            capi.lib().gdtb_matop_destroy(self.op_h)
+            capi.lib().gdtb_vecfun_destroy(self.fun_h)

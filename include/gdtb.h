@@ -309,6 +309,12 @@ int gdtb_fvop_euler_host(gdtb_fvop* L, double* u, double dt, int64_t n_steps);
  * cells.  The caller fills the ghost layers (NCCL send/recv of the neighbours' boundary layers,
  * tools/timestepper/explicit-rungekutta.hh:252-257) before calling apply. */
 int gdtb_fvop_set_slab(gdtb_fvop* L, int64_t layer_begin, int64_t layer_end);
+/* Enqueue-only building block of the multi-GPU time loop (no synchronisation): range = L(source) (euler == 0) or
+ * range = source - dt * L(source) (euler != 0) for the layers [layer_begin, layer_end) of the operator's slab
+ * (0, 0 = the whole slab).  Lets the caller overlap the interior layers with the ghost-layer exchange and finish the
+ * first / last layer afterwards.  Vectors use the slab layout of gdtb_fvop_set_slab. */
+int gdtb_fvop_step_async(gdtb_fvop* L, const double* d_source, double* d_range, int euler, double dt,
+                         int64_t layer_begin, int64_t layer_end);
 int64_t gdtb_fvop_ghost_layer_size(const gdtb_fvop* L);
 
 /* default_interpolation(order, f, fv_space) (interpolations/default.hh:76-83, spaces/basis/finite-volume.hh:244-252) */

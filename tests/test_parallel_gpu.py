@@ -1,0 +1,97 @@
+"""Multi-GPU path on real devices: world_size 2 over NCCL (skipped on a single-GPU box; run with `gpurun --gpus 2`)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import dune_gdt_b200 as gdt
+    import oracle
+    from dune_gdt_b200 import descriptors as D
+    from dune_gdt_b200 import parallel
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        ctx = gdt.Context(rank)
+        rng = np.random.default_rng(20251017)
+        # ---- FV: distributed apply and a few Euler steps against the oracle on the whole grid ------------------
+        for n, periodic, fk, params in (([96, 64], 3, D.FLUX_LINEAR, [1.0, 0.5]), ([64, 50], 0, D.FLUX_BURGERS, []),
+                                        ([24, 20, 18], 7, D.FLUX_LINEAR, [1.0, -0.5, 0.25])):
+            u = rng.random(int(np.prod(n)))
+            grid = gdt.make_cube_grid(ctx, 0.0, 1.0, n, periodic=periodic)
+            space = gdt.make_finite_volume_space(grid)
+            L = parallel.make_distributed_advection_fv_operator(gdt.NumericalUpwindFlux(fk, params), space, rank, world)
+            gd = D.grid_desc(0.0, 1.0, n, periodic=periodic)
+            fl = D.flux(fk, D.NUMFLUX_UPWIND, params)
+            ref = oracle.fv_apply(gd, fl, u)
+            src = torch.from_numpy(L.scatter_from_global(u)).cuda()
+            dst = torch.zeros_like(src)
+            L.apply(src, dst)
+            torch.cuda.synchronize()
+            own = L.owned_view(dst).cpu().numpy()
+            err = np.abs(own - ref[L.begin * L.plane:L.end * L.plane]).max() / np.abs(ref).max()
+            assert err <= 1e-12, ("apply", n, err)
+            dt, steps = 0.2 / max(n), 5
+            ref_e = oracle.fv_euler(gd, fl, u, dt, steps)
+            a, b = src, dst
+            for _ in range(steps):
+                L.euler_step(a, b, dt)
+                a, b = b, a
+            torch.cuda.synchronize()
+            own = L.owned_view(a).cpu().numpy()
+            err = np.abs(own - ref_e[L.begin * L.plane:L.end * L.plane]).max() / np.abs(ref_e).max()
+            assert err <= 1e-12, ("euler", n, err)
+        # ---- assembly: concatenated slab results == oracle on the whole grid ----------------------------------
+        n = [10, 9, 11]
+        grid = gdt.make_cube_grid(ctx, -1.0, 1.0, n)
+        space = gdt.make_continuous_lagrange_space(grid, 1)
+        slab = parallel.SlabAssembly(space, rank, world)
+        kap = rng.uniform(0.5, 2.0, int(np.prod(n)))
+        lap = D.form(D.integrand(D.INT_LAPLACE, diffusion=D.fn_elem(kap)))
+        src_f = D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 0.75 * np.pi**2, 0.5 * np.pi)
+        rhs = D.form(D.integrand(D.INT_PRODUCT, diffusion=1.0, weight=src_f))
+        slab.append(lap)
+        slab.append_rhs(rhs)
+        values, vector = slab.assemble()
+        gd = D.grid_desc(-1.0, 1.0, n)
+        rp, ci = oracle.pattern(gd, (D.SPACE_CG, 1))
+        v_ref, b_ref = oracle.assemble(gd, D.SPACE_CG, 1, rp, ci, [lap], rhs_forms=[rhs])
+        assert slab.value_offset == rp[slab.row_begin] and slab.nnz_local == rp[slab.row_end] - rp[slab.row_begin]
+        seg = v_ref[slab.value_offset:slab.value_offset + slab.nnz_local]
+        assert np.abs(values - seg).max() / np.abs(v_ref).max() <= 1e-12
+        assert np.abs(vector - b_ref[slab.row_begin:slab.row_end]).max() / np.abs(b_ref).max() <= 1e-12
+        nnz = torch.tensor([slab.nnz_local], device="cuda")
+        dist.all_reduce(nnz)
+        assert int(nnz.item()) == len(v_ref)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_fv_halo_and_slab_assembly(tmp_path, oracle, gdt):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_worker, args=(world, free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
