@@ -1,0 +1,446 @@
+// dune-gdt_b200/csrc/assemble_q2_gather.cu -- owner-computes-rows ("row gather") assembly for continuous-Lagrange
+// Q2 spaces on axis-aligned structured grids (2D / 3D), element forms with element-wise constant coefficients.
+//
+// Replaces the same chain as assemble_q1_gather.cu (LocalElementBilinearFormAssembler::apply_local,
+// local/assembler/bilinear-form-assemblers.hh:110-128; LocalElementIntegralBilinearForm::apply2,
+// local/bilinear-forms/integrals.hh:97-134; LocalLaplaceIntegrand / LocalElementProductIntegrand::evaluate,
+// local/integrands/laplace.hh:81-102, product.hh:104-130; add_to_entry [EXT]) for order 2.
+//
+// Lattice view.  The Q2 DoFs of an N_x x N_y x N_z cube grid are the points p of the lattice [0, 2 N_k]^d; p_k odd
+// means "inside an element along axis k".  The parity pattern s(p) is the YaspGrid shift bitset of the sub-entity the
+// DoF sits on, and the MCMG-based ContinuousMapper (spaces/mapper/continuous.hh:117-150) numbers the DoFs
+// [cells | faces | edges | vertices] (codim ascending), each codim by ascending shift bitset, each group
+// lexicographically (x fastest) -- common.cuh::cg_global_index.  Row p couples to the lattice box |q_k - p_k| <= 1
+// (p_k odd) or <= 2 (p_k even), clipped to the grid: 27 / 45 / 75 / 125 entries for cell / face / edge / vertex rows.
+// Sorted by global index the entries of a row are grouped by the parity pattern of q in the same group order and are
+// lexicographic inside a group, so the CSR position of every entry is a closed form: colidx is never read, rowptr only
+// once per work item.
+//
+// Sum factorisation.  On an affine axis-aligned cell with an element-wise constant coefficient the quadrature sum of
+// the reference factorises exactly into 1D reference tables (the form's own Gauss rule):
+//   L_e[i][j] = c_e sum_r |det J_e| / h_r^2  prod_k T^{(r,k)}[i_k][j_k],  T^{(r,k)} = K1 (k == r) or M1 (k != r),
+//   K1[a][b] = sum_q w_q phi_a'(x_q) phi_b'(x_q),  M1[a][b] = sum_q w_q phi_a(x_q) phi_b(x_q)   (3 x 3 each)
+// (mass: c_e |det J_e| prod_k M1).  A thread owns one row p and one value q_last of the last axis ("plane"): it sums,
+// over the <= 2^d elements that contain both p and the plane, the products built up axis by axis (x innermost) into
+// <= 5 x 5 accumulators -- no atomics, fixed order, every value written once.  Geometry (h_k = upper - lower,
+// 1 / h_k, |det J|) and coefficients are evaluated per element on the device in FP64; elements outside the grid get
+// zero factors.  Rows of one work item are consecutive in CSR: the segment is staged in shared memory and leaves the
+// SM as one TMA bulk store, double-buffered, persistent CTAs (as in assemble_q1_gather.cu).
+#include "common.cuh"
+#include "kernels.hpp"
+
+namespace gdtb {
+
+namespace {
+
+__device__ __forceinline__ void q2_fence_proxy_async_smem()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void q2_bulk_store_s2g(double* gdst, const double* ssrc, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void q2_bulk_commit()
+{
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void q2_bulk_wait_read1()
+{
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
+__device__ __forceinline__ void q2_bulk_wait0()
+{
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ double q2_cell_extent(double lo, double h, int i)
+{
+  const double lower = __dadd_rn(lo, __dmul_rn(double(i), h));
+  const double upper = __dadd_rn(lo, __dmul_rn(double(i + 1), h));
+  return __dsub_rn(upper, lower);
+}
+
+constexpr int Q2G_THREADS = 256;
+
+// per-axis description of a row's coupling box for parity S (compile time): the row's lattice coordinate is
+// p = 2 c + S; box offsets a = 0 .. A-1 mean q = p - R + a with R = S ? 1 : 2, A = S ? 3 : 5
+template <int S>
+struct AxisBox
+{
+  static constexpr int R = S ? 1 : 2;
+  static constexpr int A = S ? 3 : 5;
+  static constexpr int NE = S ? 1 : 2; // elements along this axis that contain p
+  // parity of q for offset a (p = S mod 2)
+  __host__ __device__ static constexpr int parity(int a)
+  {
+    return (S + R + a) & 1;
+  }
+  // element candidate o: lattice offset of its first node relative to the box start: S: 0; !S: 2 o
+  __host__ __device__ static constexpr int first(int o)
+  {
+    return S ? 0 : 2 * o;
+  }
+  // local 1D index (0, 1, 2 = left, middle, right node) of p in element candidate o
+  __host__ __device__ static constexpr int local(int o)
+  {
+    return S ? 1 : 2 - 2 * o;
+  }
+};
+
+struct AxisRuntime
+{
+  int idx[5];    // index of q among the box values of its own parity
+  bool valid[5]; // q inside the lattice
+  int n[2];      // number of even / odd values in the (clipped) box
+  double ha[2], hb[2]; // h and 1/h of the candidate elements (0 if outside the grid)
+  int e[2];      // element index of the candidates
+};
+
+template <int S>
+__device__ __forceinline__ void axis_setup(AxisRuntime& ax, int c, int N, double lo, double h)
+{
+  using B = AxisBox<S>;
+  const int p = 2 * c + S;
+  const int blo = max(0, p - B::R), bhi = min(2 * N, p + B::R);
+  // counts of even / odd values in [blo, bhi]
+  const int first_even = blo + (blo & 1), first_odd = blo + 1 - (blo & 1);
+  ax.n[0] = first_even <= bhi ? (bhi - first_even) / 2 + 1 : 0;
+  ax.n[1] = first_odd <= bhi ? (bhi - first_odd) / 2 + 1 : 0;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    ax.idx[a] = 0;
+    ax.valid[a] = false;
+    if (a < B::A) {
+      const int q = p - B::R + a;
+      ax.valid[a] = q >= 0 && q <= 2 * N;
+      ax.idx[a] = (q - (B::parity(a) ? first_odd : first_even)) >> 1;
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    ax.e[o] = 0;
+    ax.ha[o] = ax.hb[o] = 0.;
+    if (o < B::NE) {
+      const int e = S ? c : c - 1 + o;
+      ax.e[o] = e;
+      if (e >= 0 && e < N) {
+        const double ext = q2_cell_extent(lo, h, e);
+        ax.ha[o] = ext;
+        ax.hb[o] = __drcp_rn(ext);
+      }
+    }
+  }
+}
+
+// group order of the column groups = ascending global index: codim ascending, shift bitset ascending
+__device__ __forceinline__ constexpr int q2_group_order(int D, int rank)
+{
+  return D == 3 ? (rank == 0 ? 7 : rank == 1 ? 3 : rank == 2 ? 5 : rank == 3 ? 6 : rank == 4 ? 1 : rank == 5 ? 2
+                                                                                        : rank == 6 ? 4
+                                                                                                    : 0)
+                : (rank == 0 ? 3 : rank == 1 ? 1 : rank == 2 ? 2 : 0);
+}
+
+// One (row, plane): D == 3: SX, SY in-thread axes, SL = parity of the last (plane) axis; D == 2: SX in-thread, SL = y.
+template <int D, int SX, int SY, int SL>
+__device__ __forceinline__ void q2_row_plane(const Q2GatherParams& p, const long long lex, const int slot,
+                                             double* __restrict__ row)
+{
+  using BX = AxisBox<SX>;
+  using BY = AxisBox<SY>;
+  using BL = AxisBox<SL>;
+  const GridDev& g = p.g;
+  constexpr int last = D - 1;
+  const int Nx = (int)g.n[0], Ny = D == 3 ? (int)g.n[1] : 1, Nl = (int)g.n[last];
+  // group extents: S ? N : N + 1 along each axis; lexicographic, x fastest
+  const unsigned ex = SX ? Nx : Nx + 1, ey = D == 3 ? (SY ? Ny : Ny + 1) : 1;
+  const unsigned l32 = (unsigned)lex;
+  const unsigned t1 = l32 / ex;
+  const int cx = int(l32 - t1 * ex);
+  int cy = 0, cl;
+  if (D == 3) {
+    const unsigned t2 = t1 / ey;
+    cy = int(t1 - t2 * ey);
+    cl = (int)t2;
+  } else
+    cl = (int)t1;
+
+  AxisRuntime ax, ay, al;
+  axis_setup<SX>(ax, cx, Nx, g.lo[0], g.h[0]);
+  if (D == 3)
+    axis_setup<SY>(ay, cy, Ny, g.lo[1], g.h[1]);
+  else {
+    ay.n[0] = 1;
+    ay.n[1] = 0;
+    ay.idx[0] = 0;
+    ay.valid[0] = true;
+    ay.ha[0] = ay.hb[0] = 1.;
+    ay.e[0] = 0;
+  }
+  axis_setup<SL>(al, cl, Nl, g.lo[last], g.h[last]);
+  // the plane: offset `slot` along the last axis
+  if (slot >= BL::A)
+    return;
+  int pl = 0, idx_l = 0;
+  bool valid_l = false;
+#pragma unroll
+  for (int a = 0; a < BL::A; ++a)
+    if (a == slot) {
+      pl = BL::parity(a);
+      idx_l = al.idx[a];
+      valid_l = al.valid[a];
+    }
+  if (!valid_l)
+    return;
+  // start of each column group inside the row: groups in ascending global index order, sizes prod_k n_k[parity];
+  // bit layout of a parity pattern: bit 0 = x, bit 1 = y (3D) / last (2D), bit 2 = last (3D).  Only the groups
+  // with the plane's parity along the last axis are needed: base[px | py << 1]
+  int base[1 << (D - 1)];
+  {
+    int all[1 << D];
+    int running = 0;
+#pragma unroll
+    for (int r = 0; r < (1 << D); ++r) {
+      const int s = q2_group_order(D, r);
+      all[s] = running;
+      const int sx = s & 1, sy = D == 3 ? (s >> 1) & 1 : 0, sl = (s >> (D - 1)) & 1;
+      running += ax.n[sx] * (D == 3 ? ay.n[sy] : 1) * al.n[sl];
+    }
+#pragma unroll
+    for (int sxy = 0; sxy < (1 << (D - 1)); ++sxy)
+      base[sxy] = pl ? all[sxy | (1 << (D - 1))] : all[sxy];
+  }
+
+  constexpr int AY = D == 3 ? BY::A : 1, NEY = D == 3 ? BY::NE : 1;
+  double acc[AY][BX::A];
+#pragma unroll
+  for (int a = 0; a < AY; ++a)
+#pragma unroll
+    for (int b = 0; b < BX::A; ++b)
+      acc[a][b] = 0.;
+
+#pragma unroll
+  for (int ol = 0; ol < BL::NE; ++ol) {
+    // does element candidate ol (along the last axis) contain the plane?  local index of the plane in it
+    const int jl = slot - BL::first(ol);
+    if (jl < 0 || jl > 2)
+      continue;
+    const int il = BL::local(ol);
+#pragma unroll
+    for (int oy = 0; oy < NEY; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < BX::NE; ++ox) {
+        const double hax = ax.ha[ox], hbx = ax.hb[ox];
+        const double hay = D == 3 ? ay.ha[oy] : 1., hby = D == 3 ? ay.hb[oy] : 1.;
+        const double hal = al.ha[ol], hbl = al.hb[ol];
+        const double ie = hax * hay * hal; // |det J_e| (0 for an element outside the grid)
+        const bool valid = ie != 0.;
+        const long long e = (long long)ax.e[ox] + (long long)Nx * ((D == 3 ? ay.e[oy] : al.e[ol]) + (D == 3 ? (long long)Ny * al.e[ol] : 0));
+        const int ix = BX::local(ox), iy = D == 3 ? BY::local(oy) : 0;
+#pragma unroll 1
+        for (int gi = 0; gi < p.n_groups; ++gi) {
+          const Q2Group& G = p.group[gi];
+          double cf = G.scale;
+          if (G.coef_elem)
+            cf *= valid ? __ldg(G.coef + e) : 0.;
+          if (G.kind == Q1G_MASS) {
+            // c |det J| M1 x M1 x M1
+            const double cl_ = cf * ie * G.TM[il][jl];
+#pragma unroll
+            for (int jy = 0; jy < (D == 3 ? 3 : 1); ++jy) {
+              const double cyv = D == 3 ? cl_ * G.TM[iy][jy] : cl_;
+#pragma unroll
+              for (int jx = 0; jx < 3; ++jx)
+                acc[D == 3 ? BY::first(oy) + jy : 0][BX::first(ox) + jx] =
+                    fma(cyv, G.TM[ix][jx], acc[D == 3 ? BY::first(oy) + jy : 0][BX::first(ox) + jx]);
+            }
+          } else {
+            // Laplace with kappa = c I: sum_r c |det J| / h_r^2 (K1 along r, M1 along the other axes)
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+              double w;
+              if (r == 0)
+                w = cf * (hbx * hay * hal);
+              else if (r == last)
+                w = cf * (hax * hay * hbl);
+              else
+                w = cf * (hax * hby * hal);
+              const double cl_ = w * (r == last ? G.TK[il][jl] : G.TM[il][jl]);
+#pragma unroll
+              for (int jy = 0; jy < (D == 3 ? 3 : 1); ++jy) {
+                const double cyv = D == 3 ? cl_ * ((D == 3 && r == 1) ? G.TK[iy][jy] : G.TM[iy][jy]) : cl_;
+#pragma unroll
+                for (int jx = 0; jx < 3; ++jx)
+                  acc[D == 3 ? BY::first(oy) + jy : 0][BX::first(ox) + jx] =
+                      fma(cyv, r == 0 ? G.TK[ix][jx] : G.TM[ix][jx], acc[D == 3 ? BY::first(oy) + jy : 0][BX::first(ox) + jx]);
+              }
+            }
+          }
+        }
+      }
+  }
+
+  // scatter the plane into the row (CSR order by closed-form position)
+#pragma unroll
+  for (int a = 0; a < AY; ++a) {
+    if (D == 3 && !ay.valid[a])
+      continue;
+    const int py = D == 3 ? BY::parity(a) : 0;
+#pragma unroll
+    for (int b = 0; b < BX::A; ++b) {
+      if (!ax.valid[b])
+        continue;
+      const int px = BX::parity(b);
+      int pos;
+      if (D == 3)
+        pos = base[px | (py << 1)] + (idx_l * ay.n[py] + ay.idx[a]) * ax.n[px] + ax.idx[b];
+      else
+        pos = base[px] + idx_l * ax.n[px] + ax.idx[b];
+      row[pos] = acc[a][b];
+    }
+  }
+}
+
+template <int D, bool ACCUMULATE>
+__global__ void __launch_bounds__(Q2G_THREADS, 2)
+    k_q2_gather(const __grid_constant__ Q2GatherParams p, double* __restrict__ values, int stage_doubles)
+{
+  extern __shared__ __align__(16) double smem[];
+  int buf = 0;
+  for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    // ---- per item (uniform): row group, rows, CSR segment ---------------------------------------------------
+    int gi = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      if (k < p.n_rowgroups && item >= p.rg[k].item_begin)
+        gi = k;
+    const Q2RowGroup& rg = p.rg[gi];
+    const int slots = ((rg.s >> (D - 1)) & 1) ? 3 : 5;
+    const int rpi = Q2G_THREADS / slots;
+    const long long lrow0 = (item - rg.item_begin) * rpi; // first row of the item inside its group
+    const int nrows = (int)min((long long)rpi, rg.rows - lrow0);
+    const long long row0 = rg.row_begin + lrow0;
+    const long long start = __ldg(p.rowptr + row0);
+    const int seg = int(__ldg(p.rowptr + row0 + nrows) - start);
+    const int phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
+    double* stage = smem + buf * stage_doubles + phase;
+
+    const int lr = threadIdx.x / slots, slot = threadIdx.x - lr * slots;
+    if (lr < nrows) {
+      double* row = stage + int(__ldg(p.rowptr + row0 + lr) - start);
+      const long long lex = lrow0 + lr;
+      if (D == 3) {
+        switch (rg.s) {
+          case 0: q2_row_plane<3, 0, 0, 0>(p, lex, slot, row); break;
+          case 1: q2_row_plane<3, 1, 0, 0>(p, lex, slot, row); break;
+          case 2: q2_row_plane<3, 0, 1, 0>(p, lex, slot, row); break;
+          case 3: q2_row_plane<3, 1, 1, 0>(p, lex, slot, row); break;
+          case 4: q2_row_plane<3, 0, 0, 1>(p, lex, slot, row); break;
+          case 5: q2_row_plane<3, 1, 0, 1>(p, lex, slot, row); break;
+          case 6: q2_row_plane<3, 0, 1, 1>(p, lex, slot, row); break;
+          default: q2_row_plane<3, 1, 1, 1>(p, lex, slot, row); break;
+        }
+      } else {
+        switch (rg.s) {
+          case 0: q2_row_plane<2, 0, 0, 0>(p, lex, slot, row); break;
+          case 1: q2_row_plane<2, 1, 0, 0>(p, lex, slot, row); break;
+          case 2: q2_row_plane<2, 0, 0, 1>(p, lex, slot, row); break;
+          default: q2_row_plane<2, 1, 0, 1>(p, lex, slot, row); break;
+        }
+      }
+    }
+
+    if (ACCUMULATE) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < seg; i += blockDim.x)
+        values[start + i] += stage[i];
+      __syncthreads();
+    } else {
+      q2_fence_proxy_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int head = phase;
+        const int body = (seg - head) & ~1;
+        if (head)
+          values[start] = stage[0];
+        if (body > 0)
+          q2_bulk_store_s2g(values + start + head, stage + head, (unsigned)(body * sizeof(double)));
+        if (head + body < seg)
+          values[start + head + body] = stage[head + body];
+        q2_bulk_commit();
+        q2_bulk_wait_read1();
+      }
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  if (!ACCUMULATE && threadIdx.x == 0)
+    q2_bulk_wait0();
+}
+
+} // namespace
+
+int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate)
+{
+  const GridDev& g = p.g;
+  const int d = g.d;
+  if (d != 2 && d != 3)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: 2D and 3D grids only");
+  if (sp.size >= (1LL << 31))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: more than 2^31 degrees of freedom");
+  // row groups in ascending global index order (codim ascending, shift bitset ascending)
+  p.n_rowgroups = 0;
+  p.n_items = 0;
+  int max_row = 1;
+  for (int k = 0; k < d; ++k)
+    max_row *= 5;
+  for (int c = 0; c <= d; ++c)
+    for (int s = 0; s < (1 << d); ++s) {
+      int pc = 0;
+      for (int k = 0; k < d; ++k)
+        pc += (s >> k) & 1;
+      if (pc != d - c)
+        continue;
+      Q2RowGroup& rg = p.rg[p.n_rowgroups++];
+      rg.s = s;
+      rg.rows = 1;
+      for (int k = 0; k < d; ++k)
+        rg.rows *= ((s >> k) & 1) ? g.n[k] : g.n[k] + 1;
+      rg.row_begin = sp.cg.codim_offset[c] + sp.cg.group_offset[s];
+      const int slots = ((s >> (d - 1)) & 1) ? 3 : 5;
+      const int rpi = Q2G_THREADS / slots;
+      rg.item_begin = p.n_items;
+      p.n_items += (rg.rows + rpi - 1) / rpi;
+    }
+  // stage: the longest segment is rows_per_item rows of the longest row kind that uses that slot count
+  // (5 slots: rows up to 5^d entries, 51 rows; 3 slots: rows up to 3 * 5^(d-1), 85 rows)
+  const int seg5 = (Q2G_THREADS / 5) * max_row, seg3 = (Q2G_THREADS / 3) * (max_row / 5 * 3);
+  const int stage_doubles = ((std::max(seg5, seg3) + 2) + 1) & ~1;
+  const size_t smem = (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double);
+  auto kern = d == 3 ? (accumulate ? k_q2_gather<3, true> : k_q2_gather<3, false>)
+                     : (accumulate ? k_q2_gather<2, true> : k_q2_gather<2, false>);
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int per_sm = 0;
+  GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Q2G_THREADS, smem));
+  if (per_sm < 1)
+    return fail(GDTB_ERR_CUDA, "q2_gather: kernel does not fit on an SM");
+  long long grid = (long long)per_sm * L.sm_count;
+  if (grid > p.n_items)
+    grid = p.n_items;
+  time_begin(L, KF_Q2_GATHER);
+  kern<<<(unsigned)grid, Q2G_THREADS, smem, L.stream>>>(p, values, stage_doubles);
+  time_end(L, KF_Q2_GATHER);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+} // namespace gdtb

@@ -380,6 +380,67 @@ bool matop_q1_eligible(const gdtb_matop* op)
   return n_groups <= Q1G_MAX_GROUPS;
 }
 
+// CG-Q2 row-gather path (assemble_q2_gather.cu): element forms, Laplace with kappa = c I or mass, coefficients
+// constant or one scalar per element; needs the element pattern (its rowptr is read, colidx is not)
+bool matop_q2_eligible(const gdtb_matop* op)
+{
+  const auto q2 = [](const SpaceDev& sp) { return sp.kind == GDTB_SPACE_CG && sp.K == 2; };
+  if (!q2(op->test) || !q2(op->ansatz) || op->grid.periodic || op->slab || (op->grid.d != 2 && op->grid.d != 3))
+    return false;
+  if (!op->pattern || op->pattern->stencil != GDTB_STENCIL_ELEMENT || !q2(op->pattern->test)
+      || !q2(op->pattern->ansatz))
+    return false;
+  if (!op->coupling_forms.empty() || !op->boundary_forms.empty() || op->element_forms.empty())
+    return false;
+  int n_groups = 0;
+  for (const auto& lf : op->element_forms)
+    for (int t = 0; t < lf.form.n_terms; ++t) {
+      const gdtb_integrand& in = lf.form.terms[t];
+      if (in.kind != GDTB_INT_LAPLACE && in.kind != GDTB_INT_PRODUCT)
+        return false;
+      if (in.diffusion.kind != GDTB_FN_CONST_SCALAR && in.diffusion.kind != GDTB_FN_ELEM_SCALAR)
+        return false;
+      ++n_groups;
+    }
+  return n_groups <= Q2G_MAX_GROUPS;
+}
+
+int build_q2_params(const gdtb_matop* op, Q2GatherParams& p)
+{
+  std::memset(&p, 0, sizeof(p));
+  p.g = op->grid;
+  p.rowptr = op->pattern->d_rowptr;
+  for (const auto& lf : op->element_forms) {
+    // 1D reference tables with the form's own Gauss rule (order logic of laplace.hh:74-79 / product.hh:89-100)
+    const int m = gauss_points_for_order(form_quadrature_order(lf.form, 2, ROLE_ELEMENT));
+    if (m > MAX_Q1D)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "quadrature order too high (more than 8 Gauss points per direction)");
+    double qx[MAX_Q1D], qw[MAX_Q1D];
+    gauss_legendre_01(m, qx, qw);
+    double TM[3][3] = {{0}}, TK[3][3] = {{0}};
+    for (int q = 0; q < m; ++q) {
+      double v[3], dv[3];
+      lagrange_1d(2, qx[q], v, dv);
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          TM[a][b] += qw[q] * v[a] * v[b];
+          TK[a][b] += qw[q] * dv[a] * dv[b];
+        }
+    }
+    for (int t = 0; t < lf.form.n_terms; ++t) {
+      const gdtb_integrand& in = lf.form.terms[t];
+      Q2Group& G = p.group[p.n_groups++];
+      G.kind = in.kind == GDTB_INT_PRODUCT ? Q1G_MASS : Q1G_LAPLACE_SCALAR;
+      G.coef_elem = in.diffusion.kind == GDTB_FN_ELEM_SCALAR ? 1 : 0;
+      G.scale = lf.form.scaling * (G.coef_elem ? 1. : in.diffusion.c[0]);
+      G.coef = in.diffusion.data;
+      std::memcpy(G.TM, TM, sizeof(TM));
+      std::memcpy(G.TK, TK, sizeof(TK));
+    }
+  }
+  return GDTB_OK;
+}
+
 bool builtin_is_separable(int id)
 {
   return id == GDTB_BUILTIN_COS_PRODUCT || id == GDTB_BUILTIN_GAUSSIAN || id == GDTB_BUILTIN_INDICATOR;
@@ -651,7 +712,7 @@ int gdtb_ctx_enable_timing(gdtb_ctx* ctx, int enabled)
 int gdtb_ctx_kernel_time(gdtb_ctx* ctx, const char* family, double* total_ms, int64_t* launches)
 {
   GDTB_TRY(check_ctx(ctx));
-  static const char* names[KF_COUNT] = {"q1_gather",      "fv_apply",        "element_matrix",
+  static const char* names[KF_COUNT] = {"q1_gather",      "q2_gather",       "fv_apply",       "element_matrix",
                                         "element_vector", "coupling_matrix", "boundary_matrix"};
   int fam = -1;
   for (int i = 0; i < KF_COUNT; ++i)
@@ -1041,7 +1102,7 @@ const char* gdtb_matop_plan(gdtb_matop* op)
 {
   if (!op)
     return "";
-  op->plan = matop_q1_eligible(op) ? "q1_gather" : "generic_coloured";
+  op->plan = matop_q1_eligible(op) ? "q1_gather" : (matop_q2_eligible(op) ? "q2_gather" : "generic_coloured");
   return op->plan.c_str();
 }
 
@@ -1370,8 +1431,16 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     GDTB_TRY(launch_q1_gather(L, p, op_fast ? op->d_values : nullptr, fun_fast ? fun->d_vec : nullptr, accumulate));
   }
 
+  // --- CG-Q2 row-gather path ---------------------------------------------------------------
+  const bool op_q2 = op && !op_fast && matop_q2_eligible(op);
+  if (op_q2) {
+    Q2GatherParams p;
+    GDTB_TRY(build_q2_params(op, p));
+    GDTB_TRY(launch_q2_gather(L, p, op->test, op->d_values, accumulate));
+  }
+
   // --- generic path --------------------------------------------------------------------------
-  if (op && !op_fast) {
+  if (op && !op_fast && !op_q2) {
     const gdtb_pattern* pat = op->pattern;
     if (!accumulate)
       GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pat->nnz, L.stream));

@@ -11,6 +11,7 @@ namespace gdtb {
 enum KernelFamily
 {
   KF_Q1_GATHER = 0,
+  KF_Q2_GATHER,
   KF_FV_APPLY,
   KF_ELEMENT_MATRIX,
   KF_ELEMENT_VECTOR,
@@ -121,6 +122,41 @@ int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double*
 int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long long elem_hi, const FnDev& f, int m,
                          const double* qx, const double* qw, const double* phi /* [m][2] */, double* tab,
                          long long stride);
+
+// ---- CG-Q2 row-gather assembly (assemble_q2_gather.cu) --------------------------------------------
+constexpr int Q2G_MAX_GROUPS = 3;
+
+// one integrand of one appended form (kinds: Q1G_LAPLACE_SCALAR, Q1G_MASS); TM / TK are the 1D reference mass and
+// stiffness tables of the Q2 shape functions (nodes 0, 1/2, 1) for the form's own Gauss rule
+struct Q2Group
+{
+  int kind;
+  int coef_elem;
+  double scale;
+  const double* coef;
+  double TM[3][3];
+  double TK[3][3];
+};
+
+// rows of one sub-entity kind (parity pattern s of the lattice point): contiguous in the global numbering
+struct Q2RowGroup
+{
+  int s;
+  long long row_begin, rows, item_begin;
+};
+
+struct Q2GatherParams
+{
+  GridDev g;
+  int n_groups;
+  Q2Group group[Q2G_MAX_GROUPS];
+  int n_rowgroups;
+  Q2RowGroup rg[8];
+  long long n_items;
+  const long long* rowptr; // device CSR row pointer of the element pattern
+};
+
+int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate);
 
 // ---- sparsity pattern (pattern.cu) ----------------------------------------------------------------
 int pattern_sort_unique(Launch& L, const GridDev& g, const SpaceDev& test, const SpaceDev& ansatz, int stencil,

@@ -139,9 +139,12 @@ def element_cases():
             ("q1-laplace-tensor", n, 1, [laplace(D.fn_const(kt))], "q1_gather"),
             ("q1-laplace-builtin", n, 1, [laplace(D.fn_builtin(D.BUILTIN_QUADRATIC, 2, 1.0, 0.5))], "generic_coloured"),
             ("q1-laplace-elemtensor", n, 1, [laplace(D.fn_elem(np.tile(kt, (int(np.prod(n)), 1, 1)) * rng_elem(n)[:, None, None]))], "q1_gather"),
-            ("q2-laplace-const", n, 2, [laplace(1.0)], "generic_coloured"),
+            ("q2-laplace-const", n, 2, [laplace(1.0)], "q2_gather" if d > 1 else "generic_coloured"),
+            ("q2-laplace-scaled-overint", n, 2, [laplace(2.5, scaling=0.5, over_integrate=1)], "q2_gather" if d > 1 else "generic_coloured"),
+            ("q2-mass-elem", n, 2, [mass(D.fn_elem(rng_elem(n, seed=11)))], "q2_gather" if d > 1 else "generic_coloured"),
+            ("q2-laplace-tensor", n, 2, [laplace(D.fn_const(kt))], "generic_coloured"),
             ("q2-mass-builtin", n, 2, [mass(D.fn_builtin(D.BUILTIN_AFFINE, 1, 1.0, 0.3, 0.2, 0.1))], "generic_coloured"),
-            ("q2-laplace-elem+mass", n, 2, [D.form([D.integrand(D.INT_LAPLACE, diffusion=D.fn_elem(rng_elem(n))), D.integrand(D.INT_PRODUCT, diffusion=2.0)])], "generic_coloured"),
+            ("q2-laplace-elem+mass", n, 2, [D.form([D.integrand(D.INT_LAPLACE, diffusion=D.fn_elem(rng_elem(n))), D.integrand(D.INT_PRODUCT, diffusion=2.0)])], "q2_gather" if d > 1 else "generic_coloured"),
         ]
     cases += [
         ("q3-laplace-2d", [4, 3], 3, [laplace(1.0)], "generic_coloured"),
@@ -149,6 +152,10 @@ def element_cases():
         ("q1-underintegrated", [4, 3, 2], 1, [laplace(1.0, over_integrate=-2)], "q1_gather"),
         ("q1-single-element", [1, 1, 1], 1, [laplace(1.0)], "q1_gather"),
         ("q1-anisotropic-cells", [3, 5, 2], 1, [laplace(1.0)], "q1_gather"),
+        ("q2-single-element", [1, 1, 1], 2, [laplace(1.0)], "q2_gather"),
+        ("q2-thin-grid", [1, 7, 2], 2, [laplace(1.0), mass(0.5)], "q2_gather"),
+        ("q2-2d-single-row", [13, 1], 2, [laplace(1.0)], "q2_gather"),
+        ("q2-bigger-3d", [17, 9, 12], 2, [laplace(D.fn_elem(rng_elem([17, 9, 12])))], "q2_gather"),
     ]
     return cases
 
