@@ -159,6 +159,8 @@ struct gdtb_matop
   bool owns_values;
   std::vector<LoweredForm> element_forms, coupling_forms, boundary_forms;
   std::string plan;
+  void* d_forms = nullptr; // lowered FormDev array of the DG gather path
+  size_t d_forms_bytes = 0;
   // owner-computes-rows slab (multi-GPU): only the rows [row_begin, row_end) live in d_values
   bool slab;
   long long row_begin, row_end;   // global row range held by this process
@@ -403,6 +405,26 @@ bool matop_q2_eligible(const gdtb_matop* op)
       ++n_groups;
     }
   return n_groups <= Q2G_MAX_GROUPS;
+}
+
+// DG row-gather path (assemble_dg_gather.cu): any mix of element / inner-coupling / boundary forms on a non-periodic
+// grid with the element_and_intersection pattern
+bool matop_dg_eligible(const gdtb_matop* op)
+{
+  if (op->test.kind != GDTB_SPACE_DG || op->ansatz.kind != GDTB_SPACE_DG || op->grid.periodic || op->slab)
+    return false;
+  if (!dg_gather_supported(op->grid.d, op->test.K))
+    return false;
+  if (!op->pattern || op->pattern->stencil != GDTB_STENCIL_ELEMENT_AND_INTERSECTION
+      || op->pattern->test.kind != GDTB_SPACE_DG || op->pattern->test.K != op->test.K)
+    return false;
+  const size_t n = op->element_forms.size() + op->coupling_forms.size() + op->boundary_forms.size();
+  if (n == 0 || n > (size_t)DGG_MAX_FORMS)
+    return false;
+  for (const auto& lf : op->boundary_forms)
+    if (lf.filter != GDTB_FILTER_ALL_BOUNDARY)
+      return false;
+  return true;
 }
 
 int build_q2_params(const gdtb_matop* op, Q2GatherParams& p)
@@ -712,8 +734,8 @@ int gdtb_ctx_enable_timing(gdtb_ctx* ctx, int enabled)
 int gdtb_ctx_kernel_time(gdtb_ctx* ctx, const char* family, double* total_ms, int64_t* launches)
 {
   GDTB_TRY(check_ctx(ctx));
-  static const char* names[KF_COUNT] = {"q1_gather",      "q2_gather",       "fv_apply",       "element_matrix",
-                                        "element_vector", "coupling_matrix", "boundary_matrix"};
+  static const char* names[KF_COUNT] = {"q1_gather",      "q2_gather",      "dg_gather",       "fv_apply",
+                                        "element_matrix", "element_vector", "coupling_matrix", "boundary_matrix"};
   int fam = -1;
   for (int i = 0; i < KF_COUNT; ++i)
     if (family && std::strcmp(family, names[i]) == 0)
@@ -1035,6 +1057,7 @@ int gdtb_matop_destroy(gdtb_matop* op)
   gdtb_matop_clear_forms(op);
   if (op->owns_values)
     cudaFree(op->d_values);
+  cudaFree(op->d_forms);
   delete op;
   return GDTB_OK;
 }
@@ -1102,7 +1125,9 @@ const char* gdtb_matop_plan(gdtb_matop* op)
 {
   if (!op)
     return "";
-  op->plan = matop_q1_eligible(op) ? "q1_gather" : (matop_q2_eligible(op) ? "q2_gather" : "generic_coloured");
+  op->plan = matop_q1_eligible(op)
+                 ? "q1_gather"
+                 : (matop_q2_eligible(op) ? "q2_gather" : (matop_dg_eligible(op) ? "dg_gather" : "generic_coloured"));
   return op->plan.c_str();
 }
 
@@ -1439,8 +1464,47 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     GDTB_TRY(launch_q2_gather(L, p, op->test, op->d_values, accumulate));
   }
 
+  // --- DG row-gather path ------------------------------------------------------------------
+  const bool op_dg = op && !op_fast && !op_q2 && matop_dg_eligible(op);
+  if (op_dg) {
+    std::vector<FormDev> forms;
+    for (const auto& lf : op->element_forms) {
+      forms.emplace_back();
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_ELEMENT, forms.back()));
+    }
+    for (const auto& lf : op->coupling_forms) {
+      forms.emplace_back();
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_COUPLING, forms.back()));
+    }
+    for (const auto& lf : op->boundary_forms) {
+      forms.emplace_back();
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_BOUNDARY, forms.back()));
+    }
+    const size_t bytes = sizeof(FormDev) * forms.size();
+    if (op->d_forms_bytes < bytes) {
+      cudaFree(op->d_forms);
+      op->d_forms = nullptr;
+      if (cudaMalloc(&op->d_forms, bytes) != cudaSuccess)
+        return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the lowered forms");
+      op->d_forms_bytes = bytes;
+    }
+    // the host vector dies at the end of this scope: synchronous copy
+    GDTB_CUDA(cudaMemcpyAsync(op->d_forms, forms.data(), bytes, cudaMemcpyHostToDevice, L.stream));
+    GDTB_CUDA(cudaStreamSynchronize(L.stream));
+    DgGatherParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = op->grid;
+    p.sp = op->test;
+    p.forms = static_cast<const FormDev*>(op->d_forms);
+    p.n_elem = (int)op->element_forms.size();
+    p.n_coup = (int)op->coupling_forms.size();
+    p.n_bnd = (int)op->boundary_forms.size();
+    p.rowptr = op->pattern->d_rowptr;
+    GDTB_TRY(launch_dg_gather(L, p, op->d_values, accumulate));
+  }
+
   // --- generic path --------------------------------------------------------------------------
-  if (op && !op_fast && !op_q2) {
+  if (op && !op_fast && !op_q2 && !op_dg) {
     const gdtb_pattern* pat = op->pattern;
     if (!accumulate)
       GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pat->nnz, L.stream));

@@ -12,6 +12,7 @@ enum KernelFamily
 {
   KF_Q1_GATHER = 0,
   KF_Q2_GATHER,
+  KF_DG_GATHER,
   KF_FV_APPLY,
   KF_ELEMENT_MATRIX,
   KF_ELEMENT_VECTOR,
@@ -157,6 +158,22 @@ struct Q2GatherParams
 };
 
 int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate);
+
+// ---- DG row-gather assembly (assemble_dg_gather.cu) -----------------------------------------------
+constexpr int DGG_THREADS = 128;
+constexpr int DGG_MAX_FORMS = 8;
+
+struct DgGatherParams
+{
+  GridDev g;
+  SpaceDev sp;
+  const FormDev* forms; // device array: element forms, then coupling forms, then boundary forms
+  int n_elem, n_coup, n_bnd;
+  const long long* rowptr; // device CSR row pointer of the element_and_intersection pattern
+};
+
+bool dg_gather_supported(int d, int K);
+int launch_dg_gather(Launch& L, const DgGatherParams& p, double* values, bool accumulate);
 
 // ---- sparsity pattern (pattern.cu) ----------------------------------------------------------------
 int pattern_sort_unique(Launch& L, const GridDev& g, const SpaceDev& test, const SpaceDev& ansatz, int stencil,
