@@ -110,20 +110,26 @@ __device__ __forceinline__ double cell_extent(double lo, double h, int i)
   return __dsub_rn(upper, lower);
 }
 
+// exact v / d for v < 2^31 by one widening multiply: magic = ceil(2^(31+l) / d), l = ceil(log2 d) (kernels.hpp)
+__device__ __forceinline__ unsigned fast_div(unsigned v, const FastDiv& fd)
+{
+  return (unsigned)(((unsigned long long)v * fd.magic) >> fd.shift);
+}
+
 // vertex index -> (ix, iy, iz), x fastest; one past the last vertex decodes to i_last = N_last + 1, others 0
 template <int D>
-__device__ __forceinline__ void q1_decode(unsigned v, unsigned Vx, unsigned Vy, int& ix, int& iy, int& iz)
+__device__ __forceinline__ void q1_decode(unsigned v, const FastDiv& dx, const FastDiv& dy, int& ix, int& iy, int& iz)
 {
   ix = (int)v;
   iy = 0;
   iz = 0;
   if (D > 1) {
-    const unsigned t = v / Vx;
-    ix = int(v - t * Vx);
+    const unsigned t = fast_div(v, dx);
+    ix = int(v - t * dx.d);
     iy = (int)t;
     if (D > 2) {
-      const unsigned u = t / Vy;
-      iy = int(t - u * Vy);
+      const unsigned u = fast_div(t, dy);
+      iy = int(t - u * dy.d);
       iz = (int)u;
     }
   }
@@ -203,6 +209,23 @@ __device__ __forceinline__ void q1_add_element(const Q1GatherParams& p, int ox, 
   }
 }
 
+// single Laplace integrand with kappa = c I in 3D (the headline configuration): the three direction weights
+// w[r] = c_e |det J_e| / h_r^2 are handed in, so that the caller can share the per-axis products between the 8 cells
+__device__ __forceinline__ void q1_add_element_lap3(const Q1Group& G, int ox, int oy, int oz, const double (&w)[3],
+                                                    double* __restrict__ P0, double* __restrict__ P1)
+{
+  const int o = ox + 2 * oy + 4 * oz;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int sx = s & 1, sy = (s >> 1) & 1, sz = (s >> 2) & 1;
+    double* P = sz ? P1 : P0;
+    const int t = 3 * (oy + sy) + ox + sx;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      P[t] = fma(w[r], G.M[r * 3 + r][o][s], P[t]);
+  }
+}
+
 // writes the (dy, dx) entries of one z-plane (D == 3) / of the whole row (D < 3) in CSR order; returns the count
 template <int NP>
 __device__ __forceinline__ int q1_store_plane(double* __restrict__ row, const double* __restrict__ P, bool full,
@@ -243,7 +266,6 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
   extern __shared__ __align__(16) double smem[];
   const GridDev& g = p.g;
   const int Nx = (int)g.n[0], Ny = D > 1 ? (int)g.n[1] : 1, Nz = D > 2 ? (int)g.n[2] : 1;
-  const unsigned Vx = Nx + 1, Vy = D > 1 ? Ny + 1 : 1;
   // element range along the last direction (owner-computes slab + ghost layer)
   const int elo = (int)p.elem_lo, ehi = (int)p.elem_hi;
   const bool want_values = NG > 0 && values != nullptr;
@@ -260,8 +282,8 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
     double* stage = smem;
     if (want_values) {
       int bx, by, bz, cx, cy, cz;
-      q1_decode<D>(r0, Vx, Vy, bx, by, bz);
-      q1_decode<D>(r0 + nr, Vx, Vy, cx, cy, cz);
+      q1_decode<D>(r0, p.div_vx, p.div_vy, bx, by, bz);
+      q1_decode<D>(r0 + nr, p.div_vx, p.div_vy, cx, cy, cz);
       const long long gstart = q1_rowptr<D>(bx, by, bz, Nx, Ny, Nz);
       // one past the last vertex decodes to (0, 0, Nz + 1) [(0, Ny + 1) in 2D, Nx + 1 in 1D]: S_axis saturates
       const long long gend = q1_rowptr<D>(cx, cy, cz, Nx, Ny, Nz);
@@ -276,11 +298,13 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
     // ---- per vertex --------------------------------------------------------------------------------------
     if ((int)threadIdx.x < nr) {
       int ix, iy, iz;
-      q1_decode<D>(r0 + threadIdx.x, Vx, Vy, ix, iy, iz);
+      q1_decode<D>(r0 + threadIdx.x, p.div_vx, p.div_vy, ix, iy, iz);
       const int il[3] = {ix, iy, iz};
       const int Nl[3] = {Nx, Ny, Nz};
       // geometry of the two cells per axis around the vertex: ha[k][o] = h_k, hb[k][o] = 1 / h_k (J^{-T} = diag(1/h_k),
-      // spaces/basis/default.hh:167-174; integration element = prod h_k); zero for cells outside the grid / slab
+      // spaces/basis/default.hh:167-174; integration element = prod h_k) from the grid's per-axis tables
+      // (k_q1_axis_tables: entry i + 1 belongs to cell i, the entries of the cells -1 and N_k are zero, so cells
+      // outside the grid contribute exact zeros); along the last axis the slab's element range applies on top
       double ha[3][2], hb[3][2];
       bool vk[3][2];
 #pragma unroll
@@ -291,12 +315,16 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
           hb[k][o] = 1.;
           vk[k][o] = o == 0;
           if (k < D) {
-            const int lo = k == D - 1 ? elo : 0, hi = k == D - 1 ? ehi : Nl[k];
             const int c = il[k] - 1 + o;
-            vk[k][o] = c >= lo && c < hi;
-            const double h = cell_extent(g.lo[k], g.h[k], c);
-            ha[k][o] = vk[k][o] ? h : 0.;
-            hb[k][o] = vk[k][o] ? __drcp_rn(h) : 0.;
+            const double* tab = p.axis_tab[k] + (c + 1);
+            ha[k][o] = __ldg(tab);
+            hb[k][o] = __ldg(tab + p.axis_tab_inv);
+            vk[k][o] = c >= 0 && c < Nl[k];
+            if (k == D - 1) {
+              vk[k][o] = c >= elo && c < ehi;
+              ha[k][o] = vk[k][o] ? ha[k][o] : 0.;
+              hb[k][o] = vk[k][o] ? hb[k][o] : 0.;
+            }
           }
         }
       // element index of offset o = 0 (may be out of range; only dereferenced when valid)
@@ -318,6 +346,22 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
 #pragma unroll
         for (int k = 0; k < 9; ++k)
           P[0][k] = P[1][k] = P[2][k] = 0.;
+        constexpr bool LAP3 = NG == 1 && KIND0 == Q1G_LAPLACE_SCALAR;
+        // products shared by the cells: |det J| / h_r^2 = (1/h_r) prod_{k != r} h_k, the x factor carries the scaling
+        double fx_a[2], fx_b[2], yz_aa[2][2], yz_ba[2][2], yz_ab[2][2];
+        if (LAP3) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            fx_a[o] = p.group[0].scale * ha[0][o];
+            fx_b[o] = p.group[0].scale * hb[0][o];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              yz_aa[o][q] = ha[1][o] * ha[2][q];
+              yz_ba[o][q] = hb[1][o] * ha[2][q];
+              yz_ab[o][q] = ha[1][o] * hb[2][q];
+            }
+          }
+        }
 #pragma unroll
         for (int oz = 0; oz < 2; ++oz) {
 #pragma unroll
@@ -327,8 +371,21 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
             const double b[3] = {hb[0][ox], hb[1][oy], hb[2][oz]};
             const bool valid = vk[0][ox] && vk[1][oy] && vk[2][oz];
             const long long e = e0 + ox + (long long)Nx * (oy + (long long)Ny * oz);
-            if (want_values)
-              q1_add_element<D, NG, KIND0>(p, ox, oy, oz, a, b, valid, e, P[oz], P[oz + 1]);
+            if (want_values) {
+              if (LAP3) {
+                double w[3] = {fx_b[ox] * yz_aa[oy][oz], fx_a[ox] * yz_ba[oy][oz], fx_a[ox] * yz_ab[oy][oz]};
+                if (p.group[0].coef_elem) {
+                  const double c = valid ? __ldg(p.group[0].coef + e) : 0.;
+                  w[0] *= c;
+                  w[1] *= c;
+                  w[2] *= c;
+                }
+                q1_add_element_lap3(p.group[0], ox, oy, oz, w, P[oz], P[oz + 1]);
+              } else
+                q1_add_element<D, NG, KIND0>(p, ox, oy, oz, a, b, valid, e, P[oz], P[oz + 1]);
+            }
+            if (!p.rhs_has_const && !p.rhs_has_elem)
+              continue;
             const double ie = a[0] * a[1] * a[2];
             if (p.rhs_has_const)
               bsum = fma(ie, p.rhs_S_const[ox + 2 * oy + 4 * oz], bsum);
@@ -420,6 +477,27 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
     bulk_wait0();
 }
 
+// Per-axis geometry tables of the (tensor-product) grid, built once per grid on the device: for axis k and cell i
+// tab[k][i + 1] = h_k(i) = upper - lower with YaspGrid's coordinates origin + i h (no FMA contraction), and
+// tab[k][inv + i + 1] = 1 / h_k(i); the two border entries (cells -1 and N_k) are zero.
+__global__ void k_q1_axis_tables(const GridDev g, double* __restrict__ t0, double* __restrict__ t1,
+                                 double* __restrict__ t2, long long inv)
+{
+  double* tabs[3] = {t0, t1, t2};
+  for (int k = 0; k < g.d; ++k)
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < g.n[k] + 2;
+         j += (long long)gridDim.x * blockDim.x) {
+      const long long i = j - 1;
+      double h = 0., ih = 0.;
+      if (i >= 0 && i < g.n[k]) {
+        h = cell_extent(g.lo[k], g.h[k], (int)i);
+        ih = __drcp_rn(h);
+      }
+      tabs[k][j] = h;
+      tabs[k][inv + j] = ih;
+    }
+}
+
 // Separable right-hand side tables: for f(x) = p0 * prod_k F_k(x_k),
 //   B_k[i] = sum over the (valid) cells e in {i-1, i} of  ext_e * sum_q w_q phi_a(xi_q) F_k(lower_e + xi_q * ext_e),
 // a = local index of vertex i in cell e.  One block, strided over (axis, vertex).
@@ -464,6 +542,14 @@ __global__ void k_q1_rhs_tables(const GridDev g, long long elem_lo, long long el
 }
 
 } // namespace
+
+int launch_q1_axis_tables(Launch& L, const GridDev& g, double* const* tabs, long long inv)
+{
+  k_q1_axis_tables<<<8, 256, 0, L.stream>>>(g, tabs[0], tabs[1], tabs[2], inv);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
 
 int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long long elem_hi, const FnDev& f, int m,
                          const double* qx, const double* qw, const double* phi, double* tab, long long stride)

@@ -104,6 +104,14 @@ struct gdtb_ctx
   Timing timing;
   int* d_error_flag;
   bool error_flag_pending; // an asynchronous generic assemble has not been checked yet
+  // per-axis geometry tables of the grids seen so far (assemble_q1_gather.cu), keyed by the grid description
+  struct AxisTables
+  {
+    GridDev grid;
+    double* d_tab;
+    long long offset[3], inv;
+  };
+  std::vector<AxisTables> axis_tables;
 };
 
 struct gdtb_grid
@@ -586,12 +594,47 @@ void q1_slab_ranges(const GridDev& g, long long begin, long long end, long long&
   elem_hi = end;
 }
 
+// per-axis geometry tables of a grid (ignoring the slab), built on the device at first use
+int q1_axis_tables(gdtb_ctx* ctx, const GridDev& grid, Q1GatherParams& p)
+{
+  GridDev key = grid;
+  key.layer_lo = 0;
+  key.layer_hi = 0;
+  const gdtb_ctx::AxisTables* found = nullptr;
+  for (const auto& t : ctx->axis_tables)
+    if (std::memcmp(&t.grid, &key, sizeof(GridDev)) == 0)
+      found = &t;
+  if (!found) {
+    gdtb_ctx::AxisTables t;
+    t.grid = key;
+    long long total = 0;
+    for (int k = 0; k < 3; ++k) {
+      t.offset[k] = total;
+      total += (k < key.d ? key.n[k] : 0) + 2;
+    }
+    t.inv = total;
+    if (cudaMalloc(&t.d_tab, sizeof(double) * 2 * (size_t)total) != cudaSuccess)
+      return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the grid geometry tables");
+    double* tabs[3] = {t.d_tab + t.offset[0], t.d_tab + t.offset[1], t.d_tab + t.offset[2]};
+    GDTB_TRY(launch_q1_axis_tables(ctx->launch, key, tabs, t.inv));
+    ctx->axis_tables.push_back(t);
+    found = &ctx->axis_tables.back();
+  }
+  for (int k = 0; k < 3; ++k)
+    p.axis_tab[k] = found->d_tab + found->offset[k];
+  p.axis_tab_inv = found->inv;
+  return GDTB_OK;
+}
+
 int build_q1_params(gdtb_matop* op, gdtb_vecfun* fun, Q1GatherParams& p)
 {
   std::memset(&p, 0, sizeof(p));
   const GridDev& g = op ? op->grid : fun->grid;
   p.g = g;
   const int d = g.d;
+  p.div_vx = make_fast_div((unsigned)(g.n[0] + 1));
+  p.div_vy = make_fast_div((unsigned)(d > 1 ? g.n[1] + 1 : 1));
+  GDTB_TRY(q1_axis_tables(op ? op->ctx : fun->ctx, g, p));
   p.row_lo = op ? op->row_lo : fun->row_lo;
   p.row_hi = op ? op->row_hi : fun->row_hi;
   p.elem_lo = op ? op->elem_lo : fun->elem_lo;
@@ -691,6 +734,8 @@ int gdtb_ctx_destroy(gdtb_ctx* ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->launch.stream);
   cudaFree(ctx->d_error_flag);
+  for (auto& t : ctx->axis_tables)
+    cudaFree(t.d_tab);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return GDTB_OK;

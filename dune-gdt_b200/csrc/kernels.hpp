@@ -92,9 +92,30 @@ struct Q1Group
                       // s = ansatz index; the scalar kinds only use r == c, the mass kind only M[0]
 };
 
+// exact unsigned division v / d for v < 2^31: (v * magic) >> shift
+struct FastDiv
+{
+  unsigned d, magic, shift;
+};
+
+inline FastDiv make_fast_div(unsigned d)
+{
+  FastDiv f;
+  f.d = d;
+  unsigned l = 0;
+  while ((1ull << l) < d)
+    ++l;
+  f.shift = 31 + l;
+  f.magic = (unsigned)(((1ull << f.shift) + d - 1) / d); // <= 2^32 - 1 for d >= 2; d == 1: 2^31
+  return f;
+}
+
 struct Q1GatherParams
 {
   GridDev g;
+  FastDiv div_vx, div_vy;     // division by the number of vertices per x-line / per y-line
+  const double* axis_tab[3];  // per-axis geometry tables (k_q1_axis_tables): [h | 1/h], entry i + 1 = cell i
+  long long axis_tab_inv;     // offset of the 1/h half
   int n_groups;
   Q1Group group[Q1G_MAX_GROUPS];
   // right-hand side: b[v] = sum_o valid(o) * |det J_e| * (rhs_S_const[o] + rhs_S_elem[o] * f[e])
@@ -118,6 +139,7 @@ struct Q1GatherParams
 };
 
 int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate);
+int launch_q1_axis_tables(Launch& L, const GridDev& g, double* const* tabs, long long inv);
 
 // builds the separable right-hand-side tables B_k[i_k] for a product-separable built-in source
 int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long long elem_hi, const FnDev& f, int m,
