@@ -22,6 +22,8 @@
 // (cp.async.bulk.global.shared::cta, SASS UBLKCP) -- HBM sees only full-line sequential writes.  The kernel is
 // persistent-strided over work items with several CTAs per SM so that one CTA's store drains while the
 // others compute.  Deterministic (no atomics, fixed summation order).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.hpp"
 
@@ -143,7 +145,7 @@ constexpr int Q1G_ROWS = 256; // rows (vertices) per work item = threads per CTA
 // element touches, index 3 (oy + sy) + ox + sx; D < 3: both point to the full accumulator array, index delta_index).
 // a[k] = h_k(e) and b[k] = 1 / h_k(e), both zeroed for a cell outside the grid / slab: such an element contributes
 // exact zeros and no branch is needed.
-template <int D, int NG, int KIND0>
+template <int D, int NG, int KIND0, bool CELLDATA>
 __device__ __forceinline__ void q1_add_element(const Q1GatherParams& p, int ox, int oy, int oz, const double (&a)[3],
                                                const double (&b)[3], bool valid, long long e, double* __restrict__ P0,
                                                double* __restrict__ P1)
@@ -156,7 +158,7 @@ __device__ __forceinline__ void q1_add_element(const Q1GatherParams& p, int ox, 
     const Q1Group& G = p.group[gi];
     const int kind = KIND0 >= 0 ? KIND0 : G.kind;
     double cf = G.scale;
-    if (G.coef_elem && kind != Q1G_LAPLACE_TENSOR)
+    if (CELLDATA && G.coef_elem && kind != Q1G_LAPLACE_TENSOR)
       cf *= valid ? __ldg(G.coef + e) : 0.;
     if (kind == Q1G_LAPLACE_SCALAR) {
       // kappa = c I: L_e = c sum_r |det J| / h_r^2 M[r][r]
@@ -190,8 +192,8 @@ __device__ __forceinline__ void q1_add_element(const Q1GatherParams& p, int ox, 
       for (int r = 0; r < D; ++r)
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          const double kap =
-              G.coef_elem ? (valid ? __ldg(G.coef + e * (D * D) + r * D + c) : 0.) : G.kappa[r * 3 + c];
+          const double kap = (CELLDATA && G.coef_elem) ? (valid ? __ldg(G.coef + e * (D * D) + r * D + c) : 0.)
+                                                       : G.kappa[r * 3 + c];
           w[r * 3 + c] = cf * kap * (b[r] * b[c]) * ie;
         }
 #pragma unroll
@@ -257,7 +259,9 @@ __device__ __forceinline__ int q1_store_plane(double* __restrict__ row, const do
 // order and leaves the SM as one TMA bulk store.  Thread t owns row r0 + t: it evaluates the geometry of the 2^D
 // cells around its vertex, forms the row of each cell's local matrix that belongs to the vertex and sums the
 // contributions per stencil column in a fixed order (deterministic, no atomics).
-template <int D, int NG, int KIND0, bool ACCUMULATE>
+// CELLDATA = false: no per-element coefficient / source arrays and no per-cell right-hand-side terms are in play
+// (constant coefficients, separable analytic source): the element index is never formed.
+template <int D, int NG, int KIND0, bool ACCUMULATE, bool CELLDATA>
 __global__ void __launch_bounds__(Q1G_ROWS, 2)
     k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values, double* __restrict__ rhs,
                 long long nrows, int nitems, int stage_doubles)
@@ -329,7 +333,8 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
         }
       // element index of offset o = 0 (may be out of range; only dereferenced when valid)
       const long long e0 =
-          (long long)(ix - 1) + (long long)Nx * ((D > 1 ? iy - 1 : 0) + (long long)Ny * (D > 2 ? iz - 1 : 0));
+          CELLDATA ? (long long)(ix - 1) + (long long)Nx * ((D > 1 ? iy - 1 : 0) + (long long)Ny * (D > 2 ? iz - 1 : 0))
+                   : 0;
       const bool cx0 = ix > 0, cx1 = ix < Nx;
       const bool cy0 = D > 1 && iy > 0, cy1 = D > 1 && iy < Ny, cz0 = D > 2 && iz > 0, cz1 = D > 2 && iz < Nz;
       const bool full_xy = cx0 && cx1 && (D < 2 || (cy0 && cy1));
@@ -370,11 +375,14 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
             const double a[3] = {ha[0][ox], ha[1][oy], ha[2][oz]};
             const double b[3] = {hb[0][ox], hb[1][oy], hb[2][oz]};
             const bool valid = vk[0][ox] && vk[1][oy] && vk[2][oz];
-            const long long e = e0 + ox + (long long)Nx * (oy + (long long)Ny * oz);
+            const long long e = CELLDATA ? e0 + ox + (long long)Nx * (oy + (long long)Ny * oz) : 0;
             if (want_values) {
               if (LAP3) {
-                double w[3] = {fx_b[ox] * yz_aa[oy][oz], fx_a[ox] * yz_ba[oy][oz], fx_a[ox] * yz_ab[oy][oz]};
-                if (p.group[0].coef_elem) {
+                // scheduling fence: keeps the weights of the 8 cells from being formed all at once (register pressure)
+                double t0 = yz_aa[oy][oz];
+                asm volatile("" : "+d"(t0));
+                double w[3] = {fx_b[ox] * t0, fx_a[ox] * yz_ba[oy][oz], fx_a[ox] * yz_ab[oy][oz]};
+                if (CELLDATA && p.group[0].coef_elem) {
                   const double c = valid ? __ldg(p.group[0].coef + e) : 0.;
                   w[0] *= c;
                   w[1] *= c;
@@ -382,9 +390,9 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
                 }
                 q1_add_element_lap3(p.group[0], ox, oy, oz, w, P[oz], P[oz + 1]);
               } else
-                q1_add_element<D, NG, KIND0>(p, ox, oy, oz, a, b, valid, e, P[oz], P[oz + 1]);
+                q1_add_element<D, NG, KIND0, CELLDATA>(p, ox, oy, oz, a, b, valid, e, P[oz], P[oz + 1]);
             }
-            if (!p.rhs_has_const && !p.rhs_has_elem)
+            if (!CELLDATA || (!p.rhs_has_const && !p.rhs_has_elem))
               continue;
             const double ie = a[0] * a[1] * a[2];
             if (p.rhs_has_const)
@@ -415,9 +423,11 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
           const double a[3] = {ha[0][ox], ha[1][oy], 1.};
           const double b[3] = {hb[0][ox], hb[1][oy], 1.};
           const bool valid = vk[0][ox] && vk[1][oy];
-          const long long e = e0 + ox + (long long)Nx * oy;
+          const long long e = CELLDATA ? e0 + ox + (long long)Nx * oy : 0;
           if (want_values)
-            q1_add_element<D, NG, KIND0>(p, ox, oy, 0, a, b, valid, e, P, P);
+            q1_add_element<D, NG, KIND0, CELLDATA>(p, ox, oy, 0, a, b, valid, e, P, P);
+          if (!CELLDATA)
+            continue;
           const double ie = a[0] * a[1];
           if (p.rhs_has_const)
             bsum = fma(ie, p.rhs_S_const[o], bsum);
@@ -560,8 +570,8 @@ int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long lo
   return GDTB_OK;
 }
 
-template <int D, int NG, int KIND0>
-static int launch_q1_gather_dn(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
+template <int D, int NG, int KIND0, bool CELLDATA>
+static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
 {
   const GridDev& g = p.g;
   long long layer_rows = 1;
@@ -578,7 +588,7 @@ static int launch_q1_gather_dn(Launch& L, const Q1GatherParams& p, double* value
   const int stage_doubles = ((Q1G_ROWS * P3<D>::value + 2) + 1) & ~1;
   const bool with_values = NG > 0 && values;
   const size_t smem = with_values ? (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double) : 16;
-  auto kern = accumulate ? k_q1_gather<D, NG, KIND0, true> : k_q1_gather<D, NG, KIND0, false>;
+  auto kern = accumulate ? k_q1_gather<D, NG, KIND0, true, CELLDATA> : k_q1_gather<D, NG, KIND0, false, CELLDATA>;
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
@@ -594,6 +604,20 @@ static int launch_q1_gather_dn(Launch& L, const Q1GatherParams& p, double* value
   L.count++;
   GDTB_CUDA(cudaGetLastError());
   return GDTB_OK;
+}
+
+template <int D, int NG, int KIND0>
+static int launch_q1_gather_dn(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)
+{
+  bool celldata = rhs && p.has_rhs && (p.rhs_has_const || p.rhs_has_elem);
+  for (int g = 0; g < (values ? p.n_groups : 0); ++g)
+    celldata = celldata || p.group[g].coef_elem;
+  // The variant without the per-cell code paths measures SLOWER on B200 (0.788 vs 0.719 ms on C2: straight-line code
+  // lets ptxas keep more values live and it spills), so it is opt-in for experiments only.
+  static const bool allow_lean = std::getenv("GDTB_Q1_LEAN") != nullptr;
+  celldata = celldata || !allow_lean;
+  return celldata ? launch_q1_gather_dnc<D, NG, KIND0, true>(L, p, values, rhs, accumulate)
+                  : launch_q1_gather_dnc<D, NG, KIND0, false>(L, p, values, rhs, accumulate);
 }
 
 template <int D>
