@@ -93,121 +93,7 @@ static void lagrange_1d(int K, double x, double* v, double* dv)
 
 using namespace gdtb;
 
-// ------------------------------------------------------------------------------------------------
-// handles
-// ------------------------------------------------------------------------------------------------
-struct gdtb_ctx
-{
-  int device;
-  cudaStream_t own_stream;
-  Launch launch;
-  Timing timing;
-  int* d_error_flag;
-  bool error_flag_pending; // an asynchronous generic assemble has not been checked yet
-  // per-axis geometry tables of the grids seen so far (assemble_q1_gather.cu), keyed by the grid description
-  struct AxisTables
-  {
-    GridDev grid;
-    double* d_tab;
-    long long offset[3], inv;
-  };
-  std::vector<AxisTables> axis_tables;
-};
-
-struct gdtb_grid
-{
-  gdtb_ctx* ctx;
-  gdtb_grid_desc desc;
-  GridDev dev;
-};
-
-struct gdtb_space
-{
-  gdtb_ctx* ctx;
-  GridDev grid;
-  SpaceDev dev;
-};
-
-struct gdtb_pattern
-{
-  gdtb_ctx* ctx;
-  GridDev grid;
-  SpaceDev test, ansatz;
-  int stencil;
-  long long rows, cols, nnz;
-  long long* d_rowptr;
-  int* d_colidx;
-};
-
-namespace {
-
-struct LoweredForm
-{
-  gdtb_form form;                // cloned descriptor (data pointers replaced by device pointers)
-  std::vector<double*> owned;    // device arrays cloned from host data
-  int filter;
-};
-
-void free_form(LoweredForm& f)
-{
-  for (double* p : f.owned)
-    cudaFree(p);
-  f.owned.clear();
-}
-
-} // namespace
-
-struct gdtb_matop
-{
-  gdtb_ctx* ctx;
-  GridDev grid;
-  SpaceDev test, ansatz;
-  const gdtb_pattern* pattern;
-  double* d_values;
-  bool owns_values;
-  std::vector<LoweredForm> element_forms, coupling_forms, boundary_forms;
-  std::string plan;
-  void* d_forms = nullptr; // lowered FormDev array of the DG gather path
-  size_t d_forms_bytes = 0;
-  // owner-computes-rows slab (multi-GPU): only the rows [row_begin, row_end) live in d_values
-  bool slab;
-  long long row_begin, row_end;   // global row range held by this process
-  long long value_offset, nnz_local;
-  long long row_lo, row_hi, elem_lo, elem_hi; // vertex / element layers along the last direction
-};
-
-struct gdtb_vecfun
-{
-  gdtb_ctx* ctx;
-  GridDev grid;
-  SpaceDev space;
-  double* d_vec;
-  bool owns_vec;
-  std::vector<LoweredForm> forms;
-  double* d_sep_tab; // separable right-hand-side tables for the gather kernel
-  double* d_rule;    // qx | qw | phi for the table kernel
-  bool slab;
-  long long row_begin, row_end;
-  long long row_lo, row_hi, elem_lo, elem_hi;
-  double h_rule[4 * MAX_Q1D];
-  bool rule_uploaded;
-};
-
-struct gdtb_fvop
-{
-  gdtb_ctx* ctx;
-  GridDev grid;
-  SpaceDev space;
-  gdtb_flux flux;
-  bool ghosted;
-  double* d_tmp; // ping-pong buffer for the Euler loop
-  double* d_src; // staging for the *_host entry points
-  double* d_dst;
-  double* d_ext; // per-axis cell extents, axis k at d_ext + ext_offset[k]; reciprocals inv_ext_shift further on
-  long long ext_offset[3];
-  long long inv_ext_shift;
-  int rows_per_block; // tuning knob of the marching kernel (0 = automatic), GDTB_FV_ROWS in the environment
-};
+#include "handles.hpp"
 
 namespace {
 
