@@ -453,6 +453,27 @@ class MatrixOperator:
         check(lib().gdtb_matop_values_device(self._h, C.byref(p)))
         return p.value
 
+    def apply(self, source):
+        """ConstMatrixOperator::apply: range = matrix * source (matrix-based.hh:121-129); host numpy in / out"""
+        src = np.ascontiguousarray(source, dtype=np.float64)
+        if src.size != self.ansatz_space.mapper.size:
+            raise capi.OperatorError("when applying matrix to source and range dofs: shapes do not match")
+        out = np.empty(self.test_space.mapper.size, dtype=np.float64)
+        check(lib().gdtb_matop_apply_host(self._h, dptr(src), dptr(out)))
+        return out
+
+    def apply_inverse(self, range_vector, opts=None, initial_guess=None):
+        """ConstMatrixOperator::apply_inverse (matrix-based.hh:148-159): solves matrix * x = range on the device;
+        returns (x, info) with info = descriptors.SolverInfo"""
+        rhs = np.ascontiguousarray(range_vector, dtype=np.float64)
+        if rhs.size != self.test_space.mapper.size:
+            raise capi.OperatorError("when applying linear solver: shapes do not match")
+        x = np.zeros_like(rhs) if initial_guess is None else np.array(initial_guess, dtype=np.float64, copy=True)
+        info = D.SolverInfo()
+        o = opts if opts is not None else D.solver_opts()
+        check(lib().gdtb_matop_apply_inverse_host(self._h, dptr(rhs), dptr(x), C.byref(o), C.byref(info)))
+        return x, info
+
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             lib().gdtb_matop_destroy(self._h)
@@ -526,3 +547,89 @@ class AdvectionFvOperator:
 def make_advection_fv_operator(numerical_flux, source_space, range_space=None):
     """make_advection_fv_operator<M>(view, numerical_flux, source_space, range_space) (advection-fv.hh:130-141)"""
     return AdvectionFvOperator(numerical_flux, source_space, range_space)
+
+
+# ---- callers on either side of the hot path (SURVEY.md 8f) ---------------------------------------------
+class DirichletConstraints:
+    """dune/gdt/tools/dirichlet-constraints.hh:44-230; boundary_mask bit (2k+s) = domain face with outer normal
+    -e_k / +e_k is a Dirichlet boundary (descriptors.BOUNDARY_ALL = XT::Grid::AllDirichletBoundaryInfo)"""
+
+    def __init__(self, space, boundary_mask=D.BOUNDARY_ALL):
+        self.space = space
+        self._h = C.c_void_p()
+        check(lib().gdtb_dirichlet_create(space.grid.ctx._h, space._h, int(boundary_mask), C.byref(self._h)))
+
+    def dirichlet_DoFs(self):
+        out = np.empty(lib().gdtb_dirichlet_size(self._h), dtype=np.int64)
+        check(lib().gdtb_dirichlet_dofs_download(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    def apply(self, matrix_operator=None, functional=None, only_clear=False, ensure_symmetry=True):
+        """apply(matrix, vector, only_clear, ensure_symmetry) (dirichlet-constraints.hh:122-184)"""
+        check(
+            lib().gdtb_dirichlet_apply(
+                self._h,
+                matrix_operator._h if matrix_operator is not None else None,
+                functional._h if functional is not None else None,
+                int(only_clear),
+                int(ensure_symmetry),
+            )
+        )
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().gdtb_dirichlet_destroy(self._h)
+
+
+def make_dirichlet_constraints(space, boundary_info=D.BOUNDARY_ALL):
+    """make_dirichlet_constraints(space, boundary_info) (examples/stationary-heat-equation.cc:100)"""
+    return DirichletConstraints(space, boundary_info)
+
+
+class BilinearForm:
+    """dune/gdt/operators/bilinear-form.hh:35-470 for (error, error) products: error = discrete function - exact"""
+
+    def __init__(self, space, dofs=None, minus=None):
+        self.space, self.dofs, self.minus = space, dofs, minus
+        self._forms = []
+
+    def append(self, local_form):
+        if not isinstance(local_form, (LocalElementIntegralBilinearForm, D.Form)):
+            raise capi.WrongInputGiven("only element bilinear forms are supported by apply2")
+        self._forms.append(local_form)
+        return self
+
+    __iadd__ = append
+
+    def apply2(self):
+        total = 0.0
+        ctx = self.space.grid.ctx
+        for lf in self._forms:
+            desc = lf if isinstance(lf, D.Form) else lf.descriptor()
+            res = C.c_double()
+            dofs = None if self.dofs is None else np.ascontiguousarray(self.dofs, dtype=np.float64)
+            check(
+                lib().gdtb_bilinear_form_apply2_host(
+                    ctx._h, self.space._h, dptr(dofs) if dofs is not None else None,
+                    C.byref(self.minus) if self.minus is not None else None, C.byref(desc), C.byref(res),
+                )
+            )
+            total += res.value
+        return total
+
+
+def make_bilinear_form(space, dofs=None, minus=None):
+    return BilinearForm(space, dofs, minus)
+
+
+def default_interpolation(function, space, order=None):
+    """default_interpolation(f, space) (interpolations/default.hh:40-83): Lagrange spaces = nodal values, finite-volume
+    spaces = cell averages by a rule of the declared order"""
+    f = GridFunction(function, order or 0)
+    out = np.empty(space.mapper.size, dtype=np.float64)
+    ctx = space.grid.ctx
+    if space.kind == D.SPACE_FV:
+        check(lib().gdtb_fv_interpolate_host(ctx._h, space._h, C.byref(f), dptr(out)))
+    else:
+        check(lib().gdtb_lagrange_interpolate_host(ctx._h, space._h, C.byref(f), dptr(out)))
+    return out

@@ -6,7 +6,7 @@ without a CUDA device, an exception is raised.
 import ctypes as C
 import os
 
-from .descriptors import Flux, Form, Function, GridDesc
+from .descriptors import Flux, Form, Function, GridDesc, SolverInfo, SolverOpts
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgdtb.so")
@@ -137,6 +137,25 @@ PROTOTYPES = {
     "gdtb_fvop_step_async": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, C.c_int64, C.c_int64]),
     "gdtb_fv_interpolate": (C.c_int, [_P, _P, C.POINTER(Function), _P]),
     "gdtb_fv_interpolate_host": (C.c_int, [_P, _P, C.POINTER(Function), _DP]),
+    # callers on either side of the hot path
+    "gdtb_dirichlet_create": (C.c_int, [_P, _P, C.c_uint32, _PP]),
+    "gdtb_dirichlet_destroy": (C.c_int, [_P]),
+    "gdtb_dirichlet_size": (C.c_int64, [_P]),
+    "gdtb_dirichlet_dofs_download": (C.c_int, [_P, _I64P]),
+    "gdtb_dirichlet_device": (C.c_int, [_P, _PP, _PP]),
+    "gdtb_dirichlet_apply": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
+    "gdtb_dirichlet_apply_device": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
+    "gdtb_matop_apply": (C.c_int, [_P, _P, _P]),
+    "gdtb_matop_apply_host": (C.c_int, [_P, _DP, _DP]),
+    "gdtb_csr_apply_device": (C.c_int, [_P, _P, _P, _P, _P]),
+    "gdtb_matop_apply_inverse": (C.c_int, [_P, _P, _P, C.POINTER(SolverOpts), C.POINTER(SolverInfo)]),
+    "gdtb_matop_apply_inverse_host": (C.c_int, [_P, _DP, _DP, C.POINTER(SolverOpts), C.POINTER(SolverInfo)]),
+    "gdtb_csr_apply_inverse_device": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(SolverOpts), C.POINTER(SolverInfo)]),
+    "gdtb_matop_pattern_device": (C.c_int, [_P, _PP, _PP]),
+    "gdtb_bilinear_form_apply2": (C.c_int, [_P, _P, _P, C.POINTER(Function), C.POINTER(Form), _DP]),
+    "gdtb_bilinear_form_apply2_host": (C.c_int, [_P, _P, _DP, C.POINTER(Function), C.POINTER(Form), _DP]),
+    "gdtb_lagrange_interpolate": (C.c_int, [_P, _P, C.POINTER(Function), _P]),
+    "gdtb_lagrange_interpolate_host": (C.c_int, [_P, _P, C.POINTER(Function), _DP]),
 }
 
 _lib = None

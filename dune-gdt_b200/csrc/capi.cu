@@ -30,12 +30,12 @@ int fail(int code, const std::string& msg)
 // host-side numerics needed for lowering: Gauss-Legendre rules on [0,1] and 1D Lagrange tables
 // ([EXT] dune-geometry QuadratureRules / dune-localfunctions Lagrange basis)
 // ------------------------------------------------------------------------------------------------
-static int gauss_points_for_order(int order)
+int gauss_points_for_order(int order)
 {
   return std::max(order, 0) / 2 + 1;
 }
 
-static void gauss_legendre_01(int m, double* x, double* w)
+void gauss_legendre_01(int m, double* x, double* w)
 {
   // Newton iteration on the Legendre polynomial P_m, extended precision, roots ascending
   for (int i = 0; i < m; ++i) {
@@ -61,7 +61,7 @@ static void gauss_legendre_01(int m, double* x, double* w)
   }
 }
 
-static void lagrange_1d(int K, double x, double* v, double* dv)
+void lagrange_1d(int K, double x, double* v, double* dv)
 {
   if (K == 0) {
     v[0] = 1.;
@@ -989,6 +989,8 @@ int gdtb_matop_destroy(gdtb_matop* op)
   if (op->owns_values)
     cudaFree(op->d_values);
   cudaFree(op->d_forms);
+  cudaFree(op->d_own_rowptr);
+  cudaFree(op->d_own_colidx);
   delete op;
   return GDTB_OK;
 }
@@ -1758,3 +1760,23 @@ int gdtb_fv_interpolate_host(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_
 }
 
 } // extern "C"
+
+// ---- internal helpers shared with solve.cu (declared in handles.hpp) ----------------------------------------------
+namespace gdtb {
+int internal_check_ctx(gdtb_ctx* ctx)
+{
+  return check_ctx(ctx);
+}
+int internal_validate_function(const gdtb_function& f, const char* what)
+{
+  return validate_function(f, what);
+}
+int internal_lower_function(gdtb_ctx* ctx, const GridDev& g, gdtb_function& f, LoweredForm& owner)
+{
+  return lower_function(ctx, g, f, owner);
+}
+FnDev internal_to_dev(const gdtb_function& f)
+{
+  return to_dev(f);
+}
+} // namespace gdtb

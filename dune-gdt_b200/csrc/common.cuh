@@ -258,6 +258,39 @@ __host__ __device__ inline double builtin_eval(const FnDev& f, int d, const doub
   }
 }
 
+// gradient of the analytic built-ins (norm evaluation against an exact solution, examples/stationary-heat-equation.cc:
+// 71-85 passes the jacobian lambda explicitly)
+__host__ __device__ inline void builtin_grad(const FnDev& f, int d, const double* x, double* grad)
+{
+  grad[0] = grad[1] = grad[2] = 0.;
+  switch (f.builtin) {
+    case GDTB_BUILTIN_COS_PRODUCT:
+      for (int k = 0; k < d; ++k) {
+        double v = -f.p[0] * f.p[1] * sin(f.p[1] * x[k]);
+        for (int j = 0; j < d; ++j)
+          if (j != k)
+            v *= cos(f.p[1] * x[j]);
+        grad[k] = v;
+      }
+      break;
+    case GDTB_BUILTIN_AFFINE:
+      for (int k = 0; k < d; ++k)
+        grad[k] = f.p[1 + k];
+      break;
+    case GDTB_BUILTIN_GAUSSIAN: {
+      const double t = x[0] - f.p[0];
+      grad[0] = -(t / (f.p[1] * f.p[1])) * exp(-(t * t) / (2. * (f.p[1] * f.p[1])));
+      break;
+    }
+    case GDTB_BUILTIN_QUADRATIC:
+      for (int k = 0; k < d; ++k)
+        grad[k] = 2. * f.p[1] * x[k];
+      break;
+    default:
+      break;
+  }
+}
+
 __device__ inline double fn_scalar(const FnDev& f, int d, long long e, const double* x)
 {
   switch (f.kind) {

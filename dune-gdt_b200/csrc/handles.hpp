@@ -85,6 +85,9 @@ struct gdtb_matop
   std::string plan;
   void* d_forms = nullptr; // lowered FormDev array of the DG gather path
   size_t d_forms_bytes = 0;
+  // CSR pattern materialised on demand for the closed-form CG Q1 operator (Dirichlet constraints, SpMV, solvers)
+  long long* d_own_rowptr = nullptr;
+  int* d_own_colidx = nullptr;
   // owner-computes-rows slab (multi-GPU): only the rows [row_begin, row_end) live in d_values
   bool slab;
   long long row_begin, row_end;   // global row range held by this process
@@ -124,3 +127,14 @@ struct gdtb_fvop
   long long inv_ext_shift;
   int rows_per_block; // tuning knob of the marching kernel (0 = automatic), GDTB_FV_ROWS in the environment
 };
+
+namespace gdtb {
+// host numerics of capi.cu: Gauss-Legendre rules on [0,1] ([EXT] dune-geometry), 1D Lagrange tables
+int gauss_points_for_order(int order);
+void gauss_legendre_01(int m, double* x, double* w);
+void lagrange_1d(int K, double x, double* v, double* dv);
+int internal_check_ctx(gdtb_ctx* ctx);
+int internal_validate_function(const gdtb_function& f, const char* what);
+int internal_lower_function(gdtb_ctx* ctx, const GridDev& g, gdtb_function& f, LoweredForm& owner);
+FnDev internal_to_dev(const gdtb_function& f);
+} // namespace gdtb

@@ -21,6 +21,9 @@ FLUX_LINEAR, FLUX_BURGERS = 0, 1
 NUMFLUX_UPWIND, NUMFLUX_LAX_FRIEDRICHS = 0, 1
 ASSEMBLE_OVERWRITE, ASSEMBLE_ACCUMULATE = 0, 1
 PATTERN_AUTO, PATTERN_SORT_UNIQUE, PATTERN_STRUCTURED = 0, 1, 2
+SOLVER_CG, SOLVER_BICGSTAB = 0, 1
+PRECOND_NONE, PRECOND_JACOBI = 0, 1
+BOUNDARY_ALL = 0x3F
 MAX_TERMS = 4
 
 
@@ -67,6 +70,25 @@ class Form(C.Structure):
 
 class Flux(C.Structure):
     _fields_ = [("kind", C.c_int32), ("numflux", C.c_int32), ("p", C.c_double * 4)]
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("preconditioner", C.c_int32),
+        ("max_iter", C.c_int32),
+        ("check_every", C.c_int32),
+        ("precision", C.c_double),
+    ]
+
+
+class SolverInfo(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int32),
+        ("converged", C.c_int32),
+        ("initial_residual", C.c_double),
+        ("residual", C.c_double),
+    ]
 
 
 # ---- constructors -----------------------------------------------------------------------------
@@ -165,3 +187,9 @@ def flux(kind, numflux=NUMFLUX_UPWIND, params=()):
     for i, x in enumerate(params):
         fl.p[i] = float(x)
     return fl
+
+
+def solver_opts(type=SOLVER_CG, preconditioner=PRECOND_JACOBI, precision=1e-10, max_iter=0, check_every=0):
+    o = SolverOpts()
+    o.type, o.preconditioner, o.max_iter, o.check_every, o.precision = type, preconditioner, max_iter, check_every, precision
+    return o

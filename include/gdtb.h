@@ -334,6 +334,94 @@ int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_en
 int64_t gdtb_matop_local_nnz(const gdtb_matop* op);
 int gdtb_matop_local_rows(const gdtb_matop* op, int64_t* row_begin, int64_t* row_end, int64_t* value_offset);
 
+
+/* ==== callers on either side of the hot path (n1, n2, n4) ====================== */
+
+/* ---- DirichletConstraints (tools/dirichlet-constraints.hh:44-230) ------------------------------------ */
+typedef struct gdtb_dirichlet gdtb_dirichlet;
+#define GDTB_BOUNDARY_ALL 0x3f
+/* make_dirichlet_constraints(space, boundary_info) + the element walk that collects dirichlet_DoFs()
+ * (dirichlet-constraints.hh:85-110): the local DoFs whose local key sits on a sub-entity of a boundary
+ * intersection of Dirichlet type.  boundary_mask: bit (2 k + s) set <=> the domain face with outer normal
+ * -e_k (s = 0) / +e_k (s = 1) is a Dirichlet boundary; GDTB_BOUNDARY_ALL = XT::Grid::AllDirichletBoundaryInfo
+ * (examples/stationary-heat-equation.cc:90).  Periodic directions have no boundary intersections. */
+int gdtb_dirichlet_create(gdtb_ctx* ctx, const gdtb_space* space, uint32_t boundary_mask, gdtb_dirichlet** dc);
+int gdtb_dirichlet_destroy(gdtb_dirichlet* dc);
+/* dirichlet_DoFs().size() and the DoFs in ascending order (std::set iteration order) */
+int64_t gdtb_dirichlet_size(const gdtb_dirichlet* dc);
+int gdtb_dirichlet_dofs_download(const gdtb_dirichlet* dc, int64_t* dofs);
+/* device views: the ascending DoF list and one flag byte per DoF of the space */
+int gdtb_dirichlet_device(const gdtb_dirichlet* dc, const int64_t** d_dofs, const uint8_t** d_flags);
+/* DirichletConstraints::apply(matrix, vector, only_clear, ensure_symmetry) (dirichlet-constraints.hh:122-184):
+ * unit_row (+ unit_col) / clear_row (+ clear_col) for every Dirichlet DoF, vector[DoF] = 0; op or fun may be NULL
+ * (the one-argument overloads).  One pass over the CSR rows, no host round trip. */
+int gdtb_dirichlet_apply(gdtb_dirichlet* dc, gdtb_matop* op, gdtb_vecfun* fun, int only_clear, int ensure_symmetry);
+/* the same on caller-owned device arrays: a CSR matrix given by `pattern` + d_values and/or a vector */
+int gdtb_dirichlet_apply_device(gdtb_dirichlet* dc, const gdtb_pattern* pattern, double* d_values, double* d_vector,
+                                int only_clear, int ensure_symmetry);
+
+/* ---- ConstMatrixOperator::apply / apply_inverse (operators/matrix-based.hh:121-159) ------------------ */
+/* range = matrix * source (matrix_.mv, matrix-based.hh:121-129); device vectors of cols / rows doubles */
+int gdtb_matop_apply(gdtb_matop* op, const double* d_source, double* d_range);
+int gdtb_matop_apply_host(gdtb_matop* op, const double* source, double* range);
+/* the same for a caller-owned CSR matrix */
+int gdtb_csr_apply_device(gdtb_ctx* ctx, const gdtb_pattern* pattern, const double* d_values, const double* d_source,
+                          double* d_range);
+
+enum
+{
+  GDTB_SOLVER_CG = 0,      /* conjugate gradients (symmetric positive definite systems)  */
+  GDTB_SOLVER_BICGSTAB = 1 /* BiCGStab (unsymmetric systems, e.g. NIPDG)                 */
+};
+enum
+{
+  GDTB_PRECOND_NONE = 0,
+  GDTB_PRECOND_JACOBI = 1 /* diagonal scaling */
+};
+/* XT::LA::make_solver(matrix).apply(rhs, solution, opts) [EXT dune-xt; "type", "precision", "max_iter" keys] */
+typedef struct gdtb_solver_opts
+{
+  int32_t type;
+  int32_t preconditioner;
+  int32_t max_iter;    /* <= 0: 10 * rows */
+  int32_t check_every; /* iterations per CUDA-graph replay between two host-side convergence checks; <= 0: 25 */
+  double precision;    /* stop when |r| <= precision * |r_0| (defect reduction); <= 0: 1e-10 */
+} gdtb_solver_opts;
+typedef struct gdtb_solver_info
+{
+  int32_t iterations;
+  int32_t converged;
+  double initial_residual; /* |b - A x_0|_2 */
+  double residual;         /* |b - A x|_2 of the recursively updated residual at exit */
+} gdtb_solver_info;
+/* apply_inverse(range, source, opts) (matrix-based.hh:148-159): solves matrix * d_x = d_rhs on the device, d_x
+ * holds the initial guess on entry.  Fails with GDTB_ERR_OPERATOR when the solver does not converge
+ * (XT::LA::Exceptions::linear_solver_failed -> Exceptions::operator_error); opts / info may be NULL. */
+int gdtb_matop_apply_inverse(gdtb_matop* op, const double* d_rhs, double* d_x, const gdtb_solver_opts* opts,
+                             gdtb_solver_info* info);
+int gdtb_matop_apply_inverse_host(gdtb_matop* op, const double* rhs, double* x, const gdtb_solver_opts* opts,
+                                  gdtb_solver_info* info);
+int gdtb_csr_apply_inverse_device(gdtb_ctx* ctx, const gdtb_pattern* pattern, const double* d_values,
+                                  const double* d_rhs, double* d_x, const gdtb_solver_opts* opts,
+                                  gdtb_solver_info* info);
+/* the CSR pattern the operator's values follow (materialised on first use for the closed-form CG Q1 operator) */
+int gdtb_matop_pattern_device(gdtb_matop* op, const int64_t** d_rowptr, const int32_t** d_colidx);
+
+/* ---- BilinearForm::apply2 for norms (operators/bilinear-form.hh:35-470, examples/stationary-heat-equation.cc:
+ * 116-127) ------------------------------------------------------------------------------------------------ */
+/* result = sum over elements of the element form applied to (e, e), e = u_h - f, u_h the discrete function with
+ * DoF vector d_dofs in `space` (NULL: e = -f) and f an analytic function (NULL: e = u_h): the function is used as a
+ * one-function test and ansatz "basis" (bilinear-form.hh:340-352).  form: LocalLaplaceIntegrand (H^1 semi-norm^2) /
+ * LocalElementProductIntegrand (L^2 norm^2) or sums; quadrature order = integrand order with test = ansatz order
+ * = max(space order, f->order) plus over_integrate.  Deterministic (fixed-order two-stage reduction). */
+int gdtb_bilinear_form_apply2(gdtb_ctx* ctx, const gdtb_space* space, const double* d_dofs, const gdtb_function* f,
+                              const gdtb_form* form, double* result);
+int gdtb_bilinear_form_apply2_host(gdtb_ctx* ctx, const gdtb_space* space, const double* dofs, const gdtb_function* f,
+                                   const gdtb_form* form, double* result);
+/* default_interpolation(f, lagrange_space) (interpolations/default.hh:40-83): DoFs = f at the Lagrange points */
+int gdtb_lagrange_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* d_dofs);
+int gdtb_lagrange_interpolate_host(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* dofs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,11 @@ def lib():
             "orc_fv_interpolate": (None, [G, C.POINTER(Function), DP]),
             "orc_function_eval": (C.c_double, [C.POINTER(Function), C.c_int, DP, C.c_int64]),
             "orc_last_error": (C.c_char_p, []),
+            "orc_dirichlet_dofs": (C.c_int64, [G, C.c_int, C.c_int, C.c_uint32, I64P]),
+            "orc_dirichlet_apply": (C.c_int, [C.c_int64, I64P, I32P, DP, DP, C.c_int64, I64P, C.c_int, C.c_int]),
+            "orc_csr_mv": (None, [C.c_int64, I64P, I32P, DP, DP, DP]),
+            "orc_bilinear_form_apply2": (C.c_double, [G, C.c_int, C.c_int, DP, C.POINTER(Function), C.POINTER(Form)]),
+            "orc_lagrange_interpolate": (None, [G, C.c_int, C.c_int, C.POINTER(Function), DP]),
         }
         for name, (res, args) in protos.items():
             fn = getattr(h, name)
@@ -151,3 +156,47 @@ def fv_interpolate(grid, function):
     u = np.empty(lib().orc_num_elements(C.byref(grid)), dtype=np.float64)
     lib().orc_fv_interpolate(C.byref(grid), C.byref(function), _dp(u))
     return u
+
+
+def _i64p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def dirichlet_dofs(grid, kind, order, boundary_mask=0x3F):
+    n = lib().orc_dirichlet_dofs(C.byref(grid), kind, order, boundary_mask, None)
+    out = np.empty(n, dtype=np.int64)
+    lib().orc_dirichlet_dofs(C.byref(grid), kind, order, boundary_mask, _i64p(out))
+    return out
+
+
+def dirichlet_apply(rowptr, colidx, values, vector, dofs, only_clear=False, ensure_symmetry=True):
+    """in place on copies; returns (values, vector)"""
+    values = None if values is None else np.array(values, dtype=np.float64, copy=True)
+    vector = None if vector is None else np.array(vector, dtype=np.float64, copy=True)
+    dofs = np.ascontiguousarray(dofs, dtype=np.int64)
+    st = lib().orc_dirichlet_apply(
+        len(rowptr) - 1, _i64p(rowptr), colidx.ctypes.data_as(C.POINTER(C.c_int32)),
+        _dp(values) if values is not None else None, _dp(vector) if vector is not None else None, len(dofs), _i64p(dofs),
+        int(only_clear), int(ensure_symmetry))
+    if st != 0:
+        raise RuntimeError(lib().orc_last_error().decode())
+    return values, vector
+
+
+def csr_mv(rowptr, colidx, values, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty(len(rowptr) - 1, dtype=np.float64)
+    lib().orc_csr_mv(len(rowptr) - 1, _i64p(rowptr), colidx.ctypes.data_as(C.POINTER(C.c_int32)), _dp(values), _dp(x), _dp(y))
+    return y
+
+
+def bilinear_form_apply2(grid, kind, order, dofs, f, form):
+    dofs = None if dofs is None else np.ascontiguousarray(dofs, dtype=np.float64)
+    return lib().orc_bilinear_form_apply2(C.byref(grid), kind, order, _dp(dofs) if dofs is not None else None,
+                                          C.byref(f) if f is not None else None, C.byref(form))
+
+
+def lagrange_interpolate(grid, kind, order, f):
+    out = np.empty(space_size(grid, kind, order), dtype=np.float64)
+    lib().orc_lagrange_interpolate(C.byref(grid), kind, order, C.byref(f), _dp(out))
+    return out

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1259,6 +1260,239 @@ double orc_function_eval(const orc_function* f, int dim, const double* x, int64_
 {
   double xx[3] = {x[0], dim > 1 ? x[1] : 0., dim > 2 ? x[2] : 0.};
   return eval_scalar(f, dim, element, xx);
+}
+
+
+/* ---- "next" rows of SURVEY.md section 8f: constraints, mat-vec, norms, interpolation ---------------------------- */
+
+// DirichletConstraints::apply_local (tools/dirichlet-constraints.hh:85-110): for every boundary intersection of
+// Dirichlet type: the local DoFs attached (by their LocalKey) to the intersection itself (codim 1) and to its
+// sub-entities of codim 2..d; collected in a std::set per element, then mapped to global indices and inserted into the
+// global std::set.  Reference cube: a sub-entity is described by the set of pinned coordinates and their values in
+// {0, 1}; it is a sub-entity of face (k, s) iff direction k is pinned to s [EXT dune-geometry ReferenceElement].
+int64_t orc_dirichlet_dofs(const orc_grid* g, int kind, int order, uint32_t boundary_mask, int64_t* out)
+{
+  const Grid gr(g);
+  const Space sp(gr, kind, order);
+  std::set<int64_t> dirichlet_dofs;
+  if (kind != ORC_SPACE_FV && sp.K > 0) {
+    const int d = gr.d, K = sp.K, n1 = K + 1;
+    std::vector<int64_t> gi(sp.nloc);
+    for (int64_t e = 0; e < gr.ne; ++e) {
+      int64_t idx[3];
+      gr.coords(e, idx);
+      std::set<int> local_dofs;
+      for (int k = 0; k < d; ++k)
+        for (int s = 0; s < 2; ++s) { // intersections in the order x-, x+, y-, y+, z-, z+
+          int64_t nb[3];
+          bool boundary = false;
+          const bool neighbor = gr.neighbor(idx, k, s, nb, &boundary);
+          // a periodic wrap face is boundary() && neighbor(): AllDirichletBoundaryInfo does not see it through the
+          // periodic view [EXT]; plain boundary faces are Dirichlet iff their bit is set in the mask
+          if (!boundary || neighbor || !(boundary_mask >> (2 * k + s) & 1))
+            continue;
+          // all sub-entities of the face: pinned sets that contain (k -> s)
+          for (int pinned = 0; pinned < (1 << d); ++pinned) {
+            if (!(pinned >> k & 1))
+              continue;
+            for (int vals = 0; vals < (1 << d); ++vals) {
+              if ((vals & ~pinned) || ((vals >> k & 1) != s))
+                continue;
+              // local keys on exactly this sub-entity: a_j in {0, K} as pinned, strictly inside otherwise
+              for (int i = 0; i < sp.nloc; ++i) {
+                const int a[3] = {i % n1, d > 1 ? (i / n1) % n1 : 0, d > 2 ? i / (n1 * n1) : 0};
+                bool on = true;
+                for (int j = 0; j < d; ++j) {
+                  if (pinned >> j & 1)
+                    on = on && a[j] == ((vals >> j & 1) ? K : 0);
+                  else
+                    on = on && a[j] > 0 && a[j] < K;
+                }
+                if (on)
+                  local_dofs.insert(i);
+              }
+            }
+          }
+        }
+      if (local_dofs.empty())
+        continue;
+      sp.global_indices(idx, gi.data());
+      for (int i : local_dofs)
+        dirichlet_dofs.insert(gi[i]);
+    }
+  }
+  if (out) {
+    int64_t t = 0;
+    for (int64_t dof : dirichlet_dofs)
+      out[t++] = dof;
+  }
+  return (int64_t)dirichlet_dofs.size();
+}
+
+// DirichletConstraints::apply(matrix, vector, only_clear, ensure_symmetry) (dirichlet-constraints.hh:122-184) on a CSR
+// matrix: unit_col / unit_row (clear_col / clear_row) [EXT XT::LA::MatrixInterface], vector[DoF] = 0
+int orc_dirichlet_apply(int64_t rows, const int64_t* rowptr, const int32_t* colidx, double* values, double* vector,
+                        int64_t n_dofs, const int64_t* dofs, int only_clear, int ensure_symmetry)
+{
+  for (int64_t t = 0; t < n_dofs; ++t) {
+    const int64_t dof = dofs[t];
+    if (values) {
+      if (ensure_symmetry) // clear_col / unit_col
+        for (int64_t r = 0; r < rows; ++r)
+          for (int64_t p = rowptr[r]; p < rowptr[r + 1]; ++p)
+            if (colidx[p] == dof)
+              values[p] = (!only_clear && r == dof) ? 1. : 0.;
+      bool diag = false;
+      for (int64_t p = rowptr[dof]; p < rowptr[dof + 1]; ++p) { // clear_row / unit_row
+        diag = diag || colidx[p] == dof;
+        values[p] = (!only_clear && colidx[p] == dof) ? 1. : 0.;
+      }
+      if (!only_clear && !diag) {
+        g_error = "unit_row: the diagonal entry is not part of the pattern";
+        return 1;
+      }
+    }
+    if (vector)
+      vector[dof] = 0.;
+  }
+  return 0;
+}
+
+// matrix_.mv(source, range) (operators/matrix-based.hh:121-129)
+void orc_csr_mv(int64_t rows, const int64_t* rowptr, const int32_t* colidx, const double* values, const double* x,
+                double* y)
+{
+  for (int64_t r = 0; r < rows; ++r) {
+    double s = 0.;
+    for (int64_t p = rowptr[r]; p < rowptr[r + 1]; ++p)
+      s += values[p] * x[colidx[p]];
+    y[r] = s;
+  }
+}
+
+static void builtin_gradient(const orc_function* f, int d, const double* x, double* grad)
+{
+  grad[0] = grad[1] = grad[2] = 0.;
+  if (f->kind != ORC_FN_BUILTIN)
+    return;
+  switch (f->builtin) {
+    case ORC_BUILTIN_COS_PRODUCT:
+      for (int k = 0; k < d; ++k) {
+        double v = -f->p[0] * f->p[1] * std::sin(f->p[1] * x[k]);
+        for (int j = 0; j < d; ++j)
+          if (j != k)
+            v *= std::cos(f->p[1] * x[j]);
+        grad[k] = v;
+      }
+      break;
+    case ORC_BUILTIN_AFFINE:
+      for (int k = 0; k < d; ++k)
+        grad[k] = f->p[1 + k];
+      break;
+    case ORC_BUILTIN_GAUSSIAN: {
+      const double t = x[0] - f->p[0];
+      grad[0] = -(t / (f->p[1] * f->p[1])) * std::exp(-(t * t) / (2. * (f->p[1] * f->p[1])));
+      break;
+    }
+    case ORC_BUILTIN_QUADRATIC:
+      for (int k = 0; k < d; ++k)
+        grad[k] = 2. * f->p[1] * x[k];
+      break;
+    default:
+      break;
+  }
+}
+
+// BilinearForm::apply2 (operators/bilinear-form.hh:340-352, 446-452) with source = range = e = u_h - f: the local
+// function is a one-element "basis" for LocalElementIntegralBilinearForm::apply2 (integrals.hh:97-134), so per element
+// result += sum_q integrand(e, e)(x_q) * (ie * w_q); the element results are summed in walk order.
+double orc_bilinear_form_apply2(const orc_grid* g, int kind, int order, const double* dofs, const orc_function* f,
+                                const orc_form* form)
+{
+  const Grid gr(g);
+  const Space sp(gr, kind, order);
+  const int d = gr.d, n = sp.nloc;
+  const int e_order = std::max(dofs ? sp.K : 0, f ? f->order : 0);
+  const Rule rule(form_order(*form, e_order, element_integrand_order));
+  const int m = rule.m, my = d > 1 ? m : 1, mz = d > 2 ? m : 1;
+  Basis b;
+  b.d = d;
+  b.K = sp.K;
+  b.n = n;
+  std::vector<int64_t> gi(n);
+  double result = 0.;
+  for (int64_t e = 0; e < gr.ne; ++e) {
+    int64_t idx[3];
+    gr.coords(e, idx);
+    double lower[3], ext[3];
+    gr.cell(idx, lower, ext);
+    const double ie = gr.volume(ext);
+    sp.global_indices(idx, gi.data());
+    double local = 0.;
+    for (int qz = 0; qz < mz; ++qz)
+      for (int qy = 0; qy < my; ++qy)
+        for (int qx = 0; qx < m; ++qx) {
+          const double xh[3] = {rule.x[qx], d > 1 ? rule.x[qy] : 0., d > 2 ? rule.x[qz] : 0.};
+          const double w = rule.w[qx] * (d > 1 ? rule.w[qy] : 1.) * (d > 2 ? rule.w[qz] : 1.);
+          double x[3];
+          for (int k = 0; k < 3; ++k)
+            x[k] = lower[k] + xh[k] * ext[k];
+          double val = 0., grad[3] = {0., 0., 0.};
+          if (dofs) {
+            b.evaluate(xh, ext);
+            for (int i = 0; i < n; ++i) {
+              val += dofs[gi[i]] * b.val[i];
+              for (int r = 0; r < d; ++r)
+                grad[r] += dofs[gi[i]] * b.grad[i * 3 + r];
+            }
+          }
+          if (f) {
+            double fg[3];
+            val -= eval_scalar(f, d, e, x);
+            builtin_gradient(f, d, x, fg);
+            for (int r = 0; r < d; ++r)
+              grad[r] -= fg[r];
+          }
+          double v = 0.;
+          for (int t = 0; t < form->n_terms; ++t) {
+            const orc_integrand& in = form->terms[t];
+            if (in.kind == ORC_INT_LAPLACE) {
+              double kappa[9], kg[3];
+              eval_tensor(&in.diffusion, d, e, x, kappa);
+              matvec(d, kappa, grad, kg);
+              v += dot(d, kg, grad);
+            } else
+              v += (eval_scalar(&in.diffusion, d, e, x) * val) * val;
+          }
+          local += v * (ie * w);
+        }
+    result += form->scaling * local;
+  }
+  return result;
+}
+
+// default_interpolation into a Lagrange space (interpolations/default.hh:40-83): DoFs = f at the Lagrange points,
+// elements in walk order, later elements overwrite shared DoFs
+void orc_lagrange_interpolate(const orc_grid* g, int kind, int order, const orc_function* f, double* dofs)
+{
+  const Grid gr(g);
+  const Space sp(gr, kind, order);
+  const int d = gr.d, K = sp.K, n1 = K + 1;
+  std::vector<int64_t> gi(sp.nloc);
+  for (int64_t e = 0; e < gr.ne; ++e) {
+    int64_t idx[3];
+    gr.coords(e, idx);
+    double lower[3], ext[3];
+    gr.cell(idx, lower, ext);
+    sp.global_indices(idx, gi.data());
+    for (int i = 0; i < sp.nloc; ++i) {
+      const int a[3] = {i % n1, d > 1 ? (i / n1) % n1 : 0, d > 2 ? i / (n1 * n1) : 0};
+      double x[3] = {0., 0., 0.};
+      for (int k = 0; k < d; ++k)
+        x[k] = lower[k] + (K > 0 ? double(a[k]) / double(K) : 0.5) * ext[k];
+      dofs[gi[i]] = eval_scalar(f, d, e, x);
+    }
+  }
 }
 
 } // extern "C"

@@ -198,6 +198,23 @@ void orc_fv_interpolate(const orc_grid* g, const orc_function* f, double* u);
 /* evaluate a function descriptor at a global point (scalar view) */
 double orc_function_eval(const orc_function* f, int dim, const double* x, int64_t element);
 
+/* ---- SURVEY.md section 8f "next" rows ------------------------------------------------------------ */
+
+/* DirichletConstraints (tools/dirichlet-constraints.hh:85-110): number of Dirichlet DoFs; if out != NULL the DoFs in
+ * ascending order (std::set).  boundary_mask bit (2k+s): domain face with normal -e_k / +e_k is Dirichlet. */
+int64_t orc_dirichlet_dofs(const orc_grid* g, int kind, int order, uint32_t boundary_mask, int64_t* out);
+/* DirichletConstraints::apply (dirichlet-constraints.hh:122-184) on a CSR matrix and/or a vector (either may be NULL) */
+int orc_dirichlet_apply(int64_t rows, const int64_t* rowptr, const int32_t* colidx, double* values, double* vector,
+                        int64_t n_dofs, const int64_t* dofs, int only_clear, int ensure_symmetry);
+/* ConstMatrixOperator::apply = matrix.mv (operators/matrix-based.hh:121-129) */
+void orc_csr_mv(int64_t rows, const int64_t* rowptr, const int32_t* colidx, const double* values, const double* x,
+                double* y);
+/* BilinearForm::apply2 with source = range = u_h - f (operators/bilinear-form.hh:340-452); dofs or f may be NULL */
+double orc_bilinear_form_apply2(const orc_grid* g, int kind, int order, const double* dofs, const orc_function* f,
+                                const orc_form* form);
+/* default_interpolation into a Lagrange space (interpolations/default.hh:40-83) */
+void orc_lagrange_interpolate(const orc_grid* g, int kind, int order, const orc_function* f, double* dofs);
+
 const char* orc_last_error(void);
 
 #ifdef __cplusplus

@@ -304,3 +304,99 @@ def test_fv_burgers_1d_mass_and_reference_loop(oracle):
         fl_left = np.where((left + v) / 2 > 0, 0.5 * left * left, 0.5 * v * v)
         v = v - dt * N * (fl_right - fl_left)
     np.testing.assert_allclose(u, v, rtol=1e-12, atol=1e-14)
+
+
+# ---- SURVEY 8f "next" rows: constraints, norms, interpolation (the steps around the assembly in config 1) --------
+@pytest.mark.parametrize("dim,n,order,expected", [
+    (2, [5, 4], 1, 2 * (6 + 5) - 4),  # boundary vertices of a 6 x 5 vertex lattice
+    (2, [5, 4], 2, 2 * (11 + 9) - 4),
+    (3, [3, 4, 2], 1, 4 * 5 * 3 - 2 * 3 * 1),
+    (3, [2, 2, 2], 2, 5**3 - 3**3),
+    (1, [7], 3, 2),
+])
+def test_dirichlet_dofs_are_the_boundary_lattice_points(oracle, dim, n, order, expected):
+    """tools/dirichlet-constraints.hh:85-110 with AllDirichletBoundaryInfo: every Lagrange point on the domain boundary,
+    nothing else; the set is ascending and duplicate-free (std::set)"""
+    g = D.grid_desc(0.0, 1.0, n)
+    dofs = oracle.dirichlet_dofs(g, CG, order)
+    assert len(dofs) == expected
+    assert np.all(np.diff(dofs) > 0)
+    # geometric cross-check through the interpolation of the coordinate functions
+    on_boundary = np.zeros(oracle.space_size(g, CG, order), dtype=bool)
+    for k in range(dim):
+        p = [0.0] * 4
+        p[1 + k] = 1.0
+        xk = oracle.lagrange_interpolate(g, CG, order, D.fn_builtin(D.BUILTIN_AFFINE, 1, *p))
+        on_boundary |= (np.abs(xk) < 1e-14) | (np.abs(xk - 1.0) < 1e-14)
+    assert np.array_equal(np.where(on_boundary)[0], dofs)
+
+
+def test_dirichlet_mask_and_non_lagrange_spaces(oracle):
+    g = D.grid_desc(0.0, 1.0, [4, 3])
+    left = oracle.dirichlet_dofs(g, CG, 1, boundary_mask=0b0001)
+    assert np.array_equal(left, np.arange(4) * 5)  # vertices with ix == 0
+    assert len(oracle.dirichlet_dofs(g, FV, 0)) == 0  # P0: the only local key sits in the element interior
+    dg = oracle.dirichlet_dofs(g, DG, 1)
+    assert len(dg) == 2 * (2 * 4 + 2 * 3) - 4  # two Q1 DoFs per boundary face; a corner element's corner DoF counts once
+    gp = D.grid_desc(0.0, 1.0, [4, 3], periodic=1)
+    assert len(oracle.dirichlet_dofs(gp, DG, 1)) == 2 * (2 * 4)  # no boundary intersections in the periodic direction
+
+
+def test_heat_equation_example_with_constraints_and_norms(oracle):
+    """examples/stationary-heat-equation.cc:87-127 step by step with the oracle: assemble, DirichletConstraints::apply,
+    solve, H^1-semi and L^2 errors by BilinearForm::apply2 -- O(h) and O(h^2)"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    exact = D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 1.0, np.pi / 2)
+    h1, l2 = [], []
+    for N in (8, 16, 32):
+        g = D.grid_desc(-1.0, 1.0, [N, N])
+        rp, ci = oracle.pattern(g, (CG, 1))
+        src = D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, np.pi**2 / 2, np.pi / 2)
+        rhs = D.form(D.integrand(D.INT_PRODUCT, diffusion=1.0, weight=src))
+        v, b = oracle.assemble(g, CG, 1, rp, ci, [laplace()], rhs_forms=[rhs])
+        dofs = oracle.dirichlet_dofs(g, CG, 1)
+        v, b = oracle.dirichlet_apply(rp, ci, v, b, dofs)
+        A = sp.csr_matrix((v, ci, rp), shape=(len(b), len(b)))
+        assert abs(A - A.T).max() == 0.0  # unit_col + unit_row keep the symmetry
+        assert np.all(A.diagonal()[dofs] == 1.0) and np.all(b[dofs] == 0.0)
+        u = spla.spsolve(A.tocsc(), b)
+        assert np.all(u[dofs] == 0.0)
+        assert np.allclose(oracle.csr_mv(rp, ci, v, u), b, atol=1e-12)
+        h1.append(np.sqrt(oracle.bilinear_form_apply2(g, CG, 1, u, exact, laplace())))
+        l2.append(np.sqrt(oracle.bilinear_form_apply2(g, CG, 1, u, exact, D.form(D.integrand(D.INT_PRODUCT)))))
+    assert h1[0] / h1[1] == pytest.approx(2.0, rel=0.05) and h1[1] / h1[2] == pytest.approx(2.0, rel=0.05)
+    assert l2[0] / l2[1] == pytest.approx(4.0, rel=0.05) and l2[1] / l2[2] == pytest.approx(4.0, rel=0.05)
+
+
+def test_apply2_norms_of_known_functions(oracle):
+    """BilinearForm::apply2 (operators/bilinear-form.hh:340-452): |x + 2y|_{H1}^2 = 5 |Omega|, ||1||_{L2}^2 = |Omega|;
+    the interpolant of an affine function reproduces it, so the error norms vanish"""
+    g = D.grid_desc([0.0, 0.0], [2.0, 1.0], [6, 5])
+    f = D.fn_builtin(D.BUILTIN_AFFINE, 1, 0.5, 1.0, 2.0)
+    assert oracle.bilinear_form_apply2(g, CG, 1, None, f, laplace()) == pytest.approx(10.0, rel=1e-13)
+    one = D.fn_const(1.0)
+    assert oracle.bilinear_form_apply2(g, CG, 1, None, one, D.form(D.integrand(D.INT_PRODUCT))) == pytest.approx(2.0, rel=1e-13)
+    for order in (1, 2):
+        u = oracle.lagrange_interpolate(g, CG, order, f)
+        assert oracle.bilinear_form_apply2(g, CG, order, u, f, laplace()) < 1e-24
+        assert oracle.bilinear_form_apply2(g, CG, order, u, None, laplace()) == pytest.approx(10.0, rel=1e-13)
+
+
+def test_swipdg_esv2007_h1_errors_via_apply2(oracle):
+    """the ESV2007 table again (.mini:31), the error norm now by the restated BilinearForm::apply2 with the
+    exact solution of declared order 4 instead of the hand-written numpy quadrature above"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    exact = D.fn_builtin(D.BUILTIN_COS_PRODUCT, 4, 1.0, np.pi / 2)
+    for N, ref in zip((8, 16, 32), [2.52e-01, 1.26e-01, 6.30e-02]):
+        g = D.grid_desc(-1.0, 1.0, [N, N])
+        rp, ci = oracle.pattern(g, (DG, 1), stencil=D.STENCIL_ELEMENT_AND_INTERSECTION)
+        el, co, bo, rhs = swipdg_forms()
+        v, b = oracle.assemble(g, DG, 1, rp, ci, [el], [co], [bo], [rhs])
+        u = spla.spsolve(sp.csr_matrix((v, ci, rp), shape=(len(b), len(b))).tocsc(), b)
+        err = np.sqrt(oracle.bilinear_form_apply2(g, DG, 1, u, exact, laplace()))
+        assert err == pytest.approx(_q1_dg_h1_semi_error(N, u), rel=1e-9)
+        assert err == pytest.approx(ref, rel=6e-3), (N, err)
