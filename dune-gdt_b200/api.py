@@ -539,6 +539,22 @@ class AdvectionFvOperator:
     def euler_device(self, d_u, dt, n_steps):
         check(lib().gdtb_fvop_euler(self._h, C.c_void_p(d_u), float(dt), int(n_steps)))
 
+    def append(self, treatment):
+        """append(boundary treatment, param_type, filter) (operators/advection-fv.hh:96-123); `treatment` is a
+        descriptors.fv_boundary(kind, side_mask, a, b)"""
+        check(lib().gdtb_fvop_append_boundary(self._h, C.byref(treatment)))
+        return self
+
+    def estimate_dt(self, state, boundary_data_range=None):
+        """estimate_dt_for_hyperbolic_system(grid_view, state, flux, boundary_data_range) (tools/hyperbolic.hh:38-86)"""
+        u = np.ascontiguousarray(state, dtype=np.float64)
+        if u.size != self.space.mapper.size:
+            raise capi.ShapesDoNotMatch("state vector has the wrong size")
+        rng = None if boundary_data_range is None else np.ascontiguousarray(boundary_data_range, dtype=np.float64)
+        dt = C.c_double()
+        check(lib().gdtb_fv_estimate_dt_host(self._h, dptr(u), None if rng is None else dptr(rng), C.byref(dt)))
+        return dt.value
+
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             lib().gdtb_fvop_destroy(self._h)
@@ -547,6 +563,70 @@ class AdvectionFvOperator:
 def make_advection_fv_operator(numerical_flux, source_space, range_space=None):
     """make_advection_fv_operator<M>(view, numerical_flux, source_space, range_space) (advection-fv.hh:130-141)"""
     return AdvectionFvOperator(numerical_flux, source_space, range_space)
+
+
+def estimate_dt_for_hyperbolic_system(op, state, boundary_data_range=None):
+    """tools/hyperbolic.hh:38-86 (grid view and flux are the operator's)"""
+    return op.estimate_dt(state, boundary_data_range)
+
+
+class TimeStepperMethods:
+    """tools/timestepper/interface.hh TimeStepperMethods (the explicit Runge-Kutta members)"""
+
+    explicit_euler = D.RK_EULER
+    explicit_rungekutta_second_order_ssp = D.RK_SSP2
+    explicit_rungekutta_third_order_ssp = D.RK_SSP3
+    explicit_rungekutta_classic_fourth_order = D.RK_CLASSIC4
+    explicit_rungekutta_other = D.RK_OTHER
+
+
+class ExplicitRungeKuttaTimeStepper:
+    """tools/timestepper/explicit-rungekutta.hh:158-270: u_t = r L(u); the stepper owns the current solution (a host
+    copy of initial_values, stepped on the device)"""
+
+    def __init__(self, op, initial_values, r=1.0, t_0=0.0, method=TimeStepperMethods.explicit_euler, A=None, b=None, c=None):
+        self.op = op
+        self._u = np.array(initial_values, dtype=np.float64, copy=True)
+        if self._u.size != op.space.mapper.size:
+            raise capi.ShapesDoNotMatch("initial values have the wrong size")
+        self._h = C.c_void_p()
+        s = 0
+        arrs = [None, None, None]
+        if method == D.RK_OTHER and A is not None:
+            arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (A, b, c)]
+            s = arrs[1].size
+            if arrs[0].shape != (s, s) or arrs[2].size != s:
+                raise capi.ShapesDoNotMatch("Butcher array: A must be s x s, b and c of size s")
+        self._keep = arrs
+        check(lib().gdtb_rk_create(op._h, int(method), s, *[None if x is None else dptr(x) for x in arrs], float(r), float(t_0),
+                                   C.byref(self._h)))
+        self.dts = []
+
+    def current_time(self):
+        return lib().gdtb_rk_current_time(self._h)
+
+    def current_solution(self):
+        return self._u
+
+    def step(self, dt, max_dt=None):
+        """step(dt, max_dt) (:237-270); returns dt"""
+        ret = C.c_double()
+        check(lib().gdtb_rk_step_host(self._h, dptr(self._u), float(dt), float(dt if max_dt is None else max_dt), C.byref(ret)))
+        self.dts.append(min(dt, dt if max_dt is None else max_dt))
+        return ret.value
+
+    def solve(self, t_end, initial_dt):
+        """TimeStepperInterface::solve(t_end, initial_dt) (tools/timestepper/interface.hh:191-263); returns the dt
+        for the next step; .num_steps holds the number of steps taken"""
+        n = C.c_int64()
+        nxt = C.c_double()
+        check(lib().gdtb_rk_solve_host(self._h, dptr(self._u), float(t_end), float(initial_dt), C.byref(n), C.byref(nxt)))
+        self.num_steps = n.value
+        return nxt.value
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().gdtb_rk_destroy(self._h)
 
 
 # ---- callers on either side of the hot path (SURVEY.md 8f) ---------------------------------------------

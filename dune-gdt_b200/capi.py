@@ -6,7 +6,7 @@ without a CUDA device, an exception is raised.
 import ctypes as C
 import os
 
-from .descriptors import Flux, Form, Function, GridDesc, SolverInfo, SolverOpts
+from .descriptors import Flux, Form, Function, FvBoundary, GridDesc, SolverInfo, SolverOpts
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgdtb.so")
@@ -135,6 +135,16 @@ PROTOTYPES = {
     "gdtb_fvop_set_slab": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gdtb_fvop_ghost_layer_size": (C.c_int64, [_P]),
     "gdtb_fvop_step_async": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, C.c_int64, C.c_int64]),
+    "gdtb_fvop_append_boundary": (C.c_int, [_P, C.POINTER(FvBoundary)]),
+    "gdtb_fv_estimate_dt": (C.c_int, [_P, _P, _DP, _DP]),
+    "gdtb_fv_estimate_dt_host": (C.c_int, [_P, _DP, _DP, _DP]),
+    "gdtb_rk_create": (C.c_int, [_P, C.c_int, C.c_int, _DP, _DP, _DP, C.c_double, C.c_double, _PP]),
+    "gdtb_rk_destroy": (C.c_int, [_P]),
+    "gdtb_rk_current_time": (C.c_double, [_P]),
+    "gdtb_rk_step": (C.c_int, [_P, _P, C.c_double, C.c_double, _DP]),
+    "gdtb_rk_step_host": (C.c_int, [_P, _DP, C.c_double, C.c_double, _DP]),
+    "gdtb_rk_solve": (C.c_int, [_P, _P, C.c_double, C.c_double, _I64P, _DP]),
+    "gdtb_rk_solve_host": (C.c_int, [_P, _DP, C.c_double, C.c_double, _I64P, _DP]),
     "gdtb_fv_interpolate": (C.c_int, [_P, _P, C.POINTER(Function), _P]),
     "gdtb_fv_interpolate_host": (C.c_int, [_P, _P, C.POINTER(Function), _DP]),
     # callers on either side of the hot path

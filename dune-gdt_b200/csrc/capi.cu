@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <string>
 #include <vector>
@@ -1559,6 +1560,14 @@ static void fv_fill_params(const gdtb_fvop* L, FvParams& p)
   p.rows_per_block = L->rows_per_block;
   p.apply_lo = L->grid.layer_lo;
   p.apply_hi = L->grid.layer_hi;
+  p.bnd_ext_mask = L->bnd_ext_mask;
+  p.bnd_nf_mask = L->bnd_nf_mask;
+  for (int i = 0; i < 6; ++i) {
+    p.bnd_ext_a[i] = L->bnd_ext_a[i];
+    p.bnd_ext_b[i] = L->bnd_ext_b[i];
+    p.bnd_nf_a[i] = L->bnd_nf_a[i];
+    p.bnd_nf_b[i] = L->bnd_nf_b[i];
+  }
 }
 
 int gdtb_fvop_destroy(gdtb_fvop* L)
@@ -1570,7 +1579,34 @@ int gdtb_fvop_destroy(gdtb_fvop* L)
   cudaFree(L->d_src);
   cudaFree(L->d_dst);
   cudaFree(L->d_ext);
+  cudaFree(L->d_partial);
   delete L;
+  return GDTB_OK;
+}
+
+int gdtb_fvop_append_boundary(gdtb_fvop* L, const gdtb_fv_boundary* t)
+{
+  if (!L || !t)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_append_boundary: NULL argument");
+  if (t->kind != GDTB_FVBND_EXTRAPOLATION && t->kind != GDTB_FVBND_NUMERICAL_FLUX)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown boundary treatment");
+  const unsigned all = (1u << (2 * L->grid.d)) - 1u;
+  if (t->side_mask & ~all)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "boundary treatment: side_mask names a side the grid does not have");
+  if (t->kind == GDTB_FVBND_EXTRAPOLATION && (t->side_mask & L->bnd_ext_mask))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "two extrapolation treatments on the same boundary side");
+  for (int side = 0; side < 2 * L->grid.d; ++side) {
+    if (!(t->side_mask >> side & 1))
+      continue;
+    if (t->kind == GDTB_FVBND_EXTRAPOLATION) {
+      L->bnd_ext_a[side] = t->a;
+      L->bnd_ext_b[side] = t->b;
+    } else { // numerical boundary fluxes of several treatments add up: g is affine in f(u) . n
+      L->bnd_nf_a[side] += t->a;
+      L->bnd_nf_b[side] += t->b;
+    }
+  }
+  (t->kind == GDTB_FVBND_EXTRAPOLATION ? L->bnd_ext_mask : L->bnd_nf_mask) |= t->side_mask;
   return GDTB_OK;
 }
 
@@ -1700,6 +1736,362 @@ int gdtb_fvop_euler_host(gdtb_fvop* L, double* u, double dt, int64_t n_steps)
   cudaStream_t s = L->ctx->launch.stream;
   GDTB_CUDA(cudaMemcpyAsync(L->d_src, u, bytes, cudaMemcpyHostToDevice, s));
   GDTB_TRY(gdtb_fvop_euler(L, L->d_src, dt, n_steps));
+  GDTB_CUDA(cudaMemcpyAsync(u, L->d_src, bytes, cudaMemcpyDeviceToHost, s));
+  GDTB_CUDA(cudaStreamSynchronize(s));
+  return GDTB_OK;
+}
+
+// ---- estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh:38-86) ------------------------------------------------
+int gdtb_fv_estimate_dt(gdtb_fvop* L, const double* d_u, const double* boundary_data_range, double* dt)
+{
+  if (!L || !d_u || !dt)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fv_estimate_dt: NULL argument");
+  GDTB_TRY(check_ctx(L->ctx));
+  if (L->ghosted)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "gdtb_fv_estimate_dt: not available on a slab (reduce over the ranks yourself)");
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((L->grid.ne + 255) / 256, (long long)L->ctx->launch.sm_count * 8));
+  const int max_blocks = L->ctx->launch.sm_count * 8;
+  if (!L->d_partial && cudaMalloc(&L->d_partial, sizeof(double) * 3 * (size_t)max_blocks) != cudaSuccess)
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (dt estimate)");
+  FvParams p;
+  fv_fill_params(L, p);
+  GDTB_TRY(launch_fv_dt_reduce(L->ctx->launch, p, d_u, L->d_partial, blocks));
+  std::vector<double> h(3 * (size_t)blocks);
+  GDTB_CUDA(cudaMemcpyAsync(h.data(), L->d_partial, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, L->ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
+  // hyperbolic.hh:47-48: {numeric_limits<R>::max(), numeric_limits<R>::min()} -- min() is the smallest positive normal
+  double data_minimum = boundary_data_range ? boundary_data_range[0] : std::numeric_limits<double>::max();
+  double data_maximum = boundary_data_range ? boundary_data_range[1] : std::numeric_limits<double>::min();
+  double perimeter_over_volume = std::numeric_limits<double>::min();
+  for (int i = 0; i < blocks; ++i) {
+    data_minimum = std::min(data_minimum, h[3 * i]);
+    data_maximum = std::max(data_maximum, h[3 * i + 1]);
+    perimeter_over_volume = std::max(perimeter_over_volume, h[3 * i + 2]);
+  }
+  if (!(data_minimum < data_maximum)) // :62-64
+    data_maximum = data_minimum + 1e-6 * data_minimum;
+  // :66-74: Gauss rule of order flux.order() on the one-cell grid [min, max]
+  double max_flux_derivative = std::numeric_limits<double>::min();
+  const int m = gauss_points_for_order(L->flux.kind == GDTB_FLUX_LINEAR ? 1 : 2);
+  double qx[MAX_Q1D], qw[MAX_Q1D];
+  gauss_legendre_01(m, qx, qw);
+  for (int q = 0; q < m; ++q) {
+    const double uq = data_minimum + qx[q] * (data_maximum - data_minimum);
+    for (int ss = 0; ss < L->grid.d; ++ss) {
+      const double df = L->flux.kind == GDTB_FLUX_LINEAR ? L->flux.p[ss] : uq;
+      max_flux_derivative = std::max(max_flux_derivative, std::fabs(df));
+    }
+  }
+  *dt = 1. / (perimeter_over_volume * max_flux_derivative);
+  return GDTB_OK;
+}
+
+int gdtb_fv_estimate_dt_host(gdtb_fvop* L, const double* u, const double* boundary_data_range, double* dt)
+{
+  if (!L || !u || !dt)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fv_estimate_dt_host: NULL argument");
+  GDTB_TRY(check_ctx(L->ctx));
+  GDTB_TRY(fv_stage(L));
+  GDTB_CUDA(cudaMemcpyAsync(L->d_src, u, sizeof(double) * (size_t)fv_local_size(L), cudaMemcpyHostToDevice, L->ctx->launch.stream));
+  return gdtb_fv_estimate_dt(L, L->d_src, boundary_data_range, dt);
+}
+
+// ---- ExplicitRungeKuttaTimeStepper (tools/timestepper/explicit-rungekutta.hh:158-270) ------------------------------
+int gdtb_rk_create(gdtb_fvop* L, int method, int num_stages, const double* A, const double* b, const double* c, double r,
+                   double t0, gdtb_rk** out)
+{
+  if (!L || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_create: NULL argument");
+  GDTB_TRY(check_ctx(L->ctx));
+  if (L->ghosted)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "gdtb_rk_create: on a slab drive the stages with gdtb_fvop_step_async and exchange ghost layers in between");
+  auto ts = new gdtb_rk();
+  ts->op = L;
+  ts->r = r;
+  ts->t = t0;
+  // internal::ButcherArrayProvider (:63-141)
+  static const double A2[] = {0., 0., 1., 0.}, b2[] = {0.5, 0.5}, c2[] = {0., 1.};
+  static const double A3[] = {0., 0., 0., 1., 0., 0., 0.25, 0.25, 0.}, b3[] = {1. / 6., 1. / 6., 2. / 3.}, c3[] = {0., 1., 0.5};
+  static const double A4[] = {0., 0., 0., 0., 0.5, 0., 0., 0., 0., 0.5, 0., 0., 0., 0., 1., 0.};
+  static const double b4[] = {1. / 6., 1. / 3., 1. / 3., 1. / 6.}, c4[] = {0., 0.5, 0.5, 1.};
+  static const double A1[] = {0.}, b1[] = {1.}, c1[] = {0.};
+  switch (method) {
+    case GDTB_RK_EULER: num_stages = 1, A = A1, b = b1, c = c1; break;
+    case GDTB_RK_SSP2: num_stages = 2, A = A2, b = b2, c = c2; break;
+    case GDTB_RK_SSP3: num_stages = 3, A = A3, b = b3, c = c3; break;
+    case GDTB_RK_CLASSIC4: num_stages = 4, A = A4, b = b4, c = c4; break;
+    case GDTB_RK_OTHER:
+      if (!A || !b || !c) {
+        delete ts;
+        return fail(GDTB_ERR_NOT_IMPLEMENTED, "You have to provide a Butcher array in ExplicitRungeKuttaTimeStepper's constructor for this method!"); // :40-58
+      }
+      break;
+    default: delete ts; return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown TimeStepperMethods value");
+  }
+  if (num_stages < 1 || num_stages > GDTB_RK_MAX_STAGES) {
+    delete ts;
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_create: 1 <= num_stages <= GDTB_RK_MAX_STAGES");
+  }
+  ts->s = num_stages;
+  for (int i = 0; i < num_stages; ++i) {
+    ts->b[i] = b[i];
+    ts->c[i] = c[i];
+    for (int j = 0; j < num_stages; ++j) {
+      ts->A[i * num_stages + j] = A[i * num_stages + j];
+      // FloatCmp::ne(A[ii][jj], 0.) for jj >= ii (:216-222)
+      if (j >= i && std::fabs(A[i * num_stages + j]) > 8. * std::numeric_limits<double>::epsilon()) {
+        delete ts;
+        return fail(GDTB_ERR_INVALID_ARGUMENT, "A has to be a lower triangular matrix with 0 on the main diagonal");
+      }
+    }
+  }
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  bool ok = cudaMalloc(&ts->d_ui, bytes) == cudaSuccess;
+  for (int i = 0; ok && i < (num_stages > 1 ? num_stages : 0); ++i)
+    ok = cudaMalloc(&ts->d_k[i], bytes) == cudaSuccess;
+  if (!ok) {
+    gdtb_rk_destroy(ts);
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (Runge-Kutta stages)");
+  }
+  *out = ts;
+  return GDTB_OK;
+}
+
+int gdtb_rk_destroy(gdtb_rk* ts)
+{
+  if (!ts)
+    return GDTB_OK;
+  cudaSetDevice(ts->op->ctx->device);
+  cudaFree(ts->d_ui);
+  for (double* k : ts->d_k)
+    cudaFree(k);
+  delete ts;
+  return GDTB_OK;
+}
+
+double gdtb_rk_current_time(const gdtb_rk* ts)
+{
+  return ts ? ts->t : 0.;
+}
+
+// enqueue one step of length actual_dt: reads `in`, leaves the new solution in `outp` (Euler: outp != in, fused
+// apply + update; multi-stage: outp == in, updated in place)
+static int rk_enqueue_step(gdtb_rk* ts, double* in, double* outp, double actual_dt)
+{
+  gdtb_fvop* L = ts->op;
+  Launch& la = L->ctx->launch;
+  FvParams p;
+  fv_fill_params(L, p);
+  const int s = ts->s;
+  if (s == 1) {
+    // u_n + k_0 (r dt b_0) with k_0 = L(u_n): the fused kernel's u - acc * dt' with dt' = -(r dt b_0) (same roundings)
+    p.euler = 1;
+    p.dt = -(ts->r * actual_dt * ts->b[0]);
+    return launch_fv_apply(la, p, in, outp);
+  }
+  const long long n = fv_local_size(L);
+  for (int ii = 0; ii < s; ++ii) {
+    const double* ui = in; // stage 0: u_i = u_n
+    if (ii > 0) {
+      // u_i = u_n + sum_{jj < ii} k_jj (dt r A[ii][jj]) (:248-250); terms with A[ii][jj] == 0 add exact zeros and are skipped
+      RkAxpyParams q;
+      q.n = n;
+      q.nv = 0;
+      const double* base = in;
+      bool wrote = false;
+      for (int jj = 0; jj < ii; ++jj) {
+        const double coef = actual_dt * ts->r * ts->A[ii * s + jj];
+        if (coef == 0.)
+          continue;
+        q.v[q.nv] = ts->d_k[jj];
+        q.c[q.nv] = coef;
+        if (++q.nv == RK_MAX_TERMS) {
+          GDTB_TRY(launch_rk_axpy(la, q, base, ts->d_ui));
+          base = ts->d_ui;
+          q.nv = 0;
+          wrote = true;
+        }
+      }
+      if (q.nv > 0) {
+        GDTB_TRY(launch_rk_axpy(la, q, base, ts->d_ui));
+        wrote = true;
+      }
+      ui = wrote ? ts->d_ui : in;
+    }
+    GDTB_TRY(launch_fv_apply(la, p, ui, ts->d_k[ii])); // k_ii = L(u_i) (:253-255; the operator is autonomous)
+  }
+  // u_n += sum_ii k_ii (r dt b_ii) (:261-263)
+  RkAxpyParams q;
+  q.n = n;
+  q.nv = 0;
+  for (int ii = 0; ii < s; ++ii) {
+    const double coef = ts->r * actual_dt * ts->b[ii];
+    if (coef == 0.)
+      continue;
+    q.v[q.nv] = ts->d_k[ii];
+    q.c[q.nv] = coef;
+    if (++q.nv == RK_MAX_TERMS) {
+      GDTB_TRY(launch_rk_axpy(la, q, in, in));
+      q.nv = 0;
+    }
+  }
+  if (q.nv > 0)
+    GDTB_TRY(launch_rk_axpy(la, q, in, in));
+  (void)outp;
+  return GDTB_OK;
+}
+
+int gdtb_rk_step(gdtb_rk* ts, double* d_u, double dt, double max_dt, double* returned_dt)
+{
+  if (!ts || !d_u)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_step: NULL argument");
+  gdtb_fvop* L = ts->op;
+  GDTB_TRY(check_ctx(L->ctx));
+  const double actual_dt = std::min(dt, max_dt); // :239
+  cudaStream_t st = L->ctx->launch.stream;
+  if (ts->s == 1) {
+    GDTB_TRY(rk_enqueue_step(ts, d_u, ts->d_ui, actual_dt));
+    GDTB_CUDA(cudaMemcpyAsync(d_u, ts->d_ui, sizeof(double) * (size_t)fv_local_size(L), cudaMemcpyDeviceToDevice, st));
+  } else
+    GDTB_TRY(rk_enqueue_step(ts, d_u, d_u, actual_dt));
+  GDTB_CUDA(cudaStreamSynchronize(st));
+  ts->t += actual_dt; // :266
+  if (returned_dt)
+    *returned_dt = dt; // :268
+  return GDTB_OK;
+}
+
+namespace {
+// XT::Common::FloatCmp::{lt,gt} (numpy style, default epsilons) [EXT dune-xt]: eq(a,b) = |a-b| <= eps + eps |b|,
+// eps = 8 * 2^-52 (Dune::FloatCmp::DefaultEpsilon<double>)
+inline bool floatcmp_eq(double a, double b)
+{
+  const double eps = 8. * std::numeric_limits<double>::epsilon();
+  return std::fabs(a - b) <= eps + eps * std::fabs(b);
+}
+inline bool floatcmp_lt(double a, double b)
+{
+  return !floatcmp_eq(a, b) && a < b;
+}
+inline bool floatcmp_gt(double a, double b)
+{
+  return !floatcmp_eq(a, b) && a > b;
+}
+} // namespace
+
+int gdtb_rk_solve(gdtb_rk* ts, double* d_u, double t_end, double initial_dt, int64_t* n_steps, double* next_dt)
+{
+  if (!ts || !d_u)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_solve: NULL argument");
+  if (!(initial_dt > 0.))
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_solve: initial_dt must be positive");
+  gdtb_fvop* L = ts->op;
+  GDTB_TRY(check_ctx(L->ctx));
+  Launch& la = L->ctx->launch;
+  cudaStream_t st = la.stream;
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  // the step sequence of TimeStepperInterface::solve (interface.hh:216-255) depends on t alone: plan it on the host
+  double dt = initial_dt, t = ts->t;
+  std::vector<double> plan;
+  while (floatcmp_lt(t, t_end)) {
+    double max_dt = dt;
+    if (floatcmp_gt(t + dt, t_end))
+      max_dt = t_end - t;
+    plan.push_back(std::min(dt, max_dt));
+    t += plan.back();
+  }
+  // full steps run as replays of one captured graph (Euler: two steps per graph, ping-pong d_u -> buffer -> d_u)
+  size_t n_full = 0;
+  while (n_full < plan.size() && plan[n_full] == initial_dt)
+    ++n_full;
+  const int per_graph = ts->s == 1 ? 2 : 1;
+  const size_t replays = n_full >= 8 ? n_full / per_graph : 0;
+  int status = GDTB_OK;
+  double* cur = d_u; // where the current solution lives (Euler ping-pong)
+  size_t done = 0;
+  if (replays > 0) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const bool timing_was = L->ctx->timing.enabled;
+    L->ctx->timing.enabled = false; // event records are not capturable
+    const long long count_before = la.count;
+    GDTB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    if (ts->s == 1) {
+      status = rk_enqueue_step(ts, d_u, ts->d_ui, initial_dt);
+      if (status == GDTB_OK)
+        status = rk_enqueue_step(ts, ts->d_ui, d_u, initial_dt);
+    } else
+      status = rk_enqueue_step(ts, d_u, d_u, initial_dt);
+    cudaError_t err = cudaStreamEndCapture(st, &graph);
+    const long long launched = la.count - count_before;
+    la.count = count_before;
+    L->ctx->timing.enabled = timing_was;
+    if (status == GDTB_OK && err != cudaSuccess)
+      status = fail(GDTB_ERR_CUDA, std::string("Runge-Kutta graph capture: ") + cudaGetErrorString(err));
+    if (status == GDTB_OK && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)
+      status = fail(GDTB_ERR_CUDA, "Runge-Kutta graph instantiation failed");
+    for (size_t k = 0; status == GDTB_OK && k < replays; ++k) {
+      if (cudaGraphLaunch(exec, st) != cudaSuccess)
+        status = fail(GDTB_ERR_CUDA, "Runge-Kutta graph launch failed");
+      la.count += launched;
+    }
+    done = replays * per_graph;
+    if (exec)
+      cudaGraphExecDestroy(exec);
+    if (graph)
+      cudaGraphDestroy(graph);
+  }
+  for (size_t k = done; status == GDTB_OK && k < plan.size(); ++k) {
+    if (ts->s == 1) {
+      double* nxt = cur == d_u ? ts->d_ui : d_u;
+      status = rk_enqueue_step(ts, cur, nxt, plan[k]);
+      cur = nxt;
+    } else
+      status = rk_enqueue_step(ts, d_u, d_u, plan[k]);
+  }
+  if (status == GDTB_OK && cur != d_u)
+    GDTB_CUDA(cudaMemcpyAsync(d_u, cur, bytes, cudaMemcpyDeviceToDevice, st));
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (status == GDTB_OK && e2 != cudaSuccess)
+    status = fail(GDTB_ERR_CUDA, std::string("gdtb_rk_solve: ") + cudaGetErrorString(e2));
+  if (status != GDTB_OK)
+    return status;
+  for (double a : plan) // t += actual_dt per step (:266), same roundings as the planning loop
+    ts->t += a;
+  if (n_steps)
+    *n_steps = (int64_t)plan.size();
+  if (next_dt)
+    *next_dt = dt; // step() returns the dt it was given (interface.hh:226, explicit-rungekutta.hh:268)
+  return GDTB_OK;
+}
+
+int gdtb_rk_step_host(gdtb_rk* ts, double* u, double dt, double max_dt, double* returned_dt)
+{
+  if (!ts || !u)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_step_host: NULL argument");
+  gdtb_fvop* L = ts->op;
+  GDTB_TRY(check_ctx(L->ctx));
+  GDTB_TRY(fv_stage(L));
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  cudaStream_t s = L->ctx->launch.stream;
+  GDTB_CUDA(cudaMemcpyAsync(L->d_src, u, bytes, cudaMemcpyHostToDevice, s));
+  GDTB_TRY(gdtb_rk_step(ts, L->d_src, dt, max_dt, returned_dt));
+  GDTB_CUDA(cudaMemcpyAsync(u, L->d_src, bytes, cudaMemcpyDeviceToHost, s));
+  GDTB_CUDA(cudaStreamSynchronize(s));
+  return GDTB_OK;
+}
+
+int gdtb_rk_solve_host(gdtb_rk* ts, double* u, double t_end, double initial_dt, int64_t* n_steps, double* next_dt)
+{
+  if (!ts || !u)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_solve_host: NULL argument");
+  gdtb_fvop* L = ts->op;
+  GDTB_TRY(check_ctx(L->ctx));
+  GDTB_TRY(fv_stage(L));
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  cudaStream_t s = L->ctx->launch.stream;
+  GDTB_CUDA(cudaMemcpyAsync(L->d_src, u, bytes, cudaMemcpyHostToDevice, s));
+  GDTB_TRY(gdtb_rk_solve(ts, L->d_src, t_end, initial_dt, n_steps, next_dt));
   GDTB_CUDA(cudaMemcpyAsync(u, L->d_src, bytes, cudaMemcpyDeviceToHost, s));
   GDTB_CUDA(cudaStreamSynchronize(s));
   return GDTB_OK;

@@ -127,8 +127,28 @@ __global__ void __launch_bounds__(256) k_fv_apply(const __grid_constant__ FvPara
         int t = idx[k] + (s ? 1 : -1);
         long long nloc;
         if (t < 0 || t >= n[k]) {
-          if (!(g.periodic & (1 << k)))
-            continue; // domain boundary without neighbour: no coupling operator (advection-fv.hh:77-82)
+          if (!(g.periodic & (1 << k))) {
+            // domain boundary without neighbour: no coupling operator (advection-fv.hh:77-82), but the appended
+            // boundary treatments (local/operators/advection-fv.hh:281-296, 418-443): g * (|I| / |E|)
+            const int side = 2 * k + s;
+            double gb = 0.;
+            bool any = false;
+            if (p.bnd_ext_mask >> side & 1) {
+              const double v = p.bnd_ext_a[side] * ue + p.bnd_ext_b[side];
+              gb += numerical_flux_axis<D>(p.flux, p.lf_lambda_linear, k, s ? 1. : -1., ue, v);
+              any = true;
+            }
+            if (p.bnd_nf_mask >> side & 1) {
+              gb += p.bnd_nf_a[side] * (flux_k(p.flux, k, ue) * (s ? 1. : -1.)) + p.bnd_nf_b[side];
+              any = true;
+            }
+            if (any) {
+              contrib[nc] = gb * (hI[k] / vol);
+              key[nc] = e * 8 + side;
+              ++nc;
+            }
+            continue;
+          }
           t = (t + n[k]) % n[k];
         }
         if (t == idx[k])
@@ -197,6 +217,27 @@ __device__ __forceinline__ double flux_plus(const FvParams& p, int k, double uL,
   return (0.5 * uL * uL + 0.5 * uU * uU) * 0.5 + (uL - uU) * (0.5 * fmax(fabs(uL), fabs(uU)));
 }
 
+// Flux along +e_k through the domain boundary face on side s (0: lower, 1: upper) of a cell with value uc, produced by
+// the boundary treatments of that side.  The reference evaluates g with the outer normal n = -+e_k and adds
+// g |I| / |E| to the cell (local/operators/advection-fv.hh:293, 440); along +e_k that is g for s = 1 and -g for s = 0.
+// Extrapolation: the ghost value v = a uc + b takes the neighbour's place in flux_plus (same orientation argument).
+template <int NUMFLUX, int KIND>
+__device__ __forceinline__ double bnd_flux_plus(const FvParams& p, int k, int s, double uc)
+{
+  const int side = 2 * k + s;
+  double G = 0.;
+  if (p.bnd_ext_mask >> side & 1) {
+    const double v = p.bnd_ext_a[side] * uc + p.bnd_ext_b[side];
+    G += s ? flux_plus<NUMFLUX, KIND>(p, k, uc, v) : flux_plus<NUMFLUX, KIND>(p, k, v, uc);
+  }
+  if (p.bnd_nf_mask >> side & 1) {
+    const double fk = KIND == GDTB_FLUX_LINEAR ? p.flux.p[k] * uc : 0.5 * uc * uc;
+    const double sgn = s ? 1. : -1.;
+    G += (p.bnd_nf_a[side] * (fk * sgn) + p.bnd_nf_b[side]) * sgn;
+  }
+  return G;
+}
+
 constexpr int FV_BATCH = 4;
 
 template <int C>
@@ -228,7 +269,7 @@ __device__ __forceinline__ void st_cols(double* q, const double (&v)[C])
 // advection-fv.hh:147-152 equals g / ext_k on axis-aligned cells up to rounding.  Faces that do not exist (domain
 // boundary without periodicity) get the coefficient 0.  Loads are issued FV_BATCH layers at a time before the first
 // flux of the batch is evaluated (memory-level parallelism).
-template <int D, int NUMFLUX, int KIND, int C>
+template <int D, int NUMFLUX, int KIND, int C, bool BND>
 __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvParams p, const double* __restrict__ u,
                                                   double* __restrict__ out, int rows)
 {
@@ -261,17 +302,22 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
   const int d_xp = C - 1 + (x_hi ? (x_hi_edge ? 1 - n0 : 1) : 0);    // relative to the first cell
   double rx[C];
   ldg_cols<C>(p.inv_ext[0] + ix, rx);
-  const double cxl = x_lo ? rx[0] : 0., cxh = x_hi ? rx[C - 1] : 0.;
+  const unsigned bnd_mask = BND ? (p.bnd_ext_mask | p.bnd_nf_mask) : 0u; // sides with a boundary treatment
+  const bool bx_lo = BND && !x_lo && (bnd_mask & 1u), bx_hi = BND && !x_hi && (bnd_mask & 2u);
+  const double cxl = (x_lo || bx_lo) ? rx[0] : 0., cxh = (x_hi || bx_hi) ? rx[C - 1] : 0.;
   long long d_ym = 0, d_yp = 0;
   double cyl = 0., cyh = 0.;
+  bool by_lo = false, by_hi = false;
   if (D == 3) {
     const bool y_lo_edge = iy == 0, y_hi_edge = iy == n1 - 1;
     const bool y_lo = !y_lo_edge || per1, y_hi = !y_hi_edge || per1;
+    by_lo = BND && !y_lo && (bnd_mask & 4u);
+    by_hi = BND && !y_hi && (bnd_mask & 8u);
     d_ym = y_lo ? (y_lo_edge ? (long long)(n1 - 1) * n0 : -(long long)n0) : 0;
     d_yp = y_hi ? (y_hi_edge ? -(long long)(n1 - 1) * n0 : (long long)n0) : 0;
     const double ry = __ldg(p.inv_ext[1] + iy);
-    cyl = y_lo ? ry : 0.;
-    cyh = y_hi ? ry : 0.;
+    cyl = (y_lo || by_lo) ? ry : 0.;
+    cyh = (y_hi || by_hi) ? ry : 0.;
   }
 
   const double* pc = u + (long long)(j0 + shift) * plane + col; // own cells, layer j
@@ -288,7 +334,8 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
     ldg_cols<C>(pc + off, ub);
 #pragma unroll
     for (int c = 0; c < C; ++c)
-      G_low[c] = has ? flux_plus<NUMFLUX, KIND>(p, last, ub[c], uc[c]) : 0.;
+      G_low[c] = has ? flux_plus<NUMFLUX, KIND>(p, last, ub[c], uc[c])
+                     : (BND ? bnd_flux_plus<NUMFLUX, KIND>(p, last, 0, uc[c]) : 0.);
   }
   // layers whose upper neighbour is simply the next layer in memory: all but the top layer of an unpartitioned grid
   // (on a slab the ghost layer above carries the periodic neighbour; without periodicity the top face does not exist)
@@ -311,17 +358,18 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       double res[C], gx[C + 1];
-      gx[0] = flux_plus<NUMFLUX, KIND>(p, 0, xl[r], uc[0]);
+      gx[0] = bx_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 0, 0, uc[0]) : flux_plus<NUMFLUX, KIND>(p, 0, xl[r], uc[0]);
       if (C == 2)
         gx[1] = flux_plus<NUMFLUX, KIND>(p, 0, uc[0], uc[C - 1]);
-      gx[C] = flux_plus<NUMFLUX, KIND>(p, 0, uc[C - 1], xr[r]);
+      gx[C] = bx_hi ? bnd_flux_plus<NUMFLUX, KIND>(p, 0, 1, uc[C - 1]) : flux_plus<NUMFLUX, KIND>(p, 0, uc[C - 1], xr[r]);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const double G_up = flux_plus<NUMFLUX, KIND>(p, last, uc[c], un[r][c]);
         // faces between the thread's own cells always exist; the outer ones carry the (possibly zero) coefficient
         double acc = gx[c + 1] * (c == C - 1 ? cxh : rx[c]) - gx[c] * (c == 0 ? cxl : rx[c]);
         if (D == 3)
-          acc += flux_plus<NUMFLUX, KIND>(p, 1, uc[c], yr[r][c]) * cyh - flux_plus<NUMFLUX, KIND>(p, 1, yl[r][c], uc[c]) * cyl;
+          acc += (by_hi ? bnd_flux_plus<NUMFLUX, KIND>(p, 1, 1, uc[c]) : flux_plus<NUMFLUX, KIND>(p, 1, uc[c], yr[r][c])) * cyh
+                 - (by_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 1, 0, uc[c]) : flux_plus<NUMFLUX, KIND>(p, 1, yl[r][c], uc[c])) * cyl;
         acc += (G_up - G_low[c]) * rl[r];
         res[c] = p.euler ? uc[c] - acc * p.dt : acc; // u_n - L(u_n) dt (examples/mpi...cc:154)
         G_low[c] = G_up;
@@ -339,10 +387,11 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
     const bool has_up = !top || perl;
     double un[C], yl[C], yr[C], res[C], gx[C + 1];
     ldg_cols<C>(pc + ((top && !p.ghosted) ? (has_up ? (1 - (long long)nl) * plane : 0) : plane), un);
-    gx[0] = flux_plus<NUMFLUX, KIND>(p, 0, __ldg(pc + d_xm), uc[0]);
+    gx[0] = bx_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 0, 0, uc[0]) : flux_plus<NUMFLUX, KIND>(p, 0, __ldg(pc + d_xm), uc[0]);
     if (C == 2)
       gx[1] = flux_plus<NUMFLUX, KIND>(p, 0, uc[0], uc[C - 1]);
-    gx[C] = flux_plus<NUMFLUX, KIND>(p, 0, uc[C - 1], __ldg(pc + d_xp));
+    gx[C] = bx_hi ? bnd_flux_plus<NUMFLUX, KIND>(p, 0, 1, uc[C - 1])
+                  : flux_plus<NUMFLUX, KIND>(p, 0, uc[C - 1], __ldg(pc + d_xp));
     if (D == 3) {
       ldg_cols<C>(pc + d_ym, yl);
       ldg_cols<C>(pc + d_yp, yr);
@@ -350,10 +399,12 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
     const double rl = __ldg(prl);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const double G_up = has_up ? flux_plus<NUMFLUX, KIND>(p, last, uc[c], un[c]) : 0.;
+      const double G_up = has_up ? flux_plus<NUMFLUX, KIND>(p, last, uc[c], un[c])
+                                 : (BND ? bnd_flux_plus<NUMFLUX, KIND>(p, last, 1, uc[c]) : 0.);
       double acc = gx[c + 1] * (c == C - 1 ? cxh : rx[c]) - gx[c] * (c == 0 ? cxl : rx[c]);
       if (D == 3)
-        acc += flux_plus<NUMFLUX, KIND>(p, 1, uc[c], yr[c]) * cyh - flux_plus<NUMFLUX, KIND>(p, 1, yl[c], uc[c]) * cyl;
+        acc += (by_hi ? bnd_flux_plus<NUMFLUX, KIND>(p, 1, 1, uc[c]) : flux_plus<NUMFLUX, KIND>(p, 1, uc[c], yr[c])) * cyh
+               - (by_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 1, 0, uc[c]) : flux_plus<NUMFLUX, KIND>(p, 1, yl[c], uc[c])) * cyl;
       acc += (G_up - G_low[c]) * rl;
       res[c] = p.euler ? uc[c] - acc * p.dt : acc;
       G_low[c] = G_up;
@@ -399,18 +450,114 @@ __global__ void __launch_bounds__(256) k_fv_interpolate(const GridDev g, const F
   }
 }
 
+// ExplicitRungeKuttaTimeStepper::step (tools/timestepper/explicit-rungekutta.hh:248-263): the stage vector
+// u_i = u_n + sum_j k_j (dt r A_ij) and the update u_n += sum_i k_i (r dt b_i), terms added in the reference's order
+// (one axpy per term there, one fused pass here: each vector is read once, the result written once).
+template <int NV, int W>
+__global__ void __launch_bounds__(256) k_rk_axpy(const __grid_constant__ RkAxpyParams p, const double* __restrict__ base,
+                                                 double* __restrict__ out)
+{
+  const long long nw = p.n / W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x) {
+    if (W == 2) {
+      double2 a = __ldg(reinterpret_cast<const double2*>(base) + i);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const double2 k = __ldg(reinterpret_cast<const double2*>(p.v[j]) + i);
+        a.x += k.x * p.c[j];
+        a.y += k.y * p.c[j];
+      }
+      reinterpret_cast<double2*>(out)[i] = a;
+    } else {
+      double a = __ldg(base + i);
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        a += __ldg(p.v[j] + i) * p.c[j];
+      out[i] = a;
+    }
+  }
+  if (W == 2 && (p.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double a = base[p.n - 1];
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      a += p.v[j][p.n - 1] * p.c[j];
+    out[p.n - 1] = a;
+  }
+}
+
+// estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh:47-60, 75-82): data range of the (elementwise constant) state
+// and max over the elements of perimeter / volume; block partials {min, max, pov}, finished on the host.
+template <int D>
+__global__ void __launch_bounds__(256) k_fv_dt_reduce(const __grid_constant__ FvParams p, const double* __restrict__ u,
+                                                      double* __restrict__ partial)
+{
+  const GridDev& g = p.g;
+  double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308, pov = 0.;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < g.ne;
+       e += (long long)gridDim.x * blockDim.x) {
+    const double v = __ldg(u + e);
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+    long long idx[3];
+    elem_coords(g, e, idx);
+    double ext[3] = {1., 1., 1.};
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      ext[k] = __ldg(p.ext[k] + idx[k]);
+    double vol = ext[0], perimeter = 0.;
+    if (D > 1)
+      vol *= ext[1];
+    if (D > 2)
+      vol *= ext[2];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double a = 1.;
+#pragma unroll
+      for (int j = 0; j < D; ++j)
+        if (j != k)
+          a *= ext[j];
+      perimeter += a; // the two faces normal to e_k, in intersection order
+      perimeter += a;
+    }
+    pov = fmax(pov, perimeter / vol);
+  }
+  __shared__ double s[3][256];
+  s[0][threadIdx.x] = mn;
+  s[1][threadIdx.x] = mx;
+  s[2][threadIdx.x] = pov;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      s[0][threadIdx.x] = fmin(s[0][threadIdx.x], s[0][threadIdx.x + w]);
+      s[1][threadIdx.x] = fmax(s[1][threadIdx.x], s[1][threadIdx.x + w]);
+      s[2][threadIdx.x] = fmax(s[2][threadIdx.x], s[2][threadIdx.x + w]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[3 * blockIdx.x + 0] = s[0][0];
+    partial[3 * blockIdx.x + 1] = s[1][0];
+    partial[3 * blockIdx.x + 2] = s[2][0];
+  }
+}
+
 } // namespace
 
 template <int D, int C>
 static void launch_fv_march(const FvParams& p, const double* u, double* out, int rows, dim3 grid, dim3 block,
                             cudaStream_t stream)
 {
-  const int variant = (p.flux.numflux == GDTB_NUMFLUX_LAX_FRIEDRICHS ? 2 : 0) + (p.flux.kind == GDTB_FLUX_BURGERS ? 1 : 0);
+  const int variant = (p.flux.numflux == GDTB_NUMFLUX_LAX_FRIEDRICHS ? 2 : 0) + (p.flux.kind == GDTB_FLUX_BURGERS ? 1 : 0)
+                      + ((p.bnd_ext_mask | p.bnd_nf_mask) ? 4 : 0);
   switch (variant) {
-    case 0: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    case 1: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    case 2: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    default: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 0: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C, false><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 1: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C, false><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 2: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C, false><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 3: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C, false><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 4: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C, true><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 5: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C, true><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 6: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C, true><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    default: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C, true><<<grid, block, 0, stream>>>(p, u, out, rows); break;
   }
 }
 
@@ -467,6 +614,52 @@ int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
     }
   }
   time_end(L, KF_FV_APPLY);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+template <int W>
+static void launch_rk_axpy_w(const RkAxpyParams& p, const double* base, double* out, unsigned grid, cudaStream_t st)
+{
+  switch (p.nv) {
+    case 0: k_rk_axpy<0, W><<<grid, 256, 0, st>>>(p, base, out); break;
+    case 1: k_rk_axpy<1, W><<<grid, 256, 0, st>>>(p, base, out); break;
+    case 2: k_rk_axpy<2, W><<<grid, 256, 0, st>>>(p, base, out); break;
+    case 3: k_rk_axpy<3, W><<<grid, 256, 0, st>>>(p, base, out); break;
+    default: k_rk_axpy<4, W><<<grid, 256, 0, st>>>(p, base, out); break;
+  }
+}
+
+int launch_rk_axpy(Launch& L, const RkAxpyParams& p, const double* base, double* out)
+{
+  if (p.n <= 0)
+    return GDTB_OK;
+  if (p.nv < 0 || p.nv > RK_MAX_TERMS)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "rk_axpy: too many terms");
+  uintptr_t bits = reinterpret_cast<uintptr_t>(base) | reinterpret_cast<uintptr_t>(out);
+  for (int j = 0; j < p.nv; ++j)
+    bits |= reinterpret_cast<uintptr_t>(p.v[j]);
+  const bool two = (bits & 15) == 0 && p.n >= 2;
+  const long long work = two ? p.n / 2 : p.n;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((work + 255) / 256, (long long)L.sm_count * 8));
+  if (two)
+    launch_rk_axpy_w<2>(p, base, out, grid, L.stream);
+  else
+    launch_rk_axpy_w<1>(p, base, out, grid, L.stream);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+int launch_fv_dt_reduce(Launch& L, const FvParams& p, const double* u, double* partial, int blocks)
+{
+  switch (p.g.d) {
+    case 1: k_fv_dt_reduce<1><<<blocks, 256, 0, L.stream>>>(p, u, partial); break;
+    case 2: k_fv_dt_reduce<2><<<blocks, 256, 0, L.stream>>>(p, u, partial); break;
+    case 3: k_fv_dt_reduce<3><<<blocks, 256, 0, L.stream>>>(p, u, partial); break;
+    default: return fail(GDTB_ERR_INVALID_ARGUMENT, "fv: dimension must be 1, 2 or 3");
+  }
   L.count++;
   GDTB_CUDA(cudaGetLastError());
   return GDTB_OK;

@@ -126,6 +126,21 @@ struct gdtb_fvop
   long long ext_offset[3];
   long long inv_ext_shift;
   int rows_per_block; // tuning knob of the marching kernel (0 = automatic), GDTB_FV_ROWS in the environment
+  // boundary treatments resolved per domain side (gdtb_fvop_append_boundary)
+  unsigned bnd_ext_mask = 0, bnd_nf_mask = 0;
+  double bnd_ext_a[6] = {0, 0, 0, 0, 0, 0}, bnd_ext_b[6] = {0, 0, 0, 0, 0, 0};
+  double bnd_nf_a[6] = {0, 0, 0, 0, 0, 0}, bnd_nf_b[6] = {0, 0, 0, 0, 0, 0};
+  double* d_partial = nullptr; // block partials of the dt estimate
+};
+
+struct gdtb_rk
+{
+  gdtb_fvop* op;
+  int s;
+  double A[GDTB_RK_MAX_STAGES * GDTB_RK_MAX_STAGES], b[GDTB_RK_MAX_STAGES], c[GDTB_RK_MAX_STAGES];
+  double r, t;
+  double* d_ui = nullptr;                    // stage vector u_i (Euler: ping-pong buffer)
+  double* d_k[GDTB_RK_MAX_STAGES] = {};      // stages k_i
 };
 
 namespace gdtb {

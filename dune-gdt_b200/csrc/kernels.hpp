@@ -218,8 +218,26 @@ struct FvParams
   // layers [apply_lo, apply_hi) of the slab [g.layer_lo, g.layer_hi) to produce in this launch (overlap of the
   // interior with the ghost-layer exchange); the memory layout always follows the slab
   long long apply_lo, apply_hi;
+  // boundary treatments resolved per domain side (2k+s): extrapolation v = a u + b through the numerical flux, and/or
+  // numerical boundary flux g = a (f(u) . n) + b (local/operators/advection-fv.hh:188-457)
+  unsigned bnd_ext_mask, bnd_nf_mask;
+  double bnd_ext_a[6], bnd_ext_b[6], bnd_nf_a[6], bnd_nf_b[6];
 };
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out);
+
+// explicit Runge-Kutta vector updates (tools/timestepper/explicit-rungekutta.hh:248-263):
+// out = base + sum_j v[j] * c[j], terms added in order; nv <= RK_MAX_TERMS per launch
+constexpr int RK_MAX_TERMS = 4;
+struct RkAxpyParams
+{
+  long long n;
+  int nv;
+  const double* v[RK_MAX_TERMS];
+  double c[RK_MAX_TERMS];
+};
+int launch_rk_axpy(Launch& L, const RkAxpyParams& p, const double* base, double* out);
+// estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh:38-86): per block {min u, max u, max perimeter / volume}
+int launch_fv_dt_reduce(Launch& L, const FvParams& p, const double* u, double* partial /* 3 * blocks */, int blocks);
 int launch_fv_interpolate(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx, const double* qw,
                           double* u);
 

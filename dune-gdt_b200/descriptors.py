@@ -72,6 +72,12 @@ class Flux(C.Structure):
     _fields_ = [("kind", C.c_int32), ("numflux", C.c_int32), ("p", C.c_double * 4)]
 
 
+class FvBoundary(C.Structure):
+    """gdtb_fv_boundary / orc_fv_boundary: one boundary treatment of the FV operator (operators/advection-fv.hh:96-123)"""
+
+    _fields_ = [("kind", C.c_int32), ("side_mask", C.c_uint32), ("a", C.c_double), ("b", C.c_double)]
+
+
 class SolverOpts(C.Structure):
     _fields_ = [
         ("type", C.c_int32),
@@ -187,6 +193,28 @@ def flux(kind, numflux=NUMFLUX_UPWIND, params=()):
     for i, x in enumerate(params):
         fl.p[i] = float(x)
     return fl
+
+
+FVBND_EXTRAPOLATION, FVBND_NUMERICAL_FLUX = 0, 1
+RK_EULER, RK_SSP2, RK_SSP3, RK_CLASSIC4, RK_OTHER = 0, 1, 2, 3, 4
+
+# internal::ButcherArrayProvider (tools/timestepper/explicit-rungekutta.hh:63-141): A (row-major), b, c
+BUTCHER = {
+    RK_EULER: ([[0.0]], [1.0], [0.0]),
+    RK_SSP2: ([[0.0, 0.0], [1.0, 0.0]], [0.5, 0.5], [0.0, 1.0]),
+    RK_SSP3: ([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.25, 0.25, 0.0]], [1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0], [0.0, 1.0, 0.5]),
+    RK_CLASSIC4: (
+        [[0.0, 0.0, 0.0, 0.0], [0.5, 0.0, 0.0, 0.0], [0.0, 0.5, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0]],
+        [1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0],
+        [0.0, 0.5, 0.5, 1.0],
+    ),
+}
+
+
+def fv_boundary(kind, side_mask, a, b):
+    t = FvBoundary()
+    t.kind, t.side_mask, t.a, t.b = int(kind), int(side_mask), float(a), float(b)
+    return t
 
 
 def solver_opts(type=SOLVER_CG, preconditioner=PRECOND_JACOBI, precision=1e-10, max_iter=0, check_every=0):

@@ -67,6 +67,34 @@ int main(int argc, char* argv[])
                 << std::endl;
       ok = ok && std::abs(mass(w_h) - mass(w_0)) < 1e-9 * N && w_h.sup_norm() <= 1. + 1e-12;
     }
+    { // the same Burgers problem through the reference's time stepper (tools/timestepper/explicit-rungekutta.hh) with
+      // dt from estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh), third order SSP Runge-Kutta, u_t = -L(u)
+      const NumericalLaxFriedrichsFlux<I, d, 1> g(BurgersFlux{});
+      auto L_h = make_advection_fv_operator<M>(grid_view, g, V_h_0, V_h_0);
+      using Op = decltype(L_h);
+      auto w = default_interpolation<V>(XT::Functions::make_gaussian<E>(3, 0.33, 0.075), V_h_0);
+      const double m0 = mass(w), max0 = w.sup_norm();
+      const double dt = estimate_dt_for_hyperbolic_system(L_h, w);
+      ExplicitRungeKuttaTimeStepper<Op, TimeStepperMethods::explicit_rungekutta_third_order_ssp> stepper(L_h, w, -1.);
+      stepper.solve(0.5, dt);
+      std::cout << "burgers (SSP3, dt = " << dt << ", " << stepper.num_steps() << " steps): t = " << stepper.current_time()
+                << ", mass " << m0 / N << " -> " << mass(w) / N << ", max " << w.sup_norm() << std::endl;
+      ok = ok && std::abs(stepper.current_time() - 0.5) < 1e-12 && std::abs(mass(w) - m0) < 1e-9 * N
+           && w.sup_norm() <= max0 + 1e-12;
+    }
+    { // non-periodic: inflow value 0 on the left by extrapolation, outflow of the physical flux on the right
+      auto plain_view = grid.leaf_view();
+      auto V_np = make_finite_volume_space(plain_view);
+      const NumericalUpwindFlux<I, d, 1> g(LinearFlux{});
+      auto L_h = make_advection_fv_operator<M>(plain_view, g, V_np, V_np);
+      L_h.append(BoundaryTreatmentByCustomExtrapolation{0., 0.}, 0b01).append(BoundaryTreatmentByCustomNumericalFlux{1., 0.}, 0b10);
+      using Op = decltype(L_h);
+      auto w = default_interpolation<V>(XT::Functions::make_indicator<E>(0, 0.25, 0.5), V_np);
+      ExplicitRungeKuttaTimeStepper<Op> stepper(L_h, w, -1.);
+      stepper.solve(1., 1. / N); // exact shift: after t = 1 the indicator has left through the right boundary
+      std::cout << "linear transport with in/outflow boundaries: remaining mass " << mass(w) / N << std::endl;
+      ok = ok && std::abs(mass(w)) < 1e-12 * N;
+    }
     std::cout << (ok ? "OK" : "FAILED") << std::endl;
     return ok ? EXIT_SUCCESS : EXIT_FAILURE;
   } catch (Exception& e) {

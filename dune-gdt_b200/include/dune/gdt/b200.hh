@@ -1550,6 +1550,16 @@ public:
   }
 };
 
+// Boundary treatments (local/operators/advection-fv.hh:188-457) as value types: v = a u + b / g = a (f(u) . n) + b
+struct BoundaryTreatmentByCustomExtrapolation
+{
+  double a, b;
+};
+struct BoundaryTreatmentByCustomNumericalFlux
+{
+  double a, b;
+};
+
 // operators/advection-fv.hh:44-128
 template <class M, class GV>
 class AdvectionFvOperator
@@ -1586,6 +1596,21 @@ public:
     apply(source, range, param);
     return range;
   }
+  // append(boundary treatment, param_type, filter) (operators/advection-fv.hh:96-123).  The reference takes a C++
+  // lambda and an intersection filter; across the C ABI the treatment is one of the affine families of
+  // gdtb_fv_boundary and the filter a mask of domain sides (bit 2k+s: outer normal -e_k / +e_k).
+  AdvectionFvOperator& append(const BoundaryTreatmentByCustomExtrapolation& t, const unsigned side_mask = ~0u)
+  {
+    gdtb_fv_boundary b{GDTB_FVBND_EXTRAPOLATION, side_mask & ((1u << (2 * d)) - 1u), t.a, t.b};
+    internal::check(gdtb_fvop_append_boundary(handle_.get(), &b));
+    return *this;
+  }
+  AdvectionFvOperator& append(const BoundaryTreatmentByCustomNumericalFlux& t, const unsigned side_mask = ~0u)
+  {
+    gdtb_fv_boundary b{GDTB_FVBND_NUMERICAL_FLUX, side_mask & ((1u << (2 * d)) - 1u), t.a, t.b};
+    internal::check(gdtb_fvop_append_boundary(handle_.get(), &b));
+    return *this;
+  }
   const SpaceInterface<GV>& source_space() const
   {
     return source_space_;
@@ -1602,6 +1627,102 @@ public:
 private:
   SpaceInterface<GV> source_space_, range_space_;
   internal::Handle<gdtb_fvop, gdtb_fvop_destroy> handle_;
+};
+
+// estimate_dt_for_hyperbolic_system(grid_view, state, flux, boundary_data_range) (tools/hyperbolic.hh:38-86); grid view
+// and flux are the operator's, the state is a finite-volume DoF vector
+template <class M, class GV>
+double estimate_dt_for_hyperbolic_system(const AdvectionFvOperator<M, GV>& op,
+                                         const XT::LA::IstlDenseVector<double>& state,
+                                         const std::pair<double, double>* boundary_data_range = nullptr)
+{
+  if (state.size() != op.source_space().mapper().size())
+    throw XT::Common::Exceptions::shapes_do_not_match("state vector does not match the finite volume space");
+  double range[2] = {0., 0.}, dt = 0.;
+  if (boundary_data_range) {
+    range[0] = boundary_data_range->first;
+    range[1] = boundary_data_range->second;
+  }
+  internal::check(gdtb_fv_estimate_dt_host(op.handle(), state.data(), boundary_data_range ? range : nullptr, &dt));
+  return dt;
+}
+
+// tools/timestepper/interface.hh: TimeStepperMethods (explicit Runge-Kutta members)
+enum class TimeStepperMethods
+{
+  explicit_euler = GDTB_RK_EULER,
+  explicit_rungekutta_second_order_ssp = GDTB_RK_SSP2,
+  explicit_rungekutta_third_order_ssp = GDTB_RK_SSP3,
+  explicit_rungekutta_classic_fourth_order = GDTB_RK_CLASSIC4,
+  explicit_rungekutta_other = GDTB_RK_OTHER
+};
+
+// tools/timestepper/explicit-rungekutta.hh:158-270: u_t = r L(u).  Like the reference the stepper works on the
+// caller's initial_values vector in place (current_solution() is that vector).
+template <class OperatorImp, TimeStepperMethods method = TimeStepperMethods::explicit_euler>
+class ExplicitRungeKuttaTimeStepper
+{
+public:
+  using V = XT::LA::IstlDenseVector<double>;
+
+  ExplicitRungeKuttaTimeStepper(const OperatorImp& op,
+                                V& initial_values,
+                                const double r = 1.0,
+                                const double t_0 = 0.0,
+                                const std::vector<std::vector<double>>& A = {},
+                                const std::vector<double>& b = {},
+                                const std::vector<double>& c = {})
+    : u_(initial_values)
+  {
+    if (initial_values.size() != op.source_space().mapper().size())
+      throw XT::Common::Exceptions::shapes_do_not_match("initial values do not match the operator's source space");
+    std::vector<double> flat;
+    for (const auto& row : A) {
+      if (row.size() != A.size())
+        throw XT::Common::Exceptions::shapes_do_not_match("A has to be a square matrix"); // :210
+      flat.insert(flat.end(), row.begin(), row.end());
+    }
+    if (b.size() != A.size() || c.size() != A.size())
+      throw XT::Common::Exceptions::shapes_do_not_match("b and c must have as many entries as A has rows"); // :211-212
+    gdtb_rk* raw = nullptr;
+    internal::check(gdtb_rk_create(op.handle(), int(method), int(A.size()), A.empty() ? nullptr : flat.data(),
+                                   A.empty() ? nullptr : b.data(), A.empty() ? nullptr : c.data(), r, t_0, &raw));
+    handle_ = internal::Handle<gdtb_rk, gdtb_rk_destroy>(raw);
+  }
+  double current_time() const
+  {
+    return gdtb_rk_current_time(handle_.get());
+  }
+  V& current_solution()
+  {
+    return u_;
+  }
+  // step(dt, max_dt) (:237-270)
+  double step(const double dt, const double max_dt)
+  {
+    double ret = dt;
+    internal::check(gdtb_rk_step_host(handle_.get(), u_.data(), dt, max_dt, &ret));
+    return ret;
+  }
+  // TimeStepperInterface::solve(t_end, initial_dt) (tools/timestepper/interface.hh:191-263) with nothing saved,
+  // visualized or printed; returns the dt for the next step
+  double solve(const double t_end, const double initial_dt)
+  {
+    std::int64_t steps = 0;
+    double next = initial_dt;
+    internal::check(gdtb_rk_solve_host(handle_.get(), u_.data(), t_end, initial_dt, &steps, &next));
+    num_steps_ = steps;
+    return next;
+  }
+  std::int64_t num_steps() const
+  {
+    return num_steps_;
+  }
+
+private:
+  V& u_;
+  internal::Handle<gdtb_rk, gdtb_rk_destroy> handle_;
+  std::int64_t num_steps_ = 0;
 };
 
 // operators/advection-fv.hh:130-141

@@ -181,6 +181,34 @@ typedef struct gdtb_flux
   double p[4];
 } gdtb_flux;
 
+/* Boundary treatments of the FV operator: AdvectionFvOperator::append(lambda, ..., filter)
+ * (operators/advection-fv.hh:96-123) -> LocalAdvectionFvBoundaryTreatmentByCustomNumericalFluxOperator /
+ * ...ByCustomExtrapolationOperator (local/operators/advection-fv.hh:188-457).  The reference takes arbitrary C++
+ * lambdas; across a C ABI they are the two affine families below.  side_mask selects the boundary intersections
+ * (the reference's intersection filter): bit (2k+s) = domain face with outer normal -e_k (s = 0) / +e_k (s = 1). */
+enum
+{
+  GDTB_FVBND_EXTRAPOLATION = 0, /* v = a u + b, g = numerical_flux(u, v, n): a=1,b=0 absorbing; a=0 Dirichlet value b */
+  GDTB_FVBND_NUMERICAL_FLUX = 1 /* g = a (f(u) . n) + b: a=1,b=0 outflow of the physical flux; a=0 prescribed flux b  */
+};
+typedef struct gdtb_fv_boundary
+{
+  int32_t kind;
+  uint32_t side_mask;
+  double a, b;
+} gdtb_fv_boundary;
+
+/* TimeStepperMethods (tools/timestepper/explicit-rungekutta.hh:63-141) */
+enum
+{
+  GDTB_RK_EULER = 0,    /* explicit_euler                              */
+  GDTB_RK_SSP2 = 1,     /* explicit_rungekutta_second_order_ssp        */
+  GDTB_RK_SSP3 = 2,     /* explicit_rungekutta_third_order_ssp         */
+  GDTB_RK_CLASSIC4 = 3, /* explicit_rungekutta_classic_fourth_order    */
+  GDTB_RK_OTHER = 4     /* explicit_rungekutta_other: user Butcher array */
+};
+#define GDTB_RK_MAX_STAGES 8
+
 enum
 {
   GDTB_ASSEMBLE_OVERWRITE = 0, /* matrix/vector are known to be zero (fresh containers): values = assembled */
@@ -194,6 +222,7 @@ typedef struct gdtb_pattern gdtb_pattern;
 typedef struct gdtb_matop gdtb_matop;
 typedef struct gdtb_vecfun gdtb_vecfun;
 typedef struct gdtb_fvop gdtb_fvop;
+typedef struct gdtb_rk gdtb_rk;
 
 /* ---- context -------------------------------------------------------------------------------- */
 const char* gdtb_last_error(void);
@@ -316,6 +345,35 @@ int gdtb_fvop_set_slab(gdtb_fvop* L, int64_t layer_begin, int64_t layer_end);
 int gdtb_fvop_step_async(gdtb_fvop* L, const double* d_source, double* d_range, int euler, double dt,
                          int64_t layer_begin, int64_t layer_end);
 int64_t gdtb_fvop_ghost_layer_size(const gdtb_fvop* L);
+
+/* AdvectionFvOperator::append(boundary treatment lambda, param_type, filter) (operators/advection-fv.hh:96-123):
+ * applies on the non-periodic domain boundary faces selected by side_mask.  Treatments add up like appended local
+ * operators do; two different extrapolations on the same side are GDTB_ERR_NOT_IMPLEMENTED. */
+int gdtb_fvop_append_boundary(gdtb_fvop* L, const gdtb_fv_boundary* treatment);
+
+/* estimate_dt_for_hyperbolic_system(grid_view, state, flux, boundary_data_range) (tools/hyperbolic.hh:38-86) for the
+ * operator's grid and flux and a finite-volume state d_u (device): min / max of the state and max perimeter / volume
+ * are reduced on the device.  boundary_data_range = {min, max} or NULL for the reference's defaults. */
+int gdtb_fv_estimate_dt(gdtb_fvop* L, const double* d_u, const double* boundary_data_range, double* dt);
+int gdtb_fv_estimate_dt_host(gdtb_fvop* L, const double* u, const double* boundary_data_range, double* dt);
+
+/* ---- ExplicitRungeKuttaTimeStepper (tools/timestepper/explicit-rungekutta.hh:158-270) ---------------------------- */
+/* ExplicitRungeKuttaTimeStepper<Op, DF, method>(op, initial_values, r, t_0[, A, b, c]): solves u_t = r L(u).
+ * A (row-major, num_stages^2), b, c are read only for GDTB_RK_OTHER (num_stages <= GDTB_RK_MAX_STAGES); A must be
+ * strictly lower triangular (wrong_input_given -> GDTB_ERR_INVALID_ARGUMENT, :216-222).  The current solution lives
+ * in the caller's device vector passed to step / solve (the reference keeps a reference to initial_values). */
+int gdtb_rk_create(gdtb_fvop* L, int method, int num_stages, const double* A, const double* b, const double* c, double r,
+                   double t0, gdtb_rk** ts);
+int gdtb_rk_destroy(gdtb_rk* ts);
+double gdtb_rk_current_time(const gdtb_rk* ts);
+/* step(dt, max_dt) (:237-270): one step of length min(dt, max_dt) on d_u; *returned_dt = dt (may be NULL) */
+int gdtb_rk_step(gdtb_rk* ts, double* d_u, double dt, double max_dt, double* returned_dt);
+int gdtb_rk_step_host(gdtb_rk* ts, double* u, double dt, double max_dt, double* returned_dt);
+/* TimeStepperInterface::solve(t_end, initial_dt) (tools/timestepper/interface.hh:191-263) with nothing saved, written
+ * or printed: steps of length initial_dt, the last one shortened to hit t_end.  The steps run back to back on the
+ * device (CUDA graph replay of one step, no host synchronisation in between). */
+int gdtb_rk_solve(gdtb_rk* ts, double* d_u, double t_end, double initial_dt, int64_t* n_steps, double* next_dt);
+int gdtb_rk_solve_host(gdtb_rk* ts, double* u, double t_end, double initial_dt, int64_t* n_steps, double* next_dt);
 
 /* default_interpolation(order, f, fv_space) (interpolations/default.hh:76-83, spaces/basis/finite-volume.hh:244-252) */
 int gdtb_fv_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* d_u);

@@ -24,7 +24,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        from dune_gdt_b200.descriptors import Flux, Form, Function, GridDesc
+        from dune_gdt_b200.descriptors import Flux, Form, Function, FvBoundary, GridDesc
 
         if not os.path.exists(LIB_PATH):
             build()
@@ -54,6 +54,18 @@ def lib():
             "orc_fv_apply": (C.c_int, [G, C.POINTER(Flux), DP, DP, C.c_int]),
             "orc_fv_euler": (C.c_int, [G, C.POINTER(Flux), DP, C.c_double, C.c_int64, C.c_int]),
             "orc_fv_interpolate": (None, [G, C.POINTER(Function), DP]),
+            "orc_fv_apply_bnd": (C.c_int, [G, C.POINTER(Flux), C.c_int, C.POINTER(FvBoundary), DP, DP, C.c_int]),
+            "orc_rk_step": (
+                C.c_int,
+                [G, C.POINTER(Flux), C.c_int, C.POINTER(FvBoundary), C.c_int, DP, DP, DP, C.c_double, DP, DP, C.c_double,
+                 C.c_double, C.c_int],
+            ),
+            "orc_rk_solve": (
+                C.c_int,
+                [G, C.POINTER(Flux), C.c_int, C.POINTER(FvBoundary), C.c_int, DP, DP, DP, C.c_double, DP, C.c_double,
+                 C.c_double, C.c_double, I64P, DP, C.c_int],
+            ),
+            "orc_fv_estimate_dt": (C.c_double, [G, C.POINTER(Flux), DP, DP]),
             "orc_function_eval": (C.c_double, [C.POINTER(Function), C.c_int, DP, C.c_int64]),
             "orc_last_error": (C.c_char_p, []),
             "orc_dirichlet_dofs": (C.c_int64, [G, C.c_int, C.c_int, C.c_uint32, I64P]),
@@ -150,6 +162,57 @@ def fv_euler(grid, flux, u, dt, n_steps, num_threads=1):
     u = np.array(u, dtype=np.float64, copy=True)
     lib().orc_fv_euler(C.byref(grid), C.byref(flux), _dp(u), dt, n_steps, num_threads)
     return u
+
+
+def _bnd_array(boundary):
+    from dune_gdt_b200.descriptors import FvBoundary
+
+    arr = (FvBoundary * max(1, len(boundary)))()
+    for i, t in enumerate(boundary):
+        arr[i] = t
+    return arr
+
+
+def fv_apply_bnd(grid, flux, boundary, u, num_threads=1):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty_like(u)
+    lib().orc_fv_apply_bnd(C.byref(grid), C.byref(flux), len(boundary), _bnd_array(boundary), _dp(u), _dp(out), num_threads)
+    return out
+
+
+def _butcher(A, b, c):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    assert A.shape == (b.size, b.size) and c.size == b.size
+    return A, b, c
+
+
+def rk_step(grid, flux, butcher, u, t, dt, max_dt=None, r=1.0, boundary=(), num_threads=1):
+    """ExplicitRungeKuttaTimeStepper::step; returns (u_new, t_new)"""
+    A, b, c = _butcher(*butcher)
+    u = np.array(u, dtype=np.float64, copy=True)
+    tt = np.array([t], dtype=np.float64)
+    lib().orc_rk_step(C.byref(grid), C.byref(flux), len(boundary), _bnd_array(boundary), b.size, _dp(A), _dp(b), _dp(c),
+                      r, _dp(u), _dp(tt), dt, dt if max_dt is None else max_dt, num_threads)
+    return u, float(tt[0])
+
+
+def rk_solve(grid, flux, butcher, u, t_end, initial_dt, t0=0.0, r=1.0, boundary=(), num_threads=1):
+    """TimeStepperInterface::solve; returns (u(t_end), n_steps, t_final)"""
+    A, b, c = _butcher(*butcher)
+    u = np.array(u, dtype=np.float64, copy=True)
+    n = np.zeros(1, dtype=np.int64)
+    tf = np.zeros(1, dtype=np.float64)
+    lib().orc_rk_solve(C.byref(grid), C.byref(flux), len(boundary), _bnd_array(boundary), b.size, _dp(A), _dp(b), _dp(c),
+                       r, _dp(u), t0, t_end, initial_dt, n.ctypes.data_as(C.POINTER(C.c_int64)), _dp(tf), num_threads)
+    return u, int(n[0]), float(tf[0])
+
+
+def fv_estimate_dt(grid, flux, u, boundary_data_range=None):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    rng = None if boundary_data_range is None else np.ascontiguousarray(boundary_data_range, dtype=np.float64)
+    return lib().orc_fv_estimate_dt(C.byref(grid), C.byref(flux), _dp(u), None if rng is None else _dp(rng))
 
 
 def fv_interpolate(grid, function):

@@ -995,8 +995,13 @@ inline double numerical_flux(const orc_flux& fl, int d, double u, double v, cons
 
 // LocalizableOperator::apply (operators/localizable-operator.hh:352-379) with the coupling operators
 // registered by AdvectionFvOperator (operators/advection-fv.hh:77-82) and
-// LocalAdvectionFvCouplingOperator::apply (local/operators/advection-fv.hh:127-153)
-void fv_walk_range(const Grid& g, const orc_flux& fl, const double* u, Vec& out, int64_t e0, int64_t e1)
+// LocalAdvectionFvCouplingOperator::apply (local/operators/advection-fv.hh:127-153); boundary treatments appended by
+// AdvectionFvOperator::append (operators/advection-fv.hh:96-123) run on the boundary intersections selected by their
+// filter: LocalAdvectionFvBoundaryTreatmentByCustomNumericalFluxOperator::apply (local/operators/advection-fv.hh:281-296)
+// and ...ByCustomExtrapolationOperator::apply (:418-443).  The reference takes arbitrary lambdas; the descriptor
+// families restated here are  extrapolation v = a u + b  and  numerical boundary flux g = a (f(u) . n) + b.
+void fv_walk_range(const Grid& g, const orc_flux& fl, int n_bnd, const orc_fv_boundary* bnd, const double* u, Vec& out,
+                   int64_t e0, int64_t e1)
 {
   for (int64_t e = e0; e < e1; ++e) {
     int64_t idx[3];
@@ -1007,8 +1012,27 @@ void fv_walk_range(const Grid& g, const orc_flux& fl, const double* u, Vec& out,
       for (int s = 0; s < 2; ++s) {
         int64_t nb[3];
         bool boundary;
-        if (!g.neighbor(idx, k, s, nb, &boundary))
+        if (!g.neighbor(idx, k, s, nb, &boundary)) {
+          // a domain boundary intersection (not periodic): boundary treatments in append order
+          const Face f = make_face(g, ext_in, k, s);
+          for (int t = 0; t < n_bnd; ++t) {
+            if (!(bnd[t].side_mask >> (2 * k + s) & 1))
+              continue;
+            const double uu = u[e];
+            double gflux;
+            if (bnd[t].kind == ORC_FVBND_EXTRAPOLATION) {
+              const double vv = bnd[t].a * uu + bnd[t].b;
+              gflux = numerical_flux(fl, g.d, uu, vv, f.normal);
+            } else {
+              double fu[3];
+              flux_eval(fl, g.d, uu, fu);
+              gflux = bnd[t].a * dot(g.d, fu, f.normal) + bnd[t].b;
+            }
+            const double factor = f.ie / g.volume(ext_in); // local/operators/advection-fv.hh:293, 440
+            out.add_to_entry(e, gflux * factor);
+          }
           continue;
+        }
         const int64_t eo = g.index(nb);
         if (!(e < eo))
           continue;
@@ -1027,14 +1051,75 @@ void fv_walk_range(const Grid& g, const orc_flux& fl, const double* u, Vec& out,
   }
 }
 
-void fv_apply(const Grid& g, const orc_flux& fl, const double* u, double* out, int num_threads)
+void fv_apply(const Grid& g, const orc_flux& fl, int n_bnd, const orc_fv_boundary* bnd, const double* u, double* out,
+              int num_threads)
 {
   for (int64_t i = 0; i < g.ne; ++i) // range.set_all(0), localizable-operator.hh:359
     out[i] = 0.;
   std::vector<std::mutex> locks(num_threads > 1 ? 4096 : 0);
   Vec v{out, num_threads > 1 ? locks.data() : nullptr, 4096};
-  run_threads(g.ne, num_threads, [&](int64_t a, int64_t b) { fv_walk_range(g, fl, u, v, a, b); });
+  run_threads(g.ne, num_threads, [&](int64_t a, int64_t b) { fv_walk_range(g, fl, n_bnd, bnd, u, v, a, b); });
 }
+
+// XT::Common::FloatCmp::{eq,lt,gt}<Style::numpy> with the default epsilons [EXT dune-xt common/float_cmp*.hh]:
+// eq(a, b) := |a - b| <= atol + rtol |b|, rtol = atol = Dune::FloatCmp::DefaultEpsilon<double> = 8 * 2^-52;
+// lt(a, b) := !eq(a, b) && a < b.  Parity unpinned (third-party), only decides whether a last sliver step is taken.
+inline bool floatcmp_eq(double a, double b)
+{
+  const double eps = 8. * std::numeric_limits<double>::epsilon();
+  return std::fabs(a - b) <= eps + eps * std::fabs(b);
+}
+inline bool floatcmp_lt(double a, double b)
+{
+  return !floatcmp_eq(a, b) && a < b;
+}
+inline bool floatcmp_gt(double a, double b)
+{
+  return !floatcmp_eq(a, b) && a > b;
+}
+
+// ExplicitRungeKuttaTimeStepper::step (tools/timestepper/explicit-rungekutta.hh:237-270)
+struct RkStepper
+{
+  const Grid& g;
+  const orc_flux& fl;
+  int n_bnd;
+  const orc_fv_boundary* bnd;
+  int s;
+  const double *A, *b, *c;
+  double r;
+  int num_threads;
+  std::vector<double> u_i;
+  std::vector<std::vector<double>> k;
+  RkStepper(const Grid& g_, const orc_flux& fl_, int n_bnd_, const orc_fv_boundary* bnd_, int s_, const double* A_,
+            const double* b_, const double* c_, double r_, int nt)
+    : g(g_), fl(fl_), n_bnd(n_bnd_), bnd(bnd_), s(s_), A(A_), b(b_), c(c_), r(r_), num_threads(nt), u_i(g_.ne),
+      k(s_, std::vector<double>(g_.ne))
+  {}
+  double step(double* u_n, double& t, double dt, double max_dt)
+  {
+    const double actual_dt = std::min(dt, max_dt);
+    const int64_t n = g.ne;
+    for (int ii = 0; ii < s; ++ii) {
+      for (int64_t i = 0; i < n; ++i)
+        u_i[i] = u_n[i];
+      for (int jj = 0; jj < ii; ++jj) {
+        const double coef = actual_dt * r * A[ii * s + jj];
+        for (int64_t i = 0; i < n; ++i)
+          u_i[i] += k[jj][i] * coef;
+      }
+      // the operator here does not depend on t / dt (the flux families are autonomous)
+      fv_apply(g, fl, n_bnd, bnd, u_i.data(), k[ii].data(), num_threads);
+    }
+    for (int ii = 0; ii < s; ++ii) {
+      const double coef = r * actual_dt * b[ii];
+      for (int64_t i = 0; i < n; ++i)
+        u_n[i] += k[ii][i] * coef;
+    }
+    t += actual_dt;
+    return dt;
+  }
+};
 
 } // namespace
 
@@ -1213,8 +1298,90 @@ void orc_local_element_matrix(const orc_grid* g, int kind, int order, const orc_
 int orc_fv_apply(const orc_grid* g, const orc_flux* flux, const double* u, double* out, int num_threads)
 {
   Grid gr(g);
-  fv_apply(gr, *flux, u, out, num_threads);
+  fv_apply(gr, *flux, 0, nullptr, u, out, num_threads);
   return 0;
+}
+
+int orc_fv_apply_bnd(const orc_grid* g, const orc_flux* flux, int n_bnd, const orc_fv_boundary* bnd, const double* u,
+                     double* out, int num_threads)
+{
+  Grid gr(g);
+  fv_apply(gr, *flux, n_bnd, bnd, u, out, num_threads);
+  return 0;
+}
+
+int orc_rk_step(const orc_grid* g, const orc_flux* flux, int n_bnd, const orc_fv_boundary* bnd, int num_stages,
+                const double* A, const double* b, const double* c, double r, double* u, double* t, double dt,
+                double max_dt, int num_threads)
+{
+  Grid gr(g);
+  RkStepper st(gr, *flux, n_bnd, bnd, num_stages, A, b, c, r, num_threads);
+  st.step(u, *t, dt, max_dt);
+  return 0;
+}
+
+// TimeStepperInterface::solve (tools/timestepper/interface.hh:191-263) with num_save_steps = size_t(-1), no output:
+// while lt(t, t_end): max_dt = gt(t + dt, t_end) ? t_end - t : dt; dt = step(dt, max_dt)
+int orc_rk_solve(const orc_grid* g, const orc_flux* flux, int n_bnd, const orc_fv_boundary* bnd, int num_stages,
+                 const double* A, const double* b, const double* c, double r, double* u, double t0, double t_end,
+                 double initial_dt, int64_t* n_steps, double* t_final, int num_threads)
+{
+  Grid gr(g);
+  RkStepper st(gr, *flux, n_bnd, bnd, num_stages, A, b, c, r, num_threads);
+  double dt = initial_dt, t = t0;
+  int64_t steps = 0;
+  while (floatcmp_lt(t, t_end)) {
+    double max_dt = dt;
+    if (floatcmp_gt(t + dt, t_end))
+      max_dt = t_end - t;
+    dt = st.step(u, t, dt, max_dt);
+    ++steps;
+  }
+  if (n_steps)
+    *n_steps = steps;
+  if (t_final)
+    *t_final = t;
+  return 0;
+}
+
+// estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh:38-86) for m = 1 and a finite-volume state (order 0: one
+// quadrature point per element, the cell value).  boundary_data_range == NULL: the reference's defaults
+// {numeric_limits<R>::max(), numeric_limits<R>::min()} (the latter is the smallest positive normal, as in the reference).
+double orc_fv_estimate_dt(const orc_grid* g, const orc_flux* flux, const double* u, const double* boundary_data_range)
+{
+  Grid gr(g);
+  double data_minimum = boundary_data_range ? boundary_data_range[0] : std::numeric_limits<double>::max();
+  double data_maximum = boundary_data_range ? boundary_data_range[1] : std::numeric_limits<double>::min();
+  for (int64_t e = 0; e < gr.ne; ++e) {
+    data_minimum = std::min(data_minimum, u[e]);
+    data_maximum = std::max(data_maximum, u[e]);
+  }
+  if (!(data_minimum < data_maximum))
+    data_maximum = data_minimum + 1e-6 * data_minimum;
+  double max_flux_derivative = std::numeric_limits<double>::min();
+  // one-cell YaspGrid [min, max]; Gauss rule of order flux.order() (linear: 1, Burgers: 2; test/linear-transport/
+  // base.hh:43, test/burgers/base.hh:41); geometry.global(x) = lower + x (upper - lower) [EXT]
+  const Rule rule(flux->kind == ORC_FLUX_LINEAR ? 1 : 2);
+  for (int q = 0; q < rule.m; ++q) {
+    const double uq = data_minimum + rule.x[q] * (data_maximum - data_minimum);
+    double df[3];
+    flux_jac(*flux, gr.d, uq, df);
+    for (int ss = 0; ss < gr.d; ++ss)
+      max_flux_derivative = std::max(max_flux_derivative, std::fabs(df[ss]));
+  }
+  double perimeter_over_volume = std::numeric_limits<double>::min();
+  for (int64_t e = 0; e < gr.ne; ++e) {
+    int64_t idx[3];
+    gr.coords(e, idx);
+    double lo[3], ext[3];
+    gr.cell(idx, lo, ext);
+    double perimeter = 0.;
+    for (int k = 0; k < gr.d; ++k)
+      for (int s = 0; s < 2; ++s)
+        perimeter += make_face(gr, ext, k, s).ie;
+    perimeter_over_volume = std::max(perimeter_over_volume, perimeter / gr.volume(ext));
+  }
+  return 1. / (perimeter_over_volume * max_flux_derivative);
 }
 
 int orc_fv_euler(const orc_grid* g, const orc_flux* flux, double* u, double dt, int64_t n_steps, int num_threads)
@@ -1222,7 +1389,7 @@ int orc_fv_euler(const orc_grid* g, const orc_flux* flux, double* u, double dt, 
   Grid gr(g);
   std::vector<double> L(gr.ne);
   for (int64_t s = 0; s < n_steps; ++s) {
-    fv_apply(gr, *flux, u, L.data(), num_threads);
+    fv_apply(gr, *flux, 0, nullptr, u, L.data(), num_threads);
     for (int64_t i = 0; i < gr.ne; ++i) // u_n - L(u_n) * dt
       u[i] = u[i] - L[i] * dt;
   }

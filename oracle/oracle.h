@@ -144,6 +144,20 @@ typedef struct orc_flux
   double p[4];
 } orc_flux;
 
+/* boundary treatments of the FV operator (operators/advection-fv.hh:96-123, local/operators/advection-fv.hh:188-457);
+ * side_mask bit (2k+s): domain face with outer normal -e_k (s = 0) / +e_k (s = 1) */
+enum
+{
+  ORC_FVBND_EXTRAPOLATION = 0, /* ...ByCustomExtrapolationOperator with v = a u + b           */
+  ORC_FVBND_NUMERICAL_FLUX = 1 /* ...ByCustomNumericalFluxOperator with g = a (f(u) . n) + b  */
+};
+typedef struct orc_fv_boundary
+{
+  int32_t kind;
+  uint32_t side_mask;
+  double a, b;
+} orc_fv_boundary;
+
 /* ---- spaces / mappers ---------------------------------------------------------------------- */
 
 int64_t orc_num_elements(const orc_grid* g);
@@ -191,6 +205,20 @@ void orc_local_element_matrix(const orc_grid* g, int kind, int order, const orc_
 int orc_fv_apply(const orc_grid* g, const orc_flux* flux, const double* u, double* out, int num_threads);
 /* u <- u - L(u) * dt (examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:152-157), n_steps times */
 int orc_fv_euler(const orc_grid* g, const orc_flux* flux, double* u, double dt, int64_t n_steps, int num_threads);
+/* the same with boundary treatments appended (in this order) */
+int orc_fv_apply_bnd(const orc_grid* g, const orc_flux* flux, int n_bnd, const orc_fv_boundary* bnd, const double* u,
+                     double* out, int num_threads);
+/* ExplicitRungeKuttaTimeStepper::step (tools/timestepper/explicit-rungekutta.hh:237-270) for u_t = r L(u):
+ * Butcher array A (row-major s x s), b, c; *t is advanced by min(dt, max_dt) */
+int orc_rk_step(const orc_grid* g, const orc_flux* flux, int n_bnd, const orc_fv_boundary* bnd, int num_stages,
+                const double* A, const double* b, const double* c, double r, double* u, double* t, double dt,
+                double max_dt, int num_threads);
+/* TimeStepperInterface::solve (tools/timestepper/interface.hh:191-263), nothing saved or written */
+int orc_rk_solve(const orc_grid* g, const orc_flux* flux, int n_bnd, const orc_fv_boundary* bnd, int num_stages,
+                 const double* A, const double* b, const double* c, double r, double* u, double t0, double t_end,
+                 double initial_dt, int64_t* n_steps, double* t_final, int num_threads);
+/* estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh:38-86), m = 1, FV state; boundary_data_range: {min, max} or NULL */
+double orc_fv_estimate_dt(const orc_grid* g, const orc_flux* flux, const double* u, const double* boundary_data_range);
 /* default_interpolation into the FV space: cell average by a Gauss rule of the declared order
  * (spaces/basis/finite-volume.hh:244-252) */
 void orc_fv_interpolate(const orc_grid* g, const orc_function* f, double* u);
