@@ -50,7 +50,10 @@ class Context:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_ctx_destroy(self._h)
+            try:
+                lib().gdtb_ctx_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
             self._h = C.c_void_p()
 
 
@@ -70,7 +73,10 @@ class Grid:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_grid_destroy(self._h)
+            try:
+                lib().gdtb_grid_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
 
 
 def make_cube_grid(ctx, lower, upper, num_elements, periodic=0):
@@ -108,7 +114,10 @@ class Space:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_space_destroy(self._h)
+            try:
+                lib().gdtb_space_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
 
 
 def make_continuous_lagrange_space(grid, order):
@@ -162,7 +171,10 @@ class SparsityPattern:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_pattern_destroy(self._h)
+            try:
+                lib().gdtb_pattern_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
 
 
 def make_sparsity_pattern(test_space, ansatz_space=None, stencil=Stencil.element, method=D.PATTERN_AUTO):
@@ -373,7 +385,10 @@ class VectorBasedFunctional:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_vecfun_destroy(self._h)
+            try:
+                lib().gdtb_vecfun_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
 
 
 def make_vector_functional(space):
@@ -476,7 +491,10 @@ class MatrixOperator:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_matop_destroy(self._h)
+            try:
+                lib().gdtb_matop_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
 
 
 def make_matrix_operator(space, stencil=Stencil.element, ansatz_space=None, pattern=None):
@@ -557,7 +575,10 @@ class AdvectionFvOperator:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_fvop_destroy(self._h)
+            try:
+                lib().gdtb_fvop_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
 
 
 def make_advection_fv_operator(numerical_flux, source_space, range_space=None):
@@ -626,7 +647,10 @@ class ExplicitRungeKuttaTimeStepper:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_rk_destroy(self._h)
+            try:
+                lib().gdtb_rk_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
 
 
 # ---- callers on either side of the hot path ---------------------------------------------
@@ -658,7 +682,10 @@ class DirichletConstraints:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().gdtb_dirichlet_destroy(self._h)
+            try:
+                lib().gdtb_dirichlet_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
 
 
 def make_dirichlet_constraints(space, boundary_info=D.BOUNDARY_ALL):

@@ -60,6 +60,11 @@ __device__ __forceinline__ void q2_bulk_wait0()
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+__device__ __forceinline__ void q2_prefetch_l1(const void* ptr)
+{
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+
 __device__ __forceinline__ double q2_cell_extent(double lo, double h, int i)
 {
   const double lower = __dadd_rn(lo, __dmul_rn(double(i), h));
@@ -68,6 +73,74 @@ __device__ __forceinline__ double q2_cell_extent(double lo, double h, int i)
 }
 
 constexpr int Q2G_THREADS = 256;
+
+// Closed-form CSR row starts.  Along one axis with N elements a row at lattice coordinate p = 2 c + S couples to
+// L(c) lattice points: S = 1: 3 (never clipped); S = 0: 5 - 2 [c == 0] - 2 [c == N].  The rows of a row group are
+// lexicographic (x fastest) and a row holds Lx Ly Ll entries, so with the 1D prefix sums PL(c) = sum_{c' < c} L(c')
+// and totals T the entries before row (cx, cy, cl) of its group number
+//   Tx Ty PLl(cl) + Ll(cl) (Tx PLy(cy) + Ly(cy) PLx(cx)).
+// rowptr is never read (it is what the pattern builder produces for this space; the parity tests compare both).
+struct Q2AxisLen
+{
+  int L;        // entries along the axis for this row
+  long long PL; // entries along the axis of the rows before it
+};
+__host__ __device__ __forceinline__ Q2AxisLen q2_axis_len(int S, int c, int N)
+{
+  Q2AxisLen r;
+  if (S) {
+    r.L = 3;
+    r.PL = 3LL * c;
+  } else {
+    r.L = 5 - (c == 0 ? 2 : 0) - (c == N ? 2 : 0);
+    r.PL = 5LL * c - (c > 0 ? 2 : 0);
+  }
+  return r;
+}
+__host__ __device__ __forceinline__ long long q2_axis_total(int S, long long N)
+{
+  return S ? 3 * N : 5 * N + 1;
+}
+
+// n / d for a run-time constant d through its magic m = floor(2^64 / d) + 1 (exact for all 32-bit n; d = 1 has no magic)
+__device__ __forceinline__ unsigned q2_div(const unsigned n, const unsigned d, const unsigned long long m)
+{
+  return d == 1 ? n : (unsigned)__umul64hi((unsigned long long)n, m);
+}
+
+// decode the lexicographic row index inside a row group into element-lattice coordinates
+template <int D>
+__device__ __forceinline__ void q2_decode(const Q2RowGroup& rg, const unsigned lex, int& cx, int& cy, int& cl)
+{
+  const unsigned t1 = q2_div(lex, rg.ex, rg.mex);
+  cx = int(lex - t1 * rg.ex);
+  if (D == 3) {
+    const unsigned t2 = q2_div(t1, rg.ey, rg.mey);
+    cy = int(t1 - t2 * rg.ey);
+    cl = (int)t2;
+  } else {
+    cy = 0;
+    cl = (int)t1;
+  }
+}
+
+// number of matrix entries of the row group that precede row (cx, cy, cl); the part inside one layer of the last axis
+// stays below 2^32 (25 (N + 1)^2 entries)
+template <int D>
+__device__ __forceinline__ long long q2_row_offset(const GridDev& g, const Q2RowGroup& rg, const int cx, const int cy,
+                                                   const int cl)
+{
+  const int s = rg.s;
+  const Q2AxisLen X = q2_axis_len(s & 1, cx, (int)g.n[0]);
+  if (D == 3) {
+    const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cy, (int)g.n[1]);
+    const Q2AxisLen Z = q2_axis_len((s >> 2) & 1, cl, (int)g.n[2]);
+    const unsigned inner = rg.Tx * (unsigned)Y.PL + (unsigned)Y.L * (unsigned)X.PL;
+    return rg.TxTy * Z.PL + (long long)((unsigned long long)(unsigned)Z.L * inner);
+  }
+  const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cl, (int)g.n[1]);
+  return (long long)rg.Tx * Y.PL + (long long)((unsigned long long)(unsigned)Y.L * (unsigned)X.PL);
+}
 
 // per-axis description of a row's coupling box for parity S (compile time): the row's lattice coordinate is
 // p = 2 c + S; box offsets a = 0 .. A-1 mean q = p - R + a with R = S ? 1 : 2, A = S ? 3 : 5
@@ -150,8 +223,8 @@ __device__ __forceinline__ constexpr int q2_group_order(int D, int rank)
 
 // One (row, plane): D == 3: SX, SY in-thread axes, SL = parity of the last (plane) axis; D == 2: SX in-thread, SL = y.
 template <int D, int SX, int SY, int SL>
-__device__ __forceinline__ void q2_row_plane(const Q2GatherParams& p, const long long lex, const int slot,
-                                             double* __restrict__ row)
+__device__ __forceinline__ void q2_row_plane(const Q2GatherParams& p, const int cx, const int cy, const int cl,
+                                             const int slot, double* __restrict__ row)
 {
   using BX = AxisBox<SX>;
   using BY = AxisBox<SY>;
@@ -159,18 +232,6 @@ __device__ __forceinline__ void q2_row_plane(const Q2GatherParams& p, const long
   const GridDev& g = p.g;
   constexpr int last = D - 1;
   const int Nx = (int)g.n[0], Ny = D == 3 ? (int)g.n[1] : 1, Nl = (int)g.n[last];
-  // group extents: S ? N : N + 1 along each axis; lexicographic, x fastest
-  const unsigned ex = SX ? Nx : Nx + 1, ey = D == 3 ? (SY ? Ny : Ny + 1) : 1;
-  const unsigned l32 = (unsigned)lex;
-  const unsigned t1 = l32 / ex;
-  const int cx = int(l32 - t1 * ex);
-  int cy = 0, cl;
-  if (D == 3) {
-    const unsigned t2 = t1 / ey;
-    cy = int(t1 - t2 * ey);
-    cl = (int)t2;
-  } else
-    cl = (int)t1;
 
   AxisRuntime ax, ay, al;
   axis_setup<SX>(ax, cx, Nx, g.lo[0], g.h[0]);
@@ -308,51 +369,291 @@ __device__ __forceinline__ void q2_row_plane(const Q2GatherParams& p, const long
   }
 }
 
-template <int D, bool ACCUMULATE>
+// ---- sum-factorised variant (every coefficient constant) ------------------------------------------------------
+// With c_e = c the sum over the elements around p factorises too: along every axis the <= 2 elements that contain p
+// contribute the 1D row vectors K[a] = sum_e K1[i_e][a - first_e] / h_e and M[a] = sum_e M1[i_e][a - first_e] h_e
+// (a = box offset), and the row is   c sum_r prod_k (k == r ? K^(k) : M^(k))   (mass: c prod_k M^(k)).  The vectors
+// depend on one lattice coordinate only; k_q2_axis_tables evaluates them once per launch (geometry per element in
+// FP64 as above), the row kernel loads 22 numbers and spends 2 FMA-class instructions per matrix entry:
+//   row[a_l][a_y][a_x] = MY[a_y] * P[a_x] + Q[a_y] * MX[a_x],  P = c (ML KX + KL MX),  Q = c ML KY.
+__global__ void __launch_bounds__(128) k_q2_axis_tables(const __grid_constant__ Q2GatherParams p, double* __restrict__ tab)
+{
+  const GridDev& g = p.g;
+  const int D = g.d;
+  long long total = 0;
+  for (int k = 0; k < D; ++k)
+    total += 2 * g.n[k] + 1;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total * p.n_groups;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int gi = int(t / total);
+    long long r = t - gi * total;
+    int k = 0;
+    while (r >= 2 * g.n[k] + 1) {
+      r -= 2 * g.n[k] + 1;
+      ++k;
+    }
+    const int pt = (int)r, S = pt & 1, c = pt >> 1, N = (int)g.n[k];
+    const Q2Group& G = p.group[gi];
+    double K[5] = {0., 0., 0., 0., 0.}, M[5] = {0., 0., 0., 0., 0.};
+    for (int o = 0; o < (S ? 1 : 2); ++o) {
+      const int e = S ? c : c - 1 + o;
+      if (e < 0 || e >= N)
+        continue;
+      const double ext = q2_cell_extent(g.lo[k], g.h[k], e);
+      const double inv = __drcp_rn(ext);
+      const int first = S ? 0 : 2 * o, il = S ? 1 : 2 - 2 * o;
+      for (int j = 0; j < 3; ++j) {
+        K[first + j] = fma(inv, G.TK[il][j], K[first + j]);
+        M[first + j] = fma(ext, G.TM[il][j], M[first + j]);
+      }
+    }
+    double* out = tab + gi * p.sf_group_stride + p.sf_axis_off[k] + 10LL * pt;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      out[a] = K[a];
+      out[5 + a] = M[a];
+    }
+  }
+}
+
+// number of box offsets a in [lo, hi] with a & 1 == par
+__device__ __forceinline__ int q2_count_par(int lo, int hi, int par)
+{
+  const int first = lo + ((lo ^ par) & 1);
+  return first <= hi ? ((hi - first) >> 1) + 1 : 0;
+}
+
+template <int A>
+__device__ __forceinline__ void q2_load_axis(const double* __restrict__ t, double (&K)[A], double (&M)[A])
+{
+  // 10 doubles per lattice point, 16-byte aligned pairs: K0 K1 | K2 K3 | K4 M0 | M1 M2 | M3 M4
+  const double2* q = reinterpret_cast<const double2*>(t);
+  const double2 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+  K[0] = v0.x;
+  K[1] = v0.y;
+  K[2] = v1.x;
+  M[0] = v2.y;
+  M[1] = v3.x;
+  M[2] = v3.y;
+  if (A == 5) {
+    const double2 v4 = __ldg(q + 4);
+    K[A - 2] = v1.y;
+    K[A - 1] = v2.x;
+    M[A - 2] = v4.x;
+    M[A - 1] = v4.y;
+  }
+}
+
+// one group's contribution to the (a_y, a_x) plane of a row; FIRST: assign instead of accumulate
+template <int D, int AX, int AY, bool FIRST>
+__device__ __forceinline__ void q2_sf_group(const Q2GatherParams& p, const int gi, const int px, const int py, const int pl,
+                                            const int slot, double (&acc)[AY][AX])
+{
+  constexpr int last = D - 1;
+  const Q2Group& G = p.group[gi];
+  const double* tab = p.sf_tab + gi * p.sf_group_stride;
+  double KX[AX], MX[AX], KY[AY], MY[AY];
+  q2_load_axis<AX>(tab + p.sf_axis_off[0] + 10LL * px, KX, MX);
+  if (D == 3)
+    q2_load_axis<AY>(tab + p.sf_axis_off[1] + 10LL * py, KY, MY);
+  const double* tl = tab + p.sf_axis_off[last] + 10LL * pl;
+  const double ML = G.scale * __ldg(tl + 5 + slot);
+  if (G.kind == Q1G_MASS) {
+#pragma unroll
+    for (int a = 0; a < AY; ++a) {
+      const double m = D == 3 ? ML * MY[a] : ML;
+#pragma unroll
+      for (int b = 0; b < AX; ++b)
+        acc[a][b] = FIRST ? m * MX[b] : fma(m, MX[b], acc[a][b]);
+    }
+  } else {
+    const double KL = G.scale * __ldg(tl + slot);
+    double P[AX];
+#pragma unroll
+    for (int b = 0; b < AX; ++b)
+      P[b] = fma(ML, KX[b], KL * MX[b]);
+#pragma unroll
+    for (int a = 0; a < AY; ++a) {
+      const double q = D == 3 ? ML * KY[a] : 0.;
+#pragma unroll
+      for (int b = 0; b < AX; ++b) {
+        if (D == 3)
+          acc[a][b] = FIRST ? fma(MY[a], P[b], q * MX[b]) : fma(MY[a], P[b], fma(q, MX[b], acc[a][b]));
+        else
+          acc[a][b] = FIRST ? P[b] : acc[a][b] + P[b];
+      }
+    }
+  }
+}
+
+template <int D, int SX, int SY, int SL>
+__device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const int cx, const int cy, const int cl,
+                                                const int slot, double* __restrict__ row)
+{
+  using BX = AxisBox<SX>;
+  using BY = AxisBox<SY>;
+  using BL = AxisBox<SL>;
+  const GridDev& g = p.g;
+  constexpr int last = D - 1;
+  if (slot >= BL::A)
+    return;
+  const int Nx = (int)g.n[0], Ny = D == 3 ? (int)g.n[1] : 1, Nl = (int)g.n[last];
+  const int px = 2 * cx + SX, py = 2 * cy + SY, pl = 2 * cl + SL;
+  constexpr int AX = BX::A, AY = D == 3 ? BY::A : 1, AL = BL::A;
+  // the plane must lie inside the lattice
+  const int ql = pl - BL::R + slot;
+  if (ql < 0 || ql > 2 * Nl)
+    return;
+
+  double acc[AY][AX];
+  q2_sf_group<D, AX, AY, true>(p, 0, px, py, pl, slot, acc);
+#pragma unroll 1
+  for (int gi = 1; gi < p.n_groups; ++gi)
+    q2_sf_group<D, AX, AY, false>(p, gi, px, py, pl, slot, acc);
+
+  // parity of the lattice point at box offset a is a & 1 (S + R = 2 for both parities); the column groups of a row
+  // come in ascending global index (codim ascending, shift ascending), each lexicographic with x fastest
+  const bool interior = px >= BX::R && px + BX::R <= 2 * Nx && (D == 2 || (py >= BY::R && py + BY::R <= 2 * Ny))
+                        && pl >= BL::R && pl + BL::R <= 2 * Nl;
+  const int parl = slot & 1;
+  if (interior) {
+    // unclipped box: every count and group start is a compile-time number, only the plane is a run-time choice
+    constexpr int NX[2] = {(AX + 1) / 2, AX / 2}, NY[2] = {D == 3 ? (AY + 1) / 2 : 1, D == 3 ? AY / 2 : 0};
+    constexpr int NL[2] = {(AL + 1) / 2, AL / 2};
+    int start_[2][1 << (D - 1)]; // [plane parity][sx | sy << 1]
+    {
+      int running = 0;
+#pragma unroll
+      for (int r = 0; r < (1 << D); ++r) {
+        const int s = q2_group_order(D, r);
+        const int sx = s & 1, sy = D == 3 ? (s >> 1) & 1 : 0, sl = (s >> (D - 1)) & 1;
+        start_[sl][s & ((1 << (D - 1)) - 1)] = running;
+        running += NX[sx] * (D == 3 ? NY[sy] : 1) * NL[sl];
+      }
+    }
+    const int idx_l = slot >> 1;
+    double* plane[1 << (D - 1)];
+#pragma unroll
+    for (int sxy = 0; sxy < (1 << (D - 1)); ++sxy) {
+      const int sx = sxy & 1, sy = D == 3 ? sxy >> 1 : 0;
+      plane[sxy] = row + (parl ? start_[1][sxy] : start_[0][sxy]) + idx_l * (NX[sx] * (D == 3 ? NY[sy] : 1));
+    }
+#pragma unroll
+    for (int a = 0; a < AY; ++a)
+#pragma unroll
+      for (int b = 0; b < AX; ++b)
+        plane[(b & 1) | (D == 3 ? (a & 1) << 1 : 0)][(a >> 1) * NX[b & 1] + (b >> 1)] = acc[a][b];
+    return;
+  }
+
+  // clipped box at the grid boundary: offsets [lo, hi] are inside the lattice
+  const int xlo = max(0, BX::R - px), xhi = BX::A - 1 - max(0, px + BX::R - 2 * Nx);
+  const int ylo = D == 3 ? max(0, BY::R - py) : 0, yhi = D == 3 ? BY::A - 1 - max(0, py + BY::R - 2 * Ny) : 0;
+  const int llo = max(0, BL::R - pl), lhi = BL::A - 1 - max(0, pl + BL::R - 2 * Nl);
+  const int nx0 = q2_count_par(xlo, xhi, 0), nx1 = q2_count_par(xlo, xhi, 1);
+  const int ny0 = D == 3 ? q2_count_par(ylo, yhi, 0) : 1, ny1 = D == 3 ? q2_count_par(ylo, yhi, 1) : 0;
+  const int nl0 = q2_count_par(llo, lhi, 0), nl1 = q2_count_par(llo, lhi, 1);
+  const int idx_l = (slot - llo) >> 1;
+  int base[1 << (D - 1)];
+  {
+    int running = 0;
+#pragma unroll
+    for (int r = 0; r < (1 << D); ++r) {
+      const int s = q2_group_order(D, r);
+      const int sx = s & 1, sy = D == 3 ? (s >> 1) & 1 : 0, sl = (s >> (D - 1)) & 1;
+      if (sl == parl)
+        base[s & ((1 << (D - 1)) - 1)] = running;
+      running += (sx ? nx1 : nx0) * (D == 3 ? (sy ? ny1 : ny0) : 1) * (sl ? nl1 : nl0);
+    }
+  }
+  // entries of equal parity along x are consecutive, idx_x(b) = (b >> 1) - shift_par
+  const int shx0 = (xlo + 1) >> 1, shx1 = xlo >> 1;
+#pragma unroll
+  for (int a = 0; a < AY; ++a) {
+    if (D == 3 && (a < ylo || a > yhi))
+      continue;
+    const int pary = a & 1;
+    const int line = D == 3 ? idx_l * (pary ? ny1 : ny0) + ((a - ylo) >> 1) : idx_l;
+    double* r0 = row + base[D == 3 ? (pary << 1) : 0] + line * nx0 - shx0;
+    double* r1 = row + base[D == 3 ? (1 | (pary << 1)) : 1] + line * nx1 - shx1;
+#pragma unroll
+    for (int b = 0; b < AX; ++b) {
+      if (b < xlo || b > xhi)
+        continue;
+      if (b & 1)
+        r1[b >> 1] = acc[a][b];
+      else
+        r0[b >> 1] = acc[a][b];
+    }
+  }
+}
+
+template <bool SF, int D, int SX, int SY, int SL>
+__device__ __forceinline__ void q2_dispatch(const Q2GatherParams& p, const int cx, const int cy, const int cl,
+                                            const int slot, double* __restrict__ row)
+{
+  if (SF)
+    q2_row_plane_sf<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
+  else
+    q2_row_plane<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
+}
+
+template <int D, bool ACCUMULATE, bool SF>
 __global__ void __launch_bounds__(Q2G_THREADS, 2)
     k_q2_gather(const __grid_constant__ Q2GatherParams p, double* __restrict__ values, int stage_doubles)
 {
   extern __shared__ __align__(16) double smem[];
+  const GridDev& g = p.g;
   int buf = 0;
   for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     // ---- per item (uniform): row group, rows, CSR segment ---------------------------------------------------
     int gi = 0;
 #pragma unroll
     for (int k = 1; k < 8; ++k)
-      if (k < p.n_rowgroups && item >= p.rg[k].item_begin)
+      if (k < p.n_rowgroups && (int)item >= (int)p.rg[k].item_begin)
         gi = k;
     const Q2RowGroup& rg = p.rg[gi];
-    const int slots = ((rg.s >> (D - 1)) & 1) ? 3 : 5;
-    const int rpi = Q2G_THREADS / slots;
-    const long long lrow0 = (item - rg.item_begin) * rpi; // first row of the item inside its group
+    const int s = rg.s;
+    const bool five = !((s >> (D - 1)) & 1);
+    const int slots = five ? 5 : 3;
+    const int rpi = five ? Q2G_THREADS / 5 : Q2G_THREADS / 3;
+    const unsigned lrow0 = unsigned(item - rg.item_begin) * rpi; // first row of the item inside its group
     const int nrows = (int)min((long long)rpi, rg.rows - lrow0);
-    const long long row0 = rg.row_begin + lrow0;
-    const long long start = __ldg(p.rowptr + row0);
-    const int seg = int(__ldg(p.rowptr + row0 + nrows) - start);
+    int ux, uy, ul;
+    q2_decode<D>(rg, lrow0, ux, uy, ul);
+    const long long off0 = q2_row_offset<D>(g, rg, ux, uy, ul);
+    long long off1 = rg.value_count;
+    if ((long long)lrow0 + nrows < rg.rows) {
+      q2_decode<D>(rg, lrow0 + nrows, ux, uy, ul);
+      off1 = q2_row_offset<D>(g, rg, ux, uy, ul);
+    }
+    const long long start = rg.value_begin + off0;
+    const int seg = int(off1 - off0);
     const int phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
     double* stage = smem + buf * stage_doubles + phase;
 
-    const int lr = threadIdx.x / slots, slot = threadIdx.x - lr * slots;
+    const int lr = five ? threadIdx.x / 5 : threadIdx.x / 3, slot = threadIdx.x - lr * slots;
     if (lr < nrows) {
-      double* row = stage + int(__ldg(p.rowptr + row0 + lr) - start);
-      const long long lex = lrow0 + lr;
+      int cx, cy, cl;
+      q2_decode<D>(rg, lrow0 + lr, cx, cy, cl);
+      double* row = stage + int(q2_row_offset<D>(g, rg, cx, cy, cl) - off0);
       if (D == 3) {
         switch (rg.s) {
-          case 0: q2_row_plane<3, 0, 0, 0>(p, lex, slot, row); break;
-          case 1: q2_row_plane<3, 1, 0, 0>(p, lex, slot, row); break;
-          case 2: q2_row_plane<3, 0, 1, 0>(p, lex, slot, row); break;
-          case 3: q2_row_plane<3, 1, 1, 0>(p, lex, slot, row); break;
-          case 4: q2_row_plane<3, 0, 0, 1>(p, lex, slot, row); break;
-          case 5: q2_row_plane<3, 1, 0, 1>(p, lex, slot, row); break;
-          case 6: q2_row_plane<3, 0, 1, 1>(p, lex, slot, row); break;
-          default: q2_row_plane<3, 1, 1, 1>(p, lex, slot, row); break;
+          case 0: q2_dispatch<SF, 3, 0, 0, 0>(p, cx, cy, cl, slot, row); break;
+          case 1: q2_dispatch<SF, 3, 1, 0, 0>(p, cx, cy, cl, slot, row); break;
+          case 2: q2_dispatch<SF, 3, 0, 1, 0>(p, cx, cy, cl, slot, row); break;
+          case 3: q2_dispatch<SF, 3, 1, 1, 0>(p, cx, cy, cl, slot, row); break;
+          case 4: q2_dispatch<SF, 3, 0, 0, 1>(p, cx, cy, cl, slot, row); break;
+          case 5: q2_dispatch<SF, 3, 1, 0, 1>(p, cx, cy, cl, slot, row); break;
+          case 6: q2_dispatch<SF, 3, 0, 1, 1>(p, cx, cy, cl, slot, row); break;
+          default: q2_dispatch<SF, 3, 1, 1, 1>(p, cx, cy, cl, slot, row); break;
         }
       } else {
         switch (rg.s) {
-          case 0: q2_row_plane<2, 0, 0, 0>(p, lex, slot, row); break;
-          case 1: q2_row_plane<2, 1, 0, 0>(p, lex, slot, row); break;
-          case 2: q2_row_plane<2, 0, 0, 1>(p, lex, slot, row); break;
-          default: q2_row_plane<2, 1, 0, 1>(p, lex, slot, row); break;
+          case 0: q2_dispatch<SF, 2, 0, 0, 0>(p, cx, cy, cl, slot, row); break;
+          case 1: q2_dispatch<SF, 2, 1, 0, 0>(p, cx, cy, cl, slot, row); break;
+          case 2: q2_dispatch<SF, 2, 0, 0, 1>(p, cx, cy, cl, slot, row); break;
+          default: q2_dispatch<SF, 2, 1, 0, 1>(p, cx, cy, cl, slot, row); break;
         }
       }
     }
@@ -387,6 +688,14 @@ __global__ void __launch_bounds__(Q2G_THREADS, 2)
 
 } // namespace
 
+long long q2_sf_table_doubles(const GridDev& g)
+{
+  long long total = 0;
+  for (int k = 0; k < g.d; ++k)
+    total += 10 * (2 * g.n[k] + 1);
+  return total;
+}
+
 int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate)
 {
   const GridDev& g = p.g;
@@ -395,9 +704,13 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: 2D and 3D grids only");
   if (sp.size >= (1LL << 31))
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: more than 2^31 degrees of freedom");
+  for (int k = 0; k < d; ++k)
+    if (g.n[k] > 5000)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: more than 5000 elements along one axis");
   // row groups in ascending global index order (codim ascending, shift bitset ascending)
   p.n_rowgroups = 0;
   p.n_items = 0;
+  long long value_begin = 0;
   int max_row = 1;
   for (int k = 0; k < d; ++k)
     max_row *= 5;
@@ -418,14 +731,35 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
       const int rpi = Q2G_THREADS / slots;
       rg.item_begin = p.n_items;
       p.n_items += (rg.rows + rpi - 1) / rpi;
+      rg.ex = (unsigned)((s & 1) ? g.n[0] : g.n[0] + 1);
+      rg.ey = d == 3 ? (unsigned)((s & 2) ? g.n[1] : g.n[1] + 1) : 1u;
+      rg.mex = rg.ex > 1 ? ~0ULL / rg.ex + 1 : 0;
+      rg.mey = rg.ey > 1 ? ~0ULL / rg.ey + 1 : 0;
+      rg.Tx = (unsigned)q2_axis_total(s & 1, g.n[0]);
+      rg.TxTy = (long long)rg.Tx * (d == 3 ? q2_axis_total((s >> 1) & 1, g.n[1]) : 1);
+      rg.value_begin = value_begin;
+      rg.value_count = 1;
+      for (int k = 0; k < d; ++k)
+        rg.value_count *= q2_axis_total((s >> k) & 1, g.n[k]);
+      value_begin += rg.value_count;
     }
   // stage: the longest segment is rows_per_item rows of the longest row kind that uses that slot count
   // (5 slots: rows up to 5^d entries, 51 rows; 3 slots: rows up to 3 * 5^(d-1), 85 rows)
   const int seg5 = (Q2G_THREADS / 5) * max_row, seg3 = (Q2G_THREADS / 3) * (max_row / 5 * 3);
   const int stage_doubles = ((std::max(seg5, seg3) + 2) + 1) & ~1;
   const size_t smem = (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double);
-  auto kern = d == 3 ? (accumulate ? k_q2_gather<3, true> : k_q2_gather<3, false>)
-                     : (accumulate ? k_q2_gather<2, true> : k_q2_gather<2, false>);
+  auto kern = d == 3 ? (accumulate ? k_q2_gather<3, true, false> : k_q2_gather<3, false, false>)
+                     : (accumulate ? k_q2_gather<2, true, false> : k_q2_gather<2, false, false>);
+  if (p.sf) {
+    kern = d == 3 ? (accumulate ? k_q2_gather<3, true, true> : k_q2_gather<3, false, true>)
+                  : (accumulate ? k_q2_gather<2, true, true> : k_q2_gather<2, false, true>);
+    long long off = 0;
+    for (int k = 0; k < d; ++k) {
+      p.sf_axis_off[k] = off;
+      off += 10 * (2 * g.n[k] + 1);
+    }
+    p.sf_group_stride = off;
+  }
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
@@ -436,6 +770,11 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
   if (grid > p.n_items)
     grid = p.n_items;
   time_begin(L, KF_Q2_GATHER);
+  if (p.sf) {
+    const long long work = p.sf_group_stride / 10 * p.n_groups;
+    k_q2_axis_tables<<<(unsigned)((work + 127) / 128), 128, 0, L.stream>>>(p, const_cast<double*>(p.sf_tab));
+    L.count++;
+  }
   kern<<<(unsigned)grid, Q2G_THREADS, smem, L.stream>>>(p, values, stage_doubles);
   time_end(L, KF_Q2_GATHER);
   L.count++;

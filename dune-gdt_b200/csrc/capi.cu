@@ -990,6 +990,7 @@ int gdtb_matop_destroy(gdtb_matop* op)
   if (op->owns_values)
     cudaFree(op->d_values);
   cudaFree(op->d_forms);
+  cudaFree(op->d_q2_tab);
   cudaFree(op->d_own_rowptr);
   cudaFree(op->d_own_colidx);
   delete op;
@@ -1395,6 +1396,22 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
   if (op_q2) {
     Q2GatherParams p;
     GDTB_TRY(build_q2_params(op, p));
+    bool all_const = true;
+    for (int gi = 0; gi < p.n_groups; ++gi)
+      all_const = all_const && !p.group[gi].coef_elem;
+    if (all_const && !std::getenv("GDTB_Q2_NO_SF")) {
+      const size_t bytes = sizeof(double) * (size_t)q2_sf_table_doubles(op->grid) * (size_t)p.n_groups;
+      if (op->d_q2_tab_bytes < bytes) {
+        cudaFree(op->d_q2_tab);
+        op->d_q2_tab = nullptr;
+        op->d_q2_tab_bytes = 0;
+        if (cudaMalloc(&op->d_q2_tab, bytes) != cudaSuccess)
+          return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (Q2 sum-factorisation tables)");
+        op->d_q2_tab_bytes = bytes;
+      }
+      p.sf = 1;
+      p.sf_tab = op->d_q2_tab;
+    }
     GDTB_TRY(launch_q2_gather(L, p, op->test, op->d_values, accumulate));
   }
 

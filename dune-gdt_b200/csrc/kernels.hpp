@@ -166,6 +166,13 @@ struct Q2RowGroup
 {
   int s;
   long long row_begin, rows, item_begin;
+  long long value_begin, value_count; // CSR range of the group's rows (closed form, see q2_row_offset)
+  // row decode and row-start arithmetic of the group: extents, their division magics floor(2^64 / e) + 1, and the
+  // per-axis entry totals Tx, Tx * Ty
+  unsigned ex, ey;
+  unsigned long long mex, mey;
+  unsigned Tx;
+  long long TxTy;
 };
 
 struct Q2GatherParams
@@ -177,8 +184,15 @@ struct Q2GatherParams
   Q2RowGroup rg[8];
   long long n_items;
   const long long* rowptr; // device CSR row pointer of the element pattern
+  // sum-factorised path (all coefficients constant): per group and axis, for every lattice point p in [0, 2 N_k] the
+  // 1D row vectors K[0..5) = sum_e K1[i_e(p)][.] / h_e and M[0..5) = sum_e M1[i_e(p)][.] h_e over the <= 2 elements
+  // that contain p, indexed by box offset; layout tab[group][sf_axis_off[k] + 10 p + {K: 0..4, M: 5..9}]
+  int sf;
+  const double* sf_tab;
+  long long sf_axis_off[3], sf_group_stride;
 };
 
+long long q2_sf_table_doubles(const GridDev& g); // doubles per group
 int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate);
 
 // ---- DG row-gather assembly (assemble_dg_gather.cu) -----------------------------------------------
