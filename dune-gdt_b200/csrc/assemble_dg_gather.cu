@@ -241,6 +241,432 @@ int launch_dg_gather_dk(Launch& L, const DgGatherParams& p, double* values, bool
   return GDTB_OK;
 }
 
+// ---- factorised path: DG order 1, constant / element-wise scalar coefficients ------------------------------------
+// On an affine axis-aligned cell every integrand of the path is a product over the axes, and the Gauss rules are
+// tensor rules, so the quadrature sums of the reference factorise EXACTLY into 1D reference tables of the form's own
+// rule (m points): M1[a][b] = sum_q w_q phi_a phi_b, K1[a][b] = sum_q w_q phi_a' phi_b', and the end values
+// phi_a(s), phi_a'(s) for the pinned axis of a face.  With per-axis cell data h_o, 1/h_o:
+//   element Laplace   kappa sum_r (K1[i_r][j_r] / h_r) prod_{o != r} h_o M1[i_o][j_o]
+//   element product   w prod_o h_o M1[i_o][j_o]
+//   face normal to k  C[i_k][j_k] prod_{o != k} h_o M1[i_o][j_o],  C = the 2 x 2 matrix of the integrand's terms in
+//                     the end values (laplace-ipdg.hh:149-185, 362-367; ipdg.hh:149-170, 276-281), coefficients per
+//                     adjacent element.
+// Same roles and signs as coupling_row / boundary_row of local_forms.cuh; results agree with the quadrature loops to
+// rounding (the parity tests compare both paths against the oracle).
+struct DgFastTab
+{
+  double M1[2][2], K1[2][2], pe[2][2], de[2][2];
+};
+
+__device__ __forceinline__ double dg_coef(const FnDev& f, long long e)
+{
+  return f.kind == GDTB_FN_ELEM_SCALAR ? __ldg(f.data + e) : f.c[0];
+}
+
+__device__ __forceinline__ double dg_ext(const GridDev& g, int k, int i)
+{
+  const double lower = __dadd_rn(g.lo[k], __dmul_rn(double(i), g.h[k]));
+  const double upper = __dadd_rn(g.lo[k], __dmul_rn(double(i + 1), g.h[k]));
+  return __dsub_rn(upper, lower);
+}
+
+// blocks (element + existing neighbours) of all elements before e in the element_and_intersection pattern
+template <int D>
+__device__ __forceinline__ long long dg_blocks_before(const GridDev& g, const long long e, const int* idx)
+{
+  const long long nx = g.n[0];
+  long long P = e;
+  const long long m = D > 1 ? (long long)idx[1] + (D > 2 ? g.n[1] * idx[2] : 0) : 0; // complete x-lines before e
+  P += (e - m - (idx[0] > 0 ? 1 : 0)) + (e - m);                                       // lower / upper x neighbours
+  if (D > 1) {
+    const long long z = D > 2 ? idx[2] : 0;
+    const long long y0 = z * nx + (idx[1] > 0 ? nx : idx[0]);                  // elements before e with y == 0
+    const long long y1 = z * nx + (idx[1] == g.n[1] - 1 ? (long long)idx[0] : 0); // ... with y == n_y - 1
+    P += (e - y0) + (e - y1);
+  }
+  if (D > 2) {
+    const long long plane = nx * g.n[1];
+    P += (e - min(e, plane)) + (e - max(0LL, e - (g.n[2] - 1) * plane));
+  }
+  return P;
+}
+
+template <int D>
+__device__ __forceinline__ int dg_nblocks(const GridDev& g, const int* idx)
+{
+  int nb = 1;
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+    nb += (idx[k] > 0 ? 1 : 0) + (idx[k] < g.n[k] - 1 ? 1 : 0);
+  return nb;
+}
+
+template <int D>
+__device__ __forceinline__ void dg_decode(const DgGatherParams& p, const unsigned e, int* idx)
+{
+  const GridDev& g = p.g;
+  const unsigned nx = (unsigned)g.n[0];
+  const unsigned t1 = D > 1 ? (nx == 1 ? e : (unsigned)__umul64hi((unsigned long long)e, p.magic[0])) : 0;
+  idx[0] = int(e - t1 * nx);
+  idx[1] = idx[2] = 0;
+  if (D == 2)
+    idx[1] = (int)t1;
+  if (D == 3) {
+    const unsigned ny = (unsigned)g.n[1];
+    const unsigned t2 = ny == 1 ? t1 : (unsigned)__umul64hi((unsigned long long)t1, p.magic[1]);
+    idx[1] = int(t1 - t2 * ny);
+    idx[2] = (int)t2;
+  }
+}
+
+// intersection_h of local_forms.cuh for axis-aligned faces: |I|, or the face diameter (1D: element lengths)
+template <int D>
+__device__ __forceinline__ double dg_face_h(const IntegrandDev& t, const double* h, int k, double h_in, double h_out,
+                                            bool neighbor)
+{
+  double ie = 1., d2 = 0.;
+#pragma unroll
+  for (int o = 0; o < D; ++o)
+    if (o != k) {
+      ie *= h[o];
+      d2 += h[o] * h[o];
+    }
+  if (t.hI_kind == GDTB_HI_VOLUME)
+    return ie;
+  if (D == 1)
+    return neighbor ? 0.5 * (h_in + h_out) : h_in;
+  return sqrt(d2);
+}
+
+// block[j] += sc * c2[j_k] * prod_{o != k} tM[o][j_o]  (j = j_0 + 2 j_1 + 4 j_2)
+template <int D>
+__device__ __forceinline__ void dg_add_face_block(double* __restrict__ block, const double sc, const double* c2, int k,
+                                                  const double (*tM)[2])
+{
+  constexpr int N = 1 << D;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double v = sc * c2[(j >> k) & 1];
+#pragma unroll
+    for (int o = 0; o < D; ++o)
+      if (o != k)
+        v *= tM[o][(j >> o) & 1];
+    block[j] += v;
+  }
+}
+
+template <int D, bool ACCUMULATE>
+__global__ void __launch_bounds__(DGG_THREADS)
+    k_dg_gather_fast(const __grid_constant__ DgGatherParams p, double* __restrict__ values, int stage_doubles)
+{
+  constexpr int N = 1 << D;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ DgFastTab tabs[DGG_MAX_FORMS];
+  const GridDev& g = p.g;
+  const int n_forms = p.n_elem + p.n_coup + p.n_bnd;
+  if ((int)threadIdx.x < n_forms) {
+    const FormDev& f = p.forms[threadIdx.x];
+    DgFastTab& t = tabs[threadIdx.x];
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        double sm = 0., sk = 0.;
+        for (int q = 0; q < f.m; ++q) {
+          sm += f.qw[q] * f.phi[q][a] * f.phi[q][b];
+          sk += f.qw[q] * f.dphi[q][a] * f.dphi[q][b];
+        }
+        t.M1[a][b] = sm;
+        t.K1[a][b] = sk;
+        t.pe[a][b] = f.phi_end[a][b];
+        t.de[a][b] = f.dphi_end[a][b];
+      }
+  }
+  __syncthreads();
+  const FormDev* f_elem = p.forms;
+  const FormDev* f_coup = p.forms + p.n_elem;
+  const FormDev* f_bnd = p.forms + p.n_elem + p.n_coup;
+  const DgFastTab* t_elem = tabs;
+  const DgFastTab* t_coup = tabs + p.n_elem;
+  const DgFastTab* t_bnd = tabs + p.n_elem + p.n_coup;
+  const long long nrows_total = g.ne * N;
+  const long long nitems = (nrows_total + DGG_THREADS - 1) / DGG_THREADS;
+  constexpr int EPI = DGG_THREADS / N; // elements per item
+  int buf = 0;
+
+  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const long long e0 = item * EPI;
+    const int ne_item = (int)min((long long)EPI, g.ne - e0);
+    int idx0[3], idx1[3];
+    dg_decode<D>(p, (unsigned)e0, idx0);
+    const long long start = (long long)N * N * dg_blocks_before<D>(g, e0, idx0);
+    long long end;
+    if (e0 + ne_item < g.ne) {
+      dg_decode<D>(p, (unsigned)(e0 + ne_item), idx1);
+      end = (long long)N * N * dg_blocks_before<D>(g, e0 + ne_item, idx1);
+    } else {
+      dg_decode<D>(p, (unsigned)(g.ne - 1), idx1);
+      end = (long long)N * N * (dg_blocks_before<D>(g, g.ne - 1, idx1) + dg_nblocks<D>(g, idx1));
+    }
+    const int seg = int(end - start);
+    const int phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
+    double* stage = smem + buf * stage_doubles + phase;
+
+    const int le = threadIdx.x / N, i = threadIdx.x & (N - 1);
+    if (le < ne_item) {
+      const long long e = e0 + le;
+      int idx[3];
+      dg_decode<D>(p, (unsigned)e, idx);
+      const int nblocks = dg_nblocks<D>(g, idx);
+      double* row = stage + int((long long)N * N * dg_blocks_before<D>(g, e, idx) - start) + i * nblocks * N;
+      long long estride[3] = {1, g.n[0], g.n[0] * g.n[1]};
+      bool has_lo[D], has_hi[D];
+      double h[D], hinv[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        has_lo[k] = idx[k] > 0;
+        has_hi[k] = idx[k] < g.n[k] - 1;
+        h[k] = dg_ext(g, k, idx[k]);
+        hinv[k] = __drcp_rn(h[k]);
+      }
+      double self[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        self[j] = 0.;
+
+      // ---- element forms --------------------------------------------------------------------------------------
+      for (int f = 0; f < p.n_elem; ++f) {
+        const FormDev& F = f_elem[f];
+        const DgFastTab& T = t_elem[f];
+        double tM[D][2], tK[D][2];
+#pragma unroll
+        for (int o = 0; o < D; ++o) {
+          const int io = (i >> o) & 1;
+          tM[o][0] = h[o] * T.M1[io][0];
+          tM[o][1] = h[o] * T.M1[io][1];
+          tK[o][0] = hinv[o] * T.K1[io][0];
+          tK[o][1] = hinv[o] * T.K1[io][1];
+        }
+        for (int tt = 0; tt < F.n_terms; ++tt) {
+          const double c = F.scaling * dg_coef(F.terms[tt].diffusion, e);
+          if (F.terms[tt].kind == GDTB_INT_LAPLACE) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              double sum = 0.;
+#pragma unroll
+              for (int r = 0; r < D; ++r) {
+                double v = tK[r][(j >> r) & 1];
+#pragma unroll
+                for (int o = 0; o < D; ++o)
+                  if (o != r)
+                    v *= tM[o][(j >> o) & 1];
+                sum += v;
+              }
+              self[j] = fma(c, sum, self[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              double v = c;
+#pragma unroll
+              for (int o = 0; o < D; ++o)
+                v *= tM[o][(j >> o) & 1];
+              self[j] += v;
+            }
+          }
+        }
+      }
+
+      // ---- faces ------------------------------------------------------------------------------------------------
+      // position of the neighbour blocks in the row: z-, y-, x-, self, x+, y+, z+ (existing ones only)
+      int pos = 0;
+      int pos_lo[D], pos_hi[D];
+#pragma unroll
+      for (int k = D - 1; k >= 0; --k) {
+        pos_lo[k] = pos;
+        pos += has_lo[k] ? N : 0;
+      }
+      const int pos_self = pos;
+      pos += N;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        pos_hi[k] = pos;
+        pos += has_hi[k] ? N : 0;
+      }
+
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const int ik = (i >> k) & 1;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const bool has = s ? has_hi[k] : has_lo[k];
+          if (has) {
+            // inner face: s == 0: this element is the outside one (inside = e - stride), s == 1: it is the inside one
+            const long long e_in = s ? e : e - estride[k], e_out = s ? e + estride[k] : e;
+            const double h_in = s ? h[k] : dg_ext(g, k, idx[k] - 1), h_out = s ? dg_ext(g, k, idx[k] + 1) : h[k];
+            const double hinv_in = s ? hinv[k] : __drcp_rn(h_in), hinv_out = s ? __drcp_rn(h_out) : hinv[k];
+            double nbb[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+              nbb[j] = 0.;
+            for (int f = 0; f < p.n_coup; ++f) {
+              const FormDev& F = f_coup[f];
+              const DgFastTab& T = t_coup[f];
+              double tM[D][2];
+#pragma unroll
+              for (int o = 0; o < D; ++o) {
+                const int io = (i >> o) & 1;
+                tM[o][0] = h[o] * T.M1[io][0];
+                tM[o][1] = h[o] * T.M1[io][1];
+              }
+              // test function on its own side: inside element -> upper end (1), outside element -> lower end (0)
+              const double vi = s ? T.pe[1][ik] : T.pe[0][ik];
+              const double gi = s ? T.de[1][ik] * hinv_in : T.de[0][ik] * hinv_out;
+              double ca[2] = {0., 0.}, cb[2] = {0., 0.}; // columns of the inside / outside element
+              for (int tt = 0; tt < F.n_terms; ++tt) {
+                const IntegrandDev& in = F.terms[tt];
+                const double delta_plus = dg_coef(in.weight, e_out), delta_minus = dg_coef(in.weight, e_in);
+                if (in.kind == GDTB_INT_IPDG_INNER_COUPLING) {
+                  const double k_in = dg_coef(in.diffusion, e_in), k_out = dg_coef(in.diffusion, e_out);
+                  const double wm = delta_plus / (delta_plus + delta_minus), wp = delta_minus / (delta_plus + delta_minus);
+                  const double sp_ = in.prefactor;
+                  const double fi = s ? k_in * gi : k_out * gi; // (kappa grad psi_i) . n on the test function's side
+#pragma unroll
+                  for (int jk = 0; jk < 2; ++jk) {
+                    const double vj_in = T.pe[1][jk], vj_out = T.pe[0][jk];
+                    const double fj_in = k_in * (T.de[1][jk] * hinv_in), fj_out = k_out * (T.de[0][jk] * hinv_out);
+                    if (s) { // laplace-ipdg.hh:158-170 (in_in, in_out)
+                      ca[jk] += -1.0 * wm * fj_in * vi;
+                      ca[jk] += -1.0 * sp_ * wm * vj_in * fi;
+                      cb[jk] += -1.0 * wp * fj_out * vi;
+                      cb[jk] += sp_ * wm * vj_out * fi;
+                    } else { // laplace-ipdg.hh:172-185 (out_in, out_out)
+                      ca[jk] += wm * fj_in * vi;
+                      ca[jk] += -1.0 * sp_ * wp * vj_in * fi;
+                      cb[jk] += wp * fj_out * vi;
+                      cb[jk] += sp_ * wp * vj_out * fi;
+                    }
+                  }
+                } else { // GDTB_INT_IPDG_INNER_PENALTY, ipdg.hh:149-170
+                  const double weight = (delta_plus * delta_minus) / (delta_plus + delta_minus);
+                  const double penalty = (in.prefactor * weight) / dg_face_h<D>(in, h, k, h_in, h_out, true);
+#pragma unroll
+                  for (int jk = 0; jk < 2; ++jk) {
+                    const double vj_in = T.pe[1][jk], vj_out = T.pe[0][jk];
+                    if (s) {
+                      ca[jk] += penalty * vj_in * vi;
+                      cb[jk] += -1.0 * penalty * vj_out * vi;
+                    } else {
+                      ca[jk] += -1.0 * penalty * vj_in * vi;
+                      cb[jk] += penalty * vj_out * vi;
+                    }
+                  }
+                }
+              }
+              // own columns: inside element -> ca, outside element -> cb
+              dg_add_face_block<D>(self, F.scaling, s ? ca : cb, k, tM);
+              dg_add_face_block<D>(nbb, F.scaling, s ? cb : ca, k, tM);
+            }
+            double* blk = row + (s ? pos_hi[k] : pos_lo[k]);
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+              blk[j] = nbb[j];
+          } else {
+            // boundary face (k, s) with outer normal sg e_k
+            const double sg = s ? 1. : -1.;
+            for (int f = 0; f < p.n_bnd; ++f) {
+              const FormDev& F = f_bnd[f];
+              const DgFastTab& T = t_bnd[f];
+              double tM[D][2];
+#pragma unroll
+              for (int o = 0; o < D; ++o) {
+                const int io = (i >> o) & 1;
+                tM[o][0] = h[o] * T.M1[io][0];
+                tM[o][1] = h[o] * T.M1[io][1];
+              }
+              const double vi = T.pe[s][ik], gi = sg * (T.de[s][ik] * hinv[k]);
+              double ca[2] = {0., 0.};
+              for (int tt = 0; tt < F.n_terms; ++tt) {
+                const IntegrandDev& in = F.terms[tt];
+                if (in.kind == GDTB_INT_IPDG_DIRICHLET_COUPLING) { // laplace-ipdg.hh:362-367
+                  const double kap = dg_coef(in.diffusion, e);
+                  const double fi = kap * gi;
+#pragma unroll
+                  for (int jk = 0; jk < 2; ++jk) {
+                    const double vj = T.pe[s][jk], fj = kap * (sg * (T.de[s][jk] * hinv[k]));
+                    ca[jk] += -1.0 * fj * vi;
+                    ca[jk] += -1.0 * in.prefactor * vj * fi;
+                  }
+                } else { // GDTB_INT_IPDG_BOUNDARY_PENALTY, ipdg.hh:276-281
+                  const double penalty = (in.prefactor * dg_coef(in.weight, e)) / dg_face_h<D>(in, h, k, h[k], h[k], false);
+#pragma unroll
+                  for (int jk = 0; jk < 2; ++jk)
+                    ca[jk] += penalty * T.pe[s][jk] * vi;
+                }
+              }
+              dg_add_face_block<D>(self, F.scaling, ca, k, tM);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        row[pos_self + j] = self[j];
+    }
+
+    if (ACCUMULATE) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < seg; t += blockDim.x)
+        values[start + t] += stage[t];
+      __syncthreads();
+    } else {
+      dg_fence_proxy_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int head = phase;
+        const int body = (seg - head) & ~1;
+        if (head)
+          values[start] = stage[0];
+        if (body > 0)
+          dg_bulk_store_s2g(values + start + head, stage + head, (unsigned)(body * sizeof(double)));
+        if (head + body < seg)
+          values[start + head + body] = stage[head + body];
+        dg_bulk_commit();
+        dg_bulk_wait_read1();
+      }
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  if (!ACCUMULATE && threadIdx.x == 0)
+    dg_bulk_wait0();
+}
+
+template <int D>
+int launch_dg_gather_fast(Launch& L, DgGatherParams& p, double* values, bool accumulate)
+{
+  constexpr int N = 1 << D;
+  for (int k = 0; k < 2; ++k)
+    p.magic[k] = p.g.n[k] > 1 ? ~0ULL / (unsigned long long)p.g.n[k] + 1 : 0;
+  const int stage_doubles = ((DGG_THREADS * N * (2 * D + 1) + 2) + 1) & ~1;
+  const size_t smem = (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double);
+  auto kern = accumulate ? k_dg_gather_fast<D, true> : k_dg_gather_fast<D, false>;
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int per_sm = 0;
+  GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DGG_THREADS, smem));
+  if (per_sm < 1)
+    return fail(GDTB_ERR_CUDA, "dg_gather: kernel does not fit on an SM");
+  const long long nitems = (p.g.ne * N + DGG_THREADS - 1) / DGG_THREADS;
+  long long grid = (long long)per_sm * L.sm_count;
+  if (grid > nitems)
+    grid = nitems;
+  time_begin(L, KF_DG_GATHER);
+  kern<<<(unsigned)grid, DGG_THREADS, smem, L.stream>>>(p, values, stage_doubles);
+  time_end(L, KF_DG_GATHER);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
 } // namespace
 
 bool dg_gather_supported(int d, int K)
@@ -248,8 +674,21 @@ bool dg_gather_supported(int d, int K)
   return (K == 1 && d >= 1 && d <= 3) || (K == 2 && d >= 1 && d <= 2);
 }
 
+bool dg_gather_fast_supported(const GridDev& g, int K)
+{
+  return K == 1 && g.d >= 1 && g.d <= 3 && g.ne < (1LL << 31) / (1 << g.d);
+}
+
 int launch_dg_gather(Launch& L, const DgGatherParams& p, double* values, bool accumulate)
 {
+  if (p.fast) {
+    DgGatherParams q = p;
+    switch (p.g.d) {
+      case 1: return launch_dg_gather_fast<1>(L, q, values, accumulate);
+      case 2: return launch_dg_gather_fast<2>(L, q, values, accumulate);
+      default: return launch_dg_gather_fast<3>(L, q, values, accumulate);
+    }
+  }
   switch (p.g.d * 10 + p.sp.K) {
     case 11: return launch_dg_gather_dk<1, 1>(L, p, values, accumulate);
     case 21: return launch_dg_gather_dk<2, 1>(L, p, values, accumulate);

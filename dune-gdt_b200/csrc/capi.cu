@@ -1439,9 +1439,13 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
         return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the lowered forms");
       op->d_forms_bytes = bytes;
     }
-    // the host vector dies at the end of this scope: synchronous copy
-    GDTB_CUDA(cudaMemcpyAsync(op->d_forms, forms.data(), bytes, cudaMemcpyHostToDevice, L.stream));
-    GDTB_CUDA(cudaStreamSynchronize(L.stream));
+    // upload only when the lowered forms changed since the last assembly (the host vector dies at the end of this
+    // scope: synchronous copy)
+    if (op->h_forms_cache.size() != bytes || std::memcmp(op->h_forms_cache.data(), forms.data(), bytes) != 0) {
+      GDTB_CUDA(cudaMemcpyAsync(op->d_forms, forms.data(), bytes, cudaMemcpyHostToDevice, L.stream));
+      GDTB_CUDA(cudaStreamSynchronize(L.stream));
+      op->h_forms_cache.assign(reinterpret_cast<const char*>(forms.data()), reinterpret_cast<const char*>(forms.data()) + bytes);
+    }
     DgGatherParams p;
     std::memset(&p, 0, sizeof(p));
     p.g = op->grid;
@@ -1451,6 +1455,13 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     p.n_coup = (int)op->coupling_forms.size();
     p.n_bnd = (int)op->boundary_forms.size();
     p.rowptr = op->pattern->d_rowptr;
+    // factorised kernel: order 1 and every coefficient a constant or element-wise scalar
+    const auto scalar = [](const FnDev& f) { return f.kind == GDTB_FN_CONST_SCALAR || f.kind == GDTB_FN_ELEM_SCALAR; };
+    bool fast = dg_gather_fast_supported(op->grid, op->test.K) && !std::getenv("GDTB_DG_NO_FAST");
+    for (const FormDev& f : forms)
+      for (int t = 0; t < f.n_terms; ++t)
+        fast = fast && scalar(f.terms[t].diffusion) && scalar(f.terms[t].weight);
+    p.fast = fast ? 1 : 0;
     GDTB_TRY(launch_dg_gather(L, p, op->d_values, accumulate));
   }
 

@@ -85,6 +85,7 @@ struct gdtb_matop
   std::string plan;
   void* d_forms = nullptr; // lowered FormDev array of the DG gather path
   size_t d_forms_bytes = 0;
+  std::vector<char> h_forms_cache; // what d_forms holds
   double* d_q2_tab = nullptr; // per-axis sum-factorisation tables of the CG Q2 gather path
   size_t d_q2_tab_bytes = 0;
   // CSR pattern materialised on demand for the closed-form CG Q1 operator (Dirichlet constraints, SpMV, solvers)

@@ -206,9 +206,14 @@ struct DgGatherParams
   const FormDev* forms; // device array: element forms, then coupling forms, then boundary forms
   int n_elem, n_coup, n_bnd;
   const long long* rowptr; // device CSR row pointer of the element_and_intersection pattern
+  // factorised path (order 1, every coefficient a constant or element-wise scalar): the quadrature sums of all forms
+  // collapse into 1D tables; row starts are closed forms (rowptr is not read)
+  int fast;
+  unsigned long long magic[2]; // floor(2^64 / n_k) + 1 for the element-index decode (0 when n_k == 1)
 };
 
 bool dg_gather_supported(int d, int K);
+bool dg_gather_fast_supported(const GridDev& g, int K);
 int launch_dg_gather(Launch& L, const DgGatherParams& p, double* values, bool accumulate);
 
 // ---- sparsity pattern (pattern.cu) ----------------------------------------------------------------
