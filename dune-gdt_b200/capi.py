@@ -125,6 +125,7 @@ PROTOTYPES = {
     "gdtb_assemble_async": (C.c_int, [_P, _P, C.c_int]),
     "gdtb_matop_local_nnz": (C.c_int64, [_P]),
     "gdtb_matop_local_rows": (C.c_int, [_P, _I64P, _I64P, _I64P]),
+    "gdtb_matop_local_row_ranges": (C.c_int, [_P, C.c_int32, _I64P, _I64P, _I64P, _I64P, C.POINTER(C.c_int32)]),
     "gdtb_assemble_host": (C.c_int, [_P, _P, _DP, _DP]),
     "gdtb_fvop_create": (C.c_int, [_P, _P, C.POINTER(Flux), _PP]),
     "gdtb_fvop_destroy": (C.c_int, [_P]),

@@ -617,13 +617,13 @@ __global__ void __launch_bounds__(Q2G_THREADS, 2)
     const bool five = !((s >> (D - 1)) & 1);
     const int slots = five ? 5 : 3;
     const int rpi = five ? Q2G_THREADS / 5 : Q2G_THREADS / 3;
-    const unsigned lrow0 = unsigned(item - rg.item_begin) * rpi; // first row of the item inside its group
-    const int nrows = (int)min((long long)rpi, rg.rows - lrow0);
+    const unsigned lrow0 = unsigned(rg.lex_begin) + unsigned(item - rg.item_begin) * rpi; // first row of the item
+    const int nrows = (int)min((long long)rpi, rg.lex_end - lrow0);
     int ux, uy, ul;
     q2_decode<D>(rg, lrow0, ux, uy, ul);
     const long long off0 = q2_row_offset<D>(g, rg, ux, uy, ul);
-    long long off1 = rg.value_count;
-    if ((long long)lrow0 + nrows < rg.rows) {
+    long long off1 = rg.off_end;
+    if ((long long)lrow0 + nrows < rg.lex_end) {
       q2_decode<D>(rg, lrow0 + nrows, ux, uy, ul);
       off1 = q2_row_offset<D>(g, rg, ux, uy, ul);
     }
@@ -688,6 +688,45 @@ __global__ void __launch_bounds__(Q2G_THREADS, 2)
 
 } // namespace
 
+int q2_slab_ranges(const GridDev& g, const SpaceDev& sp, Q2SlabRange* out)
+{
+  const int d = g.d;
+  const long long Nl = g.n[d - 1];
+  const long long zb = g.layer_lo, ze = g.layer_hi;
+  int r = 0;
+  long long global_value = 0, local = 0;
+  for (int c = 0; c <= d; ++c)
+    for (int s = 0; s < (1 << d); ++s) {
+      int pc = 0;
+      for (int k = 0; k < d; ++k)
+        pc += (s >> k) & 1;
+      if (pc != d - c)
+        continue;
+      long long per_layer = 1, layer_entries = 1, total = 1;
+      for (int k = 0; k < d - 1; ++k) {
+        per_layer *= ((s >> k) & 1) ? g.n[k] : g.n[k] + 1;
+        layer_entries *= q2_axis_total((s >> k) & 1, g.n[k]);
+      }
+      const int SL = (s >> (d - 1)) & 1;
+      total = layer_entries * q2_axis_total(SL, Nl);
+      // lattice layers p_l = 2 c_l + SL of the element layers [zb, ze); the last slab also owns the top (even) layer
+      const long long cl_lo = zb, cl_hi = SL ? ze : (ze == Nl ? Nl + 1 : ze);
+      const long long layers_in_group = SL ? Nl : Nl + 1;
+      const long long off_lo = layer_entries * q2_axis_len(SL, (int)cl_lo, (int)Nl).PL;
+      const long long off_hi = cl_hi == layers_in_group ? total : layer_entries * q2_axis_len(SL, (int)cl_hi, (int)Nl).PL;
+      Q2SlabRange& R = out[r++];
+      const long long group_row_begin = sp.cg.codim_offset[c] + sp.cg.group_offset[s];
+      R.row_begin = group_row_begin + cl_lo * per_layer;
+      R.row_end = group_row_begin + cl_hi * per_layer;
+      R.value_offset = global_value + off_lo;
+      R.local_offset = local;
+      R.count = off_hi - off_lo;
+      local += R.count;
+      global_value += total;
+    }
+  return r;
+}
+
 long long q2_sf_table_doubles(const GridDev& g)
 {
   long long total = 0;
@@ -707,42 +746,50 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
   for (int k = 0; k < d; ++k)
     if (g.n[k] > 5000)
       return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: more than 5000 elements along one axis");
-  // row groups in ascending global index order (codim ascending, shift bitset ascending)
-  p.n_rowgroups = 0;
+  // row groups in ascending global index order (codim ascending, shift bitset ascending), restricted to the slab
+  Q2SlabRange ranges[8];
+  p.n_rowgroups = q2_slab_ranges(g, sp, ranges);
   p.n_items = 0;
-  long long value_begin = 0;
   int max_row = 1;
   for (int k = 0; k < d; ++k)
     max_row *= 5;
-  for (int c = 0; c <= d; ++c)
-    for (int s = 0; s < (1 << d); ++s) {
-      int pc = 0;
-      for (int k = 0; k < d; ++k)
-        pc += (s >> k) & 1;
-      if (pc != d - c)
-        continue;
-      Q2RowGroup& rg = p.rg[p.n_rowgroups++];
-      rg.s = s;
-      rg.rows = 1;
-      for (int k = 0; k < d; ++k)
-        rg.rows *= ((s >> k) & 1) ? g.n[k] : g.n[k] + 1;
-      rg.row_begin = sp.cg.codim_offset[c] + sp.cg.group_offset[s];
-      const int slots = ((s >> (d - 1)) & 1) ? 3 : 5;
-      const int rpi = Q2G_THREADS / slots;
-      rg.item_begin = p.n_items;
-      p.n_items += (rg.rows + rpi - 1) / rpi;
-      rg.ex = (unsigned)((s & 1) ? g.n[0] : g.n[0] + 1);
-      rg.ey = d == 3 ? (unsigned)((s & 2) ? g.n[1] : g.n[1] + 1) : 1u;
-      rg.mex = rg.ex > 1 ? ~0ULL / rg.ex + 1 : 0;
-      rg.mey = rg.ey > 1 ? ~0ULL / rg.ey + 1 : 0;
-      rg.Tx = (unsigned)q2_axis_total(s & 1, g.n[0]);
-      rg.TxTy = (long long)rg.Tx * (d == 3 ? q2_axis_total((s >> 1) & 1, g.n[1]) : 1);
-      rg.value_begin = value_begin;
-      rg.value_count = 1;
-      for (int k = 0; k < d; ++k)
-        rg.value_count *= q2_axis_total((s >> k) & 1, g.n[k]);
-      value_begin += rg.value_count;
-    }
+  {
+    int r = 0;
+    for (int c = 0; c <= d; ++c)
+      for (int s = 0; s < (1 << d); ++s) {
+        int pc = 0;
+        for (int k = 0; k < d; ++k)
+          pc += (s >> k) & 1;
+        if (pc != d - c)
+          continue;
+        Q2RowGroup& rg = p.rg[r];
+        rg.s = s;
+        rg.rows = 1;
+        for (int k = 0; k < d; ++k)
+          rg.rows *= ((s >> k) & 1) ? g.n[k] : g.n[k] + 1;
+        rg.row_begin = sp.cg.codim_offset[c] + sp.cg.group_offset[s];
+        rg.ex = (unsigned)((s & 1) ? g.n[0] : g.n[0] + 1);
+        rg.ey = d == 3 ? (unsigned)((s & 2) ? g.n[1] : g.n[1] + 1) : 1u;
+        rg.mex = rg.ex > 1 ? ~0ULL / rg.ex + 1 : 0;
+        rg.mey = rg.ey > 1 ? ~0ULL / rg.ey + 1 : 0;
+        rg.Tx = (unsigned)q2_axis_total(s & 1, g.n[0]);
+        rg.TxTy = (long long)rg.Tx * (d == 3 ? q2_axis_total((s >> 1) & 1, g.n[1]) : 1);
+        // owned rows: whole lattice layers along the last axis
+        const long long per_layer = (long long)rg.ex * rg.ey;
+        rg.lex_begin = ranges[r].row_begin - rg.row_begin;
+        rg.lex_end = ranges[r].row_end - rg.row_begin;
+        const int SL = (s >> (d - 1)) & 1;
+        const long long layer_entries = d == 3 ? rg.TxTy : (long long)rg.Tx;
+        const long long off_begin = layer_entries * q2_axis_len(SL, (int)(rg.lex_begin / per_layer), (int)g.n[d - 1]).PL;
+        rg.off_end = off_begin + ranges[r].count;
+        rg.value_begin = ranges[r].local_offset - off_begin;
+        const int slots = SL ? 3 : 5;
+        const int rpi = Q2G_THREADS / slots;
+        rg.item_begin = p.n_items;
+        p.n_items += (rg.lex_end - rg.lex_begin + rpi - 1) / rpi;
+        ++r;
+      }
+  }
   // stage: the longest segment is rows_per_item rows of the longest row kind that uses that slot count
   // (5 slots: rows up to 5^d entries, 51 rows; 3 slots: rows up to 3 * 5^(d-1), 85 rows)
   const int seg5 = (Q2G_THREADS / 5) * max_row, seg3 = (Q2G_THREADS / 3) * (max_row / 5 * 3);

@@ -282,10 +282,11 @@ bool matop_q1_eligible(const gdtb_matop* op)
 bool matop_q2_eligible(const gdtb_matop* op)
 {
   const auto q2 = [](const SpaceDev& sp) { return sp.kind == GDTB_SPACE_CG && sp.K == 2; };
-  if (!q2(op->test) || !q2(op->ansatz) || op->grid.periodic || op->slab || (op->grid.d != 2 && op->grid.d != 3))
+  if (!q2(op->test) || !q2(op->ansatz) || op->grid.periodic || (op->grid.d != 2 && op->grid.d != 3))
     return false;
-  if (!op->pattern || op->pattern->stencil != GDTB_STENCIL_ELEMENT || !q2(op->pattern->test)
-      || !q2(op->pattern->ansatz))
+  // the kernel places every value by closed forms; a caller-provided pattern must be the element stencil they describe
+  if (op->pattern
+      && (op->pattern->stencil != GDTB_STENCIL_ELEMENT || !q2(op->pattern->test) || !q2(op->pattern->ansatz)))
     return false;
   if (!op->coupling_forms.empty() || !op->boundary_forms.empty() || op->element_forms.empty())
     return false;
@@ -326,7 +327,7 @@ int build_q2_params(const gdtb_matop* op, Q2GatherParams& p)
 {
   std::memset(&p, 0, sizeof(p));
   p.g = op->grid;
-  p.rowptr = op->pattern->d_rowptr;
+  p.rowptr = op->pattern ? op->pattern->d_rowptr : nullptr;
   for (const auto& lf : op->element_forms) {
     // 1D reference tables with the form's own Gauss rule (order logic of laplace.hh:74-79 / product.hh:89-100)
     const int m = gauss_points_for_order(form_quadrature_order(lf.form, 2, ROLE_ELEMENT));
@@ -926,9 +927,12 @@ int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* a
   if (!test || !ansatz || !out)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_create: NULL argument");
   GDTB_TRY(check_ctx(ctx));
-  if (!pattern && !(q1_space(test->dev) && q1_space(ansatz->dev) && !test->grid.periodic))
+  const auto q2_space = [](const SpaceDev& sp) { return sp.kind == GDTB_SPACE_CG && sp.K == 2 && (sp.d == 2 || sp.d == 3); };
+  const bool closed_q1 = q1_space(test->dev) && q1_space(ansatz->dev) && !test->grid.periodic;
+  const bool closed_q2 = q2_space(test->dev) && q2_space(ansatz->dev) && !test->grid.periodic;
+  if (!pattern && !closed_q1 && !closed_q2)
     return fail(GDTB_ERR_INVALID_ARGUMENT,
-                "gdtb_matop_create: a pattern is required (only the CG Q1 element stencil has a closed form)");
+                "gdtb_matop_create: a pattern is required (only the CG Q1 / Q2 element stencils have closed forms)");
   // matrix-based.hh:73-80: matrix.rows() == range_space.mapper().size(), cols == source_space.mapper().size()
   if (pattern && (pattern->rows != test->dev.size || pattern->cols != ansatz->dev.size))
     return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "pattern shape does not match the spaces (rows = test, cols = ansatz)");
@@ -950,11 +954,18 @@ int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* a
   op->value_offset = 0;
   if (pattern)
     op->nnz_local = pattern->nnz;
-  else {
+  else if (closed_q1) {
     op->nnz_local = 1;
     for (int k = 0; k < op->grid.d; ++k)
       op->nnz_local *= 3 * op->grid.n[k] + 1;
+  } else { // CG Q2 element stencil: prod_k (4 n_k + 1) lattice couplings
+    Q2SlabRange ranges[8];
+    const int nr = q2_slab_ranges(op->grid, op->test, ranges);
+    op->nnz_local = 0;
+    for (int r = 0; r < nr; ++r)
+      op->nnz_local += ranges[r].count;
   }
+  op->n_ranges = 0;
   op->row_lo = 0;
   op->row_hi = op->grid.n[op->grid.d - 1] + 1;
   op->elem_lo = 0;
@@ -1125,18 +1136,38 @@ int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end)
   const long long n_last = op->grid.n[op->grid.d - 1];
   if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
-  if (!q1_space(op->test) || !q1_space(op->ansatz))
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab-partitioned assembly is implemented for CG Q1 spaces");
+  const bool q2 = op->test.kind == GDTB_SPACE_CG && op->test.K == 2 && (op->grid.d == 2 || op->grid.d == 3)
+                  && !op->grid.periodic && std::memcmp(&op->test, &op->ansatz, sizeof(SpaceDev)) == 0;
+  if (!(q1_space(op->test) && q1_space(op->ansatz)) && !q2)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab-partitioned assembly is implemented for CG Q1 and Q2 spaces");
   if (!op->owns_values)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_set_slab must be called before lending a value buffer");
   op->grid.layer_lo = layer_begin;
   op->grid.layer_hi = layer_end;
   op->slab = true;
-  q1_slab_ranges(op->grid, layer_begin, layer_end, op->row_lo, op->row_hi, op->elem_lo, op->elem_hi);
-  op->row_begin = op->row_lo * q1_layer_rows(op->grid);
-  op->row_end = op->row_hi * q1_layer_rows(op->grid);
-  op->value_offset = q1_layer_rowptr(op->grid, op->row_lo);
-  op->nnz_local = q1_layer_rowptr(op->grid, op->row_hi) - op->value_offset;
+  if (q2) {
+    // the MCMG numbering groups the rows by sub-entity kind: a slab owns one contiguous row range per group
+    Q2SlabRange ranges[8];
+    op->n_ranges = q2_slab_ranges(op->grid, op->test, ranges);
+    op->nnz_local = 0;
+    for (int r = 0; r < op->n_ranges; ++r) {
+      op->range_row_begin[r] = ranges[r].row_begin;
+      op->range_row_end[r] = ranges[r].row_end;
+      op->range_value_offset[r] = ranges[r].value_offset;
+      op->range_count[r] = ranges[r].count;
+      op->nnz_local += ranges[r].count;
+    }
+    op->row_begin = ranges[0].row_begin;
+    op->row_end = ranges[0].row_end;
+    op->value_offset = ranges[0].value_offset;
+  } else {
+    q1_slab_ranges(op->grid, layer_begin, layer_end, op->row_lo, op->row_hi, op->elem_lo, op->elem_hi);
+    op->row_begin = op->row_lo * q1_layer_rows(op->grid);
+    op->row_end = op->row_hi * q1_layer_rows(op->grid);
+    op->value_offset = q1_layer_rowptr(op->grid, op->row_lo);
+    op->nnz_local = q1_layer_rowptr(op->grid, op->row_hi) - op->value_offset;
+    op->n_ranges = 0;
+  }
   cudaFree(op->d_values);
   op->d_values = nullptr;
   if (cudaMalloc(&op->d_values, sizeof(double) * (size_t)op->nnz_local) != cudaSuccess)
@@ -1160,6 +1191,28 @@ int gdtb_matop_local_rows(const gdtb_matop* op, int64_t* row_begin, int64_t* row
     *row_end = op->row_end;
   if (value_offset)
     *value_offset = op->value_offset;
+  return GDTB_OK;
+}
+
+int gdtb_matop_local_row_ranges(const gdtb_matop* op, int32_t max_ranges, int64_t* row_begin, int64_t* row_end,
+                                int64_t* value_offset, int64_t* value_count, int32_t* n_ranges)
+{
+  if (!op || !n_ranges)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_local_row_ranges: NULL argument");
+  const int n = op->n_ranges > 0 ? op->n_ranges : 1;
+  *n_ranges = n;
+  if (max_ranges < n)
+    return (row_begin || row_end || value_offset || value_count) ? fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_local_row_ranges: arrays too short") : GDTB_OK;
+  for (int r = 0; r < n; ++r) {
+    if (row_begin)
+      row_begin[r] = op->n_ranges > 0 ? op->range_row_begin[r] : op->row_begin;
+    if (row_end)
+      row_end[r] = op->n_ranges > 0 ? op->range_row_end[r] : op->row_end;
+    if (value_offset)
+      value_offset[r] = op->n_ranges > 0 ? op->range_value_offset[r] : op->value_offset;
+    if (value_count)
+      value_count[r] = op->n_ranges > 0 ? op->range_count[r] : op->nnz_local;
+  }
   return GDTB_OK;
 }
 
@@ -1375,9 +1428,10 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
   const bool accumulate = mode == GDTB_ASSEMBLE_ACCUMULATE;
   const bool op_fast = op && matop_q1_eligible(op);
   const bool fun_fast = fun && vecfun_q1_eligible(fun);
-  if (op && !op_fast && (op->slab || !op->pattern))
+  const bool op_q2 = op && !op_fast && matop_q2_eligible(op);
+  if (op && !op_fast && !op_q2 && (op->slab || !op->pattern))
     return fail(GDTB_ERR_NOT_IMPLEMENTED,
-                "slab-partitioned / pattern-free operators only support forms the CG Q1 row-gather kernel covers");
+                "slab-partitioned / pattern-free operators only support forms the CG Q1 / Q2 row-gather kernels cover");
   if (fun && !fun_fast && fun->slab)
     return fail(GDTB_ERR_NOT_IMPLEMENTED,
                 "slab-partitioned functionals only support sources the CG Q1 row-gather kernel covers");
@@ -1392,7 +1446,6 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
   }
 
   // --- CG-Q2 row-gather path ---------------------------------------------------------------
-  const bool op_q2 = op && !op_fast && matop_q2_eligible(op);
   if (op_q2) {
     Q2GatherParams p;
     GDTB_TRY(build_q2_params(op, p));

@@ -166,7 +166,11 @@ struct Q2RowGroup
 {
   int s;
   long long row_begin, rows, item_begin;
-  long long value_begin, value_count; // CSR range of the group's rows (closed form, see q2_row_offset)
+  // CSR placement (closed form, see q2_row_offset): the value of row `lex` of the group lives at
+  // value_begin + q2_row_offset(lex) of the (slab-local) value buffer; [lex_begin, lex_end) are the rows to produce,
+  // off_end = q2_row_offset(lex_end)
+  long long value_begin, off_end;
+  long long lex_begin, lex_end;
   // row decode and row-start arithmetic of the group: extents, their division magics floor(2^64 / e) + 1, and the
   // per-axis entry totals Tx, Tx * Ty
   unsigned ex, ey;
@@ -193,6 +197,14 @@ struct Q2GatherParams
 };
 
 long long q2_sf_table_doubles(const GridDev& g); // doubles per group
+// Row ranges a slab of element layers [g.layer_lo, g.layer_hi) owns (owner-computes-rows: a lattice layer belongs to
+// the slab of the element layer above it, the top layer to the last slab): one contiguous range per sub-entity group
+// of the MCMG numbering, with the global CSR offset of its first value and its position in the slab-local buffer
+struct Q2SlabRange
+{
+  long long row_begin, row_end, value_offset, local_offset, count;
+};
+int q2_slab_ranges(const GridDev& g, const SpaceDev& sp, Q2SlabRange* out /* [8] */);
 int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate);
 
 // ---- DG row-gather assembly (assemble_dg_gather.cu) -----------------------------------------------

@@ -160,7 +160,7 @@ class SlabAssembly:
     The global CSR matrix is the concatenation of the ranks' value arrays in rank order (`value_offset` is the
     global position of the first local value, `row_begin/row_end` the global row range)."""
 
-    def __init__(self, space, rank, world):
+    def __init__(self, space, rank, world, with_functional=True):
         lib = capi.lib()
         g = space.grid.desc
         d = int(g.dim)
@@ -169,13 +169,22 @@ class SlabAssembly:
         self.op_h, self.fun_h = C.c_void_p(), C.c_void_p()
         ctx = space.grid.ctx
         capi.check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(self.op_h)))
-        capi.check(lib.gdtb_vecfun_create(ctx._h, space._h, C.byref(self.fun_h)))
         capi.check(lib.gdtb_matop_set_slab(self.op_h, self.begin, self.end))
-        capi.check(lib.gdtb_vecfun_set_slab(self.fun_h, self.begin, self.end))
+        if with_functional:  # the fused right-hand side exists for CG Q1 (the Q2 path assembles the matrix only)
+            capi.check(lib.gdtb_vecfun_create(ctx._h, space._h, C.byref(self.fun_h)))
+            capi.check(lib.gdtb_vecfun_set_slab(self.fun_h, self.begin, self.end))
         rb, re_, vo = C.c_int64(), C.c_int64(), C.c_int64()
         capi.check(lib.gdtb_matop_local_rows(self.op_h, C.byref(rb), C.byref(re_), C.byref(vo)))
         self.row_begin, self.row_end, self.value_offset = rb.value, re_.value, vo.value
         self.nnz_local = int(lib.gdtb_matop_local_nnz(self.op_h))
+        # CG Q2: one (row range, global value offset) per sub-entity group of the MCMG numbering; Q1: a single range
+        n = C.c_int32()
+        capi.check(lib.gdtb_matop_local_row_ranges(self.op_h, 0, None, None, None, None, C.byref(n)))
+        rbs, res, vos, cnt = (np.zeros(n.value, dtype=np.int64) for _ in range(4))
+        i64p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))  # noqa: E731
+        capi.check(lib.gdtb_matop_local_row_ranges(self.op_h, n.value, i64p(rbs), i64p(res), i64p(vos), i64p(cnt), C.byref(n)))
+        # (global row begin, global row end, global CSR offset of the first value, number of values) per range
+        self.row_ranges = [tuple(int(x) for x in t) for t in zip(rbs, res, vos, cnt)]
 
     def append(self, form):
         capi.check(capi.lib().gdtb_matop_append_element(self.op_h, C.byref(form)))
@@ -185,11 +194,26 @@ class SlabAssembly:
 
     def assemble(self):
         values = np.empty(self.nnz_local)
+        if not self.fun_h.value:
+            capi.check(capi.lib().gdtb_assemble_host(self.op_h, None, capi.dptr(values), None))
+            return values, None
         vector = np.empty(self.row_end - self.row_begin)
         capi.check(capi.lib().gdtb_assemble_host(self.op_h, self.fun_h, capi.dptr(values), capi.dptr(vector)))
         return values, vector
 
+    def assemble_device(self):
+        """enqueue the assembly on the context's stream (values stay on the device)"""
+        capi.check(capi.lib().gdtb_assemble_async(self.op_h, self.fun_h if self.fun_h.value else None, D.ASSEMBLE_OVERWRITE))
+
+    def scatter_into_global(self, values_local, values_global):
+        """place this rank's value segments (stored back to back) at their global CSR positions"""
+        at = 0
+        for _, _, offset, count in self.row_ranges:
+            values_global[offset:offset + count] = values_local[at:at + count]
+            at += count
+
     def __del__(self):
         if getattr(self, "op_h", None) and self.op_h.value:
             capi.lib().gdtb_matop_destroy(self.op_h)
-            capi.lib().gdtb_vecfun_destroy(self.fun_h)
+            if self.fun_h.value:
+                capi.lib().gdtb_vecfun_destroy(self.fun_h)

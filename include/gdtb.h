@@ -391,6 +391,12 @@ int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end);
 int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end);
 int64_t gdtb_matop_local_nnz(const gdtb_matop* op);
 int gdtb_matop_local_rows(const gdtb_matop* op, int64_t* row_begin, int64_t* row_end, int64_t* value_offset);
+/* CG Q2: the MCMG-based ContinuousMapper (spaces/mapper/continuous.hh:117-150) numbers DoFs [cells | faces | edges |
+ * vertices], each group lexicographically, so a slab owns one contiguous global row range PER GROUP (2^dim ranges);
+ * the local value buffer holds the ranges back to back, value_offset[r] is the global CSR position of range r's first
+ * value, value_count[r] its number of values.  CG Q1 operators report their single range.  Call with max_ranges = 0 and NULL arrays to query *n_ranges. */
+int gdtb_matop_local_row_ranges(const gdtb_matop* op, int32_t max_ranges, int64_t* row_begin, int64_t* row_end,
+                                int64_t* value_offset, int64_t* value_count, int32_t* n_ranges);
 
 
 /* ==== callers on either side of the hot path (n1, n2, n4) ====================== */

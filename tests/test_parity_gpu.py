@@ -489,3 +489,70 @@ def test_slab_owner_computes_rows(gdt, ctx, oracle, n, cuts):
         lib.gdtb_vecfun_destroy(fun_h)
     assert not np.isnan(got_v).any() and not np.isnan(got_b).any()
     assert rel_err(got_v, ref_v) <= TOL and rel_err(got_b, ref_b) <= TOL
+
+
+@pytest.mark.parametrize("n,cuts", [([4, 3, 6], [0, 2, 6]), ([3, 4, 7], [0, 1, 3, 7]), ([5, 6], [0, 2, 6]), ([3, 2, 4], [0, 1, 2, 3, 4])])
+def test_slab_owner_computes_rows_q2(gdt, ctx, oracle, n, cuts):
+    """CG Q2 (BASELINE config 5 is sharded across the GPUs): the MCMG numbering groups DoFs by sub-entity kind, so a
+    slab owns one contiguous row range per group; every owned row is complete without communication, the ranges of
+    all slabs tile the global rows / CSR values exactly once and reproduce the global matrix (pattern-free operator:
+    every CSR position is a closed form)"""
+    from dune_gdt_b200 import parallel
+
+    gdesc = D.grid_desc(-1.0, 1.0, n)
+    forms = [laplace(0.75), mass(0.5)]
+    rp, ci = oracle.pattern(gdesc, (CG, 2))
+    ref_v, _ = oracle.assemble(gdesc, CG, 2, rp, ci, forms)
+    space = make_space(gdt, ctx, gdesc, CG, 2)
+    got_v = np.full_like(ref_v, np.nan)
+    rows_seen = np.zeros(rp.size - 1, dtype=int)
+    world = len(cuts) - 1
+    for rank in range(world):
+        sa = parallel.SlabAssembly(space, rank, world, with_functional=False)
+        # SlabAssembly cuts evenly; re-cut to the requested layers
+        gdt.capi.check(gdt.capi.lib().gdtb_matop_set_slab(sa.op_h, cuts[rank], cuts[rank + 1]))
+        sa = _refresh_ranges(gdt, sa)
+        for f in forms:
+            sa.append(f)
+        values, _ = sa.assemble()
+        assert len(sa.row_ranges) == 2 ** len(n)
+        at = 0
+        for rb, re_, vo, cnt in sa.row_ranges:
+            assert vo == rp[rb] and cnt == rp[re_] - rp[rb]  # closed-form CSR offsets == the pattern builder's
+            rows_seen[rb:re_] += 1
+            assert np.isnan(got_v[vo:vo + cnt]).all()
+            got_v[vo:vo + cnt] = values[at:at + cnt]
+            at += cnt
+        assert at == values.size
+    assert (rows_seen == 1).all() and not np.isnan(got_v).any()
+    assert rel_err(got_v, ref_v) <= TOL
+
+
+def _refresh_ranges(gdt, sa):
+    lib = gdt.capi.lib()
+    n = C.c_int32()
+    gdt.capi.check(lib.gdtb_matop_local_row_ranges(sa.op_h, 0, None, None, None, None, C.byref(n)))
+    arrs = [np.zeros(n.value, dtype=np.int64) for _ in range(4)]
+    ptr = [a.ctypes.data_as(C.POINTER(C.c_int64)) for a in arrs]
+    gdt.capi.check(lib.gdtb_matop_local_row_ranges(sa.op_h, n.value, *ptr, C.byref(n)))
+    sa.row_ranges = [tuple(int(x) for x in t) for t in zip(*arrs)]
+    sa.nnz_local = int(lib.gdtb_matop_local_nnz(sa.op_h))
+    return sa
+
+
+def test_q2_pattern_free_operator_matches_pattern_based(gdt, ctx, oracle):
+    gdesc = D.grid_desc(0.0, 1.0, [3, 4, 2])
+    space = make_space(gdt, ctx, gdesc, CG, 2)
+    lib, check = gdt.capi.lib(), gdt.capi.check
+    op_h = C.c_void_p()
+    check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(op_h)))
+    f = laplace(1.0)
+    check(lib.gdtb_matop_append_element(op_h, C.byref(f)))
+    check(lib.gdtb_assemble(op_h, None, D.ASSEMBLE_OVERWRITE))
+    rp, ci = oracle.pattern(gdesc, (CG, 2))
+    assert lib.gdtb_matop_local_nnz(op_h) == ci.size
+    v = np.empty(ci.size)
+    check(lib.gdtb_matop_values_download(op_h, gdt.capi.dptr(v)))
+    ref_v, _ = oracle.assemble(gdesc, CG, 2, rp, ci, [f])
+    assert rel_err(v, ref_v) <= TOL
+    lib.gdtb_matop_destroy(op_h)
