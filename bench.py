@@ -196,6 +196,68 @@ def fv_extra(gdt, ctx, torch, hbm_gbs, peak_src):
     return out
 
 
+def assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src):
+    """C3 (2D SWIPDG DG-Q1 2048^2: element + inner-coupling + boundary forms) and C5 (3D Q2 Laplace 128^3) on one GPU:
+    device-resident ms per assembly and the HBM roofline of the row-gather kernel (8 nnz + 8 ndof algorithmic bytes,
+    SURVEY.md 8d).  Reported alongside the headline; the parity tests cover both paths."""
+    from dune_gdt_b200 import descriptors as D
+
+    lib, check = gdt.capi.lib(), gdt.capi.check
+    out = {}
+
+    def timed(op_h, family, reps):
+        for _ in range(3):
+            check(lib.gdtb_assemble_async(op_h, None, D.ASSEMBLE_OVERWRITE))
+        ctx.synchronize()
+        kernel_time(gdt, ctx, family)
+        for _ in range(reps):
+            check(lib.gdtb_assemble_async(op_h, None, D.ASSEMBLE_OVERWRITE))
+        ctx.synchronize()
+        ms, cnt = kernel_time(gdt, ctx, family)
+        return ms / max(cnt, 1)
+
+    def entry(name, elements, rows, nnz, per_ms, plan):
+        alg = 8.0 * nnz + 8.0 * rows
+        ach = alg / (per_ms * 1e-3) / 1e9
+        out[name] = {"plan": plan, "elements": elements, "rows": rows, "nnz": nnz, "ms_per_assembly": per_ms,
+                     "elements_per_s": elements / (per_ms * 1e-3),
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs,
+                                  "algorithmic_bytes_per_launch": alg, "bytes_per_element": alg / elements,
+                                  "peak_source": peak_src}}
+
+    # C5: pattern-free CG Q2 operator (every CSR position is a closed form)
+    n = 128
+    grid = gdt.make_cube_grid(ctx, -1.0, 1.0, [n, n, n])
+    space = gdt.make_continuous_lagrange_space(grid, 2)
+    op_h = C.c_void_p()
+    check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(op_h)))
+    lap = D.form(D.integrand(D.INT_LAPLACE, diffusion=1.0))
+    check(lib.gdtb_matop_append_element(op_h, C.byref(lap)))
+    per = timed(op_h, "q2_gather", 20)
+    entry("c5_q2_laplace_128^3", n**3, space.mapper.size, int(lib.gdtb_matop_local_nnz(op_h)), per,
+          lib.gdtb_matop_plan(op_h).decode())
+    lib.gdtb_matop_destroy(op_h)
+    del space, grid
+    torch.cuda.empty_cache()
+
+    # C3: SWIPDG as in examples/adaptive_elliptic_swipdg.cc:230-251 / test ESV2007.hh:108-112 on a Yasp grid
+    n = 2048
+    grid = gdt.make_cube_grid(ctx, -1.0, 1.0, [n, n])
+    space = gdt.make_discontinuous_lagrange_space(grid, 1)
+    pat = gdt.make_sparsity_pattern(space, space, gdt.Stencil.element_and_intersection)
+    op = gdt.MatrixOperator(space, space, pat)
+    inner = D.form([D.integrand(D.INT_IPDG_INNER_COUPLING, prefactor=1.0, diffusion=1.0, weight=1.0),
+                    D.integrand(D.INT_IPDG_INNER_PENALTY, prefactor=8.0, weight=1.0, hI_kind=D.HI_VOLUME)])
+    bnd = D.form([D.integrand(D.INT_IPDG_DIRICHLET_COUPLING, prefactor=1.0, diffusion=1.0),
+                  D.integrand(D.INT_IPDG_BOUNDARY_PENALTY, prefactor=14.0, weight=1.0, hI_kind=D.HI_VOLUME)])
+    check(lib.gdtb_matop_append_element(op._h, C.byref(lap)))
+    check(lib.gdtb_matop_append_coupling(op._h, C.byref(inner), D.FILTER_INNER_ONCE))
+    check(lib.gdtb_matop_append_boundary(op._h, C.byref(bnd), D.FILTER_ALL_BOUNDARY))
+    per = timed(op._h, "dg_gather", 20)
+    entry("c3_swipdg_dg_q1_2048^2", n * n, pat.rows, pat.nnz, per, op.plan)
+    return out
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -337,6 +399,12 @@ def run_product(args):
     if rank == 0 and world == 1:
         check(lib.gdtb_ctx_enable_timing(ctx._h, 1))
         extra = {"fv_apply_4096x4096_upwind": fv_extra(gdt, ctx, torch, hbm_gbs, peak_src)}
+        del values_host, rhs_host
+        lib.gdtb_matop_destroy(op_h)
+        lib.gdtb_vecfun_destroy(fun_h)
+        op_h = fun_h = None
+        torch.cuda.empty_cache()
+        extra.update(assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src))
         check(lib.gdtb_ctx_enable_timing(ctx._h, 0))
         if not args.no_cpu_baseline:
             import oracle
@@ -349,8 +417,9 @@ def run_product(args):
                    "sample": f"{side}^3 elements of the 256^3 grid (same h and forms), best of 2 walks of {dt:.2f} s, "
                              f"oracle port with {threads} threads + row-striped locks, pattern build untimed"}
 
-    lib.gdtb_matop_destroy(op_h)
-    lib.gdtb_vecfun_destroy(fun_h)
+    if op_h is not None:
+        lib.gdtb_matop_destroy(op_h)
+        lib.gdtb_vecfun_destroy(fun_h)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

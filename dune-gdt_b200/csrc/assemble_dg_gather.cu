@@ -256,7 +256,69 @@ int launch_dg_gather_dk(Launch& L, const DgGatherParams& p, double* values, bool
 struct DgFastTab
 {
   double M1[2][2], K1[2][2], pe[2][2], de[2][2];
+  // all coefficients constant (CC kernels): the 2 x 2 face matrices of the form's terms are affine in the cell data
+  //   mult = {1 / h_k(inside), 1 / h_k(outside), 1 / |I|, 1 / diam(I)}
+  // fa / fb[s][i_k][j_k][m]: columns of the inside / outside element for a row of the inside (s = 1) or outside
+  // (s = 0) element; boundary forms: fa[s] for the face with outer normal -+e_k, mult[0] = 1 / h_k.  F.scaling included.
+  double fa[2][2][2][4], fb[2][2][2][4];
+  double elap, emass; // element forms: sum of scaling * kappa over the Laplace terms / scaling * w over the products
 };
+
+// the CC tables of one form (role: 0 element, 1 coupling, 2 boundary); one thread
+__device__ inline void dg_fast_tables_cc(const FormDev& F, int role, DgFastTab& T)
+{
+  for (int s = 0; s < 2; ++s)
+    for (int ik = 0; ik < 2; ++ik)
+      for (int jk = 0; jk < 2; ++jk)
+        for (int m = 0; m < 4; ++m)
+          T.fa[s][ik][jk][m] = T.fb[s][ik][jk][m] = 0.;
+  T.elap = T.emass = 0.;
+  for (int tt = 0; tt < F.n_terms; ++tt) {
+    const IntegrandDev& in = F.terms[tt];
+    const double sc = F.scaling;
+    if (role == 0) {
+      if (in.kind == GDTB_INT_LAPLACE)
+        T.elap += sc * in.diffusion.c[0];
+      else
+        T.emass += sc * in.diffusion.c[0];
+      continue;
+    }
+    const int slot = in.hI_kind == GDTB_HI_VOLUME ? 2 : 3;
+    for (int ik = 0; ik < 2; ++ik)
+      for (int jk = 0; jk < 2; ++jk) {
+        if (role == 1) {
+          const double dp = in.weight.c[0], dm = in.weight.c[0]; // delta_plus, delta_minus
+          if (in.kind == GDTB_INT_IPDG_INNER_COUPLING) {
+            const double c = in.diffusion.c[0], sp_ = in.prefactor;
+            const double wm = dp / (dp + dm), wp = dm / (dp + dm);
+            // s = 1: row of the inside element (laplace-ipdg.hh:158-170)
+            T.fa[1][ik][jk][0] += sc * (-1.0 * wm * c * (T.de[1][jk] * T.pe[1][ik] + sp_ * T.pe[1][jk] * T.de[1][ik]));
+            T.fb[1][ik][jk][1] += sc * (-1.0 * wp * c * T.de[0][jk] * T.pe[1][ik]);
+            T.fb[1][ik][jk][0] += sc * (sp_ * wm * c * T.pe[0][jk] * T.de[1][ik]);
+            // s = 0: row of the outside element (laplace-ipdg.hh:172-185)
+            T.fa[0][ik][jk][0] += sc * (wm * c * T.de[1][jk] * T.pe[0][ik]);
+            T.fa[0][ik][jk][1] += sc * (-1.0 * sp_ * wp * c * T.pe[1][jk] * T.de[0][ik]);
+            T.fb[0][ik][jk][1] += sc * (wp * c * (T.de[0][jk] * T.pe[0][ik] + sp_ * T.pe[0][jk] * T.de[0][ik]));
+          } else { // inner penalty (ipdg.hh:149-170): sigma (delta+ delta- / (delta+ + delta-)) / h
+            const double pw = sc * in.prefactor * ((dp * dm) / (dp + dm));
+            T.fa[1][ik][jk][slot] += pw * T.pe[1][jk] * T.pe[1][ik];
+            T.fb[1][ik][jk][slot] += -1.0 * pw * T.pe[0][jk] * T.pe[1][ik];
+            T.fa[0][ik][jk][slot] += -1.0 * pw * T.pe[1][jk] * T.pe[0][ik];
+            T.fb[0][ik][jk][slot] += pw * T.pe[0][jk] * T.pe[0][ik];
+          }
+        } else {
+          for (int s = 0; s < 2; ++s) {
+            const double sg = s ? 1. : -1.;
+            if (in.kind == GDTB_INT_IPDG_DIRICHLET_COUPLING) // laplace-ipdg.hh:362-367
+              T.fa[s][ik][jk][0] += sc * (-1.0 * in.diffusion.c[0] * sg
+                                          * (T.de[s][jk] * T.pe[s][ik] + in.prefactor * T.pe[s][jk] * T.de[s][ik]));
+            else // boundary penalty (ipdg.hh:276-281): sigma (n . omega n) / h
+              T.fa[s][ik][jk][slot] += sc * in.prefactor * in.weight.c[0] * T.pe[s][jk] * T.pe[s][ik];
+          }
+        }
+      }
+  }
+}
 
 __device__ __forceinline__ double dg_coef(const FnDev& f, long long e)
 {
@@ -338,6 +400,25 @@ __device__ __forceinline__ double dg_face_h(const IntegrandDev& t, const double*
   return sqrt(d2);
 }
 
+// 1 / intersection_h for the CC tables: 1 / |I| (volume) or 1 / diameter (1D: element lengths) from the cell data
+template <int D>
+__device__ __forceinline__ double dg_inv_face(const double* h, const double* hinv, int k, double h_in, double h_out,
+                                              bool neighbor, bool volume)
+{
+  if (D == 1)
+    return volume ? 1. : (neighbor ? 1. / (0.5 * (h_in + h_out)) : 1. / h_in);
+  double inv = 1., d2 = 0.;
+#pragma unroll
+  for (int o = 0; o < D; ++o)
+    if (o != k) {
+      inv *= hinv[o];
+      d2 += h[o] * h[o];
+    }
+  if (volume || D == 2)
+    return inv; // 2D: the face is an interval, diameter == |I|
+  return 1. / sqrt(d2);
+}
+
 // block[j] += sc * c2[j_k] * prod_{o != k} tM[o][j_o]  (j = j_0 + 2 j_1 + 4 j_2)
 template <int D>
 __device__ __forceinline__ void dg_add_face_block(double* __restrict__ block, const double sc, const double* c2, int k,
@@ -355,7 +436,7 @@ __device__ __forceinline__ void dg_add_face_block(double* __restrict__ block, co
   }
 }
 
-template <int D, bool ACCUMULATE>
+template <int D, bool ACCUMULATE, bool CC>
 __global__ void __launch_bounds__(DGG_THREADS)
     k_dg_gather_fast(const __grid_constant__ DgGatherParams p, double* __restrict__ values, int stage_doubles)
 {
@@ -379,6 +460,8 @@ __global__ void __launch_bounds__(DGG_THREADS)
         t.pe[a][b] = f.phi_end[a][b];
         t.de[a][b] = f.dphi_end[a][b];
       }
+    if (CC)
+      dg_fast_tables_cc(f, (int)threadIdx.x < p.n_elem ? 0 : ((int)threadIdx.x < p.n_elem + p.n_coup ? 1 : 2), t);
   }
   __syncthreads();
   const FormDev* f_elem = p.forms;
@@ -445,9 +528,12 @@ __global__ void __launch_bounds__(DGG_THREADS)
           tK[o][0] = hinv[o] * T.K1[io][0];
           tK[o][1] = hinv[o] * T.K1[io][1];
         }
-        for (int tt = 0; tt < F.n_terms; ++tt) {
-          const double c = F.scaling * dg_coef(F.terms[tt].diffusion, e);
-          if (F.terms[tt].kind == GDTB_INT_LAPLACE) {
+        // CC: the terms of a form share its tables, their constant coefficients are summed up front (two passes)
+        for (int tt = 0; tt < (CC ? 2 : F.n_terms); ++tt) {
+          const double c = CC ? (tt == 0 ? T.elap : T.emass) : F.scaling * dg_coef(F.terms[tt].diffusion, e);
+          if (CC && c == 0.)
+            continue;
+          if (CC ? tt == 0 : F.terms[tt].kind == GDTB_INT_LAPLACE) {
 #pragma unroll
             for (int j = 0; j < N; ++j) {
               double sum = 0.;
@@ -517,6 +603,21 @@ __global__ void __launch_bounds__(DGG_THREADS)
                 tM[o][0] = h[o] * T.M1[io][0];
                 tM[o][1] = h[o] * T.M1[io][1];
               }
+              if (CC) {
+                const double mult[4] = {hinv_in, hinv_out, dg_inv_face<D>(h, hinv, k, h_in, h_out, true, true),
+                                        dg_inv_face<D>(h, hinv, k, h_in, h_out, true, false)};
+                double ca[2], cb[2];
+#pragma unroll
+                for (int jk = 0; jk < 2; ++jk) {
+                  const double* A = T.fa[s][ik][jk];
+                  const double* B = T.fb[s][ik][jk];
+                  ca[jk] = fma(A[0], mult[0], fma(A[1], mult[1], fma(A[2], mult[2], A[3] * mult[3])));
+                  cb[jk] = fma(B[0], mult[0], fma(B[1], mult[1], fma(B[2], mult[2], B[3] * mult[3])));
+                }
+                dg_add_face_block<D>(self, 1., s ? ca : cb, k, tM);
+                dg_add_face_block<D>(nbb, 1., s ? cb : ca, k, tM);
+                continue;
+              }
               // test function on its own side: inside element -> upper end (1), outside element -> lower end (0)
               const double vi = s ? T.pe[1][ik] : T.pe[0][ik];
               const double gi = s ? T.de[1][ik] * hinv_in : T.de[0][ik] * hinv_out;
@@ -582,6 +683,18 @@ __global__ void __launch_bounds__(DGG_THREADS)
                 tM[o][0] = h[o] * T.M1[io][0];
                 tM[o][1] = h[o] * T.M1[io][1];
               }
+              if (CC) {
+                const double mult[4] = {hinv[k], 0., dg_inv_face<D>(h, hinv, k, h[k], h[k], false, true),
+                                        dg_inv_face<D>(h, hinv, k, h[k], h[k], false, false)};
+                double cc2[2];
+#pragma unroll
+                for (int jk = 0; jk < 2; ++jk) {
+                  const double* A = T.fa[s][ik][jk];
+                  cc2[jk] = fma(A[0], mult[0], fma(A[2], mult[2], A[3] * mult[3]));
+                }
+                dg_add_face_block<D>(self, 1., cc2, k, tM);
+                continue;
+              }
               const double vi = T.pe[s][ik], gi = sg * (T.de[s][ik] * hinv[k]);
               double ca[2] = {0., 0.};
               for (int tt = 0; tt < F.n_terms; ++tt) {
@@ -643,12 +756,14 @@ __global__ void __launch_bounds__(DGG_THREADS)
 template <int D>
 int launch_dg_gather_fast(Launch& L, DgGatherParams& p, double* values, bool accumulate)
 {
+  const bool cc = p.fast == 2;
   constexpr int N = 1 << D;
   for (int k = 0; k < 2; ++k)
     p.magic[k] = p.g.n[k] > 1 ? ~0ULL / (unsigned long long)p.g.n[k] + 1 : 0;
   const int stage_doubles = ((DGG_THREADS * N * (2 * D + 1) + 2) + 1) & ~1;
   const size_t smem = (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double);
-  auto kern = accumulate ? k_dg_gather_fast<D, true> : k_dg_gather_fast<D, false>;
+  auto kern = accumulate ? (cc ? k_dg_gather_fast<D, true, true> : k_dg_gather_fast<D, true, false>)
+                         : (cc ? k_dg_gather_fast<D, false, true> : k_dg_gather_fast<D, false, false>);
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;

@@ -1514,7 +1514,12 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     for (const FormDev& f : forms)
       for (int t = 0; t < f.n_terms; ++t)
         fast = fast && scalar(f.terms[t].diffusion) && scalar(f.terms[t].weight);
-    p.fast = fast ? 1 : 0;
+    // ... and the cheaper variant when every coefficient is a constant (face matrices tabulated once per launch)
+    bool all_const = true;
+    for (const FormDev& f : forms)
+      for (int t = 0; t < f.n_terms; ++t)
+        all_const = all_const && f.terms[t].diffusion.kind == GDTB_FN_CONST_SCALAR && f.terms[t].weight.kind == GDTB_FN_CONST_SCALAR;
+    p.fast = fast ? ((all_const && !std::getenv("GDTB_DG_NO_CC")) ? 2 : 1) : 0;
     GDTB_TRY(launch_dg_gather(L, p, op->d_values, accumulate));
   }
 

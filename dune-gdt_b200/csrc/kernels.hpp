@@ -220,7 +220,7 @@ struct DgGatherParams
   const long long* rowptr; // device CSR row pointer of the element_and_intersection pattern
   // factorised path (order 1, every coefficient a constant or element-wise scalar): the quadrature sums of all forms
   // collapse into 1D tables; row starts are closed forms (rowptr is not read)
-  int fast;
+  int fast; // 0: quadrature-faithful kernel, 1: factorised, 2: factorised with constant coefficients tabulated
   unsigned long long magic[2]; // floor(2^64 / n_k) + 1 for the element-index decode (0 when n_k == 1)
 };
 

@@ -300,8 +300,28 @@ def swipdg_cases():
             ("tensor-kappa", n, 1, swipdg(kappa=D.fn_const(kt), omega=D.fn_const(kt))),
             ("builtin-kappa", n, 1, swipdg(kappa=D.fn_builtin(D.BUILTIN_QUADRATIC, 2, 1.0, 0.5))),
             ("q2", n, 2, swipdg()),
+            ("const-kappa3-omega2-scaled-mixed-hI", n, 1, _swipdg_mixed(3.0, 2.0)),
+            ("elem-kappa-scaled-mixed-hI", n, 1, _swipdg_mixed(D.fn_elem(rng_elem(n)), D.fn_elem(rng_elem(n, seed=5)))),
         ]
     return out
+
+
+def _swipdg_mixed(kappa, omega):
+    """scaled forms, an extra mass term in the element form, both intersection-diameter conventions in one form and a
+    sum of a symmetric and a non-symmetric coupling: exercises every accumulation of the factorised DG kernels"""
+    element = D.form([D.integrand(D.INT_LAPLACE, diffusion=kappa), D.integrand(D.INT_PRODUCT, diffusion=0.5)], scaling=1.5)
+    coupling = D.form([
+        D.integrand(D.INT_IPDG_INNER_COUPLING, diffusion=kappa, weight=omega, prefactor=1.0),
+        D.integrand(D.INT_IPDG_INNER_PENALTY, weight=omega, prefactor=8.0, hI_kind=D.HI_VOLUME),
+        D.integrand(D.INT_IPDG_INNER_PENALTY, weight=omega, prefactor=3.0, hI_kind=D.HI_DIAMETER),
+        D.integrand(D.INT_IPDG_INNER_COUPLING, diffusion=kappa, weight=omega, prefactor=-1.0),
+    ], scaling=0.75)
+    boundary = D.form([
+        D.integrand(D.INT_IPDG_BOUNDARY_PENALTY, weight=omega, prefactor=14.0, hI_kind=D.HI_DIAMETER),
+        D.integrand(D.INT_IPDG_DIRICHLET_COUPLING, diffusion=kappa, prefactor=1.0),
+        D.integrand(D.INT_IPDG_BOUNDARY_PENALTY, weight=omega, prefactor=2.0, hI_kind=D.HI_VOLUME),
+    ], scaling=2.0)
+    return element, coupling, boundary
 
 
 @pytest.mark.parametrize("name,n,order,forms", swipdg_cases(), ids=lambda v: v if isinstance(v, str) else None)
