@@ -1128,7 +1128,68 @@ int gdtb_matop_set_values_device(gdtb_matop* op, double* d_values)
   return GDTB_OK;
 }
 
+// interface-row halo partition: rows of the vertex layers [begin, end] (the top one is the interface layer owned by
+// the slab above) from the slab's OWN element layers [begin, end) only
+static void q1_halo_ranges(const GridDev& g, long long begin, long long end, long long& row_lo, long long& row_hi,
+                           long long& elem_lo, long long& elem_hi)
+{
+  row_lo = begin;
+  row_hi = end + 1;
+  elem_lo = begin;
+  elem_hi = end;
+  (void)g;
+}
+
+static int matop_set_slab_impl(gdtb_matop* op, int64_t layer_begin, int64_t layer_end, bool halo);
+
 int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end)
+{
+  return matop_set_slab_impl(op, layer_begin, layer_end, false);
+}
+
+int gdtb_matop_set_slab_halo(gdtb_matop* op, int64_t layer_begin, int64_t layer_end)
+{
+  if (op && !(q1_space(op->test) && q1_space(op->ansatz)))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "the interface-row halo partition is implemented for CG Q1 spaces");
+  return matop_set_slab_impl(op, layer_begin, layer_end, true);
+}
+
+int gdtb_matop_halo_layout(const gdtb_matop* op, int64_t* recv_offset, int64_t* send_offset, int64_t* count)
+{
+  if (!op || !op->slab || !op->halo)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_halo_layout: the operator is not in interface-row halo mode");
+  // one vertex layer of rows: the first local layer receives the partial sums of the slab below, the last local layer
+  // (the interface owned by the slab above) is sent up; interface layers are interior along the last direction, so
+  // both have the same CSR shape
+  const long long layer = q1_layer_rowptr(op->grid, op->row_lo + 1) - q1_layer_rowptr(op->grid, op->row_lo);
+  const long long n_last = op->grid.n[op->grid.d - 1];
+  const bool has_lower = op->grid.layer_lo > 0, has_upper = op->grid.layer_hi < n_last;
+  const long long interior = has_lower ? layer : (has_upper ? q1_layer_rowptr(op->grid, op->row_hi) - q1_layer_rowptr(op->grid, op->row_hi - 1) : 0);
+  if (recv_offset)
+    *recv_offset = has_lower ? 0 : -1;
+  if (send_offset)
+    *send_offset = has_upper ? op->nnz_local - (q1_layer_rowptr(op->grid, op->row_hi) - q1_layer_rowptr(op->grid, op->row_hi - 1)) : -1;
+  if (count)
+    *count = interior;
+  return GDTB_OK;
+}
+
+int gdtb_vecfun_set_slab_halo(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end);
+
+int gdtb_vector_add(gdtb_ctx* ctx, double* d_y, const double* d_x, int64_t n)
+{
+  if (!d_y || !d_x || n < 0)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vector_add: invalid argument");
+  GDTB_TRY(check_ctx(ctx));
+  RkAxpyParams q;
+  q.n = n;
+  q.nv = 1;
+  q.v[0] = d_x;
+  q.c[0] = 1.;
+  return launch_rk_axpy(ctx->launch, q, d_y, d_y);
+}
+
+static int matop_set_slab_impl(gdtb_matop* op, int64_t layer_begin, int64_t layer_end, bool halo)
 {
   if (!op)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
@@ -1161,7 +1222,11 @@ int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end)
     op->row_end = ranges[0].row_end;
     op->value_offset = ranges[0].value_offset;
   } else {
-    q1_slab_ranges(op->grid, layer_begin, layer_end, op->row_lo, op->row_hi, op->elem_lo, op->elem_hi);
+    if (halo)
+      q1_halo_ranges(op->grid, layer_begin, layer_end, op->row_lo, op->row_hi, op->elem_lo, op->elem_hi);
+    else
+      q1_slab_ranges(op->grid, layer_begin, layer_end, op->row_lo, op->row_hi, op->elem_lo, op->elem_hi);
+    op->halo = halo;
     op->row_begin = op->row_lo * q1_layer_rows(op->grid);
     op->row_end = op->row_hi * q1_layer_rows(op->grid);
     op->value_offset = q1_layer_rowptr(op->grid, op->row_lo);
@@ -1324,7 +1389,35 @@ int gdtb_vecfun_set_device(gdtb_vecfun* fun, double* d_vector)
   return GDTB_OK;
 }
 
+static int vecfun_set_slab_impl(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end, bool halo);
+
 int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end)
+{
+  return vecfun_set_slab_impl(fun, layer_begin, layer_end, false);
+}
+
+int gdtb_vecfun_set_slab_halo(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end)
+{
+  return vecfun_set_slab_impl(fun, layer_begin, layer_end, true);
+}
+
+int gdtb_vecfun_halo_layout(const gdtb_vecfun* fun, int64_t* recv_offset, int64_t* send_offset, int64_t* count)
+{
+  if (!fun || !fun->slab || !fun->halo)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_halo_layout: the functional is not in interface-row halo mode");
+  const long long layer = q1_layer_rows(fun->grid);
+  const long long n_last = fun->grid.n[fun->grid.d - 1];
+  const bool has_lower = fun->grid.layer_lo > 0, has_upper = fun->grid.layer_hi < n_last;
+  if (recv_offset)
+    *recv_offset = has_lower ? 0 : -1;
+  if (send_offset)
+    *send_offset = has_upper ? (fun->row_end - fun->row_begin) - layer : -1;
+  if (count)
+    *count = (has_lower || has_upper) ? layer : 0;
+  return GDTB_OK;
+}
+
+static int vecfun_set_slab_impl(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end, bool halo)
 {
   if (!fun)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "functional is NULL");
@@ -1339,7 +1432,11 @@ int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_en
   fun->grid.layer_lo = layer_begin;
   fun->grid.layer_hi = layer_end;
   fun->slab = true;
-  q1_slab_ranges(fun->grid, layer_begin, layer_end, fun->row_lo, fun->row_hi, fun->elem_lo, fun->elem_hi);
+  if (halo)
+    q1_halo_ranges(fun->grid, layer_begin, layer_end, fun->row_lo, fun->row_hi, fun->elem_lo, fun->elem_hi);
+  else
+    q1_slab_ranges(fun->grid, layer_begin, layer_end, fun->row_lo, fun->row_hi, fun->elem_lo, fun->elem_hi);
+  fun->halo = halo;
   fun->row_begin = fun->row_lo * q1_layer_rows(fun->grid);
   fun->row_end = fun->row_hi * q1_layer_rows(fun->grid);
   cudaFree(fun->d_vec);

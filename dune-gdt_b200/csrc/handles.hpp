@@ -96,6 +96,7 @@ struct gdtb_matop
   long long row_begin, row_end;   // global row range held by this process
   long long value_offset, nnz_local;
   long long row_lo, row_hi, elem_lo, elem_hi; // vertex / element layers along the last direction
+  bool halo = false; // interface-row halo partition: rows of one extra (interface) layer, own elements only
   // CG Q2 slabs: one row range per sub-entity group of the MCMG numbering (d_values holds them back to back)
   int n_ranges = 0;
   long long range_row_begin[8], range_row_end[8], range_value_offset[8], range_count[8];
@@ -116,6 +117,7 @@ struct gdtb_vecfun
   long long row_lo, row_hi, elem_lo, elem_hi;
   double h_rule[4 * MAX_Q1D];
   bool rule_uploaded;
+  bool halo = false;
 };
 
 struct gdtb_fvop

@@ -7,8 +7,10 @@ YaspGrid).  Here the grid is cut into slabs of element layers along the LAST dir
 travels to the neighbours' ghost layers (periodic wrap: rank 0 <-> rank N-1) with grouped point-to-point messages
 (`torch.distributed` P2P: NCCL send/recv over NVLink on GPUs, gloo on CPU for the host-logic tests).
 
-Assembly needs no exchange: rows are owned by the slab that owns the vertex layer, and the one element layer below a
-slab is recomputed locally (what the reference does with YaspGrid's overlap) -- see `slab_layers` / `gdtb_matop_set_slab`.
+Assembly has two partitions.  `SlabAssembly`: rows are owned by the slab that owns the vertex layer and
+the one element layer below a slab is recomputed locally (what the reference does with YaspGrid's overlap): no exchange.
+`HaloSlabAssembly`: every rank walks only its own elements, the partial sums of the interface rows (one vertex layer of
+CSR values + right-hand-side entries per slab face) travel to the owner with NCCL send / recv and are added there.
 """
 import ctypes as C
 
@@ -217,3 +219,122 @@ class SlabAssembly:
             capi.lib().gdtb_matop_destroy(self.op_h)
             if self.fun_h.value:
                 capi.lib().gdtb_vecfun_destroy(self.fun_h)
+
+
+def exchange_interface_rows(local, recv_offset, send_offset, count, rank, world, add=None, group=None):
+    """interface-row halo of the element-partitioned assembly: the last `count` entries at `send_offset` of `local`
+    (the partial sums of the interface layer owned by rank + 1) are sent up, the layer arriving from rank - 1 is added
+    to the `count` entries at `recv_offset`.  `local` is a 1D torch tensor (CUDA for NCCL, CPU for gloo); `add(y, x)`
+    performs y += x (default: torch).  Returns the received buffer (None on rank 0)."""
+    import torch
+    import torch.distributed as dist
+
+    ops, recv = [], None
+    if send_offset >= 0 and rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, local[send_offset:send_offset + count], rank + 1, group))
+    if recv_offset >= 0 and rank > 0:
+        recv = torch.empty(count, dtype=local.dtype, device=local.device)
+        ops.append(dist.P2POp(dist.irecv, recv, rank - 1, group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    if local.is_cuda:
+        # NCCL completion is stream-ordered on torch's stream; the add may run on the library's stream
+        torch.cuda.current_stream(local.device).synchronize()
+    if recv is not None:
+        target = local[recv_offset:recv_offset + count]
+        if add is None:
+            target += recv
+        else:
+            add(target, recv)
+    return recv
+
+
+class HaloSlabAssembly:
+    """Element-partitioned assembly with an interface-row halo (CG Q1): each rank walks its own element layers only;
+    the rows of the interface layer it shares with the rank above are partial and are completed on their owner by
+    one NCCL message per slab face.  After `assemble_device()` the owned rows of this rank are the first
+    `nnz_owned` values / `rows_owned` vector entries of the device buffers (same layout as `SlabAssembly`)."""
+
+    def __init__(self, space, rank, world, group=None):
+        lib = capi.lib()
+        g = space.grid.desc
+        d = int(g.dim)
+        self.rank, self.world, self.group = rank, world, group
+        self.begin, self.end = slab_layers(int(g.n[d - 1]), rank, world)
+        self.space = space
+        self.op_h, self.fun_h = C.c_void_p(), C.c_void_p()
+        ctx = space.grid.ctx
+        self.ctx = ctx
+        capi.check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(self.op_h)))
+        capi.check(lib.gdtb_vecfun_create(ctx._h, space._h, C.byref(self.fun_h)))
+        capi.check(lib.gdtb_matop_set_slab_halo(self.op_h, self.begin, self.end))
+        capi.check(lib.gdtb_vecfun_set_slab_halo(self.fun_h, self.begin, self.end))
+        rb, re_, vo = C.c_int64(), C.c_int64(), C.c_int64()
+        capi.check(lib.gdtb_matop_local_rows(self.op_h, C.byref(rb), C.byref(re_), C.byref(vo)))
+        self.row_begin, self.value_offset = rb.value, vo.value
+        self.nnz_local = int(lib.gdtb_matop_local_nnz(self.op_h))
+        self.rows_local = re_.value - rb.value
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        capi.check(lib.gdtb_matop_halo_layout(self.op_h, C.byref(a), C.byref(b), C.byref(c)))
+        self.mat_layout = (a.value, b.value, c.value)
+        capi.check(lib.gdtb_vecfun_halo_layout(self.fun_h, C.byref(a), C.byref(b), C.byref(c)))
+        self.vec_layout = (a.value, b.value, c.value)
+        # the interface layer at the top belongs to the rank above: not part of the owned rows
+        top = rank < world - 1
+        self.nnz_owned = self.nnz_local - (self.mat_layout[2] if top else 0)
+        self.rows_owned = self.rows_local - (self.vec_layout[2] if top else 0)
+
+    def append(self, form):
+        capi.check(capi.lib().gdtb_matop_append_element(self.op_h, C.byref(form)))
+
+    def append_rhs(self, form):
+        capi.check(capi.lib().gdtb_vecfun_append_element(self.fun_h, C.byref(form)))
+
+    def _device_views(self):
+        import torch
+
+        lib = capi.lib()
+        pv, pb = C.c_void_p(), C.c_void_p()
+        capi.check(lib.gdtb_matop_values_device(self.op_h, C.byref(pv)))
+        capi.check(lib.gdtb_vecfun_device(self.fun_h, C.byref(pb)))
+        dev = torch.device("cuda", self.ctx.device)
+        values = _as_tensor(pv.value, self.nnz_local, dev)
+        vector = _as_tensor(pb.value, self.rows_local, dev)
+        return values, vector
+
+    def assemble_device(self):
+        """one walk over the own elements + the interface-row exchange; returns (values, vector) device tensors that
+        alias the library's buffers (owned rows first)"""
+        import torch
+
+        lib = capi.lib()
+        capi.check(lib.gdtb_assemble_async(self.op_h, self.fun_h, D.ASSEMBLE_OVERWRITE))
+        self.ctx.synchronize()  # the exchange runs on torch's stream
+        values, vector = self._device_views()
+
+        def add(y, x):
+            capi.check(lib.gdtb_vector_add(self.ctx._h, C.c_void_p(y.data_ptr()), C.c_void_p(x.data_ptr()), y.numel()))
+
+        torch.cuda.synchronize()
+        keep = [exchange_interface_rows(values, *self.mat_layout, self.rank, self.world, add, self.group),
+                exchange_interface_rows(vector, *self.vec_layout, self.rank, self.world, add, self.group)]
+        torch.cuda.synchronize()  # received layers are complete before the add kernels read them
+        self.ctx.synchronize()
+        del keep
+        return values, vector
+
+    def __del__(self):
+        if getattr(self, "op_h", None) and self.op_h.value:
+            capi.lib().gdtb_matop_destroy(self.op_h)
+            capi.lib().gdtb_vecfun_destroy(self.fun_h)
+
+
+def _as_tensor(ptr, n, device):
+    """torch view of `n` doubles of library-owned device memory (no copy)"""
+    import torch
+
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    return torch.as_tensor(_Arr(), device=device)

@@ -389,6 +389,17 @@ int gdtb_fv_interpolate_host(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_
  * (gdtb_matop_local_rows gives the global row range and the global CSR offset of the first owned value). */
 int gdtb_matop_set_slab(gdtb_matop* op, int64_t layer_begin, int64_t layer_end);
 int gdtb_vecfun_set_slab(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end);
+/* Interface-row halo partition (the other legal scheme): this process walks only its OWN element
+ * layers [begin, end) and holds the rows of the vertex layers [begin, end]; the top layer is the interface owned by
+ * the slab above and carries partial sums that must travel there (ncclSend / ncclRecv of one layer of rows:
+ * gdtb_*_halo_layout gives the position of the layer to send up and of the layer that receives from below, -1 where
+ * there is no neighbour), followed by gdtb_vector_add of the received layer.  CG Q1 only. */
+int gdtb_matop_set_slab_halo(gdtb_matop* op, int64_t layer_begin, int64_t layer_end);
+int gdtb_vecfun_set_slab_halo(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end);
+int gdtb_matop_halo_layout(const gdtb_matop* op, int64_t* recv_offset, int64_t* send_offset, int64_t* count);
+int gdtb_vecfun_halo_layout(const gdtb_vecfun* fun, int64_t* recv_offset, int64_t* send_offset, int64_t* count);
+/* d_y[0..n) += d_x[0..n) on the context's stream (enqueue only) */
+int gdtb_vector_add(gdtb_ctx* ctx, double* d_y, const double* d_x, int64_t n);
 int64_t gdtb_matop_local_nnz(const gdtb_matop* op);
 int gdtb_matop_local_rows(const gdtb_matop* op, int64_t* row_begin, int64_t* row_end, int64_t* value_offset);
 /* CG Q2: the MCMG-based ContinuousMapper (spaces/mapper/continuous.hh:117-150) numbers DoFs [cells | faces | edges |

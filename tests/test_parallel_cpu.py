@@ -105,3 +105,64 @@ def test_slab_layers_properties():
     assert parallel.neighbours(3, 4, False) == (2, None)
     assert parallel.neighbours(0, 4, True) == (3, 1)
     assert parallel.neighbours(0, 1, True) == (0, 0)
+
+
+def _halo_worker(rank, world, port, n, out_dir):
+    """interface-row halo of the element-partitioned assembly (SURVEY.md 8e scheme 2): every rank assembles its OWN
+    element layers only (oracle with kappa = 0 outside the slab), holds the rows of the vertex layers [begin, end],
+    sends the partial interface layer up and adds what arrives from below; owned rows == the global matrix / vector"""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from dune_gdt_b200 import descriptors as D
+    from dune_gdt_b200 import parallel
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        d = len(n)
+        g = D.grid_desc(-1.0, 1.0, list(n))
+        plane_e = int(np.prod(n[:-1])) if d > 1 else 1
+        plane_v = int(np.prod([k + 1 for k in n[:-1]])) if d > 1 else 1
+        kap = np.random.default_rng(20251017).uniform(0.5, 2.0, int(np.prod(n)))
+        rp, ci = oracle.pattern(g, (D.SPACE_CG, 1))
+        f_src = np.random.default_rng(7).uniform(-1.0, 1.0, kap.size)
+        lap = lambda k: D.form(D.integrand(D.INT_LAPLACE, diffusion=D.fn_elem(k)))  # noqa: E731
+        rhs = lambda w: D.form(D.integrand(D.INT_PRODUCT, diffusion=1.0, weight=D.fn_elem(w)))  # noqa: E731
+        v_ref, b_ref = oracle.assemble(g, D.SPACE_CG, 1, rp, ci, [lap(kap)], rhs_forms=[rhs(f_src)])
+        begin, end = parallel.slab_layers(n[-1], rank, world)
+        mask = np.zeros_like(kap)
+        mask[begin * plane_e:end * plane_e] = 1.0
+        v_part, b_part = oracle.assemble(g, D.SPACE_CG, 1, rp, ci, [lap(kap * mask)], rhs_forms=[rhs(f_src * mask)])
+        r0, r1 = begin * plane_v, (end + 1) * plane_v  # rows of the vertex layers [begin, end]
+        values = torch.from_numpy(v_part[rp[r0]:rp[r1]].copy())
+        vector = torch.from_numpy(b_part[r0:r1].copy())
+        has_lo, has_hi = rank > 0, rank < world - 1
+        # interface layers are interior along the last direction: the one received and the one sent have the same shape
+        layer_nnz = int(rp[r0 + plane_v] - rp[r0]) if has_lo else int(rp[r1] - rp[r1 - plane_v])
+        if has_lo and has_hi:
+            assert layer_nnz == rp[r1] - rp[r1 - plane_v]
+        parallel.exchange_interface_rows(values, 0 if has_lo else -1, values.numel() - layer_nnz if has_hi else -1,
+                                         layer_nnz, rank, world)
+        parallel.exchange_interface_rows(vector, 0 if has_lo else -1, vector.numel() - plane_v if has_hi else -1,
+                                         plane_v, rank, world)
+        own_rows = (end - begin + (0 if has_hi else 1)) * plane_v
+        own_nnz = int(rp[r0 + own_rows] - rp[r0])
+        err_v = np.abs(values.numpy()[:own_nnz] - v_ref[rp[r0]:rp[r0] + own_nnz]).max() / np.abs(v_ref).max()
+        err_b = np.abs(vector.numpy()[:own_rows] - b_ref[r0:r0 + own_rows]).max() / np.abs(b_ref).max()
+        assert err_v <= 1e-12 and err_b <= 1e-12, (err_v, err_b)
+        total = torch.tensor([own_nnz, own_rows])
+        dist.all_reduce(total)
+        assert total.tolist() == [len(v_ref), len(b_ref)]
+        open(os.path.join(out_dir, f"halo{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, [5, 4, 6]), (3, [6, 7]), (3, [4, 3, 9])])
+def test_interface_row_halo_gloo(tmp_path, oracle, world, n):
+    import torch.multiprocessing as mp
+
+    mp.spawn(_halo_worker, args=(world, free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"halo{r}").exists() for r in range(world))

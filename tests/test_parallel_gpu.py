@@ -81,6 +81,15 @@ def _worker(rank, world, port, out_dir):
         nnz = torch.tensor([slab.nnz_local], device="cuda")
         dist.all_reduce(nnz)
         assert int(nnz.item()) == len(v_ref)
+        # ---- the other partition: own elements only + interface-row halo over NCCL (SURVEY.md 8e scheme 2) ----
+        halo = parallel.HaloSlabAssembly(space, rank, world)
+        halo.append(lap)
+        halo.append_rhs(rhs)
+        hv, hb = halo.assemble_device()
+        hv, hb = hv.cpu().numpy(), hb.cpu().numpy()
+        assert halo.value_offset == slab.value_offset and halo.nnz_owned == slab.nnz_local
+        assert np.abs(hv[:halo.nnz_owned] - seg).max() / np.abs(v_ref).max() <= 1e-12
+        assert np.abs(hb[:halo.rows_owned] - b_ref[slab.row_begin:slab.row_end]).max() / np.abs(b_ref).max() <= 1e-12
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
