@@ -258,6 +258,104 @@ def assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src):
     return out
 
 
+def run_sharded_workload(args):
+    """--workload c5 | c4 | c2-halo: the other multi-GPU rows of SURVEY.md 8e under torchrun (one rank per GPU), device
+    resident, CUDA events, max over ranks.
+      c5      3D Q2 Laplace 128^3 SHARDED across the ranks (BASELINE.json configs[4], strong scaling): z-slabs,
+              owner-computes-rows per sub-entity group, no data-path collective
+      c4      explicit FV upwind Euler steps on 4096^2 periodic, y-slabs, one ghost row per side over NCCL per step
+              (interior overlapped with the exchange), strong scaling
+      c2-halo the headline workload with the interface-row halo partition (own elements only + one NCCL message per
+              slab face + add kernel) instead of the ghost-layer recompute, weak scaling"""
+    import torch
+    import torch.distributed as dist
+
+    import dune_gdt_b200 as gdt
+    from dune_gdt_b200 import descriptors as D
+    from dune_gdt_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib, check = gdt.capi.lib(), gdt.capi.check
+    ctx = gdt.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)  # the library launches on the stream the CUDA events are recorded on
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, units, metric, unit, scaling, config):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            step()
+        end.record()
+        barrier()
+        dt = torch.tensor([start.elapsed_time(end) * 1e-3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"metric": metric, "value": units * args.steps / dt.item(), "unit": unit, "n_gpus": world,
+                              "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt.item() / args.steps,
+                              "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+                              "data": "synthetic", "config": config}))
+
+    if args.workload == "c5":
+        n = 128
+        grid = gdt.make_cube_grid(ctx, -1.0, 1.0, [n, n, n])
+        space = gdt.make_continuous_lagrange_space(grid, 2)
+        slab = parallel.SlabAssembly(space, rank, world, with_functional=False)
+        slab.append(D.form(D.integrand(D.INT_LAPLACE, diffusion=1.0)))
+
+        timed(slab.assemble_device, n**3, "elements assembled/sec (3D Q2 Laplace, 128^3 sharded, FP64)", UNIT, "strong",
+              {"workload": "3D Q2 Laplace assembly, 128^3 YaspGrid cube sharded across the GPUs (BASELINE.json configs[4])",
+               "partition": f"z-slabs x{world}, owner-computes-rows per sub-entity group, no collective",
+               "nnz_this_rank": slab.nnz_local})
+    elif args.workload in ("c4", "c4-weak"):
+        n = 4096
+        ny = n * world if args.workload == "c4-weak" else n
+        grid = gdt.make_cube_grid(ctx, [0.0, 0.0], [1.0, ny / n], [n, ny], periodic=3)
+        space = gdt.make_finite_volume_space(grid)
+        L = parallel.make_distributed_advection_fv_operator(gdt.NumericalUpwindFlux(D.FLUX_LINEAR, [1.0, 0.5]), space, rank, world)
+        a = torch.rand(L.local_size, dtype=torch.float64, device="cuda")
+        b = torch.empty_like(a)
+        state = [a, b]
+
+        def step():
+            L.euler_step(state[0], state[1], 0.25 / n)
+            state.reverse()
+
+        timed(step, n * ny, "cells updated/sec (explicit FV upwind Euler step, 4096^2 periodic, FP64)", "cells/s",
+              "weak" if args.workload == "c4-weak" else "strong",
+              {"workload": f"FV linear advection, {n} x {ny} periodic YaspGrid (BASELINE.json configs[3]), fused apply + Euler update",
+               "partition": f"y-slabs x{world}, one ghost row per side per step over NCCL send/recv, interior overlapped"})
+    else:
+        h = 2.0 / NX
+        grid = gdt.make_cube_grid(ctx, [-1.0, -1.0, -1.0], [1.0, 1.0, -1.0 + NX * world * h], [NX, NX, NX * world])
+        space = gdt.make_continuous_lagrange_space(grid, 1)
+        halo = parallel.HaloSlabAssembly(space, rank, world)
+        lap, rhs = forms()
+        halo.append(lap)
+        halo.append_rhs(rhs)
+        timed(halo.assemble_device, NX**3 * world, METRIC, UNIT, "weak",
+              {"workload": "3D Q1 Laplace + RHS assembly, 256^3 per GPU (BASELINE.json configs[1])",
+               "partition": f"z-slabs x{world}, own elements only + interface-row halo over NCCL (one layer of rows per slab face)",
+               "halo_bytes_per_face": 8 * (halo.mat_layout[2] + halo.vec_layout[2])})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -448,11 +546,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c4", "c4-weak", "c2-halo"],
+                    help="c2 (default, the headline line); c5 / c4 / c2-halo: the other multi-GPU rows, see run_sharded_workload")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200:
             args.steps, args.warmup = 5, 1
         run_reference(args)
+    elif args.workload != "c2":
+        if args.steps == 200:
+            args.steps = 50
+        run_sharded_workload(args)
     else:
         run_product(args)
 
