@@ -1499,9 +1499,20 @@ static int q1_rhs_params(gdtb_vecfun* fun, Q1GatherParams& p)
         GDTB_CUDA(cudaMemcpyAsync(fun->d_rule, fun->h_rule, sizeof(host), cudaMemcpyHostToDevice, ctx->launch.stream));
         GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
         fun->rule_uploaded = true;
+        fun->sep_valid = false;
       }
-      GDTB_TRY(launch_q1_rhs_tables(ctx->launch, g, fun->elem_lo, fun->elem_hi, to_dev(in.weight), tab.m, fun->d_rule,
-                                    fun->d_rule + MAX_Q1D, fun->d_rule + 2 * MAX_Q1D, fun->d_sep_tab, stride));
+      // the tables depend on (source, rule, slab) only: rebuilt when one of them changed since the last walk
+      const FnDev src = to_dev(in.weight);
+      if (!fun->sep_valid || std::memcmp(&src, &fun->sep_fn, sizeof(FnDev)) != 0 || fun->sep_m != tab.m
+          || fun->sep_lo != fun->elem_lo || fun->sep_hi != fun->elem_hi) {
+        GDTB_TRY(launch_q1_rhs_tables(ctx->launch, g, fun->elem_lo, fun->elem_hi, src, tab.m, fun->d_rule,
+                                      fun->d_rule + MAX_Q1D, fun->d_rule + 2 * MAX_Q1D, fun->d_sep_tab, stride));
+        fun->sep_fn = src;
+        fun->sep_m = tab.m;
+        fun->sep_lo = fun->elem_lo;
+        fun->sep_hi = fun->elem_hi;
+        fun->sep_valid = true;
+      }
       p.rhs_has_sep = 1;
       p.rhs_sep_scale = w * (in.weight.builtin == GDTB_BUILTIN_COS_PRODUCT ? in.weight.p[0] : 1.);
       p.rhs_sep_tab = fun->d_sep_tab;
@@ -1711,6 +1722,8 @@ int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* fl
       volatile double upper = L->grid.lo[k] + double(i + 1) * L->grid.h[k];
       ext.push_back(k < L->grid.d ? upper - lower : 1.);
     }
+    if (ext.size() & 1) // every axis table starts 16-byte aligned (the marching kernel reads pairs)
+      ext.push_back(1.);
   }
   // ... followed by the reciprocals 1 / ext, same layout
   L->inv_ext_shift = (long long)ext.size();

@@ -118,6 +118,11 @@ struct gdtb_vecfun
   double h_rule[4 * MAX_Q1D];
   bool rule_uploaded;
   bool halo = false;
+  // what d_sep_tab was built for
+  bool sep_valid = false;
+  FnDev sep_fn;
+  int sep_m = 0;
+  long long sep_lo = 0, sep_hi = 0;
 };
 
 struct gdtb_fvop
