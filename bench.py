@@ -322,6 +322,21 @@ def run_sharded_workload(args):
               {"workload": "3D Q2 Laplace assembly, 128^3 YaspGrid cube sharded across the GPUs (BASELINE.json configs[4])",
                "partition": f"z-slabs x{world}, owner-computes-rows per sub-entity group, no collective",
                "nnz_this_rank": slab.nnz_local})
+    elif args.workload in ("c4-p2p", "c4-weak-p2p"):
+        n = 4096
+        ny = n * world if args.workload == "c4-weak-p2p" else n
+        grid = gdt.make_cube_grid(ctx, [0.0, 0.0], [1.0, ny / n], [n, ny], periodic=3)
+        space = gdt.make_finite_volume_space(grid)
+        loop = parallel.PeerMemoryFvTimeLoop(gdt.NumericalUpwindFlux(D.FLUX_LINEAR, [1.0, 0.5]), space, rank, world)
+        loop.set_initial_values(np.random.default_rng(20251017).random(n * ny))
+        timed(lambda: loop.euler_steps(0.25 / n, 1), n * ny,
+              "cells updated/sec (explicit FV upwind Euler step, 4096^2 periodic, FP64)", "cells/s",
+              "weak" if args.workload == "c4-weak-p2p" else "strong",
+              {"workload": f"FV linear advection, {n} x {ny} periodic YaspGrid (BASELINE.json configs[3]), fused apply + Euler update",
+               "partition": f"y-slabs x{world}, ghost rows handed over INSIDE the kernel (NVLink peer stores + step counters), "
+                            "one launch per step, no host-launched collective"})
+        loop.check()
+        loop.close()
     elif args.workload in ("c4", "c4-weak"):
         n = 4096
         ny = n * world if args.workload == "c4-weak" else n
@@ -546,7 +561,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c4", "c4-weak", "c2-halo"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c4", "c4-weak", "c4-p2p", "c4-weak-p2p", "c2-halo"],
                     help="c2 (default, the headline line); c5 / c4 / c2-halo: the other multi-GPU rows, see run_sharded_workload")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -140,6 +140,11 @@ PROTOTYPES = {
     "gdtb_fvop_euler_host": (C.c_int, [_P, _DP, C.c_double, C.c_int64]),
     "gdtb_fvop_set_slab": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gdtb_fvop_ghost_layer_size": (C.c_int64, [_P]),
+    "gdtb_fvop_p2p_alloc": (C.c_int, [_P, _PP, _PP, _P]),
+    "gdtb_fvop_p2p_connect": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int]),
+    "gdtb_fvop_p2p_step": (C.c_int, [_P, C.c_int, C.c_double]),
+    "gdtb_fvop_p2p_current": (C.c_int, [_P, _PP, _I64P]),
+    "gdtb_fvop_p2p_check": (C.c_int, [_P]),
     "gdtb_fvop_step_async": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, C.c_int64, C.c_int64]),
     "gdtb_fvop_append_boundary": (C.c_int, [_P, C.POINTER(FvBoundary)]),
     "gdtb_fv_estimate_dt": (C.c_int, [_P, _P, _DP, _DP]),

@@ -1756,6 +1756,13 @@ static void fv_fill_params(const gdtb_fvop* L, FvParams& p)
   p.rows_per_block = L->rows_per_block;
   p.apply_lo = L->grid.layer_lo;
   p.apply_hi = L->grid.layer_hi;
+  p.p2p = 0;
+  p.peer_lo_ghost = p.peer_hi_ghost = nullptr;
+  p.peer_lo_flag = p.peer_hi_flag = nullptr;
+  p.my_flags = nullptr;
+  p.expect = 0;
+  p.timeout_flag = nullptr;
+  p.edge_count = nullptr;
   p.bnd_ext_mask = L->bnd_ext_mask;
   p.bnd_nf_mask = L->bnd_nf_mask;
   for (int i = 0; i < 6; ++i) {
@@ -1765,6 +1772,9 @@ static void fv_fill_params(const gdtb_fvop* L, FvParams& p)
     p.bnd_nf_b[i] = L->bnd_nf_b[i];
   }
 }
+
+static void fv_p2p_release(gdtb_fvop* L);
+static long long fv_local_size(const gdtb_fvop* L);
 
 int gdtb_fvop_destroy(gdtb_fvop* L)
 {
@@ -1776,6 +1786,7 @@ int gdtb_fvop_destroy(gdtb_fvop* L)
   cudaFree(L->d_dst);
   cudaFree(L->d_ext);
   cudaFree(L->d_partial);
+  fv_p2p_release(L);
   delete L;
   return GDTB_OK;
 }
@@ -1803,6 +1814,162 @@ int gdtb_fvop_append_boundary(gdtb_fvop* L, const gdtb_fv_boundary* t)
     }
   }
   (t->kind == GDTB_FVBND_EXTRAPOLATION ? L->bnd_ext_mask : L->bnd_nf_mask) |= t->side_mask;
+  return GDTB_OK;
+}
+
+// ---- peer-memory ghost exchange (multi-GPU FV time loop without host-launched collectives) -----------------------
+// The slab vectors of the time loop live in library-owned cudaMalloc memory that the neighbour processes open through
+// CUDA IPC.  Step s reads u[s % 2] and writes u[(s + 1) % 2]; k_fv_march<..., P2P> stores the first / last owned layer of
+// the result into the neighbours' ghost layers (NVLink peer stores) and raises their step counters; the blocks that
+// read a ghost layer wait for the counter of the previous step.  Replaces the DataHandle communicate() of
+// tools/timestepper/explicit-rungekutta.hh:252-257 for the fused Euler loop.
+static void fv_p2p_release(gdtb_fvop* L)
+{
+  for (int side = 0; side < 2; ++side) {
+    if (L->p2p_opened[side]) {
+      for (void* ptr : {(void*)L->p2p_peer_u[side][0], (void*)L->p2p_peer_u[side][1], (void*)L->p2p_peer_flags[side]})
+        if (ptr)
+          cudaIpcCloseMemHandle(ptr);
+    }
+    L->p2p_opened[side] = false;
+    L->p2p_peer_u[side][0] = L->p2p_peer_u[side][1] = nullptr;
+    L->p2p_peer_flags[side] = nullptr;
+  }
+  cudaFree(L->p2p_u[0]);
+  cudaFree(L->p2p_u[1]);
+  cudaFree(L->p2p_flags);
+  L->p2p_u[0] = L->p2p_u[1] = nullptr;
+  L->p2p_flags = nullptr;
+}
+
+int gdtb_fvop_p2p_alloc(gdtb_fvop* L, double** d_u0, double** d_u1, void* handles)
+{
+  if (!L || !handles)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_p2p_alloc: NULL argument");
+  GDTB_TRY(check_ctx(L->ctx));
+  if (!L->ghosted)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_p2p_alloc: call gdtb_fvop_set_slab first");
+  if (L->grid.d < 2)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "gdtb_fvop_p2p_alloc: 2D and 3D grids only");
+  fv_p2p_release(L);
+  const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  // flags: [0] lower ghost filled, [1] upper ghost filled, [2] wait timed out, [4..5] edge block counters
+  if (cudaMalloc(&L->p2p_u[0], bytes) != cudaSuccess || cudaMalloc(&L->p2p_u[1], bytes) != cudaSuccess
+      || cudaMalloc(&L->p2p_flags, 64 * sizeof(int)) != cudaSuccess) {
+    fv_p2p_release(L);
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (peer-memory slab vectors)");
+  }
+  GDTB_CUDA(cudaMemset(L->p2p_u[0], 0, bytes));
+  GDTB_CUDA(cudaMemset(L->p2p_u[1], 0, bytes));
+  GDTB_CUDA(cudaMemset(L->p2p_flags, 0, 64 * sizeof(int)));
+  cudaIpcMemHandle_t h[3];
+  if (cudaIpcGetMemHandle(&h[0], L->p2p_u[0]) != cudaSuccess || cudaIpcGetMemHandle(&h[1], L->p2p_u[1]) != cudaSuccess
+      || cudaIpcGetMemHandle(&h[2], L->p2p_flags) != cudaSuccess) {
+    const std::string why = cudaGetErrorString(cudaGetLastError());
+    fv_p2p_release(L);
+    return fail(GDTB_ERR_CUDA, "cudaIpcGetMemHandle failed: " + why);
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == GDTB_IPC_HANDLE_BYTES, "IPC handle size");
+  std::memcpy(handles, h, sizeof(h));
+  if (d_u0)
+    *d_u0 = L->p2p_u[0];
+  if (d_u1)
+    *d_u1 = L->p2p_u[1];
+  L->p2p_step = 0;
+  return GDTB_OK;
+}
+
+int gdtb_fvop_p2p_connect(gdtb_fvop* L, const void* lower_handles, int64_t lower_layers, int lower_is_self,
+                          const void* upper_handles, int64_t upper_layers, int upper_is_self)
+{
+  if (!L || !L->p2p_u[0])
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_p2p_connect: call gdtb_fvop_p2p_alloc first");
+  GDTB_TRY(check_ctx(L->ctx));
+  const void* hs[2] = {lower_handles, upper_handles};
+  const int self[2] = {lower_is_self, upper_is_self};
+  const int64_t layers[2] = {lower_layers, upper_layers};
+  for (int side = 0; side < 2; ++side) {
+    L->p2p_peer_layers[side] = layers[side];
+    if (self[side]) { // the periodic neighbour is this rank itself (one slab)
+      L->p2p_peer_u[side][0] = L->p2p_u[0];
+      L->p2p_peer_u[side][1] = L->p2p_u[1];
+      L->p2p_peer_flags[side] = L->p2p_flags;
+      L->p2p_peer_layers[side] = L->grid.layer_hi - L->grid.layer_lo;
+      continue;
+    }
+    if (!hs[side])
+      continue; // domain boundary without periodicity
+    if (side == 1 && hs[0] && !self[0] && std::memcmp(hs[0], hs[1], 3 * GDTB_IPC_HANDLE_BYTES) == 0) {
+      // two slabs, periodic: both neighbours are the same process; a handle can be opened once per process
+      L->p2p_peer_u[1][0] = L->p2p_peer_u[0][0];
+      L->p2p_peer_u[1][1] = L->p2p_peer_u[0][1];
+      L->p2p_peer_flags[1] = L->p2p_peer_flags[0];
+      continue;
+    }
+    cudaIpcMemHandle_t h[3];
+    std::memcpy(h, hs[side], sizeof(h));
+    void* ptr[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < 3; ++i)
+      if (cudaIpcOpenMemHandle(&ptr[i], h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        return fail(GDTB_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError()));
+    L->p2p_peer_u[side][0] = static_cast<double*>(ptr[0]);
+    L->p2p_peer_u[side][1] = static_cast<double*>(ptr[1]);
+    L->p2p_peer_flags[side] = static_cast<int*>(ptr[2]);
+    L->p2p_opened[side] = true;
+  }
+  return GDTB_OK;
+}
+
+int gdtb_fvop_p2p_step(gdtb_fvop* L, int euler, double dt)
+{
+  if (!L || !L->p2p_u[0])
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_p2p_step: call gdtb_fvop_p2p_alloc / connect first");
+  GDTB_TRY(check_ctx(L->ctx));
+  FvParams p;
+  fv_fill_params(L, p);
+  p.euler = euler ? 1 : 0;
+  p.dt = dt;
+  const long long plane = gdtb_fvop_ghost_layer_size(L);
+  const int src = (int)(L->p2p_step & 1), dst = src ^ 1;
+  p.p2p = 1;
+  if (L->p2p_peer_u[0][dst]) { // my first layer -> the lower neighbour's upper ghost layer
+    p.peer_lo_ghost = L->p2p_peer_u[0][dst] + (L->p2p_peer_layers[0] + 1) * plane;
+    p.peer_lo_flag = L->p2p_peer_flags[0] + 1;
+  }
+  if (L->p2p_peer_u[1][dst]) { // my last layer -> the upper neighbour's lower ghost layer
+    p.peer_hi_ghost = L->p2p_peer_u[1][dst];
+    p.peer_hi_flag = L->p2p_peer_flags[1] + 0;
+  }
+  p.my_flags = L->p2p_flags;
+  p.timeout_flag = L->p2p_flags + 2;
+  p.edge_count = L->p2p_flags + 4;
+  p.expect = (int)L->p2p_step;
+  GDTB_TRY(launch_fv_apply(L->ctx->launch, p, L->p2p_u[src], L->p2p_u[dst]));
+  L->p2p_step++;
+  return GDTB_OK;
+}
+
+int gdtb_fvop_p2p_current(gdtb_fvop* L, double** d_u, int64_t* step)
+{
+  if (!L || !L->p2p_u[0])
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_p2p_current: no peer-memory vectors");
+  if (d_u)
+    *d_u = L->p2p_u[L->p2p_step & 1];
+  if (step)
+    *step = L->p2p_step;
+  return GDTB_OK;
+}
+
+int gdtb_fvop_p2p_check(gdtb_fvop* L)
+{
+  if (!L || !L->p2p_flags)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_p2p_check: no peer-memory vectors");
+  GDTB_TRY(check_ctx(L->ctx));
+  int flags[3] = {0, 0, 0};
+  GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
+  GDTB_CUDA(cudaMemcpy(flags, L->p2p_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+  if (flags[2])
+    return fail(GDTB_ERR_OPERATOR, "peer-memory ghost exchange: a wait for the neighbour's step counter timed out");
   return GDTB_OK;
 }
 

@@ -251,6 +251,31 @@ __device__ __forceinline__ void ldg_cols(const double* q, double (&v)[C])
     v[0] = __ldg(q);
 }
 
+// the same through L2 only: layers another GPU may have written during this kernel (peer-memory ghost exchange)
+template <int C>
+__device__ __forceinline__ void ldcg_cols(const double* q, double (&v)[C])
+{
+  if (C == 2) {
+    const double2 t = __ldcg(reinterpret_cast<const double2*>(q));
+    v[0] = t.x;
+    v[C - 1] = t.y;
+  } else
+    v[0] = __ldcg(q);
+}
+
+// bounded wait for a counter another GPU raises in this GPU's memory (system-scope acquire); gives up after ~1 s
+__device__ __forceinline__ void fv_wait_counter(const int* counter, int expect, int* timeout_flag)
+{
+  for (long long spin = 0; spin < (1LL << 23); ++spin) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v - expect >= 0)
+      return;
+    __nanosleep(100);
+  }
+  atomicExch(timeout_flag, 1);
+}
+
 template <int C>
 __device__ __forceinline__ void st_cols(double* q, const double (&v)[C])
 {
@@ -269,7 +294,7 @@ __device__ __forceinline__ void st_cols(double* q, const double (&v)[C])
 // advection-fv.hh:147-152 equals g / ext_k on axis-aligned cells up to rounding.  Faces that do not exist (domain
 // boundary without periodicity) get the coefficient 0.  Loads are issued FV_BATCH layers at a time before the first
 // flux of the batch is evaluated (memory-level parallelism).
-template <int D, int NUMFLUX, int KIND, int C, bool BND>
+template <int D, int NUMFLUX, int KIND, int C, bool BND, bool P2P = false>
 __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvParams p, const double* __restrict__ u,
                                                   double* __restrict__ out, int rows)
 {
@@ -291,6 +316,19 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
     return;
   // local layer index of global layer j: j - layer_lo (+1 ghost layer below on a slab)
   const int shift = p.ghosted ? 1 - layer_lo : -layer_lo;
+  // peer-memory exchange: the blocks that touch the slab's first / last layer read a ghost layer the neighbour GPU
+  // filled during its previous step and hand their own boundary layer over at the end
+  const bool edge_lo = P2P && j0 == layer_lo, edge_hi = P2P && j1 == (int)g.layer_hi;
+  if (P2P) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      if (edge_lo && p.peer_lo_ghost)
+        fv_wait_counter(p.my_flags + 0, p.expect, p.timeout_flag);
+      if (edge_hi && p.peer_hi_ghost)
+        fv_wait_counter(p.my_flags + 1, p.expect, p.timeout_flag);
+    }
+    if (edge_lo || edge_hi)
+      __syncthreads();
+  }
 
   // tile axes: offsets to the neighbour cells (periodic wrap, or 0 = the cell itself where there is no face) and
   // the face coefficients 1 / ext (0 where there is no face)
@@ -331,7 +369,10 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
     const bool has = j0 > 0 || perl;
     const long long off = (j0 > 0 || p.ghosted) ? -plane : (has ? (long long)(nl - 1) * plane : 0);
     double ub[C];
-    ldg_cols<C>(pc + off, ub);
+    if (P2P)
+      ldcg_cols<C>(pc + off, ub);
+    else
+      ldg_cols<C>(pc + off, ub);
 #pragma unroll
     for (int c = 0; c < C; ++c)
       G_low[c] = has ? flux_plus<NUMFLUX, KIND>(p, last, ub[c], uc[c])
@@ -346,7 +387,10 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const double* q = pc + (long long)r * plane;
-      ldg_cols<C>(q + plane, un[r]);
+      if (P2P)
+        ldcg_cols<C>(q + plane, un[r]);
+      else
+        ldg_cols<C>(q + plane, un[r]);
       xl[r] = __ldg(q + d_xm);
       xr[r] = __ldg(q + d_xp);
       if (D == 3) {
@@ -376,6 +420,12 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
         uc[c] = un[r][c];
       }
       st_cols<C>(po + (long long)r * plane, res);
+      if (P2P) {
+        if (jb + r == layer_lo && p.peer_lo_ghost)
+          st_cols<C>(p.peer_lo_ghost + col, res);
+        if (jb + r == (int)g.layer_hi - 1 && p.peer_hi_ghost)
+          st_cols<C>(p.peer_hi_ghost + col, res);
+      }
     }
     pc += (long long)R * plane;
     po += (long long)R * plane;
@@ -386,7 +436,10 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
     const bool top = j == nl - 1;
     const bool has_up = !top || perl;
     double un[C], yl[C], yr[C], res[C], gx[C + 1];
-    ldg_cols<C>(pc + ((top && !p.ghosted) ? (has_up ? (1 - (long long)nl) * plane : 0) : plane), un);
+    if (P2P)
+      ldcg_cols<C>(pc + plane, un);
+    else
+      ldg_cols<C>(pc + ((top && !p.ghosted) ? (has_up ? (1 - (long long)nl) * plane : 0) : plane), un);
     gx[0] = bx_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 0, 0, uc[0]) : flux_plus<NUMFLUX, KIND>(p, 0, __ldg(pc + d_xm), uc[0]);
     if (C == 2)
       gx[1] = flux_plus<NUMFLUX, KIND>(p, 0, uc[0], uc[C - 1]);
@@ -411,9 +464,34 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
       uc[c] = un[c];
     }
     st_cols<C>(po, res);
+    if (P2P) {
+      if (j == layer_lo && p.peer_lo_ghost)
+        st_cols<C>(p.peer_lo_ghost + col, res);
+      if (j == (int)g.layer_hi - 1 && p.peer_hi_ghost)
+        st_cols<C>(p.peer_hi_ghost + col, res);
+    }
     pc += plane;
     po += plane;
     prl += 1;
+  }
+  if (P2P && (edge_lo || edge_hi)) {
+    // make this block's remote stores visible system-wide; the last edge block of the launch raises the neighbour's
+    // counter by one (so the counter counts steps, whatever the tiling)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      const int tiles = D == 3 ? (int)(gridDim.x * gridDim.y) : (int)gridDim.x;
+      if (edge_lo && p.peer_lo_flag && atomicAdd(p.edge_count + 0, 1) == tiles - 1) {
+        atomicExch(p.edge_count + 0, 0);
+        __threadfence_system();
+        atomicAdd_system(p.peer_lo_flag, 1);
+      }
+      if (edge_hi && p.peer_hi_flag && atomicAdd(p.edge_count + 1, 1) == tiles - 1) {
+        atomicExch(p.edge_count + 1, 0);
+        __threadfence_system();
+        atomicAdd_system(p.peer_hi_flag, 1);
+      }
+    }
   }
 }
 
@@ -543,22 +621,32 @@ __global__ void __launch_bounds__(256) k_fv_dt_reduce(const __grid_constant__ Fv
 
 } // namespace
 
-template <int D, int C>
-static void launch_fv_march(const FvParams& p, const double* u, double* out, int rows, dim3 grid, dim3 block,
-                            cudaStream_t stream)
+template <int D, int C, bool P2P>
+static void launch_fv_march_p(const FvParams& p, const double* u, double* out, int rows, dim3 grid, dim3 block,
+                              cudaStream_t stream)
 {
   const int variant = (p.flux.numflux == GDTB_NUMFLUX_LAX_FRIEDRICHS ? 2 : 0) + (p.flux.kind == GDTB_FLUX_BURGERS ? 1 : 0)
                       + ((p.bnd_ext_mask | p.bnd_nf_mask) ? 4 : 0);
   switch (variant) {
-    case 0: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C, false><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    case 1: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C, false><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    case 2: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C, false><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    case 3: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C, false><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    case 4: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C, true><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    case 5: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C, true><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    case 6: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C, true><<<grid, block, 0, stream>>>(p, u, out, rows); break;
-    default: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C, true><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 0: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C, false, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 1: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C, false, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 2: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C, false, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 3: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C, false, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 4: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C, true, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 5: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C, true, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 6: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C, true, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    default: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C, true, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
   }
+}
+
+template <int D, int C>
+static void launch_fv_march(const FvParams& p, const double* u, double* out, int rows, dim3 grid, dim3 block,
+                            cudaStream_t stream)
+{
+  if (p.p2p)
+    launch_fv_march_p<D, C, true>(p, u, out, rows, grid, block, stream);
+  else
+    launch_fv_march_p<D, C, false>(p, u, out, rows, grid, block, stream);
 }
 
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
@@ -574,7 +662,8 @@ int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
   } else {
     // two cells per thread (16-byte accesses) when every row starts 16-byte aligned
     const bool two = g.n[0] % 2 == 0 && ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(out)) & 15) == 0
-                     && (reinterpret_cast<uintptr_t>(p.inv_ext[0]) & 15) == 0;
+                     && (reinterpret_cast<uintptr_t>(p.inv_ext[0]) & 15) == 0
+                     && ((reinterpret_cast<uintptr_t>(p.peer_lo_ghost) | reinterpret_cast<uintptr_t>(p.peer_hi_ghost)) & 15) == 0;
     const long long nx = two ? g.n[0] / 2 : g.n[0]; // threads along x
     dim3 block(1, 1, 1), grid(1, 1, 1);
     long long tiles;

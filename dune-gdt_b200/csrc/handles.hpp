@@ -144,6 +144,14 @@ struct gdtb_fvop
   double bnd_ext_a[6] = {0, 0, 0, 0, 0, 0}, bnd_ext_b[6] = {0, 0, 0, 0, 0, 0};
   double bnd_nf_a[6] = {0, 0, 0, 0, 0, 0}, bnd_nf_b[6] = {0, 0, 0, 0, 0, 0};
   double* d_partial = nullptr; // block partials of the dt estimate
+  // peer-memory ghost exchange (gdtb_fvop_p2p_*): own slab vectors + flags, the neighbours' opened through CUDA IPC
+  double* p2p_u[2] = {nullptr, nullptr};
+  int* p2p_flags = nullptr;
+  double* p2p_peer_u[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; // [lower / upper neighbour][buffer]
+  int* p2p_peer_flags[2] = {nullptr, nullptr};
+  long long p2p_peer_layers[2] = {0, 0};
+  bool p2p_opened[2] = {false, false};
+  long long p2p_step = 0;
 };
 
 struct gdtb_rk

@@ -253,6 +253,19 @@ struct FvParams
   // numerical boundary flux g = a (f(u) . n) + b (local/operators/advection-fv.hh:188-457)
   unsigned bnd_ext_mask, bnd_nf_mask;
   double bnd_ext_a[6], bnd_ext_b[6], bnd_nf_a[6], bnd_nf_b[6];
+  // peer-memory ghost exchange (multi-GPU slabs, one process per GPU, buffers opened through CUDA IPC): the kernel
+  // stores the first / last owned layer of its result straight into the neighbours' ghost layers over NVLink and
+  // raises a counter in the neighbour's memory; the CTAs that read a ghost layer first wait for the neighbour's
+  // counter of the previous step.  NULL pointers: no neighbour on that side.
+  int p2p;
+  double* peer_lo_ghost; // upper ghost layer of the lower neighbour's destination buffer
+  double* peer_hi_ghost; // lower ghost layer of the upper neighbour's destination buffer
+  int* peer_lo_flag;     // lower neighbour's "upper ghost filled" counter
+  int* peer_hi_flag;     // upper neighbour's "lower ghost filled" counter
+  const int* my_flags;   // {lower ghost filled, upper ghost filled} counters of this rank
+  int expect;            // counter value that marks the ghost layers of the source buffer as complete (= step index)
+  int* edge_count;       // {lower, upper}: edge blocks of this launch that have handed their layer over (last one signals)
+  int* timeout_flag;     // set when a wait gave up (bounded spin)
 };
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out);
 

@@ -157,6 +157,113 @@ def make_distributed_advection_fv_operator(numerical_flux, space, rank, world, g
     return DistributedAdvectionFvOperator(numerical_flux, space, rank, world, group)
 
 
+class PeerMemoryFvTimeLoop:
+    """The explicit Euler loop of examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:141-159 on slabs WITHOUT a
+    host-launched collective per step: the apply kernel stores its first / last owned layer straight into the neighbour
+    GPUs' ghost layers (NVLink peer stores into buffers opened through CUDA IPC) and raises a step counter there; the
+    blocks that read a ghost layer wait for the neighbour's counter of the previous step (`gdtb_fvop_p2p_*`).  One
+    kernel launch per step and rank; NCCL is only used to pass the IPC handles around and for the initial ghost fill."""
+
+    def __init__(self, numerical_flux, space, rank, world, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from .api import AdvectionFvOperator
+
+        lib = capi.lib()
+        self.space, self.rank, self.world, self.group = space, rank, world, group
+        g = space.grid.desc
+        self.dim = int(g.dim)
+        self.n_last = int(g.n[self.dim - 1])
+        self.periodic_last = bool(g.periodic & (1 << (self.dim - 1))) and self.n_last > 1
+        self.begin, self.end = slab_layers(self.n_last, rank, world)
+        self.op = AdvectionFvOperator(numerical_flux, space)
+        capi.check(lib.gdtb_fvop_set_slab(self.op._h, self.begin, self.end))
+        self.plane = int(lib.gdtb_fvop_ghost_layer_size(self.op._h))
+        self.owned = (self.end - self.begin) * self.plane
+        self.local_size = self.owned + 2 * self.plane
+        handles = (C.c_ubyte * (3 * 64))()
+        p0, p1 = C.c_void_p(), C.c_void_p()
+        capi.check(lib.gdtb_fvop_p2p_alloc(self.op._h, C.byref(p0), C.byref(p1), handles))
+        dev = torch.device("cuda", space.grid.ctx.device)
+        self.u = [_as_tensor(p0.value, self.local_size, dev), _as_tensor(p1.value, self.local_size, dev)]
+        lower, upper = neighbours(rank, world, self.periodic_last)
+        mine = torch.tensor(list(bytes(handles)), dtype=torch.uint8, device=dev)
+        if world > 1:
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine, group=group)
+        else:
+            every = [mine]
+
+        def arg(nb):
+            if nb is None:
+                return None, 0, 0
+            if nb == rank:
+                return None, 0, 1
+            b, e = slab_layers(self.n_last, nb, world)
+            raw = bytes(every[nb].cpu().numpy().tobytes())
+            return (C.c_ubyte * len(raw)).from_buffer_copy(raw), e - b, 0
+
+        lo_h, lo_layers, lo_self = arg(lower)
+        hi_h, hi_layers, hi_self = arg(upper)
+        self._keep = (lo_h, hi_h)
+        capi.check(lib.gdtb_fvop_p2p_connect(self.op._h, lo_h, lo_layers, lo_self, hi_h, hi_layers, hi_self))
+        if world > 1:
+            dist.barrier(group=group)  # every rank has opened its neighbours' buffers
+
+    def set_initial_values(self, u_global):
+        """owned layers of a global host vector into u[0]; the ghost layers come from the neighbours once (NCCL)"""
+        import torch
+
+        loc = np.zeros(self.local_size)
+        loc[self.plane:self.plane + self.owned] = np.asarray(u_global)[self.begin * self.plane:self.end * self.plane]
+        self.space.grid.ctx.synchronize()
+        self.u[0].copy_(torch.from_numpy(loc))
+        for r in exchange_ghost_layers(self.u[0], self.plane, self.rank, self.world, self.periodic_last, self.group):
+            r.wait()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
+
+    def euler_steps(self, dt, n_steps):
+        """n_steps times u <- u - dt L(u): one kernel launch per step, the ghost exchange happens inside the kernel"""
+        lib = capi.lib()
+        for _ in range(n_steps):
+            capi.check(lib.gdtb_fvop_p2p_step(self.op._h, 1, float(dt)))
+
+    def apply_steps(self, n_steps):
+        lib = capi.lib()
+        for _ in range(n_steps):
+            capi.check(lib.gdtb_fvop_p2p_step(self.op._h, 0, 0.0))
+
+    def check(self):
+        capi.check(capi.lib().gdtb_fvop_p2p_check(self.op._h))
+
+    def current(self):
+        """device tensor (slab layout) that holds the current solution"""
+        p, s = C.c_void_p(), C.c_int64()
+        capi.check(capi.lib().gdtb_fvop_p2p_current(self.op._h, C.byref(p), C.byref(s)))
+        return self.u[s.value & 1]
+
+    def owned_view(self, u_local):
+        return u_local[self.plane:self.plane + self.owned]
+
+    def close(self):
+        """collective: nobody may free its buffers while a neighbour can still store into them"""
+        import torch
+
+        self.space.grid.ctx.synchronize()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
+        self.u = None
+        self.op = None
+
+
 class SlabAssembly:
     """Matrix operator + functional of one rank: owner-computes-rows on the rank's element slab, no communication.
     The global CSR matrix is the concatenation of the ranks' value arrays in rank order (`value_offset` is the

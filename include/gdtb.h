@@ -346,6 +346,27 @@ int gdtb_fvop_step_async(gdtb_fvop* L, const double* d_source, double* d_range, 
                          int64_t layer_begin, int64_t layer_end);
 int64_t gdtb_fvop_ghost_layer_size(const gdtb_fvop* L);
 
+/* Peer-memory ghost exchange for the multi-GPU time loop (one process per GPU on one NVLink / NVSwitch box): instead of
+ * a host-launched send / recv per step (the DataHandle communicate() of tools/timestepper/explicit-rungekutta.hh:252-257)
+ * the apply kernel itself stores its first / last owned layer into the neighbours' ghost layers and raises a step
+ * counter in their memory; the blocks that read a ghost layer wait for the counter of the previous step.
+ *   1. gdtb_fvop_set_slab, then gdtb_fvop_p2p_alloc: two library-owned slab vectors ([ghost | owned | ghost]) and
+ *      their CUDA IPC handles (3 x GDTB_IPC_HANDLE_BYTES: u0, u1, counters) to be sent to the neighbour processes;
+ *   2. gdtb_fvop_p2p_connect with the handles received from the lower / upper neighbour (NULL: no neighbour; *_is_self:
+ *      the periodic neighbour is this process) and the neighbours' numbers of owned layers;
+ *   3. fill u0 (owned part and ghost layers) once, then gdtb_fvop_p2p_step per step (enqueue only): step s reads
+ *      u[s % 2] and writes u[(s + 1) % 2]; gdtb_fvop_p2p_current gives the vector holding the current solution;
+ *   4. gdtb_fvop_p2p_check synchronises and reports a timed-out wait (GDTB_ERR_OPERATOR).
+ * All processes must have finished step 2 before any of them starts step 3, and destroy their operators only after a
+ * common barrier. */
+#define GDTB_IPC_HANDLE_BYTES 64
+int gdtb_fvop_p2p_alloc(gdtb_fvop* L, double** d_u0, double** d_u1, void* handles);
+int gdtb_fvop_p2p_connect(gdtb_fvop* L, const void* lower_handles, int64_t lower_layers, int lower_is_self,
+                          const void* upper_handles, int64_t upper_layers, int upper_is_self);
+int gdtb_fvop_p2p_step(gdtb_fvop* L, int euler, double dt);
+int gdtb_fvop_p2p_current(gdtb_fvop* L, double** d_u, int64_t* step);
+int gdtb_fvop_p2p_check(gdtb_fvop* L);
+
 /* AdvectionFvOperator::append(boundary treatment lambda, param_type, filter) (operators/advection-fv.hh:96-123):
  * applies on the non-periodic domain boundary faces selected by side_mask.  Treatments add up like appended local
  * operators do; two different extrapolations on the same side are GDTB_ERR_NOT_IMPLEMENTED. */

@@ -59,6 +59,22 @@ def _worker(rank, world, port, out_dir):
             own = L.owned_view(a).cpu().numpy()
             err = np.abs(own - ref_e[L.begin * L.plane:L.end * L.plane]).max() / np.abs(ref_e).max()
             assert err <= 1e-12, ("euler", n, err)
+        # ---- FV: the same Euler loops with the peer-memory ghost exchange (no collective per step) --------------
+        for n, periodic, fk, params in (([96, 64], 3, D.FLUX_LINEAR, [1.0, 0.5]), ([64, 50], 0, D.FLUX_BURGERS, []),
+                                        ([24, 20, 18], 7, D.FLUX_LINEAR, [1.0, -0.5, 0.25]), ([33, 40], 2, D.FLUX_BURGERS, [])):
+            u = rng.random(int(np.prod(n)))
+            grid = gdt.make_cube_grid(ctx, 0.0, 1.0, n, periodic=periodic)
+            space = gdt.make_finite_volume_space(grid)
+            loop = parallel.PeerMemoryFvTimeLoop(gdt.NumericalUpwindFlux(fk, params), space, rank, world)
+            loop.set_initial_values(u)
+            dt, steps = 0.2 / max(n), 7
+            loop.euler_steps(dt, steps)
+            loop.check()
+            ref_e = oracle.fv_euler(D.grid_desc(0.0, 1.0, n, periodic=periodic), D.flux(fk, D.NUMFLUX_UPWIND, params), u, dt, steps)
+            own = loop.owned_view(loop.current()).cpu().numpy()
+            err = np.abs(own - ref_e[loop.begin * loop.plane:loop.end * loop.plane]).max() / np.abs(ref_e).max()
+            assert err <= 1e-12, ("p2p euler", n, err)
+            loop.close()
         # ---- assembly: concatenated slab results == oracle on the whole grid ----------------------------------
         n = [10, 9, 11]
         grid = gdt.make_cube_grid(ctx, -1.0, 1.0, n)
