@@ -9,7 +9,7 @@ import os
 from .descriptors import Flux, Form, Function, FvBoundary, GridDesc, SolverInfo, SolverOpts
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgdtb.so")
+LIB_PATH = os.environ.get("GDTB_LIB") or os.path.join(_HERE, "lib", "libgdtb.so")  # GDTB_LIB: A/B builds
 
 # status codes -> exception classes named after the reference's (dune/gdt/exceptions.hh:24-75)
 

@@ -27,6 +27,14 @@
 #include "common.cuh"
 #include "kernels.hpp"
 
+// resident blocks per SM the register allocation aims for, and the number of shared-memory stages (see the kernel)
+#ifndef Q1G_MIN_BLOCKS
+#define Q1G_MIN_BLOCKS 2
+#endif
+#ifndef Q1G_DEFAULT_NBUF
+#define Q1G_DEFAULT_NBUF 2
+#endif
+
 namespace gdtb {
 
 namespace {
@@ -262,9 +270,9 @@ __device__ __forceinline__ int q1_store_plane(double* __restrict__ row, const do
 // CELLDATA = false: no per-element coefficient / source arrays and no per-cell right-hand-side terms are in play
 // (constant coefficients, separable analytic source): the element index is never formed.
 template <int D, int NG, int KIND0, bool ACCUMULATE, bool CELLDATA>
-__global__ void __launch_bounds__(Q1G_ROWS, 2)
+__global__ void __launch_bounds__(Q1G_ROWS, Q1G_MIN_BLOCKS)
     k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values, double* __restrict__ rhs,
-                long long nrows, int nitems, int stage_doubles)
+                long long nrows, int nitems, int stage_doubles, int nbuf)
 {
   constexpr int NO = 1 << D; // elements around a vertex
   extern __shared__ __align__(16) double smem[];
@@ -476,10 +484,13 @@ __global__ void __launch_bounds__(Q1G_ROWS, 2)
           if (head + body < seg)
             values[start + head + body] = stage[head + body];
           bulk_commit();
-          bulk_wait_read1(); // the buffer written two items ago is free again
+          if (nbuf == 1)
+            bulk_wait_read0(); // one stage: it must have been read out before the next item is written
+          else
+            bulk_wait_read1(); // the buffer written two items ago is free again
         }
         __syncthreads();
-        buf ^= 1;
+        buf = nbuf == 1 ? 0 : buf ^ 1;
       }
     }
   }
@@ -587,7 +598,9 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
   // two stage buffers (double-buffered bulk store), each padded for the 16-byte phase shift
   const int stage_doubles = ((Q1G_ROWS * P3<D>::value + 2) + 1) & ~1;
   const bool with_values = NG > 0 && values;
-  const size_t smem = with_values ? (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double) : 16;
+  static const int nbuf_env = std::getenv("GDTB_Q1_NBUF") ? std::atoi(std::getenv("GDTB_Q1_NBUF")) : 0;
+  const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : Q1G_DEFAULT_NBUF);
+  const size_t smem = with_values ? (size_t)nbuf * stage_doubles * sizeof(double) : 16;
   auto kern = accumulate ? k_q1_gather<D, NG, KIND0, true, CELLDATA> : k_q1_gather<D, NG, KIND0, false, CELLDATA>;
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -599,7 +612,7 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
   if (grid > nitems)
     grid = nitems;
   time_begin(L, KF_Q1_GATHER);
-  kern<<<(unsigned)grid, Q1G_ROWS, smem, L.stream>>>(p, values, rhs, nrows, (int)nitems, stage_doubles);
+  kern<<<(unsigned)grid, Q1G_ROWS, smem, L.stream>>>(p, values, rhs, nrows, (int)nitems, stage_doubles, nbuf);
   time_end(L, KF_Q1_GATHER);
   L.count++;
   GDTB_CUDA(cudaGetLastError());
