@@ -26,8 +26,17 @@
 // 1 / h_k, |det J|) and coefficients are evaluated per element on the device in FP64; elements outside the grid get
 // zero factors.  Rows of one work item are consecutive in CSR: the segment is staged in shared memory and leaves the
 // SM as one TMA bulk store, double-buffered, persistent CTAs (as in assemble_q1_gather.cu).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.hpp"
+
+// Single-group sum-factorised kernel: resident blocks per SM the register allocation aims for.  Measured on C5
+// (ms per assembly): 2 blocks x 2 stages 1.90, 3 blocks x 1 stage 1.85, 4 blocks (64 registers, 150 B of spills) x 1 stage
+// 1.76.  The other variants are register-bound at 2 blocks and keep two stages.
+#ifndef Q2G_MIN_BLOCKS
+#define Q2G_MIN_BLOCKS 4
+#endif
 
 namespace gdtb {
 
@@ -53,6 +62,11 @@ __device__ __forceinline__ void q2_bulk_commit()
 __device__ __forceinline__ void q2_bulk_wait_read1()
 {
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
+__device__ __forceinline__ void q2_bulk_wait_read0()
+{
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 __device__ __forceinline__ void q2_bulk_wait0()
@@ -486,7 +500,7 @@ __device__ __forceinline__ void q2_sf_group(const Q2GatherParams& p, const int g
   }
 }
 
-template <int D, int SX, int SY, int SL>
+template <int D, int SX, int SY, int SL, bool NG1>
 __device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const int cx, const int cy, const int cl,
                                                 const int slot, double* __restrict__ row)
 {
@@ -507,9 +521,11 @@ __device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const i
 
   double acc[AY][AX];
   q2_sf_group<D, AX, AY, true>(p, 0, px, py, pl, slot, acc);
+  if (!NG1) { // one group (the common case) lets the compiler sink the arithmetic to the stores: fewer live registers
 #pragma unroll 1
-  for (int gi = 1; gi < p.n_groups; ++gi)
-    q2_sf_group<D, AX, AY, false>(p, gi, px, py, pl, slot, acc);
+    for (int gi = 1; gi < p.n_groups; ++gi)
+      q2_sf_group<D, AX, AY, false>(p, gi, px, py, pl, slot, acc);
+  }
 
   // parity of the lattice point at box offset a is a & 1 (S + R = 2 for both parities); the column groups of a row
   // come in ascending global index (codim ascending, shift ascending), each lexicographic with x fastest
@@ -588,19 +604,22 @@ __device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const i
   }
 }
 
-template <bool SF, int D, int SX, int SY, int SL>
+template <int SF, int D, int SX, int SY, int SL>
 __device__ __forceinline__ void q2_dispatch(const Q2GatherParams& p, const int cx, const int cy, const int cl,
                                             const int slot, double* __restrict__ row)
 {
-  if (SF)
-    q2_row_plane_sf<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
+  if (SF == 2)
+    q2_row_plane_sf<D, SX, SY, SL, true>(p, cx, cy, cl, slot, row);
+  else if (SF == 1)
+    q2_row_plane_sf<D, SX, SY, SL, false>(p, cx, cy, cl, slot, row);
   else
     q2_row_plane<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
 }
 
-template <int D, bool ACCUMULATE, bool SF>
-__global__ void __launch_bounds__(Q2G_THREADS, 2)
-    k_q2_gather(const __grid_constant__ Q2GatherParams p, double* __restrict__ values, int stage_doubles)
+// SF: 0 per-element coefficients, 1 sum-factorised (constant coefficients), 2 sum-factorised with a single group
+template <int D, bool ACCUMULATE, int SF>
+__global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : 2)
+    k_q2_gather(const __grid_constant__ Q2GatherParams p, double* __restrict__ values, int stage_doubles, int nbuf)
 {
   extern __shared__ __align__(16) double smem[];
   const GridDev& g = p.g;
@@ -676,10 +695,13 @@ __global__ void __launch_bounds__(Q2G_THREADS, 2)
         if (head + body < seg)
           values[start + head + body] = stage[head + body];
         q2_bulk_commit();
-        q2_bulk_wait_read1();
+        if (nbuf == 1)
+          q2_bulk_wait_read0();
+        else
+          q2_bulk_wait_read1();
       }
       __syncthreads();
-      buf ^= 1;
+      buf = nbuf == 1 ? 0 : buf ^ 1;
     }
   }
   if (!ACCUMULATE && threadIdx.x == 0)
@@ -794,12 +816,19 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
   // (5 slots: rows up to 5^d entries, 51 rows; 3 slots: rows up to 3 * 5^(d-1), 85 rows)
   const int seg5 = (Q2G_THREADS / 5) * max_row, seg3 = (Q2G_THREADS / 3) * (max_row / 5 * 3);
   const int stage_doubles = ((std::max(seg5, seg3) + 2) + 1) & ~1;
-  const size_t smem = (size_t)(accumulate ? 1 : 2) * stage_doubles * sizeof(double);
-  auto kern = d == 3 ? (accumulate ? k_q2_gather<3, true, false> : k_q2_gather<3, false, false>)
-                     : (accumulate ? k_q2_gather<2, true, false> : k_q2_gather<2, false, false>);
+  static const int nbuf_env = std::getenv("GDTB_Q2_NBUF") ? std::atoi(std::getenv("GDTB_Q2_NBUF")) : 0;
+  const bool single_group = p.sf && p.n_groups == 1;
+  const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : (single_group ? 1 : 2));
+  const size_t smem = (size_t)nbuf * stage_doubles * sizeof(double);
+  auto kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 0> : k_q2_gather<3, false, 0>)
+                     : (accumulate ? k_q2_gather<2, true, 0> : k_q2_gather<2, false, 0>);
   if (p.sf) {
-    kern = d == 3 ? (accumulate ? k_q2_gather<3, true, true> : k_q2_gather<3, false, true>)
-                  : (accumulate ? k_q2_gather<2, true, true> : k_q2_gather<2, false, true>);
+    if (p.n_groups == 1)
+      kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 2> : k_q2_gather<3, false, 2>)
+                    : (accumulate ? k_q2_gather<2, true, 2> : k_q2_gather<2, false, 2>);
+    else
+      kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 1> : k_q2_gather<3, false, 1>)
+                    : (accumulate ? k_q2_gather<2, true, 1> : k_q2_gather<2, false, 1>);
     long long off = 0;
     for (int k = 0; k < d; ++k) {
       p.sf_axis_off[k] = off;
@@ -822,7 +851,7 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
     k_q2_axis_tables<<<(unsigned)((work + 127) / 128), 128, 0, L.stream>>>(p, const_cast<double*>(p.sf_tab));
     L.count++;
   }
-  kern<<<(unsigned)grid, Q2G_THREADS, smem, L.stream>>>(p, values, stage_doubles);
+  kern<<<(unsigned)grid, Q2G_THREADS, smem, L.stream>>>(p, values, stage_doubles, nbuf);
   time_end(L, KF_Q2_GATHER);
   L.count++;
   GDTB_CUDA(cudaGetLastError());
