@@ -958,7 +958,7 @@ int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* a
     op->nnz_local = 1;
     for (int k = 0; k < op->grid.d; ++k)
       op->nnz_local *= 3 * op->grid.n[k] + 1;
-  } else { // CG Q2 element stencil: prod_k (4 n_k + 1) lattice couplings
+  } else { // CG Q2 element stencil: prod_k (8 n_k + 1) lattice couplings
     Q2SlabRange ranges[8];
     const int nr = q2_slab_ranges(op->grid, op->test, ranges);
     op->nnz_local = 0;
