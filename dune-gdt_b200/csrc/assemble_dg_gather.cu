@@ -17,6 +17,8 @@
 // per row, colidx never.  A work item is a run of consecutive rows = one contiguous CSR segment, staged in shared
 // memory and written by a TMA bulk store (double-buffered, persistent CTAs), like the CG gather kernels.
 #include <cstdlib>
+#include <cstring>
+#include <string>
 
 #include "common.cuh"
 #include "kernels.hpp"
@@ -826,6 +828,90 @@ int launch_dg_gather(Launch& L, const DgGatherParams& p, double* values, bool ac
     case 22: return launch_dg_gather_dk<2, 2>(L, p, values, accumulate);
     default: return fail(GDTB_ERR_NOT_IMPLEMENTED, "dg_gather: unsupported (dimension, order)");
   }
+}
+
+// ---- closed-form sparsity pattern of the DG element_and_intersection stencil (non-periodic grid) --------------------
+// One thread per row (element e, local DoF i): blocks of nloc columns per existing neighbour in ascending element index
+// (z-, y-, x-, e, x+, y+, z+), row starts from dg_blocks_before.
+namespace {
+
+template <int D>
+__global__ void __launch_bounds__(128) k_dg_pattern(const __grid_constant__ DgGatherParams p, int nloc,
+                                                     long long* __restrict__ rowptr, int* __restrict__ colidx)
+{
+  const GridDev& g = p.g;
+  const long long rows = g.ne * nloc;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= rows; r += (long long)gridDim.x * blockDim.x) {
+    const long long e = r == rows ? g.ne - 1 : r / nloc;
+    const int i = r == rows ? nloc : int(r - e * nloc);
+    int idx[3];
+    dg_decode<D>(p, (unsigned)e, idx);
+    const int nb = dg_nblocks<D>(g, idx);
+    const long long start = (long long)nloc * nloc * dg_blocks_before<D>(g, e, idx) + (long long)i * nb * nloc;
+    rowptr[r] = start;
+    if (r == rows)
+      continue;
+    int* out = colidx + start;
+    const long long stride[3] = {1, g.n[0], g.n[0] * g.n[1]};
+#pragma unroll
+    for (int k = D - 1; k >= 0; --k)
+      if (idx[k] > 0)
+        for (int j = 0; j < nloc; ++j)
+          *out++ = (int)((e - stride[k]) * nloc + j);
+    for (int j = 0; j < nloc; ++j)
+      *out++ = (int)(e * nloc + j);
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      if (idx[k] < g.n[k] - 1)
+        for (int j = 0; j < nloc; ++j)
+          *out++ = (int)((e + stride[k]) * nloc + j);
+  }
+}
+
+} // namespace
+
+int pattern_structured_dg(Launch& L, const GridDev& g, const SpaceDev& sp, long long** d_rowptr, int** d_colidx,
+                          long long* nnz_out)
+{
+  if (g.periodic)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "structured DG pattern: non-periodic grids only");
+  if (sp.size >= (1LL << 31) || g.ne >= (1LL << 31))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "structured DG pattern: more than 2^31 degrees of freedom");
+  const int nloc = sp.nloc;
+  long long blocks = g.ne; // element blocks + one block per (element, existing neighbour)
+  for (int k = 0; k < g.d; ++k)
+    blocks += 2 * (g.ne / g.n[k]) * (g.n[k] - 1);
+  const long long nnz = blocks * nloc * nloc;
+  DgGatherParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.sp = sp;
+  for (int k = 0; k < 2; ++k)
+    p.magic[k] = g.n[k] > 1 ? ~0ULL / (unsigned long long)g.n[k] + 1 : 0;
+  long long* rowptr = nullptr;
+  int* colidx = nullptr;
+  if (cudaMalloc(&rowptr, sizeof(long long) * (size_t)(sp.size + 1)) != cudaSuccess
+      || cudaMalloc(&colidx, sizeof(int) * (size_t)nnz) != cudaSuccess) {
+    cudaFree(rowptr);
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "pattern: out of device memory");
+  }
+  const unsigned grid = (unsigned)std::min<long long>((sp.size + 1 + 127) / 128, (long long)L.sm_count * 64);
+  switch (g.d) {
+    case 1: k_dg_pattern<1><<<grid, 128, 0, L.stream>>>(p, nloc, rowptr, colidx); break;
+    case 2: k_dg_pattern<2><<<grid, 128, 0, L.stream>>>(p, nloc, rowptr, colidx); break;
+    default: k_dg_pattern<3><<<grid, 128, 0, L.stream>>>(p, nloc, rowptr, colidx); break;
+  }
+  L.count++;
+  cudaError_t err = cudaStreamSynchronize(L.stream);
+  if (err != cudaSuccess) {
+    cudaFree(rowptr);
+    cudaFree(colidx);
+    return fail(GDTB_ERR_CUDA, std::string("k_dg_pattern: ") + cudaGetErrorString(err));
+  }
+  *d_rowptr = rowptr;
+  *d_colidx = colidx;
+  *nnz_out = nnz;
+  return GDTB_OK;
 }
 
 } // namespace gdtb

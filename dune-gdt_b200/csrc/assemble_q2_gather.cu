@@ -27,6 +27,8 @@
 // zero factors.  Rows of one work item are consecutive in CSR: the segment is staged in shared memory and leaves the
 // SM as one TMA bulk store, double-buffered, persistent CTAs (as in assemble_q1_gather.cu).
 #include <cstdlib>
+#include <cstring>
+#include <string>
 
 #include "common.cuh"
 #include "kernels.hpp"
@@ -855,6 +857,154 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
   time_end(L, KF_Q2_GATHER);
   L.count++;
   GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+// ---- closed-form sparsity pattern of the CG Q2 element stencil ------------------------------------------------------
+// One thread per row: the columns of a row are the lattice points of its clipped coupling box, grouped by parity pattern
+// in ascending global index (codim ascending, shift ascending) and lexicographic inside a group -- written in that
+// order they are the sorted, duplicate-free row the sort-and-unique builder produces (tests compare both with the oracle).
+namespace {
+
+struct Q2PatternParams
+{
+  GridDev g;
+  int n_rowgroups;
+  Q2RowGroup rg[8];
+  long long group_row_begin[8]; // by parity pattern s
+};
+
+template <int D>
+__global__ void __launch_bounds__(128) k_q2_pattern(const __grid_constant__ Q2PatternParams p, long long rows,
+                                                     long long* __restrict__ rowptr, int* __restrict__ colidx,
+                                                     long long nnz)
+{
+  const GridDev& g = p.g;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= rows; r += (long long)gridDim.x * blockDim.x) {
+    if (r == rows) {
+      rowptr[rows] = nnz;
+      continue;
+    }
+    int gi = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      if (k < p.n_rowgroups && r >= p.rg[k].row_begin)
+        gi = k;
+    const Q2RowGroup& rg = p.rg[gi];
+    const int s = rg.s;
+    int c[3];
+    q2_decode<D>(rg, (unsigned)(r - rg.row_begin), c[0], c[1], c[2]);
+    const long long start = rg.value_begin + q2_row_offset<D>(g, rg, c[0], c[1], c[2]);
+    rowptr[r] = start;
+    // clipped coupling box per axis in lattice coordinates
+    int qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
+    const int cc[3] = {c[0], D == 3 ? c[1] : c[2], c[2]}; // axis order x, y (2D: last), z
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const int S = (s >> k) & 1, R = S ? 1 : 2, pk = 2 * cc[k] + S;
+      qlo[k] = max(0, pk - R);
+      qhi[k] = min(2 * (int)g.n[k], pk + R);
+    }
+    int* out = colidx + start;
+    for (int rank = 0; rank < (1 << D); ++rank) {
+      const int sq = q2_group_order(D, rank);
+      // first lattice value of the group's parity inside the box, per axis
+      int f[3] = {0, 0, 0};
+      bool empty = false;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const int par = (sq >> k) & 1;
+        f[k] = qlo[k] + ((qlo[k] ^ par) & 1);
+        empty = empty || f[k] > qhi[k];
+      }
+      if (empty)
+        continue;
+      const long long ex = (sq & 1) ? g.n[0] : g.n[0] + 1;
+      const long long ey = D == 3 ? ((sq & 2) ? g.n[1] : g.n[1] + 1) : ((sq & 2) ? g.n[1] : g.n[1] + 1);
+      const long long base = p.group_row_begin[sq];
+      if (D == 3) {
+        for (int qz = f[2]; qz <= qhi[2]; qz += 2)
+          for (int qy = f[1]; qy <= qhi[1]; qy += 2)
+            for (int qx = f[0]; qx <= qhi[0]; qx += 2)
+              *out++ = (int)(base + (qx >> 1) + ex * ((qy >> 1) + ey * (long long)(qz >> 1)));
+      } else {
+        for (int qy = f[1]; qy <= qhi[1]; qy += 2)
+          for (int qx = f[0]; qx <= qhi[0]; qx += 2)
+            *out++ = (int)(base + (qx >> 1) + ex * (long long)(qy >> 1));
+      }
+    }
+  }
+}
+
+} // namespace
+
+int pattern_structured_cg_q2(Launch& L, const GridDev& g, const SpaceDev& sp, long long** d_rowptr, int** d_colidx,
+                             long long* nnz_out)
+{
+  const int d = g.d;
+  if (d != 2 && d != 3)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "structured Q2 pattern: 2D and 3D grids only");
+  // reuse the row-group setup of the gather kernel on the whole grid
+  Q2GatherParams gp;
+  std::memset(&gp, 0, sizeof(gp));
+  gp.g = g;
+  gp.g.layer_lo = 0;
+  gp.g.layer_hi = g.n[d - 1];
+  Q2PatternParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.g = gp.g;
+  Q2SlabRange ranges[8];
+  p.n_rowgroups = q2_slab_ranges(gp.g, sp, ranges);
+  long long nnz = 0;
+  {
+    int r = 0;
+    for (int c = 0; c <= d; ++c)
+      for (int s = 0; s < (1 << d); ++s) {
+        int pc = 0;
+        for (int k = 0; k < d; ++k)
+          pc += (s >> k) & 1;
+        if (pc != d - c)
+          continue;
+        Q2RowGroup& rg = p.rg[r];
+        rg.s = s;
+        rg.row_begin = ranges[r].row_begin;
+        rg.rows = ranges[r].row_end - ranges[r].row_begin;
+        rg.ex = (unsigned)((s & 1) ? g.n[0] : g.n[0] + 1);
+        rg.ey = d == 3 ? (unsigned)((s & 2) ? g.n[1] : g.n[1] + 1) : 1u;
+        rg.mex = rg.ex > 1 ? ~0ULL / rg.ex + 1 : 0;
+        rg.mey = rg.ey > 1 ? ~0ULL / rg.ey + 1 : 0;
+        rg.Tx = (unsigned)q2_axis_total(s & 1, g.n[0]);
+        rg.TxTy = (long long)rg.Tx * (d == 3 ? q2_axis_total((s >> 1) & 1, g.n[1]) : 1);
+        rg.value_begin = ranges[r].value_offset;
+        p.group_row_begin[s] = ranges[r].row_begin;
+        nnz += ranges[r].count;
+        ++r;
+      }
+  }
+  if (sp.size >= (1LL << 31))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "structured Q2 pattern: more than 2^31 degrees of freedom");
+  long long* rowptr = nullptr;
+  int* colidx = nullptr;
+  if (cudaMalloc(&rowptr, sizeof(long long) * (size_t)(sp.size + 1)) != cudaSuccess
+      || cudaMalloc(&colidx, sizeof(int) * (size_t)nnz) != cudaSuccess) {
+    cudaFree(rowptr);
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "pattern: out of device memory");
+  }
+  const unsigned grid = (unsigned)std::min<long long>((sp.size + 1 + 127) / 128, (long long)L.sm_count * 64);
+  if (d == 3)
+    k_q2_pattern<3><<<grid, 128, 0, L.stream>>>(p, sp.size, rowptr, colidx, nnz);
+  else
+    k_q2_pattern<2><<<grid, 128, 0, L.stream>>>(p, sp.size, rowptr, colidx, nnz);
+  L.count++;
+  cudaError_t err = cudaStreamSynchronize(L.stream);
+  if (err != cudaSuccess) {
+    cudaFree(rowptr);
+    cudaFree(colidx);
+    return fail(GDTB_ERR_CUDA, std::string("k_q2_pattern: ") + cudaGetErrorString(err));
+  }
+  *d_rowptr = rowptr;
+  *d_colidx = colidx;
+  *nnz_out = nnz;
   return GDTB_OK;
 }
 

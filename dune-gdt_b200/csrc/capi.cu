@@ -849,10 +849,19 @@ int gdtb_pattern_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space*
     return fail(GDTB_ERR_INVALID_ARGUMENT, "Unknown Stencil encountered"); // sparsity-pattern.hh:174-177
   if (std::memcmp(&test->grid, &ansatz->grid, sizeof(GridDev)) != 0)
     return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "test and ansatz space live on different grids");
-  const bool structured_ok =
+  const bool same_space = std::memcmp(&test->dev, &ansatz->dev, sizeof(SpaceDev)) == 0;
+  const bool structured_q1 =
       stencil == GDTB_STENCIL_ELEMENT && q1_space(test->dev) && q1_space(ansatz->dev) && !test->grid.periodic;
+  const bool structured_q2 = stencil == GDTB_STENCIL_ELEMENT && same_space && test->dev.kind == GDTB_SPACE_CG
+                             && test->dev.K == 2 && (test->grid.d == 2 || test->grid.d == 3) && !test->grid.periodic
+                             && test->dev.size < (1LL << 31);
+  const bool structured_dg = stencil == GDTB_STENCIL_ELEMENT_AND_INTERSECTION && same_space
+                             && test->dev.kind == GDTB_SPACE_DG && !test->grid.periodic && test->dev.size < (1LL << 31);
+  const bool structured_ok = structured_q1 || structured_q2 || structured_dg;
   if (method == GDTB_PATTERN_STRUCTURED && !structured_ok)
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "structured pattern generator only covers the CG Q1 element stencil");
+    return fail(GDTB_ERR_NOT_IMPLEMENTED,
+                "structured pattern generators cover the CG Q1 / Q2 element stencils and the DG element_and_intersection "
+                "stencil on non-periodic grids");
   auto p = std::make_unique<gdtb_pattern>();
   p->ctx = ctx;
   p->grid = test->grid;
@@ -864,8 +873,12 @@ int gdtb_pattern_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space*
   p->d_rowptr = nullptr;
   p->d_colidx = nullptr;
   const bool use_structured = method == GDTB_PATTERN_STRUCTURED || (method == GDTB_PATTERN_AUTO && structured_ok);
-  if (use_structured)
+  if (use_structured && structured_q1)
     GDTB_TRY(pattern_structured_cg_q1(ctx->launch, p->grid, p->test, &p->d_rowptr, &p->d_colidx, &p->nnz));
+  else if (use_structured && structured_q2)
+    GDTB_TRY(pattern_structured_cg_q2(ctx->launch, p->grid, p->test, &p->d_rowptr, &p->d_colidx, &p->nnz));
+  else if (use_structured)
+    GDTB_TRY(pattern_structured_dg(ctx->launch, p->grid, p->test, &p->d_rowptr, &p->d_colidx, &p->nnz));
   else
     GDTB_TRY(
         pattern_sort_unique(ctx->launch, p->grid, p->test, p->ansatz, stencil, &p->d_rowptr, &p->d_colidx, &p->nnz));

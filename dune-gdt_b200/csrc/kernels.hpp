@@ -233,6 +233,13 @@ int pattern_sort_unique(Launch& L, const GridDev& g, const SpaceDev& test, const
                         long long** d_rowptr, int** d_colidx, long long* nnz);
 int pattern_structured_cg_q1(Launch& L, const GridDev& g, const SpaceDev& sp, long long** d_rowptr, int** d_colidx,
                              long long* nnz);
+// closed-form generators of the other two gather paths (same CSR the sort-and-unique builder produces):
+// CG Q2 element stencil on the lattice numbering (assemble_q2_gather.cu), DG element_and_intersection stencil on a
+// non-periodic grid (assemble_dg_gather.cu)
+int pattern_structured_cg_q2(Launch& L, const GridDev& g, const SpaceDev& sp, long long** d_rowptr, int** d_colidx,
+                             long long* nnz);
+int pattern_structured_dg(Launch& L, const GridDev& g, const SpaceDev& sp, long long** d_rowptr, int** d_colidx,
+                          long long* nnz);
 
 // ---- finite volumes (fv.cu) -----------------------------------------------------------------------
 struct FvParams

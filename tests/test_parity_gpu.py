@@ -108,6 +108,34 @@ def test_pattern_bit_exact_structured_q1(gdt, ctx, oracle, n):
     assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
 
 
+@pytest.mark.parametrize("n", [[1, 1], [9, 2], [2, 5], [1, 1, 1], [4, 3, 2], [1, 3, 2], [3, 1, 1], [2, 2, 5]])
+def test_pattern_bit_exact_structured_q2(gdt, ctx, oracle, n):
+    """closed-form CG Q2 element stencil on the MCMG lattice numbering == the reference's insert + sort (oracle)"""
+    gdesc = D.grid_desc(0.0, 1.0, n)
+    space = make_space(gdt, ctx, gdesc, CG, 2)
+    rowptr, colidx = gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT, D.PATTERN_STRUCTURED).download()
+    rp, ci = oracle.pattern(gdesc, (CG, 2))
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+
+
+@pytest.mark.parametrize("n,order", [([1], 1), ([7], 1), ([7], 2), ([1, 1], 1), ([6, 5], 1), ([1, 4], 1), ([3, 4], 2), ([1, 1, 1], 1),
+                                     ([4, 3, 3], 1), ([2, 1, 3], 1), ([2, 2, 2], 2), ([5, 4], 0)])
+def test_pattern_bit_exact_structured_dg(gdt, ctx, oracle, n, order):
+    """closed-form DG element_and_intersection stencil (blocks by ascending neighbour index) == the oracle"""
+    gdesc = D.grid_desc(0.0, 1.0, n)
+    space = make_space(gdt, ctx, gdesc, DG, order)
+    rowptr, colidx = gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT_AND_INTERSECTION, D.PATTERN_STRUCTURED).download()
+    rp, ci = oracle.pattern(gdesc, (DG, order), stencil=D.STENCIL_ELEMENT_AND_INTERSECTION)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+
+
+def test_structured_pattern_limits(gdt, ctx):
+    space = make_space(gdt, ctx, D.grid_desc(0.0, 1.0, [4, 4], 3), DG, 1)
+    with pytest.raises(gdt.capi.NotImplementedGdt):  # periodic grids go through sort-and-unique
+        gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT_AND_INTERSECTION, D.PATTERN_STRUCTURED)
+    gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT_AND_INTERSECTION, D.PATTERN_AUTO)
+
+
 def test_pattern_c1_size(gdt, ctx):
     # C1: 2D Q1 128^2: 16641 DoFs, 148225 nnz (SURVEY section 8)
     space = make_space(gdt, ctx, D.grid_desc(-1.0, 1.0, [128, 128]), CG, 1)
