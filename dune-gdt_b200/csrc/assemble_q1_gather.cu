@@ -375,8 +375,45 @@ __global__ void __launch_bounds__(Q1G_ROWS, Q1G_MIN_BLOCKS)
             }
           }
         }
+        // Constant kappa = c I (the headline configuration): the sum over the 8 cells factorises as well.  Per axis
+        // the row couples to the offsets d = -1, 0, +1 through K^k[d] = sum_cells K1[.][.] / h_k and
+        // M^k[d] = sum_cells M1[.][.] h_k (1D tables of the form's rule; the vertex is node 1 of the lower and node 0 of
+        // the upper cell) and the stencil is c (K^x M^y M^z + M^x K^y M^z + M^x M^y K^z): 3 FP64 instructions per entry
+        // instead of 8.  Cells outside the grid / slab carry h = 1/h = 0 and drop out.
+        const bool sf3 = LAP3 && want_values && !(CELLDATA && p.group[0].coef_elem);
+        if (sf3) {
+          const Q1Group& G = p.group[0];
+          double Kv[3][3], Mv[3][3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const double sc = k == 0 ? G.scale : 1.;
+            Kv[k][0] = sc * (hb[k][0] * G.K1[1][0]);
+            Kv[k][1] = sc * fma(hb[k][0], G.K1[1][1], hb[k][1] * G.K1[0][0]);
+            Kv[k][2] = sc * (hb[k][1] * G.K1[0][1]);
+            Mv[k][0] = sc * (ha[k][0] * G.M1[1][0]);
+            Mv[k][1] = sc * fma(ha[k][0], G.M1[1][1], ha[k][1] * G.M1[0][0]);
+            Mv[k][2] = sc * (ha[k][1] * G.M1[0][1]);
+          }
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz) {
+            if ((dz == 0 && !cz0) || (dz == 2 && !cz1))
+              continue;
+            double Pl[9];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const double A = Mv[1][dy] * Mv[2][dz];
+              const double B = fma(Kv[1][dy], Mv[2][dz], Mv[1][dy] * Kv[2][dz]);
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx)
+                Pl[3 * dy + dx] = fma(Kv[0][dx], A, Mv[0][dx] * B);
+            }
+            row += q1_store_plane<9>(row, Pl, full_xy, cx0, cx1, cy0, cy1);
+          }
+        }
 #pragma unroll
         for (int oz = 0; oz < 2; ++oz) {
+          if (sf3 && (!CELLDATA || (!p.rhs_has_const && !p.rhs_has_elem)))
+            break;
 #pragma unroll
           for (int oxy = 0; oxy < 4; ++oxy) {
             const int ox = oxy & 1, oy = oxy >> 1;
@@ -384,7 +421,7 @@ __global__ void __launch_bounds__(Q1G_ROWS, Q1G_MIN_BLOCKS)
             const double b[3] = {hb[0][ox], hb[1][oy], hb[2][oz]};
             const bool valid = vk[0][ox] && vk[1][oy] && vk[2][oz];
             const long long e = CELLDATA ? e0 + ox + (long long)Nx * (oy + (long long)Ny * oz) : 0;
-            if (want_values) {
+            if (want_values && !sf3) {
               if (LAP3) {
                 // scheduling fence: keeps the weights of the 8 cells from being formed all at once (register pressure)
                 double t0 = yz_aa[oy][oz];
@@ -408,7 +445,7 @@ __global__ void __launch_bounds__(Q1G_ROWS, Q1G_MIN_BLOCKS)
             if (p.rhs_has_elem)
               bsum = fma(ie * p.rhs_S_elem[ox + 2 * oy + 4 * oz], valid ? __ldg(p.rhs_elem + e) : 0., bsum);
           }
-          if (want_values) {
+          if (want_values && !sf3) {
             if (oz == 0) {
               if (cz0)
                 row += q1_store_plane<9>(row, P[0], full_xy, cx0, cx1, cy0, cy1);

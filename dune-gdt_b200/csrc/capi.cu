@@ -536,6 +536,11 @@ int build_q1_params(gdtb_matop* op, gdtb_vecfun* fun, Q1GatherParams& p)
       for (int t = 0; t < lf.form.n_terms; ++t) {
         const gdtb_integrand& in = lf.form.terms[t];
         Q1Group& G = p.group[p.n_groups++];
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            G.K1[a][b] = tab.G[1][1][a][b];
+            G.M1[a][b] = tab.G[0][0][a][b];
+          }
         const gdtb_function& f = in.diffusion;
         G.scale = lf.form.scaling;
         G.coef = f.data;

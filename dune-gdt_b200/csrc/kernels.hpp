@@ -90,6 +90,7 @@ struct Q1Group
   const double* coef; // device array
   double M[9][8][8];  // M[r*3+c][o][s]: o = offset of the element around the vertex (test index i = (2^d-1) ^ o),
                       // s = ansatz index; the scalar kinds only use r == c, the mass kind only M[0]
+  double K1[2][2], M1[2][2]; // 1D reference stiffness / mass tables of the form's rule (sum-factorised constant path)
 };
 
 // exact unsigned division v / d for v < 2^31: (v * magic) >> shift
