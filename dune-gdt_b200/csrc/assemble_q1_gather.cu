@@ -270,7 +270,7 @@ __device__ __forceinline__ int q1_store_plane(double* __restrict__ row, const do
 // CELLDATA = false: no per-element coefficient / source arrays and no per-cell right-hand-side terms are in play
 // (constant coefficients, separable analytic source): the element index is never formed.
 template <int D, int NG, int KIND0, bool ACCUMULATE, bool CELLDATA>
-__global__ void __launch_bounds__(Q1G_ROWS, Q1G_MIN_BLOCKS)
+__global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLACE_SCALAR && !CELLDATA) ? Q1G_MIN_BLOCKS : 2)
     k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values, double* __restrict__ rhs,
                 long long nrows, int nitems, int stage_doubles, int nbuf)
 {
@@ -662,8 +662,10 @@ static int launch_q1_gather_dn(Launch& L, const Q1GatherParams& p, double* value
   bool celldata = rhs && p.has_rhs && (p.rhs_has_const || p.rhs_has_elem);
   for (int g = 0; g < (values ? p.n_groups : 0); ++g)
     celldata = celldata || p.group[g].coef_elem;
-  // The variant without the per-cell code paths measures SLOWER on B200 (0.788 vs 0.719 ms on C2: straight-line code
-  // lets ptxas keep more values live and it spills), so it is opt-in for experiments only.
+  // The variant without the per-cell code paths measures SLOWER on B200 and is opt-in for experiments only.  Before the
+  // sum-factorised path: 0.788 vs 0.719 ms on C2.  With it (the lean kernel then is the pure sum-factorised one, 106
+  // registers): 0.612 ms at 2 blocks x 2 stages, 0.579 at 2 x 1, 0.604 at 3 blocks (80 registers) x 1, 0.640 at 4 blocks
+  // (64 registers) x 1 -- against 0.565 ms for the default build.
   static const bool allow_lean = std::getenv("GDTB_Q1_LEAN") != nullptr;
   celldata = celldata || !allow_lean;
   return celldata ? launch_q1_gather_dnc<D, NG, KIND0, true>(L, p, values, rhs, accumulate)
