@@ -555,8 +555,12 @@ int matop_pattern(gdtb_matop* op, const long long** rowptr, const int** colidx)
     return GDTB_OK;
   }
   if (!op->d_own_rowptr) {
+    // pattern-free operators exist for the CG Q1 and CG Q2 element stencils: materialise the closed-form pattern
     long long nnz = 0;
-    GDTB_TRY(pattern_structured_cg_q1(op->ctx->launch, op->grid, op->test, &op->d_own_rowptr, &op->d_own_colidx, &nnz));
+    if (op->test.K == 2)
+      GDTB_TRY(pattern_structured_cg_q2(op->ctx->launch, op->grid, op->test, &op->d_own_rowptr, &op->d_own_colidx, &nnz));
+    else
+      GDTB_TRY(pattern_structured_cg_q1(op->ctx->launch, op->grid, op->test, &op->d_own_rowptr, &op->d_own_colidx, &nnz));
   }
   *rowptr = op->d_own_rowptr;
   *colidx = op->d_own_colidx;

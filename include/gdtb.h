@@ -261,7 +261,7 @@ enum
 {
   GDTB_PATTERN_AUTO = 0,        /* structured closed form when available, else sort-unique */
   GDTB_PATTERN_SORT_UNIQUE = 1, /* emit (row,col) keys per element/intersection, radix sort, unique, CSR */
-  GDTB_PATTERN_STRUCTURED = 2   /* closed-form tensor-product stencil generator */
+  GDTB_PATTERN_STRUCTURED = 2   /* closed-form generators: CG Q1 / Q2 element stencil, DG element_and_intersection */
 };
 /* replaces make_sparsity_pattern(test, ansatz, view, stencil) (tools/sparsity-pattern.hh:163-178) */
 int gdtb_pattern_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* ansatz, int stencil, int method,
@@ -275,8 +275,9 @@ int gdtb_pattern_device(const gdtb_pattern* pattern, const int64_t** d_rowptr, c
 
 /* ---- MatrixOperator (operators/matrix-based.hh:245-508) -------------------------------------- */
 /* make_matrix_operator<M>(view, source_space, range_space, pattern) (matrix-based.hh:514-598):
- * rows = range/test space, cols = source/ansatz space.  `pattern` may be NULL for continuous Q1 spaces: their
- * element stencil has a closed form, the values then follow the layout gdtb_pattern_create would produce. */
+ * rows = range/test space, cols = source/ansatz space.  `pattern` may be NULL for continuous Q1 and Q2 spaces on
+ * non-periodic grids: their element stencils have closed forms, the values then follow the layout
+ * gdtb_pattern_create would produce (the pattern is materialised only if a later call needs colidx). */
 int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* ansatz, const gdtb_pattern* pattern,
                       gdtb_matop** op);
 int gdtb_matop_destroy(gdtb_matop* op);

@@ -603,4 +603,14 @@ def test_q2_pattern_free_operator_matches_pattern_based(gdt, ctx, oracle):
     check(lib.gdtb_matop_values_download(op_h, gdt.capi.dptr(v)))
     ref_v, _ = oracle.assemble(gdesc, CG, 2, rp, ci, [f])
     assert rel_err(v, ref_v) <= TOL
+    # the closed-form pattern is materialised on demand (mat-vec, constraints, solvers): same CSR as the oracle's
+    import scipy.sparse as sp
+
+    d_rp, d_ci = C.c_void_p(), C.c_void_p()
+    check(lib.gdtb_matop_pattern_device(op_h, C.byref(d_rp), C.byref(d_ci)))
+    x = np.random.default_rng(SEED).uniform(-1.0, 1.0, rp.size - 1)
+    y = np.empty_like(x)
+    check(lib.gdtb_matop_apply_host(op_h, gdt.capi.dptr(x), gdt.capi.dptr(y)))
+    A = sp.csr_matrix((ref_v, ci, rp), shape=(rp.size - 1, rp.size - 1))
+    assert rel_err(y, A @ x) <= TOL
     lib.gdtb_matop_destroy(op_h)
