@@ -156,6 +156,9 @@ PROTOTYPES = {
     "gdtb_rk_step_host": (C.c_int, [_P, _DP, C.c_double, C.c_double, _DP]),
     "gdtb_rk_solve": (C.c_int, [_P, _P, C.c_double, C.c_double, _I64P, _DP]),
     "gdtb_rk_solve_host": (C.c_int, [_P, _DP, C.c_double, C.c_double, _I64P, _DP]),
+    "gdtb_rk_p2p_handles": (C.c_int, [_P, _PP, _P]),
+    "gdtb_rk_p2p_connect": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int]),
+    "gdtb_rk_p2p_check": (C.c_int, [_P]),
     "gdtb_fv_interpolate": (C.c_int, [_P, _P, C.POINTER(Function), _P]),
     "gdtb_fv_interpolate_host": (C.c_int, [_P, _P, C.POINTER(Function), _DP]),
     # callers on either side of the hot path

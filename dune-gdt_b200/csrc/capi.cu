@@ -1775,6 +1775,7 @@ static void fv_fill_params(const gdtb_fvop* L, FvParams& p)
   p.apply_lo = L->grid.layer_lo;
   p.apply_hi = L->grid.layer_hi;
   p.p2p = 0;
+  p.wait_lo = p.wait_hi = 0;
   p.peer_lo_ghost = p.peer_hi_ghost = nullptr;
   p.peer_lo_flag = p.peer_hi_flag = nullptr;
   p.my_flags = nullptr;
@@ -1958,6 +1959,8 @@ int gdtb_fvop_p2p_step(gdtb_fvop* L, int euler, double dt)
     p.peer_hi_ghost = L->p2p_peer_u[1][dst];
     p.peer_hi_flag = L->p2p_peer_flags[1] + 0;
   }
+  p.wait_lo = p.peer_lo_ghost != nullptr;
+  p.wait_hi = p.peer_hi_ghost != nullptr;
   p.my_flags = L->p2p_flags;
   p.timeout_flag = L->p2p_flags + 2;
   p.edge_count = L->p2p_flags + 4;
@@ -2184,10 +2187,9 @@ int gdtb_rk_create(gdtb_fvop* L, int method, int num_stages, const double* A, co
   if (!L || !out)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_create: NULL argument");
   GDTB_TRY(check_ctx(L->ctx));
-  if (L->ghosted)
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "gdtb_rk_create: on a slab drive the stages with gdtb_fvop_step_async and exchange ghost layers in between");
   auto ts = new gdtb_rk();
   ts->op = L;
+  ts->slab = L->ghosted;
   ts->r = r;
   ts->t = t0;
   // internal::ButcherArrayProvider (:63-141)
@@ -2227,9 +2229,20 @@ int gdtb_rk_create(gdtb_fvop* L, int method, int num_stages, const double* A, co
     }
   }
   const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
+  if (ts->slab && (num_stages < 2 || L->grid.d < 2)) {
+    delete ts;
+    return fail(GDTB_ERR_NOT_IMPLEMENTED,
+                "Runge-Kutta stepping on a slab needs >= 2 stages and a 2D / 3D grid (explicit Euler: gdtb_fvop_p2p_step)");
+  }
   bool ok = cudaMalloc(&ts->d_ui, bytes) == cudaSuccess;
   for (int i = 0; ok && i < (num_stages > 1 ? num_stages : 0); ++i)
-    ok = cudaMalloc(&ts->d_k[i], bytes) == cudaSuccess;
+    ok = cudaMalloc(&ts->d_k[i], bytes) == cudaSuccess && cudaMemset(ts->d_k[i], 0, bytes) == cudaSuccess;
+  if (ok && ts->slab) {
+    ok = cudaMalloc(&ts->p2p_un, bytes) == cudaSuccess && cudaMalloc(&ts->p2p_ui[0], bytes) == cudaSuccess
+         && cudaMalloc(&ts->p2p_ui[1], bytes) == cudaSuccess && cudaMalloc(&ts->p2p_flags, 64 * sizeof(int)) == cudaSuccess
+         && cudaMemset(ts->p2p_un, 0, bytes) == cudaSuccess && cudaMemset(ts->p2p_ui[0], 0, bytes) == cudaSuccess
+         && cudaMemset(ts->p2p_ui[1], 0, bytes) == cudaSuccess && cudaMemset(ts->p2p_flags, 0, 64 * sizeof(int)) == cudaSuccess;
+  }
   if (!ok) {
     gdtb_rk_destroy(ts);
     return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (Runge-Kutta stages)");
@@ -2246,8 +2259,184 @@ int gdtb_rk_destroy(gdtb_rk* ts)
   cudaFree(ts->d_ui);
   for (double* k : ts->d_k)
     cudaFree(k);
+  for (int side = 0; side < 2; ++side)
+    if (ts->peer_opened[side])
+      for (void* ptr : {(void*)ts->peer_un[side], (void*)ts->peer_ui[side][0], (void*)ts->peer_ui[side][1], (void*)ts->peer_flags[side]})
+        if (ptr)
+          cudaIpcCloseMemHandle(ptr);
+  cudaFree(ts->p2p_un);
+  cudaFree(ts->p2p_ui[0]);
+  cudaFree(ts->p2p_ui[1]);
+  cudaFree(ts->p2p_flags);
   delete ts;
   return GDTB_OK;
+}
+
+// ---- Runge-Kutta on slabs: stage vectors handed over by peer stores (explicit-rungekutta.hh:252-257) ----------------
+int gdtb_rk_p2p_handles(gdtb_rk* ts, double** d_un, void* handles)
+{
+  if (!ts || !ts->slab || !handles)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_p2p_handles: the stepper was not created on a slab operator");
+  GDTB_TRY(check_ctx(ts->op->ctx));
+  cudaIpcMemHandle_t h[4];
+  void* ptr[4] = {ts->p2p_un, ts->p2p_ui[0], ts->p2p_ui[1], ts->p2p_flags};
+  for (int i = 0; i < 4; ++i)
+    if (cudaIpcGetMemHandle(&h[i], ptr[i]) != cudaSuccess)
+      return fail(GDTB_ERR_CUDA, std::string("cudaIpcGetMemHandle failed: ") + cudaGetErrorString(cudaGetLastError()));
+  std::memcpy(handles, h, sizeof(h));
+  if (d_un)
+    *d_un = ts->p2p_un;
+  return GDTB_OK;
+}
+
+int gdtb_rk_p2p_connect(gdtb_rk* ts, const void* lower_handles, int64_t lower_layers, int lower_is_self,
+                        const void* upper_handles, int64_t upper_layers, int upper_is_self)
+{
+  if (!ts || !ts->slab)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_p2p_connect: the stepper was not created on a slab operator");
+  gdtb_fvop* L = ts->op;
+  GDTB_TRY(check_ctx(L->ctx));
+  const void* hs[2] = {lower_handles, upper_handles};
+  const int self[2] = {lower_is_self, upper_is_self};
+  const int64_t layers[2] = {lower_layers, upper_layers};
+  for (int side = 0; side < 2; ++side) {
+    ts->peer_layers[side] = layers[side];
+    ts->has_peer[side] = false;
+    if (self[side]) {
+      ts->peer_un[side] = ts->p2p_un;
+      ts->peer_ui[side][0] = ts->p2p_ui[0];
+      ts->peer_ui[side][1] = ts->p2p_ui[1];
+      ts->peer_flags[side] = ts->p2p_flags;
+      ts->peer_layers[side] = L->grid.layer_hi - L->grid.layer_lo;
+      ts->has_peer[side] = true;
+      continue;
+    }
+    if (!hs[side])
+      continue;
+    if (side == 1 && hs[0] && !self[0] && std::memcmp(hs[0], hs[1], 4 * GDTB_IPC_HANDLE_BYTES) == 0) {
+      ts->peer_un[1] = ts->peer_un[0];
+      ts->peer_ui[1][0] = ts->peer_ui[0][0];
+      ts->peer_ui[1][1] = ts->peer_ui[0][1];
+      ts->peer_flags[1] = ts->peer_flags[0];
+      ts->has_peer[1] = true;
+      continue;
+    }
+    cudaIpcMemHandle_t h[4];
+    std::memcpy(h, hs[side], sizeof(h));
+    void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 4; ++i)
+      if (cudaIpcOpenMemHandle(&ptr[i], h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        return fail(GDTB_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError()));
+    ts->peer_un[side] = static_cast<double*>(ptr[0]);
+    ts->peer_ui[side][0] = static_cast<double*>(ptr[1]);
+    ts->peer_ui[side][1] = static_cast<double*>(ptr[2]);
+    ts->peer_flags[side] = static_cast<int*>(ptr[3]);
+    ts->peer_opened[side] = true;
+    ts->has_peer[side] = true;
+  }
+  return GDTB_OK;
+}
+
+int gdtb_rk_p2p_check(gdtb_rk* ts)
+{
+  if (!ts || !ts->slab)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_p2p_check: the stepper was not created on a slab operator");
+  GDTB_TRY(check_ctx(ts->op->ctx));
+  int flags[3] = {0, 0, 0};
+  GDTB_CUDA(cudaStreamSynchronize(ts->op->ctx->launch.stream));
+  GDTB_CUDA(cudaMemcpy(flags, ts->p2p_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+  if (flags[2])
+    return fail(GDTB_ERR_OPERATOR, "Runge-Kutta on slabs: a wait for the neighbour's counter timed out");
+  return GDTB_OK;
+}
+
+// which = 0: the solution vector u_n, 1 / 2: the two stage buffers
+static int rk_p2p_send(gdtb_rk* ts, int which)
+{
+  gdtb_fvop* L = ts->op;
+  const long long plane = gdtb_fvop_ghost_layer_size(L);
+  P2pSendParams q;
+  q.src = which == 0 ? ts->p2p_un : ts->p2p_ui[which - 1];
+  q.plane = plane;
+  q.layers = L->grid.layer_hi - L->grid.layer_lo;
+  double* lo = !ts->has_peer[0] ? nullptr : (which == 0 ? ts->peer_un[0] : ts->peer_ui[0][which - 1]);
+  double* hi = !ts->has_peer[1] ? nullptr : (which == 0 ? ts->peer_un[1] : ts->peer_ui[1][which - 1]);
+  q.peer_lo_ghost = lo ? lo + (ts->peer_layers[0] + 1) * plane : nullptr; // the lower neighbour's upper ghost layer
+  q.peer_hi_ghost = hi;                                                   // the upper neighbour's lower ghost layer
+  q.peer_lo_flag = lo ? ts->peer_flags[0] + 1 : nullptr;
+  q.peer_hi_flag = hi ? ts->peer_flags[1] + 0 : nullptr;
+  q.edge_count = ts->p2p_flags + 4;
+  GDTB_TRY(launch_p2p_send_layers(L->ctx->launch, q));
+  ts->sends++;
+  return GDTB_OK;
+}
+
+// one step on the slab: the stage vectors are formed on the owned layers, their boundary layers handed to the
+// neighbours, and every apply waits (inside the kernel) until the neighbours' hand-over of its source has arrived
+static int rk_enqueue_step_slab(gdtb_rk* ts, double actual_dt)
+{
+  gdtb_fvop* L = ts->op;
+  Launch& la = L->ctx->launch;
+  const int s = ts->s;
+  const long long plane = gdtb_fvop_ghost_layer_size(L);
+  const long long owned = plane * (L->grid.layer_hi - L->grid.layer_lo);
+  double* un = ts->p2p_un;
+  for (int ii = 0; ii < s; ++ii) {
+    const double* ui = un;
+    if (ii > 0) {
+      double* dst = ts->p2p_ui[ts->ui_parity];
+      RkAxpyParams q;
+      q.n = owned;
+      q.nv = 0;
+      const double* base = un + plane;
+      bool wrote = false;
+      for (int jj = 0; jj < ii; ++jj) {
+        const double coef = actual_dt * ts->r * ts->A[ii * s + jj];
+        if (coef == 0.)
+          continue;
+        q.v[q.nv] = ts->d_k[jj] + plane;
+        q.c[q.nv] = coef;
+        if (++q.nv == RK_MAX_TERMS) {
+          GDTB_TRY(launch_rk_axpy(la, q, base, dst + plane));
+          base = dst + plane;
+          q.nv = 0;
+          wrote = true;
+        }
+      }
+      if (q.nv > 0 || !wrote) // (all coefficients zero: u_i = u_n, still a distinct buffer so that the hand-over order holds)
+        GDTB_TRY(launch_rk_axpy(la, q, base, dst + plane));
+      GDTB_TRY(rk_p2p_send(ts, 1 + ts->ui_parity));
+      ui = dst;
+      ts->ui_parity ^= 1;
+    }
+    FvParams p;
+    fv_fill_params(L, p);
+    p.p2p = 1;
+    p.wait_lo = ts->has_peer[0];
+    p.wait_hi = ts->has_peer[1];
+    p.my_flags = ts->p2p_flags;
+    p.timeout_flag = ts->p2p_flags + 2;
+    p.edge_count = ts->p2p_flags + 5;
+    p.expect = (int)ts->sends;
+    GDTB_TRY(launch_fv_apply(la, p, ui, ts->d_k[ii]));
+  }
+  RkAxpyParams q;
+  q.n = owned;
+  q.nv = 0;
+  for (int ii = 0; ii < s; ++ii) {
+    const double coef = ts->r * actual_dt * ts->b[ii];
+    if (coef == 0.)
+      continue;
+    q.v[q.nv] = ts->d_k[ii] + plane;
+    q.c[q.nv] = coef;
+    if (++q.nv == RK_MAX_TERMS) {
+      GDTB_TRY(launch_rk_axpy(la, q, un + plane, un + plane));
+      q.nv = 0;
+    }
+  }
+  if (q.nv > 0)
+    GDTB_TRY(launch_rk_axpy(la, q, un + plane, un + plane));
+  return rk_p2p_send(ts, 0);
 }
 
 double gdtb_rk_current_time(const gdtb_rk* ts)
@@ -2330,7 +2519,11 @@ int gdtb_rk_step(gdtb_rk* ts, double* d_u, double dt, double max_dt, double* ret
   GDTB_TRY(check_ctx(L->ctx));
   const double actual_dt = std::min(dt, max_dt); // :239
   cudaStream_t st = L->ctx->launch.stream;
-  if (ts->s == 1) {
+  if (ts->slab) {
+    if (d_u != ts->p2p_un)
+      return fail(GDTB_ERR_INVALID_ARGUMENT, "on a slab the solution lives in the stepper's own vector (gdtb_rk_p2p_handles)");
+    GDTB_TRY(rk_enqueue_step_slab(ts, actual_dt));
+  } else if (ts->s == 1) {
     GDTB_TRY(rk_enqueue_step(ts, d_u, ts->d_ui, actual_dt));
     GDTB_CUDA(cudaMemcpyAsync(d_u, ts->d_ui, sizeof(double) * (size_t)fv_local_size(L), cudaMemcpyDeviceToDevice, st));
   } else
@@ -2386,7 +2579,10 @@ int gdtb_rk_solve(gdtb_rk* ts, double* d_u, double t_end, double initial_dt, int
   while (n_full < plan.size() && plan[n_full] == initial_dt)
     ++n_full;
   const int per_graph = ts->s == 1 ? 2 : 1;
-  const size_t replays = n_full >= 8 ? n_full / per_graph : 0;
+  if (ts->slab && d_u != ts->p2p_un)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "on a slab the solution lives in the stepper's own vector (gdtb_rk_p2p_handles)");
+  // (slab mode: the counters each apply waits for advance from step to step, so the steps are enqueued one by one)
+  const size_t replays = (n_full >= 8 && !ts->slab) ? n_full / per_graph : 0;
   int status = GDTB_OK;
   double* cur = d_u; // where the current solution lives (Euler ping-pong)
   size_t done = 0;
@@ -2423,7 +2619,9 @@ int gdtb_rk_solve(gdtb_rk* ts, double* d_u, double t_end, double initial_dt, int
       cudaGraphDestroy(graph);
   }
   for (size_t k = done; status == GDTB_OK && k < plan.size(); ++k) {
-    if (ts->s == 1) {
+    if (ts->slab)
+      status = rk_enqueue_step_slab(ts, plan[k]);
+    else if (ts->s == 1) {
       double* nxt = cur == d_u ? ts->d_ui : d_u;
       status = rk_enqueue_step(ts, cur, nxt, plan[k]);
       cur = nxt;

@@ -321,9 +321,9 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
   const bool edge_lo = P2P && j0 == layer_lo, edge_hi = P2P && j1 == (int)g.layer_hi;
   if (P2P) {
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-      if (edge_lo && p.peer_lo_ghost)
+      if (edge_lo && p.wait_lo)
         fv_wait_counter(p.my_flags + 0, p.expect, p.timeout_flag);
-      if (edge_hi && p.peer_hi_ghost)
+      if (edge_hi && p.wait_hi)
         fv_wait_counter(p.my_flags + 1, p.expect, p.timeout_flag);
     }
     if (edge_lo || edge_hi)
@@ -563,6 +563,30 @@ __global__ void __launch_bounds__(256) k_rk_axpy(const __grid_constant__ RkAxpyP
   }
 }
 
+// Stage-vector hand-over of the slab Runge-Kutta loop: first owned layer -> lower neighbour's upper ghost layer, last
+// owned layer -> upper neighbour's lower ghost layer; every block fences system-wide, the last one raises the counters.
+__global__ void __launch_bounds__(256) k_p2p_send_layers(const __grid_constant__ P2pSendParams p)
+{
+  const double* first = p.src + p.plane;
+  const double* last = p.src + p.layers * p.plane;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < p.plane; c += (long long)gridDim.x * blockDim.x) {
+    if (p.peer_lo_ghost)
+      p.peer_lo_ghost[c] = first[c];
+    if (p.peer_hi_ghost)
+      p.peer_hi_ghost[c] = last[c];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(p.edge_count, 1) == (int)gridDim.x - 1) {
+    atomicExch(p.edge_count, 0);
+    __threadfence_system();
+    if (p.peer_lo_flag)
+      atomicAdd_system(p.peer_lo_flag, 1);
+    if (p.peer_hi_flag)
+      atomicAdd_system(p.peer_hi_flag, 1);
+  }
+}
+
 // estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh:47-60, 75-82): data range of the (elementwise constant) state
 // and max over the elements of perimeter / volume; block partials {min, max, pov}, finished on the host.
 template <int D>
@@ -736,6 +760,15 @@ int launch_rk_axpy(Launch& L, const RkAxpyParams& p, const double* base, double*
     launch_rk_axpy_w<2>(p, base, out, grid, L.stream);
   else
     launch_rk_axpy_w<1>(p, base, out, grid, L.stream);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+int launch_p2p_send_layers(Launch& L, const P2pSendParams& p)
+{
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((p.plane + 255) / 256, (long long)L.sm_count * 2));
+  k_p2p_send_layers<<<grid, 256, 0, L.stream>>>(p);
   L.count++;
   GDTB_CUDA(cudaGetLastError());
   return GDTB_OK;

@@ -162,6 +162,20 @@ struct gdtb_rk
   double r, t;
   double* d_ui = nullptr;                    // stage vector u_i (Euler: ping-pong buffer)
   double* d_k[GDTB_RK_MAX_STAGES] = {};      // stages k_i
+  // slab mode (operator with gdtb_fvop_set_slab): solution and stage vectors are stepper-owned, exported through CUDA
+  // IPC, and their boundary layers are handed to the neighbours by peer stores (gdtb_rk_p2p_*)
+  bool slab = false;
+  double* p2p_un = nullptr;
+  double* p2p_ui[2] = {nullptr, nullptr};
+  int* p2p_flags = nullptr; // [0] lower ghost filled, [1] upper ghost filled, [2] timeout, [4] edge counter
+  double* peer_un[2] = {nullptr, nullptr};      // [lower / upper neighbour]
+  double* peer_ui[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int* peer_flags[2] = {nullptr, nullptr};
+  long long peer_layers[2] = {0, 0};
+  bool peer_opened[2] = {false, false};
+  bool has_peer[2] = {false, false};
+  long long sends = 0; // hand-overs issued so far (= value the neighbours' counters must have reached)
+  int ui_parity = 0;
 };
 
 namespace gdtb {

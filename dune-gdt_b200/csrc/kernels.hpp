@@ -266,6 +266,7 @@ struct FvParams
   // raises a counter in the neighbour's memory; the CTAs that read a ghost layer first wait for the neighbour's
   // counter of the previous step.  NULL pointers: no neighbour on that side.
   int p2p;
+  int wait_lo, wait_hi;  // a neighbour fills the lower / upper ghost layer of the source: wait for its counter
   double* peer_lo_ghost; // upper ghost layer of the lower neighbour's destination buffer
   double* peer_hi_ghost; // lower ghost layer of the upper neighbour's destination buffer
   int* peer_lo_flag;     // lower neighbour's "upper ghost filled" counter
@@ -289,6 +290,20 @@ struct RkAxpyParams
 };
 int launch_rk_axpy(Launch& L, const RkAxpyParams& p, const double* base, double* out);
 // estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh:38-86): per block {min u, max u, max perimeter / volume}
+// hands the first / last owned layer of a slab vector over to the neighbours' ghost layers (peer stores) and raises their
+// step counters: the exchange of the Runge-Kutta stage vectors (tools/timestepper/explicit-rungekutta.hh:252-257)
+struct P2pSendParams
+{
+  const double* src;   // slab vector [ghost | owned | ghost]
+  long long plane;     // cells per layer
+  long long layers;    // owned layers
+  double* peer_lo_ghost;
+  double* peer_hi_ghost;
+  int* peer_lo_flag;
+  int* peer_hi_flag;
+  int* edge_count;
+};
+int launch_p2p_send_layers(Launch& L, const P2pSendParams& p);
 int launch_fv_dt_reduce(Launch& L, const FvParams& p, const double* u, double* partial /* 3 * blocks */, int blocks);
 int launch_fv_interpolate(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx, const double* qw,
                           double* u);

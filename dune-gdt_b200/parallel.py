@@ -264,6 +264,116 @@ class PeerMemoryFvTimeLoop:
         self.op = None
 
 
+class PeerMemoryRkTimeStepper:
+    """ExplicitRungeKuttaTimeStepper (tools/timestepper/explicit-rungekutta.hh:158-270) on slabs: the reference exchanges
+    every stage vector with a DataHandle communicate() (:252-257); here the stepper-owned solution / stage vectors are
+    opened by the neighbour processes through CUDA IPC, a small kernel hands the boundary layers over after every stage
+    vector and every operator apply waits inside the kernel for its source (`gdtb_rk_p2p_*`).  >= 2 stages."""
+
+    def __init__(self, numerical_flux, space, rank, world, method, r=-1.0, t_0=0.0, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from .api import AdvectionFvOperator
+
+        lib = capi.lib()
+        self.space, self.rank, self.world, self.group = space, rank, world, group
+        g = space.grid.desc
+        self.dim = int(g.dim)
+        self.n_last = int(g.n[self.dim - 1])
+        self.periodic_last = bool(g.periodic & (1 << (self.dim - 1))) and self.n_last > 1
+        self.begin, self.end = slab_layers(self.n_last, rank, world)
+        self.op = AdvectionFvOperator(numerical_flux, space)
+        capi.check(lib.gdtb_fvop_set_slab(self.op._h, self.begin, self.end))
+        self.plane = int(lib.gdtb_fvop_ghost_layer_size(self.op._h))
+        self.owned = (self.end - self.begin) * self.plane
+        self.local_size = self.owned + 2 * self.plane
+        self._h = C.c_void_p()
+        capi.check(lib.gdtb_rk_create(self.op._h, int(method), 0, None, None, None, float(r), float(t_0), C.byref(self._h)))
+        handles = (C.c_ubyte * (4 * 64))()
+        p0 = C.c_void_p()
+        capi.check(lib.gdtb_rk_p2p_handles(self._h, C.byref(p0), handles))
+        dev = torch.device("cuda", space.grid.ctx.device)
+        self._ptr = p0.value
+        self.u = _as_tensor(p0.value, self.local_size, dev)
+        lower, upper = neighbours(rank, world, self.periodic_last)
+        mine = torch.tensor(list(bytes(handles)), dtype=torch.uint8, device=dev)
+        if world > 1:
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine, group=group)
+        else:
+            every = [mine]
+
+        def arg(nb):
+            if nb is None:
+                return None, 0, 0
+            if nb == rank:
+                return None, 0, 1
+            b, e = slab_layers(self.n_last, nb, world)
+            raw = bytes(every[nb].cpu().numpy().tobytes())
+            return (C.c_ubyte * len(raw)).from_buffer_copy(raw), e - b, 0
+
+        lo_h, lo_layers, lo_self = arg(lower)
+        hi_h, hi_layers, hi_self = arg(upper)
+        self._keep = (lo_h, hi_h)
+        capi.check(lib.gdtb_rk_p2p_connect(self._h, lo_h, lo_layers, lo_self, hi_h, hi_layers, hi_self))
+        if world > 1:
+            dist.barrier(group=group)
+
+    def set_initial_values(self, u_global):
+        import torch
+
+        loc = np.zeros(self.local_size)
+        loc[self.plane:self.plane + self.owned] = np.asarray(u_global)[self.begin * self.plane:self.end * self.plane]
+        self.space.grid.ctx.synchronize()
+        self.u.copy_(torch.from_numpy(loc))
+        for r in exchange_ghost_layers(self.u, self.plane, self.rank, self.world, self.periodic_last, self.group):
+            r.wait()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
+
+    def step(self, dt, max_dt=None):
+        ret = C.c_double()
+        capi.check(capi.lib().gdtb_rk_step(self._h, C.c_void_p(self._ptr), float(dt), float(dt if max_dt is None else max_dt),
+                                           C.byref(ret)))
+        return ret.value
+
+    def solve(self, t_end, initial_dt):
+        n, nxt = C.c_int64(), C.c_double()
+        capi.check(capi.lib().gdtb_rk_solve(self._h, C.c_void_p(self._ptr), float(t_end), float(initial_dt), C.byref(n),
+                                            C.byref(nxt)))
+        self.num_steps = n.value
+        return nxt.value
+
+    def current_time(self):
+        return capi.lib().gdtb_rk_current_time(self._h)
+
+    def check(self):
+        capi.check(capi.lib().gdtb_rk_p2p_check(self._h))
+
+    def owned_view(self):
+        return self.u[self.plane:self.plane + self.owned]
+
+    def close(self):
+        """collective: nobody may free its buffers while a neighbour can still store into them"""
+        import torch
+
+        self.space.grid.ctx.synchronize()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
+        self.u = None
+        if self._h.value:
+            capi.lib().gdtb_rk_destroy(self._h)
+            self._h = C.c_void_p()
+        self.op = None
+
+
 class SlabAssembly:
     """Matrix operator + functional of one rank: owner-computes-rows on the rank's element slab, no communication.
     The global CSR matrix is the concatenation of the ranks' value arrays in rank order (`value_offset` is the

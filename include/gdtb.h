@@ -397,6 +397,19 @@ int gdtb_rk_step_host(gdtb_rk* ts, double* u, double dt, double max_dt, double* 
 int gdtb_rk_solve(gdtb_rk* ts, double* d_u, double t_end, double initial_dt, int64_t* n_steps, double* next_dt);
 int gdtb_rk_solve_host(gdtb_rk* ts, double* u, double t_end, double initial_dt, int64_t* n_steps, double* next_dt);
 
+/* Runge-Kutta on slabs (operator with gdtb_fvop_set_slab; >= 2 stages, 2D / 3D): the reference exchanges every stage
+ * vector k_i with a DataHandle communicate() (explicit-rungekutta.hh:252-257).  Here the stepper owns the solution vector
+ * and two alternating stage vectors in memory the neighbour processes open through CUDA IPC; after every stage vector
+ * (and after the update of u_n) a small kernel stores the first / last owned layer into the neighbours' ghost layers and
+ * raises their counters, and every operator apply waits inside the kernel for the counter of its source.
+ *   gdtb_rk_create on the slab operator, gdtb_rk_p2p_handles (solution vector in slab layout + 4 IPC handles),
+ *   gdtb_rk_p2p_connect (as gdtb_fvop_p2p_connect), fill the solution vector incl. ghost layers once, then
+ *   gdtb_rk_step / gdtb_rk_solve with d_u = that vector; gdtb_rk_p2p_check reports a timed-out wait. */
+int gdtb_rk_p2p_handles(gdtb_rk* ts, double** d_un, void* handles /* 4 * GDTB_IPC_HANDLE_BYTES */);
+int gdtb_rk_p2p_connect(gdtb_rk* ts, const void* lower_handles, int64_t lower_layers, int lower_is_self,
+                        const void* upper_handles, int64_t upper_layers, int upper_is_self);
+int gdtb_rk_p2p_check(gdtb_rk* ts);
+
 /* default_interpolation(order, f, fv_space) (interpolations/default.hh:76-83, spaces/basis/finite-volume.hh:244-252) */
 int gdtb_fv_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_function* f, double* d_u);
 /* same with a host result buffer of gdtb_space_size doubles (per-element function data may live on the host) */

@@ -75,6 +75,26 @@ def _worker(rank, world, port, out_dir):
             err = np.abs(own - ref_e[loop.begin * loop.plane:loop.end * loop.plane]).max() / np.abs(ref_e).max()
             assert err <= 1e-12, ("p2p euler", n, err)
             loop.close()
+        # ---- FV: Runge-Kutta on slabs, stage vectors handed over by peer stores ------------------------------
+        for n, periodic, fk, params, method in (([64, 48], 3, D.FLUX_BURGERS, [], D.RK_SSP3),
+                                                ([40, 33], 0, D.FLUX_LINEAR, [1.0, 0.5], D.RK_SSP2),
+                                                ([12, 10, 16], 7, D.FLUX_LINEAR, [1.0, -0.5, 0.25], D.RK_CLASSIC4)):
+            u = rng.uniform(0.1, 1.0, int(np.prod(n)))
+            grid = gdt.make_cube_grid(ctx, 0.0, 1.0, n, periodic=periodic)
+            space = gdt.make_finite_volume_space(grid)
+            ts = parallel.PeerMemoryRkTimeStepper(gdt.NumericalUpwindFlux(fk, params), space, rank, world, method)
+            ts.set_initial_values(u)
+            gd = D.grid_desc(0.0, 1.0, n, periodic=periodic)
+            fl = D.flux(fk, D.NUMFLUX_UPWIND, params)
+            dt = 0.3 * oracle.fv_estimate_dt(gd, fl, u)
+            ts.solve(5.5 * dt, dt)
+            ts.check()
+            ref, steps, t = oracle.rk_solve(gd, fl, D.BUTCHER[method], u, 5.5 * dt, dt, r=-1.0)
+            assert ts.num_steps == steps and ts.current_time() == t
+            own = ts.owned_view().cpu().numpy()
+            err = np.abs(own - ref[ts.begin * ts.plane:ts.end * ts.plane]).max() / np.abs(ref).max()
+            assert err <= 1e-12, ("p2p rk", n, err)
+            ts.close()
         # ---- assembly: concatenated slab results == oracle on the whole grid ----------------------------------
         n = [10, 9, 11]
         grid = gdt.make_cube_grid(ctx, -1.0, 1.0, n)
