@@ -499,15 +499,17 @@ def test_error_conventions(gdt, ctx):
 # ------------------------------------------------------------------------------------------------------------------
 # element-block partition (multi-GPU layout), exercised on one device
 # ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("constant_kappa", [False, True], ids=["elem-kappa+mass", "const-kappa"])
 @pytest.mark.parametrize("n,cuts", [([6, 5, 8], [0, 3, 8]), ([6, 5, 9], [0, 1, 4, 9]), ([7, 6], [0, 2, 6]), ([12], [0, 5, 12])])
-def test_slab_owner_computes_rows(gdt, ctx, oracle, n, cuts):
+def test_slab_owner_computes_rows(gdt, ctx, oracle, n, cuts, constant_kappa):
     """every slab produces its owned rows completely and without communication; the concatenation of all slabs is
-    the global matrix / vector"""
+    the global matrix / vector (constant kappa: the sum-factorised row kernel of the headline configuration, which is
+    what `bench.py --gpus N` runs on every rank)"""
     lib = gdt.capi.lib()
     check = gdt.capi.check
     gdesc = D.grid_desc(-1.0, 1.0, n)
     kappa = rng_elem(n)
-    forms = [laplace(D.fn_elem(kappa)), mass(0.5)]
+    forms = [laplace(0.75)] if constant_kappa else [laplace(D.fn_elem(kappa)), mass(0.5)]
     src = D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 2.0, 1.3)
     rp, ci = oracle.pattern(gdesc, (CG, 1))
     ref_v, ref_b = oracle.assemble(gdesc, CG, 1, rp, ci, forms, rhs_forms=[source(src), source(D.fn_const(0.25))])
