@@ -124,6 +124,9 @@ PROTOTYPES = {
     "gdtb_assemble": (C.c_int, [_P, _P, C.c_int]),
     "gdtb_assemble_async": (C.c_int, [_P, _P, C.c_int]),
     "gdtb_matop_local_nnz": (C.c_int64, [_P]),
+    "gdtb_host_closed_form_rowptr": (C.c_int, [C.POINTER(GridDesc), C.c_int, C.c_int, _I64P]),
+    "gdtb_host_slab_row_ranges": (C.c_int, [C.POINTER(GridDesc), C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int32, _I64P, _I64P,
+                                  _I64P, _I64P, C.POINTER(C.c_int32)]),
     "gdtb_matop_set_slab_halo": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gdtb_vecfun_set_slab_halo": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gdtb_matop_halo_layout": (C.c_int, [_P, _I64P, _I64P, _I64P]),

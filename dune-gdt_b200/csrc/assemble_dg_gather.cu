@@ -343,7 +343,7 @@ __device__ __forceinline__ double dg_ext(const GridDev& g, int k, int i)
 
 // blocks (element + existing neighbours) of all elements before e in the element_and_intersection pattern
 template <int D>
-__device__ __forceinline__ long long dg_blocks_before(const GridDev& g, const long long e, const int* idx)
+__host__ __device__ __forceinline__ long long dg_blocks_before(const GridDev& g, const long long e, const int* idx)
 {
   const long long nx = g.n[0];
   long long P = e;
@@ -363,7 +363,7 @@ __device__ __forceinline__ long long dg_blocks_before(const GridDev& g, const lo
 }
 
 template <int D>
-__device__ __forceinline__ int dg_nblocks(const GridDev& g, const int* idx)
+__host__ __device__ __forceinline__ int dg_nblocks(const GridDev& g, const int* idx)
 {
   int nb = 1;
 #pragma unroll
@@ -911,6 +911,34 @@ int pattern_structured_dg(Launch& L, const GridDev& g, const SpaceDev& sp, long 
   *d_rowptr = rowptr;
   *d_colidx = colidx;
   *nnz_out = nnz;
+  return GDTB_OK;
+}
+
+template <int D>
+static void dg_host_rowptr_d(const GridDev& g, int nloc, long long* rowptr)
+{
+  long long r = 0;
+  int idx[3] = {0, 0, 0};
+  for (long long e = 0; e < g.ne; ++e) {
+    idx[0] = int(e % g.n[0]);
+    idx[1] = D > 1 ? int((e / g.n[0]) % g.n[1]) : 0;
+    idx[2] = D > 2 ? int(e / (g.n[0] * g.n[1])) : 0;
+    const long long base = (long long)nloc * nloc * dg_blocks_before<D>(g, e, idx);
+    const int nb = dg_nblocks<D>(g, idx);
+    for (int i = 0; i < nloc; ++i)
+      rowptr[r++] = base + (long long)i * nb * nloc;
+    if (e == g.ne - 1)
+      rowptr[r] = base + (long long)nloc * nb * nloc;
+  }
+}
+
+int dg_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr)
+{
+  switch (g.d) {
+    case 1: dg_host_rowptr_d<1>(g, sp.nloc, rowptr); break;
+    case 2: dg_host_rowptr_d<2>(g, sp.nloc, rowptr); break;
+    default: dg_host_rowptr_d<3>(g, sp.nloc, rowptr); break;
+  }
   return GDTB_OK;
 }
 

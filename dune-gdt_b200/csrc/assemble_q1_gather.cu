@@ -73,12 +73,12 @@ __device__ __forceinline__ void bulk_wait0()
 
 // number of stencil columns before vertex index i along one axis with N cells: sum_{i' < i} n(i'),
 // n(i') = 2 at the two ends, 3 inside
-__device__ __forceinline__ int S_axis(int i, int N)
+__host__ __device__ __forceinline__ int S_axis(int i, int N)
 {
   return i == 0 ? 0 : (i > N ? 3 * N + 1 : 3 * i - 1);
 }
 
-__device__ __forceinline__ int n_axis(int i, int N)
+__host__ __device__ __forceinline__ int n_axis(int i, int N)
 {
   return 1 + (i > 0 ? 1 : 0) + (i < N ? 1 : 0);
 }
@@ -98,7 +98,7 @@ __device__ __forceinline__ constexpr int delta_index(int dx, int dy, int dz)
 
 // closed-form CSR row pointer of vertex (ix, iy, iz) of the CG-Q1 element stencil (tensor-product pattern)
 template <int D>
-__device__ __forceinline__ long long q1_rowptr(int ix, int iy, int iz, int Nx, int Ny, int Nz)
+__host__ __device__ __forceinline__ long long q1_rowptr(int ix, int iy, int iz, int Nx, int Ny, int Nz)
 {
   if (D == 1)
     return S_axis(ix, Nx);
@@ -698,6 +698,23 @@ int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double*
     case 3: return launch_q1_gather_d<3>(L, p, values, rhs, accumulate);
     default: return fail(GDTB_ERR_INVALID_ARGUMENT, "q1_gather: dimension must be 1, 2 or 3");
   }
+}
+
+int q1_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr)
+{
+  const int Nx = (int)g.n[0], Ny = g.d > 1 ? (int)g.n[1] : 1, Nz = g.d > 2 ? (int)g.n[2] : 1;
+  long long r = 0;
+  for (int iz = 0; iz <= (g.d > 2 ? Nz : 0); ++iz)
+    for (int iy = 0; iy <= (g.d > 1 ? Ny : 0); ++iy)
+      for (int ix = 0; ix <= Nx; ++ix)
+        rowptr[r++] = g.d == 1 ? q1_rowptr<1>(ix, 0, 0, Nx, Ny, Nz)
+                               : (g.d == 2 ? q1_rowptr<2>(ix, iy, 0, Nx, Ny, Nz) : q1_rowptr<3>(ix, iy, iz, Nx, Ny, Nz));
+  if (r != sp.size)
+    return fail(GDTB_ERR_SPACE, "q1_host_rowptr: space size mismatch");
+  // one past the last vertex decodes to i_last = N_last + 1 (the S_axis of the last axis saturates)
+  rowptr[r] = g.d == 1 ? q1_rowptr<1>(Nx + 1, 0, 0, Nx, Ny, Nz)
+                       : (g.d == 2 ? q1_rowptr<2>(0, Ny + 1, 0, Nx, Ny, Nz) : q1_rowptr<3>(0, 0, Nz + 1, Nx, Ny, Nz));
+  return GDTB_OK;
 }
 
 } // namespace gdtb

@@ -119,14 +119,19 @@ __host__ __device__ __forceinline__ long long q2_axis_total(int S, long long N)
 }
 
 // n / d for a run-time constant d through its magic m = floor(2^64 / d) + 1 (exact for all 32-bit n; d = 1 has no magic)
-__device__ __forceinline__ unsigned q2_div(const unsigned n, const unsigned d, const unsigned long long m)
+__host__ __device__ __forceinline__ unsigned q2_div(const unsigned n, const unsigned d, const unsigned long long m)
 {
+#ifdef __CUDA_ARCH__
   return d == 1 ? n : (unsigned)__umul64hi((unsigned long long)n, m);
+#else
+  (void)m;
+  return n / d;
+#endif
 }
 
 // decode the lexicographic row index inside a row group into element-lattice coordinates
 template <int D>
-__device__ __forceinline__ void q2_decode(const Q2RowGroup& rg, const unsigned lex, int& cx, int& cy, int& cl)
+__host__ __device__ __forceinline__ void q2_decode(const Q2RowGroup& rg, const unsigned lex, int& cx, int& cy, int& cl)
 {
   const unsigned t1 = q2_div(lex, rg.ex, rg.mex);
   cx = int(lex - t1 * rg.ex);
@@ -143,7 +148,7 @@ __device__ __forceinline__ void q2_decode(const Q2RowGroup& rg, const unsigned l
 // number of matrix entries of the row group that precede row (cx, cy, cl); the part inside one layer of the last axis
 // stays below 2^32 (25 (N + 1)^2 entries)
 template <int D>
-__device__ __forceinline__ long long q2_row_offset(const GridDev& g, const Q2RowGroup& rg, const int cx, const int cy,
+__host__ __device__ __forceinline__ long long q2_row_offset(const GridDev& g, const Q2RowGroup& rg, const int cx, const int cy,
                                                    const int cl)
 {
   const int s = rg.s;
@@ -1006,6 +1011,49 @@ int pattern_structured_cg_q2(Launch& L, const GridDev& g, const SpaceDev& sp, lo
   *d_colidx = colidx;
   *nnz_out = nnz;
   return GDTB_OK;
+}
+
+int q2_host_rowptr(const GridDev& g0, const SpaceDev& sp, long long* rowptr)
+{
+  GridDev g = g0;
+  const int d = g.d;
+  g.layer_lo = 0;
+  g.layer_hi = g.n[d - 1];
+  Q2SlabRange ranges[8];
+  q2_slab_ranges(g, sp, ranges);
+  int r = 0;
+  long long row = 0;
+  for (int c = 0; c <= d; ++c)
+    for (int s = 0; s < (1 << d); ++s) {
+      int pc = 0;
+      for (int k = 0; k < d; ++k)
+        pc += (s >> k) & 1;
+      if (pc != d - c)
+        continue;
+      Q2RowGroup rg;
+      std::memset(&rg, 0, sizeof(rg));
+      rg.s = s;
+      rg.ex = (unsigned)((s & 1) ? g.n[0] : g.n[0] + 1);
+      rg.ey = d == 3 ? (unsigned)((s & 2) ? g.n[1] : g.n[1] + 1) : 1u;
+      rg.Tx = (unsigned)q2_axis_total(s & 1, g.n[0]);
+      rg.TxTy = (long long)rg.Tx * (d == 3 ? q2_axis_total((s >> 1) & 1, g.n[1]) : 1);
+      if (ranges[r].row_begin != row)
+        return fail(GDTB_ERR_SPACE, "q2_host_rowptr: row groups are not contiguous");
+      for (long long lex = 0; lex < ranges[r].row_end - ranges[r].row_begin; ++lex) {
+        int cx, cy, cl;
+        if (d == 3) {
+          q2_decode<3>(rg, (unsigned)lex, cx, cy, cl);
+          rowptr[row++] = ranges[r].value_offset + q2_row_offset<3>(g, rg, cx, cy, cl);
+        } else {
+          q2_decode<2>(rg, (unsigned)lex, cx, cy, cl);
+          rowptr[row++] = ranges[r].value_offset + q2_row_offset<2>(g, rg, cx, cy, cl);
+        }
+      }
+      if (r == (1 << d) - 1)
+        rowptr[row] = ranges[r].value_offset + ranges[r].count;
+      ++r;
+    }
+  return row == sp.size ? GDTB_OK : fail(GDTB_ERR_SPACE, "q2_host_rowptr: space size mismatch");
 }
 
 } // namespace gdtb

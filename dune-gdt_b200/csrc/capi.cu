@@ -709,26 +709,19 @@ int64_t gdtb_ctx_launch_count(const gdtb_ctx* ctx)
 }
 
 // ---- grid / spaces ---------------------------------------------------------------------------
-int gdtb_grid_create_cube(gdtb_ctx* ctx, const gdtb_grid_desc* desc, gdtb_grid** out)
+// GridDev of a cube grid description (host arithmetic only)
+static int make_grid_dev(const gdtb_grid_desc* desc, GridDev& d)
 {
-  if (!ctx || !desc || !out)
-    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_grid_create_cube: NULL argument");
   if (desc->dim < 1 || desc->dim > 3)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "grid dimension must be 1, 2 or 3");
-  auto g = new gdtb_grid();
-  g->ctx = ctx;
-  g->desc = *desc;
-  GridDev& d = g->dev;
   std::memset(&d, 0, sizeof(d));
   d.d = desc->dim;
   d.periodic = desc->periodic & ((1 << desc->dim) - 1);
   d.ne = 1;
   for (int k = 0; k < 3; ++k) {
     if (k < desc->dim) {
-      if (desc->n[k] < 1 || !(desc->upper[k] > desc->lower[k])) {
-        delete g;
+      if (desc->n[k] < 1 || !(desc->upper[k] > desc->lower[k]))
         return fail(GDTB_ERR_INVALID_ARGUMENT, "grid needs n >= 1 and upper > lower in every direction");
-      }
       d.lo[k] = desc->lower[k];
       d.n[k] = desc->n[k];
       d.h[k] = (desc->upper[k] - desc->lower[k]) / double(desc->n[k]);
@@ -741,6 +734,19 @@ int gdtb_grid_create_cube(gdtb_ctx* ctx, const gdtb_grid_desc* desc, gdtb_grid**
   }
   d.layer_lo = 0;
   d.layer_hi = d.n[d.d - 1];
+  return GDTB_OK;
+}
+
+int gdtb_grid_create_cube(gdtb_ctx* ctx, const gdtb_grid_desc* desc, gdtb_grid** out)
+{
+  if (!ctx || !desc || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_grid_create_cube: NULL argument");
+  GridDev d;
+  GDTB_TRY(make_grid_dev(desc, d));
+  auto g = new gdtb_grid();
+  g->ctx = ctx;
+  g->desc = *desc;
+  g->dev = d;
   *out = g;
   return GDTB_OK;
 }
@@ -756,13 +762,12 @@ int64_t gdtb_grid_num_elements(const gdtb_grid* grid)
   return grid ? grid->dev.ne : 0;
 }
 
-int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order, gdtb_space** out)
+// SpaceDev of a space on a grid (host arithmetic only): sizes and the MCMG offsets of the continuous mapper
+static int make_space_dev(const GridDev& g, int kind, int order, SpaceDev& sp)
 {
-  if (!ctx || !grid || !out)
-    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_space_create: NULL argument");
   if (kind < GDTB_SPACE_CG || kind > GDTB_SPACE_FV)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown space kind");
-  const int d = grid->dev.d;
+  const int d = g.d;
   int K = order;
   if (kind == GDTB_SPACE_FV)
     K = 0;
@@ -772,12 +777,8 @@ int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order,
     return fail(GDTB_ERR_SPACE, "negative polynomial order");
   if (K > MAX_K || (d == 3 && K > 2))
     return fail(GDTB_ERR_FINITE_ELEMENT, "Lagrange order not supported (max 3 in 1d/2d, 2 in 3d)");
-  if (kind == GDTB_SPACE_CG && grid->dev.periodic)
+  if (kind == GDTB_SPACE_CG && g.periodic)
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "continuous Lagrange spaces on periodic grid views are not supported");
-  auto s = new gdtb_space();
-  s->ctx = ctx;
-  s->grid = grid->dev;
-  SpaceDev& sp = s->dev;
   std::memset(&sp, 0, sizeof(sp));
   sp.kind = kind;
   sp.K = K;
@@ -802,15 +803,96 @@ int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order,
         sp.cg.group_offset[sh] = entities;
         long long cnt = 1;
         for (int k = 0; k < d; ++k)
-          cnt *= ((sh >> k) & 1) ? grid->dev.n[k] : grid->dev.n[k] + 1;
+          cnt *= ((sh >> k) & 1) ? g.n[k] : g.n[k] + 1;
         entities += cnt;
       }
       running += entities * b;
     }
     sp.size = running;
   } else
-    sp.size = grid->dev.ne * sp.nloc;
+    sp.size = g.ne * sp.nloc;
+  return GDTB_OK;
+}
+
+int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order, gdtb_space** out)
+{
+  if (!ctx || !grid || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_space_create: NULL argument");
+  SpaceDev sp;
+  GDTB_TRY(make_space_dev(grid->dev, kind, order, sp));
+  auto s = new gdtb_space();
+  s->ctx = ctx;
+  s->grid = grid->dev;
+  s->dev = sp;
   *out = s;
+  return GDTB_OK;
+}
+
+// Host-side view of the closed-form CSR geometry the gather kernels and the structured pattern generators use (no
+// device needed): row pointers of the CG Q1 / CG Q2 element stencil or the DG element_and_intersection stencil on a
+// non-periodic grid, and the row ranges a slab of element layers owns.  Lets a binder size its containers before any
+// device work -- and lets the CPU test-suite check the layout arithmetic against the oracle's patterns.
+int gdtb_host_closed_form_rowptr(const gdtb_grid_desc* grid, int kind, int order, int64_t* rowptr)
+{
+  if (!grid || !rowptr)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_host_closed_form_rowptr: NULL argument");
+  GridDev g;
+  SpaceDev sp;
+  GDTB_TRY(make_grid_dev(grid, g));
+  GDTB_TRY(make_space_dev(g, kind, order, sp));
+  if (g.periodic)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "closed-form row pointers exist for non-periodic grids");
+  if (kind == GDTB_SPACE_CG && sp.K == 1)
+    return q1_host_rowptr(g, sp, (long long*)rowptr);
+  if (kind == GDTB_SPACE_CG && sp.K == 2 && (g.d == 2 || g.d == 3))
+    return q2_host_rowptr(g, sp, (long long*)rowptr);
+  if (kind == GDTB_SPACE_DG)
+    return dg_host_rowptr(g, sp, (long long*)rowptr);
+  return fail(GDTB_ERR_NOT_IMPLEMENTED, "closed-form row pointers: CG Q1, CG Q2 (2D / 3D) and DG spaces");
+}
+
+int gdtb_host_slab_row_ranges(const gdtb_grid_desc* grid, int kind, int order, int64_t layer_begin, int64_t layer_end,
+                              int32_t max_ranges, int64_t* row_begin, int64_t* row_end, int64_t* value_offset,
+                              int64_t* value_count, int32_t* n_ranges)
+{
+  if (!grid || !n_ranges)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_host_slab_row_ranges: NULL argument");
+  GridDev g;
+  SpaceDev sp;
+  GDTB_TRY(make_grid_dev(grid, g));
+  GDTB_TRY(make_space_dev(g, kind, order, sp));
+  const long long n_last = g.n[g.d - 1];
+  if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
+  if (g.periodic || kind != GDTB_SPACE_CG || (sp.K != 1 && !(sp.K == 2 && (g.d == 2 || g.d == 3))))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab row ranges: CG Q1 and CG Q2 (2D / 3D) on non-periodic grids");
+  g.layer_lo = layer_begin;
+  g.layer_hi = layer_end;
+  Q2SlabRange ranges[8];
+  int n = 1;
+  if (sp.K == 2)
+    n = q2_slab_ranges(g, sp, ranges);
+  else {
+    long long row_lo, row_hi, elem_lo, elem_hi;
+    q1_slab_ranges(g, layer_begin, layer_end, row_lo, row_hi, elem_lo, elem_hi);
+    ranges[0].row_begin = row_lo * q1_layer_rows(g);
+    ranges[0].row_end = row_hi * q1_layer_rows(g);
+    ranges[0].value_offset = q1_layer_rowptr(g, row_lo);
+    ranges[0].count = q1_layer_rowptr(g, row_hi) - ranges[0].value_offset;
+  }
+  *n_ranges = n;
+  if (max_ranges < n)
+    return (row_begin || row_end || value_offset || value_count) ? fail(GDTB_ERR_INVALID_ARGUMENT, "arrays too short") : GDTB_OK;
+  for (int r = 0; r < n; ++r) {
+    if (row_begin)
+      row_begin[r] = ranges[r].row_begin;
+    if (row_end)
+      row_end[r] = ranges[r].row_end;
+    if (value_offset)
+      value_offset[r] = ranges[r].value_offset;
+    if (value_count)
+      value_count[r] = ranges[r].count;
+  }
   return GDTB_OK;
 }
 

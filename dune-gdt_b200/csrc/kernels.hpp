@@ -241,6 +241,10 @@ int pattern_structured_cg_q2(Launch& L, const GridDev& g, const SpaceDev& sp, lo
                              long long* nnz);
 int pattern_structured_dg(Launch& L, const GridDev& g, const SpaceDev& sp, long long** d_rowptr, int** d_colidx,
                           long long* nnz);
+// the same closed-form row pointers evaluated on the host (rowptr[0 .. size]); no device involved
+int q1_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr);
+int q2_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr);
+int dg_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr);
 
 // ---- finite volumes (fv.cu) -----------------------------------------------------------------------
 struct FvParams

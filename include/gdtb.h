@@ -273,6 +273,16 @@ int64_t gdtb_pattern_nnz(const gdtb_pattern* pattern);
 int gdtb_pattern_download(const gdtb_pattern* pattern, int64_t* rowptr, int32_t* colidx);
 int gdtb_pattern_device(const gdtb_pattern* pattern, const int64_t** d_rowptr, const int32_t** d_colidx);
 
+/* Host-side view of the closed-form CSR geometry (no device, no context needed): the row pointers the structured
+ * pattern generators / gather kernels use for the CG Q1 and CG Q2 element stencils and the DG element_and_intersection
+ * stencil on a non-periodic grid (rowptr: gdtb_space_size + 1 entries), and the row ranges a slab of element layers
+ * [layer_begin, layer_end) owns (as gdtb_matop_local_row_ranges reports them after gdtb_matop_set_slab).  For sizing
+ * containers before any device work (make_*_sparsity_pattern(...).size() in the reference, tools/sparsity-pattern.hh). */
+int gdtb_host_closed_form_rowptr(const gdtb_grid_desc* grid, int kind, int order, int64_t* rowptr);
+int gdtb_host_slab_row_ranges(const gdtb_grid_desc* grid, int kind, int order, int64_t layer_begin, int64_t layer_end,
+                              int32_t max_ranges, int64_t* row_begin, int64_t* row_end, int64_t* value_offset,
+                              int64_t* value_count, int32_t* n_ranges);
+
 /* ---- MatrixOperator (operators/matrix-based.hh:245-508) -------------------------------------- */
 /* make_matrix_operator<M>(view, source_space, range_space, pattern) (matrix-based.hh:514-598):
  * rows = range/test space, cols = source/ansatz space.  `pattern` may be NULL for continuous Q1 and Q2 spaces on
