@@ -1,8 +1,8 @@
-// dune-gdt_b200/examples/stationary-heat-equation.cc -- the assembly part of dune-gdt's
-// examples/stationary-heat-equation.cc (lines 60-106) written against the B200 facade: same types, same calls.
-// What differs from the reference driver is only (i) the include, (ii) the GenericFunction lambda, which cannot
-// cross the C ABI as code and is replaced by the built-in analytic source of the same formula, and (iii) the steps
-// after the walk (constraints, solve, norms), which SURVEY.md section 8(f) lists as "next" rows.
+// dune-gdt_b200/examples/stationary-heat-equation.cc -- dune-gdt's examples/stationary-heat-equation.cc (lines 60-127:
+// assembly, Dirichlet constraints, solve, error norms) written against the B200 facade: same types, same calls.
+// What differs from the reference driver is only (i) the include, (ii) the GenericFunction lambdas, which cannot
+// cross the C ABI as code and are replaced by the built-in analytic functions of the same formulas, and (iii) the
+// VTK output, which is out of scope.  Every step runs on the device (there is no CPU path behind the facade).
 //
 //   ./stationary-heat-equation [num_elements_per_direction = 128] [dim = 2]
 #include <cmath>
@@ -38,9 +38,14 @@ int run(const unsigned int num_elements)
   auto rhs_func = make_vector_functional<V>(space);
   rhs_func.append(LocalElementIntegralFunctional<E>(LocalProductIntegrand<E>().with_ansatz(source)));
 
+  using I = XT::Grid::extract_intersection_t<GV>;
+  const XT::Grid::AllDirichletBoundaryInfo<I> boundary_info;
+  auto dirichlet_constraints = make_dirichlet_constraints(space, boundary_info);
+
   auto walker = XT::Grid::make_walker(grid_view);
   walker.append(lhs_op);
   walker.append(rhs_func);
+  walker.append(dirichlet_constraints);
   walker.walk(/*thread_parallel=*/true);
 
   const auto& A = lhs_op.matrix();
@@ -56,7 +61,36 @@ int run(const unsigned int num_elements)
   std::cout << "dofs: " << space.mapper().size() << "  nnz: " << A.non_zeros() << "\n"
             << "|A 1|_inf = " << Aones.sup_norm() << "\n"
             << "sum(b) = " << rhs_sum << " (integral of the source: " << expected << ")" << std::endl;
-  const bool ok = Aones.sup_norm() < 1e-12 && std::abs(rhs_sum - expected) < 1e-3 * expected;
+  bool ok = Aones.sup_norm() < 1e-12 && std::abs(rhs_sum - expected) < 1e-3 * expected;
+
+  // examples/stationary-heat-equation.cc:108-127: constraints, solve, error against the exact solution
+  // u = prod_i cos(pi/2 x_i) (homogeneous Dirichlet values on [-1, 1]^d)
+  dirichlet_constraints.apply(lhs_op.matrix(), rhs_func.vector());
+  auto solution = make_discrete_function<V>(space);
+  auto solver = XT::LA::make_solver(lhs_op.matrix());
+  solver.apply(rhs_func.vector(), solution.dofs().vector());
+
+  const auto exact_solution = XT::Functions::make_cosine_product<E>(3, 1., M_PI_2);
+  const auto error = solution - exact_solution;
+
+  auto h1_prod = make_bilinear_form(grid_view, error, error);
+  h1_prod += LocalElementIntegralBilinearForm<E>(LocalLaplaceIntegrand<E>(diffusion));
+
+  auto l2_prod = make_bilinear_form(grid_view, error, error);
+  l2_prod += LocalElementIntegralBilinearForm<E>(LocalProductIntegrand<E>());
+
+  walker.append(h1_prod);
+  walker.append(l2_prod);
+  walker.walk(/*thread_parallel=*/true);
+
+  const double h = 2. / num_elements;
+  const double h1_error = std::sqrt(h1_prod.result()), l2_error = std::sqrt(l2_prod.result());
+  std::cout << "Dirichlet DoFs: " << dirichlet_constraints.dirichlet_DoFs().size() << ", solver iterations: "
+            << solver.info().iterations << "\n"
+            << "error in H^1 semi-norm: " << h1_error << "\n"
+            << "error in L^2 norm:      " << l2_error << std::endl;
+  // Q1 on a uniform grid: first order in H^1, second order in L^2
+  ok = ok && solver.info().converged && h1_error < 3. * h && l2_error < 3. * h * h;
   std::cout << (ok ? "OK" : "FAILED") << std::endl;
   return ok ? EXIT_SUCCESS : EXIT_FAILURE;
 }

@@ -21,6 +21,7 @@
 #include <exception>
 #include <functional>
 #include <memory>
+#include <set>
 #include <sstream>
 #include <string>
 #include <utility>
@@ -52,6 +53,10 @@ private:
 };
 
 class NotImplemented : public Exception
+{
+  using Exception::Exception;
+};
+class InvalidStateException : public Exception
 {
   using Exception::Exception;
 };
@@ -508,9 +513,19 @@ public:
       m = std::max(m, x < 0 ? -x : x);
     return m;
   }
+  // the device-resident functional this host copy mirrors (set by VectorBasedFunctional; non-owning)
+  void bind_device(gdtb_vecfun* f)
+  {
+    device_ = f;
+  }
+  gdtb_vecfun* device() const
+  {
+    return device_;
+  }
 
 private:
   std::vector<R> data_;
+  gdtb_vecfun* device_ = nullptr;
 };
 
 // XT::LA::SparsityPatternDefault stand-in: the CSR pattern lives on the device, a host copy is made on demand
@@ -605,17 +620,24 @@ public:
         return values_[std::size_t(k)];
     return R(0);
   }
-  // y = A x (ConstMatrixOperator::apply, operators/matrix-based.hh:121-129), host side convenience
+  // y = A x (ConstMatrixOperator::apply, operators/matrix-based.hh:121-129): the CSR mat-vec runs on the device with
+  // the operator's values (this host container mirrors them); a matrix without a device operator cannot multiply
   void mv(const IstlDenseVector<R>& x, IstlDenseVector<R>& y) const
   {
-    const auto& rp = pattern_.rowptr();
-    const auto& ci = pattern_.colidx();
-    for (std::size_t i = 0; i < rows_; ++i) {
-      R s = 0;
-      for (std::int64_t k = rp[i]; k < rp[i + 1]; ++k)
-        s += values_[std::size_t(k)] * x[std::size_t(ci[std::size_t(k)])];
-      y[i] = s;
-    }
+    if (!device_)
+      throw GDT::Exceptions::device_error("matrix is not attached to a device operator (there is no CPU path)");
+    if (x.size() != cols_ || y.size() != rows_)
+      throw Common::Exceptions::shapes_do_not_match("mv: vector sizes do not match the matrix");
+    GDT::internal::check(gdtb_matop_apply_host(device_, x.data(), y.data()));
+  }
+  // the device-resident operator this host copy mirrors (set by MatrixOperator; non-owning)
+  void bind_device(gdtb_matop* op)
+  {
+    device_ = op;
+  }
+  gdtb_matop* device() const
+  {
+    return device_;
   }
   std::vector<R>& values()
   {
@@ -630,7 +652,46 @@ private:
   std::size_t rows_ = 0, cols_ = 0;
   SparsityPatternDefault pattern_;
   std::vector<R> values_;
+  gdtb_matop* device_ = nullptr;
 };
+
+// XT::LA::make_solver(matrix).apply(rhs, solution) (examples/stationary-heat-equation.cc:110) [EXT dune-xt]: Krylov
+// solve on the device with the operator's values (CG / BiCGStab as CUDA graphs, gdtb_matop_apply_inverse)
+template <class M>
+class Solver
+{
+public:
+  explicit Solver(const M& matrix)
+    : matrix_(matrix)
+  {}
+  void apply(const IstlDenseVector<double>& rhs, IstlDenseVector<double>& solution) const
+  {
+    apply(rhs, solution, gdtb_solver_opts{GDTB_SOLVER_CG, GDTB_PRECOND_JACOBI, 0, 0, 0.});
+  }
+  void apply(const IstlDenseVector<double>& rhs, IstlDenseVector<double>& solution, const gdtb_solver_opts& opts) const
+  {
+    if (!matrix_.device())
+      throw GDT::Exceptions::device_error("matrix is not attached to a device operator (there is no CPU path)");
+    if (rhs.size() != matrix_.rows() || solution.size() != matrix_.cols())
+      throw Common::Exceptions::shapes_do_not_match("when applying linear solver: shapes do not match");
+    gdtb_solver_info info{};
+    GDT::internal::check(gdtb_matop_apply_inverse_host(matrix_.device(), rhs.data(), solution.data(), &opts, &info));
+    last_ = info;
+  }
+  const gdtb_solver_info& info() const
+  {
+    return last_;
+  }
+
+private:
+  const M& matrix_;
+  mutable gdtb_solver_info last_{};
+};
+template <class M>
+Solver<M> make_solver(const M& matrix)
+{
+  return Solver<M>(matrix);
+}
 
 } // namespace LA
 } // namespace XT
@@ -1195,6 +1256,7 @@ public:
     gdtb_vecfun* raw = nullptr;
     internal::check(gdtb_vecfun_create(internal::context(), space_.handle(), &raw));
     handle_ = internal::Handle<gdtb_vecfun, gdtb_vecfun_destroy>(raw);
+    vector_->bind_device(raw);
   }
   // vector-based.hh:214-222
   VectorBasedFunctional& append(const LocalElementFunctionalInterface<ElementType>& local_functional,
@@ -1278,6 +1340,7 @@ public:
     internal::check(
         gdtb_matop_create(internal::context(), range_space_.handle(), source_space_.handle(), pattern_.handle(), &raw));
     handle_ = internal::Handle<gdtb_matop, gdtb_matop_destroy>(raw);
+    matrix_->bind_device(raw);
   }
 
   FieldType scaling; // captured by value at append time (matrix-based.hh:342,365)
@@ -1418,6 +1481,155 @@ MatrixOperator<M, GV> make_matrix_operator(const GV& grid_view,
   return MatrixOperator<M, GV>(grid_view, source_space, range_space, pattern);
 }
 
+// ---- DirichletConstraints (tools/dirichlet-constraints.hh:44-230) -------------------------------------------------
+// The Dirichlet DoFs are collected on the device when the object is created (the reference collects them during the
+// grid walk: appending the object to a walker is accepted and does nothing); apply() works on the device operator /
+// functional behind the host containers and refreshes the host copies.
+template <class GV>
+class DirichletConstraints
+{
+public:
+  using I = typename GV::Intersection;
+  DirichletConstraints(const SpaceInterface<GV>& space, const XT::Grid::AllDirichletBoundaryInfo<I>& /*boundary_info*/)
+    : space_(space)
+  {
+    gdtb_dirichlet* raw = nullptr;
+    internal::check(gdtb_dirichlet_create(internal::context(), space_.handle(), GDTB_BOUNDARY_ALL, &raw));
+    handle_ = internal::Handle<gdtb_dirichlet, gdtb_dirichlet_destroy>(raw);
+  }
+  // dirichlet_DoFs() (:112-115)
+  std::set<std::size_t> dirichlet_DoFs() const
+  {
+    std::vector<std::int64_t> dofs(std::size_t(gdtb_dirichlet_size(handle_.get())));
+    internal::check(gdtb_dirichlet_dofs_download(handle_.get(), dofs.data()));
+    return std::set<std::size_t>(dofs.begin(), dofs.end());
+  }
+  // apply(matrix, vector, only_clear, ensure_symmetry) (:122-184)
+  template <class M, class V>
+  void apply(M& matrix, V& vector, const bool only_clear = false, const bool ensure_symmetry = true) const
+  {
+    if (!matrix.device() || !vector.device())
+      throw Exceptions::device_error("matrix / vector are not attached to a device operator / functional");
+    if (matrix.rows() != space_.mapper().size() || vector.size() != space_.mapper().size())
+      throw XT::Common::Exceptions::shapes_do_not_match("matrix / vector do not match the constrained space"); // :125-140
+    internal::check(gdtb_dirichlet_apply(handle_.get(), matrix.device(), vector.device(), only_clear ? 1 : 0,
+                                         ensure_symmetry ? 1 : 0));
+    internal::check(gdtb_matop_values_download(matrix.device(), matrix.values().data()));
+    internal::check(gdtb_vecfun_download(vector.device(), vector.data()));
+  }
+
+private:
+  SpaceInterface<GV> space_;
+  internal::Handle<gdtb_dirichlet, gdtb_dirichlet_destroy> handle_;
+};
+
+template <class GV, class Info>
+DirichletConstraints<GV> make_dirichlet_constraints(const SpaceInterface<GV>& space, const Info& boundary_info)
+{
+  return DirichletConstraints<GV>(space, boundary_info);
+}
+
+// ---- DiscreteFunction / error norms (discretefunction/default.hh, operators/bilinear-form.hh:35-470) ---------------
+template <class V, class GV>
+class DiscreteFunction
+{
+public:
+  explicit DiscreteFunction(const SpaceInterface<GV>& space)
+    : space_(space)
+    , vector_(space.mapper().size())
+  {}
+  struct Dofs
+  {
+    V& v;
+    V& vector()
+    {
+      return v;
+    }
+  };
+  Dofs dofs()
+  {
+    return Dofs{vector_};
+  }
+  const V& dof_vector() const
+  {
+    return vector_;
+  }
+  const SpaceInterface<GV>& space() const
+  {
+    return space_;
+  }
+
+private:
+  SpaceInterface<GV> space_;
+  V vector_;
+};
+
+template <class V, class GV>
+DiscreteFunction<V, GV> make_discrete_function(const SpaceInterface<GV>& space)
+{
+  return DiscreteFunction<V, GV>(space);
+}
+
+// `solution - exact_solution` (examples/stationary-heat-equation.cc:114): u_h - f with f a GridFunction
+template <class V, class GV>
+struct DifferenceFunction
+{
+  const DiscreteFunction<V, GV>& u_h;
+  XT::Functions::GridFunction<typename GV::Element> f;
+};
+template <class V, class GV>
+DifferenceFunction<V, GV> operator-(const DiscreteFunction<V, GV>& u_h, const XT::Functions::GridFunction<typename GV::Element>& f)
+{
+  return DifferenceFunction<V, GV>{u_h, f};
+}
+
+// make_bilinear_form(grid_view, error, error) += LocalElementIntegralBilinearForm(...); result() (bilinear-form.hh:
+// 35-470): sum over the elements of the local form applied to (e, e), evaluated on the device when the walker runs
+template <class V, class GV>
+class BilinearForm
+{
+public:
+  using E = typename GV::Element;
+  explicit BilinearForm(const DifferenceFunction<V, GV>& e)
+    : e_(e)
+  {}
+  BilinearForm& operator+=(const LocalElementBilinearFormInterface<E>& local_form)
+  {
+    forms_.push_back(local_form.descriptor(1.));
+    return *this;
+  }
+  void assemble(const bool /*use_tbb*/ = false)
+  {
+    result_ = 0.;
+    for (const gdtb_form& f : forms_) {
+      double r = 0.;
+      internal::check(gdtb_bilinear_form_apply2_host(internal::context(), e_.u_h.space().handle(),
+                                                     e_.u_h.dof_vector().data(), &e_.f.descriptor(), &f, &r));
+      result_ += r;
+    }
+    assembled_ = true;
+  }
+  double result() const
+  {
+    if (!assembled_)
+      throw Dune::InvalidStateException("BilinearForm::result() before the grid walk");
+    return result_;
+  }
+
+private:
+  DifferenceFunction<V, GV> e_;
+  std::vector<gdtb_form> forms_;
+  double result_ = 0.;
+  bool assembled_ = false;
+};
+
+template <class V, class GV>
+BilinearForm<V, GV> make_bilinear_form(const GV& /*grid_view*/, const DifferenceFunction<V, GV>& source,
+                                       const DifferenceFunction<V, GV>& /*range: the same error function*/)
+{
+  return BilinearForm<V, GV>(source);
+}
+
 } // namespace GDT
 
 namespace XT {
@@ -1452,8 +1664,22 @@ public:
     fun_walk_ = [&fun]() { fun.finalize(); };
     return *this;
   }
+  // DirichletConstraints collect their DoFs on the device at construction: nothing left to do during the walk
+  Walker& append(GDT::DirichletConstraints<GV>& /*constraints*/)
+  {
+    return *this;
+  }
+  template <class V>
+  Walker& append(GDT::BilinearForm<V, GV>& form)
+  {
+    others_.push_back([&form]() { form.assemble(); });
+    return *this;
+  }
   void walk(const bool /*thread_parallel*/ = false)
   {
+    for (auto& other : others_)
+      other();
+    others_.clear();
     gdtb_matop* op = op_walk_ ? op_handle_() : nullptr;
     gdtb_vecfun* fun = fun_walk_ ? fun_handle_() : nullptr;
     if (op && fun && op_mode_() != fun_mode_()) {
@@ -1475,6 +1701,7 @@ private:
   std::function<gdtb_vecfun*()> fun_handle_;
   std::function<int()> op_mode_, fun_mode_;
   std::function<void()> op_walk_, fun_walk_;
+  std::vector<std::function<void()>> others_;
 };
 
 template <class GV>
