@@ -7,7 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXAMPLES = os.path.join(ROOT, "dune-gdt_b200", "examples")
-PROGS = ["stationary-heat-equation", "linear-transport-fv"]
+PROGS = ["stationary-heat-equation", "linear-transport-fv", "elliptic-swipdg"]
 
 
 def build_examples():
@@ -35,7 +35,9 @@ def test_examples_fail_loudly_without_a_gpu(gdt):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("args", [["stationary-heat-equation", "128", "2"], ["stationary-heat-equation", "48", "3"],
-                                  ["linear-transport-fv", "1024"]])
+                                  ["linear-transport-fv", "1024"],
+                                  ["elliptic-swipdg"],  # the reference's ESV2007 H^1 table on 8^2, 16^2, 32^2 (3 digits)
+                                  ["elliptic-swipdg", "256"]])
 def test_examples_run(gdt, args):
     build_examples()
     r = subprocess.run([os.path.join(EXAMPLES, args[0])] + args[1:], capture_output=True, text=True, timeout=300)
