@@ -472,7 +472,9 @@ def run_product(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                 "traffic": traffic, "kernel": "k_q1_gather<3,false>", "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_element": alg_bytes / elements_local, "ms_per_launch": per_launch_ms,
-                "peak_source": peak_src}
+                "peak_source": peak_src,
+                "note": "the kernel only writes (no array inputs): the copy-derived peak (half reads, half writes) is "
+                        "not an upper bound for it; a pure fill reaches about 7.4 TB/s on this box (tools/copy_bandwidth.py)"}
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
     e2e_steps = max(1, min(args.steps, 5))
