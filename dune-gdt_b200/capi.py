@@ -91,6 +91,8 @@ PROTOTYPES = {
     "gdtb_space_size": (C.c_int64, [_P]),
     "gdtb_space_max_local_size": (C.c_int32, [_P]),
     "gdtb_space_global_indices": (C.c_int, [_P, C.c_int64, _I64P]),
+    "gdtb_form_quadrature_order": (C.c_int, [_P, C.POINTER(Form), C.c_int, _I32P]),
+    "gdtb_gauss_rule": (C.c_int, [C.c_int, _I32P, _DP, _DP]),
     "gdtb_pattern_create": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _PP]),
     "gdtb_pattern_destroy": (C.c_int, [_P]),
     "gdtb_pattern_rows": (C.c_int64, [_P]),

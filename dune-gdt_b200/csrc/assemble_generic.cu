@@ -138,8 +138,10 @@ __global__ void __launch_bounds__(128)
         }
         double vi, gi[3];
         basis_at<D>(pv, pd, inv_ext, ai0, ai1, ai2, vi, gi);
-        const double w = fn_scalar(term.diffusion, D, e, x);
-        const double fx = fn_scalar(term.weight, D, e, x);
+        const double xh[3] = {f.qx[qx], D > 1 ? f.qx[qy] : 0., D > 2 ? f.qx[qz] : 0.};
+        const EvalPt pt = {qx + m * (qy + my * qz), idx, xh};
+        const double w = fn_scalar(term.diffusion, g, e, x, pt);
+        const double fx = fn_scalar(term.weight, g, e, x, pt);
         const double v = (w * vi) * fx; // conversion.hh:109-116 -> product.hh:126-128
         l += v * ie * wq;               // local/functionals/integrals.hh:96
       }

@@ -106,41 +106,124 @@ int check_ctx(gdtb_ctx* ctx)
   return GDTB_OK;
 }
 
+// SpaceDev of a space on a grid (host arithmetic only): sizes and the MCMG offsets of the continuous mapper
+int make_space_dev(const GridDev& g, int kind, int order, SpaceDev& sp)
+{
+  if (kind < GDTB_SPACE_CG || kind > GDTB_SPACE_FV)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown space kind");
+  const int d = g.d;
+  int K = order;
+  if (kind == GDTB_SPACE_FV)
+    K = 0;
+  else if (kind == GDTB_SPACE_CG && order < 1)
+    return fail(GDTB_ERR_SPACE, "continuous Lagrange spaces need order >= 1");
+  else if (order < 0)
+    return fail(GDTB_ERR_SPACE, "negative polynomial order");
+  if (K > MAX_K || (d == 3 && K > 2))
+    return fail(GDTB_ERR_FINITE_ELEMENT, "Lagrange order not supported (max 3 in 1d/2d, 2 in 3d)");
+  if (kind == GDTB_SPACE_CG && g.periodic)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "continuous Lagrange spaces on periodic grid views are not supported");
+  std::memset(&sp, 0, sizeof(sp));
+  sp.kind = kind;
+  sp.K = K;
+  sp.d = d;
+  sp.nloc = ipow(K + 1, d);
+  if (kind == GDTB_SPACE_CG) {
+    // MCMGMapper offsets: codim 0..d, YaspGrid sub-entity groups by shift bitset (common.cuh)
+    long long running = 0;
+    for (int c = 0; c <= d; ++c) {
+      long long b = 1;
+      for (int j = 0; j < d - c; ++j)
+        b *= (K - 1);
+      sp.cg.block[c] = b;
+      sp.cg.codim_offset[c] = running;
+      long long entities = 0;
+      for (int sh = 0; sh < (1 << d); ++sh) {
+        int pc = 0;
+        for (int k = 0; k < d; ++k)
+          pc += (sh >> k) & 1;
+        if (pc != d - c)
+          continue;
+        sp.cg.group_offset[sh] = entities;
+        long long cnt = 1;
+        for (int k = 0; k < d; ++k)
+          cnt *= ((sh >> k) & 1) ? g.n[k] : g.n[k] + 1;
+        entities += cnt;
+      }
+      running += entities * b;
+    }
+    sp.size = running;
+  } else
+    sp.size = g.ne * sp.nloc;
+  return GDTB_OK;
+}
+
+
 long long function_data_size(const gdtb_function& f, const GridDev& g)
 {
-  if (f.kind == GDTB_FN_ELEM_SCALAR)
-    return g.ne;
-  if (f.kind == GDTB_FN_ELEM_TENSOR)
-    return g.ne * g.d * g.d;
-  return 0;
+  switch (f.kind) {
+    case GDTB_FN_ELEM_SCALAR: return g.ne;
+    case GDTB_FN_ELEM_TENSOR: return g.ne * g.d * g.d;
+    case GDTB_FN_QP_SCALAR: return g.ne * f.qp_per_element;
+    case GDTB_FN_QP_TENSOR: return g.ne * f.qp_per_element * g.d * g.d;
+    case GDTB_FN_DOF_VECTOR: {
+      SpaceDev sp;
+      return make_space_dev(g, f.space_kind, f.space_order, sp) == GDTB_OK ? sp.size : 0;
+    }
+    default: return 0;
+  }
+}
+
+bool fn_has_data(const gdtb_function& f)
+{
+  return f.kind == GDTB_FN_ELEM_SCALAR || f.kind == GDTB_FN_ELEM_TENSOR || f.kind == GDTB_FN_QP_SCALAR
+         || f.kind == GDTB_FN_QP_TENSOR || f.kind == GDTB_FN_DOF_VECTOR;
 }
 
 int validate_function(const gdtb_function& f, const char* what)
 {
-  if (f.kind < GDTB_FN_CONST_SCALAR || f.kind > GDTB_FN_BUILTIN)
+  if (f.kind < GDTB_FN_CONST_SCALAR || f.kind > GDTB_FN_DOF_VECTOR)
     return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": unknown function kind");
   if (f.kind == GDTB_FN_BUILTIN && (f.builtin < GDTB_BUILTIN_COS_PRODUCT || f.builtin > GDTB_BUILTIN_QUADRATIC))
     return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": unknown built-in function id");
-  if ((f.kind == GDTB_FN_ELEM_SCALAR || f.kind == GDTB_FN_ELEM_TENSOR) && !f.data)
-    return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": per-element function without data");
+  if (fn_has_data(f) && !f.data)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": array-backed function without data");
+  if ((f.kind == GDTB_FN_QP_SCALAR || f.kind == GDTB_FN_QP_TENSOR) && f.qp_per_element < 1)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": per-quadrature-point function needs qp_per_element >= 1");
   if (f.order < 0)
     return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": negative polynomial order");
   return GDTB_OK;
 }
 
-// clone-on-append of a grid function: host arrays are copied to the device
+// clone-on-append of a grid function: host arrays are copied to the device; a discrete function also gets a
+// device-resident copy of its space description (the mapper the kernels evaluate it through)
 int lower_function(gdtb_ctx* ctx, const GridDev& g, gdtb_function& f, LoweredForm& owner)
 {
+  if (f.kind == GDTB_FN_DOF_VECTOR) {
+    SpaceDev sp;
+    GDTB_TRY(make_space_dev(g, f.space_kind, f.space_order, sp));
+  }
   const long long n = function_data_size(f, g);
   if (n > 0 && !f.data_on_device) {
     double* d = nullptr;
     if (cudaMalloc(&d, sizeof(double) * (size_t)n) != cudaSuccess)
-      return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory while cloning a per-element function");
+      return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory while cloning an array-backed grid function");
     owner.owned.push_back(d);
     GDTB_CUDA(cudaMemcpyAsync(d, f.data, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->launch.stream));
     GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
     f.data = d;
     f.data_on_device = 1;
+  }
+  if (f.kind == GDTB_FN_DOF_VECTOR) {
+    SpaceDev sp;
+    GDTB_TRY(make_space_dev(g, f.space_kind, f.space_order, sp));
+    void* d = nullptr;
+    if (cudaMalloc(&d, sizeof(SpaceDev)) != cudaSuccess)
+      return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory while cloning a discrete function");
+    owner.owned.push_back(static_cast<double*>(d));
+    GDTB_CUDA(cudaMemcpyAsync(d, &sp, sizeof(SpaceDev), cudaMemcpyHostToDevice, ctx->launch.stream));
+    GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+    owner.dof_spaces.emplace_back(f.data, static_cast<const SpaceDev*>(d));
   }
   return GDTB_OK;
 }
@@ -167,16 +250,21 @@ int lower_form(gdtb_ctx* ctx, const GridDev& g, const gdtb_form* form, int filte
   return GDTB_OK;
 }
 
-FnDev to_dev(const gdtb_function& f)
+FnDev to_dev(const gdtb_function& f, const LoweredForm* owner = nullptr)
 {
   FnDev d;
   d.kind = f.kind;
   d.order = f.order;
   d.builtin = f.builtin;
-  d.pad = 0;
+  d.nq = f.qp_per_element;
   std::memcpy(d.c, f.c, sizeof(d.c));
   std::memcpy(d.p, f.p, sizeof(d.p));
   d.data = f.data;
+  d.space = nullptr;
+  if (owner)
+    for (const auto& ds : owner->dof_spaces)
+      if (ds.first == f.data)
+        d.space = ds.second;
   return d;
 }
 
@@ -214,7 +302,7 @@ int form_quadrature_order(const gdtb_form& f, int K, FormRole role)
   return order + f.over_integrate;
 }
 
-int make_form_dev(const gdtb_form& f, int K, FormRole role, FormDev& out)
+int make_form_dev(const gdtb_form& f, int K, FormRole role, FormDev& out, const LoweredForm* owner = nullptr)
 {
   std::memset(&out, 0, sizeof(out));
   out.n_terms = f.n_terms;
@@ -232,9 +320,33 @@ int make_form_dev(const gdtb_form& f, int K, FormRole role, FormDev& out)
     d.kind = f.terms[t].kind;
     d.hI_kind = f.terms[t].hI_kind;
     d.prefactor = f.terms[t].prefactor;
-    d.diffusion = to_dev(f.terms[t].diffusion);
-    d.weight = to_dev(f.terms[t].weight);
+    d.diffusion = to_dev(f.terms[t].diffusion, owner);
+    d.weight = to_dev(f.terms[t].weight, owner);
   }
+  return GDTB_OK;
+}
+
+// caller-sampled coefficient arrays must have been sampled for the rule the form is integrated with
+int check_qp_functions(const gdtb_form& f, int K, FormRole role, int d)
+{
+  bool any = false;
+  for (int t = 0; t < f.n_terms; ++t)
+    for (const gdtb_function* fn : {&f.terms[t].diffusion, &f.terms[t].weight})
+      any = any || fn->kind == GDTB_FN_QP_SCALAR || fn->kind == GDTB_FN_QP_TENSOR;
+  if (!any)
+    return GDTB_OK;
+  if (role == ROLE_COUPLING || role == ROLE_BOUNDARY)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED,
+                "per-quadrature-point functions (GDTB_FN_QP_*) are volume-rule data: element forms and functionals only");
+  const int m = gauss_points_for_order(form_quadrature_order(f, K, role));
+  const int nq = ipow(m, d);
+  for (int t = 0; t < f.n_terms; ++t)
+    for (const gdtb_function* fn : {&f.terms[t].diffusion, &f.terms[t].weight})
+      if ((fn->kind == GDTB_FN_QP_SCALAR || fn->kind == GDTB_FN_QP_TENSOR) && fn->qp_per_element != nq)
+        return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH,
+                    "per-quadrature-point function: qp_per_element = " + std::to_string(fn->qp_per_element)
+                        + " but the form is integrated with " + std::to_string(nq) + " points per element ("
+                        + std::to_string(m) + " per direction; see gdtb_form_quadrature_order / gdtb_gauss_rule)");
   return GDTB_OK;
 }
 
@@ -265,7 +377,7 @@ bool matop_q1_eligible(const gdtb_matop* op)
     for (int t = 0; t < lf.form.n_terms; ++t) {
       const gdtb_integrand& in = lf.form.terms[t];
       if (in.kind == GDTB_INT_LAPLACE) {
-        if (in.diffusion.kind == GDTB_FN_BUILTIN)
+        if (in.diffusion.kind >= GDTB_FN_BUILTIN) // varies inside a cell: analytic, per quadrature point, discrete
           return false;
       } else if (in.kind == GDTB_INT_PRODUCT) {
         if (in.diffusion.kind != GDTB_FN_CONST_SCALAR && in.diffusion.kind != GDTB_FN_ELEM_SCALAR)
@@ -762,58 +874,6 @@ int64_t gdtb_grid_num_elements(const gdtb_grid* grid)
   return grid ? grid->dev.ne : 0;
 }
 
-// SpaceDev of a space on a grid (host arithmetic only): sizes and the MCMG offsets of the continuous mapper
-static int make_space_dev(const GridDev& g, int kind, int order, SpaceDev& sp)
-{
-  if (kind < GDTB_SPACE_CG || kind > GDTB_SPACE_FV)
-    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown space kind");
-  const int d = g.d;
-  int K = order;
-  if (kind == GDTB_SPACE_FV)
-    K = 0;
-  else if (kind == GDTB_SPACE_CG && order < 1)
-    return fail(GDTB_ERR_SPACE, "continuous Lagrange spaces need order >= 1");
-  else if (order < 0)
-    return fail(GDTB_ERR_SPACE, "negative polynomial order");
-  if (K > MAX_K || (d == 3 && K > 2))
-    return fail(GDTB_ERR_FINITE_ELEMENT, "Lagrange order not supported (max 3 in 1d/2d, 2 in 3d)");
-  if (kind == GDTB_SPACE_CG && g.periodic)
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "continuous Lagrange spaces on periodic grid views are not supported");
-  std::memset(&sp, 0, sizeof(sp));
-  sp.kind = kind;
-  sp.K = K;
-  sp.d = d;
-  sp.nloc = ipow(K + 1, d);
-  if (kind == GDTB_SPACE_CG) {
-    // MCMGMapper offsets: codim 0..d, YaspGrid sub-entity groups by shift bitset (common.cuh)
-    long long running = 0;
-    for (int c = 0; c <= d; ++c) {
-      long long b = 1;
-      for (int j = 0; j < d - c; ++j)
-        b *= (K - 1);
-      sp.cg.block[c] = b;
-      sp.cg.codim_offset[c] = running;
-      long long entities = 0;
-      for (int sh = 0; sh < (1 << d); ++sh) {
-        int pc = 0;
-        for (int k = 0; k < d; ++k)
-          pc += (sh >> k) & 1;
-        if (pc != d - c)
-          continue;
-        sp.cg.group_offset[sh] = entities;
-        long long cnt = 1;
-        for (int k = 0; k < d; ++k)
-          cnt *= ((sh >> k) & 1) ? g.n[k] : g.n[k] + 1;
-        entities += cnt;
-      }
-      running += entities * b;
-    }
-    sp.size = running;
-  } else
-    sp.size = g.ne * sp.nloc;
-  return GDTB_OK;
-}
-
 int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order, gdtb_space** out)
 {
   if (!ctx || !grid || !out)
@@ -922,6 +982,38 @@ int gdtb_space_global_indices(const gdtb_space* space, int64_t element, int64_t*
   elem_coords(space->grid, element, idx);
   for (int i = 0; i < space->dev.nloc; ++i)
     out[i] = global_index(space->grid, space->dev, idx, i);
+  return GDTB_OK;
+}
+
+// ---- quadrature ----------------------------------------------------------------------------------
+int gdtb_form_quadrature_order(const gdtb_space* space, const gdtb_form* form, int role, int32_t* order)
+{
+  if (!space || !form || !order)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_form_quadrature_order: NULL argument");
+  if (form->n_terms < 1 || form->n_terms > GDTB_MAX_TERMS)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "form: n_terms must be in [1, GDTB_MAX_TERMS]");
+  FormRole r;
+  switch (role) {
+    case GDTB_ROLE_ELEMENT: r = ROLE_ELEMENT; break;
+    case GDTB_ROLE_FUNCTIONAL: r = ROLE_RHS; break;
+    case GDTB_ROLE_COUPLING: r = ROLE_COUPLING; break;
+    case GDTB_ROLE_BOUNDARY: r = ROLE_BOUNDARY; break;
+    default: return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_form_quadrature_order: unknown role");
+  }
+  *order = form_quadrature_order(*form, space->dev.K, r);
+  return GDTB_OK;
+}
+
+int gdtb_gauss_rule(int order, int32_t* m, double* points01, double* weights)
+{
+  if (!m)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_gauss_rule: NULL argument");
+  const int mm = gauss_points_for_order(order);
+  *m = mm;
+  if (mm > MAX_Q1D)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "quadrature order too high (more than 8 Gauss points per direction)");
+  if (points01 && weights)
+    gauss_legendre_01(mm, points01, weights);
   return GDTB_OK;
 }
 
@@ -1117,6 +1209,8 @@ int gdtb_matop_append_element(gdtb_matop* op, const gdtb_form* form)
     for (int t = 0; t < form->n_terms && t < GDTB_MAX_TERMS; ++t)
       if (form->terms[t].kind != GDTB_INT_LAPLACE && form->terms[t].kind != GDTB_INT_PRODUCT)
         return fail(GDTB_ERR_INTEGRAND, "element bilinear forms take Laplace / product integrands");
+  if (form && form->n_terms >= 1 && form->n_terms <= GDTB_MAX_TERMS)
+    GDTB_TRY(check_qp_functions(*form, op->test.K, ROLE_ELEMENT, op->grid.d));
   LoweredForm lf;
   GDTB_TRY(lower_form(op->ctx, op->grid, form, 0, lf));
   op->element_forms.push_back(std::move(lf));
@@ -1136,6 +1230,8 @@ int gdtb_matop_append_coupling(gdtb_matop* op, const gdtb_form* form, int filter
     for (int t = 0; t < form->n_terms && t < GDTB_MAX_TERMS; ++t)
       if (form->terms[t].kind != GDTB_INT_IPDG_INNER_COUPLING && form->terms[t].kind != GDTB_INT_IPDG_INNER_PENALTY)
         return fail(GDTB_ERR_INTEGRAND, "This integrand cannot be used on an inner intersection!");
+  if (form && form->n_terms >= 1 && form->n_terms <= GDTB_MAX_TERMS)
+    GDTB_TRY(check_qp_functions(*form, op->test.K, ROLE_COUPLING, op->grid.d));
   LoweredForm lf;
   GDTB_TRY(lower_form(op->ctx, op->grid, form, filter, lf));
   op->coupling_forms.push_back(std::move(lf));
@@ -1156,6 +1252,8 @@ int gdtb_matop_append_boundary(gdtb_matop* op, const gdtb_form* form, int filter
       if (form->terms[t].kind != GDTB_INT_IPDG_DIRICHLET_COUPLING
           && form->terms[t].kind != GDTB_INT_IPDG_BOUNDARY_PENALTY)
         return fail(GDTB_ERR_INTEGRAND, "This integrand cannot be used on a boundary intersection!"); // ipdg.hh:93-94
+  if (form && form->n_terms >= 1 && form->n_terms <= GDTB_MAX_TERMS)
+    GDTB_TRY(check_qp_functions(*form, op->test.K, ROLE_BOUNDARY, op->grid.d));
   LoweredForm lf;
   GDTB_TRY(lower_form(op->ctx, op->grid, form, filter, lf));
   op->boundary_forms.push_back(std::move(lf));
@@ -1442,6 +1540,8 @@ int gdtb_vecfun_append_element(gdtb_vecfun* fun, const gdtb_form* form)
   GDTB_TRY(check_ctx(fun->ctx));
   if (form && (form->n_terms != 1 || form->terms[0].kind != GDTB_INT_PRODUCT))
     return fail(GDTB_ERR_INTEGRAND, "element functionals take LocalProductIntegrand(w).with_ansatz(f) (one term)");
+  if (form)
+    GDTB_TRY(check_qp_functions(*form, fun->space.K, ROLE_RHS, fun->grid.d));
   LoweredForm lf;
   GDTB_TRY(lower_form(fun->ctx, fun->grid, form, 0, lf));
   fun->forms.push_back(std::move(lf));
@@ -1682,15 +1782,15 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     std::vector<FormDev> forms;
     for (const auto& lf : op->element_forms) {
       forms.emplace_back();
-      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_ELEMENT, forms.back()));
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_ELEMENT, forms.back(), &lf));
     }
     for (const auto& lf : op->coupling_forms) {
       forms.emplace_back();
-      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_COUPLING, forms.back()));
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_COUPLING, forms.back(), &lf));
     }
     for (const auto& lf : op->boundary_forms) {
       forms.emplace_back();
-      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_BOUNDARY, forms.back()));
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_BOUNDARY, forms.back(), &lf));
     }
     const size_t bytes = sizeof(FormDev) * forms.size();
     if (op->d_forms_bytes < bytes) {
@@ -1738,19 +1838,19 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pat->nnz, L.stream));
     for (const auto& lf : op->element_forms) {
       FormDev fd;
-      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_ELEMENT, fd));
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_ELEMENT, fd, &lf));
       GDTB_TRY(launch_element_matrix(L, op->grid, op->test, fd, pat->d_rowptr, pat->d_colidx, op->d_values,
                                      ctx->d_error_flag));
     }
     for (const auto& lf : op->coupling_forms) {
       FormDev fd;
-      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_COUPLING, fd));
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_COUPLING, fd, &lf));
       GDTB_TRY(launch_coupling_matrix(L, op->grid, op->test, fd, lf.filter, pat->d_rowptr, pat->d_colidx,
                                       op->d_values, ctx->d_error_flag));
     }
     for (const auto& lf : op->boundary_forms) {
       FormDev fd;
-      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_BOUNDARY, fd));
+      GDTB_TRY(make_form_dev(lf.form, op->test.K, ROLE_BOUNDARY, fd, &lf));
       GDTB_TRY(launch_boundary_matrix(L, op->grid, op->test, fd, pat->d_rowptr, pat->d_colidx, op->d_values,
                                       ctx->d_error_flag));
     }
@@ -1761,7 +1861,7 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)fun->space.size, L.stream));
     for (const auto& lf : fun->forms) {
       FormDev fd;
-      GDTB_TRY(make_form_dev(lf.form, fun->space.K, ROLE_RHS, fd));
+      GDTB_TRY(make_form_dev(lf.form, fun->space.K, ROLE_RHS, fd, &lf));
       GDTB_TRY(launch_element_vector(L, fun->grid, fun->space, fd, fun->d_vec));
     }
   }
@@ -1830,7 +1930,9 @@ int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* fl
   for (long long i = 0; i < L->inv_ext_shift; ++i)
     ext.push_back(1. / ext[(size_t)i]);
   if (cudaMalloc(&L->d_ext, sizeof(double) * ext.size()) != cudaSuccess
-      || cudaMemcpy(L->d_ext, ext.data(), sizeof(double) * ext.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      || cudaMemcpyAsync(L->d_ext, ext.data(), sizeof(double) * ext.size(), cudaMemcpyHostToDevice, ctx->launch.stream)
+             != cudaSuccess
+      || cudaStreamSynchronize(ctx->launch.stream) != cudaSuccess) {
     cudaFree(L->d_ext);
     delete L;
     return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (fv geometry tables)");
@@ -2766,17 +2868,25 @@ int gdtb_fv_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_funct
   if (space->dev.kind != GDTB_SPACE_FV)
     return fail(GDTB_ERR_SPACE, "gdtb_fv_interpolate needs a finite volume space");
   GDTB_TRY(validate_function(*f, "function"));
-  if ((f->kind == GDTB_FN_ELEM_SCALAR || f->kind == GDTB_FN_ELEM_TENSOR) && !f->data_on_device)
-    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fv_interpolate: per-element data must live on the device");
+  if (fn_has_data(*f) && !f->data_on_device)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fv_interpolate: array-backed function data must live on the device");
+  if (f->kind == GDTB_FN_DOF_VECTOR || f->kind == GDTB_FN_QP_TENSOR || f->kind == GDTB_FN_ELEM_TENSOR
+      || f->kind == GDTB_FN_CONST_TENSOR)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "gdtb_fv_interpolate: f must be a scalar constant, per-element, "
+                                          "per-quadrature-point or analytic function");
   const int m = gauss_points_for_order(f->order);
   if (m > MAX_Q1D)
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "quadrature order too high");
+  if (f->kind == GDTB_FN_QP_SCALAR && f->qp_per_element != ipow(m, space->grid.d))
+    return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH,
+                "gdtb_fv_interpolate: qp_per_element does not match the Gauss rule of the function's declared order");
   double host[2 * MAX_Q1D] = {0};
   gauss_legendre_01(m, host, host + MAX_Q1D);
   double* d_rule = nullptr;
   if (cudaMalloc(&d_rule, sizeof(host)) != cudaSuccess)
     return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory");
-  cudaError_t err = cudaMemcpy(d_rule, host, sizeof(host), cudaMemcpyHostToDevice);
+  // on the context's own stream: a blocking copy on the legacy stream is not ordered against a non-blocking stream
+  cudaError_t err = cudaMemcpyAsync(d_rule, host, sizeof(host), cudaMemcpyHostToDevice, ctx->launch.stream);
   int st = GDTB_OK;
   if (err == cudaSuccess)
     st = launch_fv_interpolate(ctx->launch, space->grid, to_dev(*f), m, d_rule, d_rule + MAX_Q1D, d_u);
@@ -2828,8 +2938,8 @@ int internal_lower_function(gdtb_ctx* ctx, const GridDev& g, gdtb_function& f, L
 {
   return lower_function(ctx, g, f, owner);
 }
-FnDev internal_to_dev(const gdtb_function& f)
+FnDev internal_to_dev(const gdtb_function& f, const LoweredForm* owner)
 {
-  return to_dev(f);
+  return to_dev(f, owner);
 }
 } // namespace gdtb

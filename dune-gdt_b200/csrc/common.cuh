@@ -80,10 +80,11 @@ struct FnDev
   int kind;
   int order;
   int builtin;
-  int pad;
+  int nq; // GDTB_FN_QP_*: quadrature points per element of the sampled array
   double c[9];
   double p[8];
-  const double* data; // device pointer
+  const double* data;    // device pointer
+  const SpaceDev* space; // GDTB_FN_DOF_VECTOR: the discrete function's space (device-resident copy)
 };
 
 struct IntegrandDev
@@ -291,6 +292,98 @@ __host__ __device__ inline void builtin_grad(const FnDev& f, int d, const double
   }
 }
 
+// 1D Lagrange basis of order K on the equidistant nodes a / K at x in [0, 1] (values only)
+__host__ __device__ inline void lagrange_values_1d(int K, double x, double* v)
+{
+  if (K == 0) {
+    v[0] = 1.;
+    return;
+  }
+  for (int a = 0; a <= K; ++a) {
+    const double ta = double(a) / K;
+    double val = 1.;
+    for (int b = 0; b <= K; ++b)
+      if (b != a)
+        val *= (x - double(b) / K) / (ta - double(b) / K);
+    v[a] = val;
+  }
+}
+
+// Where a grid function is evaluated: index of the point inside the element's volume rule (GDTB_FN_QP_*: caller-sampled
+// arrays are indexed [element][q]; q < 0: no rule context) and the element / reference point (GDTB_FN_DOF_VECTOR)
+struct EvalPt
+{
+  int q;
+  const long long* idx;
+  const double* xh;
+};
+
+// u_h(x) = sum_i dofs[global_index(e, i)] phi_i(xhat) (LocalDiscreteFunction::evaluate, discretefunction/default.hh)
+__device__ inline double dof_vector_eval(const FnDev& f, const GridDev& g, const long long* idx, const double* xh)
+{
+  const SpaceDev sp = *f.space;
+  double v[3][MAX_K + 1];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k < g.d)
+      lagrange_values_1d(sp.K, xh[k], v[k]);
+    else
+      v[k][0] = 1.;
+  }
+  const int n1 = sp.K + 1;
+  double u = 0.;
+  for (int i = 0; i < sp.nloc; ++i) {
+    const int a0 = i % n1, a1 = g.d > 1 ? (i / n1) % n1 : 0, a2 = g.d > 2 ? i / (n1 * n1) : 0;
+    u += __ldg(f.data + global_index(g, sp, idx, i)) * (v[0][a0] * v[1][a1] * v[2][a2]);
+  }
+  return u;
+}
+
+__device__ inline double fn_scalar(const FnDev& f, const GridDev& g, long long e, const double* x, const EvalPt& pt)
+{
+  switch (f.kind) {
+    case GDTB_FN_ELEM_SCALAR:
+      return __ldg(f.data + e);
+    case GDTB_FN_BUILTIN:
+      return builtin_eval(f, g.d, x);
+    case GDTB_FN_QP_SCALAR:
+      return __ldg(f.data + e * f.nq + pt.q);
+    case GDTB_FN_DOF_VECTOR:
+      return dof_vector_eval(f, g, pt.idx, pt.xh);
+    default:
+      return f.c[0];
+  }
+}
+
+// d x d tensor, row-major with leading dimension 3; scalar kinds mean c * I (laplace.hh:41)
+__device__ inline void fn_tensor(const FnDev& f, const GridDev& g, long long e, const double* x, const EvalPt& pt,
+                                 double* T)
+{
+  const int d = g.d;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    T[i] = 0.;
+  if (f.kind == GDTB_FN_CONST_TENSOR) {
+    for (int r = 0; r < d; ++r)
+      for (int c = 0; c < d; ++c)
+        T[r * 3 + c] = f.c[r * d + c];
+  } else if (f.kind == GDTB_FN_ELEM_TENSOR) {
+    for (int r = 0; r < d; ++r)
+      for (int c = 0; c < d; ++c)
+        T[r * 3 + c] = __ldg(f.data + e * d * d + r * d + c);
+  } else if (f.kind == GDTB_FN_QP_TENSOR) {
+    const double* src = f.data + (e * f.nq + pt.q) * (d * d);
+    for (int r = 0; r < d; ++r)
+      for (int c = 0; c < d; ++c)
+        T[r * 3 + c] = __ldg(src + r * d + c);
+  } else {
+    const double s = fn_scalar(f, g, e, x, pt);
+    for (int r = 0; r < d; ++r)
+      T[r * 3 + r] = s;
+  }
+}
+
+// variants without a point context (constants, per-element data, analytic built-ins)
 __device__ inline double fn_scalar(const FnDev& f, int d, long long e, const double* x)
 {
   switch (f.kind) {

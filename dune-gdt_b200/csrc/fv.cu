@@ -522,7 +522,9 @@ __global__ void __launch_bounds__(256) k_fv_interpolate(const GridDev g, const F
             x[k] = lower[k] + qx[q[k]] * ext[k];
             w *= qw[q[k]];
           }
-          integral += fn_scalar(f, D, e, x) * vol * w;
+          const double xh[3] = {qx[q0], D > 1 ? qx[qy] : 0., D > 2 ? qx[qz] : 0.};
+          const EvalPt pt = {q0 + m * (qy + my * qz), idx, xh};
+          integral += fn_scalar(f, g, e, x, pt) * vol * w;
         }
     u[e] = integral / vol; // spaces/basis/finite-volume.hh:249-250
   }

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -61,6 +62,8 @@ struct LoweredForm
 {
   gdtb_form form;                // cloned descriptor (data pointers replaced by device pointers)
   std::vector<double*> owned;    // device arrays cloned from host data
+  // discrete functions (GDTB_FN_DOF_VECTOR): DoF array -> device-resident copy of the function's space description
+  std::vector<std::pair<const double*, const SpaceDev*>> dof_spaces;
   int filter;
 };
 
@@ -186,5 +189,5 @@ void lagrange_1d(int K, double x, double* v, double* dv);
 int internal_check_ctx(gdtb_ctx* ctx);
 int internal_validate_function(const gdtb_function& f, const char* what);
 int internal_lower_function(gdtb_ctx* ctx, const GridDev& g, gdtb_function& f, LoweredForm& owner);
-FnDev internal_to_dev(const gdtb_function& f);
+FnDev internal_to_dev(const gdtb_function& f, const LoweredForm* owner = nullptr);
 } // namespace gdtb

@@ -197,11 +197,13 @@ __device__ inline void element_row(const GridDev& g, const FormDev& f, const Tab
         // coefficients of the summands at this point
         double kap[GDTB_MAX_TERMS][9];
         double wgt[GDTB_MAX_TERMS];
+        const double xh[3] = {f.qx[qx], D > 1 ? f.qx[qy] : 0., D > 2 ? f.qx[qz] : 0.};
+        const EvalPt pt = {qx + m * (qy + my * qz), idx, xh};
         for (int tt = 0; tt < f.n_terms; ++tt) {
           if (f.terms[tt].kind == GDTB_INT_LAPLACE)
-            fn_tensor(f.terms[tt].diffusion, D, e, x, kap[tt]);
+            fn_tensor(f.terms[tt].diffusion, g, e, x, pt, kap[tt]);
           else
-            wgt[tt] = fn_scalar(f.terms[tt].diffusion, D, e, x);
+            wgt[tt] = fn_scalar(f.terms[tt].diffusion, g, e, x, pt);
         }
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -266,16 +268,17 @@ __device__ inline void coupling_row(const GridDev& g, const FormDev& f, const Ta
       for (int tt = 0; tt < f.n_terms; ++tt) {
         const IntegrandDev& in = f.terms[tt];
         double w_in[9], w_out[9], wn[3];
-        fn_tensor(in.weight, D, e_in, x_in, w_in);
-        fn_tensor(in.weight, D, e_out, x_out, w_out);
+        const EvalPt p_in = {-1, idx_in, xh_in}, p_out = {-1, idx_out, xh_out};
+        fn_tensor(in.weight, g, e_in, x_in, p_in, w_in);
+        fn_tensor(in.weight, g, e_out, x_out, p_out, w_out);
         matvecD<D>(w_out, face.normal, wn);
         const double delta_plus = dotD<D>(face.normal, wn);
         matvecD<D>(w_in, face.normal, wn);
         const double delta_minus = dotD<D>(face.normal, wn);
         if (in.kind == GDTB_INT_IPDG_INNER_COUPLING) {
           double k_in[9], k_out[9], kg[3];
-          fn_tensor(in.diffusion, D, e_in, x_in, k_in);
-          fn_tensor(in.diffusion, D, e_out, x_out, k_out);
+          fn_tensor(in.diffusion, g, e_in, x_in, p_in, k_in);
+          fn_tensor(in.diffusion, g, e_out, x_out, p_out, k_out);
           const double weight_minus = delta_plus / (delta_plus + delta_minus);
           const double weight_plus = delta_minus / (delta_plus + delta_minus);
           const double sp_ = in.prefactor;
@@ -362,9 +365,10 @@ __device__ inline void boundary_row(const GridDev& g, const FormDev& f, const Ta
         va[j] = 0.;
       for (int tt = 0; tt < f.n_terms; ++tt) {
         const IntegrandDev& in = f.terms[tt];
+        const EvalPt pt = {-1, idx, xh};
         if (in.kind == GDTB_INT_IPDG_DIRICHLET_COUPLING) { // laplace-ipdg.hh:362-367
           double kap[9], kg[3];
-          fn_tensor(in.diffusion, D, e, x, kap);
+          fn_tensor(in.diffusion, g, e, x, pt, kap);
           matvecD<D>(kap, gi, kg);
           const double fi = dotD<D>(kg, face.normal);
 #pragma unroll
@@ -378,7 +382,7 @@ __device__ inline void boundary_row(const GridDev& g, const FormDev& f, const Ta
           }
         } else { // GDTB_INT_IPDG_BOUNDARY_PENALTY, ipdg.hh:276-281
           double w[9], wn[3];
-          fn_tensor(in.weight, D, e, x, w);
+          fn_tensor(in.weight, g, e, x, pt, w);
           matvecD<D>(w, face.normal, wn);
           const double h = intersection_h<D>(in, face, ext, ext, false);
           const double penalty = (in.prefactor * dotD<D>(face.normal, wn)) / h;

@@ -464,10 +464,12 @@ __global__ void __launch_bounds__(RED_BLOCK)
               grad[k] -= fg[k];
           }
           double v = 0.;
+          const double xh[3] = {F.qx[qx], D > 1 ? F.qx[qy] : 0., D > 2 ? F.qx[qz] : 0.};
+          const EvalPt pt = {qx + m * (qy + my * qz), idx, xh};
           for (int t = 0; t < F.n_terms; ++t) {
             if (F.terms[t].kind == GDTB_INT_LAPLACE) {
               double kap[9], kg[3] = {0., 0., 0.};
-              fn_tensor(F.terms[t].diffusion, D, e, x, kap);
+              fn_tensor(F.terms[t].diffusion, g, e, x, pt, kap);
               for (int r = 0; r < D; ++r)
                 for (int c = 0; c < D; ++c)
                   kg[r] += kap[r * 3 + c] * grad[c];
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__(RED_BLOCK)
                 s += kg[r] * grad[r];
               v += s; // laplace.hh:101
             } else
-              v += (fn_scalar(F.terms[t].diffusion, D, e, x) * val) * val; // product.hh:128
+              v += (fn_scalar(F.terms[t].diffusion, g, e, x, pt) * val) * val; // product.hh:128
           }
           local += v * (ie * w); // integrals.hh:119,131
         }
@@ -894,6 +896,10 @@ static int dirichlet_apply_impl(gdtb_dirichlet* dc, long long rows, long long co
 {
   gdtb_ctx* ctx = dc->ctx;
   Launch& L = ctx->launch;
+  // the kernel below reuses the context's device error flag: report a pending out-of-pattern error of an earlier
+  // asynchronous assembly first instead of clearing it
+  if (ctx->error_flag_pending)
+    GDTB_TRY(gdtb_ctx_synchronize(ctx));
   if (d_values) {
     // dirichlet-constraints.hh is only meaningful for square operators on the constrained space
     if (rows != dc->space.size || cols != dc->space.size)
@@ -1007,9 +1013,12 @@ int gdtb_matop_apply_host(gdtb_matop* op, const double* source, double* range)
   DeviceBuffer s, r;
   GDTB_TRY(s.alloc(sizeof(double) * (size_t)op->ansatz.size));
   GDTB_TRY(r.alloc(sizeof(double) * (size_t)op->test.size));
-  GDTB_CUDA(cudaMemcpy(s.p, source, sizeof(double) * (size_t)op->ansatz.size, cudaMemcpyHostToDevice));
+  // uploads on the context's stream: a blocking copy on the legacy stream is not ordered against a non-blocking stream
+  cudaStream_t st = op->ctx->launch.stream;
+  GDTB_CUDA(cudaMemcpyAsync(s.p, source, sizeof(double) * (size_t)op->ansatz.size, cudaMemcpyHostToDevice, st));
   GDTB_TRY(gdtb_matop_apply(op, s.as<double>(), r.as<double>()));
-  GDTB_CUDA(cudaMemcpy(range, r.p, sizeof(double) * (size_t)op->test.size, cudaMemcpyDeviceToHost));
+  GDTB_CUDA(cudaMemcpyAsync(range, r.p, sizeof(double) * (size_t)op->test.size, cudaMemcpyDeviceToHost, st));
+  GDTB_CUDA(cudaStreamSynchronize(st));
   return GDTB_OK;
 }
 
@@ -1049,10 +1058,12 @@ int gdtb_matop_apply_inverse_host(gdtb_matop* op, const double* rhs, double* x, 
   DeviceBuffer b, sol;
   GDTB_TRY(b.alloc(bytes));
   GDTB_TRY(sol.alloc(bytes));
-  GDTB_CUDA(cudaMemcpy(b.p, rhs, bytes, cudaMemcpyHostToDevice));
-  GDTB_CUDA(cudaMemcpy(sol.p, x, bytes, cudaMemcpyHostToDevice));
+  cudaStream_t stream = op->ctx->launch.stream;
+  GDTB_CUDA(cudaMemcpyAsync(b.p, rhs, bytes, cudaMemcpyHostToDevice, stream));
+  GDTB_CUDA(cudaMemcpyAsync(sol.p, x, bytes, cudaMemcpyHostToDevice, stream));
   const int st = gdtb_matop_apply_inverse(op, b.as<double>(), sol.as<double>(), opts, info);
-  GDTB_CUDA(cudaMemcpy(x, sol.p, bytes, cudaMemcpyDeviceToHost));
+  GDTB_CUDA(cudaMemcpyAsync(x, sol.p, bytes, cudaMemcpyDeviceToHost, stream));
+  GDTB_CUDA(cudaStreamSynchronize(stream));
   return st;
 }
 
@@ -1080,6 +1091,9 @@ int gdtb_bilinear_form_apply2(gdtb_ctx* ctx, const gdtb_space* space, const doub
     return fail(GDTB_ERR_INVALID_ARGUMENT, "form: n_terms must be in [1, GDTB_MAX_TERMS]");
   if (f) {
     GDTB_TRY(internal_validate_function(*f, "apply2: f"));
+    if (f->kind > GDTB_FN_BUILTIN)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "apply2: f must be a constant, per-element or analytic function (a discrete "
+                                            "function enters through the DoF vector argument)");
     if (f->kind == GDTB_FN_CONST_TENSOR || f->kind == GDTB_FN_ELEM_TENSOR)
       return fail(GDTB_ERR_INVALID_ARGUMENT, "apply2: f must be scalar");
   }
@@ -1098,7 +1112,7 @@ int gdtb_bilinear_form_apply2(gdtb_ctx* ctx, const gdtb_space* space, const doub
   if (f) {
     ff = *f;
     status = internal_lower_function(ctx, g, ff, owner);
-    P->f = internal_to_dev(ff);
+    P->f = internal_to_dev(ff, &owner);
   }
   // order of the one-function basis: the discrete function's order, or the declared order of f if that is higher
   const int e_order = std::max(d_dofs ? sp.K : 0, f ? f->order : 0);
@@ -1118,7 +1132,7 @@ int gdtb_bilinear_form_apply2(gdtb_ctx* ctx, const gdtb_space* space, const doub
     order = std::max(order, in.diffusion.order + e_order + e_order); // laplace.hh:74-79, product.hh:89-100
     F.terms[t].kind = in.kind;
     F.terms[t].prefactor = in.prefactor;
-    F.terms[t].diffusion = internal_to_dev(in.diffusion);
+    F.terms[t].diffusion = internal_to_dev(in.diffusion, &owner);
   }
   if (status == GDTB_OK) {
     F.m = gauss_points_for_order(order + fm.over_integrate);
@@ -1162,7 +1176,8 @@ int gdtb_bilinear_form_apply2_host(gdtb_ctx* ctx, const gdtb_space* space, const
   DeviceBuffer d;
   if (dofs) {
     GDTB_TRY(d.alloc(sizeof(double) * (size_t)space->dev.size));
-    GDTB_CUDA(cudaMemcpy(d.p, dofs, sizeof(double) * (size_t)space->dev.size, cudaMemcpyHostToDevice));
+    GDTB_CUDA(cudaMemcpyAsync(d.p, dofs, sizeof(double) * (size_t)space->dev.size, cudaMemcpyHostToDevice,
+                              ctx->launch.stream));
   }
   return gdtb_bilinear_form_apply2(ctx, space, dofs ? d.as<double>() : nullptr, f, form, result);
 }
@@ -1175,6 +1190,8 @@ int gdtb_lagrange_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb
   if (space->dev.kind == GDTB_SPACE_FV)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_lagrange_interpolate: use gdtb_fv_interpolate for finite-volume spaces");
   GDTB_TRY(internal_validate_function(*f, "interpolate: f"));
+  if (f->kind > GDTB_FN_BUILTIN)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "interpolate: f must be a constant, per-element or analytic function");
   if (f->kind == GDTB_FN_CONST_TENSOR || f->kind == GDTB_FN_ELEM_TENSOR)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "interpolate: f must be scalar");
   LoweredForm owner;

@@ -11,6 +11,8 @@ import numpy as np
 SPACE_CG, SPACE_DG, SPACE_FV = 0, 1, 2
 STENCIL_ELEMENT, STENCIL_INTERSECTION, STENCIL_ELEMENT_AND_INTERSECTION = 0, 1, 2
 FN_CONST_SCALAR, FN_CONST_TENSOR, FN_ELEM_SCALAR, FN_ELEM_TENSOR, FN_BUILTIN = 0, 1, 2, 3, 4
+FN_QP_SCALAR, FN_QP_TENSOR, FN_DOF_VECTOR = 5, 6, 7
+ROLE_ELEMENT, ROLE_FUNCTIONAL, ROLE_COUPLING, ROLE_BOUNDARY = 0, 1, 2, 3
 BUILTIN_COS_PRODUCT, BUILTIN_AFFINE, BUILTIN_GAUSSIAN, BUILTIN_INDICATOR, BUILTIN_QUADRATIC = 1, 2, 3, 4, 5
 INT_LAPLACE, INT_PRODUCT = 0, 1
 INT_IPDG_INNER_COUPLING, INT_IPDG_INNER_PENALTY = 2, 3
@@ -46,6 +48,10 @@ class Function(C.Structure):
         ("c", C.c_double * 9),
         ("p", C.c_double * 8),
         ("data", C.POINTER(C.c_double)),
+        ("qp_per_element", C.c_int32),
+        ("space_kind", C.c_int32),
+        ("space_order", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -153,6 +159,31 @@ def fn_builtin(builtin, order, *params):
     for i, x in enumerate(params):
         f.p[i] = float(x)
     return f
+
+
+def fn_qp(values, order):
+    """Coefficient data sampled at the quadrature points of the form it will be appended to: array of shape
+    (n_elem, n_qp) (scalar) or (n_elem, n_qp, d, d) (tensor), q = q_0 + m (q_1 + m q_2); `order` is the declared
+    polynomial order (it enters the form's quadrature order, which in turn fixes n_qp)."""
+    a = np.ascontiguousarray(values, dtype=np.float64)
+    assert a.ndim in (2, 4)
+    f = Function()
+    f.order = int(order)
+    f.kind = FN_QP_SCALAR if a.ndim == 2 else FN_QP_TENSOR
+    f.qp_per_element = a.shape[1]
+    f.data = a.ctypes.data_as(C.POINTER(C.c_double))
+    return _keep(f, a)
+
+
+def fn_dofs(dofs, space_kind, space_order):
+    """A discrete function of the space (space_kind, space_order) on the form's grid, given by its DoF vector (host)."""
+    a = np.ascontiguousarray(dofs, dtype=np.float64)
+    f = Function()
+    f.kind = FN_DOF_VECTOR
+    f.order = int(space_order)
+    f.space_kind, f.space_order = int(space_kind), int(space_order)
+    f.data = a.ctypes.data_as(C.POINTER(C.c_double))
+    return _keep(f, a)
 
 
 def _as_function(x):

@@ -93,7 +93,19 @@ enum
   GDTB_FN_CONST_TENSOR = 1, /* c[0 .. d*d) row-major                                             */
   GDTB_FN_ELEM_SCALAR = 2,  /* data[e], e = element index of the grid view                        */
   GDTB_FN_ELEM_TENSOR = 3,  /* data[e*d*d + r*d + c]                                              */
-  GDTB_FN_BUILTIN = 4       /* see GDTB_BUILTIN_*                                                 */
+  GDTB_FN_BUILTIN = 4,      /* see GDTB_BUILTIN_*                                                 */
+  /* Arbitrary coefficient data (an XT::Functions::GenericFunction lambda, measured data, ...) sampled by the caller
+   * at the quadrature points of the form it is appended to: data[e * qp_per_element + q] (scalar) or
+   * data[(e * qp_per_element + q) * d * d + r * d + c] (tensor), q = q_0 + m (q_1 + m q_2) the tensor Gauss rule with
+   * m = gdtb_gauss_points(gdtb_form_quadrature_order(...)) points per direction, x_q = lower_e + xhat_q * (upper_e -
+   * lower_e).  Element forms and functionals only (volume rules). */
+  GDTB_FN_QP_SCALAR = 5,
+  GDTB_FN_QP_TENSOR = 6,
+  /* A discrete function u_h = sum_i data[global_index(e, i)] phi_i of the Lagrange / FV space (space_kind,
+   * space_order) on the same grid (XT::Functions::GridFunction wrapping a DiscreteFunction,
+   * discretefunction/default.hh): evaluated on the device at every quadrature point; as a d x d function it means
+   * u_h * I.  `order` should be space_order (DiscreteFunction::order()). */
+  GDTB_FN_DOF_VECTOR = 7
 };
 
 enum
@@ -114,6 +126,10 @@ typedef struct gdtb_function
   double c[9];
   double p[8];
   const double* data;
+  int32_t qp_per_element; /* GDTB_FN_QP_*: quadrature points per element `data` was sampled for (checked at append) */
+  int32_t space_kind;     /* GDTB_FN_DOF_VECTOR: GDTB_SPACE_* and polynomial order of the discrete function's space */
+  int32_t space_order;
+  int32_t reserved;
 } gdtb_function;
 
 enum
@@ -255,6 +271,22 @@ int gdtb_space_destroy(gdtb_space* space);
 int64_t gdtb_space_size(const gdtb_space* space);
 int32_t gdtb_space_max_local_size(const gdtb_space* space);
 int gdtb_space_global_indices(const gdtb_space* space, int64_t element, int64_t* out);
+
+/* ---- quadrature (what a binder needs to pre-sample a user lambda into GDTB_FN_QP_*) ------------------------------ */
+enum
+{
+  GDTB_ROLE_ELEMENT = 0,  /* LocalElementIntegralBilinearForm         (integrals.hh:115: integrand.order + over_integrate) */
+  GDTB_ROLE_FUNCTIONAL = 1, /* LocalElementIntegralFunctional           (local/functionals/integrals.hh:85)              */
+  GDTB_ROLE_COUPLING = 2, /* LocalCouplingIntersectionIntegralBilinearForm (integrals.hh:225-229)                        */
+  GDTB_ROLE_BOUNDARY = 3  /* LocalIntersectionIntegralBilinearForm    (integrals.hh:354-355)                             */
+};
+/* polynomial order the reference integrates `form` with on `space` (laplace.hh:74-79, product.hh:89-100,
+ * conversion.hh:92, combined.hh:293-299, laplace-ipdg.hh:95-105, ipdg.hh:100-111) */
+int gdtb_form_quadrature_order(const gdtb_space* space, const gdtb_form* form, int role, int32_t* order);
+/* Dune::QuadratureRules<double, 1>::rule(cube, order) [EXT dune-geometry]: m = order / 2 + 1 Gauss-Legendre points on
+ * [0, 1] (ascending) and their weights; the d-dimensional rule is the tensor product, first coordinate fastest.
+ * points01 / weights may be NULL (query m only). */
+int gdtb_gauss_rule(int order, int32_t* m, double* points01, double* weights);
 
 /* ---- sparsity pattern ----------------------------------------------------------------------- */
 enum

@@ -24,7 +24,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        from dune_gdt_b200.descriptors import Flux, Form, Function, FvBoundary, GridDesc
+        from dune_gdt_b200.descriptors import Flux, Form, Function, FvBoundary, GridDesc, Integrand
 
         if not os.path.exists(LIB_PATH):
             build()
@@ -68,6 +68,8 @@ def lib():
             "orc_fv_estimate_dt": (C.c_double, [G, C.POINTER(Flux), DP, DP]),
             "orc_function_eval": (C.c_double, [C.POINTER(Function), C.c_int, DP, C.c_int64]),
             "orc_last_error": (C.c_char_p, []),
+            "orc_element_integrand_evaluate": (
+                C.c_int, [C.POINTER(Integrand), C.c_int, C.c_int, DP, DP, C.c_int, DP, DP, DP, DP]),
             "orc_dirichlet_dofs": (C.c_int64, [G, C.c_int, C.c_int, C.c_uint32, I64P]),
             "orc_dirichlet_apply": (C.c_int, [C.c_int64, I64P, I32P, DP, DP, C.c_int64, I64P, C.c_int, C.c_int]),
             "orc_csr_mv": (None, [C.c_int64, I64P, I32P, DP, DP, DP]),
@@ -262,4 +264,20 @@ def bilinear_form_apply2(grid, kind, order, dofs, f, form):
 def lagrange_interpolate(grid, kind, order, f):
     out = np.empty(space_size(grid, kind, order), dtype=np.float64)
     lib().orc_lagrange_interpolate(C.byref(grid), kind, order, C.byref(f), _dp(out))
+    return out
+
+
+def element_integrand_evaluate(integrand, dim, test_values, test_grads, ansatz_values, ansatz_grads, x):
+    """LocalLaplaceIntegrand / LocalElementProductIntegrand::evaluate on caller-supplied bases at one point; returns
+    result[n_test, n_ansatz] (the reference's evaluates_correctly_for_scalar_bases tests)"""
+    tv = np.ascontiguousarray(test_values, dtype=np.float64)
+    tg = np.ascontiguousarray(test_grads, dtype=np.float64).reshape(len(tv), dim)
+    av = np.ascontiguousarray(ansatz_values, dtype=np.float64)
+    ag = np.ascontiguousarray(ansatz_grads, dtype=np.float64).reshape(len(av), dim)
+    xx = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros((len(tv), len(av)))
+    st = lib().orc_element_integrand_evaluate(C.byref(integrand), dim, len(tv), _dp(tv), _dp(tg), len(av), _dp(av),
+                                              _dp(ag), _dp(xx), _dp(out))
+    if st != 0:
+        raise RuntimeError(lib().orc_last_error().decode())
     return out

@@ -359,7 +359,33 @@ double builtin_eval(const orc_function* f, int d, const double* x)
   }
 }
 
-double eval_scalar(const orc_function* f, int d, int64_t e, const double* x)
+// Where a grid function is evaluated: the quadrature point index inside the element's rule (ORC_FN_QP_*: the
+// caller-sampled array is indexed [element][q]) and the element / reference point (ORC_FN_DOF_VECTOR: a discrete
+// function is evaluated through its local basis, discretefunction/default.hh).  q < 0: no rule context.
+struct Pt
+{
+  int q = -1;
+  int nq = 0;
+  const Grid* g = nullptr;
+  const int64_t* idx = nullptr;
+  const double* xh = nullptr;
+};
+
+double dof_vector_eval(const orc_function* f, const Pt& pt)
+{
+  // u_h(x) = sum_i dofs[global_index(e, i)] * phi_i(xhat)  (LocalDiscreteFunction::evaluate)
+  const Space sp(*pt.g, f->space_kind, f->space_order);
+  int64_t gi[MAXN];
+  double val[MAXN];
+  sp.global_indices(pt.idx, gi);
+  shape(sp.d, sp.K, pt.xh, val, nullptr);
+  double u = 0.;
+  for (int i = 0; i < sp.nloc; ++i)
+    u += f->data[gi[i]] * val[i];
+  return u;
+}
+
+double eval_scalar(const orc_function* f, int d, int64_t e, const double* x, const Pt& pt = Pt())
 {
   switch (f->kind) {
     case ORC_FN_CONST_SCALAR:
@@ -368,13 +394,19 @@ double eval_scalar(const orc_function* f, int d, int64_t e, const double* x)
       return f->data[e];
     case ORC_FN_BUILTIN:
       return builtin_eval(f, d, x);
+    case ORC_FN_QP_SCALAR:
+      assert(pt.q >= 0 && pt.nq == f->qp_per_element);
+      return f->data[e * pt.nq + pt.q];
+    case ORC_FN_DOF_VECTOR:
+      assert(pt.g && pt.idx && pt.xh);
+      return dof_vector_eval(f, pt);
     default:
       return f->c[0];
   }
 }
 
 // d x d view (row-major, leading dimension 3); scalar functions mean c * I (laplace.hh:41, ipdg.hh:61)
-void eval_tensor(const orc_function* f, int d, int64_t e, const double* x, double* T)
+void eval_tensor(const orc_function* f, int d, int64_t e, const double* x, double* T, const Pt& pt = Pt())
 {
   for (int i = 0; i < 9; ++i)
     T[i] = 0.;
@@ -389,8 +421,14 @@ void eval_tensor(const orc_function* f, int d, int64_t e, const double* x, doubl
         for (int c = 0; c < d; ++c)
           T[r * 3 + c] = f->data[e * d * d + r * d + c];
       break;
+    case ORC_FN_QP_TENSOR:
+      assert(pt.q >= 0 && pt.nq == f->qp_per_element);
+      for (int r = 0; r < d; ++r)
+        for (int c = 0; c < d; ++c)
+          T[r * 3 + c] = f->data[(e * pt.nq + pt.q) * d * d + r * d + c];
+      break;
     default: {
-      const double s = eval_scalar(f, d, e, x);
+      const double s = eval_scalar(f, d, e, x, pt);
       for (int r = 0; r < d; ++r)
         T[r * 3 + r] = s;
     }
@@ -451,26 +489,36 @@ int form_order(const orc_form& f, int p, int (*term_order)(const orc_integrand&,
   return o + f.over_integrate;
 }
 
-void element_integrand_evaluate(const orc_integrand& t, const Basis& b, int d, int64_t e, const double* x,
-                                double* result /* n*n, overwritten */)
+// test and ansatz basis are separate arguments like in the reference (laplace.hh:81-102: test_basis.jacobians /
+// ansatz_basis.jacobians; the assembler passes the same space twice) -- the pointwise known-answer tests of
+// dune/gdt/test/integrands/integrands_laplace.cc:71-91 and integrands_product.cc:58-76 use different ones.
+void element_integrand_evaluate2(const orc_integrand& t, const Basis& test, const Basis& ansatz, int d, int64_t e,
+                                 const double* x, double* result /* n_test * n_ansatz, overwritten */,
+                                 const Pt& pt = Pt())
 {
-  const int n = b.n;
+  const int nt = test.n, na = ansatz.n;
   if (t.kind == ORC_INT_LAPLACE) {
     // laplace.hh:81-102: result[ii][jj] += (weight * ansatz_grads[jj][rr]) * test_grads[ii][rr]
     double kappa[9];
-    eval_tensor(&t.diffusion, d, e, x, kappa);
-    for (int ii = 0; ii < n; ++ii)
-      for (int jj = 0; jj < n; ++jj) {
+    eval_tensor(&t.diffusion, d, e, x, kappa, pt);
+    for (int ii = 0; ii < nt; ++ii)
+      for (int jj = 0; jj < na; ++jj) {
         double kg[3];
-        matvec(d, kappa, &b.grad[jj * 3], kg);
-        result[ii * n + jj] = 0. + dot(d, kg, &b.grad[ii * 3]);
+        matvec(d, kappa, &ansatz.grad[jj * 3], kg);
+        result[ii * na + jj] = 0. + dot(d, kg, &test.grad[ii * 3]);
       }
   } else { // ORC_INT_PRODUCT, product.hh:104-130: result[ii][jj] = (weight * test[ii]) * ansatz[jj]
-    const double w = eval_scalar(&t.diffusion, d, e, x);
-    for (int ii = 0; ii < n; ++ii)
-      for (int jj = 0; jj < n; ++jj)
-        result[ii * n + jj] = (w * b.val[ii]) * b.val[jj];
+    const double w = eval_scalar(&t.diffusion, d, e, x, pt);
+    for (int ii = 0; ii < nt; ++ii)
+      for (int jj = 0; jj < na; ++jj)
+        result[ii * na + jj] = (w * test.val[ii]) * ansatz.val[jj];
   }
+}
+
+void element_integrand_evaluate(const orc_integrand& t, const Basis& b, int d, int64_t e, const double* x,
+                                double* result /* n*n, overwritten */, const Pt& pt = Pt())
+{
+  element_integrand_evaluate2(t, b, b, d, e, x, result, pt);
 }
 
 void local_element_matrix(const Grid& g, const Space& sp, const orc_form& form, const int64_t* idx, double* L)
@@ -500,9 +548,15 @@ void local_element_matrix(const Grid& g, const Space& sp, const orc_form& form, 
           x[k] = lower[k] + xh[k] * ext[k];
         const double factor = ie * w; // integrals.hh:119
         b.evaluate(xh, ext);
-        element_integrand_evaluate(form.terms[0], b, d, e, x, values);
+        Pt pt;
+        pt.q = qx + m * (qy + m * qz);
+        pt.nq = m * my * mz;
+        pt.g = &g;
+        pt.idx = idx;
+        pt.xh = xh;
+        element_integrand_evaluate(form.terms[0], b, d, e, x, values, pt);
         for (int t = 1; t < form.n_terms; ++t) { // combined.hh:212-227
-          element_integrand_evaluate(form.terms[t], b, d, e, x, scratch);
+          element_integrand_evaluate(form.terms[t], b, d, e, x, scratch, pt);
           for (int i = 0; i < n * n; ++i)
             values[i] += scratch[i];
         }
@@ -542,8 +596,14 @@ void local_element_vector(const Grid& g, const Space& sp, const orc_form& form, 
         for (int k = 0; k < 3; ++k)
           x[k] = lower[k] + xh[k] * ext[k];
         b.evaluate(xh, ext);
-        const double w = eval_scalar(&t.diffusion, d, e, x);
-        const double f = eval_scalar(&t.weight, d, e, x);
+        Pt pt;
+        pt.q = qx + m * (qy + m * qz);
+        pt.nq = m * my * mz;
+        pt.g = &g;
+        pt.idx = idx;
+        pt.xh = xh;
+        const double w = eval_scalar(&t.diffusion, d, e, x, pt);
+        const double f = eval_scalar(&t.weight, d, e, x, pt);
         for (int i = 0; i < n; ++i) {
           const double v = (w * b.val[i]) * f;
           l[i] += v * ie * wq; // local/functionals/integrals.hh:96
@@ -664,16 +724,22 @@ void local_coupling_matrices(const Grid& g, const Space& sp, const orc_form& for
           T[i] = 0.;
         const orc_integrand& in = form.terms[t];
         double w_in[9], w_out[9], wn[3];
-        eval_tensor(&in.weight, d, e_in, x_in, w_in);
-        eval_tensor(&in.weight, d, e_out, x_out, w_out);
+        Pt p_in, p_out; // no volume-rule index on a face: ORC_FN_QP_* are element-form functions
+        p_in.g = p_out.g = &g;
+        p_in.idx = idx_in;
+        p_in.xh = xh_in;
+        p_out.idx = idx_out;
+        p_out.xh = xh_out;
+        eval_tensor(&in.weight, d, e_in, x_in, w_in, p_in);
+        eval_tensor(&in.weight, d, e_out, x_out, w_out, p_out);
         matvec(d, w_out, f.normal, wn);
         const double delta_plus = dot(d, f.normal, wn);
         matvec(d, w_in, f.normal, wn);
         const double delta_minus = dot(d, f.normal, wn);
         if (in.kind == ORC_INT_IPDG_INNER_COUPLING) {
           double k_in[9], k_out[9];
-          eval_tensor(&in.diffusion, d, e_in, x_in, k_in);
-          eval_tensor(&in.diffusion, d, e_out, x_out, k_out);
+          eval_tensor(&in.diffusion, d, e_in, x_in, k_in, p_in);
+          eval_tensor(&in.diffusion, d, e_out, x_out, k_out, p_out);
           const double weight_minus = delta_plus / (delta_plus + delta_minus);
           const double weight_plus = delta_minus / (delta_plus + delta_minus);
           const double sp_ = in.prefactor;
@@ -765,9 +831,13 @@ void local_boundary_matrix(const Grid& g, const Space& sp, const orc_form& form,
         for (int i = 0; i < nn; ++i)
           T[i] = 0.;
         const orc_integrand& in = form.terms[t];
+        Pt pt;
+        pt.g = &g;
+        pt.idx = idx;
+        pt.xh = xh;
         if (in.kind == ORC_INT_IPDG_DIRICHLET_COUPLING) {
           double kap[9];
-          eval_tensor(&in.diffusion, d, e, x, kap);
+          eval_tensor(&in.diffusion, d, e, x, kap, pt);
           double fl[MAXN];
           for (int j = 0; j < n; ++j) {
             double kg[3];
@@ -781,7 +851,7 @@ void local_boundary_matrix(const Grid& g, const Space& sp, const orc_form& form,
             }
         } else { // ORC_INT_IPDG_BOUNDARY_PENALTY
           double w[9], wn[3];
-          eval_tensor(&in.weight, d, e, x, w);
+          eval_tensor(&in.weight, d, e, x, w, pt);
           matvec(d, w, f.normal, wn);
           const double h = intersection_h(g, in, f, ext, ext, false);
           const double penalty = (in.prefactor * dot(d, f.normal, wn)) / h;
@@ -1417,7 +1487,13 @@ void orc_fv_interpolate(const orc_grid* g, const orc_function* f, double* u)
           double x[3];
           for (int k = 0; k < 3; ++k)
             x[k] = lower[k] + xh[k] * ext[k];
-          integral += eval_scalar(f, d, e, x) * vol * w; // XT::Grid::element_integral [EXT]
+          Pt pt;
+          pt.q = qx + m * (qy + m * qz);
+          pt.nq = m * my * mz;
+          pt.g = &gr;
+          pt.idx = idx;
+          pt.xh = xh;
+          integral += eval_scalar(f, d, e, x, pt) * vol * w; // XT::Grid::element_integral [EXT]
         }
     u[e] = integral / vol;
   }
@@ -1621,15 +1697,21 @@ double orc_bilinear_form_apply2(const orc_grid* g, int kind, int order, const do
               grad[r] -= fg[r];
           }
           double v = 0.;
+          Pt pt;
+          pt.q = qx + m * (qy + m * qz);
+          pt.nq = m * my * mz;
+          pt.g = &gr;
+          pt.idx = idx;
+          pt.xh = xh;
           for (int t = 0; t < form->n_terms; ++t) {
             const orc_integrand& in = form->terms[t];
             if (in.kind == ORC_INT_LAPLACE) {
               double kappa[9], kg[3];
-              eval_tensor(&in.diffusion, d, e, x, kappa);
+              eval_tensor(&in.diffusion, d, e, x, kappa, pt);
               matvec(d, kappa, grad, kg);
               v += dot(d, kg, grad);
             } else
-              v += (eval_scalar(&in.diffusion, d, e, x) * val) * val;
+              v += (eval_scalar(&in.diffusion, d, e, x, pt) * val) * val;
           }
           local += v * (ie * w);
         }
@@ -1660,6 +1742,40 @@ void orc_lagrange_interpolate(const orc_grid* g, int kind, int order, const orc_
       dofs[gi[i]] = eval_scalar(f, d, e, x);
     }
   }
+}
+
+// LocalLaplaceIntegrand / LocalElementProductIntegrand::evaluate (laplace.hh:81-102, product.hh:104-130) on
+// caller-supplied test / ansatz basis values and (physical) gradients at one point: result[ii * n_ansatz + jj].  The
+// same code path orc_assemble uses (element_integrand_evaluate2); lets the tests reproduce the reference's pointwise
+// known-answer tests with polynomial bases (dune/gdt/test/integrands/integrands_laplace.cc:71-91,
+// integrands_product.cc:58-76), which pin the index convention of a non-symmetric diffusion tensor.
+int orc_element_integrand_evaluate(const orc_integrand* integrand, int dim, int n_test, const double* test_values,
+                                   const double* test_grads /* n_test * dim */, int n_ansatz,
+                                   const double* ansatz_values, const double* ansatz_grads /* n_ansatz * dim */,
+                                   const double* x, double* result)
+{
+  if (n_test > MAXN || n_ansatz > MAXN) {
+    g_error = "local size exceeds MAXN";
+    return 1;
+  }
+  Basis test, ansatz;
+  test.d = ansatz.d = dim;
+  test.K = ansatz.K = 0;
+  test.n = n_test;
+  ansatz.n = n_ansatz;
+  for (int i = 0; i < n_test; ++i) {
+    test.val[i] = test_values ? test_values[i] : 0.;
+    for (int r = 0; r < 3; ++r)
+      test.grad[i * 3 + r] = (test_grads && r < dim) ? test_grads[i * dim + r] : 0.;
+  }
+  for (int i = 0; i < n_ansatz; ++i) {
+    ansatz.val[i] = ansatz_values ? ansatz_values[i] : 0.;
+    for (int r = 0; r < 3; ++r)
+      ansatz.grad[i * 3 + r] = (ansatz_grads && r < dim) ? ansatz_grads[i * dim + r] : 0.;
+  }
+  double xx[3] = {x[0], dim > 1 ? x[1] : 0., dim > 2 ? x[2] : 0.};
+  element_integrand_evaluate2(*integrand, test, ansatz, dim, 0, xx, result);
+  return 0;
 }
 
 } // extern "C"

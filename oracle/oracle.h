@@ -67,7 +67,10 @@ enum
   ORC_FN_CONST_TENSOR = 1, /* c[0..d*d) row-major                                   */
   ORC_FN_ELEM_SCALAR = 2,  /* data[e]                                               */
   ORC_FN_ELEM_TENSOR = 3,  /* data[e*d*d + r*d + c]                                 */
-  ORC_FN_BUILTIN = 4       /* analytic scalar function of the global coordinate     */
+  ORC_FN_BUILTIN = 4,      /* analytic scalar function of the global coordinate     */
+  ORC_FN_QP_SCALAR = 5,    /* data[e * qp_per_element + q], sampled at the form's own rule (element forms)      */
+  ORC_FN_QP_TENSOR = 6,    /* data[(e * qp_per_element + q) * d * d + r * d + c]                                */
+  ORC_FN_DOF_VECTOR = 7    /* discrete function of the space (space_kind, space_order), DoF vector in data      */
 };
 
 enum
@@ -88,6 +91,10 @@ typedef struct orc_function
   double c[9];
   double p[8];
   const double* data;
+  int32_t qp_per_element;
+  int32_t space_kind;
+  int32_t space_order;
+  int32_t reserved2;
 } orc_function;
 
 enum
@@ -242,6 +249,12 @@ double orc_bilinear_form_apply2(const orc_grid* g, int kind, int order, const do
                                 const orc_form* form);
 /* default_interpolation into a Lagrange space (interpolations/default.hh:40-83) */
 void orc_lagrange_interpolate(const orc_grid* g, int kind, int order, const orc_function* f, double* dofs);
+
+/* pointwise integrand evaluation on caller-supplied bases (the reference's evaluates_correctly_* tests,
+ * dune/gdt/test/integrands/integrands_laplace.cc:71-91, integrands_product.cc:58-76) */
+int orc_element_integrand_evaluate(const orc_integrand* integrand, int dim, int n_test, const double* test_values,
+                                   const double* test_grads, int n_ansatz, const double* ansatz_values,
+                                   const double* ansatz_grads, const double* x, double* result);
 
 const char* orc_last_error(void);
 

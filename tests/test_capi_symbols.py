@@ -40,7 +40,7 @@ def test_library_is_built_for_sm_100a_only(gdt):
 def test_descriptor_layouts_match_the_header(gdt):
     D = gdt.descriptors
     assert C.sizeof(D.GridDesc) == 4 + 4 + 24 + 24 + 24
-    assert C.sizeof(D.Function) == 16 + 72 + 64 + 8
+    assert C.sizeof(D.Function) == 16 + 72 + 64 + 8 + 16
     assert C.sizeof(D.Integrand) == 16 + 2 * C.sizeof(D.Function)
     assert C.sizeof(D.Form) == 16 + 4 * C.sizeof(D.Integrand)
     assert C.sizeof(D.Flux) == 8 + 32

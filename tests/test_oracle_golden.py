@@ -400,3 +400,47 @@ def test_swipdg_esv2007_h1_errors_via_apply2(oracle):
         err = np.sqrt(oracle.bilinear_form_apply2(g, DG, 1, u, exact, laplace()))
         assert err == pytest.approx(_q1_dg_h1_semi_error(N, u), rel=1e-9)
         assert err == pytest.approx(ref, rel=6e-3), (N, err)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pointwise integrand identities of the reference's own tests: polynomial bases
+# {x, x^2 y} (ansatz) / {y, x y^3} (test) and the NON-symmetric diffusion tensor kappa(x) = x y [[x, y], [1, 2]]
+# (dune/gdt/test/integrands/integrands.hh:75-104, integrands_laplace.cc:45-52, 71-91; integrands_product.cc:58-76).
+# They pin the index convention of a full tensor: values[i][j] = (kappa grad phi_j) . grad psi_i, kappa row-major.
+# ------------------------------------------------------------------------------------------------------------------
+def _kat_points(oracle, order):
+    x1, _ = oracle.gauss_rule(order)
+    return [(a, b) for b in x1 for a in x1]
+
+
+def _ulp_close(a, b, ulps=4):
+    # EXPECT_DOUBLE_EQ: within 4 units in the last place
+    return np.all(np.abs(a - b) <= ulps * np.spacing(np.maximum(np.abs(a), np.abs(b))))
+
+
+def test_laplace_integrand_pointwise_reference_kat(oracle):
+    # integrand order = kappa.order (3) + test.order (4) + ansatz.order (3) (laplace.hh:74-79)
+    for x, y in _kat_points(oracle, 3 + 4 + 3):
+        kappa = x * y * np.array([[x, y], [1.0, 2.0]])
+        integrand = D.integrand(D.INT_LAPLACE, diffusion=D.fn_const(kappa, order=3))
+        ansatz_v, ansatz_g = [x, x**2 * y], [[1.0, 0.0], [2.0 * x * y, x**2]]
+        test_v, test_g = [y, x * y**3], [[0.0, 1.0], [y**3, 3.0 * x * y**2]]
+        got = oracle.element_integrand_evaluate(integrand, 2, test_v, test_g, ansatz_v, ansatz_g, [x, y])
+        expected = x * y * np.array([
+            [1.0, 2.0 * (x * y + x**2)],
+            [x * y**3 + 3.0 * x * y**2, 3.0 * x**2 * y**4 + 6.0 * (x**2 * y**3 + x**3 * y**2)],
+        ])
+        assert _ulp_close(got, expected), (x, y, got, expected)
+        # the transposed convention (kappa^T, i.e. (kappa grad psi_i) . grad phi_j) must NOT reproduce the table
+        wrong = D.integrand(D.INT_LAPLACE, diffusion=D.fn_const(kappa.T.copy(), order=3))
+        bad = oracle.element_integrand_evaluate(wrong, 2, test_v, test_g, ansatz_v, ansatz_g, [x, y])
+        assert not _ulp_close(bad, expected, ulps=64)
+
+
+def test_product_integrand_pointwise_reference_kat(oracle):
+    for x, y in _kat_points(oracle, 2 + 4 + 3):  # weight.order + test.order + ansatz.order (product.hh:89-100)
+        integrand = D.integrand(D.INT_PRODUCT, diffusion=D.fn_const(x * y, order=2))
+        got = oracle.element_integrand_evaluate(integrand, 2, [y, x * y**3], np.zeros((2, 2)), [x, x**2 * y],
+                                                np.zeros((2, 2)), [x, y])
+        expected = np.array([[(x * y) ** 2, (x * y) ** 3], [x**3 * y**4, x**4 * y**5]])
+        assert _ulp_close(got, expected), (x, y, got, expected)
