@@ -21,6 +21,8 @@
 // as no two entities of a launch share a global row: CG element forms are launched once per parity colour
 // (2^d colours), DG face forms once per (direction, parity[, periodic wrap]) class.  The colour order is
 // fixed, hence results are run-to-run bit-identical.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.hpp"
 #include "local_forms.cuh"
@@ -406,6 +408,70 @@ struct BoundaryLauncher
   }
 };
 
+struct SampleRule
+{
+  double qx[MAX_Q1D];
+};
+
+// GridFunction -> one value (tensor) per quadrature point of the tensor Gauss rule with m points per direction: what
+// LocalLaplaceIntegrand / LocalElementProductIntegrand::evaluate ask the bound local function for at every point
+// (laplace.hh:96, product.hh:124), x_q = lower + xhat_q * ext like geometry.global(xhat_q) [EXT]
+__global__ void __launch_bounds__(256)
+    k_sample_function(const GridDev g, const FnDev f, const int m, const SampleRule rule, const int tensor,
+                      const long long e_begin, const long long e_end, double* __restrict__ out)
+{
+  const double* qx = rule.qx;
+  const int d = g.d;
+  const int nq = m * (d > 1 ? m : 1) * (d > 2 ? m : 1);
+  const long long total = (e_end - e_begin) * nq;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long el = t / nq;
+    const int q = int(t - el * nq);
+    const long long e = e_begin + el;
+    long long idx[3];
+    elem_coords(g, e, idx);
+    double lower[3], ext[3];
+    cell_geometry(g, idx, lower, ext);
+    const int qk[3] = {q % m, d > 1 ? (q / m) % m : 0, d > 2 ? q / (m * m) : 0};
+    double xh[3], x[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      xh[k] = k < d ? qx[qk[k]] : 0.;
+      x[k] = k < d ? lower[k] + xh[k] * ext[k] : 0.;
+    }
+    const EvalPt pt = {q, idx, xh};
+    if (tensor) {
+      double T[9];
+      fn_tensor(f, g, e, x, pt, T);
+      double* dst = out + t * (d * d);
+      for (int r = 0; r < d; ++r)
+        for (int c = 0; c < d; ++c)
+          dst[r * d + c] = T[r * 3 + c];
+    } else
+      out[t] = fn_scalar(f, g, e, x, pt);
+  }
+}
+
+} // namespace
+
+int launch_sample_function(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx, int tensor,
+                           long long e_begin, long long e_end, double* out)
+{
+  SampleRule rule;
+  for (int q = 0; q < MAX_Q1D; ++q)
+    rule.qx[q] = q < m ? qx[q] : 0.;
+  const int nq = m * (g.d > 1 ? m : 1) * (g.d > 2 ? m : 1);
+  const long long total = (e_end - e_begin) * nq;
+  if (total <= 0)
+    return GDTB_OK;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)L.sm_count * 32);
+  k_sample_function<<<grid, 256, 0, L.stream>>>(g, f, m, rule, tensor, e_begin, e_end, out);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+namespace {
 } // namespace
 
 int launch_element_matrix(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, const long long* rowptr,

@@ -22,6 +22,7 @@
 // (cp.async.bulk.global.shared::cta, SASS UBLKCP) -- HBM sees only full-line sequential writes.  The kernel is
 // persistent-strided over work items with several CTAs per SM so that one CTA's store drains while the
 // others compute.  Deterministic (no atomics, fixed summation order).
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -697,6 +698,359 @@ int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double*
     case 2: return launch_q1_gather_d<2>(L, p, values, rhs, accumulate);
     case 3: return launch_q1_gather_d<3>(L, p, values, rhs, accumulate);
     default: return fail(GDTB_ERR_INVALID_ARGUMENT, "q1_gather: dimension must be 1, 2 or 3");
+  }
+}
+
+// ==================================================================================================================
+// Coefficients that vary inside a cell (one value / tensor per quadrature point): k_q1_gather_qp
+// ==================================================================================================================
+namespace {
+
+template <int D, int M>
+struct QpCount
+{
+  static constexpr int value = D == 1 ? M : (D == 2 ? M * M : M * M * M);
+};
+
+// out[s] += w * sum_q kq[q] prod_k PT[t_k][q_k][i_k][s_k]: one (r, c) term of one element's local-matrix row, by sum
+// factorisation over the tensor rule (last axis first).  i_k = local index of the vertex in the element, s = ansatz
+// vertex, t_k = point-table type along axis k; all of them compile-time constants after unrolling, so the tables are
+// read as constant-bank operands straight from the kernel parameters.
+template <int D, int M>
+__device__ __forceinline__ void q1qp_term(const CgQpGroup& G, const double (&kq)[QpCount<D, M>::value], const int tx,
+                                          const int ty, const int tz, const int ix, const int iy, const int iz,
+                                          const double w, double (&out)[1 << D])
+{
+  if constexpr (D == 3) {
+    double A[M][M][2];
+#pragma unroll
+    for (int qx = 0; qx < M; ++qx)
+#pragma unroll
+      for (int qy = 0; qy < M; ++qy)
+#pragma unroll
+        for (int sz = 0; sz < 2; ++sz) {
+          double a = 0.;
+#pragma unroll
+          for (int qz = 0; qz < M; ++qz)
+            a = fma(kq[qx + M * (qy + M * qz)], G.pt[tz][qz][iz][sz], a);
+          A[qx][qy][sz] = a;
+        }
+    double B[M][2][2];
+#pragma unroll
+    for (int qx = 0; qx < M; ++qx)
+#pragma unroll
+      for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+        for (int sz = 0; sz < 2; ++sz) {
+          double b = 0.;
+#pragma unroll
+          for (int qy = 0; qy < M; ++qy)
+            b = fma(A[qx][qy][sz], G.pt[ty][qy][iy][sy], b);
+          B[qx][sy][sz] = b;
+        }
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int sx = s & 1, sy = (s >> 1) & 1, sz = s >> 2;
+      double c = 0.;
+#pragma unroll
+      for (int qx = 0; qx < M; ++qx)
+        c = fma(B[qx][sy][sz], G.pt[tx][qx][ix][sx], c);
+      out[s] = fma(w, c, out[s]);
+    }
+  } else if constexpr (D == 2) {
+    double A[M][2];
+#pragma unroll
+    for (int qx = 0; qx < M; ++qx)
+#pragma unroll
+      for (int sy = 0; sy < 2; ++sy) {
+        double a = 0.;
+#pragma unroll
+        for (int qy = 0; qy < M; ++qy)
+          a = fma(kq[qx + M * qy], G.pt[ty][qy][iy][sy], a);
+        A[qx][sy] = a;
+      }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int sx = s & 1, sy = s >> 1;
+      double c = 0.;
+#pragma unroll
+      for (int qx = 0; qx < M; ++qx)
+        c = fma(A[qx][sy], G.pt[tx][qx][ix][sx], c);
+      out[s] = fma(w, c, out[s]);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      double c = 0.;
+#pragma unroll
+      for (int qx = 0; qx < M; ++qx)
+        c = fma(kq[qx], G.pt[tx][qx][ix][s], c);
+      out[s] = fma(w, c, out[s]);
+    }
+  }
+}
+
+// row i = (2^D - 1) ^ o of the local matrix of element e (offset o around the vertex): all (r, c) terms of the integrand
+template <int D, int M, int KIND>
+__device__ __forceinline__ void q1qp_element(const CgQpGroup& G, const long long e, const int ox, const int oy,
+                                             const int oz, const double (&a)[3], const double (&b)[3],
+                                             double (&out)[1 << D])
+{
+  constexpr int NQ = QpCount<D, M>::value;
+  const int ix = 1 - ox, iy = 1 - oy, iz = 1 - oz;
+  const double ie = a[0] * (D > 1 ? a[1] : 1.) * (D > 2 ? a[2] : 1.); // integrals.hh:119
+  double kq[NQ];
+  if (KIND == Q1G_LAPLACE_TENSOR) {
+    const double* src = G.coef + e * (long long)(NQ * D * D);
+    // the (r, c) loop stays rolled (the point-table type becomes a run-time index into the constant bank): D * D unrolled
+    // copies of the contraction per element would not fit the instruction cache
+#pragma unroll 1
+    for (int rc = 0; rc < D * D; ++rc) {
+      const int r = rc / D, c = rc - r * D;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        kq[q] = __ldg(src + q * (D * D) + rc);
+      // (kappa grad phi_j) . grad psi_i: test derivative along r, ansatz derivative along c (laplace.hh:98-101)
+      const int t0 = 0 == r ? (0 == c ? QPT_KK : QPT_KM) : (0 == c ? QPT_MK : QPT_MM);
+      const int t1 = 1 == r ? (1 == c ? QPT_KK : QPT_KM) : (1 == c ? QPT_MK : QPT_MM);
+      const int t2 = 2 == r ? (2 == c ? QPT_KK : QPT_KM) : (2 == c ? QPT_MK : QPT_MM);
+      const double br = r == 0 ? b[0] : (r == 1 ? b[1] : b[2]), bc = c == 0 ? b[0] : (c == 1 ? b[1] : b[2]);
+      q1qp_term<D, M>(G, kq, t0, t1, t2, ix, iy, iz, G.scale * (ie * (br * bc)), out);
+    }
+  } else {
+    const double* src = G.coef + e * (long long)NQ;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      kq[q] = __ldg(src + q);
+    if (KIND == Q1G_MASS)
+      q1qp_term<D, M>(G, kq, QPT_MM, QPT_MM, QPT_MM, ix, iy, iz, G.scale * ie, out);
+    else {
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+        q1qp_term<D, M>(G, kq, r == 0 ? QPT_KK : QPT_MM, r == 1 ? QPT_KK : QPT_MM, r == 2 ? QPT_KK : QPT_MM, ix, iy, iz,
+                        G.scale * (ie * (b[r] * b[r])), out);
+    }
+  }
+}
+
+// Same work decomposition and data movement as k_q1_gather (one thread per vertex row, Q1G_ROWS rows per item, the
+// item's CSR segment staged in shared memory and written by one TMA bulk store); the per-element arithmetic is the
+// sum-factorised quadrature loop above.
+template <int D, int M, int KIND, bool ACCUMULATE>
+__global__ void __launch_bounds__(Q1G_ROWS, 1)
+    k_q1_gather_qp(const __grid_constant__ Q1QpParams p, double* __restrict__ values, long long nrows, int nitems,
+                   int stage_doubles, int nbuf)
+{
+  constexpr int NO = 1 << D;
+  extern __shared__ __align__(16) double smem[];
+  const GridDev& g = p.g;
+  const CgQpGroup& G = p.group;
+  const int Nx = (int)g.n[0], Ny = D > 1 ? (int)g.n[1] : 1, Nz = D > 2 ? (int)g.n[2] : 1;
+  const int elo = (int)p.elem_lo, ehi = (int)p.elem_hi;
+  int buf = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const long long l0 = (long long)item * Q1G_ROWS;
+    const int nr = (int)min((long long)Q1G_ROWS, nrows - l0);
+    const unsigned r0 = (unsigned)(p.row_offset + l0);
+    int bx, by, bz, cx, cy, cz;
+    q1_decode<D>(r0, p.div_vx, p.div_vy, bx, by, bz);
+    q1_decode<D>(r0 + nr, p.div_vx, p.div_vy, cx, cy, cz);
+    const long long gstart = q1_rowptr<D>(bx, by, bz, Nx, Ny, Nz);
+    const long long gend = q1_rowptr<D>(cx, cy, cz, Nx, Ny, Nz);
+    const int seg = int(gend - gstart);
+    const long long start = gstart - p.value_offset;
+    const unsigned start32 = (unsigned)gstart;
+    const int phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
+    double* stage = smem + buf * stage_doubles + phase;
+
+    if ((int)threadIdx.x < nr) {
+      int ix, iy, iz;
+      q1_decode<D>(r0 + threadIdx.x, p.div_vx, p.div_vy, ix, iy, iz);
+      const int il[3] = {ix, iy, iz};
+      const int Nl[3] = {Nx, Ny, Nz};
+      double ha[3][2], hb[3][2];
+      bool vk[3][2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          ha[k][o] = 1.;
+          hb[k][o] = 1.;
+          vk[k][o] = o == 0;
+          if (k < D) {
+            const int c = il[k] - 1 + o;
+            const double* tab = p.axis_tab[k] + (c + 1);
+            ha[k][o] = __ldg(tab);
+            hb[k][o] = __ldg(tab + p.axis_tab_inv);
+            vk[k][o] = c >= 0 && c < Nl[k];
+            if (k == D - 1)
+              vk[k][o] = c >= elo && c < ehi;
+          }
+        }
+      const long long e0 =
+          (long long)(ix - 1) + (long long)Nx * ((D > 1 ? iy - 1 : 0) + (long long)Ny * (D > 2 ? iz - 1 : 0));
+      const bool cx0 = ix > 0, cx1 = ix < Nx;
+      const bool cy0 = D > 1 && iy > 0, cy1 = D > 1 && iy < Ny, cz0 = D > 2 && iz > 0, cz1 = D > 2 && iz < Nz;
+      const bool full_xy = cx0 && cx1 && (D < 2 || (cy0 && cy1));
+      double* row = stage + ((unsigned)q1_rowptr<D>(ix, iy, iz, Nx, Ny, Nz) - start32);
+      if constexpr (D == 3) {
+        double P[3][9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          P[0][k] = P[1][k] = P[2][k] = 0.;
+#pragma unroll
+        for (int oz = 0; oz < 2; ++oz) {
+#pragma unroll
+          for (int oxy = 0; oxy < 4; ++oxy) {
+            const int ox = oxy & 1, oy = oxy >> 1;
+            if (!(vk[0][ox] && vk[1][oy] && vk[2][oz]))
+              continue;
+            const double a[3] = {ha[0][ox], ha[1][oy], ha[2][oz]};
+            const double b[3] = {hb[0][ox], hb[1][oy], hb[2][oz]};
+            const long long e = e0 + ox + (long long)Nx * (oy + (long long)Ny * oz);
+            double out[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+            q1qp_element<D, M, KIND>(G, e, ox, oy, oz, a, b, out);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+              const int sx = s & 1, sy = (s >> 1) & 1, sz = s >> 2;
+              P[oz + sz][3 * (oy + sy) + ox + sx] += out[s];
+            }
+          }
+          if (oz == 0) {
+            if (cz0)
+              row += q1_store_plane<9>(row, P[0], full_xy, cx0, cx1, cy0, cy1);
+          } else {
+            row += q1_store_plane<9>(row, P[1], full_xy, cx0, cx1, cy0, cy1);
+            if (cz1)
+              q1_store_plane<9>(row, P[2], full_xy, cx0, cx1, cy0, cy1);
+          }
+        }
+      } else {
+        constexpr int ND = P3<D>::value;
+        double P[ND];
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+          P[k] = 0.;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          const int ox = o & 1, oy = (o >> 1) & 1;
+          if (!(vk[0][ox] && vk[1][oy]))
+            continue;
+          const double a[3] = {ha[0][ox], ha[1][oy], 1.};
+          const double b[3] = {hb[0][ox], hb[1][oy], 1.};
+          const long long e = e0 + ox + (long long)Nx * oy;
+          double out[NO];
+#pragma unroll
+          for (int s = 0; s < NO; ++s)
+            out[s] = 0.;
+          q1qp_element<D, M, KIND>(G, e, ox, oy, 0, a, b, out);
+#pragma unroll
+          for (int s = 0; s < NO; ++s)
+            P[delta_index<D>(ox - 1 + (s & 1), oy - 1 + ((s >> 1) & 1), 0)] += out[s];
+        }
+        q1_store_plane<ND>(row, P, full_xy, cx0, cx1, cy0, cy1);
+      }
+    }
+
+    if (ACCUMULATE) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < seg; i += blockDim.x)
+        values[start + i] += stage[i];
+      __syncthreads();
+    } else {
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int head = phase;
+        const int body = (seg - head) & ~1;
+        if (head)
+          values[start] = stage[0];
+        if (body > 0)
+          bulk_store_s2g(values + start + head, stage + head, (unsigned)(body * sizeof(double)));
+        if (head + body < seg)
+          values[start + head + body] = stage[head + body];
+        bulk_commit();
+        if (nbuf == 1)
+          bulk_wait_read0();
+        else
+          bulk_wait_read1();
+      }
+      __syncthreads();
+      buf = nbuf == 1 ? 0 : buf ^ 1;
+    }
+  }
+  if (!ACCUMULATE && threadIdx.x == 0)
+    bulk_wait0();
+}
+
+template <int D, int M, int KIND>
+int launch_q1_qp_dmk(Launch& L, const Q1QpParams& p, double* values, bool accumulate)
+{
+  const GridDev& g = p.g;
+  long long layer_rows = 1;
+  for (int k = 0; k < D - 1; ++k)
+    layer_rows *= g.n[k] + 1;
+  if (layer_rows * (g.n[D - 1] + 1) >= (1LL << 31) - Q1G_ROWS)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q1_gather: more than 2^31 vertices");
+  const long long nrows = (p.row_hi - p.row_lo) * layer_rows;
+  const long long nitems = (nrows + Q1G_ROWS - 1) / Q1G_ROWS;
+  if (nitems <= 0)
+    return GDTB_OK;
+  const int stage_doubles = ((Q1G_ROWS * P3<D>::value + 2) + 1) & ~1;
+  const int nbuf = accumulate ? 1 : 2;
+  const size_t smem = (size_t)nbuf * stage_doubles * sizeof(double);
+  auto kern = accumulate ? k_q1_gather_qp<D, M, KIND, true> : k_q1_gather_qp<D, M, KIND, false>;
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int per_sm = 0;
+  GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Q1G_ROWS, smem));
+  if (per_sm < 1)
+    return fail(GDTB_ERR_CUDA, "q1_gather_qp: kernel does not fit on an SM");
+  long long grid = std::min<long long>((long long)per_sm * L.sm_count, nitems);
+  time_begin(L, KF_Q1_GATHER);
+  kern<<<(unsigned)grid, Q1G_ROWS, smem, L.stream>>>(p, values, nrows, (int)nitems, stage_doubles, nbuf);
+  time_end(L, KF_Q1_GATHER);
+  L.count++;
+  GDTB_CUDA(cudaGetLastError());
+  return GDTB_OK;
+}
+
+template <int D, int M>
+int launch_q1_qp_dm(Launch& L, const Q1QpParams& p, double* values, bool accumulate)
+{
+  switch (p.group.kind) {
+    case Q1G_LAPLACE_SCALAR: return launch_q1_qp_dmk<D, M, Q1G_LAPLACE_SCALAR>(L, p, values, accumulate);
+    case Q1G_MASS: return launch_q1_qp_dmk<D, M, Q1G_MASS>(L, p, values, accumulate);
+    default: return launch_q1_qp_dmk<D, M, Q1G_LAPLACE_TENSOR>(L, p, values, accumulate);
+  }
+}
+
+template <int D>
+int launch_q1_qp_d(Launch& L, const Q1QpParams& p, double* values, bool accumulate)
+{
+  switch (p.group.m) {
+    case 1: return launch_q1_qp_dm<D, 1>(L, p, values, accumulate);
+    case 2: return launch_q1_qp_dm<D, 2>(L, p, values, accumulate);
+    case 3: return launch_q1_qp_dm<D, 3>(L, p, values, accumulate);
+    default: return fail(GDTB_ERR_NOT_IMPLEMENTED, "q1_gather_qp: 1 to 3 Gauss points per direction");
+  }
+}
+
+} // namespace
+
+bool q1_qp_supported(int d, int m, int kind)
+{
+  (void)kind;
+  return d >= 1 && d <= 3 && m >= 1 && m <= 3;
+}
+
+int launch_q1_gather_qp(Launch& L, const Q1QpParams& p, double* values, bool accumulate)
+{
+  switch (p.g.d) {
+    case 1: return launch_q1_qp_d<1>(L, p, values, accumulate);
+    case 2: return launch_q1_qp_d<2>(L, p, values, accumulate);
+    case 3: return launch_q1_qp_d<3>(L, p, values, accumulate);
+    default: return fail(GDTB_ERR_INVALID_ARGUMENT, "q1_gather_qp: dimension must be 1, 2 or 3");
   }
 }
 

@@ -242,8 +242,77 @@ __device__ __forceinline__ constexpr int q2_group_order(int D, int rank)
                 : (rank == 0 ? 3 : rank == 1 ? 1 : rank == 2 ? 2 : 0);
 }
 
+// ---- coefficients per quadrature point (kernels.hpp, CgQpGroup): sum factorisation over the tensor rule -------------
+// A[qy][qx] = sum_ql kq[qx, qy, ql] * pl[ql]: the plane's factor PT[t_l][ql][i_l][j_l] contracted first
+template <int D, int M>
+__device__ __forceinline__ void q2qp_contract_last(const double (&kq)[D == 3 ? M * M * M : M * M], const double (&pl)[M],
+                                                   double (&A)[D == 3 ? M : 1][M])
+{
+#pragma unroll
+  for (int qy = 0; qy < (D == 3 ? M : 1); ++qy)
+#pragma unroll
+    for (int qx = 0; qx < M; ++qx) {
+      double a = 0.;
+#pragma unroll
+      for (int ql = 0; ql < M; ++ql)
+        a = fma(kq[D == 3 ? qx + M * (qy + M * ql) : qx + M * ql], pl[ql], a);
+      A[qy][qx] = a;
+    }
+}
+
+// blk[jy][jx] += w * sum_{qy, qx} A[qy][qx] PT[ty][qy][iy][jy] PT[tx][qx][ix][jx]
+template <int D, int M>
+__device__ __forceinline__ void q2qp_plane_term(const CgQpGroup& G, const double (&A)[D == 3 ? M : 1][M], const int ty,
+                                                const int tx, const int iy, const int ix, const double w,
+                                                double (&blk)[D == 3 ? 3 : 1][3])
+{
+  if constexpr (D == 3) {
+    double B[3][M]; // [jy][qx]
+#pragma unroll
+    for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+      for (int qx = 0; qx < M; ++qx) {
+        double b = 0.;
+#pragma unroll
+        for (int qy = 0; qy < M; ++qy)
+          b = fma(A[qy][qx], G.pt[ty][qy][iy][jy], b);
+        B[jy][qx] = b;
+      }
+#pragma unroll
+    for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+      for (int jx = 0; jx < 3; ++jx) {
+        double c = 0.;
+#pragma unroll
+        for (int qx = 0; qx < M; ++qx)
+          c = fma(B[jy][qx], G.pt[tx][qx][ix][jx], c);
+        blk[jy][jx] = fma(w, c, blk[jy][jx]);
+      }
+  } else {
+#pragma unroll
+    for (int jx = 0; jx < 3; ++jx) {
+      double c = 0.;
+#pragma unroll
+      for (int qx = 0; qx < M; ++qx)
+        c = fma(A[0][qx], G.pt[tx][qx][ix][jx], c);
+      blk[0][jx] = fma(w, c, blk[0][jx]);
+    }
+  }
+}
+
+// the factors PT[t][ql][il][jl] of the plane (jl is a run-time value of the thread: select, do not index)
+template <int M>
+__device__ __forceinline__ void q2qp_plane_factors(const CgQpGroup& G, const int t, const int il, const int jl, double (&pl)[M])
+{
+#pragma unroll
+  for (int ql = 0; ql < M; ++ql)
+    pl[ql] = jl == 0 ? G.pt[t][ql][il][0] : (jl == 1 ? G.pt[t][ql][il][1] : G.pt[t][ql][il][2]);
+}
+
 // One (row, plane): D == 3: SX, SY in-thread axes, SL = parity of the last (plane) axis; D == 2: SX in-thread, SL = y.
-template <int D, int SX, int SY, int SL>
+// M == 0: element-wise constant coefficients (1D reference tables); M > 0: one integrand of kind KIND with a coefficient
+// value / tensor per quadrature point, M Gauss points per direction.
+template <int D, int SX, int SY, int SL, int M = 0, int KIND = 0>
 __device__ __forceinline__ void q2_row_plane(const Q2GatherParams& p, const int cx, const int cy, const int cl,
                                              const int slot, double* __restrict__ row)
 {
@@ -326,6 +395,62 @@ __device__ __forceinline__ void q2_row_plane(const Q2GatherParams& p, const int 
         const bool valid = ie != 0.;
         const long long e = (long long)ax.e[ox] + (long long)Nx * ((D == 3 ? ay.e[oy] : al.e[ol]) + (D == 3 ? (long long)Ny * al.e[ol] : 0));
         const int ix = BX::local(ox), iy = D == 3 ? BY::local(oy) : 0;
+        if constexpr (M > 0) {
+          if (!valid)
+            continue;
+          const CgQpGroup& G = p.qp;
+          constexpr int NQ = D == 3 ? M * M * M : M * M;
+          double blk[D == 3 ? 3 : 1][3];
+#pragma unroll
+          for (int jy = 0; jy < (D == 3 ? 3 : 1); ++jy)
+#pragma unroll
+            for (int jx = 0; jx < 3; ++jx)
+              blk[jy][jx] = 0.;
+          double kq[NQ], pl[M], A[D == 3 ? M : 1][M];
+          const double hb_[3] = {hbx, D == 3 ? hby : hbl, hbl}; // 1 / h along x, y (2D: last), last
+          if constexpr (KIND == Q1G_LAPLACE_TENSOR) {
+            const double* src = G.coef + e * (long long)(NQ * D * D);
+#pragma unroll 1
+            for (int rc = 0; rc < D * D; ++rc) {
+              const int r = rc / D, c = rc - r * D;
+#pragma unroll
+              for (int q = 0; q < NQ; ++q)
+                kq[q] = __ldg(src + q * (D * D) + rc);
+              // axis k takes the test derivative if k == r and the ansatz derivative if k == c (laplace.hh:98-101)
+              const int tx = 0 == r ? (0 == c ? QPT_KK : QPT_KM) : (0 == c ? QPT_MK : QPT_MM);
+              const int ty = 1 == r ? (1 == c ? QPT_KK : QPT_KM) : (1 == c ? QPT_MK : QPT_MM);
+              const int tl = last == r ? (last == c ? QPT_KK : QPT_KM) : (last == c ? QPT_MK : QPT_MM);
+              q2qp_plane_factors<M>(G, tl, il, jl, pl);
+              q2qp_contract_last<D, M>(kq, pl, A);
+              const double br = r == 0 ? hb_[0] : (r == 1 ? hb_[1] : hb_[2]), bc = c == 0 ? hb_[0] : (c == 1 ? hb_[1] : hb_[2]);
+              q2qp_plane_term<D, M>(G, A, ty, tx, iy, ix, G.scale * (ie * (br * bc)), blk);
+            }
+          } else {
+            const double* src = G.coef + e * (long long)NQ;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+              kq[q] = __ldg(src + q);
+            q2qp_plane_factors<M>(G, QPT_MM, il, jl, pl);
+            q2qp_contract_last<D, M>(kq, pl, A);
+            if constexpr (KIND == Q1G_MASS)
+              q2qp_plane_term<D, M>(G, A, QPT_MM, QPT_MM, iy, ix, G.scale * ie, blk);
+            else {
+              // kappa = c(x) I: r = x and (3D) r = y share the mass factor along the last axis, r = last has its own
+              q2qp_plane_term<D, M>(G, A, QPT_MM, QPT_KK, iy, ix, G.scale * (ie * (hbx * hbx)), blk);
+              if constexpr (D == 3)
+                q2qp_plane_term<D, M>(G, A, QPT_KK, QPT_MM, iy, ix, G.scale * (ie * (hby * hby)), blk);
+              q2qp_plane_factors<M>(G, QPT_KK, il, jl, pl);
+              q2qp_contract_last<D, M>(kq, pl, A);
+              q2qp_plane_term<D, M>(G, A, QPT_MM, QPT_MM, iy, ix, G.scale * (ie * (hbl * hbl)), blk);
+            }
+          }
+#pragma unroll
+          for (int jy = 0; jy < (D == 3 ? 3 : 1); ++jy)
+#pragma unroll
+            for (int jx = 0; jx < 3; ++jx)
+              acc[D == 3 ? BY::first(oy) + jy : 0][BX::first(ox) + jx] += blk[jy][jx];
+          continue;
+        }
 #pragma unroll 1
         for (int gi = 0; gi < p.n_groups; ++gi) {
           const Q2Group& G = p.group[gi];
@@ -611,11 +736,13 @@ __device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const i
   }
 }
 
-template <int SF, int D, int SX, int SY, int SL>
+template <int SF, int D, int SX, int SY, int SL, int M = 0, int KIND = 0>
 __device__ __forceinline__ void q2_dispatch(const Q2GatherParams& p, const int cx, const int cy, const int cl,
                                             const int slot, double* __restrict__ row)
 {
-  if (SF == 2)
+  if constexpr (SF == 3)
+    q2_row_plane<D, SX, SY, SL, M, KIND>(p, cx, cy, cl, slot, row);
+  else if (SF == 2)
     q2_row_plane_sf<D, SX, SY, SL, true>(p, cx, cy, cl, slot, row);
   else if (SF == 1)
     q2_row_plane_sf<D, SX, SY, SL, false>(p, cx, cy, cl, slot, row);
@@ -623,9 +750,10 @@ __device__ __forceinline__ void q2_dispatch(const Q2GatherParams& p, const int c
     q2_row_plane<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
 }
 
-// SF: 0 per-element coefficients, 1 sum-factorised (constant coefficients), 2 sum-factorised with a single group
-template <int D, bool ACCUMULATE, int SF>
-__global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : 2)
+// SF: 0 per-element coefficients, 1 sum-factorised (constant coefficients), 2 sum-factorised with a single group,
+// 3 one integrand of kind KIND with a coefficient per quadrature point (M Gauss points per direction)
+template <int D, bool ACCUMULATE, int SF, int M = 0, int KIND = 0>
+__global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF == 3 ? 1 : 2))
     k_q2_gather(const __grid_constant__ Q2GatherParams p, double* __restrict__ values, int stage_doubles, int nbuf)
 {
   extern __shared__ __align__(16) double smem[];
@@ -665,21 +793,21 @@ __global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : 2)
       double* row = stage + int(q2_row_offset<D>(g, rg, cx, cy, cl) - off0);
       if (D == 3) {
         switch (rg.s) {
-          case 0: q2_dispatch<SF, 3, 0, 0, 0>(p, cx, cy, cl, slot, row); break;
-          case 1: q2_dispatch<SF, 3, 1, 0, 0>(p, cx, cy, cl, slot, row); break;
-          case 2: q2_dispatch<SF, 3, 0, 1, 0>(p, cx, cy, cl, slot, row); break;
-          case 3: q2_dispatch<SF, 3, 1, 1, 0>(p, cx, cy, cl, slot, row); break;
-          case 4: q2_dispatch<SF, 3, 0, 0, 1>(p, cx, cy, cl, slot, row); break;
-          case 5: q2_dispatch<SF, 3, 1, 0, 1>(p, cx, cy, cl, slot, row); break;
-          case 6: q2_dispatch<SF, 3, 0, 1, 1>(p, cx, cy, cl, slot, row); break;
-          default: q2_dispatch<SF, 3, 1, 1, 1>(p, cx, cy, cl, slot, row); break;
+          case 0: q2_dispatch<SF, 3, 0, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
+          case 1: q2_dispatch<SF, 3, 1, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
+          case 2: q2_dispatch<SF, 3, 0, 1, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
+          case 3: q2_dispatch<SF, 3, 1, 1, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
+          case 4: q2_dispatch<SF, 3, 0, 0, 1, M, KIND>(p, cx, cy, cl, slot, row); break;
+          case 5: q2_dispatch<SF, 3, 1, 0, 1, M, KIND>(p, cx, cy, cl, slot, row); break;
+          case 6: q2_dispatch<SF, 3, 0, 1, 1, M, KIND>(p, cx, cy, cl, slot, row); break;
+          default: q2_dispatch<SF, 3, 1, 1, 1, M, KIND>(p, cx, cy, cl, slot, row); break;
         }
       } else {
         switch (rg.s) {
-          case 0: q2_dispatch<SF, 2, 0, 0, 0>(p, cx, cy, cl, slot, row); break;
-          case 1: q2_dispatch<SF, 2, 1, 0, 0>(p, cx, cy, cl, slot, row); break;
-          case 2: q2_dispatch<SF, 2, 0, 0, 1>(p, cx, cy, cl, slot, row); break;
-          default: q2_dispatch<SF, 2, 1, 0, 1>(p, cx, cy, cl, slot, row); break;
+          case 0: q2_dispatch<SF, 2, 0, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
+          case 1: q2_dispatch<SF, 2, 1, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
+          case 2: q2_dispatch<SF, 2, 0, 0, 1, M, KIND>(p, cx, cy, cl, slot, row); break;
+          default: q2_dispatch<SF, 2, 1, 0, 1, M, KIND>(p, cx, cy, cl, slot, row); break;
         }
       }
     }
@@ -764,7 +892,60 @@ long long q2_sf_table_doubles(const GridDev& g)
   return total;
 }
 
+namespace {
+
+using Q2Kernel = void (*)(const Q2GatherParams, double*, int, int);
+
+template <int D, int M>
+Q2Kernel q2_qp_kernel_dm(int kind, bool accumulate)
+{
+  switch (kind) {
+    case Q1G_LAPLACE_SCALAR:
+      return accumulate ? k_q2_gather<D, true, 3, M, Q1G_LAPLACE_SCALAR> : k_q2_gather<D, false, 3, M, Q1G_LAPLACE_SCALAR>;
+    case Q1G_MASS: return accumulate ? k_q2_gather<D, true, 3, M, Q1G_MASS> : k_q2_gather<D, false, 3, M, Q1G_MASS>;
+    default:
+      return accumulate ? k_q2_gather<D, true, 3, M, Q1G_LAPLACE_TENSOR> : k_q2_gather<D, false, 3, M, Q1G_LAPLACE_TENSOR>;
+  }
+}
+
+template <int D>
+Q2Kernel q2_qp_kernel_d(int m, int kind, bool accumulate)
+{
+  switch (m) {
+    case 2: return q2_qp_kernel_dm<D, 2>(kind, accumulate);
+    case 3: return q2_qp_kernel_dm<D, 3>(kind, accumulate);
+    case 4: return q2_qp_kernel_dm<D, 4>(kind, accumulate);
+    default: return nullptr;
+  }
+}
+
+int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate, bool qp);
+
+} // namespace
+
+bool q2_qp_supported(int d, int m, int kind)
+{
+  (void)kind;
+  return (d == 2 && m >= 2 && m <= 4) || (d == 3 && m >= 2 && m <= 3);
+}
+
 int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate)
+{
+  return launch_q2_impl(L, p, sp, values, accumulate, false);
+}
+
+int launch_q2_gather_qp(Launch& L, Q2GatherParams& p, const CgQpGroup& group, const SpaceDev& sp, double* values,
+                        bool accumulate)
+{
+  p.qp = group;
+  p.sf = 0;
+  p.n_groups = 0;
+  return launch_q2_impl(L, p, sp, values, accumulate, true);
+}
+
+namespace {
+
+int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate, bool qp)
 {
   const GridDev& g = p.g;
   const int d = g.d;
@@ -827,9 +1008,13 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
   const bool single_group = p.sf && p.n_groups == 1;
   const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : (single_group ? 1 : 2));
   const size_t smem = (size_t)nbuf * stage_doubles * sizeof(double);
-  auto kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 0> : k_q2_gather<3, false, 0>)
-                     : (accumulate ? k_q2_gather<2, true, 0> : k_q2_gather<2, false, 0>);
-  if (p.sf) {
+  Q2Kernel kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 0> : k_q2_gather<3, false, 0>)
+                         : (accumulate ? k_q2_gather<2, true, 0> : k_q2_gather<2, false, 0>);
+  if (qp) {
+    if (!q2_qp_supported(d, p.qp.m, p.qp.kind))
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather_qp: unsupported number of Gauss points per direction");
+    kern = d == 3 ? q2_qp_kernel_d<3>(p.qp.m, p.qp.kind, accumulate) : q2_qp_kernel_d<2>(p.qp.m, p.qp.kind, accumulate);
+  } else if (p.sf) {
     if (p.n_groups == 1)
       kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 2> : k_q2_gather<3, false, 2>)
                     : (accumulate ? k_q2_gather<2, true, 2> : k_q2_gather<2, false, 2>);
@@ -864,6 +1049,8 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
   GDTB_CUDA(cudaGetLastError());
   return GDTB_OK;
 }
+
+} // namespace
 
 // ---- closed-form sparsity pattern of the CG Q2 element stencil ------------------------------------------------------
 // One thread per row: the columns of a row are the lattice points of its clipped coupling box, grouped by parity pattern

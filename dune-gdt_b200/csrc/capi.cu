@@ -435,6 +435,67 @@ bool matop_dg_eligible(const gdtb_matop* op)
   return true;
 }
 
+// CG Q1 / Q2 row gather with coefficients that vary inside a cell (assemble_q1_gather.cu::k_q1_gather_qp,
+// assemble_q2_gather.cu SF = 3): Laplace (scalar or full-tensor kappa) / product element forms whose coefficients are
+// arbitrary grid functions -- sampled by the caller (GDTB_FN_QP_*), analytic, discrete (GDTB_FN_DOF_VECTOR) or, mixed in
+// with those, constants / per-element values.  Every coefficient is turned into one value per quadrature point.
+bool fn_is_tensor(const gdtb_function& f)
+{
+  return f.kind == GDTB_FN_CONST_TENSOR || f.kind == GDTB_FN_ELEM_TENSOR || f.kind == GDTB_FN_QP_TENSOR;
+}
+
+bool matop_cg_qp_eligible(const gdtb_matop* op)
+{
+  const SpaceDev& sp = op->test;
+  if (sp.kind != GDTB_SPACE_CG || std::memcmp(&op->test, &op->ansatz, sizeof(SpaceDev)) != 0 || op->grid.periodic)
+    return false;
+  const int d = op->grid.d;
+  if (!(sp.K == 1 || (sp.K == 2 && (d == 2 || d == 3))))
+    return false;
+  if (op->pattern
+      && (op->pattern->stencil != GDTB_STENCIL_ELEMENT || std::memcmp(&op->pattern->test, &sp, sizeof(SpaceDev)) != 0
+          || std::memcmp(&op->pattern->ansatz, &sp, sizeof(SpaceDev)) != 0))
+    return false;
+  if (!op->coupling_forms.empty() || !op->boundary_forms.empty() || op->element_forms.empty())
+    return false;
+  if (std::getenv("GDTB_NO_QP_GATHER"))
+    return false;
+  for (const auto& lf : op->element_forms) {
+    const int m = gauss_points_for_order(form_quadrature_order(lf.form, sp.K, ROLE_ELEMENT));
+    for (int t = 0; t < lf.form.n_terms; ++t) {
+      const gdtb_integrand& in = lf.form.terms[t];
+      if (in.kind != GDTB_INT_LAPLACE && in.kind != GDTB_INT_PRODUCT)
+        return false;
+      if (in.kind == GDTB_INT_PRODUCT && fn_is_tensor(in.diffusion))
+        return false;
+      const int kind = in.kind == GDTB_INT_PRODUCT ? Q1G_MASS
+                                                    : (fn_is_tensor(in.diffusion) ? Q1G_LAPLACE_TENSOR : Q1G_LAPLACE_SCALAR);
+      if (!(sp.K == 1 ? q1_qp_supported(d, m, kind) : q2_qp_supported(d, m, kind)))
+        return false;
+    }
+  }
+  return true;
+}
+
+// 1D point tables of a rule: pt[t][q][a][b] = w_q D^ta phi_a(x_q) D^tb phi_b(x_q) (kernels.hpp, QPT_*)
+void qp_point_tables(int K, int m, double qx[MAX_Q1D], double pt[4][MAX_Q1D][3][3])
+{
+  double qw[MAX_Q1D];
+  gauss_legendre_01(m, qx, qw);
+  std::memset(pt, 0, sizeof(double) * 4 * MAX_Q1D * 9);
+  for (int q = 0; q < m; ++q) {
+    double v[MAX_K + 1], dv[MAX_K + 1];
+    lagrange_1d(K, qx[q], v, dv);
+    for (int a = 0; a <= K; ++a)
+      for (int b = 0; b <= K; ++b) {
+        pt[QPT_MM][q][a][b] = qw[q] * v[a] * v[b];
+        pt[QPT_KK][q][a][b] = qw[q] * dv[a] * dv[b];
+        pt[QPT_KM][q][a][b] = qw[q] * dv[a] * v[b];
+        pt[QPT_MK][q][a][b] = qw[q] * v[a] * dv[b];
+      }
+  }
+}
+
 int build_q2_params(const gdtb_matop* op, Q2GatherParams& p)
 {
   std::memset(&p, 0, sizeof(p));
@@ -595,7 +656,14 @@ void q1_slab_ranges(const GridDev& g, long long begin, long long end, long long&
 }
 
 // per-axis geometry tables of a grid (ignoring the slab), built on the device at first use
+int q1_axis_tables(gdtb_ctx* ctx, const GridDev& grid, const double* (&axis_tab)[3], long long& axis_tab_inv);
+
 int q1_axis_tables(gdtb_ctx* ctx, const GridDev& grid, Q1GatherParams& p)
+{
+  return q1_axis_tables(ctx, grid, p.axis_tab, p.axis_tab_inv);
+}
+
+int q1_axis_tables(gdtb_ctx* ctx, const GridDev& grid, const double* (&axis_tab)[3], long long& axis_tab_inv)
 {
   GridDev key = grid;
   key.layer_lo = 0;
@@ -621,8 +689,8 @@ int q1_axis_tables(gdtb_ctx* ctx, const GridDev& grid, Q1GatherParams& p)
     found = &ctx->axis_tables.back();
   }
   for (int k = 0; k < 3; ++k)
-    p.axis_tab[k] = found->d_tab + found->offset[k];
-  p.axis_tab_inv = found->inv;
+    axis_tab[k] = found->d_tab + found->offset[k];
+  axis_tab_inv = found->inv;
   return GDTB_OK;
 }
 
@@ -1194,6 +1262,7 @@ int gdtb_matop_destroy(gdtb_matop* op)
     cudaFree(op->d_values);
   cudaFree(op->d_forms);
   cudaFree(op->d_q2_tab);
+  cudaFree(op->d_qp_scratch);
   cudaFree(op->d_own_rowptr);
   cudaFree(op->d_own_colidx);
   delete op;
@@ -1269,9 +1338,16 @@ const char* gdtb_matop_plan(gdtb_matop* op)
 {
   if (!op)
     return "";
-  op->plan = matop_q1_eligible(op)
-                 ? "q1_gather"
-                 : (matop_q2_eligible(op) ? "q2_gather" : (matop_dg_eligible(op) ? "dg_gather" : "generic_coloured"));
+  if (matop_q1_eligible(op))
+    op->plan = "q1_gather";
+  else if (matop_q2_eligible(op))
+    op->plan = "q2_gather";
+  else if (matop_cg_qp_eligible(op))
+    op->plan = op->test.K == 1 ? "q1_gather_qp" : "q2_gather_qp";
+  else if (matop_dg_eligible(op))
+    op->plan = "dg_gather";
+  else
+    op->plan = "generic_coloured";
   return op->plan.c_str();
 }
 
@@ -1722,6 +1798,78 @@ static int q1_rhs_params(gdtb_vecfun* fun, Q1GatherParams& p)
   return GDTB_OK;
 }
 
+// CG Q1 / Q2 element forms with coefficients that vary inside a cell: one gather launch per integrand (the first one
+// overwrites, the others accumulate), every coefficient given / sampled per quadrature point of its form's rule
+static int assemble_cg_qp(gdtb_matop* op, bool accumulate)
+{
+  gdtb_ctx* ctx = op->ctx;
+  Launch& L = ctx->launch;
+  const GridDev& g = op->grid;
+  const int d = g.d, K = op->test.K;
+  const long long n_last = g.n[d - 1];
+  const long long plane = g.ne / n_last; // elements per layer of the last direction
+  // element layers the owned rows need (the slab plus the ghost layer below it)
+  const long long lay_lo = K == 1 ? op->elem_lo : std::max<long long>(g.layer_lo - 1, 0);
+  const long long lay_hi = K == 1 ? op->elem_hi : g.layer_hi;
+  const long long e_begin = lay_lo * plane, e_end = lay_hi * plane;
+  bool first = !accumulate;
+  for (const auto& lf : op->element_forms) {
+    const int m = gauss_points_for_order(form_quadrature_order(lf.form, K, ROLE_ELEMENT));
+    const int nq = ipow(m, d);
+    CgQpGroup G;
+    std::memset(&G, 0, sizeof(G));
+    double qx[MAX_Q1D];
+    qp_point_tables(K, m, qx, G.pt);
+    G.m = m;
+    for (int t = 0; t < lf.form.n_terms; ++t) {
+      const gdtb_integrand& in = lf.form.terms[t];
+      const gdtb_function& f = in.diffusion;
+      const bool tensor = fn_is_tensor(f);
+      G.kind = in.kind == GDTB_INT_PRODUCT ? Q1G_MASS : (tensor ? Q1G_LAPLACE_TENSOR : Q1G_LAPLACE_SCALAR);
+      G.scale = lf.form.scaling;
+      const int comps = tensor ? d * d : 1;
+      if (f.kind == GDTB_FN_QP_SCALAR || f.kind == GDTB_FN_QP_TENSOR)
+        G.coef = f.data; // already one value per quadrature point, indexed by the global element index
+      else {
+        const size_t bytes = sizeof(double) * (size_t)(e_end - e_begin) * nq * comps;
+        if (op->d_qp_scratch_bytes < bytes) {
+          cudaFree(op->d_qp_scratch);
+          op->d_qp_scratch = nullptr;
+          op->d_qp_scratch_bytes = 0;
+          if (cudaMalloc(&op->d_qp_scratch, bytes) != cudaSuccess)
+            return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (coefficient samples)");
+          op->d_qp_scratch_bytes = bytes;
+        }
+        GDTB_TRY(launch_sample_function(L, g, to_dev(f, &lf), m, qx, tensor ? 1 : 0, e_begin, e_end, op->d_qp_scratch));
+        G.coef = op->d_qp_scratch - e_begin * (long long)(nq * comps);
+      }
+      if (K == 1) {
+        Q1QpParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.g = g;
+        p.div_vx = make_fast_div((unsigned)(g.n[0] + 1));
+        p.div_vy = make_fast_div((unsigned)(d > 1 ? g.n[1] + 1 : 1));
+        GDTB_TRY(q1_axis_tables(ctx, g, p.axis_tab, p.axis_tab_inv));
+        p.group = G;
+        p.row_lo = op->row_lo;
+        p.row_hi = op->row_hi;
+        p.elem_lo = op->elem_lo;
+        p.elem_hi = op->elem_hi;
+        p.value_offset = q1_layer_rowptr(g, p.row_lo);
+        p.row_offset = p.row_lo * q1_layer_rows(g);
+        GDTB_TRY(launch_q1_gather_qp(L, p, op->d_values, !first));
+      } else {
+        Q2GatherParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.g = g;
+        GDTB_TRY(launch_q2_gather_qp(L, p, G, op->test, op->d_values, !first));
+      }
+      first = false;
+    }
+  }
+  return GDTB_OK;
+}
+
 static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchronize)
 {
   if (!op && !fun)
@@ -1737,7 +1885,8 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
   const bool op_fast = op && matop_q1_eligible(op);
   const bool fun_fast = fun && vecfun_q1_eligible(fun);
   const bool op_q2 = op && !op_fast && matop_q2_eligible(op);
-  if (op && !op_fast && !op_q2 && (op->slab || !op->pattern))
+  const bool op_qp = op && !op_fast && !op_q2 && matop_cg_qp_eligible(op);
+  if (op && !op_fast && !op_q2 && !op_qp && (op->slab || !op->pattern))
     return fail(GDTB_ERR_NOT_IMPLEMENTED,
                 "slab-partitioned / pattern-free operators only support forms the CG Q1 / Q2 row-gather kernels cover");
   if (fun && !fun_fast && fun->slab)
@@ -1776,8 +1925,12 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     GDTB_TRY(launch_q2_gather(L, p, op->test, op->d_values, accumulate));
   }
 
+  // --- CG row gather with coefficients per quadrature point ----------------------------------
+  if (op_qp)
+    GDTB_TRY(assemble_cg_qp(op, accumulate));
+
   // --- DG row-gather path ------------------------------------------------------------------
-  const bool op_dg = op && !op_fast && !op_q2 && matop_dg_eligible(op);
+  const bool op_dg = op && !op_fast && !op_q2 && !op_qp && matop_dg_eligible(op);
   if (op_dg) {
     std::vector<FormDev> forms;
     for (const auto& lf : op->element_forms) {
@@ -1832,7 +1985,7 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
   }
 
   // --- generic path --------------------------------------------------------------------------
-  if (op && !op_fast && !op_q2 && !op_dg) {
+  if (op && !op_fast && !op_q2 && !op_qp && !op_dg) {
     const gdtb_pattern* pat = op->pattern;
     if (!accumulate)
       GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pat->nnz, L.stream));

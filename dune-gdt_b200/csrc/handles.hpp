@@ -91,6 +91,8 @@ struct gdtb_matop
   std::vector<char> h_forms_cache; // what d_forms holds
   double* d_q2_tab = nullptr; // per-axis sum-factorisation tables of the CG Q2 gather path
   size_t d_q2_tab_bytes = 0;
+  double* d_qp_scratch = nullptr; // coefficient samples (one value / tensor per quadrature point) of the *_qp paths
+  size_t d_qp_scratch_bytes = 0;
   // CSR pattern materialised on demand for the closed-form CG Q1 operator (Dirichlet constraints, SpMV, solvers)
   long long* d_own_rowptr = nullptr;
   int* d_own_colidx = nullptr;

@@ -147,6 +147,51 @@ int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long lo
                          const double* qx, const double* qw, const double* phi /* [m][2] */, double* tab,
                          long long stride);
 
+// ---- CG row gather with coefficients that vary inside a cell -----------------------------------------------------
+// LocalLaplaceIntegrand / LocalElementProductIntegrand with an arbitrary GridFunction (laplace.hh:40-48, product.hh:
+// 56-65): the coefficient arrives as one value (or one d x d tensor) per quadrature point of the form's own rule --
+// caller-sampled (GDTB_FN_QP_*) or sampled on the device from an analytic / discrete function (k_sample_function).
+// The quadrature sum of integrals.hh:116-132 is evaluated per element by sum factorisation over the tensor rule:
+//   L_e[i][j] = scale |det J_e| sum_{r,c} (1/h_r)(1/h_c) sum_q kappa_rc(x_q) prod_k PT^{(k==r, k==c)}[q_k][i_k][j_k],
+//   PT^{(ta,tb)}[q][a][b] = w_q D^ta phi_a(x_q) D^tb phi_b(x_q)   (1D point tables, a = test, b = ansatz)
+// (mass: PT^{(0,0)} along every axis), one integrand per launch, rows owned and written once like in the
+// constant-coefficient gather kernels.
+enum
+{
+  QPT_MM = 0, // phi_a  phi_b
+  QPT_KK = 1, // phi_a' phi_b'
+  QPT_KM = 2, // phi_a' phi_b   (test derivative)
+  QPT_MK = 3  // phi_a  phi_b'  (ansatz derivative)
+};
+
+struct CgQpGroup
+{
+  int kind;           // Q1G_LAPLACE_SCALAR, Q1G_LAPLACE_TENSOR or Q1G_MASS
+  int m;              // Gauss points per direction
+  double scale;       // MatrixOperator::scaling at append time
+  const double* coef; // device array [e][q] (scalar kinds) or [e][q][d * d]; e = element index of the grid view
+  double pt[4][MAX_Q1D][3][3];
+};
+
+struct Q1QpParams
+{
+  GridDev g;
+  FastDiv div_vx, div_vy;
+  const double* axis_tab[3];
+  long long axis_tab_inv;
+  CgQpGroup group;
+  long long value_offset, row_offset;
+  long long row_lo, row_hi, elem_lo, elem_hi;
+};
+bool q1_qp_supported(int d, int m, int kind);
+int launch_q1_gather_qp(Launch& L, const Q1QpParams& p, double* values, bool accumulate);
+
+// samples a grid function at the quadrature points of the tensor rule with m points per direction: out[(e - e_begin) *
+// m^d + q] (scalar) or out[((e - e_begin) * m^d + q) * d * d + r * d + c] (tensor = 1: scalar functions mean c * I) for the
+// elements e_begin <= e < e_end
+int launch_sample_function(Launch& L, const GridDev& g, const FnDev& f, int m, const double* qx /* host, m points */,
+                           int tensor, long long e_begin, long long e_end, double* out);
+
 // ---- CG-Q2 row-gather assembly (assemble_q2_gather.cu) --------------------------------------------
 constexpr int Q2G_MAX_GROUPS = 3;
 
@@ -195,6 +240,7 @@ struct Q2GatherParams
   int sf;
   const double* sf_tab;
   long long sf_axis_off[3], sf_group_stride;
+  CgQpGroup qp; // launch_q2_gather_qp: the one integrand with a coefficient per quadrature point
 };
 
 long long q2_sf_table_doubles(const GridDev& g); // doubles per group
@@ -207,6 +253,10 @@ struct Q2SlabRange
 };
 int q2_slab_ranges(const GridDev& g, const SpaceDev& sp, Q2SlabRange* out /* [8] */);
 int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate);
+// the same row / plane decomposition with ONE integrand whose coefficient is given per quadrature point
+bool q2_qp_supported(int d, int m, int kind);
+int launch_q2_gather_qp(Launch& L, Q2GatherParams& p, const CgQpGroup& group, const SpaceDev& sp, double* values,
+                        bool accumulate);
 
 // ---- DG row-gather assembly (assemble_dg_gather.cu) -----------------------------------------------
 constexpr int DGG_THREADS = 128;

@@ -99,6 +99,20 @@ def test_cg_matrix_parity_variable_coefficients(gdt, ctx, oracle, name, n, order
     assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
     ref, _ = oracle.assemble(gdesc, CG, order, rp, ci, forms)
     assert rel_err(values, ref) <= TOL, plan
+    # the fast path: owner-computes-rows gather with the coefficient stream per quadrature point (Q1 in 1-3D, Q2 in 2D /
+    # 3D, up to 3 Gauss points per direction in 3D); everything else is the quadrature-faithful coloured scatter
+    m, _ = form_points(gdt, ctx, gdesc, CG, order, forms[0], D.ROLE_ELEMENT)
+    fast = (order == 1 and m <= 3) or (order == 2 and len(n) > 1 and m <= (3 if len(n) == 3 else 4))
+    assert plan == (f"q{order}_gather_qp" if fast else "generic_coloured"), (plan, m)
+    # ... and it agrees with the quadrature-faithful kernels to rounding
+    import os
+
+    os.environ["GDTB_NO_QP_GATHER"] = "1"
+    try:
+        _, _, generic, _, plan2 = gpu_assemble(gdt, ctx, gdesc, CG, order, D.STENCIL_ELEMENT, element=forms)
+    finally:
+        del os.environ["GDTB_NO_QP_GATHER"]
+    assert plan2 == "generic_coloured" and rel_err(values, generic) <= TOL
 
 
 @pytest.mark.parametrize("n", [[9], [6, 5], [5, 4, 3]])

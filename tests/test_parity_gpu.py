@@ -165,13 +165,13 @@ def element_cases():
             ("q1-laplace-elem", n, 1, [laplace(D.fn_elem(rng_elem(n)))], "q1_gather"),
             ("q1-laplace-elem+mass-elem", n, 1, [laplace(D.fn_elem(rng_elem(n))), mass(D.fn_elem(rng_elem(n, seed=7)))], "q1_gather"),
             ("q1-laplace-tensor", n, 1, [laplace(D.fn_const(kt))], "q1_gather"),
-            ("q1-laplace-builtin", n, 1, [laplace(D.fn_builtin(D.BUILTIN_QUADRATIC, 2, 1.0, 0.5))], "generic_coloured"),
+            ("q1-laplace-builtin", n, 1, [laplace(D.fn_builtin(D.BUILTIN_QUADRATIC, 2, 1.0, 0.5))], "q1_gather_qp"),
             ("q1-laplace-elemtensor", n, 1, [laplace(D.fn_elem(np.tile(kt, (int(np.prod(n)), 1, 1)) * rng_elem(n)[:, None, None]))], "q1_gather"),
             ("q2-laplace-const", n, 2, [laplace(1.0)], "q2_gather" if d > 1 else "generic_coloured"),
             ("q2-laplace-scaled-overint", n, 2, [laplace(2.5, scaling=0.5, over_integrate=1)], "q2_gather" if d > 1 else "generic_coloured"),
             ("q2-mass-elem", n, 2, [mass(D.fn_elem(rng_elem(n, seed=11)))], "q2_gather" if d > 1 else "generic_coloured"),
-            ("q2-laplace-tensor", n, 2, [laplace(D.fn_const(kt))], "generic_coloured"),
-            ("q2-mass-builtin", n, 2, [mass(D.fn_builtin(D.BUILTIN_AFFINE, 1, 1.0, 0.3, 0.2, 0.1))], "generic_coloured"),
+            ("q2-laplace-tensor", n, 2, [laplace(D.fn_const(kt))], "q2_gather_qp" if d > 1 else "generic_coloured"),
+            ("q2-mass-builtin", n, 2, [mass(D.fn_builtin(D.BUILTIN_AFFINE, 1, 1.0, 0.3, 0.2, 0.1))], "q2_gather_qp" if d > 1 else "generic_coloured"),
             ("q2-laplace-elem+mass", n, 2, [D.form([D.integrand(D.INT_LAPLACE, diffusion=D.fn_elem(rng_elem(n))), D.integrand(D.INT_PRODUCT, diffusion=2.0)])], "q2_gather" if d > 1 else "generic_coloured"),
         ]
     cases += [

@@ -1,6 +1,10 @@
 """Times the non-headline configurations of SURVEY.md section 8 (C1, C3, C5) through the C ABI; device-resident, CUDA events.
 
-  python tools/bench_configs.py [c1] [c3] [c5] [--n N]
+  python tools/bench_configs.py [c1] [c3] [c5] [c2-qp] [c2-qpt] [c2-builtin] [c5-qp] [c5-qpt] [c5-builtin] [--n N]
+
+The *-qp / *-qpt / *-builtin variants assemble C2 / C5 with a coefficient that varies inside every cell: one random
+value (qp) or one full 3 x 3 tensor (qpt) per quadrature point in a device array, or an analytic kappa(x) sampled on the
+device (builtin).  GDTB_NO_QP_GATHER=1 times the quadrature-faithful coloured-scatter kernels on the same input.
 """
 import ctypes as C
 import json
@@ -58,10 +62,51 @@ def run(name, gdesc, kind, order, stencil, element=(), coupling=(), boundary=(),
     print(json.dumps(out), flush=True)
 
 
+def qp_function(ne, nq, d, tensor, order):
+    """device-resident coefficient samples (borrowed by the library: data_on_device = 1)"""
+    g = torch.Generator(device="cuda").manual_seed(20251017)
+    if tensor:
+        a = 0.2 * torch.rand(ne, nq, d, d, dtype=torch.float64, device="cuda", generator=g)
+        a += torch.eye(d, dtype=torch.float64, device="cuda")
+    else:
+        a = 0.5 + torch.rand(ne, nq, dtype=torch.float64, device="cuda", generator=g)
+    f = D.Function()
+    f.kind = D.FN_QP_TENSOR if tensor else D.FN_QP_SCALAR
+    f.order = order
+    f.qp_per_element = nq
+    f.data_on_device = 1
+    f.data = C.cast(a.data_ptr(), C.POINTER(C.c_double))
+    f._keep = a
+    return f
+
+
+def variable_kappa(which, n, order):
+    """(name suffix, Laplace form) for the *-qp / *-qpt / *-builtin variants; kappa has the declared order --kappa-order
+    (default 0), so the rule has order kappa_order + 2 p: 2 points per direction for Q1 and 3 for Q2 by default"""
+    out = []
+    prefix = "c2" if order == 1 else "c5"
+    kord = int(sys.argv[sys.argv.index("--kappa-order") + 1]) if "--kappa-order" in sys.argv else 0
+    m = (kord + 2 * order) // 2 + 1
+    if f"{prefix}-qp" in which:
+        out.append(("scalar kappa per quadrature point", D.form(D.integrand(D.INT_LAPLACE, diffusion=qp_function(n**3, m**3, 3, False, kord)))))
+    if f"{prefix}-qpt" in which:
+        out.append(("3x3 kappa per quadrature point", D.form(D.integrand(D.INT_LAPLACE, diffusion=qp_function(n**3, m**3, 3, True, kord)))))
+    if f"{prefix}-builtin" in which:
+        out.append(("analytic kappa(x) = 1 + 0.5 |x|^2 sampled on the device",
+                    D.form(D.integrand(D.INT_LAPLACE, diffusion=D.fn_builtin(D.BUILTIN_QUADRATIC, kord, 1.0, 0.5)))))
+    return [(f"{label} ({m}^3 points per element)", form) for label, form in out]
+
+
 def main():
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c3", "c5"]
+    which = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()] or ["c1", "c3", "c5"]
     n_override = int(sys.argv[sys.argv.index("--n") + 1]) if "--n" in sys.argv else None
     lap = D.form(D.integrand(D.INT_LAPLACE, diffusion=1.0))
+    for order, n_default in ((1, 256), (2, 128)):
+        n = n_override or n_default
+        for label, form in variable_kappa(which, n, order):
+            run(f"C{2 if order == 1 else 5} 3D Q{order} {n}^3, {label}", D.grid_desc(-1.0, 1.0, [n, n, n]), D.SPACE_CG, order,
+                D.STENCIL_ELEMENT, element=[form], reps=3)
+            torch.cuda.empty_cache()
     if "c1" in which:
         n = n_override or 128
         run(f"C1 2D Q1 {n}^2", D.grid_desc(-1.0, 1.0, [n, n]), D.SPACE_CG, 1, D.STENCIL_ELEMENT, element=[lap], reps=20)
