@@ -196,14 +196,45 @@ def fv_extra(gdt, ctx, torch, hbm_gbs, peak_src):
     return out
 
 
+def demangle(name):
+    """c++filt if the box has it; the mangled symbol otherwise (it is what ncu launch lists show either way)"""
+    if not name:
+        return name
+    try:
+        out = subprocess.run(["c++filt", name], capture_output=True, text=True, timeout=5).stdout.strip()
+        return out or name
+    except (OSError, subprocess.TimeoutExpired):
+        return name
+
+
+def kernel_name(gdt, ctx, family):
+    return demangle(gdt.capi.lib().gdtb_ctx_kernel_name(ctx._h, family.encode()).decode())
+
+
+def qp_function(torch, ne, nq, order):
+    """one coefficient value per quadrature point in a device array the library borrows (data_on_device = 1)"""
+    from dune_gdt_b200 import descriptors as D
+
+    g = torch.Generator(device="cuda").manual_seed(20251017)
+    a = 0.5 + torch.rand(ne, nq, dtype=torch.float64, device="cuda", generator=g)
+    f = D.Function()
+    f.kind, f.order, f.qp_per_element, f.data_on_device = D.FN_QP_SCALAR, order, nq, 1
+    f.data = C.cast(a.data_ptr(), C.POINTER(C.c_double))
+    f._keep = a
+    return f
+
+
 def assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src):
-    """C3 (2D SWIPDG DG-Q1 2048^2: element + inner-coupling + boundary forms) and C5 (3D Q2 Laplace 128^3) on one GPU:
-    device-resident ms per assembly and the HBM roofline of the row-gather kernel (8 nnz + 8 ndof algorithmic bytes,
-    SURVEY.md 8d).  Reported alongside the headline; the parity tests cover both paths."""
+    """The other single-GPU configurations, device resident, each with the roofline of ITS dominant kernel:
+      C5 3D Q2 Laplace 128^3 and C3 2D SWIPDG DG-Q1 2048^2 (constant coefficients; the launches write the matrix only:
+      algorithmic bytes = 8 nnz), C2 with one kappa value per ELEMENT (the non-specialised Q1 number) and C2 / C5 with one
+      kappa value per QUADRATURE POINT (HBM: 8 nnz written + 8 n_qp read per element; also given against the FP64 peak),
+      and the sort-and-unique pattern build for C2.  The parity tests cover every one of these paths."""
     from dune_gdt_b200 import descriptors as D
 
     lib, check = gdt.capi.lib(), gdt.capi.check
     out = {}
+    fp64_peak = 34.1  # TFLOP/s, measured on this pool's B200 (profiles/r02_fp64_peak.json, tools/microbench/fp64_peak.cu)
 
     def timed(op_h, family, reps):
         for _ in range(3):
@@ -216,28 +247,57 @@ def assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src):
         ms, cnt = kernel_time(gdt, ctx, family)
         return ms / max(cnt, 1)
 
-    def entry(name, elements, rows, nnz, per_ms, plan):
-        alg = 8.0 * nnz + 8.0 * rows
+    def entry(name, elements, rows, nnz, per_ms, plan, family, read_bytes=0.0, flops=None, note=None):
+        alg = 8.0 * nnz + read_bytes  # the launch writes every CSR value once (no vector), reads only the coefficients
         ach = alg / (per_ms * 1e-3) / 1e9
-        out[name] = {"plan": plan, "elements": elements, "rows": rows, "nnz": nnz, "ms_per_assembly": per_ms,
-                     "elements_per_s": elements / (per_ms * 1e-3),
+        out[name] = {"plan": plan, "kernel": kernel_name(gdt, ctx, family), "elements": elements, "rows": rows, "nnz": nnz,
+                     "ms_per_assembly": per_ms, "elements_per_s": elements / (per_ms * 1e-3),
                      "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs,
                                   "algorithmic_bytes_per_launch": alg, "bytes_per_element": alg / elements,
                                   "peak_source": peak_src}}
+        if flops is not None:
+            tf = flops / (per_ms * 1e-3) / 1e12
+            out[name]["fp64"] = {"flops_per_launch": flops, "achieved_tflops": tf, "peak_tflops": fp64_peak,
+                                 "frac": tf / fp64_peak, "peak_source": "measured DFMA loop (profiles/r02_fp64_peak.json)"}
+        if note:
+            out[name]["note"] = note
 
-    # C5: pattern-free CG Q2 operator (every CSR position is a closed form)
-    n = 128
-    grid = gdt.make_cube_grid(ctx, -1.0, 1.0, [n, n, n])
-    space = gdt.make_continuous_lagrange_space(grid, 2)
-    op_h = C.c_void_p()
-    check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(op_h)))
     lap = D.form(D.integrand(D.INT_LAPLACE, diffusion=1.0))
-    check(lib.gdtb_matop_append_element(op_h, C.byref(lap)))
-    per = timed(op_h, "q2_gather", 20)
-    entry("c5_q2_laplace_128^3", n**3, space.mapper.size, int(lib.gdtb_matop_local_nnz(op_h)), per,
-          lib.gdtb_matop_plan(op_h).decode())
-    lib.gdtb_matop_destroy(op_h)
-    del space, grid
+
+    def cg_case(name, n, order, form, family, reps, read_bytes=0.0, flops=None, note=None):
+        grid = gdt.make_cube_grid(ctx, -1.0, 1.0, [n, n, n])
+        space = gdt.make_continuous_lagrange_space(grid, order)
+        op_h = C.c_void_p()
+        check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(op_h)))  # closed-form CSR positions
+        check(lib.gdtb_matop_append_element(op_h, C.byref(form)))
+        per = timed(op_h, family, reps)
+        entry(name, n**3, space.mapper.size, int(lib.gdtb_matop_local_nnz(op_h)), per, lib.gdtb_matop_plan(op_h).decode(),
+              family, read_bytes, flops, note)
+        lib.gdtb_matop_destroy(op_h)
+        del space, grid
+        torch.cuda.empty_cache()
+
+    # C5, constant kappa: the sum-factorised Q2 gather
+    cg_case("c5_q2_laplace_128^3", 128, 2, lap, "q2_gather", 20)
+    # C2 with one kappa value per element: what "assembly" costs when kappa is data (no constant-coefficient identities)
+    kap = torch.rand(256**3, dtype=torch.float64, device="cuda") + 0.5
+    fe = D.Function()
+    fe.kind, fe.data_on_device, fe.data = D.FN_ELEM_SCALAR, 1, C.cast(kap.data_ptr(), C.POINTER(C.c_double))
+    cg_case("c2_q1_laplace_256^3_kappa_per_element", 256, 1, D.form(D.integrand(D.INT_LAPLACE, diffusion=fe)), "q1_gather", 20,
+            read_bytes=8.0 * 256**3)
+    del kap
+    # kappa per quadrature point (declared order 0: 2^3 points for Q1, 3^3 for Q2): the quadrature loop itself, sum-factorised
+    f1 = qp_function(torch, 256**3, 8, 0)
+    cg_case("c2_q1_laplace_256^3_kappa_per_qp", 256, 1, D.form(D.integrand(D.INT_LAPLACE, diffusion=f1)), "q1_gather", 5,
+            read_bytes=8.0 * 8 * 256**3, flops=2.0 * 8 * 3 * 8 * 8 * 256**3,
+            note="flops: dense B^T D B count without symmetry, 2 * n_qp * d * n^2 per element (SURVEY.md 8d)")
+    del f1
+    f2 = qp_function(torch, 128**3, 27, 0)
+    cg_case("c5_q2_laplace_128^3_kappa_per_qp", 128, 2, D.form(D.integrand(D.INT_LAPLACE, diffusion=f2)), "q2_gather", 3,
+            read_bytes=8.0 * 27 * 128**3, flops=2.0 * 27 * 3 * 27 * 27 * 128**3,
+            note="flops: dense B^T D B count, 118 098 per element (SURVEY.md 8d); the kernel executes the sum-factorised "
+                 "form (about 1 300 flops per local-matrix row)")
+    del f2
     torch.cuda.empty_cache()
 
     # C3: SWIPDG as in examples/adaptive_elliptic_swipdg.cc:230-251 / test ESV2007.hh:108-112 on a Yasp grid
@@ -254,92 +314,131 @@ def assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src):
     check(lib.gdtb_matop_append_coupling(op._h, C.byref(inner), D.FILTER_INNER_ONCE))
     check(lib.gdtb_matop_append_boundary(op._h, C.byref(bnd), D.FILTER_ALL_BOUNDARY))
     per = timed(op._h, "dg_gather", 20)
-    entry("c3_swipdg_dg_q1_2048^2", n * n, pat.rows, pat.nnz, per, op.plan)
+    entry("c3_swipdg_dg_q1_2048^2", n * n, pat.rows, pat.nnz, per, op.plan, "dg_gather")
+    del op, pat, space, grid
+    torch.cuda.empty_cache()
+
+    # K1: the sort-and-unique pattern builder on C2 (setup, not part of a step): emit keys, radix sort, unique, row pointer
+    grid = gdt.make_cube_grid(ctx, -1.0, 1.0, [256, 256, 256])
+    space = gdt.make_continuous_lagrange_space(grid, 1)
+    times = {}
+    for label, method in (("sort_unique", D.PATTERN_SORT_UNIQUE), ("closed_form", D.PATTERN_STRUCTURED)):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        pat = gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT, method)
+        ctx.synchronize()
+        times[label] = time.perf_counter() - t0
+        nnz = pat.nnz
+        del pat
+        torch.cuda.empty_cache()
+    out["c2_pattern_build_256^3"] = {"nnz": nnz, "sort_unique_s": times["sort_unique"], "closed_form_s": times["closed_form"],
+                                    "note": "includes allocation; CUB radix sort / select inside the sort-and-unique builder"}
     return out
 
 
-def run_sharded_workload(args):
-    """--workload c5 | c4 | c2-halo: the other multi-GPU rows of SURVEY.md 8e under torchrun (one rank per GPU), device
-    resident, CUDA events, max over ranks.
-      c5      3D Q2 Laplace 128^3 SHARDED across the ranks (BASELINE.json configs[4], strong scaling): z-slabs,
-              owner-computes-rows per sub-entity group, no data-path collective
-      c4      explicit FV upwind Euler steps on 4096^2 periodic, y-slabs, one ghost row per side over NCCL per step
-              (interior overlapped with the exchange), strong scaling
-      c2-halo the headline workload with the interface-row halo partition (own elements only + one NCCL message per
-              slab face + add kernel) instead of the ghost-layer recompute, weak scaling"""
-    import torch
-    import torch.distributed as dist
+class Env:
+    """one process per GPU: torch.distributed (NCCL) plumbing + the library context on a torch stream"""
 
-    import dune_gdt_b200 as gdt
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        import dune_gdt_b200 as gdt
+
+        self.torch, self.dist, self.gdt = torch, dist, gdt
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.ctx = gdt.Context(self.local_rank)
+        # the library launches on the stream bench.py times with torch CUDA events (a non-default torch stream: handle 0
+        # would mean "use the library's own stream")
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        self.ctx.set_stream(self.stream.cuda_stream)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, value):
+        t = self.torch.tensor([value], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def sharded_workload(env, workload, steps, warmup):
+    """The other multi-GPU rows of SURVEY.md 8e (one rank per GPU), device resident, CUDA events, max over ranks; returns
+    the JSON record (every rank computes it, rank 0 prints it).
+      c5           3D Q2 Laplace 128^3 SHARDED across the ranks (BASELINE.json configs[4], strong scaling): z-slabs,
+                   owner-computes-rows per sub-entity group, no data-path collective
+      c4 / c4-weak explicit FV upwind Euler steps on 4096^2 periodic, y-slabs, one ghost row per side over NCCL per step
+                   (interior overlapped with the exchange)
+      c4-p2p / c4-weak-p2p   the same with the ghost rows handed over INSIDE the kernel (NVLink peer stores)
+      c2-halo      the headline workload with the interface-row halo partition (own elements only + one message per
+                   slab face + add) instead of the ghost-layer recompute, weak scaling"""
+    torch, gdt = env.torch, env.gdt
     from dune_gdt_b200 import descriptors as D
     from dune_gdt_b200 import parallel
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib, check = gdt.capi.lib(), gdt.capi.check
-    ctx = gdt.Context(local_rank)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)  # the library launches on the stream the CUDA events are recorded on
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rank, world, ctx = env.rank, env.world, env.ctx
+    warmup = max(warmup, 3)
 
     def timed(step, units, metric, unit, scaling, config):
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(warmup):
             step()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        env.barrier()
         start.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         end.record()
-        barrier()
-        dt = torch.tensor([start.elapsed_time(end) * 1e-3], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            print(json.dumps({"metric": metric, "value": units * args.steps / dt.item(), "unit": unit, "n_gpus": world,
-                              "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt.item() / args.steps,
-                              "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
-                              "data": "synthetic", "config": config}))
+        env.barrier()
+        dt = env.max_over_ranks(start.elapsed_time(end) * 1e-3)
+        return {"workload": workload, "metric": metric, "value": units * steps / dt, "unit": unit, "n_gpus": world,
+                "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config}
 
-    if args.workload == "c5":
+    if workload == "c5":
         n = 128
         grid = gdt.make_cube_grid(ctx, -1.0, 1.0, [n, n, n])
         space = gdt.make_continuous_lagrange_space(grid, 2)
         slab = parallel.SlabAssembly(space, rank, world, with_functional=False)
         slab.append(D.form(D.integrand(D.INT_LAPLACE, diffusion=1.0)))
-
-        timed(slab.assemble_device, n**3, "elements assembled/sec (3D Q2 Laplace, 128^3 sharded, FP64)", UNIT, "strong",
-              {"workload": "3D Q2 Laplace assembly, 128^3 YaspGrid cube sharded across the GPUs (BASELINE.json configs[4])",
-               "partition": f"z-slabs x{world}, owner-computes-rows per sub-entity group, no collective",
-               "nnz_this_rank": slab.nnz_local})
-    elif args.workload in ("c4-p2p", "c4-weak-p2p"):
+        return timed(slab.assemble_device, n**3, "elements assembled/sec (3D Q2 Laplace, 128^3 sharded, FP64)", UNIT, "strong",
+                     {"workload": "3D Q2 Laplace assembly, 128^3 YaspGrid cube sharded across the GPUs (BASELINE.json configs[4])",
+                      "partition": f"z-slabs x{world}, owner-computes-rows per sub-entity group, no collective",
+                      "nnz_this_rank": slab.nnz_local})
+    if workload in ("c4-p2p", "c4-weak-p2p"):
         n = 4096
-        ny = n * world if args.workload == "c4-weak-p2p" else n
+        ny = n * world if workload == "c4-weak-p2p" else n
         grid = gdt.make_cube_grid(ctx, [0.0, 0.0], [1.0, ny / n], [n, ny], periodic=3)
         space = gdt.make_finite_volume_space(grid)
         loop = parallel.PeerMemoryFvTimeLoop(gdt.NumericalUpwindFlux(D.FLUX_LINEAR, [1.0, 0.5]), space, rank, world)
         loop.set_initial_values(np.random.default_rng(20251017).random(n * ny))
-        timed(lambda: loop.euler_steps(0.25 / n, 1), n * ny,
-              "cells updated/sec (explicit FV upwind Euler step, 4096^2 periodic, FP64)", "cells/s",
-              "weak" if args.workload == "c4-weak-p2p" else "strong",
-              {"workload": f"FV linear advection, {n} x {ny} periodic YaspGrid (BASELINE.json configs[3]), fused apply + Euler update",
-               "partition": f"y-slabs x{world}, ghost rows handed over INSIDE the kernel (NVLink peer stores + step counters), "
-                            "one launch per step, no host-launched collective"})
+        rec = timed(lambda: loop.euler_steps(0.25 / n, 1), n * ny,
+                    "cells updated/sec (explicit FV upwind Euler step, 4096^2 periodic, FP64)", "cells/s",
+                    "weak" if workload == "c4-weak-p2p" else "strong",
+                    {"workload": f"FV linear advection, {n} x {ny} periodic YaspGrid (BASELINE.json configs[3]), fused apply + Euler update",
+                     "partition": f"y-slabs x{world}, ghost rows handed over INSIDE the kernel (NVLink peer stores + step counters), "
+                                  "one launch per step, no host-launched collective"})
         loop.check()
         loop.close()
-    elif args.workload in ("c4", "c4-weak"):
+        return rec
+    if workload in ("c4", "c4-weak"):
         n = 4096
-        ny = n * world if args.workload == "c4-weak" else n
+        ny = n * world if workload == "c4-weak" else n
         grid = gdt.make_cube_grid(ctx, [0.0, 0.0], [1.0, ny / n], [n, ny], periodic=3)
         space = gdt.make_finite_volume_space(grid)
         L = parallel.make_distributed_advection_fv_operator(gdt.NumericalUpwindFlux(D.FLUX_LINEAR, [1.0, 0.5]), space, rank, world)
@@ -351,11 +450,11 @@ def run_sharded_workload(args):
             L.euler_step(state[0], state[1], 0.25 / n)
             state.reverse()
 
-        timed(step, n * ny, "cells updated/sec (explicit FV upwind Euler step, 4096^2 periodic, FP64)", "cells/s",
-              "weak" if args.workload == "c4-weak" else "strong",
-              {"workload": f"FV linear advection, {n} x {ny} periodic YaspGrid (BASELINE.json configs[3]), fused apply + Euler update",
-               "partition": f"y-slabs x{world}, one ghost row per side per step over NCCL send/recv, interior overlapped"})
-    else:
+        return timed(step, n * ny, "cells updated/sec (explicit FV upwind Euler step, 4096^2 periodic, FP64)", "cells/s",
+                     "weak" if workload == "c4-weak" else "strong",
+                     {"workload": f"FV linear advection, {n} x {ny} periodic YaspGrid (BASELINE.json configs[3]), fused apply + Euler update",
+                      "partition": f"y-slabs x{world}, one ghost row per side per step over NCCL send/recv, interior overlapped"})
+    if workload == "c2-halo":
         h = 2.0 / NX
         grid = gdt.make_cube_grid(ctx, [-1.0, -1.0, -1.0], [1.0, 1.0, -1.0 + NX * world * h], [NX, NX, NX * world])
         space = gdt.make_continuous_lagrange_space(grid, 1)
@@ -363,37 +462,113 @@ def run_sharded_workload(args):
         lap, rhs = forms()
         halo.append(lap)
         halo.append_rhs(rhs)
-        timed(halo.assemble_device, NX**3 * world, METRIC, UNIT, "weak",
-              {"workload": "3D Q1 Laplace + RHS assembly, 256^3 per GPU (BASELINE.json configs[1])",
-               "partition": f"z-slabs x{world}, own elements only + interface-row halo over NCCL (one layer of rows per slab face)",
-               "halo_bytes_per_face": 8 * (halo.mat_layout[2] + halo.vec_layout[2])})
-    if world > 1:
-        dist.destroy_process_group()
+        return timed(halo.assemble_device, NX**3 * world, METRIC, UNIT, "weak",
+                     {"workload": "3D Q1 Laplace + RHS assembly, 256^3 per GPU (BASELINE.json configs[1])",
+                      "partition": f"z-slabs x{world}, own elements only + interface-row halo (one layer of rows per slab face)",
+                      "halo_bytes_per_face": 8 * (halo.mat_layout[2] + halo.vec_layout[2])})
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def run_sharded_workload(args):
+    env = Env()
+    rec = sharded_workload(env, args.workload, args.steps, args.warmup)
+    if env.rank == 0:
+        print(json.dumps(rec))
+    env.close()
+
+
+def neighbour_self_check(env, op_h, fun_h, space, rows_local, nnz_local):
+    """N > 1: every rank ALSO assembles the first vertex layer of the slab above it (from its own top element layer as the
+    ghost layer below) and sends it up; the owner compares it with its own first layer, which it produced from ITS ghost
+    layer: both are complete rows of the same global matrix / vector, so they must be bit-identical.  Returns the number
+    of differing entries over all ranks (0 = the partition is consistent)."""
+    torch, dist, gdt = env.torch, env.dist, env.gdt
+    from dune_gdt_b200 import descriptors as D
+
+    lib, check = gdt.capi.lib(), gdt.capi.check
+    rank, world, ctx = env.rank, env.world, env.ctx
+    layer_rows = (NX + 1) ** 2
+    layer_nnz = 3 * (3 * NX + 1) ** 2  # an interior vertex layer: 3 z-planes of (3 N + 1)^2 entries
+    bad = 0
+    probe_v = probe_b = None
+    if rank + 1 < world:
+        ph, pf = C.c_void_p(), C.c_void_p()
+        check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(ph)))
+        check(lib.gdtb_vecfun_create(ctx._h, space._h, C.byref(pf)))
+        lo = (rank + 1) * NX
+        check(lib.gdtb_matop_set_slab(ph, lo, lo + 1))
+        check(lib.gdtb_vecfun_set_slab(pf, lo, lo + 1))
+        lap, rhs = forms()
+        check(lib.gdtb_matop_append_element(ph, C.byref(lap)))
+        check(lib.gdtb_vecfun_append_element(pf, C.byref(rhs)))
+        check(lib.gdtb_assemble(ph, pf, D.ASSEMBLE_OVERWRITE))
+        assert lib.gdtb_matop_local_nnz(ph) == layer_nnz
+        pv, pb = C.c_void_p(), C.c_void_p()
+        check(lib.gdtb_matop_values_device(ph, C.byref(pv)))
+        check(lib.gdtb_vecfun_device(pf, C.byref(pb)))
+        probe_v = as_tensor(torch, pv.value, layer_nnz).clone()
+        probe_b = as_tensor(torch, pb.value, layer_rows).clone()
+        lib.gdtb_matop_destroy(ph)
+        lib.gdtb_vecfun_destroy(pf)
+    ops = []
+    recv_v = recv_b = None
+    if rank + 1 < world:
+        ops += [dist.P2POp(dist.isend, probe_v, rank + 1), dist.P2POp(dist.isend, probe_b, rank + 1)]
+    if rank > 0:
+        recv_v = torch.empty(layer_nnz, dtype=torch.float64, device="cuda")
+        recv_b = torch.empty(layer_rows, dtype=torch.float64, device="cuda")
+        ops += [dist.P2POp(dist.irecv, recv_v, rank - 1), dist.P2POp(dist.irecv, recv_b, rank - 1)]
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    if rank > 0:
+        pv, pb = C.c_void_p(), C.c_void_p()
+        check(lib.gdtb_matop_values_device(op_h, C.byref(pv)))
+        check(lib.gdtb_vecfun_device(fun_h, C.byref(pb)))
+        mine_v = as_tensor(torch, pv.value, nnz_local)[:layer_nnz]
+        mine_b = as_tensor(torch, pb.value, rows_local)[:layer_rows]
+        torch.cuda.synchronize()
+        bad = int((mine_v != recv_v).sum().item() + (mine_b != recv_b).sum().item())
+    t = torch.tensor([bad], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
+
+
+def as_tensor(torch, ptr, n):
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    return torch.as_tensor(_Arr(), device="cuda")
+
+
+def oracle_checksum(threads):
+    """the first 1024 CSR values + the first 1024 right-hand-side entries of the C2 system from the CPU oracle: the
+    values belong to vertices of the line iy = iz = 0, the right-hand-side entries to the vertex lines iy <= 3 of the
+    plane iz = 0 -- they only see the elements ey <= 3, ez = 0, so a 256 x 5 x 2 sub-grid with the same h (and the same
+    257 vertices per line) reproduces them exactly, row for row"""
+    import oracle
+    from dune_gdt_b200 import descriptors as D
+
+    h = 2.0 / NX
+    g = D.grid_desc([-1.0, -1.0, -1.0], [1.0, -1.0 + 5 * h, -1.0 + 2 * h], [NX, 5, 2])
+    rp, ci = oracle.pattern(g, (D.SPACE_CG, 1))
+    lap, rhs = forms()
+    v, b = oracle.assemble(g, D.SPACE_CG, 1, rp, ci, [lap], rhs_forms=[rhs], num_threads=threads)
+    # rows of the vertices (ix, 0, 0): 8 entries at the two ends, 12 inside -- identical in the full grid
+    n_rows = int(np.searchsorted(rp, 1024, side="right"))
+    assert n_rows <= NX + 1
+    return float(v[:1024].sum() + b[:1024].sum()), v[:1024], b[:1024]
 
 
 def run_product(args):
-    import torch
-    import torch.distributed as dist
-
-    import dune_gdt_b200 as gdt
+    env = Env()
+    torch, dist, gdt = env.torch, env.dist, env.gdt
     from dune_gdt_b200 import descriptors as D
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world, local_rank, ctx = env.rank, env.world, env.local_rank, env.ctx
     lib = gdt.capi.lib()
     check = gdt.capi.check
-    ctx = gdt.Context(local_rank)
-    # the library launches on the stream bench.py times with torch CUDA events (a non-default torch stream: handle 0
-    # would mean "use the library's own stream")
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
+    barrier = env.barrier
 
     # global grid: 256 x 256 x (256 * world), h = 2/256 everywhere; this rank owns element layers [rank*256, (rank+1)*256)
     h = 2.0 / NX
@@ -413,12 +588,6 @@ def run_product(args):
     check(lib.gdtb_matop_local_rows(op_h, C.byref(rb), C.byref(re_), C.byref(vo)))
     rows_local = re_.value - rb.value
     elements_local = NX**3
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- device-resident throughput -----------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -441,10 +610,7 @@ def run_product(args):
     launches = ctx.launch_count - launches0
     kern_ms, kern_n = kernel_time(gdt, ctx, "q1_gather")
     check(lib.gdtb_ctx_enable_timing(ctx._h, 0))
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = t.item()
+    ms_total = env.max_over_ranks(ms_total)
     value = elements_local * world * args.steps / (ms_total * 1e-3)
     clocks = None
     if sampler:
@@ -464,17 +630,29 @@ def run_product(args):
     alg_bytes = 8.0 * nnz_local + 8.0 * rows_local  # every CSR value and RHS entry written once, no array inputs
     per_launch_ms = kern_ms / max(kern_n, 1)
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "q1_gather_traffic.json")
-    if os.path.exists(prof):
-        with open(prof) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+    traffic, traffic_src = None, None
+    for name in ("r02_q1_gather_traffic.json", "q1_gather_traffic.json"):
+        prof = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(prof):
+            with open(prof) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic_src = f"profiles/{name} (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one launch)"
+            break
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                "traffic": traffic, "kernel": "k_q1_gather<3,false>", "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name(gdt, ctx, "q1_gather"),
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_element": alg_bytes / elements_local, "ms_per_launch": per_launch_ms,
                 "peak_source": peak_src,
                 "note": "the kernel only writes (no array inputs): the copy-derived peak (half reads, half writes) is "
                         "not an upper bound for it; a pure fill reaches about 7.4 TB/s on this box (tools/copy_bandwidth.py)"}
+
+    # ---- N > 1: the partition is consistent across the ranks (bit-identical interface rows) ------------------
+    self_check = None
+    if world > 1:
+        differing = neighbour_self_check(env, op_h, fun_h, space, rows_local, nnz_local)
+        self_check = {"interface_layers_compared": world - 1, "differing_entries": differing, "ok": differing == 0,
+                      "what": "every rank re-assembles the first vertex layer of the slab above it and the owner compares "
+                              "it bit for bit with its own (matrix rows + right-hand side)"}
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
     e2e_steps = max(1, min(args.steps, 5))
@@ -498,27 +676,29 @@ def run_product(args):
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - te
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
+    e2e_s = env.max_over_ranks(time.perf_counter() - te)
     e2e_value = elements_local * world * e2e_steps / e2e_s
     checksum = float(values_host[:1024].sum() + rhs_host[:1024].sum())
+    head_values = values_host[:1024].numpy().copy()
+    head_rhs = rhs_host[:1024].numpy().copy()
+    d2h = 8 * (nnz_local + rows_local)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * C.sizeof(D.Form),
-           "d2h_bytes_per_step": 8 * (nnz_local + rows_local), "steps": e2e_steps,
-           "ms_per_step": 1e3 * e2e_s / e2e_steps, "result_checksum": checksum}
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "ms_per_step": 1e3 * e2e_s / e2e_steps, "result_checksum": checksum,
+           "d2h_gb_per_s_per_rank": d2h / (e2e_s / e2e_steps) / 1e9,
+           "note": "bound by the device-to-host copy of the 3.77 GB result per rank into pinned host memory (the assembly "
+                   "itself is 0.6 ms of the step); with N ranks on one host the copies share the host's memory / PCIe "
+                   "root bandwidth"}
+    del values_host, rhs_host
+    lib.gdtb_matop_destroy(op_h)
+    lib.gdtb_vecfun_destroy(fun_h)
+    torch.cuda.empty_cache()
 
     extra = None
     cpu = None
-    if rank == 0 and world == 1:
+    if world == 1:
         check(lib.gdtb_ctx_enable_timing(ctx._h, 1))
         extra = {"fv_apply_4096x4096_upwind": fv_extra(gdt, ctx, torch, hbm_gbs, peak_src)}
-        del values_host, rhs_host
-        lib.gdtb_matop_destroy(op_h)
-        lib.gdtb_vecfun_destroy(fun_h)
-        op_h = fun_h = None
-        torch.cuda.empty_cache()
         extra.update(assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src))
         check(lib.gdtb_ctx_enable_timing(ctx._h, 0))
         if not args.no_cpu_baseline:
@@ -526,15 +706,27 @@ def run_product(args):
 
             oracle.build()
             threads = os.cpu_count() or 1
+            # the oracle as the CHECKER of what the timed steps produced: first 1024 values + first 1024 rhs entries
+            ref_sum, ref_v, ref_b = oracle_checksum(threads)
+            scale = max(float(np.abs(ref_v).max()), float(np.abs(ref_b).max()))
+            err = max(float(np.abs(head_values - ref_v).max()), float(np.abs(head_rhs - ref_b).max())) / scale
+            e2e["result_checksum_check"] = {"oracle_checksum": ref_sum, "max_rel_err_first_1024": err, "ok": err <= 1e-12}
             side = cpu_sample_side(threads, budget_s=8.0)
             rate, dt = cpu_assemble_rate(side, threads, repeats=2)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{side}^3 elements of the 256^3 grid (same h and forms), best of 2 walks of {dt:.2f} s, "
                              f"oracle port with {threads} threads + row-striped locks, pattern build untimed"}
+    else:
+        # the multi-GPU rows that DO communicate, so that the scaling record carries them next to the headline
+        extra = {"multi_gpu": {}}
+        sub_steps = max(10, min(args.steps, 50))
+        for wl in ("c5", "c2-halo", "c4-weak-p2p", "c4-weak"):
+            try:
+                extra["multi_gpu"][wl] = sharded_workload(env, wl, sub_steps, args.warmup)
+            except Exception as exc:  # a failed side workload must not take the headline line with it
+                extra["multi_gpu"][wl] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
 
-    if op_h is not None:
-        lib.gdtb_matop_destroy(op_h)
-        lib.gdtb_vecfun_destroy(fun_h)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -549,11 +741,12 @@ def run_product(args):
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        if self_check:
+            line["self_check"] = self_check
         if extra:
             line["extra"] = extra
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    env.close()
 
 
 def main():

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "gdtb_ctx_destroy": (C.c_int, [_P]),
     "gdtb_ctx_set_stream": (C.c_int, [_P, _P]),
     "gdtb_ctx_synchronize": (C.c_int, [_P]),
+    "gdtb_ctx_kernel_name": (C.c_char_p, [_P, C.c_char_p]),
     "gdtb_ctx_launch_count": (C.c_int64, [_P]),
     "gdtb_ctx_enable_timing": (C.c_int, [_P, C.c_int]),
     "gdtb_ctx_kernel_time": (C.c_int, [_P, C.c_char_p, _DP, _I64P]),
@@ -181,6 +182,7 @@ PROTOTYPES = {
     "gdtb_matop_apply_inverse_host": (C.c_int, [_P, _DP, _DP, C.POINTER(SolverOpts), C.POINTER(SolverInfo)]),
     "gdtb_csr_apply_inverse_device": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(SolverOpts), C.POINTER(SolverInfo)]),
     "gdtb_matop_pattern_device": (C.c_int, [_P, _PP, _PP]),
+    "gdtb_bilinear_form_quadrature_order": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Form), _I32P]),
     "gdtb_bilinear_form_apply2": (C.c_int, [_P, _P, _P, C.POINTER(Function), C.POINTER(Form), _DP]),
     "gdtb_bilinear_form_apply2_host": (C.c_int, [_P, _P, _DP, C.POINTER(Function), C.POINTER(Form), _DP]),
     "gdtb_lagrange_interpolate": (C.c_int, [_P, _P, C.POINTER(Function), _P]),

@@ -242,6 +242,7 @@ int launch_dg_gather_dk(Launch& L, const DgGatherParams& p, double* values, bool
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)
     grid = nitems;
+  note_kernel(L, KF_DG_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_DG_GATHER);
   kern<<<(unsigned)grid, DGG_THREADS, smem, L.stream>>>(p, values, stage_doubles);
   time_end(L, KF_DG_GATHER);
@@ -790,6 +791,7 @@ int launch_dg_gather_fast(Launch& L, DgGatherParams& p, double* values, bool acc
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)
     grid = nitems;
+  note_kernel(L, KF_DG_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_DG_GATHER);
   kern<<<(unsigned)grid, DGG_THREADS, smem, L.stream>>>(p, values, stage_doubles, nbuf);
   time_end(L, KF_DG_GATHER);

@@ -649,6 +649,7 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)
     grid = nitems;
+  note_kernel(L, KF_Q1_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_Q1_GATHER);
   kern<<<(unsigned)grid, Q1G_ROWS, smem, L.stream>>>(p, values, rhs, nrows, (int)nitems, stage_doubles, nbuf);
   time_end(L, KF_Q1_GATHER);
@@ -1007,6 +1008,7 @@ int launch_q1_qp_dmk(Launch& L, const Q1QpParams& p, double* values, bool accumu
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "q1_gather_qp: kernel does not fit on an SM");
   long long grid = std::min<long long>((long long)per_sm * L.sm_count, nitems);
+  note_kernel(L, KF_Q1_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_Q1_GATHER);
   kern<<<(unsigned)grid, Q1G_ROWS, smem, L.stream>>>(p, values, nrows, (int)nitems, stage_doubles, nbuf);
   time_end(L, KF_Q1_GATHER);

@@ -1037,6 +1037,7 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > p.n_items)
     grid = p.n_items;
+  note_kernel(L, KF_Q2_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_Q2_GATHER);
   if (p.sf) {
     const long long work = p.sf_group_stride / 10 * p.n_groups;

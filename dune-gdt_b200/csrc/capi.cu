@@ -166,6 +166,7 @@ long long function_data_size(const gdtb_function& f, const GridDev& g)
     case GDTB_FN_ELEM_TENSOR: return g.ne * g.d * g.d;
     case GDTB_FN_QP_SCALAR: return g.ne * f.qp_per_element;
     case GDTB_FN_QP_TENSOR: return g.ne * f.qp_per_element * g.d * g.d;
+    case GDTB_FN_QP_VALUE_GRAD: return g.ne * f.qp_per_element * (1 + g.d);
     case GDTB_FN_DOF_VECTOR: {
       SpaceDev sp;
       return make_space_dev(g, f.space_kind, f.space_order, sp) == GDTB_OK ? sp.size : 0;
@@ -177,18 +178,18 @@ long long function_data_size(const gdtb_function& f, const GridDev& g)
 bool fn_has_data(const gdtb_function& f)
 {
   return f.kind == GDTB_FN_ELEM_SCALAR || f.kind == GDTB_FN_ELEM_TENSOR || f.kind == GDTB_FN_QP_SCALAR
-         || f.kind == GDTB_FN_QP_TENSOR || f.kind == GDTB_FN_DOF_VECTOR;
+         || f.kind == GDTB_FN_QP_TENSOR || f.kind == GDTB_FN_DOF_VECTOR || f.kind == GDTB_FN_QP_VALUE_GRAD;
 }
 
 int validate_function(const gdtb_function& f, const char* what)
 {
-  if (f.kind < GDTB_FN_CONST_SCALAR || f.kind > GDTB_FN_DOF_VECTOR)
+  if (f.kind < GDTB_FN_CONST_SCALAR || f.kind > GDTB_FN_QP_VALUE_GRAD)
     return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": unknown function kind");
   if (f.kind == GDTB_FN_BUILTIN && (f.builtin < GDTB_BUILTIN_COS_PRODUCT || f.builtin > GDTB_BUILTIN_QUADRATIC))
     return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": unknown built-in function id");
   if (fn_has_data(f) && !f.data)
     return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": array-backed function without data");
-  if ((f.kind == GDTB_FN_QP_SCALAR || f.kind == GDTB_FN_QP_TENSOR) && f.qp_per_element < 1)
+  if ((f.kind == GDTB_FN_QP_SCALAR || f.kind == GDTB_FN_QP_TENSOR || f.kind == GDTB_FN_QP_VALUE_GRAD) && f.qp_per_element < 1)
     return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": per-quadrature-point function needs qp_per_element >= 1");
   if (f.order < 0)
     return fail(GDTB_ERR_INVALID_ARGUMENT, std::string(what) + ": negative polynomial order");
@@ -239,6 +240,8 @@ int lower_form(gdtb_ctx* ctx, const GridDev& g, const gdtb_form* form, int filte
   for (int t = 0; t < form->n_terms; ++t) {
     GDTB_TRY(validate_function(out.form.terms[t].diffusion, "integrand.diffusion"));
     GDTB_TRY(validate_function(out.form.terms[t].weight, "integrand.weight"));
+    if (out.form.terms[t].diffusion.kind == GDTB_FN_QP_VALUE_GRAD || out.form.terms[t].weight.kind == GDTB_FN_QP_VALUE_GRAD)
+      return fail(GDTB_ERR_INVALID_ARGUMENT, "GDTB_FN_QP_VALUE_GRAD is the `f` of gdtb_bilinear_form_apply2, not a coefficient");
     int st = lower_function(ctx, g, out.form.terms[t].diffusion, out);
     if (st == GDTB_OK)
       st = lower_function(ctx, g, out.form.terms[t].weight, out);
@@ -881,6 +884,19 @@ int gdtb_ctx_kernel_time(gdtb_ctx* ctx, const char* family, double* total_ms, in
   if (launches)
     *launches = (int64_t)n;
   return GDTB_OK;
+}
+
+static const char* const kFamilyNames[KF_COUNT] = {"q1_gather",      "q2_gather",      "dg_gather",       "fv_apply",
+                                                   "element_matrix", "element_vector", "coupling_matrix", "boundary_matrix"};
+
+const char* gdtb_ctx_kernel_name(const gdtb_ctx* ctx, const char* family)
+{
+  if (!ctx || !family)
+    return "";
+  for (int i = 0; i < KF_COUNT; ++i)
+    if (std::strcmp(family, kFamilyNames[i]) == 0)
+      return ctx->timing.last_kernel[i].c_str();
+  return "";
 }
 
 int64_t gdtb_ctx_launch_count(const gdtb_ctx* ctx)

@@ -1,6 +1,7 @@
 // dune-gdt_b200/csrc/kernels.hpp -- host-callable launchers of the CUDA kernels (internal).
 #pragma once
 
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -25,6 +26,8 @@ struct Timing
 {
   bool enabled = false;
   std::vector<cudaEvent_t> start[KF_COUNT], stop[KF_COUNT];
+  // (mangled) symbol of the kernel instantiation each family launched last (gdtb_ctx_kernel_name)
+  std::string last_kernel[KF_COUNT];
 };
 
 struct Launch
@@ -43,6 +46,16 @@ inline void time_begin(Launch& L, int family)
     cudaEventCreate(&e);
     cudaEventRecord(e, L.stream);
     L.timing->start[family].push_back(e);
+  }
+}
+
+// remembers which instantiation a family launched (cudaFuncGetName: the symbol as it appears in ncu launch lists)
+inline void note_kernel(Launch& L, int family, const void* kernel)
+{
+  if (L.timing) {
+    const char* name = nullptr;
+    if (cudaFuncGetName(&name, kernel) == cudaSuccess && name)
+      L.timing->last_kernel[family] = name;
   }
 }
 

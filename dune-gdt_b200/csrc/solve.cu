@@ -457,7 +457,13 @@ __global__ void __launch_bounds__(RED_BLOCK)
           }
           if (P.has_f) {
             double fg[3] = {0., 0., 0.};
-            val -= fn_scalar(P.f, D, e, x);
+            if (P.f.kind == GDTB_FN_QP_VALUE_GRAD) {
+              const double* src = P.f.data + (e * (long long)(m * my * mz) + (qx + m * (qy + my * qz))) * (1 + D);
+              val -= __ldg(src);
+              for (int k = 0; k < D; ++k)
+                fg[k] = __ldg(src + 1 + k);
+            } else
+              val -= fn_scalar(P.f, D, e, x);
             if (P.f.kind == GDTB_FN_BUILTIN)
               builtin_grad(P.f, D, x, fg);
             for (int k = 0; k < 3; ++k)
@@ -1091,9 +1097,9 @@ int gdtb_bilinear_form_apply2(gdtb_ctx* ctx, const gdtb_space* space, const doub
     return fail(GDTB_ERR_INVALID_ARGUMENT, "form: n_terms must be in [1, GDTB_MAX_TERMS]");
   if (f) {
     GDTB_TRY(internal_validate_function(*f, "apply2: f"));
-    if (f->kind > GDTB_FN_BUILTIN)
-      return fail(GDTB_ERR_NOT_IMPLEMENTED, "apply2: f must be a constant, per-element or analytic function (a discrete "
-                                            "function enters through the DoF vector argument)");
+    if (f->kind > GDTB_FN_BUILTIN && f->kind != GDTB_FN_QP_VALUE_GRAD)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "apply2: f must be a constant, per-element, analytic or value-and-gradient "
+                                            "sampled function (a discrete function enters through the DoF vector)");
     if (f->kind == GDTB_FN_CONST_TENSOR || f->kind == GDTB_FN_ELEM_TENSOR)
       return fail(GDTB_ERR_INVALID_ARGUMENT, "apply2: f must be scalar");
   }
@@ -1138,6 +1144,9 @@ int gdtb_bilinear_form_apply2(gdtb_ctx* ctx, const gdtb_space* space, const doub
     F.m = gauss_points_for_order(order + fm.over_integrate);
     if (F.m > MAX_Q1D)
       status = fail(GDTB_ERR_NOT_IMPLEMENTED, "quadrature order too high (more than 8 Gauss points per direction)");
+    else if (f && f->kind == GDTB_FN_QP_VALUE_GRAD && f->qp_per_element != ipow(F.m, g.d))
+      status = fail(GDTB_ERR_SHAPES_DO_NOT_MATCH,
+                    "apply2: f was not sampled for the rule of this form (gdtb_bilinear_form_quadrature_order)");
   }
   DeviceBuffer dP, partial, res;
   const int nb = (int)std::min<long long>(std::max<long long>((g.ne + RED_BLOCK - 1) / RED_BLOCK, 1),
@@ -1165,6 +1174,21 @@ int gdtb_bilinear_form_apply2(gdtb_ctx* ctx, const gdtb_space* space, const doub
   }
   free_form(owner);
   return status;
+}
+
+int gdtb_bilinear_form_quadrature_order(const gdtb_space* space, int has_dofs, int f_order, const gdtb_form* form,
+                                        int32_t* order)
+{
+  if (!space || !form || !order)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_bilinear_form_quadrature_order: NULL argument");
+  if (form->n_terms < 1 || form->n_terms > GDTB_MAX_TERMS)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "form: n_terms must be in [1, GDTB_MAX_TERMS]");
+  const int e_order = std::max(has_dofs ? space->dev.K : 0, std::max(f_order, 0));
+  int o = 0;
+  for (int t = 0; t < form->n_terms; ++t)
+    o = std::max(o, form->terms[t].diffusion.order + e_order + e_order);
+  *order = o + form->over_integrate;
+  return GDTB_OK;
 }
 
 int gdtb_bilinear_form_apply2_host(gdtb_ctx* ctx, const gdtb_space* space, const double* dofs, const gdtb_function* f,

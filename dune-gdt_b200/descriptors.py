@@ -11,7 +11,7 @@ import numpy as np
 SPACE_CG, SPACE_DG, SPACE_FV = 0, 1, 2
 STENCIL_ELEMENT, STENCIL_INTERSECTION, STENCIL_ELEMENT_AND_INTERSECTION = 0, 1, 2
 FN_CONST_SCALAR, FN_CONST_TENSOR, FN_ELEM_SCALAR, FN_ELEM_TENSOR, FN_BUILTIN = 0, 1, 2, 3, 4
-FN_QP_SCALAR, FN_QP_TENSOR, FN_DOF_VECTOR = 5, 6, 7
+FN_QP_SCALAR, FN_QP_TENSOR, FN_DOF_VECTOR, FN_QP_VALUE_GRAD = 5, 6, 7, 8
 ROLE_ELEMENT, ROLE_FUNCTIONAL, ROLE_COUPLING, ROLE_BOUNDARY = 0, 1, 2, 3
 BUILTIN_COS_PRODUCT, BUILTIN_AFFINE, BUILTIN_GAUSSIAN, BUILTIN_INDICATOR, BUILTIN_QUADRATIC = 1, 2, 3, 4, 5
 INT_LAPLACE, INT_PRODUCT = 0, 1

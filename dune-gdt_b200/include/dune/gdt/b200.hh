@@ -10,8 +10,12 @@
 // LA containers, walker, ApplyOn filters) are provided as thin stand-ins in namespace Dune::XT -- they are
 // [EXT] to dune-gdt and only cover what the hot path needs.
 //
-// What cannot cross a C ABI: user lambdas.  XT::Functions::GridFunction therefore wraps constants, per-element
-// arrays and the built-in analytic functions of gdtb.h instead of GenericFunction lambdas.
+// What cannot cross a C ABI as code: user lambdas.  XT::Functions::GenericFunction keeps the lambda on the host; when a
+// local form that uses it is appended to an operator / functional, the facade asks the library for the rule the
+// reference would integrate that form with (gdtb_form_quadrature_order, gdtb_gauss_rule), evaluates the lambda at
+// every quadrature point of every element -- exactly the calls the reference's integrand makes -- and hands the
+// samples over as GDTB_FN_QP_* arrays.  Constants, per-element arrays and the built-in analytic functions of gdtb.h
+// need no sampling.
 #ifndef DUNE_GDT_B200_HH
 #define DUNE_GDT_B200_HH
 
@@ -79,6 +83,11 @@ struct Parameter
 {
   Parameter() = default;
   Parameter(std::initializer_list<std::pair<std::string, std::vector<double>>>) {}
+};
+struct ParameterType
+{
+  ParameterType() = default;
+  ParameterType(std::initializer_list<std::pair<std::string, std::size_t>>) {}
 };
 } // namespace Common
 } // namespace XT
@@ -371,12 +380,98 @@ struct CustomBoundaryIntersections : IntersectionFilter<GV>
 
 namespace Functions {
 
+namespace internal {
+// a host-side function of the global coordinate: what is left of a GenericFunction lambda after type erasure
+struct Generic
+{
+  int order = 0;
+  int comps = 1; // 1: scalar, d * d: matrix-valued (row-major)
+  std::function<void(const double* x, double* out)> evaluate;
+  std::function<void(const double* x, double* grad)> jacobian; // scalar functions only; may be empty
+};
+} // namespace internal
+
+// XT::Functions::GenericFunction<d, r, rC> [EXT dune-xt functions/generic/function.hh]: order + evaluate lambda
+// (+ name, parameter type, jacobian lambda), examples/stationary-heat-equation.cc:67-85.  Scalar (r = rC = 1) and
+// matrix-valued (r = rC = d) functions.
+template <std::size_t d, std::size_t r = 1, std::size_t rC = 1, class R = double>
+class GenericFunction
+{
+public:
+  using DomainType = FieldVector<double, int(d)>;
+  using RangeReturnType = typename std::conditional<r == 1 && rC == 1, double, FieldMatrix<double, int(r), int(rC)>>::type;
+  using DerivativeRangeReturnType = FieldMatrix<double, int(r), int(d)>;
+  using EvaluateType = std::function<RangeReturnType(const DomainType&, const Common::Parameter&)>;
+  using JacobianType = std::function<DerivativeRangeReturnType(const DomainType&, const Common::Parameter&)>;
+
+  GenericFunction(const int ord, EvaluateType evaluate, const std::string& /*name*/ = "GenericFunction",
+                  const Common::ParameterType& /*param_type*/ = {}, JacobianType jacobian = nullptr)
+    : generic_(std::make_shared<internal::Generic>())
+  {
+    static_assert((r == 1 && rC == 1) || (r == d && rC == d), "scalar or d x d matrix-valued functions");
+    generic_->order = ord;
+    generic_->comps = int(r * rC);
+    generic_->evaluate = [evaluate](const double* x, double* out) {
+      DomainType xx;
+      for (std::size_t k = 0; k < d; ++k)
+        xx[k] = x[k];
+      store(evaluate(xx, Common::Parameter()), out);
+    };
+    if (jacobian)
+      generic_->jacobian = [jacobian](const double* x, double* grad) {
+        DomainType xx;
+        for (std::size_t k = 0; k < d; ++k)
+          xx[k] = x[k];
+        const auto J = jacobian(xx, Common::Parameter());
+        for (std::size_t k = 0; k < d; ++k)
+          grad[k] = J[0][k];
+      };
+  }
+  int order() const
+  {
+    return generic_->order;
+  }
+  const std::shared_ptr<internal::Generic>& generic() const
+  {
+    return generic_;
+  }
+
+private:
+  static void store(const double v, double* out)
+  {
+    out[0] = v;
+  }
+  static void store(const FieldMatrix<double, int(r), int(rC)>& v, double* out)
+  {
+    for (std::size_t i = 0; i < r; ++i)
+      for (std::size_t j = 0; j < rC; ++j)
+        out[i * rC + j] = v[i][j];
+  }
+  std::shared_ptr<internal::Generic> generic_;
+};
+
 // XT::Functions::GridFunction<E, r, rC>: a constant (scalar -> c * I for r = rC = d, laplace.hh:41), a constant
-// matrix, a per-element array, or a built-in analytic function.  Cloned by value.
+// matrix, a per-element array, a built-in analytic function, or a GenericFunction (sampled when the local form it is
+// used in is appended).  Cloned by value.
 template <class E, std::size_t r = 1, std::size_t rC = 1, class R = double>
 class GridFunction
 {
 public:
+  // a GenericFunction lambda: scalar, or matrix-valued; a scalar lambda used as a d x d function means c(x) * I
+  template <std::size_t fr, std::size_t frC>
+  GridFunction(const GenericFunction<E::dimension, fr, frC>& function)
+    : generic_(function.generic())
+  {
+    static_assert((fr == 1 && frC == 1) || (fr == r && frC == rC), "function shape does not match");
+    fn_.kind = GDTB_FN_CONST_SCALAR; // placeholder: replaced by the samples at append time
+    fn_.order = function.order();
+    fn_.c[0] = 1.;
+  }
+  const std::shared_ptr<internal::Generic>& generic() const
+  {
+    return generic_;
+  }
+
   GridFunction(const double value = 1., const int order = 0)
   {
     fn_.kind = GDTB_FN_CONST_SCALAR;
@@ -406,6 +501,7 @@ public:
 private:
   gdtb_function fn_{};
   std::shared_ptr<std::vector<double>> storage_;
+  std::shared_ptr<internal::Generic> generic_;
 };
 
 // element-wise constant data (e.g. a heterogeneous diffusion field), values[e] for element index e
@@ -878,9 +974,12 @@ XT::LA::SparsityPatternDefault make_element_and_intersection_sparsity_pattern(co
 
 // ---- integrands (local/integrands/*.hh) -----------------------------------------------------------------------
 namespace internal {
+using GenericPtr = std::shared_ptr<XT::Functions::internal::Generic>;
 struct IntegrandTerms
 {
   std::vector<gdtb_integrand> terms;
+  // GenericFunction lambdas behind terms[i].diffusion / terms[i].weight (null: the descriptor is complete)
+  std::vector<std::pair<GenericPtr, GenericPtr>> generic;
   // keep per-element storage of the wrapped grid functions alive until the form has been appended (= cloned)
   std::vector<std::shared_ptr<void>> keep;
 };
@@ -888,9 +987,18 @@ inline IntegrandTerms concat(const IntegrandTerms& a, const IntegrandTerms& b)
 {
   IntegrandTerms out = a;
   out.terms.insert(out.terms.end(), b.terms.begin(), b.terms.end());
+  out.generic.insert(out.generic.end(), b.generic.begin(), b.generic.end());
   out.keep.insert(out.keep.end(), b.keep.begin(), b.keep.end());
   return out;
 }
+template <class F>
+GenericPtr generic_of(const F* f)
+{
+  return f ? f->generic() : GenericPtr();
+}
+// appends one integrand term together with the lambdas behind its functions
+template <class FD, class FW>
+void push_term(IntegrandTerms& t, int kind, const FD* diffusion, const FW* weight, double prefactor, int hI_kind);
 inline gdtb_form make_form(const IntegrandTerms& t, int over_integrate, double scaling)
 {
   if (t.terms.empty() || t.terms.size() > GDTB_MAX_TERMS)
@@ -919,6 +1027,109 @@ gdtb_integrand make_term(int kind, const F* diffusion, const F* weight, double p
   if (weight)
     in.weight = weight->descriptor();
   return in;
+}
+template <class FD, class FW>
+void push_term(IntegrandTerms& t, int kind, const FD* diffusion, const FW* weight, double prefactor, int hI_kind)
+{
+  gdtb_integrand in{};
+  in.kind = kind;
+  in.hI_kind = hI_kind;
+  in.prefactor = prefactor;
+  in.diffusion.kind = GDTB_FN_CONST_SCALAR;
+  in.diffusion.c[0] = 1.;
+  in.weight.kind = GDTB_FN_CONST_SCALAR;
+  in.weight.c[0] = 1.;
+  if (diffusion)
+    in.diffusion = diffusion->descriptor();
+  if (weight)
+    in.weight = weight->descriptor();
+  t.terms.push_back(in);
+  t.generic.emplace_back(generic_of(diffusion), generic_of(weight));
+}
+
+// A local form ready for gdtb_*_append_*: the descriptor plus the sample arrays its GDTB_FN_QP_* functions point to
+struct LoweredForm
+{
+  gdtb_form form{};
+  std::vector<std::shared_ptr<std::vector<double>>> samples;
+};
+
+// x_q = lower_e + xhat_q * (upper_e - lower_e) with YaspGrid's coordinates lower = origin + i h, upper = origin +
+// (i + 1) h [EXT]: the points the reference hands to a bound local function (geometry.global(xhat))
+inline void sample_generic(const XT::Functions::internal::Generic& g, const gdtb_grid_desc& grid, int m, const double* xh,
+                           bool with_jacobian, std::vector<double>& out)
+{
+  const int d = grid.dim;
+  long long ne = 1;
+  double h[3] = {1., 1., 1.};
+  for (int k = 0; k < d; ++k) {
+    ne *= grid.n[k];
+    h[k] = (grid.upper[k] - grid.lower[k]) / double(grid.n[k]);
+  }
+  int nq = 1;
+  for (int k = 0; k < d; ++k)
+    nq *= m;
+  const int comps = with_jacobian ? 1 + d : g.comps;
+  out.assign(std::size_t(ne) * nq * comps, 0.);
+  double x[3] = {0., 0., 0.};
+  for (long long e = 0; e < ne; ++e) {
+    const long long idx[3] = {e % grid.n[0], (e / grid.n[0]) % grid.n[1], e / (grid.n[0] * grid.n[1])};
+    double lower[3], ext[3];
+    for (int k = 0; k < d; ++k) {
+      volatile double lo = grid.lower[k] + double(idx[k]) * h[k];
+      volatile double up = grid.lower[k] + double(idx[k] + 1) * h[k];
+      lower[k] = lo;
+      ext[k] = up - lo;
+    }
+    for (int q = 0; q < nq; ++q) {
+      const int qk[3] = {q % m, (q / m) % m, q / (m * m)};
+      for (int k = 0; k < d; ++k)
+        x[k] = lower[k] + xh[qk[k]] * ext[k];
+      double* dst = out.data() + (std::size_t(e) * nq + q) * comps;
+      g.evaluate(x, dst);
+      if (with_jacobian)
+        g.jacobian(x, dst + 1);
+    }
+  }
+}
+
+// samples every GenericFunction lambda of the form at the points of the rule the reference integrates the form with
+inline LoweredForm lower_form(const IntegrandTerms& t, int over_integrate, double scaling, int role, gdtb_space* space,
+                              const gdtb_grid_desc& grid)
+{
+  LoweredForm out;
+  out.form = make_form(t, over_integrate, scaling);
+  bool any = false;
+  for (const auto& g : t.generic)
+    any = any || g.first || g.second;
+  if (!any)
+    return out;
+  if (role == GDTB_ROLE_COUPLING || role == GDTB_ROLE_BOUNDARY)
+    throw Dune::NotImplemented("GenericFunction lambdas in intersection integrands (use constants, per-element data or "
+                               "the built-in functions there)");
+  std::int32_t order = 0, m = 0;
+  check(gdtb_form_quadrature_order(space, &out.form, role, &order)); // the placeholders carry the declared orders
+  double xh[8], w[8];
+  check(gdtb_gauss_rule(order, &m, xh, w));
+  int nq = 1;
+  for (int k = 0; k < grid.dim; ++k)
+    nq *= m;
+  for (std::size_t i = 0; i < t.terms.size(); ++i)
+    for (int which = 0; which < 2; ++which) {
+      const GenericPtr& g = which == 0 ? t.generic[i].first : t.generic[i].second;
+      if (!g)
+        continue;
+      gdtb_function& fn = which == 0 ? out.form.terms[i].diffusion : out.form.terms[i].weight;
+      auto samples = std::make_shared<std::vector<double>>();
+      sample_generic(*g, grid, m, xh, false, *samples);
+      fn.kind = g->comps == 1 ? GDTB_FN_QP_SCALAR : GDTB_FN_QP_TENSOR;
+      fn.order = g->order;
+      fn.qp_per_element = nq;
+      fn.data = samples->data();
+      fn.data_on_device = 0;
+      out.samples.push_back(samples);
+    }
+  return out;
 }
 } // namespace internal
 
@@ -968,15 +1179,13 @@ class LocalLaplaceIntegrand : public LocalBinaryElementIntegrandInterface<E>
 public:
   LocalLaplaceIntegrand(XT::Functions::GridFunction<E, d, d> diffusion = 1.)
   {
-    this->terms_.terms.push_back(
-        internal::make_term(GDTB_INT_LAPLACE, &diffusion, (decltype(&diffusion)) nullptr, 0., GDTB_HI_DIAMETER));
+    internal::push_term(this->terms_, GDTB_INT_LAPLACE, &diffusion, (decltype(&diffusion)) nullptr, 0., GDTB_HI_DIAMETER);
     this->terms_.keep.push_back(std::make_shared<XT::Functions::GridFunction<E, d, d>>(diffusion));
   }
   // element-wise constant scalar diffusion (kappa_e * I)
   LocalLaplaceIntegrand(const XT::Functions::GridFunction<E>& diffusion, int /*scalar tag*/)
   {
-    this->terms_.terms.push_back(
-        internal::make_term(GDTB_INT_LAPLACE, &diffusion, (decltype(&diffusion)) nullptr, 0., GDTB_HI_DIAMETER));
+    internal::push_term(this->terms_, GDTB_INT_LAPLACE, &diffusion, (decltype(&diffusion)) nullptr, 0., GDTB_HI_DIAMETER);
     this->terms_.keep.push_back(std::make_shared<XT::Functions::GridFunction<E>>(diffusion));
   }
 };
@@ -989,14 +1198,13 @@ public:
   LocalElementProductIntegrand(XT::Functions::GridFunction<E> weight = 1.)
     : weight_(weight)
   {
-    this->terms_.terms.push_back(
-        internal::make_term(GDTB_INT_PRODUCT, &weight_, (decltype(&weight_)) nullptr, 0., GDTB_HI_DIAMETER));
+    internal::push_term(this->terms_, GDTB_INT_PRODUCT, &weight_, (decltype(&weight_)) nullptr, 0., GDTB_HI_DIAMETER);
     this->terms_.keep.push_back(std::make_shared<XT::Functions::GridFunction<E>>(weight_));
   }
   LocalUnaryElementIntegrandInterface<E> with_ansatz(const XT::Functions::GridFunction<E>& function) const
   {
     internal::IntegrandTerms t;
-    t.terms.push_back(internal::make_term(GDTB_INT_PRODUCT, &weight_, &function, 0., GDTB_HI_DIAMETER));
+    internal::push_term(t, GDTB_INT_PRODUCT, &weight_, &function, 0., GDTB_HI_DIAMETER);
     t.keep.push_back(std::make_shared<XT::Functions::GridFunction<E>>(weight_));
     t.keep.push_back(std::make_shared<XT::Functions::GridFunction<E>>(function));
     return LocalUnaryElementIntegrandInterface<E>(t);
@@ -1069,8 +1277,8 @@ public:
                 XT::Functions::GridFunction<E, d, d> diffusion,
                 XT::Functions::GridFunction<E, d, d> weight_function = 1.)
   {
-    this->terms_.terms.push_back(internal::make_term(
-        GDTB_INT_IPDG_INNER_COUPLING, &diffusion, &weight_function, symmetry_prefactor, GDTB_HI_DIAMETER));
+    internal::push_term(this->terms_, 
+        GDTB_INT_IPDG_INNER_COUPLING, &diffusion, &weight_function, symmetry_prefactor, GDTB_HI_DIAMETER);
   }
 };
 // local/integrands/laplace-ipdg.hh:237-252 (binary use: the bilinear form on Dirichlet faces)
@@ -1083,11 +1291,11 @@ class DirichletCoupling : public LocalBinaryIntersectionIntegrandInterface<I>
 public:
   DirichletCoupling(const double& symmetry_prefactor, XT::Functions::GridFunction<E, d, d> diffusion)
   {
-    this->terms_.terms.push_back(internal::make_term(GDTB_INT_IPDG_DIRICHLET_COUPLING,
+    internal::push_term(this->terms_, GDTB_INT_IPDG_DIRICHLET_COUPLING,
                                                      &diffusion,
                                                      (decltype(&diffusion)) nullptr,
                                                      symmetry_prefactor,
-                                                     GDTB_HI_DIAMETER));
+                                                     GDTB_HI_DIAMETER);
   }
 };
 } // namespace LocalLaplaceIPDGIntegrands
@@ -1105,11 +1313,11 @@ public:
                XT::Functions::GridFunction<E, d, d> weight_function = 1.,
                const IntersectionDiameter intersection_diameter = IntersectionDiameter::diameter)
   {
-    this->terms_.terms.push_back(internal::make_term(GDTB_INT_IPDG_INNER_PENALTY,
+    internal::push_term(this->terms_, GDTB_INT_IPDG_INNER_PENALTY,
                                                      (decltype(&weight_function)) nullptr,
                                                      &weight_function,
                                                      penalty,
-                                                     int(intersection_diameter)));
+                                                     int(intersection_diameter));
   }
 };
 // local/integrands/ipdg.hh:201-213
@@ -1124,11 +1332,11 @@ public:
                   XT::Functions::GridFunction<E, d, d> weight_function = 1.,
                   const IntersectionDiameter intersection_diameter = IntersectionDiameter::diameter)
   {
-    this->terms_.terms.push_back(internal::make_term(GDTB_INT_IPDG_BOUNDARY_PENALTY,
+    internal::push_term(this->terms_, GDTB_INT_IPDG_BOUNDARY_PENALTY,
                                                      (decltype(&weight_function)) nullptr,
                                                      &weight_function,
                                                      penalty,
-                                                     int(intersection_diameter)));
+                                                     int(intersection_diameter));
   }
 };
 } // namespace LocalIPDGIntegrands
@@ -1140,6 +1348,8 @@ class LocalElementBilinearFormInterface
 public:
   virtual ~LocalElementBilinearFormInterface() = default;
   virtual gdtb_form descriptor(double scaling) const = 0;
+  // the descriptor with every GenericFunction lambda sampled at the rule of this form on `space`
+  virtual internal::LoweredForm lowered(double scaling, gdtb_space* space, const gdtb_grid_desc& grid) const = 0;
 };
 template <class I>
 class LocalCouplingIntersectionBilinearFormInterface
@@ -1147,6 +1357,8 @@ class LocalCouplingIntersectionBilinearFormInterface
 public:
   virtual ~LocalCouplingIntersectionBilinearFormInterface() = default;
   virtual gdtb_form descriptor(double scaling) const = 0;
+  // the descriptor with every GenericFunction lambda sampled at the rule of this form on `space`
+  virtual internal::LoweredForm lowered(double scaling, gdtb_space* space, const gdtb_grid_desc& grid) const = 0;
 };
 template <class I>
 class LocalIntersectionBilinearFormInterface
@@ -1154,6 +1366,8 @@ class LocalIntersectionBilinearFormInterface
 public:
   virtual ~LocalIntersectionBilinearFormInterface() = default;
   virtual gdtb_form descriptor(double scaling) const = 0;
+  // the descriptor with every GenericFunction lambda sampled at the rule of this form on `space`
+  virtual internal::LoweredForm lowered(double scaling, gdtb_space* space, const gdtb_grid_desc& grid) const = 0;
 };
 template <class E>
 class LocalElementFunctionalInterface
@@ -1161,6 +1375,7 @@ class LocalElementFunctionalInterface
 public:
   virtual ~LocalElementFunctionalInterface() = default;
   virtual gdtb_form descriptor() const = 0;
+  virtual internal::LoweredForm lowered(gdtb_space* space, const gdtb_grid_desc& grid) const = 0;
 };
 
 // integrals.hh:52-63
@@ -1176,6 +1391,10 @@ public:
   gdtb_form descriptor(double scaling) const override
   {
     return internal::make_form(terms_, over_integrate_, scaling);
+  }
+  internal::LoweredForm lowered(double scaling, gdtb_space* space, const gdtb_grid_desc& grid) const override
+  {
+    return internal::lower_form(terms_, over_integrate_, scaling, GDTB_ROLE_ELEMENT, space, grid);
   }
 
 private:
@@ -1197,6 +1416,10 @@ public:
   {
     return internal::make_form(terms_, over_integrate_, scaling);
   }
+  internal::LoweredForm lowered(double scaling, gdtb_space* space, const gdtb_grid_desc& grid) const override
+  {
+    return internal::lower_form(terms_, over_integrate_, scaling, GDTB_ROLE_COUPLING, space, grid);
+  }
 
 private:
   internal::IntegrandTerms terms_;
@@ -1217,6 +1440,10 @@ public:
   {
     return internal::make_form(terms_, over_integrate_, scaling);
   }
+  internal::LoweredForm lowered(double scaling, gdtb_space* space, const gdtb_grid_desc& grid) const override
+  {
+    return internal::lower_form(terms_, over_integrate_, scaling, GDTB_ROLE_BOUNDARY, space, grid);
+  }
 
 private:
   internal::IntegrandTerms terms_;
@@ -1235,6 +1462,10 @@ public:
   gdtb_form descriptor() const override
   {
     return internal::make_form(terms_, over_integrate_, 1.);
+  }
+  internal::LoweredForm lowered(gdtb_space* space, const gdtb_grid_desc& grid) const override
+  {
+    return internal::lower_form(terms_, over_integrate_, 1., GDTB_ROLE_FUNCTIONAL, space, grid);
   }
 
 private:
@@ -1263,8 +1494,9 @@ public:
                                 const XT::Common::Parameter& /*param*/ = {},
                                 const XT::Grid::ElementFilter<GV>& /*filter*/ = XT::Grid::ApplyOn::AllElements<GV>())
   {
-    const gdtb_form f = local_functional.descriptor();
-    internal::check(gdtb_vecfun_append_element(handle_.get(), &f));
+    // cloned by the library (samples of GenericFunction lambdas included) before `f` goes out of scope
+    const internal::LoweredForm f = local_functional.lowered(space_.handle(), space_.grid_view().desc());
+    internal::check(gdtb_vecfun_append_element(handle_.get(), &f.form));
     return *this;
   }
   // vector-based.hh:276-279
@@ -1350,8 +1582,9 @@ public:
                          const XT::Common::Parameter& /*param*/ = {},
                          const XT::Grid::ElementFilter<GV>& /*filter*/ = XT::Grid::ApplyOn::AllElements<GV>())
   {
-    const gdtb_form f = local_bilinear_form.descriptor(scaling);
-    internal::check(gdtb_matop_append_element(handle_.get(), &f));
+    const internal::LoweredForm f =
+        local_bilinear_form.lowered(scaling, range_space_.handle(), range_space_.grid_view().desc());
+    internal::check(gdtb_matop_append_element(handle_.get(), &f.form));
     return *this;
   }
   MatrixOperator& operator+=(const LocalElementBilinearFormInterface<E>& local_bilinear_form) // :450-455
@@ -1363,7 +1596,8 @@ public:
                          const XT::Common::Parameter& /*param*/ = {},
                          const XT::Grid::IntersectionFilter<GV>& filter = XT::Grid::ApplyOn::AllIntersections<GV>())
   {
-    const gdtb_form f = local_bilinear_form.descriptor(scaling);
+    const gdtb_form f =
+        local_bilinear_form.lowered(scaling, range_space_.handle(), range_space_.grid_view().desc()).form;
     const int flt = filter.gdtb_filter();
     if (flt != GDTB_FILTER_INNER_ONCE && flt != GDTB_FILTER_INNER_AND_PERIODIC_ONCE)
       throw Dune::NotImplemented("coupling forms are supported with ApplyOn::InnerIntersectionsOnce (and the "
@@ -1376,7 +1610,8 @@ public:
                          const XT::Common::Parameter& /*param*/ = {},
                          const XT::Grid::IntersectionFilter<GV>& filter = XT::Grid::ApplyOn::AllIntersections<GV>())
   {
-    const gdtb_form f = local_bilinear_form.descriptor(scaling);
+    const gdtb_form f =
+        local_bilinear_form.lowered(scaling, range_space_.handle(), range_space_.grid_view().desc()).form;
     if (filter.gdtb_filter() != GDTB_FILTER_ALL_BOUNDARY)
       throw Dune::NotImplemented("boundary forms are supported with CustomBoundaryIntersections(AllDirichlet...) only");
     internal::check(gdtb_matop_append_boundary(handle_.get(), &f, GDTB_FILTER_ALL_BOUNDARY));
@@ -1603,8 +1838,30 @@ public:
     result_ = 0.;
     for (const gdtb_form& f : forms_) {
       double r = 0.;
+      gdtb_function fn = e_.f.descriptor();
+      std::vector<double> samples;
+      if (e_.f.generic()) {
+        // an exact solution given by lambdas (value + jacobian, examples/stationary-heat-equation.cc:71-85): sampled at
+        // the points of the rule this form is integrated with
+        const auto& g = *e_.f.generic();
+        if (g.comps != 1 || !g.jacobian)
+          throw Dune::NotImplemented("norms against a GenericFunction need a scalar function with a jacobian lambda");
+        const gdtb_grid_desc& grid = e_.u_h.space().grid_view().desc();
+        std::int32_t order = 0, m = 0;
+        internal::check(gdtb_bilinear_form_quadrature_order(e_.u_h.space().handle(), 1, g.order, &f, &order));
+        double xh[8], w[8];
+        internal::check(gdtb_gauss_rule(order, &m, xh, w));
+        internal::sample_generic(g, grid, m, xh, true, samples);
+        fn = gdtb_function{};
+        fn.kind = GDTB_FN_QP_VALUE_GRAD;
+        fn.order = g.order;
+        fn.qp_per_element = 1;
+        for (int k = 0; k < grid.dim; ++k)
+          fn.qp_per_element *= m;
+        fn.data = samples.data();
+      }
       internal::check(gdtb_bilinear_form_apply2_host(internal::context(), e_.u_h.space().handle(),
-                                                     e_.u_h.dof_vector().data(), &e_.f.descriptor(), &f, &r));
+                                                     e_.u_h.dof_vector().data(), &fn, &f, &r));
       result_ += r;
     }
     assembled_ = true;

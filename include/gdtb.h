@@ -84,9 +84,12 @@ enum
 };
 
 /* XT::Functions::GridFunction<E, r, rC> stand-ins.  User lambdas cannot cross a C ABI as code, so a
- * grid function is a constant, a per-element array or one of a few analytic built-ins evaluated at the
- * global coordinate.  `order` is what GridFunction::order() would return: it enters the quadrature
- * order exactly like in the reference (laplace.hh:74-79, product.hh:89-100, conversion.hh:92). */
+ * grid function is a constant, a per-element array, one of a few analytic built-ins evaluated at the
+ * global coordinate, an array the binder sampled at the quadrature points of the form (this is how an
+ * XT::Functions::GenericFunction lambda crosses the boundary: the C++ facade samples it, see
+ * dune-gdt_b200/include/dune/gdt/b200.hh), or a discrete function given by its DoF vector.  `order` is what
+ * GridFunction::order() would return: it enters the quadrature order exactly like in the reference
+ * (laplace.hh:74-79, product.hh:89-100, conversion.hh:92). */
 enum
 {
   GDTB_FN_CONST_SCALAR = 0, /* c[0]; used as a d x d function it means c[0] * I (laplace.hh:41) */
@@ -105,7 +108,12 @@ enum
    * space_order) on the same grid (XT::Functions::GridFunction wrapping a DiscreteFunction,
    * discretefunction/default.hh): evaluated on the device at every quadrature point; as a d x d function it means
    * u_h * I.  `order` should be space_order (DiscreteFunction::order()). */
-  GDTB_FN_DOF_VECTOR = 7
+  GDTB_FN_DOF_VECTOR = 7,
+  /* A function together with its jacobian, sampled like GDTB_FN_QP_SCALAR: data[(e * qp_per_element + q) * (1 + d)] is
+   * the value, the next d entries the gradient.  Accepted as the analytic function `f` of gdtb_bilinear_form_apply2
+   * (the exact solution of examples/stationary-heat-equation.cc:71-85 with its jacobian lambda); the rule is the one
+   * gdtb_bilinear_form_quadrature_order reports. */
+  GDTB_FN_QP_VALUE_GRAD = 8
 };
 
 enum
@@ -257,6 +265,9 @@ int64_t gdtb_ctx_launch_count(const gdtb_ctx* ctx);
  * resets them. */
 int gdtb_ctx_enable_timing(gdtb_ctx* ctx, int enabled);
 int gdtb_ctx_kernel_time(gdtb_ctx* ctx, const char* family, double* total_ms, int64_t* launches);
+/* (mangled) symbol of the kernel instantiation the family launched last, as it shows up in an ncu launch list; "" if the
+ * family has not launched yet (gather families only) */
+const char* gdtb_ctx_kernel_name(const gdtb_ctx* ctx, const char* family);
 
 /* ---- grid / spaces -------------------------------------------------------------------------- */
 /* replaces XT::Grid::make_cube_grid + leaf_view (examples/stationary-heat-equation.cc:87-88) */
@@ -566,6 +577,9 @@ int gdtb_matop_pattern_device(gdtb_matop* op, const int64_t** d_rowptr, const in
  * one-function test and ansatz "basis" (bilinear-form.hh:340-352).  form: LocalLaplaceIntegrand (H^1 semi-norm^2) /
  * LocalElementProductIntegrand (L^2 norm^2) or sums; quadrature order = integrand order with test = ansatz order
  * = max(space order, f->order) plus over_integrate.  Deterministic (fixed-order two-stage reduction). */
+/* order of the rule gdtb_bilinear_form_apply2 integrates with (f_order: declared order of f, -1 without f) */
+int gdtb_bilinear_form_quadrature_order(const gdtb_space* space, int has_dofs, int f_order, const gdtb_form* form,
+                                        int32_t* order);
 int gdtb_bilinear_form_apply2(gdtb_ctx* ctx, const gdtb_space* space, const double* d_dofs, const gdtb_function* f,
                               const gdtb_form* form, double* result);
 int gdtb_bilinear_form_apply2_host(gdtb_ctx* ctx, const gdtb_space* space, const double* dofs, const gdtb_function* f,

@@ -7,7 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXAMPLES = os.path.join(ROOT, "dune-gdt_b200", "examples")
-PROGS = ["stationary-heat-equation", "linear-transport-fv", "elliptic-swipdg"]
+PROGS = ["stationary-heat-equation", "linear-transport-fv", "elliptic-swipdg", "generic-function-check"]
 
 
 def build_examples():
@@ -37,7 +37,9 @@ def test_examples_fail_loudly_without_a_gpu(gdt):
 @pytest.mark.parametrize("args", [["stationary-heat-equation", "128", "2"], ["stationary-heat-equation", "48", "3"],
                                   ["linear-transport-fv", "1024"],
                                   ["elliptic-swipdg"],  # the reference's ESV2007 H^1 table on 8^2, 16^2, 32^2 (3 digits)
-                                  ["elliptic-swipdg", "256"]])
+                                  ["elliptic-swipdg", "256"],
+                                  # GenericFunction lambdas (sampled by the facade) vs built-in / constant coefficients
+                                  ["generic-function-check"]])
 def test_examples_run(gdt, args):
     build_examples()
     r = subprocess.run([os.path.join(EXAMPLES, args[0])] + args[1:], capture_output=True, text=True, timeout=300)

@@ -102,6 +102,34 @@ __global__ void __launch_bounds__(256) k_dmma16x8x8(double* out, int iters, doub
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DFMA and DMMA interleaved in every warp: do the two share one datapath or run side by side?
+__global__ void __launch_bounds__(256) k_mixed(double* out, int iters, double a, double b)
+{
+  double acc[8], c[4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    acc[i] = threadIdx.x + i;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    c[i][0] = c[i][1] = threadIdx.x + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dmma(c[i][0], c[i][1], a, b);
+      acc[2 * i] = fma(acc[2 * i], a, b);
+      acc[2 * i + 1] = fma(acc[2 * i + 1], a, b);
+    }
+  }
+  double s = 0.;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    s += acc[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F>
 static double time_ms(F f)
 {
@@ -141,6 +169,10 @@ int main()
   const double d1684 = 2. * 512 * 4 * iters * (n_thr / 32) / (ms * 1e-3) / 1e12;
   ms = time_ms([&] { k_dmma16x8x8<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
   const double d1688 = 2. * 1024 * 4 * iters * (n_thr / 32) / (ms * 1e-3) / 1e12;
+  ms = time_ms([&] { k_mixed<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
+  // per iteration and warp: 4 DMMA (256 FMA each) + 8 DFMA warp instructions (32 FMA each)
+  const double mixed = 2. * (4 * 256 + 8 * 32) * iters * (n_thr / 32) / (ms * 1e-3) / 1e12;
+  printf("{\"mixed_dfma_dmma_tflops\": %.2f}\n", mixed);
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"dfma_tflops\": %.2f, \"dmma_m8n8k4_tflops_8acc\": %.2f, "
          "\"dmma_m8n8k4_tflops_4acc\": %.2f, \"dmma_m16n8k4_tflops\": %.2f, \"dmma_m16n8k8_tflops\": %.2f}\n",
          p.name, p.multiProcessorCount, dfma, dmma8, dmma4, d1684, d1688);
