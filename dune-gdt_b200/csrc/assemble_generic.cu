@@ -287,6 +287,7 @@ int dispatch_dk(int d, int K, Args&&... args)
     case 30: return Launcher<3, 0>::run(args...);
     case 31: return Launcher<3, 1>::run(args...);
     case 32: return Launcher<3, 2>::run(args...);
+    case 33: return Launcher<3, 3>::run(args...);
     default:
       return fail(GDTB_ERR_FINITE_ELEMENT, "unsupported (dimension, order) combination for the generic kernels");
   }

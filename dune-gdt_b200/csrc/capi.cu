@@ -119,8 +119,8 @@ int make_space_dev(const GridDev& g, int kind, int order, SpaceDev& sp)
     return fail(GDTB_ERR_SPACE, "continuous Lagrange spaces need order >= 1");
   else if (order < 0)
     return fail(GDTB_ERR_SPACE, "negative polynomial order");
-  if (K > MAX_K || (d == 3 && K > 2))
-    return fail(GDTB_ERR_FINITE_ELEMENT, "Lagrange order not supported (max 3 in 1d/2d, 2 in 3d)");
+  if (K > MAX_K)
+    return fail(GDTB_ERR_FINITE_ELEMENT, "Lagrange order not supported (max 3)");
   if (kind == GDTB_SPACE_CG && g.periodic)
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "continuous Lagrange spaces on periodic grid views are not supported");
   std::memset(&sp, 0, sizeof(sp));

@@ -184,3 +184,26 @@ def test_swipdg_inner_and_periodic_once_parity(gdt, ctx, oracle, n, periodic, or
         coupling_filter=D.FILTER_INNER_ONCE)
     wraps = any(((periodic >> k) & 1) and n[k] >= 2 for k in range(len(n)))
     assert (rel_err(inner_only, ref) > 1e-3) == wraps
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Q3 in 3D (local/finite-elements/lagrange.hh:107-136 allows cubes up to order 7 in 3D; spaces/mapper/continuous.hh:
+# 77-81, 124-133: orders >= 3 on Yasp grids): mapper, pattern and element forms through the quadrature-faithful kernels
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", [CG, DG])
+def test_q3_in_3d_mapping_pattern_and_matrix(gdt, ctx, oracle, kind):
+    n = [3, 2, 2]
+    gdesc = D.grid_desc([0.0, -1.0, 0.5], [3.0, 1.0, 2.0], n)
+    space = make_space(gdt, ctx, gdesc, kind, 3)
+    assert space.mapper.size == oracle.space_size(gdesc, kind, 3) == (10 * 7 * 7 if kind == CG else 12 * 64)
+    for e in range(int(np.prod(n))):
+        assert np.array_equal(space.mapper.global_indices(e), oracle.global_indices(gdesc, kind, 3, e))
+    kappa = D.fn_elem(np.random.default_rng(SEED).uniform(0.5, 2.0, int(np.prod(n))))
+    forms = [laplace(kappa), mass(0.5)]
+    rowptr, colidx, values, b, plan = gpu_assemble(gdt, ctx, gdesc, kind, 3, D.STENCIL_ELEMENT, element=forms,
+                                                   rhs=[source(D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 1.0, 1.3))])
+    assert plan == "generic_coloured"
+    rp, ci = oracle.pattern(gdesc, (kind, 3))
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+    ref_v, ref_b = oracle.assemble(gdesc, kind, 3, rp, ci, forms, rhs_forms=[source(D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 1.0, 1.3))])
+    assert rel_err(values, ref_v) <= TOL and rel_err(b, ref_b) <= TOL
