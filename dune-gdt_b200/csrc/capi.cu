@@ -1874,6 +1874,9 @@ static int assemble_cg_qp(gdtb_matop* op, bool accumulate)
         p.value_offset = q1_layer_rowptr(g, p.row_lo);
         p.row_offset = p.row_lo * q1_layer_rows(g);
         GDTB_TRY(launch_q1_gather_qp(L, p, op->d_values, !first));
+      } else if (q2_qp_xfused_supported(d, m, G.kind)) {
+        const bool sampled = !(f.kind == GDTB_FN_QP_SCALAR || f.kind == GDTB_FN_QP_TENSOR);
+        GDTB_TRY(launch_q2_qp_xfused(L, g, G, op->test, sampled ? e_begin : 0, sampled ? e_end : g.ne, op->d_values, !first));
       } else {
         Q2GatherParams p;
         std::memset(&p, 0, sizeof(p));

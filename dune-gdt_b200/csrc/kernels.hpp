@@ -270,6 +270,12 @@ int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* v
 bool q2_qp_supported(int d, int m, int kind);
 int launch_q2_gather_qp(Launch& L, Q2GatherParams& p, const CgQpGroup& group, const SpaceDev& sp, double* values,
                         bool accumulate);
+// 3D, scalar coefficient: the x-fused kernel (assemble_q2_qp.cu; three local-matrix rows per element and thread, the
+// coefficient stream staged in shared memory by TMA bulk loads); [coef_e_begin, coef_e_end) = elements the coefficient
+// array holds (indexed by the element index of the grid view)
+bool q2_qp_xfused_supported(int d, int m, int kind);
+int launch_q2_qp_xfused(Launch& L, const GridDev& g, const CgQpGroup& group, const SpaceDev& sp, long long coef_e_begin,
+                        long long coef_e_end, double* values, bool accumulate);
 
 // ---- DG row-gather assembly (assemble_dg_gather.cu) -----------------------------------------------
 constexpr int DGG_THREADS = 128;

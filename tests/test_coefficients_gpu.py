@@ -207,3 +207,72 @@ def test_q3_in_3d_mapping_pattern_and_matrix(gdt, ctx, oracle, kind):
     assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
     ref_v, ref_b = oracle.assemble(gdesc, kind, 3, rp, ci, forms, rhs_forms=[source(D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 1.0, 1.3))])
     assert rel_err(values, ref_v) <= TOL and rel_err(b, ref_b) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CG Q2 in 3D with a scalar coefficient per quadrature point: the x-fused kernel (assemble_q2_qp.cu)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [[5, 4, 3], [35, 3, 2], [31, 2, 2], [32, 2, 3], [1, 1, 1], [2, 1, 5], [63, 2, 2]])
+@pytest.mark.parametrize("variant", ["laplace-m3", "laplace-m2-underintegrated", "mass-m3", "laplace+mass-two-forms"])
+def test_q2_3d_qp_xfused_parity(gdt, ctx, oracle, n, variant):
+    import os
+
+    gdesc = D.grid_desc([0.0, -1.0, 0.5], [3.0, 1.0, 2.0], n)
+    if variant == "laplace-m3":
+        forms = [laplace(qp_scalar(n, 27, 0), scaling=0.75)]
+    elif variant == "laplace-m2-underintegrated":
+        forms = [laplace(qp_scalar(n, 8, 0), over_integrate=-2)]
+    elif variant == "mass-m3":
+        forms = [mass(qp_scalar(n, 27, 1, seed=5))]
+    else:
+        forms = [laplace(qp_scalar(n, 27, 1)), mass(qp_scalar(n, 27, 0, seed=9), scaling=2.0)]
+    rowptr, colidx, values, _, plan = gpu_assemble(gdt, ctx, gdesc, CG, 2, D.STENCIL_ELEMENT, element=forms)
+    assert plan == "q2_gather_qp"
+    rp, ci = oracle.pattern(gdesc, (CG, 2))
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+    ref, _ = oracle.assemble(gdesc, CG, 2, rp, ci, forms)
+    assert rel_err(values, ref) <= TOL
+    # the per-row kernel (assemble_q2_gather.cu, SF = 3) and the path without TMA bulk loads produce the same matrix
+    for env in ("GDTB_Q2_QP_NO_XFUSED", "GDTB_Q2_QP_NO_TMA"):
+        os.environ[env] = "1"
+        try:
+            _, _, other, _, _ = gpu_assemble(gdt, ctx, gdesc, CG, 2, D.STENCIL_ELEMENT, element=forms)
+        finally:
+            del os.environ[env]
+        assert rel_err(other, ref) <= TOL, env
+
+
+@pytest.mark.parametrize("order,n,cuts", [(2, [4, 3, 6], [0, 2, 6]), (2, [33, 2, 5], [0, 1, 3, 5]), (1, [6, 5, 8], [0, 3, 8]), (1, [7, 6], [0, 2, 6])])
+def test_slab_owner_computes_rows_variable_coefficients(gdt, ctx, oracle, order, n, cuts):
+    """coefficients that vary inside the cells on slabs (multi-GPU layout): caller-sampled data indexed by the GLOBAL
+    element index and an analytic function sampled on the device for the slab's element layers only"""
+    lib, check = gdt.capi.lib(), gdt.capi.check
+    gdesc = D.grid_desc(-1.0, 1.0, n)
+    d = len(n)
+    m = 3 if order == 2 else 2
+    forms = [laplace(qp_scalar(n, m**d, 0)), mass(D.fn_builtin(D.BUILTIN_AFFINE, 1 if order == 2 else 0, 1.0, 0.3, 0.2, 0.1))]
+    rp, ci = oracle.pattern(gdesc, (CG, order))
+    ref_v, _ = oracle.assemble(gdesc, CG, order, rp, ci, forms)
+    space = make_space(gdt, ctx, gdesc, CG, order)
+    got_v = np.full_like(ref_v, np.nan)
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        op_h = C.c_void_p()
+        check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(op_h)))
+        check(lib.gdtb_matop_set_slab(op_h, lo, hi))
+        for f in forms:
+            check(lib.gdtb_matop_append_element(op_h, C.byref(f)))
+        assert lib.gdtb_matop_plan(op_h).decode() == f"q{order}_gather_qp"
+        check(lib.gdtb_assemble(op_h, None, D.ASSEMBLE_OVERWRITE))
+        nr = C.c_int32()
+        check(lib.gdtb_matop_local_row_ranges(op_h, 0, None, None, None, None, C.byref(nr)))
+        vo, vc = (C.c_int64 * nr.value)(), (C.c_int64 * nr.value)()
+        check(lib.gdtb_matop_local_row_ranges(op_h, nr.value, None, None, vo, vc, C.byref(nr)))
+        v = np.empty(lib.gdtb_matop_local_nnz(op_h))
+        check(lib.gdtb_matop_values_download(op_h, gdt.capi.dptr(v)))
+        pos = 0
+        for r in range(nr.value):
+            got_v[vo[r] : vo[r] + vc[r]] = v[pos : pos + vc[r]]
+            pos += vc[r]
+        lib.gdtb_matop_destroy(op_h)
+    assert not np.isnan(got_v).any()
+    assert rel_err(got_v, ref_v) <= TOL
