@@ -386,6 +386,7 @@ def sharded_workload(env, workload, steps, warmup):
       c4 / c4-weak explicit FV upwind Euler steps on 4096^2 periodic, y-slabs, one ghost row per side over NCCL per step
                    (interior overlapped with the exchange)
       c4-p2p / c4-weak-p2p   the same with the ghost rows handed over INSIDE the kernel (NVLink peer stores)
+      c3 / c3-weak 2D SWIPDG DG-Q1 2048^2 (BASELINE.json configs[2]), y-slabs of element-owned rows, no collective
       c2-halo      the headline workload with the interface-row halo partition (own elements only + one message per
                    slab face + add) instead of the ghost-layer recompute, weak scaling"""
     torch, gdt = env.torch, env.gdt
@@ -420,6 +421,23 @@ def sharded_workload(env, workload, steps, warmup):
                      {"workload": "3D Q2 Laplace assembly, 128^3 YaspGrid cube sharded across the GPUs (BASELINE.json configs[4])",
                       "partition": f"z-slabs x{world}, owner-computes-rows per sub-entity group, no collective",
                       "nnz_this_rank": slab.nnz_local})
+    if workload in ("c3", "c3-weak"):
+        # BASELINE.json configs[2] at throughput size: SWIPDG DG-Q1 (element + inner coupling + Dirichlet boundary forms),
+        # y-slabs of element rows; rows are element-owned, the neighbour across a slab face enters through its index only
+        n = 2048
+        ny = n * world if workload == "c3-weak" else n
+        grid = gdt.make_cube_grid(ctx, [-1.0, -1.0], [1.0, -1.0 + ny * (2.0 / n)], [n, ny])
+        space = gdt.make_discontinuous_lagrange_space(grid, 1)
+        slab = parallel.SlabAssembly(space, rank, world, with_functional=False)
+        slab.append(D.form(D.integrand(D.INT_LAPLACE, diffusion=1.0)))
+        slab.append_coupling(D.form([D.integrand(D.INT_IPDG_INNER_COUPLING, prefactor=1.0, diffusion=1.0, weight=1.0),
+                                     D.integrand(D.INT_IPDG_INNER_PENALTY, prefactor=8.0, weight=1.0, hI_kind=D.HI_VOLUME)]))
+        slab.append_boundary(D.form([D.integrand(D.INT_IPDG_DIRICHLET_COUPLING, prefactor=1.0, diffusion=1.0),
+                                     D.integrand(D.INT_IPDG_BOUNDARY_PENALTY, prefactor=14.0, weight=1.0, hI_kind=D.HI_VOLUME)]))
+        return timed(slab.assemble_device, n * ny, "elements assembled/sec (2D SWIPDG DG-Q1, 2048^2, FP64)", UNIT,
+                     "weak" if workload == "c3-weak" else "strong",
+                     {"workload": f"2D SWIPDG DG-Q1 assembly, {n} x {ny} YaspGrid (BASELINE.json configs[2] at throughput size)",
+                      "partition": f"y-slabs x{world}, element-owned rows, no collective", "nnz_this_rank": slab.nnz_local})
     if workload in ("c4-p2p", "c4-weak-p2p"):
         n = 4096
         ny = n * world if workload == "c4-weak-p2p" else n
@@ -720,7 +738,7 @@ def run_product(args):
         # the multi-GPU rows that DO communicate, so that the scaling record carries them next to the headline
         extra = {"multi_gpu": {}}
         sub_steps = max(10, min(args.steps, 50))
-        for wl in ("c5", "c2-halo", "c4-weak-p2p", "c4-weak"):
+        for wl in ("c5", "c3", "c2-halo", "c4-weak-p2p", "c4-weak"):
             try:
                 extra["multi_gpu"][wl] = sharded_workload(env, wl, sub_steps, args.warmup)
             except Exception as exc:  # a failed side workload must not take the headline line with it
@@ -756,7 +774,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c4", "c4-weak", "c4-p2p", "c4-weak-p2p", "c2-halo"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c3", "c3-weak", "c4", "c4-weak", "c4-p2p", "c4-weak-p2p", "c2-halo"],
                     help="c2 (default, the headline line); c5 / c4 / c2-halo: the other multi-GPU rows, see run_sharded_workload")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -101,15 +101,17 @@ __global__ void __launch_bounds__(DGG_THREADS)
   const Tables* t_elem = tabs;
   const Tables* t_coup = tabs + p.n_elem;
   const Tables* t_bnd = tabs + p.n_elem + p.n_coup;
-  const long long nrows_total = g.ne * N;
+  // rows of the element range [e_begin, e_end) this process owns (a slab of element layers; the whole grid otherwise):
+  // DG rows are element-owned, the neighbours only enter through their index, geometry and coefficients
+  const long long row_first = p.e_begin * N, nrows_total = (p.e_end - p.e_begin) * N;
   const long long nitems = (nrows_total + DGG_THREADS - 1) / DGG_THREADS;
   int buf = 0;
 
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const long long r0 = item * DGG_THREADS;
-    const int nr = (int)min((long long)DGG_THREADS, nrows_total - r0);
-    const long long start = __ldg(p.rowptr + r0);
-    const int seg = int(__ldg(p.rowptr + r0 + nr) - start);
+    const long long r0 = row_first + item * DGG_THREADS;
+    const int nr = (int)min((long long)DGG_THREADS, row_first + nrows_total - r0);
+    const long long start = __ldg(p.rowptr + r0) - p.value_offset;
+    const int seg = int(__ldg(p.rowptr + r0 + nr) - p.value_offset - start);
     const int phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
     double* stage = smem + buf * stage_doubles + phase;
 
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(DGG_THREADS)
           }
       }
       // the row in CSR order: blocks by ascending neighbour index
-      double* row = stage + int(__ldg(p.rowptr + r) - start);
+      double* row = stage + int(__ldg(p.rowptr + r) - p.value_offset - start);
 #pragma unroll
       for (int k = D - 1; k >= 0; --k)
         if (has_lo[k]) {
@@ -238,7 +240,7 @@ int launch_dg_gather_dk(Launch& L, const DgGatherParams& p, double* values, bool
   GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DGG_THREADS, smem));
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "dg_gather: kernel does not fit on an SM");
-  const long long nitems = (p.g.ne * N + DGG_THREADS - 1) / DGG_THREADS;
+  const long long nitems = ((p.e_end - p.e_begin) * N + DGG_THREADS - 1) / DGG_THREADS;
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)
     grid = nitems;
@@ -480,24 +482,24 @@ __global__ void __launch_bounds__(DGG_THREADS)
   const DgFastTab* t_elem = tabs;
   const DgFastTab* t_coup = tabs + p.n_elem;
   const DgFastTab* t_bnd = tabs + p.n_elem + p.n_coup;
-  const long long nrows_total = g.ne * N;
-  const long long nitems = (nrows_total + DGG_THREADS - 1) / DGG_THREADS;
   constexpr int EPI = DGG_THREADS / N; // elements per item
+  // the element range [e_begin, e_end) this process owns (a slab of element layers; the whole grid otherwise)
+  const long long nitems = (p.e_end - p.e_begin + EPI - 1) / EPI;
   int buf = 0;
 
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const long long e0 = item * EPI;
-    const int ne_item = (int)min((long long)EPI, g.ne - e0);
+    const long long e0 = p.e_begin + item * EPI;
+    const int ne_item = (int)min((long long)EPI, p.e_end - e0);
     int idx0[3], idx1[3];
     dg_decode<D>(p, (unsigned)e0, idx0);
-    const long long start = (long long)N * N * dg_blocks_before<D>(g, e0, idx0);
+    const long long start = (long long)N * N * dg_blocks_before<D>(g, e0, idx0) - p.value_offset;
     long long end;
     if (e0 + ne_item < g.ne) {
       dg_decode<D>(p, (unsigned)(e0 + ne_item), idx1);
-      end = (long long)N * N * dg_blocks_before<D>(g, e0 + ne_item, idx1);
+      end = (long long)N * N * dg_blocks_before<D>(g, e0 + ne_item, idx1) - p.value_offset;
     } else {
       dg_decode<D>(p, (unsigned)(g.ne - 1), idx1);
-      end = (long long)N * N * (dg_blocks_before<D>(g, g.ne - 1, idx1) + dg_nblocks<D>(g, idx1));
+      end = (long long)N * N * (dg_blocks_before<D>(g, g.ne - 1, idx1) + dg_nblocks<D>(g, idx1)) - p.value_offset;
     }
     const int seg = int(end - start);
     const int phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(DGG_THREADS)
       int idx[3];
       dg_decode<D>(p, (unsigned)e, idx);
       const int nblocks = dg_nblocks<D>(g, idx);
-      double* row = stage + int((long long)N * N * dg_blocks_before<D>(g, e, idx) - start) + i * nblocks * N;
+      double* row = stage + int((long long)N * N * dg_blocks_before<D>(g, e, idx) - p.value_offset - start) + i * nblocks * N;
       long long estride[3] = {1, g.n[0], g.n[0] * g.n[1]};
       bool has_lo[D], has_hi[D];
       double h[D], hinv[D];
@@ -787,7 +789,7 @@ int launch_dg_gather_fast(Launch& L, DgGatherParams& p, double* values, bool acc
   GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DGG_THREADS, smem));
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "dg_gather: kernel does not fit on an SM");
-  const long long nitems = (p.g.ne * N + DGG_THREADS - 1) / DGG_THREADS;
+  const long long nitems = ((p.e_end - p.e_begin) * N + DGG_THREADS - 1) / DGG_THREADS;
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)
     grid = nitems;
@@ -932,6 +934,21 @@ static void dg_host_rowptr_d(const GridDev& g, int nloc, long long* rowptr)
     if (e == g.ne - 1)
       rowptr[r] = base + (long long)nloc * nb * nloc;
   }
+}
+
+long long dg_value_offset(const GridDev& g, const SpaceDev& sp, long long e)
+{
+  const long long nn = (long long)sp.nloc * sp.nloc;
+  const long long ee = std::min(e, g.ne - 1);
+  int idx[3] = {int(ee % g.n[0]), g.d > 1 ? int((ee / g.n[0]) % g.n[1]) : 0, g.d > 2 ? int(ee / (g.n[0] * g.n[1])) : 0};
+  long long blocks;
+  int nb;
+  switch (g.d) {
+    case 1: blocks = dg_blocks_before<1>(g, ee, idx); nb = dg_nblocks<1>(g, idx); break;
+    case 2: blocks = dg_blocks_before<2>(g, ee, idx); nb = dg_nblocks<2>(g, idx); break;
+    default: blocks = dg_blocks_before<3>(g, ee, idx); nb = dg_nblocks<3>(g, idx); break;
+  }
+  return nn * (e >= g.ne ? blocks + nb : blocks);
 }
 
 int dg_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr)

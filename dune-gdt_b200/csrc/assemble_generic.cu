@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128)
 template <int D, int K>
 __global__ void __launch_bounds__(128)
     k_element_vector(const GridDev g, const SpaceDev sp, const __grid_constant__ FormDev f, const Range range,
-                     double* __restrict__ vec)
+                     double* __restrict__ vec, const RowMap rows)
 {
   using L = Loc<D, K>;
   constexpr int N = L::N;
@@ -147,7 +147,17 @@ __global__ void __launch_bounds__(128)
         const double v = (w * vi) * fx; // conversion.hh:109-116 -> product.hh:126-128
         l += v * ie * wq;               // local/functionals/integrals.hh:96
       }
-  const long long row = global_index(g, sp, idx, i);
+  long long row = global_index(g, sp, idx, i);
+  if (rows.n > 0) { // slab: only the owned rows live in the local vector
+    long long local = -1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < rows.n && row >= rows.begin[r] && row < rows.end[r])
+        local = rows.local[r] + (row - rows.begin[r]);
+    if (local < 0)
+      return;
+    row = local;
+  }
   vec[row] += l; // functional-assemblers.hh:84-85
 }
 
@@ -320,7 +330,7 @@ struct ElementMatrixLauncher
 template <int D, int K>
 struct ElementVectorLauncher
 {
-  static int run(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, double* vec)
+  static int run(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, double* vec, const RowMap& rows)
   {
     time_begin(L, KF_ELEMENT_VECTOR);
     const bool coloured = sp.kind == GDTB_SPACE_CG;
@@ -330,7 +340,7 @@ struct ElementVectorLauncher
       if (!element_range(g, coloured, c, r))
         continue;
       const long long threads = r.total() * Loc<D, K>::N;
-      k_element_vector<D, K><<<blocks_for(threads, 128), 128, 0, L.stream>>>(g, sp, f, r, vec);
+      k_element_vector<D, K><<<blocks_for(threads, 128), 128, 0, L.stream>>>(g, sp, f, r, vec, rows);
       L.count++;
     }
     time_end(L, KF_ELEMENT_VECTOR);
@@ -481,9 +491,10 @@ int launch_element_matrix(Launch& L, const GridDev& g, const SpaceDev& sp, const
   return dispatch_dk<ElementMatrixLauncher>(g.d, sp.K, L, g, sp, f, rowptr, colidx, values, error_flag);
 }
 
-int launch_element_vector(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, double* vec)
+int launch_element_vector(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, double* vec,
+                          const RowMap& rows)
 {
-  return dispatch_dk<ElementVectorLauncher>(g.d, sp.K, L, g, sp, f, vec);
+  return dispatch_dk<ElementVectorLauncher>(g.d, sp.K, L, g, sp, f, vec, rows);
 }
 
 int launch_coupling_matrix(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, int filter,

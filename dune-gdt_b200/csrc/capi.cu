@@ -422,12 +422,14 @@ bool matop_q2_eligible(const gdtb_matop* op)
 // grid with the element_and_intersection pattern
 bool matop_dg_eligible(const gdtb_matop* op)
 {
-  if (op->test.kind != GDTB_SPACE_DG || op->ansatz.kind != GDTB_SPACE_DG || op->grid.periodic || op->slab)
+  if (op->test.kind != GDTB_SPACE_DG || op->ansatz.kind != GDTB_SPACE_DG || op->grid.periodic)
     return false;
   if (!dg_gather_supported(op->grid.d, op->test.K))
     return false;
-  if (!op->pattern || op->pattern->stencil != GDTB_STENCIL_ELEMENT_AND_INTERSECTION
-      || op->pattern->test.kind != GDTB_SPACE_DG || op->pattern->test.K != op->test.K)
+  // a pattern-free operator follows the closed-form element_and_intersection stencil; a given pattern must be that one
+  if (op->pattern
+      && (op->pattern->stencil != GDTB_STENCIL_ELEMENT_AND_INTERSECTION || op->pattern->test.kind != GDTB_SPACE_DG
+          || op->pattern->test.K != op->test.K))
     return false;
   const size_t n = op->element_forms.size() + op->coupling_forms.size() + op->boundary_forms.size();
   if (n == 0 || n > (size_t)DGG_MAX_FORMS)
@@ -1008,13 +1010,20 @@ int gdtb_host_slab_row_ranges(const gdtb_grid_desc* grid, int kind, int order, i
   const long long n_last = g.n[g.d - 1];
   if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
-  if (g.periodic || kind != GDTB_SPACE_CG || (sp.K != 1 && !(sp.K == 2 && (g.d == 2 || g.d == 3))))
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab row ranges: CG Q1 and CG Q2 (2D / 3D) on non-periodic grids");
+  const bool dg = kind == GDTB_SPACE_DG;
+  if (g.periodic || (!dg && (kind != GDTB_SPACE_CG || (sp.K != 1 && !(sp.K == 2 && (g.d == 2 || g.d == 3))))))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab row ranges: CG Q1, CG Q2 (2D / 3D) and DG on non-periodic grids");
   g.layer_lo = layer_begin;
   g.layer_hi = layer_end;
   Q2SlabRange ranges[8];
   int n = 1;
-  if (sp.K == 2)
+  if (dg) {
+    const long long plane = g.ne / n_last;
+    ranges[0].row_begin = layer_begin * plane * sp.nloc;
+    ranges[0].row_end = layer_end * plane * sp.nloc;
+    ranges[0].value_offset = dg_value_offset(g, sp, layer_begin * plane);
+    ranges[0].count = dg_value_offset(g, sp, layer_end * plane) - ranges[0].value_offset;
+  } else if (sp.K == 2)
     n = q2_slab_ranges(g, sp, ranges);
   else {
     long long row_lo, row_hi, elem_lo, elem_hi;
@@ -1206,9 +1215,13 @@ int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* a
   const auto q2_space = [](const SpaceDev& sp) { return sp.kind == GDTB_SPACE_CG && sp.K == 2 && (sp.d == 2 || sp.d == 3); };
   const bool closed_q1 = q1_space(test->dev) && q1_space(ansatz->dev) && !test->grid.periodic;
   const bool closed_q2 = q2_space(test->dev) && q2_space(ansatz->dev) && !test->grid.periodic;
-  if (!pattern && !closed_q1 && !closed_q2)
+  // discontinuous spaces: the element_and_intersection stencil (what an IPDG operator needs) has a closed form too
+  const bool closed_dg = test->dev.kind == GDTB_SPACE_DG && ansatz->dev.kind == GDTB_SPACE_DG && !test->grid.periodic
+                         && test->dev.size < (1LL << 31);
+  if (!pattern && !closed_q1 && !closed_q2 && !closed_dg)
     return fail(GDTB_ERR_INVALID_ARGUMENT,
-                "gdtb_matop_create: a pattern is required (only the CG Q1 / Q2 element stencils have closed forms)");
+                "gdtb_matop_create: a pattern is required (only the CG Q1 / Q2 element stencils and the DG "
+                "element_and_intersection stencil on non-periodic grids have closed forms)");
   // matrix-based.hh:73-80: matrix.rows() == range_space.mapper().size(), cols == source_space.mapper().size()
   if (pattern && (pattern->rows != test->dev.size || pattern->cols != ansatz->dev.size))
     return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "pattern shape does not match the spaces (rows = test, cols = ansatz)");
@@ -1234,7 +1247,9 @@ int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* a
     op->nnz_local = 1;
     for (int k = 0; k < op->grid.d; ++k)
       op->nnz_local *= 3 * op->grid.n[k] + 1;
-  } else { // CG Q2 element stencil: prod_k (8 n_k + 1) lattice couplings
+  } else if (closed_dg)
+    op->nnz_local = dg_value_offset(op->grid, op->test, op->grid.ne);
+  else { // CG Q2 element stencil: prod_k (8 n_k + 1) lattice couplings
     Q2SlabRange ranges[8];
     const int nr = q2_slab_ranges(op->grid, op->test, ranges);
     op->nnz_local = 0;
@@ -1489,14 +1504,31 @@ static int matop_set_slab_impl(gdtb_matop* op, int64_t layer_begin, int64_t laye
     return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
   const bool q2 = op->test.kind == GDTB_SPACE_CG && op->test.K == 2 && (op->grid.d == 2 || op->grid.d == 3)
                   && !op->grid.periodic && std::memcmp(&op->test, &op->ansatz, sizeof(SpaceDev)) == 0;
-  if (!(q1_space(op->test) && q1_space(op->ansatz)) && !q2)
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab-partitioned assembly is implemented for CG Q1 and Q2 spaces");
+  const bool dg = op->test.kind == GDTB_SPACE_DG && !op->grid.periodic
+                  && std::memcmp(&op->test, &op->ansatz, sizeof(SpaceDev)) == 0 && !halo;
+  if (!(q1_space(op->test) && q1_space(op->ansatz)) && !q2 && !dg)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED,
+                "slab-partitioned assembly is implemented for CG Q1 / Q2 spaces and DG spaces on non-periodic grids");
+  if (dg && op->pattern
+      && (op->pattern->stencil != GDTB_STENCIL_ELEMENT_AND_INTERSECTION || op->pattern->test.kind != GDTB_SPACE_DG))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "DG slabs follow the element_and_intersection stencil");
   if (!op->owns_values)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_matop_set_slab must be called before lending a value buffer");
   op->grid.layer_lo = layer_begin;
   op->grid.layer_hi = layer_end;
   op->slab = true;
-  if (q2) {
+  if (dg) {
+    // DG rows are element-owned: the slab's rows are those of its own elements, contiguous in the global numbering;
+    // the neighbours across the slab faces enter through their index, geometry and coefficients only (no exchange)
+    const long long plane = op->grid.ne / n_last;
+    op->elem_lo = layer_begin;
+    op->elem_hi = layer_end;
+    op->row_begin = layer_begin * plane * op->test.nloc;
+    op->row_end = layer_end * plane * op->test.nloc;
+    op->value_offset = dg_value_offset(op->grid, op->test, layer_begin * plane);
+    op->nnz_local = dg_value_offset(op->grid, op->test, layer_end * plane) - op->value_offset;
+    op->n_ranges = 0;
+  } else if (q2) {
     // the MCMG numbering groups the rows by sub-entity kind: a slab owns one contiguous row range per group
     Q2SlabRange ranges[8];
     op->n_ranges = q2_slab_ranges(op->grid, op->test, ranges);
@@ -1589,6 +1621,7 @@ int gdtb_vecfun_create(gdtb_ctx* ctx, const gdtb_space* space, gdtb_vecfun** out
   f->rule_uploaded = false;
   f->row_begin = 0;
   f->row_end = space->dev.size;
+  f->local_size = space->dev.size;
   f->row_lo = 0;
   f->row_hi = space->grid.n[space->grid.d - 1] + 1;
   f->elem_lo = 0;
@@ -1645,8 +1678,7 @@ int gdtb_vecfun_set_zero(gdtb_vecfun* fun)
   if (!fun)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "functional is NULL");
   GDTB_TRY(check_ctx(fun->ctx));
-  GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)(fun->row_end - fun->row_begin),
-                            fun->ctx->launch.stream));
+  GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)fun->local_size, fun->ctx->launch.stream));
   GDTB_CUDA(cudaStreamSynchronize(fun->ctx->launch.stream));
   return GDTB_OK;
 }
@@ -1656,8 +1688,8 @@ int gdtb_vecfun_download(const gdtb_vecfun* fun, double* vector)
   if (!fun || !vector)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_download: NULL argument");
   GDTB_TRY(check_ctx(fun->ctx));
-  GDTB_CUDA(cudaMemcpyAsync(vector, fun->d_vec, sizeof(double) * (size_t)(fun->row_end - fun->row_begin),
-                            cudaMemcpyDeviceToHost, fun->ctx->launch.stream));
+  GDTB_CUDA(cudaMemcpyAsync(vector, fun->d_vec, sizeof(double) * (size_t)fun->local_size, cudaMemcpyDeviceToHost,
+                            fun->ctx->launch.stream));
   GDTB_CUDA(cudaStreamSynchronize(fun->ctx->launch.stream));
   return GDTB_OK;
 }
@@ -1717,24 +1749,57 @@ static int vecfun_set_slab_impl(gdtb_vecfun* fun, int64_t layer_begin, int64_t l
   const long long n_last = fun->grid.n[fun->grid.d - 1];
   if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
-  if (!q1_space(fun->space))
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab-partitioned assembly is implemented for CG Q1 spaces");
+  const SpaceDev& sp = fun->space;
+  const bool q1 = q1_space(sp);
+  const bool q2 = sp.kind == GDTB_SPACE_CG && sp.K == 2 && (fun->grid.d == 2 || fun->grid.d == 3);
+  const bool element_owned = sp.kind != GDTB_SPACE_CG;
+  if (halo && !q1)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "the interface-row halo partition is implemented for CG Q1 spaces");
+  if (!q1 && !q2 && !element_owned)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "slab-partitioned functionals: CG Q1 / Q2, DG and FV spaces");
   if (!fun->owns_vec)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vecfun_set_slab must be called before lending a vector buffer");
   fun->grid.layer_lo = layer_begin;
   fun->grid.layer_hi = layer_end;
   fun->slab = true;
-  if (halo)
-    q1_halo_ranges(fun->grid, layer_begin, layer_end, fun->row_lo, fun->row_hi, fun->elem_lo, fun->elem_hi);
-  else
-    q1_slab_ranges(fun->grid, layer_begin, layer_end, fun->row_lo, fun->row_hi, fun->elem_lo, fun->elem_hi);
   fun->halo = halo;
-  fun->row_begin = fun->row_lo * q1_layer_rows(fun->grid);
-  fun->row_end = fun->row_hi * q1_layer_rows(fun->grid);
+  fun->n_ranges = 0;
+  if (q1) {
+    if (halo)
+      q1_halo_ranges(fun->grid, layer_begin, layer_end, fun->row_lo, fun->row_hi, fun->elem_lo, fun->elem_hi);
+    else
+      q1_slab_ranges(fun->grid, layer_begin, layer_end, fun->row_lo, fun->row_hi, fun->elem_lo, fun->elem_hi);
+    fun->row_begin = fun->row_lo * q1_layer_rows(fun->grid);
+    fun->row_end = fun->row_hi * q1_layer_rows(fun->grid);
+    fun->local_size = fun->row_end - fun->row_begin;
+  } else if (q2) {
+    // one owned row range per sub-entity group of the MCMG numbering, back to back in the local vector
+    Q2SlabRange ranges[8];
+    fun->n_ranges = q2_slab_ranges(fun->grid, sp, ranges);
+    fun->local_size = 0;
+    for (int r = 0; r < fun->n_ranges; ++r) {
+      fun->range_row_begin[r] = ranges[r].row_begin;
+      fun->range_row_end[r] = ranges[r].row_end;
+      fun->range_local[r] = fun->local_size;
+      fun->local_size += ranges[r].row_end - ranges[r].row_begin;
+    }
+    fun->row_begin = ranges[0].row_begin;
+    fun->row_end = ranges[0].row_end;
+    fun->elem_lo = std::max<long long>(layer_begin - 1, 0);
+    fun->elem_hi = layer_end;
+  } else {
+    // DG / FV: the rows of the slab's own elements
+    const long long plane = fun->grid.ne / n_last;
+    fun->elem_lo = layer_begin;
+    fun->elem_hi = layer_end;
+    fun->row_begin = layer_begin * plane * sp.nloc;
+    fun->row_end = layer_end * plane * sp.nloc;
+    fun->local_size = fun->row_end - fun->row_begin;
+  }
   cudaFree(fun->d_vec);
   fun->d_vec = nullptr;
-  const size_t bytes = sizeof(double) * (size_t)(fun->row_end - fun->row_begin);
-  if (cudaMalloc(&fun->d_vec, bytes) != cudaSuccess)
+  const size_t bytes = sizeof(double) * (size_t)fun->local_size;
+  if (cudaMalloc(&fun->d_vec, std::max<size_t>(bytes, 8)) != cudaSuccess)
     return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory for the vector of the slab");
   GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, bytes, fun->ctx->launch.stream));
   return GDTB_OK;
@@ -1905,12 +1970,14 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
   const bool fun_fast = fun && vecfun_q1_eligible(fun);
   const bool op_q2 = op && !op_fast && matop_q2_eligible(op);
   const bool op_qp = op && !op_fast && !op_q2 && matop_cg_qp_eligible(op);
-  if (op && !op_fast && !op_q2 && !op_qp && (op->slab || !op->pattern))
+  const bool op_dg = op && !op_fast && !op_q2 && !op_qp && matop_dg_eligible(op);
+  if (op && !op_fast && !op_q2 && !op_qp && !op_dg && (op->slab || !op->pattern))
     return fail(GDTB_ERR_NOT_IMPLEMENTED,
-                "slab-partitioned / pattern-free operators only support forms the CG Q1 / Q2 row-gather kernels cover");
-  if (fun && !fun_fast && fun->slab)
+                "slab-partitioned / pattern-free operators only support forms the row-gather kernels cover (CG Q1 / Q2 "
+                "element forms, DG forms with the element_and_intersection stencil)");
+  if (fun && !fun_fast && fun->slab && fun->halo)
     return fail(GDTB_ERR_NOT_IMPLEMENTED,
-                "slab-partitioned functionals only support sources the CG Q1 row-gather kernel covers");
+                "the interface-row halo partition only supports sources the CG Q1 row-gather kernel covers");
 
   // --- CG-Q1 row-gather path: matrix and right-hand side in ONE pass over the vertices ---------
   if (op_fast || fun_fast) {
@@ -1949,7 +2016,6 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     GDTB_TRY(assemble_cg_qp(op, accumulate));
 
   // --- DG row-gather path ------------------------------------------------------------------
-  const bool op_dg = op && !op_fast && !op_q2 && !op_qp && matop_dg_eligible(op);
   if (op_dg) {
     std::vector<FormDev> forms;
     for (const auto& lf : op->element_forms) {
@@ -1987,7 +2053,10 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     p.n_elem = (int)op->element_forms.size();
     p.n_coup = (int)op->coupling_forms.size();
     p.n_bnd = (int)op->boundary_forms.size();
-    p.rowptr = op->pattern->d_rowptr;
+    const long long plane = op->grid.ne / op->grid.n[op->grid.d - 1];
+    p.e_begin = op->slab ? op->elem_lo * plane : 0;
+    p.e_end = op->slab ? op->elem_hi * plane : op->grid.ne;
+    p.value_offset = op->slab ? op->value_offset : 0;
     // factorised kernel: order 1 and every coefficient a constant or element-wise scalar
     const auto scalar = [](const FnDev& f) { return f.kind == GDTB_FN_CONST_SCALAR || f.kind == GDTB_FN_ELEM_SCALAR; };
     bool fast = dg_gather_fast_supported(op->grid, op->test.K) && !std::getenv("GDTB_DG_NO_FAST");
@@ -2000,6 +2069,12 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       for (int t = 0; t < f.n_terms; ++t)
         all_const = all_const && f.terms[t].diffusion.kind == GDTB_FN_CONST_SCALAR && f.terms[t].weight.kind == GDTB_FN_CONST_SCALAR;
     p.fast = fast ? ((all_const && !std::getenv("GDTB_DG_NO_CC")) ? 2 : 1) : 0;
+    if (!p.fast) { // the quadrature-faithful kernel reads the row pointer (materialised for a pattern-free operator)
+      const long long* rp = nullptr;
+      const int* ci = nullptr;
+      GDTB_TRY(internal_matop_pattern(op, &rp, &ci));
+      p.rowptr = rp;
+    }
     GDTB_TRY(launch_dg_gather(L, p, op->d_values, accumulate));
   }
 
@@ -2030,11 +2105,26 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
   }
   if (fun && !fun_fast) {
     if (!accumulate)
-      GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)fun->space.size, L.stream));
+      GDTB_CUDA(cudaMemsetAsync(fun->d_vec, 0, sizeof(double) * (size_t)fun->local_size, L.stream));
+    // slabs: walk the element layers the owned rows need (continuous spaces: plus the ghost layer below) and keep the
+    // contributions to the owned rows only -- complete rows without communication, like the matrix
+    RowMap rows;
+    std::memset(&rows, 0, sizeof(rows));
+    GridDev walk = fun->grid;
+    if (fun->slab) {
+      walk.layer_lo = fun->elem_lo;
+      walk.layer_hi = fun->elem_hi;
+      rows.n = fun->n_ranges > 0 ? fun->n_ranges : 1;
+      for (int r = 0; r < rows.n; ++r) {
+        rows.begin[r] = fun->n_ranges > 0 ? fun->range_row_begin[r] : fun->row_begin;
+        rows.end[r] = fun->n_ranges > 0 ? fun->range_row_end[r] : fun->row_end;
+        rows.local[r] = fun->n_ranges > 0 ? fun->range_local[r] : 0;
+      }
+    }
     for (const auto& lf : fun->forms) {
       FormDev fd;
       GDTB_TRY(make_form_dev(lf.form, fun->space.K, ROLE_RHS, fd, &lf));
-      GDTB_TRY(launch_element_vector(L, fun->grid, fun->space, fd, fun->d_vec));
+      GDTB_TRY(launch_element_vector(L, walk, fun->space, fd, fun->d_vec, rows));
     }
   }
   if (synchronize)

@@ -120,6 +120,12 @@ struct gdtb_vecfun
   bool slab;
   long long row_begin, row_end;
   long long row_lo, row_hi, elem_lo, elem_hi;
+  // slabs of spaces whose owned rows are not one range (CG Q2: one range per sub-entity group) or that take the
+  // quadrature-faithful kernel: global row ranges and their positions in the local vector (n_ranges == 0: [row_begin,
+  // row_end) at position 0)
+  int n_ranges = 0;
+  long long range_row_begin[8], range_row_end[8], range_local[8];
+  long long local_size = 0;
   double h_rule[4 * MAX_Q1D];
   bool rule_uploaded;
   bool halo = false;
@@ -192,4 +198,6 @@ int internal_check_ctx(gdtb_ctx* ctx);
 int internal_validate_function(const gdtb_function& f, const char* what);
 int internal_lower_function(gdtb_ctx* ctx, const GridDev& g, gdtb_function& f, LoweredForm& owner);
 FnDev internal_to_dev(const gdtb_function& f, const LoweredForm* owner = nullptr);
+// the CSR pattern an operator's values follow (solve.cu): the caller's, or the closed-form one materialised on demand
+int internal_matop_pattern(gdtb_matop* op, const long long** rowptr, const int** colidx);
 } // namespace gdtb

@@ -72,7 +72,14 @@ inline void time_end(Launch& L, int family)
 // ---- generic, quadrature-faithful kernels (assemble_generic.cu) -----------------------------------
 int launch_element_matrix(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, const long long* rowptr,
                           const int* colidx, double* values, int* error_flag);
-int launch_element_vector(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, double* vec);
+// owned global row ranges -> positions in a slab-local vector (n == 0: the vector is global)
+struct RowMap
+{
+  int n;
+  long long begin[8], end[8], local[8];
+};
+int launch_element_vector(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, double* vec,
+                          const RowMap& rows);
 int launch_coupling_matrix(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, int filter,
                            const long long* rowptr, const int* colidx, double* values, int* error_flag);
 int launch_boundary_matrix(Launch& L, const GridDev& g, const SpaceDev& sp, const FormDev& f, const long long* rowptr,
@@ -292,6 +299,9 @@ struct DgGatherParams
   // collapse into 1D tables; row starts are closed forms (rowptr is not read)
   int fast; // 0: quadrature-faithful kernel, 1: factorised, 2: factorised with constant coefficients tabulated
   unsigned long long magic[2]; // floor(2^64 / n_k) + 1 for the element-index decode (0 when n_k == 1)
+  // element-owned rows: this process produces the rows of the elements [e_begin, e_end) (a slab of element layers),
+  // `values` starts at the global CSR position value_offset
+  long long e_begin, e_end, value_offset;
 };
 
 bool dg_gather_supported(int d, int K);
@@ -314,6 +324,8 @@ int pattern_structured_dg(Launch& L, const GridDev& g, const SpaceDev& sp, long 
 int q1_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr);
 int q2_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr);
 int dg_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr);
+// global CSR position of the first value of element e in the DG element_and_intersection stencil (e == ne: nnz)
+long long dg_value_offset(const GridDev& g, const SpaceDev& sp, long long e);
 
 // ---- finite volumes (fv.cu) -----------------------------------------------------------------------
 struct FvParams

@@ -565,7 +565,12 @@ int matop_pattern(gdtb_matop* op, const long long** rowptr, const int** colidx)
   if (!op->d_own_rowptr) {
     // pattern-free operators exist for the CG Q1 and CG Q2 element stencils: materialise the closed-form pattern
     long long nnz = 0;
-    if (op->test.K == 2)
+    GridDev whole = op->grid; // the pattern is the global one even when the operator holds a slab of its rows
+    whole.layer_lo = 0;
+    whole.layer_hi = whole.n[whole.d - 1];
+    if (op->test.kind == GDTB_SPACE_DG)
+      GDTB_TRY(pattern_structured_dg(op->ctx->launch, whole, op->test, &op->d_own_rowptr, &op->d_own_colidx, &nnz));
+    else if (op->test.K == 2)
       GDTB_TRY(pattern_structured_cg_q2(op->ctx->launch, op->grid, op->test, &op->d_own_rowptr, &op->d_own_colidx, &nnz));
     else
       GDTB_TRY(pattern_structured_cg_q1(op->ctx->launch, op->grid, op->test, &op->d_own_rowptr, &op->d_own_colidx, &nnz));
@@ -574,6 +579,17 @@ int matop_pattern(gdtb_matop* op, const long long** rowptr, const int** colidx)
   *colidx = op->d_own_colidx;
   return GDTB_OK;
 }
+
+} // namespace
+
+namespace gdtb {
+int internal_matop_pattern(gdtb_matop* op, const long long** rowptr, const int** colidx)
+{
+  return matop_pattern(op, rowptr, colidx);
+}
+} // namespace gdtb
+
+namespace {
 
 int matop_csr(gdtb_matop* op, CsrView& A)
 {

@@ -389,7 +389,7 @@ class SlabAssembly:
         ctx = space.grid.ctx
         capi.check(lib.gdtb_matop_create(ctx._h, space._h, space._h, None, C.byref(self.op_h)))
         capi.check(lib.gdtb_matop_set_slab(self.op_h, self.begin, self.end))
-        if with_functional:  # the fused right-hand side exists for CG Q1 (the Q2 path assembles the matrix only)
+        if with_functional:
             capi.check(lib.gdtb_vecfun_create(ctx._h, space._h, C.byref(self.fun_h)))
             capi.check(lib.gdtb_vecfun_set_slab(self.fun_h, self.begin, self.end))
         rb, re_, vo = C.c_int64(), C.c_int64(), C.c_int64()
@@ -408,6 +408,14 @@ class SlabAssembly:
     def append(self, form):
         capi.check(capi.lib().gdtb_matop_append_element(self.op_h, C.byref(form)))
 
+    def append_coupling(self, form, filter=D.FILTER_INNER_ONCE):
+        """DG spaces: inner-intersection forms (the neighbour across a slab face enters through its index, geometry and
+        coefficients only -- no exchange)"""
+        capi.check(capi.lib().gdtb_matop_append_coupling(self.op_h, C.byref(form), filter))
+
+    def append_boundary(self, form):
+        capi.check(capi.lib().gdtb_matop_append_boundary(self.op_h, C.byref(form), D.FILTER_ALL_BOUNDARY))
+
     def append_rhs(self, form):
         capi.check(capi.lib().gdtb_vecfun_append_element(self.fun_h, C.byref(form)))
 
@@ -416,7 +424,7 @@ class SlabAssembly:
         if not self.fun_h.value:
             capi.check(capi.lib().gdtb_assemble_host(self.op_h, None, capi.dptr(values), None))
             return values, None
-        vector = np.empty(self.row_end - self.row_begin)
+        vector = np.empty(sum(re_ - rb for rb, re_, _, _ in self.row_ranges))  # the owned rows, range after range
         capi.check(capi.lib().gdtb_assemble_host(self.op_h, self.fun_h, capi.dptr(values), capi.dptr(vector)))
         return values, vector
 

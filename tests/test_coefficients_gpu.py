@@ -276,3 +276,84 @@ def test_slab_owner_computes_rows_variable_coefficients(gdt, ctx, oracle, order,
         lib.gdtb_matop_destroy(op_h)
     assert not np.isnan(got_v).any()
     assert rel_err(got_v, ref_v) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# slabs of element-owned rows (DG: BASELINE config 3 on several GPUs) and right-hand sides on slabs of any space
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,cuts", [([7], [0, 3, 7]), ([6, 5], [0, 2, 5]), ([5, 4], [0, 1, 2, 3, 4]), ([4, 3, 5], [0, 2, 5])])
+@pytest.mark.parametrize("coefficients", ["const", "elem", "analytic"])
+def test_slab_dg_swipdg_matrix_and_rhs(gdt, ctx, oracle, n, cuts, coefficients):
+    """SWIPDG on slabs of element layers: rows are element-owned, the coupling with the element across a slab face
+    needs its index, geometry and coefficients only -- every rank's rows are complete without any exchange (factorised
+    kernels for constant / element-wise coefficients, quadrature-faithful kernel otherwise), pattern-free operator"""
+    from dune_gdt_b200 import parallel
+
+    gdesc = D.grid_desc(-1.0, 1.0, n)
+    if coefficients == "const":
+        kappa = omega = 1.5
+    elif coefficients == "elem":
+        kappa = D.fn_elem(np.random.default_rng(SEED).uniform(0.5, 2.0, int(np.prod(n))))
+        omega = D.fn_elem(np.random.default_rng(SEED + 1).uniform(0.5, 2.0, int(np.prod(n))))
+    else:
+        kappa = omega = D.fn_builtin(D.BUILTIN_QUADRATIC, 2, 1.0, 0.5)
+    el, co, bo = swipdg(kappa=kappa, omega=omega)
+    force = D.fn_builtin(D.BUILTIN_COS_PRODUCT, 2, 0.5 * np.pi**2, 0.5 * np.pi)
+    rp, ci = oracle.pattern(gdesc, (DG, 1), stencil=D.STENCIL_ELEMENT_AND_INTERSECTION)
+    ref_v, ref_b = oracle.assemble(gdesc, DG, 1, rp, ci, [el], [co], [bo], [source(force)])
+    space = make_space(gdt, ctx, gdesc, DG, 1)
+    got_v, got_b = np.full_like(ref_v, np.nan), np.full_like(ref_b, np.nan)
+    world = len(cuts) - 1
+    for rank in range(world):
+        slab = parallel.SlabAssembly(space, rank, world)
+        # the test's cuts instead of the even split
+        lib = gdt.capi.lib()
+        gdt.capi.check(lib.gdtb_matop_set_slab(slab.op_h, cuts[rank], cuts[rank + 1]))
+        gdt.capi.check(lib.gdtb_vecfun_set_slab(slab.fun_h, cuts[rank], cuts[rank + 1]))
+        rb, re_, vo = C.c_int64(), C.c_int64(), C.c_int64()
+        gdt.capi.check(lib.gdtb_matop_local_rows(slab.op_h, C.byref(rb), C.byref(re_), C.byref(vo)))
+        nnz = lib.gdtb_matop_local_nnz(slab.op_h)
+        assert vo.value == rp[rb.value] and nnz == rp[re_.value] - rp[rb.value]
+        slab.append(el)
+        slab.append_coupling(co)
+        slab.append_boundary(bo)
+        slab.append_rhs(source(force))
+        assert lib.gdtb_matop_plan(slab.op_h).decode() == "dg_gather"
+        v, b = np.empty(nnz), np.empty(re_.value - rb.value)
+        gdt.capi.check(lib.gdtb_assemble_host(slab.op_h, slab.fun_h, gdt.capi.dptr(v), gdt.capi.dptr(b)))
+        got_v[vo.value : vo.value + nnz] = v
+        got_b[rb.value : re_.value] = b
+    assert not np.isnan(got_v).any() and not np.isnan(got_b).any()
+    assert rel_err(got_v, ref_v) <= TOL and rel_err(got_b, ref_b) <= TOL
+
+
+@pytest.mark.parametrize("n,cuts", [([4, 3, 6], [0, 2, 6]), ([5, 6], [0, 2, 6])])
+def test_slab_q2_rhs_on_owned_row_ranges(gdt, ctx, oracle, n, cuts):
+    """CG Q2 right-hand side on slabs: the owned rows are one range per sub-entity group, held back to back"""
+    from dune_gdt_b200 import parallel
+
+    gdesc = D.grid_desc(-1.0, 1.0, n)
+    src = D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 2.0, 1.3)
+    rp, ci = oracle.pattern(gdesc, (CG, 2))
+    _, ref_b = oracle.assemble(gdesc, CG, 2, rp, ci, rhs_forms=[source(src)])
+    space = make_space(gdt, ctx, gdesc, CG, 2)
+    got = np.full_like(ref_b, np.nan)
+    world = len(cuts) - 1
+    lib = gdt.capi.lib()
+    for rank in range(world):
+        slab = parallel.SlabAssembly(space, rank, world)
+        gdt.capi.check(lib.gdtb_matop_set_slab(slab.op_h, cuts[rank], cuts[rank + 1]))
+        gdt.capi.check(lib.gdtb_vecfun_set_slab(slab.fun_h, cuts[rank], cuts[rank + 1]))
+        nr = C.c_int32()
+        gdt.capi.check(lib.gdtb_matop_local_row_ranges(slab.op_h, 0, None, None, None, None, C.byref(nr)))
+        rbs, res = (C.c_int64 * nr.value)(), (C.c_int64 * nr.value)()
+        gdt.capi.check(lib.gdtb_matop_local_row_ranges(slab.op_h, nr.value, rbs, res, None, None, C.byref(nr)))
+        slab.append_rhs(source(src))
+        total = sum(res[r] - rbs[r] for r in range(nr.value))
+        b = np.empty(total)
+        gdt.capi.check(lib.gdtb_assemble_host(None, slab.fun_h, None, gdt.capi.dptr(b)))
+        at = 0
+        for r in range(nr.value):
+            got[rbs[r] : res[r]] = b[at : at + res[r] - rbs[r]]
+            at += res[r] - rbs[r]
+    assert not np.isnan(got).any() and rel_err(got, ref_b) <= TOL
