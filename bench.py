@@ -388,7 +388,8 @@ def sharded_workload(env, workload, steps, warmup):
       c4-p2p / c4-weak-p2p   the same with the ghost rows handed over INSIDE the kernel (NVLink peer stores)
       c3 / c3-weak 2D SWIPDG DG-Q1 2048^2 (BASELINE.json configs[2]), y-slabs of element-owned rows, no collective
       c2-halo      the headline workload with the interface-row halo partition (own elements only + one message per
-                   slab face + add) instead of the ghost-layer recompute, weak scaling"""
+                   slab face + add) instead of the ghost-layer recompute, weak scaling
+      c2-halo-p2p  the same with the interface rows handed over inside the gather kernel (peer stores + counters)"""
     torch, gdt = env.torch, env.gdt
     from dune_gdt_b200 import descriptors as D
     from dune_gdt_b200 import parallel
@@ -472,18 +473,24 @@ def sharded_workload(env, workload, steps, warmup):
                      "weak" if workload == "c4-weak" else "strong",
                      {"workload": f"FV linear advection, {n} x {ny} periodic YaspGrid (BASELINE.json configs[3]), fused apply + Euler update",
                       "partition": f"y-slabs x{world}, one ghost row per side per step over NCCL send/recv, interior overlapped"})
-    if workload == "c2-halo":
+    if workload in ("c2-halo", "c2-halo-p2p"):
         h = 2.0 / NX
         grid = gdt.make_cube_grid(ctx, [-1.0, -1.0, -1.0], [1.0, 1.0, -1.0 + NX * world * h], [NX, NX, NX * world])
         space = gdt.make_continuous_lagrange_space(grid, 1)
-        halo = parallel.HaloSlabAssembly(space, rank, world)
+        p2p = workload == "c2-halo-p2p"
+        halo = parallel.HaloSlabAssembly(space, rank, world, p2p=p2p)
         lap, rhs = forms()
         halo.append(lap)
         halo.append_rhs(rhs)
-        return timed(halo.assemble_device, NX**3 * world, METRIC, UNIT, "weak",
-                     {"workload": "3D Q1 Laplace + RHS assembly, 256^3 per GPU (BASELINE.json configs[1])",
-                      "partition": f"z-slabs x{world}, own elements only + interface-row halo (one layer of rows per slab face)",
-                      "halo_bytes_per_face": 8 * (halo.mat_layout[2] + halo.vec_layout[2])})
+        how = ("handed over INSIDE the gather kernel (NVLink peer stores + counters, no host-launched collective)" if p2p
+               else "one NCCL message per slab face + add kernel, stream-ordered")
+        rec = timed(halo.assemble_device, NX**3 * world, METRIC, UNIT, "weak",
+                    {"workload": "3D Q1 Laplace + RHS assembly, 256^3 per GPU (BASELINE.json configs[1])",
+                     "partition": f"z-slabs x{world}, own elements only + interface-row halo (one layer of rows per slab face) {how}",
+                     "halo_bytes_per_face": 8 * (halo.mat_layout[2] + halo.vec_layout[2])})
+        halo.check()
+        halo.close()
+        return rec
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -738,7 +745,7 @@ def run_product(args):
         # the multi-GPU rows that DO communicate, so that the scaling record carries them next to the headline
         extra = {"multi_gpu": {}}
         sub_steps = max(10, min(args.steps, 50))
-        for wl in ("c5", "c3", "c2-halo", "c4-weak-p2p", "c4-weak"):
+        for wl in ("c5", "c3", "c2-halo-p2p", "c2-halo", "c4-weak-p2p", "c4-weak"):
             try:
                 extra["multi_gpu"][wl] = sharded_workload(env, wl, sub_steps, args.warmup)
             except Exception as exc:  # a failed side workload must not take the headline line with it
@@ -774,7 +781,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c3", "c3-weak", "c4", "c4-weak", "c4-p2p", "c4-weak-p2p", "c2-halo"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c3", "c3-weak", "c4", "c4-weak", "c4-p2p", "c4-weak-p2p", "c2-halo", "c2-halo-p2p"],
                     help="c2 (default, the headline line); c5 / c4 / c2-halo: the other multi-GPU rows, see run_sharded_workload")
     args = ap.parse_args()
     if args.impl == "reference":

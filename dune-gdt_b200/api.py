@@ -37,12 +37,15 @@ class Context:
         self._h = C.c_void_p()
         check(lib().gdtb_ctx_create(device, C.byref(self._h)))
         self.device = device
+        self.stream_handle = None  # the cudaStream_t handed to set_stream (None: the context's own stream)
 
     def synchronize(self):
         check(lib().gdtb_ctx_synchronize(self._h))
 
     def set_stream(self, cuda_stream):
+        """run the library on a caller-provided cudaStream_t (0 / None: back to the context's own stream)"""
         check(lib().gdtb_ctx_set_stream(self._h, C.c_void_p(cuda_stream)))
+        self.stream_handle = cuda_stream or None
 
     @property
     def launch_count(self):

@@ -148,6 +148,19 @@ __device__ __forceinline__ void q1_decode(unsigned v, const FastDiv& dx, const F
 
 constexpr int Q1G_ROWS = 256; // rows (vertices) per work item = threads per CTA
 
+// bounded wait for a counter another GPU raises in this GPU's memory (system-scope acquire); gives up after ~1 s
+__device__ __forceinline__ void q1_wait_counter(const int* counter, int expect, int* timeout_flag)
+{
+  for (long long spin = 0; spin < (1LL << 23); ++spin) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v - expect >= 0)
+      return;
+    __nanosleep(100);
+  }
+  atomicExch(timeout_flag, 1);
+}
+
 // Contribution of ONE element (offset (ox, oy, oz) around the vertex) to the vertex' row: the row i = (2^D-1) ^ o of
 // its local matrix L_e = sum_g scale_g * coefficient_g(e) * sum_{r,c} (1/h_r)(1/h_c) |det J_e| M_g[r][c] is added to
 // the stencil accumulators.  P0 / P1 receive the ansatz vertices with s_last = 0 / 1 (D == 3: the two z-planes the
@@ -270,7 +283,7 @@ __device__ __forceinline__ int q1_store_plane(double* __restrict__ row, const do
 // contributions per stencil column in a fixed order (deterministic, no atomics).
 // CELLDATA = false: no per-element coefficient / source arrays and no per-cell right-hand-side terms are in play
 // (constant coefficients, separable analytic source): the element index is never formed.
-template <int D, int NG, int KIND0, bool ACCUMULATE, bool CELLDATA>
+template <int D, int NG, int KIND0, bool ACCUMULATE, bool CELLDATA, bool P2P = false>
 __global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLACE_SCALAR && !CELLDATA) ? Q1G_MIN_BLOCKS : 2)
     k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values, double* __restrict__ rhs,
                 long long nrows, int nitems, int stage_doubles, int nbuf)
@@ -284,11 +297,27 @@ __global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_L
   const bool want_values = NG > 0 && values != nullptr;
   int buf = 0;
 
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    // peer-memory halo: highest rows first (the top layer is what the neighbour above waits for), the bottom layer --
+    // which waits for the neighbour below -- last
+    const int item = P2P ? nitems - 1 - it : it;
     // ---- per item (uniform over the CTA): the CSR segment -------------------------------------------------
     const long long l0 = (long long)item * Q1G_ROWS; // first local row
     const int nr = (int)min((long long)Q1G_ROWS, nrows - l0);
     const unsigned r0 = (unsigned)(p.row_offset + l0); // first global row (= vertex index)
+    const Q1HaloP2p& H = p.halo;
+    const long long top_row = nrows - H.layer_rows;
+    const bool recv_item = P2P && H.has_lower && l0 < H.layer_rows;
+    const bool send_item = P2P && H.has_upper && l0 + nr > top_row;
+    if (P2P && (recv_item || send_item)) {
+      if (threadIdx.x == 0) {
+        if (recv_item)
+          q1_wait_counter(H.my_flags + 0, H.expect_data, H.my_flags + 2); // the lower neighbour's layer has arrived
+        if (send_item)
+          q1_wait_counter(H.my_flags + 1, H.expect_ack, H.my_flags + 2);  // the neighbour has consumed this buffer's previous content
+      }
+      __syncthreads();
+    }
     long long start = 0;
     int seg = 0, phase = 0;
     unsigned start32 = 0;
@@ -494,12 +523,36 @@ __global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_L
           bsum += t2;
         }
         const long long r = l0 + threadIdx.x;
+        if (P2P && recv_item && r < H.layer_rows)
+          bsum += __ldcg(H.recv_rhs + r); // partial sum of the interface row from the slab below
+        if (P2P && send_item && r >= top_row)
+          H.peer_rhs[r - top_row] = bsum; // partial sum of a row the slab above owns
         if (ACCUMULATE)
           rhs[r] += bsum;
         else
           rhs[r] = bsum;
       }
     }
+
+    if (P2P && want_values && (recv_item || send_item)) {
+      __syncthreads(); // the item's rows are complete in shared memory
+      const long long top_value = (long long)p.halo.layer_values; // values of one interface layer
+      if (recv_item) {
+        // add the partial rows that arrived from below (bottom layer = local values [0, layer_values))
+        const int n = (int)min((long long)seg, top_value - start);
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+          stage[i] += __ldcg(H.recv_values + start + i);
+      }
+      if (send_item) {
+        // the top layer's partial rows go to the owner: local values [nnz_local - layer_values, nnz_local)
+        const long long first = (long long)(p.halo_top_value_start);
+        const int skip = (int)max(0LL, first - start);
+        for (int i = threadIdx.x + skip; i < seg; i += blockDim.x)
+          H.peer_values[start + i - first] = stage[i];
+      }
+    }
+    if (P2P && send_item)
+      __threadfence_system(); // peer stores (values and right-hand side) before the counter
 
     if (want_values) {
       if (ACCUMULATE) {
@@ -529,6 +582,16 @@ __global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_L
         }
         __syncthreads();
         buf = nbuf == 1 ? 0 : buf ^ 1;
+      }
+    }
+    if (P2P && (recv_item || send_item)) {
+      if (!want_values || ACCUMULATE)
+        __syncthreads(); // every thread's peer stores / receive-buffer reads are done (the value path synchronised above)
+      if (threadIdx.x == 0) {
+        if (send_item)
+          atomicAdd_system(H.peer_flags + 0, 1); // one more item of this step's interface layer is in place
+        if (recv_item)
+          atomicAdd_system(H.lower_flags + 1, 1); // this item no longer needs the receive buffer
       }
     }
   }
@@ -639,7 +702,11 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
   static const int nbuf_env = std::getenv("GDTB_Q1_NBUF") ? std::atoi(std::getenv("GDTB_Q1_NBUF")) : 0;
   const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : Q1G_DEFAULT_NBUF);
   const size_t smem = with_values ? (size_t)nbuf * stage_doubles * sizeof(double) : 16;
-  auto kern = accumulate ? k_q1_gather<D, NG, KIND0, true, CELLDATA> : k_q1_gather<D, NG, KIND0, false, CELLDATA>;
+  if (accumulate && p.halo_p2p)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q1_gather: the peer-memory halo works in overwrite mode");
+  auto kern = accumulate ? k_q1_gather<D, NG, KIND0, true, CELLDATA, false>
+                         : (p.halo_p2p ? k_q1_gather<D, NG, KIND0, false, CELLDATA, true>
+                                       : k_q1_gather<D, NG, KIND0, false, CELLDATA, false>);
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
@@ -1054,6 +1121,15 @@ int launch_q1_gather_qp(Launch& L, const Q1QpParams& p, double* values, bool acc
     case 3: return launch_q1_qp_d<3>(L, p, values, accumulate);
     default: return fail(GDTB_ERR_INVALID_ARGUMENT, "q1_gather_qp: dimension must be 1, 2 or 3");
   }
+}
+
+int q1_halo_items(long long layer_rows, long long layers, bool top)
+{
+  const long long nrows = (layers + 1) * layer_rows; // the slab's own vertex layers plus the interface layer on top
+  const long long nitems = (nrows + Q1G_ROWS - 1) / Q1G_ROWS;
+  if (!top)
+    return (int)std::min(nitems, (layer_rows + Q1G_ROWS - 1) / Q1G_ROWS); // items with a row below layer_rows
+  return (int)(nitems - (nrows - layer_rows) / Q1G_ROWS);                  // items with a row in the last layer
 }
 
 int q1_host_rowptr(const GridDev& g, const SpaceDev& sp, long long* rowptr)

@@ -1270,6 +1270,8 @@ int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* a
   return GDTB_OK;
 }
 
+static void halo_p2p_release(gdtb_matop* op);
+
 int gdtb_matop_clear_forms(gdtb_matop* op)
 {
   if (!op)
@@ -1289,6 +1291,7 @@ int gdtb_matop_destroy(gdtb_matop* op)
   if (!op)
     return GDTB_OK;
   gdtb_matop_clear_forms(op);
+  halo_p2p_release(op);
   if (op->owns_values)
     cudaFree(op->d_values);
   cudaFree(op->d_forms);
@@ -1480,6 +1483,107 @@ int gdtb_matop_halo_layout(const gdtb_matop* op, int64_t* recv_offset, int64_t* 
 }
 
 int gdtb_vecfun_set_slab_halo(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end);
+
+// ---- peer-memory interface-row halo ---------------------------------------------------------------------------
+static void halo_p2p_release(gdtb_matop* op)
+{
+  if (op->halo_opened_upper) {
+    cudaIpcCloseMemHandle(op->halo_peer_recv);
+    cudaIpcCloseMemHandle(op->halo_peer_flags);
+  }
+  if (op->halo_opened_lower)
+    cudaIpcCloseMemHandle(op->halo_lower_flags);
+  cudaFree(op->halo_recv);
+  cudaFree(op->halo_flags);
+  op->halo_recv = op->halo_peer_recv = nullptr;
+  op->halo_flags = op->halo_peer_flags = op->halo_lower_flags = nullptr;
+  op->halo_opened_lower = op->halo_opened_upper = op->halo_connected = false;
+  op->halo_step = 0;
+}
+
+static void halo_layer_sizes(const gdtb_matop* op, long long& layer_rows, long long& layer_values)
+{
+  layer_rows = q1_layer_rows(op->grid);
+  // interface layers are interior along the last direction: every one has the same CSR shape
+  layer_values = q1_layer_rowptr(op->grid, 2) - q1_layer_rowptr(op->grid, 1);
+}
+
+int gdtb_halo_p2p_alloc(gdtb_matop* op, void* handles)
+{
+  if (!op || !handles)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_halo_p2p_alloc: NULL argument");
+  GDTB_TRY(check_ctx(op->ctx));
+  if (!op->slab || !op->halo)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_halo_p2p_alloc: call gdtb_matop_set_slab_halo first");
+  if (op->grid.n[op->grid.d - 1] < 2)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_halo_p2p_alloc: the grid has no interior vertex layer");
+  halo_p2p_release(op);
+  long long layer_rows, layer_values;
+  halo_layer_sizes(op, layer_rows, layer_values);
+  const size_t bytes = sizeof(double) * 2 * (size_t)(layer_values + layer_rows);
+  if (cudaMalloc(&op->halo_recv, bytes) != cudaSuccess || cudaMalloc(&op->halo_flags, 64 * sizeof(int)) != cudaSuccess) {
+    halo_p2p_release(op);
+    return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (peer-memory halo buffers)");
+  }
+  GDTB_CUDA(cudaMemset(op->halo_recv, 0, bytes));
+  GDTB_CUDA(cudaMemset(op->halo_flags, 0, 64 * sizeof(int)));
+  cudaIpcMemHandle_t h[2];
+  if (cudaIpcGetMemHandle(&h[0], op->halo_recv) != cudaSuccess || cudaIpcGetMemHandle(&h[1], op->halo_flags) != cudaSuccess) {
+    const std::string why = cudaGetErrorString(cudaGetLastError());
+    halo_p2p_release(op);
+    return fail(GDTB_ERR_CUDA, "cudaIpcGetMemHandle failed: " + why);
+  }
+  std::memcpy(handles, h, sizeof(h));
+  return GDTB_OK;
+}
+
+int gdtb_halo_p2p_connect(gdtb_matop* op, const void* lower_handles, int64_t lower_layers, const void* upper_handles)
+{
+  if (!op || !op->halo_recv)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_halo_p2p_connect: call gdtb_halo_p2p_alloc first");
+  GDTB_TRY(check_ctx(op->ctx));
+  const long long n_last = op->grid.n[op->grid.d - 1];
+  const bool has_lower = op->grid.layer_lo > 0, has_upper = op->grid.layer_hi < n_last;
+  if ((has_lower && (!lower_handles || lower_layers < 1)) || (has_upper && !upper_handles))
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_halo_p2p_connect: a neighbour's handles are missing");
+  if (has_upper) {
+    cudaIpcMemHandle_t h[2];
+    std::memcpy(h, upper_handles, sizeof(h));
+    void* ptr[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i)
+      if (cudaIpcOpenMemHandle(&ptr[i], h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        return fail(GDTB_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError()));
+    op->halo_peer_recv = static_cast<double*>(ptr[0]);
+    op->halo_peer_flags = static_cast<int*>(ptr[1]);
+    op->halo_opened_upper = true;
+  }
+  if (has_lower) {
+    cudaIpcMemHandle_t h[2];
+    std::memcpy(h, lower_handles, sizeof(h));
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, h[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+      return fail(GDTB_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError()));
+    op->halo_lower_flags = static_cast<int*>(ptr);
+    op->halo_opened_lower = true;
+    op->halo_lower_layers = lower_layers;
+  }
+  op->halo_connected = true;
+  op->halo_step = 0;
+  return GDTB_OK;
+}
+
+int gdtb_halo_p2p_check(gdtb_matop* op)
+{
+  if (!op || !op->halo_flags)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_halo_p2p_check: no peer-memory halo");
+  GDTB_TRY(check_ctx(op->ctx));
+  GDTB_CUDA(cudaStreamSynchronize(op->ctx->launch.stream));
+  int flags[4] = {0, 0, 0, 0};
+  GDTB_CUDA(cudaMemcpy(flags, op->halo_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+  if (flags[2])
+    return fail(GDTB_ERR_OPERATOR, "peer-memory halo: a wait for the neighbour's counter timed out");
+  return GDTB_OK;
+}
 
 int gdtb_vector_add(gdtb_ctx* ctx, double* d_y, const double* d_x, int64_t n)
 {
@@ -1985,6 +2089,39 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     GDTB_TRY(build_q1_params(op_fast ? op : nullptr, fun_fast ? fun : nullptr, p));
     if (fun_fast)
       GDTB_TRY(q1_rhs_params(fun, p));
+    const bool halo_p2p = op_fast && op->halo && op->halo_connected;
+    if (halo_p2p) {
+      if (fun && !fun_fast)
+        return fail(GDTB_ERR_NOT_IMPLEMENTED, "peer-memory halo: the functional must take the CG Q1 gather path");
+      const long long n_last = op->grid.n[op->grid.d - 1];
+      long long layer_rows, layer_values;
+      halo_layer_sizes(op, layer_rows, layer_values);
+      Q1HaloP2p& H = p.halo;
+      p.halo_p2p = 1;
+      p.halo_top_value_start = op->nnz_local - layer_values;
+      H.has_lower = op->grid.layer_lo > 0;
+      H.has_upper = op->grid.layer_hi < n_last;
+      H.layer_rows = layer_rows;
+      H.layer_values = layer_values;
+      const long long s = op->halo_step, par = s & 1, stride = layer_values + layer_rows;
+      H.recv_values = op->halo_recv + par * stride;
+      H.recv_rhs = H.recv_values + layer_values;
+      H.my_flags = op->halo_flags;
+      if (H.has_upper) {
+        H.peer_values = op->halo_peer_recv + par * stride;
+        H.peer_rhs = H.peer_values + layer_values;
+        H.peer_flags = op->halo_peer_flags;
+        // the rank above acknowledges every bottom item of every step; the buffer of this parity was last used at
+        // step s - 2, i.e. steps 0 .. s - 2 must have been consumed
+        const long long n_bottom = q1_halo_items(layer_rows, 1, false);
+        H.expect_ack = (int)(std::max<long long>(s - 1, 0) * n_bottom);
+      }
+      if (H.has_lower) {
+        H.lower_flags = op->halo_lower_flags;
+        H.expect_data = (int)((s + 1) * q1_halo_items(layer_rows, op->halo_lower_layers, true));
+      }
+      op->halo_step++;
+    }
     GDTB_TRY(launch_q1_gather(L, p, op_fast ? op->d_values : nullptr, fun_fast ? fun->d_vec : nullptr, accumulate));
   }
 

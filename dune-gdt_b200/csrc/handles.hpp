@@ -102,6 +102,14 @@ struct gdtb_matop
   long long value_offset, nnz_local;
   long long row_lo, row_hi, elem_lo, elem_hi; // vertex / element layers along the last direction
   bool halo = false; // interface-row halo partition: rows of one extra (interface) layer, own elements only
+  // peer-memory halo (gdtb_halo_p2p_*): own receive buffers (two step parities) + flags, the neighbours' opened via CUDA IPC
+  double* halo_recv = nullptr;
+  int* halo_flags = nullptr;
+  double* halo_peer_recv = nullptr; // upper neighbour's receive buffers
+  int* halo_peer_flags = nullptr;   // upper neighbour's flags
+  int* halo_lower_flags = nullptr;  // lower neighbour's flags
+  bool halo_opened_lower = false, halo_opened_upper = false, halo_connected = false;
+  long long halo_step = 0, halo_lower_layers = 0;
   // CG Q2 slabs: one row range per sub-entity group of the MCMG numbering (d_values holds them back to back)
   int n_ranges = 0;
   long long range_row_begin[8], range_row_end[8], range_value_offset[8], range_count[8];

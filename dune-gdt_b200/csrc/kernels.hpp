@@ -131,6 +131,26 @@ inline FastDiv make_fast_div(unsigned d)
   return f;
 }
 
+// Interface-row halo handed over INSIDE the gather kernel (multi-GPU, one process per GPU, buffers opened through CUDA
+// IPC): the slab walks its own elements only; the rows of its top vertex layer are partial sums that belong to the
+// slab above -- the work items of that layer are computed first and stored straight into the neighbour's receive
+// buffer (NVLink peer stores) followed by a counter increment in the neighbour's memory; the items of the bottom layer
+// are computed last, wait for the lower neighbour's counter and add what arrived before their rows leave the SM.
+struct Q1HaloP2p
+{
+  int has_lower, has_upper;
+  long long layer_rows, layer_values; // one interface layer: vertices, CSR values
+  double* peer_values;                // upper neighbour's receive buffer (this step's parity)
+  double* peer_rhs;
+  int* peer_flags;                    // upper neighbour: [0] data counter
+  const double* recv_values;          // own receive buffer (this step's parity)
+  const double* recv_rhs;
+  int* my_flags;                      // [0] data counter (raised by the lower neighbour), [1] acknowledgements (by the upper), [2] timeout
+  int* lower_flags;                   // lower neighbour's flags: [1] is raised when a bottom item has consumed its data
+  int expect_data;                    // data counter value that marks this step's layer as complete
+  int expect_ack;                     // acknowledgements needed before this step's parity buffer may be overwritten
+};
+
 struct Q1GatherParams
 {
   GridDev g;
@@ -157,9 +177,15 @@ struct Q1GatherParams
   // element layers [elem_lo, elem_hi) (the owned ones plus the ghost layer below)
   long long row_lo, row_hi;
   long long elem_lo, elem_hi;
+  int halo_p2p; // the interface-row halo travels inside the kernel (halo below)
+  long long halo_top_value_start; // local position of the first value of the top (interface) layer
+  Q1HaloP2p halo;
 };
 
 int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate);
+// work items (chunks of Q1G_ROWS rows) that touch the first / last vertex layer of a slab holding `layers` layers of
+// `layer_rows` rows: the number of counter increments per step in the peer-memory halo
+int q1_halo_items(long long layer_rows, long long layers, bool top);
 int launch_q1_axis_tables(Launch& L, const GridDev& g, double* const* tabs, long long inv);
 
 // builds the separable right-hand-side tables B_k[i_k] for a product-separable built-in source

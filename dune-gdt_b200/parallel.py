@@ -446,11 +446,14 @@ class SlabAssembly:
                 capi.lib().gdtb_vecfun_destroy(self.fun_h)
 
 
-def exchange_interface_rows(local, recv_offset, send_offset, count, rank, world, add=None, group=None):
+def exchange_interface_rows(local, recv_offset, send_offset, count, rank, world, add=None, group=None,
+                            stream_ordered=False):
     """interface-row halo of the element-partitioned assembly: the last `count` entries at `send_offset` of `local`
     (the partial sums of the interface layer owned by rank + 1) are sent up, the layer arriving from rank - 1 is added
     to the `count` entries at `recv_offset`.  `local` is a 1D torch tensor (CUDA for NCCL, CPU for gloo); `add(y, x)`
-    performs y += x (default: torch).  Returns the received buffer (None on rank 0)."""
+    performs y += x (default: torch).  `stream_ordered`: the producer of `local`, the transfer and `add` all run on
+    torch's current stream (the library context was given that stream): nothing synchronises with the host.  Returns the
+    received buffer (None on rank 0)."""
     import torch
     import torch.distributed as dist
 
@@ -462,9 +465,9 @@ def exchange_interface_rows(local, recv_offset, send_offset, count, rank, world,
         ops.append(dist.P2POp(dist.irecv, recv, rank - 1, group))
     if ops:
         for r in dist.batch_isend_irecv(ops):
-            r.wait()
-    if local.is_cuda:
-        # NCCL completion is stream-ordered on torch's stream; the add may run on the library's stream
+            r.wait()  # NCCL: orders torch's current stream after the transfer (no host synchronisation); gloo: blocks
+    if local.is_cuda and not stream_ordered:
+        # the add may run on another stream than torch's current one
         torch.cuda.current_stream(local.device).synchronize()
     if recv is not None:
         target = local[recv_offset:recv_offset + count]
@@ -481,11 +484,13 @@ class HaloSlabAssembly:
     one NCCL message per slab face.  After `assemble_device()` the owned rows of this rank are the first
     `nnz_owned` values / `rows_owned` vector entries of the device buffers (same layout as `SlabAssembly`)."""
 
-    def __init__(self, space, rank, world, group=None):
+    def __init__(self, space, rank, world, group=None, p2p=False):
+        """p2p: the interface rows travel INSIDE the gather kernel (NVLink peer stores into the neighbour's receive buffer
+        + counters, gdtb_halo_p2p_*) instead of one NCCL message per slab face followed by an add kernel"""
         lib = capi.lib()
         g = space.grid.desc
         d = int(g.dim)
-        self.rank, self.world, self.group = rank, world, group
+        self.rank, self.world, self.group, self.p2p = rank, world, group, bool(p2p) and world > 1
         self.begin, self.end = slab_layers(int(g.n[d - 1]), rank, world)
         self.space = space
         self.op_h, self.fun_h = C.c_void_p(), C.c_void_p()
@@ -495,6 +500,31 @@ class HaloSlabAssembly:
         capi.check(lib.gdtb_vecfun_create(ctx._h, space._h, C.byref(self.fun_h)))
         capi.check(lib.gdtb_matop_set_slab_halo(self.op_h, self.begin, self.end))
         capi.check(lib.gdtb_vecfun_set_slab_halo(self.fun_h, self.begin, self.end))
+        if self.p2p:
+            import torch
+            import torch.distributed as dist
+
+            handles = (C.c_ubyte * (2 * 64))()
+            capi.check(lib.gdtb_halo_p2p_alloc(self.op_h, handles))
+            dev = torch.device("cuda", ctx.device)
+            mine = torch.tensor(list(bytes(handles)), dtype=torch.uint8, device=dev)
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine, group=group)
+
+            def raw(nb):
+                if nb < 0 or nb >= world:
+                    return None
+                b = bytes(every[nb].cpu().numpy().tobytes())
+                return (C.c_ubyte * len(b)).from_buffer_copy(b)
+
+            lo_h, hi_h = raw(rank - 1), raw(rank + 1)
+            lo_layers = 0
+            if rank > 0:
+                b, e = slab_layers(int(g.n[d - 1]), rank - 1, world)
+                lo_layers = e - b
+            self._keep = (lo_h, hi_h)
+            capi.check(lib.gdtb_halo_p2p_connect(self.op_h, lo_h, lo_layers, hi_h))
+            dist.barrier(group=group)  # every rank has opened its neighbours' buffers
         rb, re_, vo = C.c_int64(), C.c_int64(), C.c_int64()
         capi.check(lib.gdtb_matop_local_rows(self.op_h, C.byref(rb), C.byref(re_), C.byref(vo)))
         self.row_begin, self.value_offset = rb.value, vo.value
@@ -534,20 +564,49 @@ class HaloSlabAssembly:
         import torch
 
         lib = capi.lib()
+        if self.p2p:  # the exchange happens inside the kernel: nothing follows the walk
+            capi.check(lib.gdtb_assemble_async(self.op_h, self.fun_h, D.ASSEMBLE_OVERWRITE))
+            return self._device_views()
+        # stream-ordered when the library launches on torch's current stream (ctx.set_stream(torch stream)): the walk,
+        # the NCCL transfer and the add kernels queue up behind each other without a host round trip
+        ordered = self.ctx.stream_handle is not None and self.ctx.stream_handle == torch.cuda.current_stream().cuda_stream
         capi.check(lib.gdtb_assemble_async(self.op_h, self.fun_h, D.ASSEMBLE_OVERWRITE))
-        self.ctx.synchronize()  # the exchange runs on torch's stream
+        if not ordered:
+            self.ctx.synchronize()  # the exchange runs on torch's stream
         values, vector = self._device_views()
 
         def add(y, x):
             capi.check(lib.gdtb_vector_add(self.ctx._h, C.c_void_p(y.data_ptr()), C.c_void_p(x.data_ptr()), y.numel()))
 
-        torch.cuda.synchronize()
-        keep = [exchange_interface_rows(values, *self.mat_layout, self.rank, self.world, add, self.group),
-                exchange_interface_rows(vector, *self.vec_layout, self.rank, self.world, add, self.group)]
-        torch.cuda.synchronize()  # received layers are complete before the add kernels read them
-        self.ctx.synchronize()
+        keep = [exchange_interface_rows(values, *self.mat_layout, self.rank, self.world, add, self.group, ordered),
+                exchange_interface_rows(vector, *self.vec_layout, self.rank, self.world, add, self.group, ordered)]
+        for t in keep:
+            if t is not None and ordered:
+                t.record_stream(torch.cuda.current_stream())  # the add kernels read the receive buffers asynchronously
+        if not ordered:
+            torch.cuda.synchronize()  # received layers are complete before the add kernels read them
+            self.ctx.synchronize()
         del keep
         return values, vector
+
+    def check(self):
+        """peer-memory mode: synchronise and report a timed-out wait"""
+        if self.p2p:
+            capi.check(capi.lib().gdtb_halo_p2p_check(self.op_h))
+
+    def close(self):
+        """collective (peer-memory mode): nobody frees its receive buffers while a neighbour can still store into them"""
+        if self.p2p:
+            import torch
+            import torch.distributed as dist
+
+            self.ctx.synchronize()
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+        if self.op_h.value:
+            capi.lib().gdtb_matop_destroy(self.op_h)
+            capi.lib().gdtb_vecfun_destroy(self.fun_h)
+            self.op_h = C.c_void_p()
 
     def __del__(self):
         if getattr(self, "op_h", None) and self.op_h.value:

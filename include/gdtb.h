@@ -486,6 +486,21 @@ int gdtb_matop_set_slab_halo(gdtb_matop* op, int64_t layer_begin, int64_t layer_
 int gdtb_vecfun_set_slab_halo(gdtb_vecfun* fun, int64_t layer_begin, int64_t layer_end);
 int gdtb_matop_halo_layout(const gdtb_matop* op, int64_t* recv_offset, int64_t* send_offset, int64_t* count);
 int gdtb_vecfun_halo_layout(const gdtb_vecfun* fun, int64_t* recv_offset, int64_t* send_offset, int64_t* count);
+/* The same partition with the halo handed over INSIDE the gather kernel (one process per GPU on one NVLink / NVSwitch
+ * box) instead of a host-launched send / recv + add: the work items of the top (interface) layer are computed first and
+ * stored straight into the receive buffer of the rank above (peer stores into memory opened through CUDA IPC), each
+ * followed by a counter increment in that rank's memory; the items of the bottom layer are computed last, wait for the
+ * counter of the rank below and add what arrived before their rows leave the SM.  Receive buffers alternate between
+ * two step parities and the consumer acknowledges every step, so a rank may run ahead by at most one assembly.
+ *   1. gdtb_matop_set_slab_halo (+ gdtb_vecfun_set_slab_halo), then gdtb_halo_p2p_alloc: the rank's receive buffers and
+ *      counters + 2 IPC handles to be sent to both neighbours;
+ *   2. gdtb_halo_p2p_connect with the handles of the rank below / above (NULL: none) and the number of element layers of
+ *      the rank below; all ranks must have connected before any of them assembles;
+ *   3. gdtb_assemble[_async](op, fun, OVERWRITE) as usual -- no exchange call follows; gdtb_halo_p2p_check
+ *      synchronises and reports a timed-out wait (GDTB_ERR_OPERATOR). */
+int gdtb_halo_p2p_alloc(gdtb_matop* op, void* handles /* 2 * GDTB_IPC_HANDLE_BYTES */);
+int gdtb_halo_p2p_connect(gdtb_matop* op, const void* lower_handles, int64_t lower_layers, const void* upper_handles);
+int gdtb_halo_p2p_check(gdtb_matop* op);
 /* d_y[0..n) += d_x[0..n) on the context's stream (enqueue only) */
 int gdtb_vector_add(gdtb_ctx* ctx, double* d_y, const double* d_x, int64_t n);
 int64_t gdtb_matop_local_nnz(const gdtb_matop* op);

@@ -126,6 +126,21 @@ def _worker(rank, world, port, out_dir):
         assert halo.value_offset == slab.value_offset and halo.nnz_owned == slab.nnz_local
         assert np.abs(hv[:halo.nnz_owned] - seg).max() / np.abs(v_ref).max() <= 1e-12
         assert np.abs(hb[:halo.rows_owned] - b_ref[slab.row_begin:slab.row_end]).max() / np.abs(b_ref).max() <= 1e-12
+        # ---- ... and with the interface rows handed over INSIDE the gather kernel (peer stores + counters): several
+        # back-to-back assemblies without any host synchronisation exercise both buffer parities and the acknowledgements
+        for forms in ([lap], [D.form(D.integrand(D.INT_LAPLACE, diffusion=0.75))]):
+            p2p = parallel.HaloSlabAssembly(space, rank, world, p2p=True)
+            p2p.append(forms[0])
+            p2p.append_rhs(rhs)
+            ref_v, _ = oracle.assemble(gd, D.SPACE_CG, 1, rp, ci, forms)
+            for _ in range(5):
+                pv, pb = p2p.assemble_device()
+            p2p.check()
+            pv, pb = pv.cpu().numpy(), pb.cpu().numpy()
+            ref_seg = ref_v[slab.value_offset:slab.value_offset + slab.nnz_local]
+            assert np.abs(pv[:p2p.nnz_owned] - ref_seg).max() / np.abs(ref_v).max() <= 1e-12
+            assert np.abs(pb[:p2p.rows_owned] - b_ref[slab.row_begin:slab.row_end]).max() / np.abs(b_ref).max() <= 1e-12
+            p2p.close()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
