@@ -193,6 +193,32 @@ def fv_extra(gdt, ctx, torch, hbm_gbs, peak_src):
                      "roofline": {"bound": "hbm", "achieved": bytes_per / (per * 1e-3) / 1e9, "peak": hbm_gbs,
                                   "unit": "GB/s", "frac": bytes_per / (per * 1e-3) / 1e9 / hbm_gbs,
                                   "peak_source": peak_src}}
+    # the caller of the apply: one SSP3 Runge-Kutta step (tools/timestepper/explicit-rungekutta.hh:237-270), stages fused
+    # into the applies (9 vector passes) against separate axpy passes (18)
+    lib, check = gdt.capi.lib(), gdt.capi.check
+    L = gdt.make_advection_fv_operator(gdt.NumericalUpwindFlux(D.FLUX_LINEAR, [1.0, 0.5]), space)
+    u = torch.rand(n * n, dtype=torch.float64, device="cuda")
+    for label, env in (("fused", None), ("separate_axpy", "GDTB_RK_NO_FUSE")):
+        if env:
+            os.environ[env] = "1"
+        ts = C.c_void_p()
+        check(lib.gdtb_rk_create(L._h, D.RK_SSP3, 0, None, None, None, -1.0, 0.0, C.byref(ts)))
+        dt = 0.1 / n
+        for _ in range(3):
+            check(lib.gdtb_rk_step(ts, C.c_void_p(u.data_ptr()), dt, dt, None))
+        ctx.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        s_.record()
+        for _ in range(reps):
+            check(lib.gdtb_rk_step(ts, C.c_void_p(u.data_ptr()), dt, dt, None))
+        e_.record()
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        out.setdefault("ssp3_step", {})[label] = {"ms_per_step": s_.elapsed_time(e_) / reps}
+        lib.gdtb_rk_destroy(ts)
+        if env:
+            del os.environ[env]
     return out
 
 

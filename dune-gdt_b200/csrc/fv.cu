@@ -294,11 +294,50 @@ __device__ __forceinline__ void st_cols(double* q, const double (&v)[C])
 // advection-fv.hh:147-152 equals g / ext_k on axis-aligned cells up to rounding.  Faces that do not exist (domain
 // boundary without periodicity) get the coefficient 0.  Loads are issued FV_BATCH layers at a time before the first
 // flux of the batch is evaluated (memory-level parallelism).
-template <int D, int NUMFLUX, int KIND, int C, bool BND, bool P2P = false>
+template <int D, int NUMFLUX, int KIND, int C, bool BND, bool P2P = false, int NS = -1>
 __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvParams p, const double* __restrict__ u,
                                                   double* __restrict__ out, int rows)
 {
   static_assert(D == 2 || D == 3, "marching kernel is for 2D / 3D grids");
+  static_assert(NS < 0 || (!BND && !P2P), "the fused stage combination covers the plain periodic / inner kernel");
+  // NS >= 0: Runge-Kutta stage fused into the apply: every value of the source is u + sum_{j < NS} stage_v[j] stage_c[j]
+  // (terms added in order like the separate axpy pass), formed where it is loaded
+  auto ldc = [&](const double* q, double(&v)[C]) {
+    ldg_cols<C>(q, v);
+    if (NS > 0) {
+      const long long o = q - u;
+#pragma unroll
+      for (int j = 0; j < (NS > 0 ? NS : 0); ++j) {
+        double t[C];
+        ldg_cols<C>(p.stage_v[j] + o, t);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          v[c] += t[c] * p.stage_c[j];
+      }
+    }
+  };
+  auto ld1 = [&](const double* q) {
+    double a = __ldg(q);
+    if (NS > 0) {
+      const long long o = q - u;
+#pragma unroll
+      for (int j = 0; j < (NS > 0 ? NS : 0); ++j)
+        a += __ldg(p.stage_v[j] + o) * p.stage_c[j];
+    }
+    return a;
+  };
+  // what a cell's result is: L(u_i), the fused Euler update, or (out_mode 1) the Runge-Kutta update of the step
+  auto result = [&](const double* po_, const double uc_, const double acc) {
+    if (NS >= 0 && p.out_mode == 1) {
+      const long long o = po_ - out;
+      double t = __ldg(u + o);
+      for (int j = 0; j < p.n_out; ++j)
+        t += __ldg(p.out_v[j] + o) * p.out_c[j];
+      t += acc * p.out_cL;
+      return t;
+    }
+    return p.euler ? uc_ - acc * p.dt : acc; // u_n - L(u_n) dt (examples/mpi...cc:154)
+  };
   const GridDev& g = p.g;
   constexpr int last = D - 1;
   constexpr int R = FV_BATCH;
@@ -362,7 +401,7 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
   double* po = out + (long long)(j0 + shift) * plane + col;
   const double* prl = p.inv_ext[last] + j0;
   double uc[C], G_low[C];
-  ldg_cols<C>(pc, uc);
+  ldc(pc, uc);
   // flux through the lower face of the first layer (on a slab the ghost layer below carries the neighbour); 0 if
   // there is no face
   {
@@ -372,7 +411,7 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
     if (P2P)
       ldcg_cols<C>(pc + off, ub);
     else
-      ldg_cols<C>(pc + off, ub);
+      ldc(pc + off, ub);
 #pragma unroll
     for (int c = 0; c < C; ++c)
       G_low[c] = has ? flux_plus<NUMFLUX, KIND>(p, last, ub[c], uc[c])
@@ -390,12 +429,12 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
       if (P2P)
         ldcg_cols<C>(q + plane, un[r]);
       else
-        ldg_cols<C>(q + plane, un[r]);
-      xl[r] = __ldg(q + d_xm);
-      xr[r] = __ldg(q + d_xp);
+        ldc(q + plane, un[r]);
+      xl[r] = ld1(q + d_xm);
+      xr[r] = ld1(q + d_xp);
       if (D == 3) {
-        ldg_cols<C>(q + d_ym, yl[r]);
-        ldg_cols<C>(q + d_yp, yr[r]);
+        ldc(q + d_ym, yl[r]);
+        ldc(q + d_yp, yr[r]);
       }
       rl[r] = __ldg(prl + r);
     }
@@ -415,7 +454,7 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
           acc += (by_hi ? bnd_flux_plus<NUMFLUX, KIND>(p, 1, 1, uc[c]) : flux_plus<NUMFLUX, KIND>(p, 1, uc[c], yr[r][c])) * cyh
                  - (by_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 1, 0, uc[c]) : flux_plus<NUMFLUX, KIND>(p, 1, yl[r][c], uc[c])) * cyl;
         acc += (G_up - G_low[c]) * rl[r];
-        res[c] = p.euler ? uc[c] - acc * p.dt : acc; // u_n - L(u_n) dt (examples/mpi...cc:154)
+        res[c] = result(po + (long long)r * plane + c, uc[c], acc);
         G_low[c] = G_up;
         uc[c] = un[r][c];
       }
@@ -439,15 +478,15 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
     if (P2P)
       ldcg_cols<C>(pc + plane, un);
     else
-      ldg_cols<C>(pc + ((top && !p.ghosted) ? (has_up ? (1 - (long long)nl) * plane : 0) : plane), un);
-    gx[0] = bx_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 0, 0, uc[0]) : flux_plus<NUMFLUX, KIND>(p, 0, __ldg(pc + d_xm), uc[0]);
+      ldc(pc + ((top && !p.ghosted) ? (has_up ? (1 - (long long)nl) * plane : 0) : plane), un);
+    gx[0] = bx_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 0, 0, uc[0]) : flux_plus<NUMFLUX, KIND>(p, 0, ld1(pc + d_xm), uc[0]);
     if (C == 2)
       gx[1] = flux_plus<NUMFLUX, KIND>(p, 0, uc[0], uc[C - 1]);
     gx[C] = bx_hi ? bnd_flux_plus<NUMFLUX, KIND>(p, 0, 1, uc[C - 1])
-                  : flux_plus<NUMFLUX, KIND>(p, 0, uc[C - 1], __ldg(pc + d_xp));
+                  : flux_plus<NUMFLUX, KIND>(p, 0, uc[C - 1], ld1(pc + d_xp));
     if (D == 3) {
-      ldg_cols<C>(pc + d_ym, yl);
-      ldg_cols<C>(pc + d_yp, yr);
+      ldc(pc + d_ym, yl);
+      ldc(pc + d_yp, yr);
     }
     const double rl = __ldg(prl);
 #pragma unroll
@@ -459,7 +498,7 @@ __global__ void __launch_bounds__(256) k_fv_march(const __grid_constant__ FvPara
         acc += (by_hi ? bnd_flux_plus<NUMFLUX, KIND>(p, 1, 1, uc[c]) : flux_plus<NUMFLUX, KIND>(p, 1, uc[c], yr[c])) * cyh
                - (by_lo ? bnd_flux_plus<NUMFLUX, KIND>(p, 1, 0, uc[c]) : flux_plus<NUMFLUX, KIND>(p, 1, yl[c], uc[c])) * cyl;
       acc += (G_up - G_low[c]) * rl;
-      res[c] = p.euler ? uc[c] - acc * p.dt : acc;
+      res[c] = result(po + c, uc[c], acc);
       G_low[c] = G_up;
       uc[c] = un[c];
     }
@@ -647,12 +686,35 @@ __global__ void __launch_bounds__(256) k_fv_dt_reduce(const __grid_constant__ Fv
 
 } // namespace
 
+// Runge-Kutta stage combination fused into the apply: NS stage vectors are combined with the source at every load
+template <int D, int C, int NS>
+static void launch_fv_march_fused(const FvParams& p, const double* u, double* out, int rows, dim3 grid, dim3 block,
+                                  cudaStream_t stream)
+{
+  const int variant = (p.flux.numflux == GDTB_NUMFLUX_LAX_FRIEDRICHS ? 2 : 0) + (p.flux.kind == GDTB_FLUX_BURGERS ? 1 : 0);
+  switch (variant) {
+    case 0: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C, false, false, NS><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 1: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C, false, false, NS><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    case 2: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_LINEAR, C, false, false, NS><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+    default: k_fv_march<D, GDTB_NUMFLUX_LAX_FRIEDRICHS, GDTB_FLUX_BURGERS, C, false, false, NS><<<grid, block, 0, stream>>>(p, u, out, rows); break;
+  }
+}
+
 template <int D, int C, bool P2P>
 static void launch_fv_march_p(const FvParams& p, const double* u, double* out, int rows, dim3 grid, dim3 block,
                               cudaStream_t stream)
 {
   const int variant = (p.flux.numflux == GDTB_NUMFLUX_LAX_FRIEDRICHS ? 2 : 0) + (p.flux.kind == GDTB_FLUX_BURGERS ? 1 : 0)
                       + ((p.bnd_ext_mask | p.bnd_nf_mask) ? 4 : 0);
+  if (!P2P && p.n_stage >= 0 && variant < 4) {
+    switch (p.n_stage) {
+      case 0: launch_fv_march_fused<D, C, 0>(p, u, out, rows, grid, block, stream); break;
+      case 1: launch_fv_march_fused<D, C, 1>(p, u, out, rows, grid, block, stream); break;
+      case 2: launch_fv_march_fused<D, C, 2>(p, u, out, rows, grid, block, stream); break;
+      default: launch_fv_march_fused<D, C, 3>(p, u, out, rows, grid, block, stream); break;
+    }
+    return;
+  }
   switch (variant) {
     case 0: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_LINEAR, C, false, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
     case 1: k_fv_march<D, GDTB_NUMFLUX_UPWIND, GDTB_FLUX_BURGERS, C, false, P2P><<<grid, block, 0, stream>>>(p, u, out, rows); break;
@@ -681,6 +743,13 @@ int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
   const long long layers = p.apply_hi - p.apply_lo;
   if (layers <= 0)
     return GDTB_OK;
+  uintptr_t fused_bits = 0;
+  if (p.n_stage >= 0) {
+    if (g.d == 1 || p.p2p || (p.bnd_ext_mask | p.bnd_nf_mask) || p.n_stage > 3 || p.n_out > 3)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "fv: the fused Runge-Kutta stage needs the plain 2D / 3D kernel");
+    for (int j = 0; j < p.n_stage; ++j)
+      fused_bits |= reinterpret_cast<uintptr_t>(p.stage_v[j]);
+  }
   time_begin(L, KF_FV_APPLY);
   if (g.d == 1) {
     const int block = 256;
@@ -689,7 +758,8 @@ int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
     // two cells per thread (16-byte accesses) when every row starts 16-byte aligned
     const bool two = g.n[0] % 2 == 0 && ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(out)) & 15) == 0
                      && (reinterpret_cast<uintptr_t>(p.inv_ext[0]) & 15) == 0
-                     && ((reinterpret_cast<uintptr_t>(p.peer_lo_ghost) | reinterpret_cast<uintptr_t>(p.peer_hi_ghost)) & 15) == 0;
+                     && ((reinterpret_cast<uintptr_t>(p.peer_lo_ghost) | reinterpret_cast<uintptr_t>(p.peer_hi_ghost)) & 15) == 0
+                     && (fused_bits & 15) == 0;
     const long long nx = two ? g.n[0] / 2 : g.n[0]; // threads along x
     dim3 block(1, 1, 1), grid(1, 1, 1);
     long long tiles;

@@ -386,6 +386,16 @@ struct FvParams
   int expect;            // counter value that marks the ghost layers of the source buffer as complete (= step index)
   int* edge_count;       // {lower, upper}: edge blocks of this launch that have handed their layer over (last one signals)
   int* timeout_flag;     // set when a wait gave up (bounded spin)
+  // Runge-Kutta stage combination fused into the apply (tools/timestepper/explicit-rungekutta.hh:248-263): the operator
+  // is applied to u_i = u + sum_j stage_v[j] * stage_c[j], formed on the fly at every load (same order of additions as
+  // the separate axpy pass, so the same roundings) -- the stage vector is never written.  out_mode 1: the last stage
+  // writes the step's result u + sum_j out_v[j] * out_c[j] + L(u_i) * out_cL instead of k_i = L(u_i).
+  int n_stage;
+  const double* stage_v[3];
+  double stage_c[3];
+  int out_mode, n_out;
+  const double* out_v[3];
+  double out_c[3], out_cL;
 };
 int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out);
 
