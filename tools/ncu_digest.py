@@ -58,24 +58,27 @@ def main():
             name = h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]
             print(f"    {name:28s} {v:8.3f}")
         print()
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    srows = list(csv.reader(io.StringIO(src)))
-    if len(srows) > 2:
-        sh = srows[0]
-        def col(name):
-            for i, h in enumerate(sh):
-                if h.strip() == name:
-                    return i
-            return -1
-        ci, cs, cx = col("# Samples"), col("Source"), col("Instructions Executed")
-        if ci < 0:
-            ci = col("Warp Stall Sampling (All Samples)")
-        if ci >= 0 and cs >= 0:
-            body = [r for r in srows[1:] if len(r) > max(ci, cs)]
-            total = sum(num(r[ci]) for r in body) or 1.0
-            print(f"  hottest source lines by warp-state samples ({int(total)} samples):")
-            for r in sorted(body, key=lambda r: -num(r[ci]))[:top]:
-                print(f"    {100 * num(r[ci]) / total:5.1f} %  {r[cs].strip()[:150]}")
+    # source view "cuda,sass": one aggregate row per CUDA source line (needs -lineinfo + --import-source on), followed
+    # by that line's SASS rows (empty "Line No"); several files (headers inlined into the kernel) follow each other
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
+                         capture_output=True, text=True).stdout
+    fname, hdr2, lines = "", None, []
+    for r in csv.reader(io.StringIO(src)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            fname = r[1].split("/")[-1]
+        elif r[0] == "Line No":
+            hdr2 = r
+        elif hdr2 and r[0].strip().isdigit():
+            lines.append((fname, r))
+    if hdr2 and lines:
+        ci, cx = hdr2.index("# Samples"), hdr2.index("Instructions Executed")
+        total = sum(num(r[ci]) for _, r in lines) or 1.0
+        total_x = sum(num(r[cx]) for _, r in lines) or 1.0
+        print(f"  hottest source lines by warp-state samples ({int(total)} samples; second column: share of the warp instructions executed):")
+        for f, r in sorted(lines, key=lambda fr: -num(fr[1][ci]))[:top]:
+            print(f"    {100 * num(r[ci]) / total:5.1f} %  {100 * num(r[cx]) / total_x:5.1f} %  {f}:{r[0]}  {r[1].strip()[:120]}")
 
 
 if __name__ == "__main__":
