@@ -193,6 +193,23 @@ def fv_extra(gdt, ctx, torch, hbm_gbs, peak_src):
                      "roofline": {"bound": "hbm", "achieved": bytes_per / (per * 1e-3) / 1e9, "peak": hbm_gbs,
                                   "unit": "GB/s", "frac": bytes_per / (per * 1e-3) / 1e9 / hbm_gbs,
                                   "peak_source": peak_src}}
+    # scale: a device copy of the same 134 MB vector (read + write = the apply's 16 B/cell) on the same box -- at this
+    # size launch ramp-up and tail keep a plain copy below the 2 GB copy MEASURED_PEAKS.json quotes
+    a = torch.rand(n * n, dtype=torch.float64, device="cuda")
+    b = torch.empty_like(a)
+    for _ in range(5):
+        b.copy_(a)
+    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s_.record()
+    for _ in range(50):
+        b.copy_(a)
+    e_.record()
+    torch.cuda.synchronize()
+    copy_ms = s_.elapsed_time(e_) / 50
+    out["same_size_device_copy"] = {"ms": copy_ms, "GBps": 16.0 * n * n / (copy_ms * 1e-3) / 1e9,
+                                    "apply_over_copy": out["linear_transport"]["ms_per_apply"] / copy_ms}
+    del a, b
     # the caller of the apply: one SSP3 Runge-Kutta step (tools/timestepper/explicit-rungekutta.hh:237-270), stages fused
     # into the applies (9 vector passes) against separate axpy passes (18)
     lib, check = gdt.capi.lib(), gdt.capi.check

@@ -138,6 +138,8 @@ PROTOTYPES = {
     "gdtb_halo_p2p_connect": (C.c_int, [_P, _P, C.c_int64, _P]),
     "gdtb_halo_p2p_check": (C.c_int, [_P]),
     "gdtb_vector_add": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "gdtb_vector_upload": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "gdtb_vector_download": (C.c_int, [_P, _P, _P, C.c_int64]),
     "gdtb_matop_local_rows": (C.c_int, [_P, _I64P, _I64P, _I64P]),
     "gdtb_matop_local_row_ranges": (C.c_int, [_P, C.c_int32, _I64P, _I64P, _I64P, _I64P, C.POINTER(C.c_int32)]),
     "gdtb_assemble_host": (C.c_int, [_P, _P, _DP, _DP]),

@@ -147,6 +147,9 @@ __device__ __forceinline__ void q1_decode(unsigned v, const FastDiv& dx, const F
 }
 
 constexpr int Q1G_ROWS = 256; // rows (vertices) per work item = threads per CTA
+#ifndef Q1G_ROWS_PREF
+#define Q1G_ROWS_PREF 224 // the same with the coefficient prefetch slots (k_q1_gather<..., PREF>)
+#endif
 
 // bounded wait for a counter another GPU raises in this GPU's memory (system-scope acquire); gives up after ~1 s
 __device__ __forceinline__ void q1_wait_counter(const int* counter, int expect, int* timeout_flag)
@@ -283,8 +286,11 @@ __device__ __forceinline__ int q1_store_plane(double* __restrict__ row, const do
 // contributions per stencil column in a fixed order (deterministic, no atomics).
 // CELLDATA = false: no per-element coefficient / source arrays and no per-cell right-hand-side terms are in play
 // (constant coefficients, separable analytic source): the element index is never formed.
-template <int D, int NG, int KIND0, bool ACCUMULATE, bool CELLDATA, bool P2P = false>
-__global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLACE_SCALAR && !CELLDATA) ? Q1G_MIN_BLOCKS : 2)
+// PREF (3D, one Laplace integrand with one kappa per element): the eight coefficients a vertex needs are fetched one
+// item ahead by cp.async into private shared-memory slots, so their DRAM latency hides behind the previous item's
+// arithmetic; ROWS is lowered to make room for the slots next to the two stages of two resident blocks.
+template <int D, int NG, int KIND0, bool ACCUMULATE, bool CELLDATA, bool P2P = false, int ROWS = Q1G_ROWS, bool PREF = false>
+__global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLACE_SCALAR && !CELLDATA) ? Q1G_MIN_BLOCKS : 2)
     k_q1_gather(const __grid_constant__ Q1GatherParams p, double* __restrict__ values, double* __restrict__ rhs,
                 long long nrows, int nitems, int stage_doubles, int nbuf)
 {
@@ -296,14 +302,64 @@ __global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_L
   const int elo = (int)p.elem_lo, ehi = (int)p.elem_hi;
   const bool want_values = NG > 0 && values != nullptr;
   int buf = 0;
+  // PREF: slot (o, t) = kappa of the cell with offset o around the vertex of thread t (0 for a cell outside the grid /
+  // slab), behind the stage buffers
+  double* const slots = smem + (size_t)nbuf * stage_doubles;
+  auto prefetch_coef = [&](int item_) {
+    const long long l0_ = (long long)item_ * ROWS;
+    if (item_ < nitems && l0_ + threadIdx.x < nrows) {
+      int ix, iy, iz;
+      q1_decode<D>((unsigned)(p.row_offset + l0_) + threadIdx.x, p.div_vx, p.div_vy, ix, iy, iz);
+      const long long e0 = (long long)(ix - 1) + (long long)Nx * ((iy - 1) + (long long)Ny * (iz - 1));
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int cx_ = ix - 1 + (o & 1), cy_ = iy - 1 + ((o >> 1) & 1), cz_ = iz - 1 + (o >> 2);
+        const bool valid = cx_ >= 0 && cx_ < Nx && cy_ >= 0 && cy_ < Ny && cz_ >= elo && cz_ < ehi;
+        double* dst = slots + o * ROWS + threadIdx.x;
+        if (valid) {
+          const double* src = p.group[0].coef + (e0 + (o & 1) + (long long)Nx * (((o >> 1) & 1) + (long long)Ny * (o >> 2)));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
+                       : "memory");
+        } else
+          *dst = 0.;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // ... and two items ahead of that one thread per cell line asks the TMA unit to pull the line's window into L2
+  // (cp.async.bulk.prefetch.L2): the DRAM reads of the coefficient stream then arrive as a few long bursts instead of
+  // many 256-byte requests scattered between the writes (every read burst costs a bus turn-around in a write-only stream)
+  auto prefetch_lines_l2 = [&](int item_) {
+    if (item_ >= nitems || threadIdx.x >= 4)
+      return;
+    int ix, iy, iz;
+    q1_decode<D>((unsigned)(p.row_offset + (long long)item_ * ROWS), p.div_vx, p.div_vy, ix, iy, iz);
+    const long long ne = (long long)Nx * Ny * Nz;
+    const long long first = (long long)(ix - 1) + (long long)Nx * ((iy - 1 + (int)(threadIdx.x & 1)) + (long long)Ny * (iz - 1 + (int)(threadIdx.x >> 1)));
+    long long lo = max(first, 0LL), hi = min(first + ROWS + 2, ne);
+    if (hi - lo < 4)
+      return;
+    const double* src = p.group[0].coef + lo;
+    if (reinterpret_cast<unsigned long long>(src) & 8ULL) { // 16-byte alignment of the bulk prefetch
+      ++src;
+      ++lo;
+    }
+    const unsigned bytes = (unsigned)(((hi - lo) & ~1LL) * sizeof(double));
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+  };
+  if (PREF) {
+    prefetch_coef(blockIdx.x);
+    prefetch_lines_l2(blockIdx.x + (int)gridDim.x);
+    prefetch_lines_l2(blockIdx.x + 2 * (int)gridDim.x);
+  }
 
   for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
     // peer-memory halo: highest rows first (the top layer is what the neighbour above waits for), the bottom layer --
     // which waits for the neighbour below -- last
     const int item = P2P ? nitems - 1 - it : it;
     // ---- per item (uniform over the CTA): the CSR segment -------------------------------------------------
-    const long long l0 = (long long)item * Q1G_ROWS; // first local row
-    const int nr = (int)min((long long)Q1G_ROWS, nrows - l0);
+    const long long l0 = (long long)item * ROWS; // first local row
+    const int nr = (int)min((long long)ROWS, nrows - l0);
     const unsigned r0 = (unsigned)(p.row_offset + l0); // first global row (= vertex index)
     const Q1HaloP2p& H = p.halo;
     const long long top_row = nrows - H.layer_rows;
@@ -338,6 +394,16 @@ __global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_L
     }
 
     // ---- per vertex --------------------------------------------------------------------------------------
+    double c8[8];
+    if (PREF) {
+      // this item's coefficients arrived while the previous item was computed; the next item's are requested now
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        c8[o] = slots[o * ROWS + threadIdx.x];
+      prefetch_coef(it + (int)gridDim.x);
+      prefetch_lines_l2(it + 3 * (int)gridDim.x);
+    }
     if ((int)threadIdx.x < nr) {
       int ix, iy, iz;
       q1_decode<D>(r0 + threadIdx.x, p.div_vx, p.div_vy, ix, iy, iz);
@@ -410,7 +476,7 @@ __global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_L
         // M^k[d] = sum_cells M1[.][.] h_k (1D tables of the form's rule; the vertex is node 1 of the lower and node 0 of
         // the upper cell) and the stencil is c (K^x M^y M^z + M^x K^y M^z + M^x M^y K^z): 3 FP64 instructions per entry
         // instead of 8.  Cells outside the grid / slab carry h = 1/h = 0 and drop out.
-        const bool sf3 = LAP3 && want_values && !(CELLDATA && p.group[0].coef_elem);
+        const bool sf3 = LAP3 && want_values && !(CELLDATA && p.group[0].coef_elem) && !p.no_sf3;
         if (sf3) {
           const Q1Group& G = p.group[0];
           double Kv[3][3], Mv[3][3];
@@ -458,7 +524,7 @@ __global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_L
                 asm volatile("" : "+d"(t0));
                 double w[3] = {fx_b[ox] * t0, fx_a[ox] * yz_ba[oy][oz], fx_a[ox] * yz_ab[oy][oz]};
                 if (CELLDATA && p.group[0].coef_elem) {
-                  const double c = valid ? __ldg(p.group[0].coef + e) : 0.;
+                  const double c = PREF ? c8[ox + 2 * oy + 4 * oz] : (valid ? __ldg(p.group[0].coef + e) : 0.);
                   w[0] *= c;
                   w[1] *= c;
                   w[2] *= c;
@@ -693,24 +759,36 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
   if (total_rows >= (1LL << 31) - Q1G_ROWS)
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "q1_gather: more than 2^31 vertices");
   const long long nrows = (p.row_hi - p.row_lo) * layer_rows;
-  const long long nitems = (nrows + Q1G_ROWS - 1) / Q1G_ROWS;
-  if (nitems <= 0)
+  if (nrows <= 0)
     return GDTB_OK;
   // two stage buffers (double-buffered bulk store), each padded for the 16-byte phase shift
-  const int stage_doubles = ((Q1G_ROWS * P3<D>::value + 2) + 1) & ~1;
   const bool with_values = NG > 0 && values;
-  static const int nbuf_env = std::getenv("GDTB_Q1_NBUF") ? std::atoi(std::getenv("GDTB_Q1_NBUF")) : 0;
-  const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : Q1G_DEFAULT_NBUF);
-  const size_t smem = with_values ? (size_t)nbuf * stage_doubles * sizeof(double) : 16;
+  static const bool no_sf3 = std::getenv("GDTB_Q1_NO_SF3") != nullptr;
+  const_cast<Q1GatherParams&>(p).no_sf3 = no_sf3 ? 1 : 0;
   if (accumulate && p.halo_p2p)
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "q1_gather: the peer-memory halo works in overwrite mode");
+  // one kappa per element (3D Laplace): coefficients prefetched one item ahead (see the kernel)
+  static const bool no_pref = std::getenv("GDTB_Q1_NO_PREFETCH") != nullptr;
+  constexpr bool CAN_PREF = D == 3 && NG == 1 && KIND0 == Q1G_LAPLACE_SCALAR && CELLDATA;
+  const bool pref = CAN_PREF && with_values && p.group[0].coef_elem && !accumulate && !p.halo_p2p && !no_pref;
+  const int rows_per_item = pref ? Q1G_ROWS_PREF : Q1G_ROWS;
+  const long long nitems = (nrows + rows_per_item - 1) / rows_per_item;
+  // two stage buffers (double-buffered bulk store), each padded for the 16-byte phase shift
+  const int stage_doubles = ((rows_per_item * P3<D>::value + 2) + 1) & ~1;
+  static const int nbuf_env = std::getenv("GDTB_Q1_NBUF") ? std::atoi(std::getenv("GDTB_Q1_NBUF")) : 0;
+  const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : Q1G_DEFAULT_NBUF);
+  const size_t smem =
+      with_values ? ((size_t)nbuf * stage_doubles + (pref ? 8 * Q1G_ROWS_PREF : 0)) * sizeof(double) : 16;
   auto kern = accumulate ? k_q1_gather<D, NG, KIND0, true, CELLDATA, false>
                          : (p.halo_p2p ? k_q1_gather<D, NG, KIND0, false, CELLDATA, true>
                                        : k_q1_gather<D, NG, KIND0, false, CELLDATA, false>);
+  if constexpr (CAN_PREF)
+    if (pref)
+      kern = k_q1_gather<D, NG, KIND0, false, CELLDATA, false, Q1G_ROWS_PREF, true>;
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Q1G_ROWS, smem));
+  GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rows_per_item, smem));
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "q1_gather: kernel does not fit on an SM");
   long long grid = (long long)per_sm * L.sm_count;
@@ -718,7 +796,7 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
     grid = nitems;
   note_kernel(L, KF_Q1_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_Q1_GATHER);
-  kern<<<(unsigned)grid, Q1G_ROWS, smem, L.stream>>>(p, values, rhs, nrows, (int)nitems, stage_doubles, nbuf);
+  kern<<<(unsigned)grid, rows_per_item, smem, L.stream>>>(p, values, rhs, nrows, (int)nitems, stage_doubles, nbuf);
   time_end(L, KF_Q1_GATHER);
   L.count++;
   GDTB_CUDA(cudaGetLastError());

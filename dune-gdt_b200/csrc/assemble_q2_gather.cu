@@ -590,10 +590,24 @@ __global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF ==
     double* stage = smem + buf * stage_doubles + phase;
 
     const int lr = five ? threadIdx.x / 5 : threadIdx.x / 3, slot = threadIdx.x - lr * slots;
+    int cx = 0, cy = 0, cl = 0, row_off = 0;
     if (lr < nrows) {
-      int cx, cy, cl;
       q2_decode<D>(rg, lrow0 + lr, cx, cy, cl);
-      double* row = stage + int(q2_row_offset<D>(g, rg, cx, cy, cl) - off0);
+      row_off = int(q2_row_offset<D>(g, rg, cx, cy, cl) - off0);
+    }
+    // the stage about to be written must have been read out by the bulk store that used it last: waiting HERE (after
+    // this item's index arithmetic) instead of right after the store lets the drain overlap the bookkeeping
+    if (!ACCUMULATE && item != (long long)blockIdx.x) {
+      if (threadIdx.x == 0) {
+        if (nbuf == 1)
+          q2_bulk_wait_read0();
+        else
+          q2_bulk_wait_read1();
+      }
+      __syncthreads();
+    }
+    if (lr < nrows) {
+      double* row = stage + row_off;
       if (D == 3) {
         switch (rg.s) {
           case 0: q2_dispatch<SF, 3, 0, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
@@ -633,12 +647,7 @@ __global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF ==
         if (head + body < seg)
           values[start + head + body] = stage[head + body];
         q2_bulk_commit();
-        if (nbuf == 1)
-          q2_bulk_wait_read0();
-        else
-          q2_bulk_wait_read1();
       }
-      __syncthreads();
       buf = nbuf == 1 ? 0 : buf ^ 1;
     }
   }

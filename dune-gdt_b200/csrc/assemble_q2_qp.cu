@@ -417,6 +417,10 @@ __global__ void __launch_bounds__(XF_THREADS, 2)
       mbar_wait(&bar, parity);
       parity ^= 1;
     }
+    // the output stage must have been read out by the previous item's bulk store: waited for here, after this item's
+    // index arithmetic and coefficient loads, so that the drain overlaps them
+    if (!ACCUMULATE && item != (long long)blockIdx.x && threadIdx.x == 0)
+      q2_bulk_wait_read0();
     __syncthreads();
 
     switch (k) {
@@ -456,9 +460,7 @@ __global__ void __launch_bounds__(XF_THREADS, 2)
             values[start1 + head + body] = stage1[head + body];
         }
         q2_bulk_commit();
-        q2_bulk_wait_read0(); // one stage: it must have been read out before the next item is written
       }
-      __syncthreads();
     }
   }
   if (!ACCUMULATE && threadIdx.x == 0)

@@ -420,11 +420,37 @@ bool matop_q2_eligible(const gdtb_matop* op)
 
 // DG row-gather path (assemble_dg_gather.cu): any mix of element / inner-coupling / boundary forms on a non-periodic
 // grid with the element_and_intersection pattern
+// every coefficient of the DG forms is a constant or one scalar per element: the factorised kernels apply
+bool matop_dg_scalar_coefficients(const gdtb_matop* op)
+{
+  const auto scalar = [](const gdtb_function& f) { return f.kind == GDTB_FN_CONST_SCALAR || f.kind == GDTB_FN_ELEM_SCALAR; };
+  for (const auto* list : {&op->element_forms, &op->coupling_forms, &op->boundary_forms})
+    for (const auto& lf : *list)
+      for (int t = 0; t < lf.form.n_terms; ++t)
+        if (!scalar(lf.form.terms[t].diffusion) || !scalar(lf.form.terms[t].weight))
+          return false;
+  return true;
+}
+
+bool grid_dg_closed_form(const GridDev& g)
+{
+  for (int k = 0; k < g.d; ++k)
+    if (((g.periodic >> k) & 1) && g.n[k] < 3)
+      return false;
+  return true;
+}
+
 bool matop_dg_eligible(const gdtb_matop* op)
 {
-  if (op->test.kind != GDTB_SPACE_DG || op->ansatz.kind != GDTB_SPACE_DG || op->grid.periodic)
+  if (op->test.kind != GDTB_SPACE_DG || op->ansatz.kind != GDTB_SPACE_DG)
     return false;
   if (!dg_gather_supported(op->grid.d, op->test.K))
+    return false;
+  // periodic grid views: the factorised kernels know the wrap neighbours (periodic directions with >= 3 cells); the
+  // quadrature-faithful gather kernel does not
+  if (op->grid.periodic
+      && !(grid_dg_closed_form(op->grid) && dg_gather_fast_supported(op->grid, op->test.K)
+           && matop_dg_scalar_coefficients(op) && !std::getenv("GDTB_DG_NO_FAST")))
     return false;
   // a pattern-free operator follows the closed-form element_and_intersection stencil; a given pattern must be that one
   if (op->pattern
@@ -986,8 +1012,9 @@ int gdtb_host_closed_form_rowptr(const gdtb_grid_desc* grid, int kind, int order
   SpaceDev sp;
   GDTB_TRY(make_grid_dev(grid, g));
   GDTB_TRY(make_space_dev(g, kind, order, sp));
-  if (g.periodic)
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "closed-form row pointers exist for non-periodic grids");
+  if (g.periodic && !(kind == GDTB_SPACE_DG && grid_dg_closed_form(g)))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED,
+                "closed-form row pointers exist for non-periodic grids (DG: also periodic directions with >= 3 cells)");
   if (kind == GDTB_SPACE_CG && sp.K == 1)
     return q1_host_rowptr(g, sp, (long long*)rowptr);
   if (kind == GDTB_SPACE_CG && sp.K == 2 && (g.d == 2 || g.d == 3))
@@ -1128,7 +1155,8 @@ int gdtb_pattern_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space*
                              && test->dev.K == 2 && (test->grid.d == 2 || test->grid.d == 3) && !test->grid.periodic
                              && test->dev.size < (1LL << 31);
   const bool structured_dg = stencil == GDTB_STENCIL_ELEMENT_AND_INTERSECTION && same_space
-                             && test->dev.kind == GDTB_SPACE_DG && !test->grid.periodic && test->dev.size < (1LL << 31);
+                             && test->dev.kind == GDTB_SPACE_DG && grid_dg_closed_form(test->grid)
+                             && test->dev.size < (1LL << 31);
   const bool structured_ok = structured_q1 || structured_q2 || structured_dg;
   if (method == GDTB_PATTERN_STRUCTURED && !structured_ok)
     return fail(GDTB_ERR_NOT_IMPLEMENTED,
@@ -1216,8 +1244,8 @@ int gdtb_matop_create(gdtb_ctx* ctx, const gdtb_space* test, const gdtb_space* a
   const bool closed_q1 = q1_space(test->dev) && q1_space(ansatz->dev) && !test->grid.periodic;
   const bool closed_q2 = q2_space(test->dev) && q2_space(ansatz->dev) && !test->grid.periodic;
   // discontinuous spaces: the element_and_intersection stencil (what an IPDG operator needs) has a closed form too
-  const bool closed_dg = test->dev.kind == GDTB_SPACE_DG && ansatz->dev.kind == GDTB_SPACE_DG && !test->grid.periodic
-                         && test->dev.size < (1LL << 31);
+  const bool closed_dg = test->dev.kind == GDTB_SPACE_DG && ansatz->dev.kind == GDTB_SPACE_DG
+                         && grid_dg_closed_form(test->grid) && test->dev.size < (1LL << 31);
   if (!pattern && !closed_q1 && !closed_q2 && !closed_dg)
     return fail(GDTB_ERR_INVALID_ARGUMENT,
                 "gdtb_matop_create: a pattern is required (only the CG Q1 / Q2 element stencils and the DG "
@@ -1596,6 +1624,26 @@ int gdtb_vector_add(gdtb_ctx* ctx, double* d_y, const double* d_x, int64_t n)
   q.v[0] = d_x;
   q.c[0] = 1.;
   return launch_rk_axpy(ctx->launch, q, d_y, d_y);
+}
+
+int gdtb_vector_upload(gdtb_ctx* ctx, double* d_dst, const double* src, int64_t n)
+{
+  if (!d_dst || !src || n < 0)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vector_upload: invalid argument");
+  GDTB_TRY(check_ctx(ctx));
+  GDTB_CUDA(cudaMemcpyAsync(d_dst, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+  return GDTB_OK;
+}
+
+int gdtb_vector_download(gdtb_ctx* ctx, double* dst, const double* d_src, int64_t n)
+{
+  if (!dst || !d_src || n < 0)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_vector_download: invalid argument");
+  GDTB_TRY(check_ctx(ctx));
+  GDTB_CUDA(cudaMemcpyAsync(dst, d_src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->launch.stream));
+  GDTB_CUDA(cudaStreamSynchronize(ctx->launch.stream));
+  return GDTB_OK;
 }
 
 static int matop_set_slab_impl(gdtb_matop* op, int64_t layer_begin, int64_t layer_end, bool halo)
@@ -2190,6 +2238,9 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
     p.n_elem = (int)op->element_forms.size();
     p.n_coup = (int)op->coupling_forms.size();
     p.n_bnd = (int)op->boundary_forms.size();
+    for (size_t f = 0; f < op->coupling_forms.size(); ++f)
+      if (op->coupling_forms[f].filter == GDTB_FILTER_INNER_AND_PERIODIC_ONCE)
+        p.coup_on_periodic |= 1u << f;
     const long long plane = op->grid.ne / op->grid.n[op->grid.d - 1];
     p.e_begin = op->slab ? op->elem_lo * plane : 0;
     p.e_end = op->slab ? op->elem_hi * plane : op->grid.ne;
@@ -2206,6 +2257,8 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       for (int t = 0; t < f.n_terms; ++t)
         all_const = all_const && f.terms[t].diffusion.kind == GDTB_FN_CONST_SCALAR && f.terms[t].weight.kind == GDTB_FN_CONST_SCALAR;
     p.fast = fast ? ((all_const && !std::getenv("GDTB_DG_NO_CC")) ? 2 : 1) : 0;
+    if (p.fast)
+      GDTB_TRY(q1_axis_tables(op->ctx, op->grid, p.axis_tab, p.axis_tab_inv));
     if (!p.fast) { // the quadrature-faithful kernel reads the row pointer (materialised for a pattern-free operator)
       const long long* rp = nullptr;
       const int* ci = nullptr;

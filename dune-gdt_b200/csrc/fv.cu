@@ -13,6 +13,7 @@
 // the cell, so results differ from the face-once walk only by FMA contraction (a few ulp).  Cell extents come from
 // per-axis tables computed once per operator with YaspGrid's own formula.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.hpp"
@@ -238,7 +239,10 @@ __device__ __forceinline__ double bnd_flux_plus(const FvParams& p, int k, int s,
   return G;
 }
 
-constexpr int FV_BATCH = 4;
+#ifndef GDTB_FV_BATCH
+#define GDTB_FV_BATCH 4
+#endif
+constexpr int FV_BATCH = GDTB_FV_BATCH;
 
 template <int C>
 __device__ __forceinline__ void ldg_cols(const double* q, double (&v)[C])
@@ -764,7 +768,9 @@ int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
     dim3 block(1, 1, 1), grid(1, 1, 1);
     long long tiles;
     if (g.d == 2) {
-      block.x = (unsigned)std::min<long long>(128, ((nx + 31) / 32) * 32);
+      static const int bx_env = std::getenv("GDTB_FV_BLOCK") ? std::atoi(std::getenv("GDTB_FV_BLOCK")) : 0; // A/B knob
+      const long long bx = (bx_env == 64 || bx_env == 128 || bx_env == 256) ? bx_env : 128;
+      block.x = (unsigned)std::min<long long>(bx, ((nx + 31) / 32) * 32);
       grid.x = (unsigned)((nx + block.x - 1) / block.x);
       tiles = grid.x;
     } else {

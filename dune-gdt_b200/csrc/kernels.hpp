@@ -178,6 +178,7 @@ struct Q1GatherParams
   long long row_lo, row_hi;
   long long elem_lo, elem_hi;
   int halo_p2p; // the interface-row halo travels inside the kernel (halo below)
+  int no_sf3;   // A/B knob (GDTB_Q1_NO_SF3): constant kappa through the per-cell sum instead of the sum-factorised stencil
   long long halo_top_value_start; // local position of the first value of the top (interface) layer
   Q1HaloP2p halo;
 };
@@ -328,6 +329,11 @@ struct DgGatherParams
   // element-owned rows: this process produces the rows of the elements [e_begin, e_end) (a slab of element layers),
   // `values` starts at the global CSR position value_offset
   long long e_begin, e_end, value_offset;
+  // bit f: coupling form f also runs over the periodic wrap faces (GDTB_FILTER_INNER_AND_PERIODIC_ONCE)
+  unsigned coup_on_periodic;
+  // factorised kernels: per-axis geometry tables of the grid (k_q1_axis_tables: [h | 1/h], entry i + 1 = cell i)
+  const double* axis_tab[3];
+  long long axis_tab_inv;
 };
 
 bool dg_gather_supported(int d, int K);

@@ -54,7 +54,10 @@ __device__ __forceinline__ double q2_cell_extent(double lo, double h, int i)
   return __dsub_rn(upper, lower);
 }
 
-constexpr int Q2G_THREADS = 256;
+#ifndef Q2G_THREADS_N
+#define Q2G_THREADS_N 256
+#endif
+constexpr int Q2G_THREADS = Q2G_THREADS_N;
 
 // Closed-form CSR row starts.  Along one axis with N elements a row at lattice coordinate p = 2 c + S couples to
 // L(c) lattice points: S = 1: 3 (never clipped); S = 0: 5 - 2 [c == 0] - 2 [c == N].  The rows of a row group are

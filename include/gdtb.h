@@ -503,6 +503,11 @@ int gdtb_halo_p2p_connect(gdtb_matop* op, const void* lower_handles, int64_t low
 int gdtb_halo_p2p_check(gdtb_matop* op);
 /* d_y[0..n) += d_x[0..n) on the context's stream (enqueue only) */
 int gdtb_vector_add(gdtb_ctx* ctx, double* d_y, const double* d_x, int64_t n);
+/* Plain vector transfers between host and device memory on the context's stream, synchronised on return: for hosts
+ * without a CUDA runtime of their own (the C++ facade fills the slab vectors of gdtb_rk_p2p_handles /
+ * gdtb_fvop_p2p_alloc with these, where the Python mirror uses torch tensors). */
+int gdtb_vector_upload(gdtb_ctx* ctx, double* d_dst, const double* src, int64_t n);
+int gdtb_vector_download(gdtb_ctx* ctx, double* dst, const double* d_src, int64_t n);
 int64_t gdtb_matop_local_nnz(const gdtb_matop* op);
 int gdtb_matop_local_rows(const gdtb_matop* op, int64_t* row_begin, int64_t* row_end, int64_t* value_offset);
 /* CG Q2: the MCMG-based ContinuousMapper (spaces/mapper/continuous.hh:117-150) numbers DoFs [cells | faces | edges |

@@ -171,9 +171,12 @@ def test_swipdg_inner_and_periodic_once_parity(gdt, ctx, oracle, n, periodic, or
     gdesc = D.grid_desc(-1.0, 1.0, n, periodic)
     kappa = D.fn_elem(np.random.default_rng(SEED).uniform(0.5, 2.0, int(np.prod(n))))
     el, co, bo = swipdg(kappa=kappa, omega=kappa)
-    rowptr, colidx, values, _, _ = gpu_assemble(
+    rowptr, colidx, values, _, plan = gpu_assemble(
         gdt, ctx, gdesc, DG, order, D.STENCIL_ELEMENT_AND_INTERSECTION, element=[el], coupling=[co], boundary=[bo],
         coupling_filter=D.FILTER_INNER_AND_PERIODIC_ONCE)
+    # order 1, periodic directions with >= 3 cells: the factorised row-gather kernel knows the wrap neighbours
+    closed = all(n[k] >= 3 for k in range(len(n)) if (periodic >> k) & 1)
+    assert plan == ("dg_gather" if order == 1 and closed else "generic_coloured")
     rp, ci = oracle.pattern(gdesc, (DG, order), stencil=D.STENCIL_ELEMENT_AND_INTERSECTION)
     assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
     ref, _ = oracle.assemble(gdesc, DG, order, rp, ci, [el], [co], [bo])  # the oracle's walk sees the periodic view
@@ -184,6 +187,24 @@ def test_swipdg_inner_and_periodic_once_parity(gdt, ctx, oracle, n, periodic, or
         coupling_filter=D.FILTER_INNER_ONCE)
     wraps = any(((periodic >> k) & 1) and n[k] >= 2 for k in range(len(n)))
     assert (rel_err(inner_only, ref) > 1e-3) == wraps
+
+
+@pytest.mark.parametrize("n,periodic", [([9], 1), ([9, 7], 3), ([8, 5], 2), ([5, 4, 6], 5), ([3, 3, 3], 7)])
+@pytest.mark.parametrize("hi", [D.HI_VOLUME, D.HI_DIAMETER])
+def test_swipdg_periodic_constant_coefficients_row_gather(gdt, ctx, oracle, n, periodic, hi):
+    """constant coefficients on a periodic grid view (the tabulated variant of the factorised kernel), anisotropic cells,
+    pattern-free operator"""
+    lo, up = [0.0, -1.0, 0.5][:len(n)], [3.0, 1.0, 2.0][:len(n)]
+    gdesc = D.grid_desc(lo, up, n, periodic)
+    el, co, bo = swipdg(kappa=1.3, omega=0.7, hI=hi)
+    rowptr, colidx, values, _, plan = gpu_assemble(
+        gdt, ctx, gdesc, DG, 1, D.STENCIL_ELEMENT_AND_INTERSECTION, element=[el], coupling=[co], boundary=[bo],
+        coupling_filter=D.FILTER_INNER_AND_PERIODIC_ONCE)
+    assert plan == "dg_gather"
+    rp, ci = oracle.pattern(gdesc, (DG, 1), stencil=D.STENCIL_ELEMENT_AND_INTERSECTION)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+    ref, _ = oracle.assemble(gdesc, DG, 1, rp, ci, [el], [co], [bo])
+    assert rel_err(values, ref) <= TOL
 
 
 # ------------------------------------------------------------------------------------------------------------------

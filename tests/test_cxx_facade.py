@@ -7,7 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXAMPLES = os.path.join(ROOT, "dune-gdt_b200", "examples")
-PROGS = ["stationary-heat-equation", "linear-transport-fv", "elliptic-swipdg", "generic-function-check"]
+PROGS = ["stationary-heat-equation", "linear-transport-fv", "elliptic-swipdg", "generic-function-check", "parallel-slabs"]
 
 
 def build_examples():
@@ -39,9 +39,26 @@ def test_examples_fail_loudly_without_a_gpu(gdt):
                                   ["elliptic-swipdg"],  # the reference's ESV2007 H^1 table on 8^2, 16^2, 32^2 (3 digits)
                                   ["elliptic-swipdg", "256"],
                                   # GenericFunction lambdas (sampled by the facade) vs built-in / constant coefficients
-                                  ["generic-function-check"]])
+                                  ["generic-function-check"],
+                                  # multi-GPU entry points of the facade with one rank (a periodic slab is its own neighbour)
+                                  ["parallel-slabs"]])
 def test_examples_run(gdt, args):
     build_examples()
     r = subprocess.run([os.path.join(EXAMPLES, args[0])] + args[1:], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().endswith("OK")
+
+
+@pytest.mark.gpu
+def test_parallel_facade_two_gpus(gdt):
+    """Parallel::SlabAssembler / HaloSlabAssembler / PeerMemoryRungeKuttaTimeStepper / PeerMemoryEulerTimeLoop with one
+    C++ process per GPU (tools/mprun.sh; handles exchanged through Parallel::FileRendezvous)"""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    build_examples()
+    r = subprocess.run([os.path.join(ROOT, "tools", "mprun.sh"), "2", os.path.join(EXAMPLES, "parallel-slabs")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "OK" in r.stdout and "FAILED" not in r.stdout

@@ -34,6 +34,18 @@ def test_closed_form_rowptr_matches_the_reference_pattern(gdt, oracle, kind, ord
     assert np.array_equal(got, rp)
 
 
+@pytest.mark.parametrize("n,periodic", [([7], 1), ([3], 1), ([6, 5], 3), ([6, 5], 1), ([5, 4], 2), ([4, 3, 3], 7),
+                                        ([4, 3, 5], 5), ([3, 3, 4], 2)])
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_closed_form_rowptr_on_periodic_dg_grids(gdt, oracle, n, periodic, order):
+    """periodic directions with >= 3 cells: every element has two neighbours there, the wrap neighbour's block is ordered
+    by its element index (tools/sparsity-pattern.hh:74-95 through the periodic view)"""
+    gdesc = D.grid_desc(0.0, 1.0, n, periodic)
+    rp, _ = oracle.pattern(gdesc, (DG, order), stencil=D.STENCIL_ELEMENT_AND_INTERSECTION)
+    got = host_rowptr(gdt, gdesc, DG, order, rp.size - 1)
+    assert np.array_equal(got, rp)
+
+
 def test_closed_form_rowptr_at_the_benchmark_sizes(gdt):
     """nnz of BASELINE's configurations from the closed forms alone: no pattern is ever built"""
     for n, kind, order, rows, nnz in (([128, 128], CG, 1, 16641, 148225), ([64, 64, 64], CG, 1, 65**3, 193**3),
@@ -70,8 +82,8 @@ def test_host_layout_error_conventions(gdt):
     lib = gdt.capi.lib()
     rp = np.zeros(64, dtype=np.int64)
     p = rp.ctypes.data_as(C.POINTER(C.c_int64))
-    per = D.grid_desc(0.0, 1.0, [4, 4], 3)
-    assert lib.gdtb_host_closed_form_rowptr(C.byref(per), DG, 1, p) == 7  # periodic: sort-and-unique only
+    per = D.grid_desc(0.0, 1.0, [4, 2], 3)
+    assert lib.gdtb_host_closed_form_rowptr(C.byref(per), DG, 1, p) == 7  # periodic with < 3 cells: sort-and-unique only
     g1 = D.grid_desc(0.0, 1.0, [4])
     assert lib.gdtb_host_closed_form_rowptr(C.byref(g1), CG, 2, p) == 7  # CG Q2 closed forms are 2D / 3D
     assert lib.gdtb_host_closed_form_rowptr(C.byref(g1), CG, 0, p) == 5  # space_error: CG needs order >= 1

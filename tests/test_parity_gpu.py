@@ -130,10 +130,16 @@ def test_pattern_bit_exact_structured_dg(gdt, ctx, oracle, n, order):
 
 
 def test_structured_pattern_limits(gdt, ctx):
-    space = make_space(gdt, ctx, D.grid_desc(0.0, 1.0, [4, 4], 3), DG, 1)
-    with pytest.raises(gdt.capi.NotImplementedGdt):  # periodic grids go through sort-and-unique
+    space = make_space(gdt, ctx, D.grid_desc(0.0, 1.0, [4, 2], 3), DG, 1)
+    with pytest.raises(gdt.capi.NotImplementedGdt):  # a periodic direction with < 3 cells goes through sort-and-unique
         gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT_AND_INTERSECTION, D.PATTERN_STRUCTURED)
     gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT_AND_INTERSECTION, D.PATTERN_AUTO)
+    # periodic directions with >= 3 cells have a closed form: same CSR as the sort-and-unique builder
+    space = make_space(gdt, ctx, D.grid_desc(0.0, 1.0, [4, 5], 3), DG, 1)
+    a = gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT_AND_INTERSECTION, D.PATTERN_STRUCTURED)
+    b = gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT_AND_INTERSECTION, D.PATTERN_SORT_UNIQUE)
+    (rp_a, ci_a), (rp_b, ci_b) = a.download(), b.download()
+    assert np.array_equal(rp_a, rp_b) and np.array_equal(ci_a, ci_b)
 
 
 def test_pattern_c1_size(gdt, ctx):

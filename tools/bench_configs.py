@@ -107,6 +107,20 @@ def main():
             run(f"C{2 if order == 1 else 5} 3D Q{order} {n}^3, {label}", D.grid_desc(-1.0, 1.0, [n, n, n]), D.SPACE_CG, order,
                 D.STENCIL_ELEMENT, element=[form], reps=3)
             torch.cuda.empty_cache()
+    if "c2-elem" in which:
+        n = n_override or 256
+        g_ = torch.Generator(device="cuda").manual_seed(7)
+        kap = 0.5 + torch.rand(n**3, dtype=torch.float64, device="cuda", generator=g_)
+        f = D.Function()
+        f.kind = D.FN_ELEM_SCALAR
+        f.data_on_device = 1
+        f.data = C.cast(kap.data_ptr(), C.POINTER(C.c_double))
+        f._keep = kap
+        run(f"C2 3D Q1 {n}^3, one kappa per element", D.grid_desc(-1.0, 1.0, [n, n, n]), D.SPACE_CG, 1, D.STENCIL_ELEMENT,
+            element=[D.form(D.integrand(D.INT_LAPLACE, diffusion=f))], reps=10)
+    if "c2" in which:
+        n = n_override or 256
+        run(f"C2 3D Q1 {n}^3", D.grid_desc(-1.0, 1.0, [n, n, n]), D.SPACE_CG, 1, D.STENCIL_ELEMENT, element=[lap], reps=10)
     if "c1" in which:
         n = n_override or 128
         run(f"C1 2D Q1 {n}^2", D.grid_desc(-1.0, 1.0, [n, n]), D.SPACE_CG, 1, D.STENCIL_ELEMENT, element=[lap], reps=20)
