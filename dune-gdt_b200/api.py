@@ -109,10 +109,15 @@ class _Mapper:
 
 
 class Space:
-    def __init__(self, grid, kind, order):
-        self.grid, self.kind, self.order = grid, kind, order
+    def __init__(self, grid, kind, order, range_dim=1):
+        self.grid, self.kind, self.order, self.range_dim = grid, kind, order, range_dim
         self._h = C.c_void_p()
-        check(lib().gdtb_space_create(grid.ctx._h, grid._h, kind, order, C.byref(self._h)))
+        if range_dim != 1:
+            if kind != D.SPACE_FV:
+                raise capi.NotImplementedGdt("vector-valued spaces: finite volume spaces only")
+            check(lib().gdtb_fv_space_create(grid.ctx._h, grid._h, int(range_dim), C.byref(self._h)))
+        else:
+            check(lib().gdtb_space_create(grid.ctx._h, grid._h, kind, order, C.byref(self._h)))
         self.mapper = _Mapper(self)
 
     def __del__(self):
@@ -133,9 +138,9 @@ def make_discontinuous_lagrange_space(grid, order):
     return Space(grid, D.SPACE_DG, order)
 
 
-def make_finite_volume_space(grid):
-    """dune/gdt/spaces/l2/finite-volume.hh:208-230"""
-    return Space(grid, D.SPACE_FV, 0)
+def make_finite_volume_space(grid, range_dim=1):
+    """make_finite_volume_space<m>(grid_view) (dune/gdt/spaces/l2/finite-volume.hh:208-230): m = range_dim DoFs per element"""
+    return Space(grid, D.SPACE_FV, 0, range_dim)
 
 
 class SparsityPattern:
@@ -522,6 +527,40 @@ class NumericalLaxFriedrichsFlux(NumericalUpwindFlux):
     """dune/gdt/local/numerical-fluxes/lax-friedrichs.hh:60-88"""
 
     numflux = D.NUMFLUX_LAX_FRIEDRICHS
+
+
+class NumericalVijayasundaramFlux(NumericalUpwindFlux):
+    """dune/gdt/local/numerical-fluxes/vijayasundaram.hh:29-153 with the flux's own eigendecomposition (EulerTools, the
+    lambda of examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:402-409); systems only"""
+
+    numflux = D.NUMFLUX_VIJAYASUNDARAM
+
+
+class EulerTools:
+    """dune/gdt/tools/euler.hh: conversions between primitive and conservative variables (host side; flux, jacobian and
+    eigendecomposition live in the device kernels) and the flux descriptor of the Euler equations"""
+
+    def __init__(self, d, gamma):
+        self.d, self.gamma, self.m = int(d), float(gamma), int(d) + 2
+
+    def flux(self):
+        """params of a Numerical*Flux: D.FLUX_EULER with p[0] = gamma"""
+        return D.FLUX_EULER, [self.gamma]
+
+    def conservative(self, density, velocity, pressure):
+        """(rho, rho v, E), E = p / (gamma - 1) + rho |v|^2 / 2 (euler.hh:127-131, 153-157)"""
+        v = np.atleast_1d(np.asarray(velocity, dtype=np.float64))
+        if v.size == 1 and self.d > 1:
+            v = np.full(self.d, float(v[0]))
+        return np.concatenate([[density], density * v, [pressure / (self.gamma - 1.0) + 0.5 * density * float(v @ v)]])
+
+    def primitive(self, w):
+        """(rho, v, p) (euler.hh:133-147); w of shape (..., m)"""
+        w = np.asarray(w, dtype=np.float64)
+        rho = w[..., 0]
+        v = w[..., 1:1 + self.d] / rho[..., None]
+        p = (self.gamma - 1.0) * (w[..., self.m - 1] - 0.5 * rho * (v * v).sum(-1))
+        return rho, v, p
 
 
 class AdvectionFvOperator:

@@ -88,6 +88,7 @@ PROTOTYPES = {
     "gdtb_grid_destroy": (C.c_int, [_P]),
     "gdtb_grid_num_elements": (C.c_int64, [_P]),
     "gdtb_space_create": (C.c_int, [_P, _P, C.c_int, C.c_int, _PP]),
+    "gdtb_fv_space_create": (C.c_int, [_P, _P, C.c_int, _PP]),
     "gdtb_space_destroy": (C.c_int, [_P]),
     "gdtb_space_size": (C.c_int64, [_P]),
     "gdtb_space_max_local_size": (C.c_int32, [_P]),

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fv_system.hpp"
 #include "kernels.hpp"
 
 namespace gdtb {
@@ -992,6 +993,25 @@ int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order,
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_space_create: NULL argument");
   SpaceDev sp;
   GDTB_TRY(make_space_dev(grid->dev, kind, order, sp));
+  auto s = new gdtb_space();
+  s->ctx = ctx;
+  s->grid = grid->dev;
+  s->dev = sp;
+  *out = s;
+  return GDTB_OK;
+}
+
+int gdtb_fv_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int range_dim, gdtb_space** out)
+{
+  if (!ctx || !grid || !out)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fv_space_create: NULL argument");
+  if (range_dim < 1 || range_dim > 4)
+    return fail(GDTB_ERR_SPACE, "finite volume spaces: 1 <= range_dim <= 4");
+  SpaceDev sp;
+  GDTB_TRY(make_space_dev(grid->dev, GDTB_SPACE_FV, 0, sp));
+  // FiniteVolumeMapper<GV, m>: m consecutive DoFs per element (spaces/mapper/finite-volume.hh:92-108)
+  sp.nloc = range_dim;
+  sp.size = grid->dev.ne * range_dim;
   auto s = new gdtb_space();
   s->ctx = ctx;
   s->grid = grid->dev;
@@ -2343,6 +2363,29 @@ int gdtb_assemble_host(gdtb_matop* op, gdtb_vecfun* fun, double* values, double*
 }
 
 // ---- AdvectionFvOperator -----------------------------------------------------------------------
+// operators on a finite volume space with m > 1 components (fv_system.cu)
+static bool fv_is_system(const gdtb_fvop* L)
+{
+  return L->space.nloc > 1;
+}
+
+static void fvsys_fill_params(const gdtb_fvop* L, FvSysParams& p)
+{
+  p.g = L->grid;
+  p.m = L->space.nloc;
+  p.numflux = L->flux.numflux;
+  p.gamma = L->flux.p[0];
+  p.half_over_lambda = L->flux.numflux == GDTB_NUMFLUX_LAX_FRIEDRICHS ? 0.5 / L->flux.p[1] : 0.;
+  for (int k = 0; k < 3; ++k)
+    p.inv_ext[k] = L->d_ext + L->inv_ext_shift + L->ext_offset[k];
+  p.euler = 0;
+  p.dt = 0.;
+}
+
+#define GDTB_NO_SYSTEMS(L, what)                                                                                            \
+  if (fv_is_system(L))                                                                                                      \
+  return fail(GDTB_ERR_NOT_IMPLEMENTED, what ": not available for systems (m > 1) yet")
+
 int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* flux, gdtb_fvop** out)
 {
   if (!space || !flux || !out)
@@ -2350,10 +2393,28 @@ int gdtb_fvop_create(gdtb_ctx* ctx, const gdtb_space* space, const gdtb_flux* fl
   GDTB_TRY(check_ctx(ctx));
   if (space->dev.kind != GDTB_SPACE_FV)
     return fail(GDTB_ERR_OPERATOR, "Use LocalAdvectionDgCouplingOperator instead!"); // local/operators/advection-fv.hh:131-134
-  if (flux->kind != GDTB_FLUX_LINEAR && flux->kind != GDTB_FLUX_BURGERS)
-    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown flux function");
-  if (flux->numflux != GDTB_NUMFLUX_UPWIND && flux->numflux != GDTB_NUMFLUX_LAX_FRIEDRICHS)
-    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown numerical flux");
+  if (flux->kind == GDTB_FLUX_EULER) {
+    // systems (m = d + 2): tools/euler.hh covers d = 1, 2
+    if (space->grid.d > 2)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "Euler equations: d = 1, 2 (tools/euler.hh:310, 348)");
+    if (space->dev.nloc != space->grid.d + 2)
+      return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "the Euler flux needs make_finite_volume_space<d + 2>");
+    if (flux->numflux == GDTB_NUMFLUX_UPWIND)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "NumericalUpwindFlux is only available for m = 1 (upwind.hh:44)");
+    if (flux->numflux != GDTB_NUMFLUX_VIJAYASUNDARAM && flux->numflux != GDTB_NUMFLUX_LAX_FRIEDRICHS)
+      return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown numerical flux");
+    if (flux->numflux == GDTB_NUMFLUX_LAX_FRIEDRICHS && !(flux->p[1] > 0.))
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "Not yet implemented for m > 1 if lambda is not provided!"); // lax-friedrichs.hh:40-41
+    if (!(flux->p[0] > 1.))
+      return fail(GDTB_ERR_INVALID_ARGUMENT, "Euler equations: gamma > 1 expected in p[0]");
+  } else {
+    if (flux->kind != GDTB_FLUX_LINEAR && flux->kind != GDTB_FLUX_BURGERS)
+      return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown flux function");
+    if (flux->numflux != GDTB_NUMFLUX_UPWIND && flux->numflux != GDTB_NUMFLUX_LAX_FRIEDRICHS)
+      return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown numerical flux");
+    if (space->dev.nloc != 1)
+      return fail(GDTB_ERR_SHAPES_DO_NOT_MATCH, "scalar flux functions need a finite volume space with one component");
+  }
   auto L = new gdtb_fvop();
   L->ctx = ctx;
   L->grid = space->grid;
@@ -2457,6 +2518,7 @@ int gdtb_fvop_append_boundary(gdtb_fvop* L, const gdtb_fv_boundary* t)
 {
   if (!L || !t)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_append_boundary: NULL argument");
+  GDTB_NO_SYSTEMS(L, "gdtb_fvop_append_boundary");
   if (t->kind != GDTB_FVBND_EXTRAPOLATION && t->kind != GDTB_FVBND_NUMERICAL_FLUX)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown boundary treatment");
   const unsigned all = (1u << (2 * L->grid.d)) - 1u;
@@ -2650,13 +2712,14 @@ int64_t gdtb_fvop_ghost_layer_size(const gdtb_fvop* L)
 static long long fv_local_size(const gdtb_fvop* L)
 {
   const long long plane = gdtb_fvop_ghost_layer_size(L);
-  return plane * (L->grid.layer_hi - L->grid.layer_lo + (L->ghosted ? 2 : 0));
+  return plane * (L->grid.layer_hi - L->grid.layer_lo + (L->ghosted ? 2 : 0)) * L->space.nloc;
 }
 
 int gdtb_fvop_set_slab(gdtb_fvop* L, int64_t layer_begin, int64_t layer_end)
 {
   if (!L)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "operator is NULL");
+  GDTB_NO_SYSTEMS(L, "gdtb_fvop_set_slab");
   const long long n_last = L->grid.n[L->grid.d - 1];
   if (layer_begin < 0 || layer_end > n_last || layer_begin >= layer_end)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "slab must satisfy 0 <= begin < end <= n[last]");
@@ -2673,6 +2736,13 @@ int gdtb_fvop_apply(gdtb_fvop* L, const double* d_source, double* d_range)
   if (!L || !d_source || !d_range)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_apply: NULL argument");
   GDTB_TRY(check_ctx(L->ctx));
+  if (fv_is_system(L)) {
+    FvSysParams q;
+    fvsys_fill_params(L, q);
+    GDTB_TRY(launch_fvsys_apply(L->ctx->launch, q, d_source, d_range));
+    GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
+    return GDTB_OK;
+  }
   FvParams p;
   fv_fill_params(L, p);
   GDTB_TRY(launch_fv_apply(L->ctx->launch, p, d_source, d_range));
@@ -2686,6 +2756,7 @@ int gdtb_fvop_step_async(gdtb_fvop* L, const double* d_source, double* d_range, 
   if (!L || !d_source || !d_range)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_step_async: NULL argument");
   GDTB_TRY(check_ctx(L->ctx));
+  GDTB_NO_SYSTEMS(L, "gdtb_fvop_step_async");
   FvParams p;
   fv_fill_params(L, p);
   if (layer_begin != 0 || layer_end != 0) {
@@ -2741,10 +2812,19 @@ int gdtb_fvop_euler(gdtb_fvop* L, double* d_u, double dt, int64_t n_steps)
   fv_fill_params(L, p);
   p.euler = 1;
   p.dt = dt;
+  FvSysParams q;
+  if (fv_is_system(L)) {
+    fvsys_fill_params(L, q);
+    q.euler = 1;
+    q.dt = dt;
+  }
   double* a = d_u;
   double* b = L->d_tmp;
   for (int64_t s = 0; s < n_steps; ++s) {
-    GDTB_TRY(launch_fv_apply(L->ctx->launch, p, a, b));
+    if (fv_is_system(L))
+      GDTB_TRY(launch_fvsys_apply(L->ctx->launch, q, a, b));
+    else
+      GDTB_TRY(launch_fv_apply(L->ctx->launch, p, a, b));
     std::swap(a, b);
   }
   if (a != d_u) // odd number of steps: result sits in the internal buffer
@@ -2778,14 +2858,60 @@ int gdtb_fv_estimate_dt(gdtb_fvop* L, const double* d_u, const double* boundary_
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "gdtb_fv_estimate_dt: not available on a slab (reduce over the ranks yourself)");
   const int blocks = (int)std::max<long long>(1, std::min<long long>((L->grid.ne + 255) / 256, (long long)L->ctx->launch.sm_count * 8));
   const int max_blocks = L->ctx->launch.sm_count * 8;
-  if (!L->d_partial && cudaMalloc(&L->d_partial, sizeof(double) * 3 * (size_t)max_blocks) != cudaSuccess)
+  if (!L->d_partial && cudaMalloc(&L->d_partial, sizeof(double) * 8 * (size_t)max_blocks) != cudaSuccess)
     return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (dt estimate)");
   FvParams p;
   fv_fill_params(L, p);
+  // (for a system the scalar reduction is only used for max perimeter / volume: it reads the first ne entries of d_u)
   GDTB_TRY(launch_fv_dt_reduce(L->ctx->launch, p, d_u, L->d_partial, blocks));
   std::vector<double> h(3 * (size_t)blocks);
   GDTB_CUDA(cudaMemcpyAsync(h.data(), L->d_partial, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, L->ctx->launch.stream));
   GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
+  if (fv_is_system(L)) {
+    // hyperbolic.hh:50-86 for m > 1: data range per component, Gauss rule of order flux.order() (EulerTools::flux_order()
+    // = 4) on the one-cell grid [min, max] in R^m, largest infinity norm of the flux jacobians there
+    if (boundary_data_range)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "gdtb_fv_estimate_dt: boundary data ranges for systems");
+    const int m = L->space.nloc;
+    double perimeter_over_volume = std::numeric_limits<double>::min();
+    for (int i = 0; i < blocks; ++i)
+      perimeter_over_volume = std::max(perimeter_over_volume, h[3 * i + 2]);
+    FvSysParams q;
+    fvsys_fill_params(L, q);
+    GDTB_TRY(launch_fvsys_minmax(L->ctx->launch, q, d_u, L->d_partial, blocks));
+    std::vector<double> mm(2 * (size_t)m * blocks);
+    GDTB_CUDA(cudaMemcpyAsync(mm.data(), L->d_partial, sizeof(double) * mm.size(), cudaMemcpyDeviceToHost, L->ctx->launch.stream));
+    GDTB_CUDA(cudaStreamSynchronize(L->ctx->launch.stream));
+    double lo[4], hi[4];
+    for (int c = 0; c < m; ++c) {
+      lo[c] = std::numeric_limits<double>::max();
+      hi[c] = std::numeric_limits<double>::min();
+      for (int i = 0; i < blocks; ++i) {
+        lo[c] = std::min(lo[c], mm[(size_t)i * 2 * m + c]);
+        hi[c] = std::max(hi[c], mm[(size_t)i * 2 * m + m + c]);
+      }
+      if (!(lo[c] < hi[c]))
+        hi[c] = lo[c] + 1e-6 * lo[c];
+    }
+    const int nq = gauss_points_for_order(4);
+    double qx[MAX_Q1D], qw[MAX_Q1D];
+    gauss_legendre_01(nq, qx, qw);
+    double max_flux_derivative = std::numeric_limits<double>::min();
+    long long total = 1;
+    for (int c = 0; c < m; ++c)
+      total *= nq;
+    for (long long t = 0; t < total; ++t) {
+      double w[4];
+      long long r = t;
+      for (int c = 0; c < m; ++c) {
+        w[c] = lo[c] + qx[r % nq] * (hi[c] - lo[c]);
+        r /= nq;
+      }
+      max_flux_derivative = std::max(max_flux_derivative, euler_jacobian_inf_norm(L->grid.d, L->flux.p[0], w));
+    }
+    *dt = 1. / (perimeter_over_volume * max_flux_derivative);
+    return GDTB_OK;
+  }
   // hyperbolic.hh:47-48: {numeric_limits<R>::max(), numeric_limits<R>::min()} -- min() is the smallest positive normal
   double data_minimum = boundary_data_range ? boundary_data_range[0] : std::numeric_limits<double>::max();
   double data_maximum = boundary_data_range ? boundary_data_range[1] : std::numeric_limits<double>::min();
@@ -2830,6 +2956,7 @@ int gdtb_rk_create(gdtb_fvop* L, int method, int num_stages, const double* A, co
   if (!L || !out)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_rk_create: NULL argument");
   GDTB_TRY(check_ctx(L->ctx));
+  GDTB_NO_SYSTEMS(L, "gdtb_rk_create");
   auto ts = new gdtb_rk();
   ts->op = L;
   ts->slab = L->ghosted;

@@ -19,8 +19,8 @@ INT_IPDG_INNER_COUPLING, INT_IPDG_INNER_PENALTY = 2, 3
 INT_IPDG_DIRICHLET_COUPLING, INT_IPDG_BOUNDARY_PENALTY = 4, 5
 HI_DIAMETER, HI_VOLUME = 0, 1
 FILTER_INNER_ONCE, FILTER_INNER_AND_PERIODIC_ONCE, FILTER_ALL_BOUNDARY = 0, 1, 2
-FLUX_LINEAR, FLUX_BURGERS = 0, 1
-NUMFLUX_UPWIND, NUMFLUX_LAX_FRIEDRICHS = 0, 1
+FLUX_LINEAR, FLUX_BURGERS, FLUX_EULER = 0, 1, 2
+NUMFLUX_UPWIND, NUMFLUX_LAX_FRIEDRICHS, NUMFLUX_VIJAYASUNDARAM = 0, 1, 2
 ASSEMBLE_OVERWRITE, ASSEMBLE_ACCUMULATE = 0, 1
 PATTERN_AUTO, PATTERN_SORT_UNIQUE, PATTERN_STRUCTURED = 0, 1, 2
 SOLVER_CG, SOLVER_BICGSTAB = 0, 1

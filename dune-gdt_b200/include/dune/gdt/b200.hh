@@ -852,13 +852,34 @@ public:
     internal::check(gdtb_space_create(internal::context(), grid_view_.handle(), kind, order, &raw));
     handle_ = internal::Handle<gdtb_space, gdtb_space_destroy>(raw);
   }
+  // make_finite_volume_space<m>: m components per element (spaces/l2/finite-volume.hh:208-230)
+  struct FiniteVolumeSystem
+  {
+    int range_dim;
+  };
+  SpaceInterface(const GV& grid_view, const FiniteVolumeSystem fv)
+    : grid_view_(grid_view)
+    , kind_(GDTB_SPACE_FV)
+    , order_(0)
+    , range_dim_(fv.range_dim)
+    , mapper_(*this)
+  {
+    gdtb_space* raw = nullptr;
+    internal::check(gdtb_fv_space_create(internal::context(), grid_view_.handle(), fv.range_dim, &raw));
+    handle_ = internal::Handle<gdtb_space, gdtb_space_destroy>(raw);
+  }
   SpaceInterface(const SpaceInterface& other)
     : grid_view_(other.grid_view_)
     , kind_(other.kind_)
     , order_(other.order_)
+    , range_dim_(other.range_dim_)
     , mapper_(*this)
     , handle_(other.handle_)
   {}
+  int range_dim() const
+  {
+    return range_dim_;
+  }
   const GV& grid_view() const
   {
     return grid_view_;
@@ -889,6 +910,7 @@ public:
 private:
   GV grid_view_;
   int kind_, order_;
+  int range_dim_ = 1;
   MapperInterface<GV> mapper_;
   internal::Handle<gdtb_space, gdtb_space_destroy> handle_;
 };
@@ -935,6 +957,15 @@ template <class GV>
 SpaceInterface<GV> make_finite_volume_space(const GV& grid_view)
 {
   return SpaceInterface<GV>(grid_view, GDTB_SPACE_FV, 0);
+}
+
+// make_finite_volume_space<m>(grid_view) (spaces/l2/finite-volume.hh:208-230, m > 1: systems)
+template <std::size_t m, class GV>
+SpaceInterface<GV> make_finite_volume_space(const GV& grid_view)
+{
+  if (m == 1)
+    return SpaceInterface<GV>(grid_view, GDTB_SPACE_FV, 0);
+  return SpaceInterface<GV>(grid_view, typename SpaceInterface<GV>::FiniteVolumeSystem{int(m)});
 }
 
 // ---- sparsity patterns (tools/sparsity-pattern.hh:34-178) ---------------------------------------------------
@@ -2032,7 +2063,107 @@ public:
     this->flux_.kind = GDTB_FLUX_BURGERS;
     this->flux_.numflux = GDTB_NUMFLUX_LAX_FRIEDRICHS;
   }
+  NumericalLaxFriedrichsFlux() = default;
+  void set_euler(const double gamma, const double lambda)
+  {
+    this->flux_.kind = GDTB_FLUX_EULER;
+    this->flux_.numflux = GDTB_NUMFLUX_LAX_FRIEDRICHS;
+    this->flux_.p[0] = gamma;
+    this->flux_.p[1] = lambda;
+  }
 };
+
+// tools/euler.hh: EulerTools<d> -- conversions on the host; flux, jacobian and eigendecomposition live in the kernels
+// (the GenericFunction lambdas `euler_tools.flux(w)` / `flux_jacobian(w)` and the flux_eigen_decomposition lambda of the
+// reference's 2d_euler driver are exactly these, examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:387-409)
+template <std::size_t d, class R = double>
+class EulerTools
+{
+  static_assert(d == 1 || d == 2, "tools/euler.hh: flux jacobian and eigendecomposition exist for d = 1, 2");
+
+public:
+  static constexpr std::size_t m = d + 2;
+  explicit EulerTools(const double gmma)
+    : gamma_(gmma)
+  {}
+  int flux_order() const
+  {
+    return 4;
+  }
+  double gamma() const
+  {
+    return gamma_;
+  }
+  // (rho, rho v, E), E = p / (gamma - 1) + rho |v|^2 / 2 (euler.hh:127-131, 153-157); scalar velocity: every component
+  FieldVector<R, int(m)> conservative(const R rho, const FieldVector<R, int(d)>& v, const R p) const
+  {
+    FieldVector<R, int(m)> w{};
+    R v2 = 0;
+    w[0] = rho;
+    for (std::size_t i = 0; i < d; ++i) {
+      w[1 + i] = rho * v[i];
+      v2 += v[i] * v[i];
+    }
+    w[m - 1] = p / (gamma_ - 1.) + 0.5 * rho * v2;
+    return w;
+  }
+  FieldVector<R, int(m)> conservative(const R rho, const R velocity, const R p) const
+  {
+    FieldVector<R, int(d)> v{};
+    for (auto& c : v)
+      c = velocity;
+    return conservative(rho, v, p);
+  }
+  R density(const FieldVector<R, int(m)>& w) const
+  {
+    return w[0];
+  }
+  R pressure(const FieldVector<R, int(m)>& w) const
+  {
+    R v2 = 0;
+    for (std::size_t i = 0; i < d; ++i)
+      v2 += (w[1 + i] / w[0]) * (w[1 + i] / w[0]);
+    return (gamma_ - 1.) * (w[m - 1] - 0.5 * w[0] * v2);
+  }
+
+private:
+  double gamma_;
+};
+
+// the Euler flux as a value (stands for the GenericFunction<m, d, m> built from EulerTools::flux / flux_jacobian)
+struct EulerFlux
+{
+  double gamma;
+};
+template <std::size_t d>
+EulerFlux make_euler_flux(const EulerTools<d>& tools)
+{
+  return EulerFlux{tools.gamma()};
+}
+
+// local/numerical-fluxes/vijayasundaram.hh:29-153, eigendecomposition from EulerTools
+template <class I, std::size_t d, std::size_t m>
+class NumericalVijayasundaramFlux : public NumericalFluxInterface<I, d, m>
+{
+  static_assert(m == d + 2, "the Euler equations have m = d + 2 components");
+
+public:
+  NumericalVijayasundaramFlux(const EulerFlux& f)
+  {
+    this->flux_.kind = GDTB_FLUX_EULER;
+    this->flux_.numflux = GDTB_NUMFLUX_VIJAYASUNDARAM;
+    this->flux_.p[0] = f.gamma;
+  }
+};
+
+// local/numerical-fluxes/lax-friedrichs.hh:33-58 for systems: lambda has to be provided (:40-41)
+template <class I, std::size_t d, std::size_t m>
+NumericalLaxFriedrichsFlux<I, d, m> make_numerical_lax_friedrichs_flux(const EulerFlux& f, const double lambda)
+{
+  NumericalLaxFriedrichsFlux<I, d, m> g;
+  g.set_euler(f.gamma, lambda);
+  return g;
+}
 
 // Boundary treatments (local/operators/advection-fv.hh:188-457) as value types: v = a u + b / g = a (f(u) . n) + b
 struct BoundaryTreatmentByCustomExtrapolation
@@ -2052,9 +2183,9 @@ public:
   using V = XT::LA::IstlDenseVector<double>;
   static constexpr std::size_t d = GV::dimension;
 
-  template <class I>
+  template <class I, std::size_t m>
   AdvectionFvOperator(const GV& /*assembly_grid_view*/,
-                      const NumericalFluxInterface<I, d, 1>& numerical_flux,
+                      const NumericalFluxInterface<I, d, m>& numerical_flux,
                       const SpaceInterface<GV>& source_space,
                       const SpaceInterface<GV>& range_space)
     : source_space_(source_space)
@@ -2210,9 +2341,9 @@ private:
 };
 
 // operators/advection-fv.hh:130-141
-template <class M, class GV, class I, std::size_t d>
+template <class M, class GV, class I, std::size_t d, std::size_t m>
 AdvectionFvOperator<M, GV> make_advection_fv_operator(const GV& assembly_grid_view,
-                                                      const NumericalFluxInterface<I, d, 1>& numerical_flux,
+                                                      const NumericalFluxInterface<I, d, m>& numerical_flux,
                                                       const SpaceInterface<GV>& source_space,
                                                       const SpaceInterface<GV>& range_space)
 {
@@ -2226,6 +2357,51 @@ V default_interpolation(const XT::Functions::GridFunction<typename GV::Element>&
 {
   V u(std::size_t(fv_space.mapper().size()), 0.);
   internal::check(gdtb_fv_interpolate_host(internal::context(), fv_space.handle(), &f.descriptor(), u.data()));
+  return u;
+}
+
+// default_interpolation<V>(order, lambda, fv_space) for a vector-valued lambda x -> FieldVector<double, m>
+// (interpolations/default.hh:76-83 with spaces/basis/finite-volume.hh:244-252: cell averages by the Gauss rule of the
+// given order; order 0 = the value at the cell centre).  Evaluated on the host (a lambda cannot cross the C ABI), the
+// DoF vector is [element][component].
+template <class V, class GV, class F>
+auto default_interpolation(const int order, F&& f, const SpaceInterface<GV>& fv_space)
+    -> decltype(f(std::declval<FieldVector<double, int(GV::dimension)>>(), XT::Common::Parameter{}), V())
+{
+  constexpr int d = int(GV::dimension);
+  const gdtb_grid_desc& g = fv_space.grid_view().desc();
+  const int m = fv_space.range_dim();
+  std::int32_t nq = 0;
+  std::vector<double> qx(16), qw(16);
+  internal::check(gdtb_gauss_rule(order, &nq, qx.data(), qw.data()));
+  std::int64_t ne = 1;
+  for (int k = 0; k < d; ++k)
+    ne *= g.n[k];
+  V u(std::size_t(ne * m), 0.);
+  for (std::int64_t e = 0; e < ne; ++e) {
+    std::int64_t idx[3] = {0, 0, 0}, r = e;
+    for (int k = 0; k < d; ++k) {
+      idx[k] = r % g.n[k];
+      r /= g.n[k];
+    }
+    int total = 1;
+    for (int k = 0; k < d; ++k)
+      total *= nq;
+    for (int q = 0; q < total; ++q) {
+      FieldVector<double, d> x{};
+      double w = 1.;
+      int qq = q;
+      for (int k = 0; k < d; ++k) {
+        const double h = (g.upper[k] - g.lower[k]) / double(g.n[k]);
+        x[k] = g.lower[k] + (double(idx[k]) + qx[qq % nq]) * h;
+        w *= qw[qq % nq];
+        qq /= nq;
+      }
+      const auto val = f(x, XT::Common::Parameter{});
+      for (int c = 0; c < m; ++c)
+        u[std::size_t(e * m + c)] += w * val[c];
+    }
+  }
   return u;
 }
 

@@ -188,14 +188,22 @@ enum
 
 enum
 {
-  GDTB_FLUX_LINEAR = 0, /* f(u) = a u, a = p[0..d)  (test/linear-transport/base.hh:50-57) */
-  GDTB_FLUX_BURGERS = 1 /* f(u) = u^2/2 (1,...,1)   (test/burgers/base.hh:38-44)          */
+  GDTB_FLUX_LINEAR = 0,  /* f(u) = a u, a = p[0..d)  (test/linear-transport/base.hh:50-57) */
+  GDTB_FLUX_BURGERS = 1, /* f(u) = u^2/2 (1,...,1)   (test/burgers/base.hh:38-44)          */
+  /* Euler equations of gas dynamics, m = d + 2 conservative variables w = (rho, rho v, E), d = 1, 2: EulerTools<d>::flux
+   * / flux_jacobian / eigenvalues_ / eigenvectors_ / eigenvectors_inv_flux_jacobian (tools/euler.hh:212-236, 262-316,
+   * 325-462); p[0] = gamma.  Needs a finite volume space with m components (gdtb_fv_space_create). */
+  GDTB_FLUX_EULER = 2
 };
 
 enum
 {
-  GDTB_NUMFLUX_UPWIND = 0,        /* NumericalUpwindFlux<I,d,1>      upwind.hh:44-73         */
-  GDTB_NUMFLUX_LAX_FRIEDRICHS = 1 /* NumericalLaxFriedrichsFlux      lax-friedrichs.hh:60-88 */
+  GDTB_NUMFLUX_UPWIND = 0,         /* NumericalUpwindFlux<I,d,1>      upwind.hh:44-73         */
+  GDTB_NUMFLUX_LAX_FRIEDRICHS = 1, /* NumericalLaxFriedrichsFlux      lax-friedrichs.hh:60-88; systems (m > 1): the
+                                      caller provides lambda = p[1] (lax-friedrichs.hh:40-41)  */
+  /* NumericalVijayasundaramFlux<I,d,m> (vijayasundaram.hh:111-133) with the flux's own eigendecomposition (the lambda
+   * the reference's 2d_euler driver passes, examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:402-409) */
+  GDTB_NUMFLUX_VIJAYASUNDARAM = 2
 };
 
 typedef struct gdtb_flux
@@ -277,6 +285,11 @@ int64_t gdtb_grid_num_elements(const gdtb_grid* grid);
 
 /* replaces make_{continuous_lagrange,discontinuous_lagrange,finite_volume}_space */
 int gdtb_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int kind, int order, gdtb_space** space);
+/* make_finite_volume_space<m>(grid_view) (spaces/l2/finite-volume.hh:208-230): m DoFs per element, global index
+ * m * element + i (spaces/mapper/finite-volume.hh:92-97); 1 <= range_dim <= 4.  An advection operator on such a space
+ * (gdtb_fvop_create with GDTB_FLUX_EULER) supports gdtb_fvop_apply[_host], gdtb_fvop_euler[_host] and
+ * gdtb_fv_estimate_dt[_host] on periodic or unpartitioned grids. */
+int gdtb_fv_space_create(gdtb_ctx* ctx, const gdtb_grid* grid, int range_dim, gdtb_space** space);
 int gdtb_space_destroy(gdtb_space* space);
 /* MapperInterface::size / max_local_size / global_indices (spaces/mapper/interfaces.hh) */
 int64_t gdtb_space_size(const gdtb_space* space);

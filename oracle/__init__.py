@@ -75,6 +75,12 @@ def lib():
             "orc_csr_mv": (None, [C.c_int64, I64P, I32P, DP, DP, DP]),
             "orc_bilinear_form_apply2": (C.c_double, [G, C.c_int, C.c_int, DP, C.POINTER(Function), C.POINTER(Form)]),
             "orc_lagrange_interpolate": (None, [G, C.c_int, C.c_int, C.POINTER(Function), DP]),
+            "orc_fvsys_apply": (C.c_int, [G, C.POINTER(Flux), DP, DP]),
+            "orc_fvsys_euler": (C.c_int, [G, C.POINTER(Flux), DP, C.c_double, C.c_int64]),
+            "orc_fvsys_estimate_dt": (C.c_double, [G, C.POINTER(Flux), DP]),
+            "orc_euler_flux": (None, [C.c_int, C.c_double, DP, DP]),
+            "orc_euler_jacobian": (None, [C.c_int, C.c_double, DP, DP]),
+            "orc_euler_eigen": (None, [C.c_int, C.c_double, DP, DP, DP, DP, DP]),
         }
         for name, (res, args) in protos.items():
             fn = getattr(h, name)
@@ -281,3 +287,52 @@ def element_integrand_evaluate(integrand, dim, test_values, test_grads, ansatz_v
     if st != 0:
         raise RuntimeError(lib().orc_last_error().decode())
     return out
+
+
+# ---- systems of conservation laws: the Euler equations (tools/euler.hh), m = d + 2 components per cell ------------------
+def fvsys_apply(grid, flux, u):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty_like(u)
+    assert lib().orc_fvsys_apply(C.byref(grid), C.byref(flux), _dp(u), _dp(out)) == 0
+    return out
+
+
+def fvsys_euler(grid, flux, u, dt, n_steps):
+    u = np.array(u, dtype=np.float64, copy=True)
+    assert lib().orc_fvsys_euler(C.byref(grid), C.byref(flux), _dp(u), dt, n_steps) == 0
+    return u
+
+
+def fvsys_estimate_dt(grid, flux, u):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    return lib().orc_fvsys_estimate_dt(C.byref(grid), C.byref(flux), _dp(u))
+
+
+def euler_flux(d, gamma, w):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    f = np.empty((d, d + 2))
+    lib().orc_euler_flux(d, gamma, _dp(w), _dp(f))
+    return f
+
+
+def euler_jacobian(d, gamma, w):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    J = np.empty((d, d + 2, d + 2))
+    lib().orc_euler_jacobian(d, gamma, _dp(w), _dp(J))
+    return J
+
+
+def euler_eigen(d, gamma, w, n):
+    """(eigenvalues, T, T^{-1}) of sum_s n_s A_s(w) (EulerTools::*_flux_jacobian)"""
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    n = np.ascontiguousarray(n, dtype=np.float64)
+    m = d + 2
+    ev, T, Ti = np.empty(m), np.empty((m, m)), np.empty((m, m))
+    lib().orc_euler_eigen(d, gamma, _dp(w), _dp(n), _dp(ev), _dp(T), _dp(Ti))
+    return ev, T, Ti
+
+
+def euler_conservative(gamma, rho, v, p):
+    """EulerTools::conservative (tools/euler.hh:153-157)"""
+    v = np.atleast_1d(np.asarray(v, dtype=np.float64))
+    return np.concatenate([[rho], rho * v, [p / (gamma - 1.0) + 0.5 * rho * float(v @ v)]])

@@ -1191,6 +1191,246 @@ struct RkStepper
   }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Systems of conservation laws (m > 1): the Euler equations.  EulerTools<d> (tools/euler.hh), d = 1, 2, m = d + 2,
+// conservative variables w = (rho, rho v, E); operation order follows the reference.
+// ------------------------------------------------------------------------------------------------
+struct Euler
+{
+  int d;
+  double gamma;
+  int m() const
+  {
+    return d + 2;
+  }
+  // primitives(w) (tools/euler.hh:136-147)
+  void primitives(const double* w, double& rho, double* v, double& p) const
+  {
+    rho = w[0];
+    double v2 = 0.;
+    for (int i = 0; i < d; ++i) {
+      v[i] = w[1 + i] / w[0];
+      v2 += v[i] * v[i];
+    }
+    p = (gamma - 1.) * (w[d + 1] - 0.5 * rho * v2);
+  }
+  // flux(w)[s][i] (:212-236)
+  void flux(const double* w, double* f) const
+  {
+    const int M = m();
+    double rho, v[3], p;
+    primitives(w, rho, v, p);
+    const double E = w[M - 1];
+    for (int ss = 0; ss < d; ++ss) {
+      double* f_s = f + ss * M;
+      f_s[0] = rho * v[ss];
+      for (int ii = 0; ii < d; ++ii)
+        f_s[1 + ii] = rho * v[ii] * v[ss] + (ss == ii ? 1 : 0) * p;
+      f_s[M - 1] = (E + p) * v[ss];
+    }
+  }
+  // flux_jacobian(w)[s][r][c] (:262-316)
+  void jacobian(const double* w, double* J) const
+  {
+    const int M = m();
+    for (int i = 0; i < d * M * M; ++i)
+      J[i] = 0.;
+    const double rho = w[0], E = w[M - 1];
+    double v[3] = {0., 0., 0.};
+    for (int i = 0; i < d; ++i)
+      v[i] = w[1 + i] / w[0];
+    const double gamma_1 = gamma - 1.;
+    double vnorm2 = 0.;
+    for (int i = 0; i < d; ++i)
+      vnorm2 += v[i] * v[i];
+    const double ek = 0.5 * vnorm2;
+    auto at = [&](int s_, int r, int c) -> double& { return J[(s_ * M + r) * M + c]; };
+    if (d == 1) {
+      at(0, 0, 1) = 1.;
+      at(0, 1, 0) = gamma_1 * ek - v[0] * v[0];
+      at(0, 1, 1) = (3. - gamma) * v[0];
+      at(0, 1, 2) = gamma_1;
+      at(0, 2, 0) = v[0] * (gamma_1 * vnorm2 - (gamma * E) / rho);
+      at(0, 2, 1) = ((gamma * E) / rho) - gamma_1 * v[0] * v[0] - gamma_1 * ek;
+      at(0, 2, 2) = gamma * v[0];
+    } else {
+      at(0, 0, 1) = 1.;
+      at(0, 1, 0) = gamma_1 * ek - v[0] * v[0];
+      at(0, 1, 1) = (3. - gamma) * v[0];
+      at(0, 1, 2) = -1. * gamma_1 * v[1];
+      at(0, 1, 3) = gamma_1;
+      at(0, 2, 0) = -1. * v[0] * v[1];
+      at(0, 2, 1) = v[1];
+      at(0, 2, 2) = v[0];
+      at(0, 3, 0) = v[0] * (gamma_1 * vnorm2 - (gamma * E) / rho);
+      at(0, 3, 1) = ((gamma * E) / rho) - gamma_1 * v[0] * v[0] - gamma_1 * ek;
+      at(0, 3, 2) = -1. * gamma_1 * v[0] * v[1];
+      at(0, 3, 3) = gamma * v[0];
+      at(1, 0, 2) = 1.;
+      at(1, 1, 0) = -1. * v[0] * v[1];
+      at(1, 1, 1) = v[1];
+      at(1, 1, 2) = v[0];
+      at(1, 2, 0) = 0.5 * gamma_1 * vnorm2 - v[1] * v[1];
+      at(1, 2, 1) = -1. * gamma_1 * v[0];
+      at(1, 2, 2) = (3. - gamma) * v[1];
+      at(1, 2, 3) = gamma_1;
+      at(1, 3, 0) = v[1] * (gamma_1 * vnorm2 - ((gamma * E) / rho));
+      at(1, 3, 1) = -1. * gamma_1 * v[0] * v[1];
+      at(1, 3, 2) = ((gamma * E) / rho) - gamma_1 * v[1] * v[1] - gamma_1 * ek;
+      at(1, 3, 3) = gamma * v[1];
+    }
+  }
+  // eigenvalues_ / eigenvectors_ / eigenvectors_inv_flux_jacobian(w, n) (:325-462); T, Ti row-major m x m
+  void eigen(const double* w, const double* n, double* ev, double* T, double* Ti) const
+  {
+    const int M = m();
+    double rho, v[3] = {0., 0., 0.}, p;
+    primitives(w, rho, v, p);
+    const double E = w[M - 1];
+    const double a = std::sqrt(gamma * p / rho);
+    const double H = (E + p) / rho;
+    const double rho_over_2a = rho / (2 * a);
+    double v2 = 0., vn = 0.;
+    for (int i = 0; i < d; ++i) {
+      v2 += v[i] * v[i];
+      vn += v[i] * n[i];
+    }
+    const double ek = 0.5 * v2;
+    const double Mach = std::sqrt(v2) / a;
+    const double gamma_1 = gamma - 1.;
+    auto t = [&](int r, int c) -> double& { return T[r * M + c]; };
+    auto ti = [&](int r, int c) -> double& { return Ti[r * M + c]; };
+    if (d == 1) {
+      ev[0] = vn, ev[1] = vn + a, ev[2] = vn - a;
+      t(0, 0) = 1., t(0, 1) = rho_over_2a, t(0, 2) = rho_over_2a;
+      t(1, 0) = v[0], t(1, 1) = rho_over_2a * (v[0] + a * n[0]), t(1, 2) = rho_over_2a * (v[0] - a * n[0]);
+      t(2, 0) = ek, t(2, 1) = rho_over_2a * (H + a * vn), t(2, 2) = rho_over_2a * (H - a * vn);
+      ti(0, 0) = 1. - (gamma_1 / 2.) * Mach * Mach;
+      ti(0, 1) = gamma_1 * v[0] / (a * a);
+      ti(0, 2) = -gamma_1 / (a * a);
+      ti(1, 0) = (a / rho) * ((gamma_1 / 2.) * Mach * Mach - vn / a);
+      ti(1, 1) = (1. / rho) * (n[0] - gamma_1 * (v[0] / a));
+      ti(1, 2) = gamma_1 / (rho * a);
+      ti(2, 0) = (a / rho) * ((gamma_1 / 2.) * Mach * Mach + vn / a);
+      ti(2, 1) = (-1. / rho) * (n[0] + gamma_1 * (v[0] / a));
+      ti(2, 2) = gamma_1 / (rho * a);
+    } else {
+      ev[0] = vn, ev[1] = vn, ev[2] = vn + a, ev[3] = vn - a;
+      t(0, 0) = 1., t(0, 1) = 0., t(0, 2) = rho_over_2a, t(0, 3) = rho_over_2a;
+      t(1, 0) = v[0], t(1, 1) = rho * n[1], t(1, 2) = rho_over_2a * (v[0] + a * n[0]), t(1, 3) = rho_over_2a * (v[0] - a * n[0]);
+      t(2, 0) = v[1], t(2, 1) = -rho * n[0], t(2, 2) = rho_over_2a * (v[1] + a * n[1]), t(2, 3) = rho_over_2a * (v[1] - a * n[1]);
+      t(3, 0) = ek, t(3, 1) = rho * (v[0] * n[1] - v[1] * n[0]), t(3, 2) = rho_over_2a * (H + a * vn), t(3, 3) = rho_over_2a * (H - a * vn);
+      ti(0, 0) = 1. - (gamma_1 / 2.) * Mach * Mach;
+      ti(0, 1) = gamma_1 * v[0] / (a * a);
+      ti(0, 2) = gamma_1 * v[1] / (a * a);
+      ti(0, 3) = -gamma_1 / (a * a);
+      ti(1, 0) = (1. / rho) * (v[1] * n[0] - v[0] * n[1]);
+      ti(1, 1) = n[1] / rho;
+      ti(1, 2) = -n[0] / rho;
+      ti(1, 3) = 0.;
+      ti(2, 0) = (a / rho) * ((gamma_1 / 2.) * Mach * Mach - vn / a);
+      ti(2, 1) = (1. / rho) * (n[0] - gamma_1 * (v[0] / a));
+      ti(2, 2) = (1. / rho) * (n[1] - gamma_1 * (v[1] / a));
+      ti(2, 3) = gamma_1 / (rho * a);
+      ti(3, 0) = (a / rho) * ((gamma_1 / 2.) * Mach * Mach + vn / a);
+      ti(3, 1) = (-1. / rho) * (n[0] + gamma_1 * (v[0] / a));
+      ti(3, 2) = (-1. / rho) * (n[1] + gamma_1 * (v[1] / a));
+      ti(3, 3) = gamma_1 / (rho * a);
+    }
+  }
+};
+
+// numerical flux g(u, v, n) for systems: NumericalVijayasundaramFlux::apply (local/numerical-fluxes/vijayasundaram.hh:111-133)
+// with the EulerTools eigendecomposition (the lambda of examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:402-409), or
+// NumericalLaxFriedrichsFlux::apply (lax-friedrichs.hh:66-88) with the given lambda = p[1]
+void system_numerical_flux(const orc_flux& fl, const Euler& eu, const double* u, const double* v, const double* n, double* g)
+{
+  const int M = eu.m();
+  if (fl.numflux == ORC_NUMFLUX_VIJAYASUNDARAM) {
+    double w[4], ev[4], T[16], Ti[16];
+    for (int i = 0; i < M; ++i)
+      w[i] = 0.5 * (u[i] + v[i]);
+    eu.eigen(w, n, ev, T, Ti);
+    // P_plus = T * lambda_plus * T_inv, P_minus = T * lambda_minus * T_inv (matrix products, left to right)
+    double TLp[16], TLm[16], Pp[16], Pm[16];
+    for (int r = 0; r < M; ++r)
+      for (int c = 0; c < M; ++c) {
+        TLp[r * M + c] = T[r * M + c] * std::max(ev[c], 0.);
+        TLm[r * M + c] = T[r * M + c] * std::min(ev[c], 0.);
+      }
+    for (int r = 0; r < M; ++r)
+      for (int c = 0; c < M; ++c) {
+        double sp = 0., sm = 0.;
+        for (int k = 0; k < M; ++k) {
+          sp += TLp[r * M + k] * Ti[k * M + c];
+          sm += TLm[r * M + k] * Ti[k * M + c];
+        }
+        Pp[r * M + c] = sp;
+        Pm[r * M + c] = sm;
+      }
+    for (int r = 0; r < M; ++r) {
+      double a = 0., b = 0.;
+      for (int c = 0; c < M; ++c) {
+        a += Pp[r * M + c] * u[c];
+        b += Pm[r * M + c] * v[c];
+      }
+      g[r] = a + b;
+    }
+    return;
+  }
+  const double lambda = fl.p[1];
+  double fu[8], fv[8];
+  eu.flux(u, fu);
+  eu.flux(v, fv);
+  for (int i = 0; i < M; ++i)
+    g[i] = 0.;
+  for (int dd = 0; dd < eu.d; ++dd)
+    for (int i = 0; i < M; ++i)
+      g[i] += (fu[dd * M + i] + fv[dd * M + i]) * (n[dd] * 0.5);
+  for (int i = 0; i < M; ++i)
+    g[i] += (u[i] - v[i]) * (0.5 / lambda);
+}
+
+// LocalizableOperator::apply + LocalAdvectionFvCouplingOperator::apply (local/operators/advection-fv.hh:127-153) for m
+// components per cell (DoF m * element + i, spaces/mapper/finite-volume.hh:92-97); no boundary treatments
+void fvsys_apply(const Grid& g, const orc_flux& fl, const double* u, double* out)
+{
+  const Euler eu{g.d, fl.p[0]};
+  const int M = eu.m();
+  for (int64_t i = 0; i < g.ne * M; ++i)
+    out[i] = 0.;
+  for (int64_t e = 0; e < g.ne; ++e) {
+    int64_t idx[3];
+    g.coords(e, idx);
+    double lo_in[3], ext_in[3];
+    g.cell(idx, lo_in, ext_in);
+    for (int k = 0; k < g.d; ++k)
+      for (int s = 0; s < 2; ++s) {
+        int64_t nb[3];
+        bool boundary;
+        if (!g.neighbor(idx, k, s, nb, &boundary))
+          continue;
+        const int64_t eo = g.index(nb);
+        if (!(e < eo))
+          continue;
+        double lo_out[3], ext_out[3];
+        g.cell(nb, lo_out, ext_out);
+        const Face f = make_face(g, ext_in, k, s);
+        double gf[4];
+        system_numerical_flux(fl, eu, u + e * M, u + eo * M, f.normal, gf);
+        const double h_intersection = f.ie;
+        const double hinv_inside = 1. / g.volume(ext_in);
+        const double hinv_outside = 1. / g.volume(ext_out);
+        for (int ii = 0; ii < M; ++ii) {
+          const double g_ii = gf[ii] * h_intersection;
+          out[e * M + ii] += g_ii * hinv_inside;
+          out[eo * M + ii] += -g_ii * hinv_outside;
+        }
+      }
+  }
+}
+
 } // namespace
 
 // ==================================================================================================
@@ -1776,6 +2016,105 @@ int orc_element_integrand_evaluate(const orc_integrand* integrand, int dim, int 
   double xx[3] = {x[0], dim > 1 ? x[1] : 0., dim > 2 ? x[2] : 0.};
   element_integrand_evaluate2(*integrand, test, ansatz, dim, 0, xx, result);
   return 0;
+}
+
+
+// ---- systems (m = d + 2): Euler equations ---------------------------------------------------------------------------
+int orc_fvsys_apply(const orc_grid* g, const orc_flux* flux, const double* u, double* out)
+{
+  Grid gr(g);
+  if (flux->kind != ORC_FLUX_EULER || gr.d > 2)
+    return 1;
+  fvsys_apply(gr, *flux, u, out);
+  return 0;
+}
+
+// explicit_euler of examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:141-159: u <- u - L(u) dt, n_steps times
+int orc_fvsys_euler(const orc_grid* g, const orc_flux* flux, double* u, double dt, int64_t n_steps)
+{
+  Grid gr(g);
+  if (flux->kind != ORC_FLUX_EULER || gr.d > 2)
+    return 1;
+  const int64_t n = gr.ne * (gr.d + 2);
+  std::vector<double> L(n);
+  for (int64_t s = 0; s < n_steps; ++s) {
+    fvsys_apply(gr, *flux, u, L.data());
+    for (int64_t i = 0; i < n; ++i)
+      u[i] = u[i] - L[i] * dt;
+  }
+  return 0;
+}
+
+// estimate_dt_for_hyperbolic_system (tools/hyperbolic.hh:38-86) for the Euler flux (order 4) and a finite volume state
+double orc_fvsys_estimate_dt(const orc_grid* g, const orc_flux* flux, const double* u)
+{
+  Grid gr(g);
+  const Euler eu{gr.d, flux->p[0]};
+  const int M = eu.m();
+  double lo[4], hi[4];
+  for (int c = 0; c < M; ++c) {
+    lo[c] = std::numeric_limits<double>::max();
+    hi[c] = std::numeric_limits<double>::min();
+  }
+  for (int64_t e = 0; e < gr.ne; ++e)
+    for (int c = 0; c < M; ++c) {
+      lo[c] = std::min(lo[c], u[e * M + c]);
+      hi[c] = std::max(hi[c], u[e * M + c]);
+    }
+  for (int c = 0; c < M; ++c)
+    if (!(lo[c] < hi[c]))
+      hi[c] = lo[c] + 1e-6 * lo[c];
+  double max_flux_derivative = std::numeric_limits<double>::min();
+  const int nq = gauss_m(4);
+  double qx[8], qw[8];
+  gauss01(nq, qx, qw);
+  int64_t total = 1;
+  for (int c = 0; c < M; ++c)
+    total *= nq;
+  std::vector<double> J(gr.d * M * M);
+  for (int64_t t = 0; t < total; ++t) {
+    double w[4];
+    int64_t r = t;
+    for (int c = 0; c < M; ++c) {
+      w[c] = lo[c] + qx[r % nq] * (hi[c] - lo[c]);
+      r /= nq;
+    }
+    eu.jacobian(w, J.data());
+    for (int ss = 0; ss < gr.d; ++ss)
+      for (int rr = 0; rr < M; ++rr) {
+        double sum = 0.;
+        for (int cc = 0; cc < M; ++cc)
+          sum += std::fabs(J[(ss * M + rr) * M + cc]);
+        max_flux_derivative = std::max(max_flux_derivative, sum); // FieldMatrix::infinity_norm
+      }
+  }
+  double perimeter_over_volume = std::numeric_limits<double>::min();
+  for (int64_t e = 0; e < gr.ne; ++e) {
+    int64_t idx[3];
+    gr.coords(e, idx);
+    double lower[3], ext[3];
+    gr.cell(idx, lower, ext);
+    double perimeter = 0;
+    for (int k = 0; k < gr.d; ++k)
+      for (int s = 0; s < 2; ++s)
+        perimeter += make_face(gr, ext, k, s).ie;
+    perimeter_over_volume = std::max(perimeter_over_volume, perimeter / gr.volume(ext));
+  }
+  return 1. / (perimeter_over_volume * max_flux_derivative);
+}
+
+// EulerTools pieces for the property tests: flux [d][m], jacobian [d][m][m], eigendecomposition of jacobian . n
+void orc_euler_flux(int d, double gamma, const double* w, double* f)
+{
+  Euler{d, gamma}.flux(w, f);
+}
+void orc_euler_jacobian(int d, double gamma, const double* w, double* J)
+{
+  Euler{d, gamma}.jacobian(w, J);
+}
+void orc_euler_eigen(int d, double gamma, const double* w, const double* n, double* ev, double* T, double* Ti)
+{
+  Euler{d, gamma}.eigen(w, n, ev, T, Ti);
 }
 
 } // extern "C"

@@ -134,14 +134,16 @@ typedef struct orc_form
 
 enum
 {
-  ORC_FLUX_LINEAR = 0, /* f(u) = a * u, a = p[0..d)          */
-  ORC_FLUX_BURGERS = 1 /* f(u) = 0.5 u^2 * (1,...,1)         */
+  ORC_FLUX_LINEAR = 0,  /* f(u) = a * u, a = p[0..d)          */
+  ORC_FLUX_BURGERS = 1, /* f(u) = 0.5 u^2 * (1,...,1)         */
+  ORC_FLUX_EULER = 2    /* EulerTools<d>::flux, p[0] = gamma (tools/euler.hh), m = d + 2 */
 };
 
 enum
 {
   ORC_NUMFLUX_UPWIND = 0,
-  ORC_NUMFLUX_LAX_FRIEDRICHS = 1
+  ORC_NUMFLUX_LAX_FRIEDRICHS = 1,
+  ORC_NUMFLUX_VIJAYASUNDARAM = 2 /* local/numerical-fluxes/vijayasundaram.hh:111-133 (systems) */
 };
 
 typedef struct orc_flux
@@ -229,6 +231,16 @@ double orc_fv_estimate_dt(const orc_grid* g, const orc_flux* flux, const double*
 /* default_interpolation into the FV space: cell average by a Gauss rule of the declared order
  * (spaces/basis/finite-volume.hh:244-252) */
 void orc_fv_interpolate(const orc_grid* g, const orc_function* f, double* u);
+
+/* systems of conservation laws: the Euler equations (flux kind ORC_FLUX_EULER, p[0] = gamma; Lax-Friedrichs: lambda =
+ * p[1]), m = d + 2 components per cell, DoF m * element + i; tools/euler.hh, local/operators/advection-fv.hh:127-153,
+ * examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:141-159, tools/hyperbolic.hh:38-86 */
+int orc_fvsys_apply(const orc_grid* g, const orc_flux* flux, const double* u, double* out);
+int orc_fvsys_euler(const orc_grid* g, const orc_flux* flux, double* u, double dt, int64_t n_steps);
+double orc_fvsys_estimate_dt(const orc_grid* g, const orc_flux* flux, const double* u);
+void orc_euler_flux(int d, double gamma, const double* w, double* f);
+void orc_euler_jacobian(int d, double gamma, const double* w, double* J);
+void orc_euler_eigen(int d, double gamma, const double* w, const double* n, double* ev, double* T, double* Ti);
 
 /* evaluate a function descriptor at a global point (scalar view) */
 double orc_function_eval(const orc_function* f, int dim, const double* x, int64_t element);

@@ -7,7 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXAMPLES = os.path.join(ROOT, "dune-gdt_b200", "examples")
-PROGS = ["stationary-heat-equation", "linear-transport-fv", "elliptic-swipdg", "generic-function-check", "parallel-slabs"]
+PROGS = ["stationary-heat-equation", "linear-transport-fv", "elliptic-swipdg", "generic-function-check", "parallel-slabs", "euler-2d"]
 
 
 def build_examples():
@@ -41,7 +41,9 @@ def test_examples_fail_loudly_without_a_gpu(gdt):
                                   # GenericFunction lambdas (sampled by the facade) vs built-in / constant coefficients
                                   ["generic-function-check"],
                                   # multi-GPU entry points of the facade with one rank (a periodic slab is its own neighbour)
-                                  ["parallel-slabs"]])
+                                  ["parallel-slabs"],
+                                  # the reference's 2d_euler driver (systems, m = 4): conservation, positivity, symmetry
+                                  ["euler-2d", "64", "0.25"]])
 def test_examples_run(gdt, args):
     build_examples()
     r = subprocess.run([os.path.join(EXAMPLES, args[0])] + args[1:], capture_output=True, text=True, timeout=300)
