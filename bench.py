@@ -210,6 +210,31 @@ def fv_extra(gdt, ctx, torch, hbm_gbs, peak_src):
     out["same_size_device_copy"] = {"ms": copy_ms, "GBps": 16.0 * n * n / (copy_ms * 1e-3) / 1e9,
                                     "apply_over_copy": out["linear_transport"]["ms_per_apply"] / copy_ms}
     del a, b
+    # systems (m = 4): the 2D Euler equations with the Vijayasundaram flux (examples/mpi_2019_02...cc:381-434), 2048^2 cells
+    ns = 2048
+    sgrid = gdt.make_cube_grid(ctx, -1.0, 1.0, [ns, ns], periodic=3)
+    sspace = gdt.make_finite_volume_space(sgrid, 4)
+    euler = gdt.EulerTools(2, 1.4)
+    Ls = gdt.make_advection_fv_operator(gdt.NumericalVijayasundaramFlux(*euler.flux()), sspace)
+    w = torch.empty(ns * ns, 4, dtype=torch.float64, device="cuda")
+    w[:, 0] = 1.0 + 0.5 * torch.rand(ns * ns, dtype=torch.float64, device="cuda")
+    w[:, 1:3] = 0.2 * (torch.rand(ns * ns, 2, dtype=torch.float64, device="cuda") - 0.5)
+    w[:, 3] = 2.0 + torch.rand(ns * ns, dtype=torch.float64, device="cuda")
+    wo = torch.empty_like(w)
+    for _ in range(3):
+        Ls.apply_device(w.data_ptr(), wo.data_ptr())
+    kernel_time(gdt, ctx, "fv_apply")
+    for _ in range(20):
+        Ls.apply_device(w.data_ptr(), wo.data_ptr())
+    ms, cnt = kernel_time(gdt, ctx, "fv_apply")
+    per = ms / max(cnt, 1)
+    out["euler_2d_vijayasundaram_2048^2"] = {
+        "cells_per_s": ns * ns / (per * 1e-3), "ms_per_apply": per,
+        "roofline": {"bound": "hbm", "achieved": 64.0 * ns * ns / (per * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": 64.0 * ns * ns / (per * 1e-3) / 1e9 / hbm_gbs, "peak_source": peak_src},
+        "note": "64 B/cell (4 components in, 4 out); every face flux (eigendecomposition of a 4 x 4 jacobian) is evaluated "
+                "from both sides: FP64-pipe bound, not HBM bound"}
+    del w, wo
     # the caller of the apply: one SSP3 Runge-Kutta step (tools/timestepper/explicit-rungekutta.hh:237-270), stages fused
     # into the applies (9 vector passes) against separate axpy passes (18)
     lib, check = gdt.capi.lib(), gdt.capi.check
