@@ -444,6 +444,11 @@ class MatrixOperator:
     def plan(self):
         return lib().gdtb_matop_plan(self._h).decode()
 
+    @property
+    def plan_reason(self):
+        """why the operator takes the generic kernels ("" on a row-gather path)"""
+        return lib().gdtb_matop_plan_reason(self._h).decode()
+
     def assemble(self, use_tbb=False):
         """one grid walk (matrix-based.hh:496-500); afterwards the functor list is empty like after Walker::walk"""
         if len(self._functionals) > 1:

@@ -110,6 +110,7 @@ PROTOTYPES = {
     "gdtb_matop_clear_forms": (C.c_int, [_P]),
     "gdtb_matop_num_forms": (C.c_int, [_P]),
     "gdtb_matop_plan": (C.c_char_p, [_P]),
+    "gdtb_matop_plan_reason": (C.c_char_p, [_P]),
     "gdtb_matop_set_zero": (C.c_int, [_P]),
     "gdtb_matop_values_download": (C.c_int, [_P, _DP]),
     "gdtb_matop_values_upload": (C.c_int, [_P, _DP]),

@@ -536,6 +536,14 @@ int launch_dg_gather_fast(Launch& L, DgGatherParams& p, double* values, bool acc
   GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DGG_THREADS, smem));
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "dg_gather: kernel does not fit on an SM");
+  // shared-memory carve-out: what the resident blocks need (dynamic + static + 1 KB each), the rest of the 256 KB stays L1
+  {
+    cudaFuncAttributes fa;
+    GDTB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const size_t per_block = smem + fa.sharedSizeBytes + 1024;
+    GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)std::min<size_t>(100, ((size_t)per_sm * per_block * 100) / (228 * 1024) + 2)));
+  }
   const long long nitems = ((p.e_end - p.e_begin) * N + DGG_THREADS - 1) / DGG_THREADS;
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)

@@ -791,6 +791,14 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
   GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rows_per_item, smem));
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "q1_gather: kernel does not fit on an SM");
+  // shared-memory carve-out: what the resident blocks need (dynamic + static + 1 KB each), the rest of the 256 KB stays L1
+  {
+    cudaFuncAttributes fa;
+    GDTB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const size_t per_block = smem + fa.sharedSizeBytes + 1024;
+    GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)std::min<size_t>(100, ((size_t)per_sm * per_block * 100) / (228 * 1024) + 2)));
+  }
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > nitems)
     grid = nitems;
@@ -1152,6 +1160,14 @@ int launch_q1_qp_dmk(Launch& L, const Q1QpParams& p, double* values, bool accumu
   GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Q1G_ROWS, smem));
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "q1_gather_qp: kernel does not fit on an SM");
+  // shared-memory carve-out: what the resident blocks need (dynamic + static + 1 KB each), the rest of the 256 KB stays L1
+  {
+    cudaFuncAttributes fa;
+    GDTB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const size_t per_block = smem + fa.sharedSizeBytes + 1024;
+    GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)std::min<size_t>(100, ((size_t)per_sm * per_block * 100) / (228 * 1024) + 2)));
+  }
   long long grid = std::min<long long>((long long)per_sm * L.sm_count, nitems);
   note_kernel(L, KF_Q1_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_Q1_GATHER);

@@ -846,6 +846,14 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
   GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Q2G_THREADS, smem));
   if (per_sm < 1)
     return fail(GDTB_ERR_CUDA, "q2_gather: kernel does not fit on an SM");
+  // shared-memory carve-out: what the resident blocks need (dynamic + static + 1 KB each), the rest of the 256 KB stays L1
+  {
+    cudaFuncAttributes fa;
+    GDTB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const size_t per_block = smem + fa.sharedSizeBytes + 1024;
+    GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)std::min<size_t>(100, ((size_t)per_sm * per_block * 100) / (228 * 1024) + 2)));
+  }
   long long grid = (long long)per_sm * L.sm_count;
   if (grid > p.n_items)
     grid = p.n_items;

@@ -309,8 +309,16 @@ __device__ __forceinline__ long long xf_offset_of_lex(const GridDev& g, const Q2
   return q2_row_offset<3>(g, rg, ux, uy, ul);
 }
 
+// register budget: 2 blocks x 5 warps per SM.  __launch_bounds__(160, 2) makes ptxas stop at 168 registers (it rounds
+// the block up to 6 warps); XF_MAXNREG states the budget directly (200 x 160 x 2 = 64 000 registers).
+#ifdef XF_MAXNREG
+#define XF_KERNEL_ATTR __maxnreg__(XF_MAXNREG)
+#else
+#define XF_KERNEL_ATTR __launch_bounds__(XF_THREADS, 2)
+#endif
+
 template <int M, int KIND, bool ACCUMULATE>
-__global__ void __launch_bounds__(XF_THREADS, 2)
+__global__ void XF_KERNEL_ATTR
     k_q2_qp_xfused(const __grid_constant__ XfParams p, double* __restrict__ values)
 {
   constexpr int NQ = M * M * M;
@@ -556,7 +564,12 @@ int launch_q2_qp_xfused(Launch& L, const GridDev& g, const CgQpGroup& group, con
   const size_t smem = sizeof(double) * ((size_t)XF_STAGE + 4 * (size_t)p.line_cap);
   XfKernel kern = group.m == 2 ? xf_kernel_m<2>(group.kind, accumulate) : xf_kernel_m<3>(group.kind, accumulate);
   GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // two resident blocks need 2 x (smem + 1 KB) of the 228 KB: the rest stays L1 (register spills of the unrolled
+  // arithmetic and the table loads live there) instead of the maximal shared-memory carve-out
+  static const int carve_env = std::getenv("GDTB_XF_CARVEOUT") ? std::atoi(std::getenv("GDTB_XF_CARVEOUT")) : 0;
+  int carve = carve_env > 0 ? carve_env : (int)((2 * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 1;
+  carve = std::min(100, std::max(carve, 1));
+  GDTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   int per_sm = 0;
   GDTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XF_THREADS, smem));
   if (per_sm < 1)

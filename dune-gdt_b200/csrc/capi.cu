@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include <cstdio>
+
 #include "fv_system.hpp"
 #include "kernels.hpp"
 
@@ -1433,6 +1435,44 @@ const char* gdtb_matop_plan(gdtb_matop* op)
   return op->plan.c_str();
 }
 
+const char* gdtb_matop_plan_reason(gdtb_matop* op)
+{
+  if (!op)
+    return "";
+  if (std::string(gdtb_matop_plan(op)) != "generic_coloured")
+    return "";
+  const SpaceDev& sp = op->test;
+  const GridDev& g = op->grid;
+  const bool cg = sp.kind == GDTB_SPACE_CG, dg = sp.kind == GDTB_SPACE_DG;
+  const size_t n_forms = op->element_forms.size() + op->coupling_forms.size() + op->boundary_forms.size();
+  if (n_forms == 0)
+    return "no forms appended";
+  if (std::memcmp(&op->test, &op->ansatz, sizeof(SpaceDev)) != 0)
+    return "test and ansatz space differ";
+  if (sp.kind == GDTB_SPACE_FV)
+    return "finite volume spaces have no row-gather assembly kernel";
+  if (cg && sp.K >= 3)
+    return "continuous Lagrange order >= 3: only the quadrature-faithful kernels cover it";
+  if (cg && sp.K == 2 && g.d == 1)
+    return "the CG Q2 row-gather kernels are 2D / 3D";
+  if (cg && (!op->coupling_forms.empty() || !op->boundary_forms.empty()))
+    return "intersection forms on a continuous space";
+  if (cg && op->pattern && op->pattern->stencil != GDTB_STENCIL_ELEMENT)
+    return "the CG row-gather kernels follow the element stencil";
+  if (dg && !dg_gather_supported(g.d, sp.K))
+    return "DG row gather: order 1 (1D - 3D) or order 2 (1D / 2D)";
+  if (dg && op->pattern && op->pattern->stencil != GDTB_STENCIL_ELEMENT_AND_INTERSECTION)
+    return "the DG row-gather kernels follow the element_and_intersection stencil";
+  if (dg && g.periodic && !grid_dg_closed_form(g))
+    return "periodic direction with fewer than 3 cells";
+  if (dg && g.periodic && (sp.K != 1 || !matop_dg_scalar_coefficients(op)))
+    return "periodic grid view: only the factorised DG kernels (order 1, constant / element-wise scalar coefficients) know "
+           "the wrap neighbours";
+  if (n_forms > (size_t)DGG_MAX_FORMS)
+    return "too many forms for one gather pass";
+  return "this combination of integrands / coefficient kinds has no row-gather kernel";
+}
+
 int gdtb_matop_set_zero(gdtb_matop* op)
 {
   if (!op)
@@ -2290,6 +2330,12 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
 
   // --- generic path --------------------------------------------------------------------------
   if (op && !op_fast && !op_q2 && !op_qp && !op_dg) {
+    static const bool warn_generic = std::getenv("GDTB_WARN_GENERIC") != nullptr;
+    if (warn_generic && !op->warned_generic) {
+      op->warned_generic = true;
+      std::fprintf(stderr, "gdtb: operator %p assembles through the generic coloured-scatter kernels: %s\n", (void*)op,
+                   gdtb_matop_plan_reason(op));
+    }
     const gdtb_pattern* pat = op->pattern;
     if (!accumulate)
       GDTB_CUDA(cudaMemsetAsync(op->d_values, 0, sizeof(double) * (size_t)pat->nnz, L.stream));

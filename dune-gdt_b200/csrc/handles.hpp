@@ -86,6 +86,7 @@ struct gdtb_matop
   bool owns_values;
   std::vector<LoweredForm> element_forms, coupling_forms, boundary_forms;
   std::string plan;
+  bool warned_generic = false; // GDTB_WARN_GENERIC: the slow-path note has been printed for this operator
   void* d_forms = nullptr; // lowered FormDev array of the DG gather path
   size_t d_forms_bytes = 0;
   std::vector<char> h_forms_cache; // what d_forms holds

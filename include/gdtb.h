@@ -358,6 +358,10 @@ int gdtb_matop_clear_forms(gdtb_matop* op);
 int gdtb_matop_num_forms(const gdtb_matop* op);
 /* name of the kernel family the next assemble will use: "q1_gather", "generic_coloured", ... (diagnostics) */
 const char* gdtb_matop_plan(gdtb_matop* op);
+/* Why the next assemble takes that family: for "generic_coloured" (the quadrature-faithful any-configuration kernels,
+ * several times the compulsory memory traffic) the first property of the operator that rules out the row-gather
+ * kernels, "" otherwise.  With GDTB_WARN_GENERIC=1 in the environment gdtb_assemble prints it once per operator. */
+const char* gdtb_matop_plan_reason(gdtb_matop* op);
 int gdtb_matop_set_zero(gdtb_matop* op);
 int gdtb_matop_values_download(const gdtb_matop* op, double* values);
 int gdtb_matop_values_upload(gdtb_matop* op, const double* values);

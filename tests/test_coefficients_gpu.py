@@ -224,6 +224,16 @@ def test_q3_in_3d_mapping_pattern_and_matrix(gdt, ctx, oracle, kind):
     rowptr, colidx, values, b, plan = gpu_assemble(gdt, ctx, gdesc, kind, 3, D.STENCIL_ELEMENT, element=forms,
                                                    rhs=[source(D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 1.0, 1.3))])
     assert plan == "generic_coloured"
+    if kind == CG:  # the cliff is not silent: the operator says why it takes the generic kernels
+        space = make_space(gdt, ctx, gdesc, kind, 3)
+        op = gdt.MatrixOperator(space, space, gdt.SparsityPattern(space, space, D.STENCIL_ELEMENT))
+        gdt.capi.check(gdt.capi.lib().gdtb_matop_append_element(op._h, C.byref(forms[0])))
+        assert "order >= 3" in op.plan_reason
+        lib = gdt.capi.lib()
+        q1 = make_space(gdt, ctx, gdesc, kind, 1)
+        fast = gdt.MatrixOperator(q1, q1, gdt.SparsityPattern(q1, q1, D.STENCIL_ELEMENT))
+        gdt.capi.check(lib.gdtb_matop_append_element(fast._h, C.byref(forms[0])))
+        assert fast.plan == "q1_gather" and fast.plan_reason == ""
     rp, ci = oracle.pattern(gdesc, (kind, 3))
     assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
     ref_v, ref_b = oracle.assemble(gdesc, kind, 3, rp, ci, forms, rhs_forms=[source(D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 1.0, 1.3))])
