@@ -2426,6 +2426,8 @@ static void fvsys_fill_params(const gdtb_fvop* L, FvSysParams& p)
     p.inv_ext[k] = L->d_ext + L->inv_ext_shift + L->ext_offset[k];
   p.euler = 0;
   p.dt = 0.;
+  p.wall_mask = L->bnd_nf_mask;
+  p.mirror_mask = L->bnd_ext_mask;
 }
 
 #define GDTB_NO_SYSTEMS(L, what)                                                                                            \
@@ -2564,12 +2566,21 @@ int gdtb_fvop_append_boundary(gdtb_fvop* L, const gdtb_fv_boundary* t)
 {
   if (!L || !t)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "gdtb_fvop_append_boundary: NULL argument");
-  GDTB_NO_SYSTEMS(L, "gdtb_fvop_append_boundary");
-  if (t->kind != GDTB_FVBND_EXTRAPOLATION && t->kind != GDTB_FVBND_NUMERICAL_FLUX)
-    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown boundary treatment");
   const unsigned all = (1u << (2 * L->grid.d)) - 1u;
   if (t->side_mask & ~all)
     return fail(GDTB_ERR_INVALID_ARGUMENT, "boundary treatment: side_mask names a side the grid does not have");
+  if (fv_is_system(L)) {
+    // systems: the impermeable-wall treatments of the Euler equations (the masks of the scalar families are reused:
+    // numerical boundary flux -> wall flux, extrapolation -> mirrored state)
+    if (t->kind != GDTB_FVBND_EULER_IMPERMEABLE_WALL && t->kind != GDTB_FVBND_EULER_INVISCID_MIRROR)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "boundary treatments of systems: GDTB_FVBND_EULER_IMPERMEABLE_WALL / _INVISCID_MIRROR");
+    if (t->kind == GDTB_FVBND_EULER_INVISCID_MIRROR && (t->side_mask & L->bnd_ext_mask))
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "two extrapolation treatments on the same boundary side");
+    (t->kind == GDTB_FVBND_EULER_INVISCID_MIRROR ? L->bnd_ext_mask : L->bnd_nf_mask) |= t->side_mask;
+    return GDTB_OK;
+  }
+  if (t->kind != GDTB_FVBND_EXTRAPOLATION && t->kind != GDTB_FVBND_NUMERICAL_FLUX)
+    return fail(GDTB_ERR_INVALID_ARGUMENT, "unknown boundary treatment");
   if (t->kind == GDTB_FVBND_EXTRAPOLATION && (t->side_mask & L->bnd_ext_mask))
     return fail(GDTB_ERR_NOT_IMPLEMENTED, "two extrapolation treatments on the same boundary side");
   for (int side = 0; side < 2 * L->grid.d; ++side) {

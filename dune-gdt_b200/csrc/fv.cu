@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "fv_tma.hpp"
 #include "kernels.hpp"
 
 namespace gdtb {
@@ -755,7 +756,14 @@ int launch_fv_apply(Launch& L, const FvParams& p, const double* u, double* out)
       fused_bits |= reinterpret_cast<uintptr_t>(p.stage_v[j]);
   }
   time_begin(L, KF_FV_APPLY);
-  if (g.d == 1) {
+  // GDTB_FV_TMA=1: source staged in shared memory by TMA bulk loads (fv_tma.cu: warp-specialised loader / marching warps,
+  // mbarrier ring).  Measured on B200 at 4096^2: 54.7 - 58.9 us against 50.9 us for the register-marching kernel below (the
+  // L2 -> SM path caps both the same way, B300_MICROARCH "LTS throughput cap ... LDG == TMA"), so it is opt-in; read per
+  // launch so that one process can compare both.
+  const char* tma_env = std::getenv("GDTB_FV_TMA");
+  if (tma_env && tma_env[0] == '1' && fv_tma_eligible(p, u, out)) {
+    GDTB_TRY(launch_fv_tma(L, p, u, out));
+  } else if (g.d == 1) {
     const int block = 256;
     k_fv_apply<1><<<(unsigned)((layers + block - 1) / block), block, 0, L.stream>>>(p, u, out);
   } else {

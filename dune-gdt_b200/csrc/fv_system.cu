@@ -176,6 +176,52 @@ __global__ void __launch_bounds__(128) k_fvsys_apply(const __grid_constant__ FvS
     const int nk = (int)g.n[k];
     const bool per = ((g.periodic >> k) & 1) && nk > 1;
     const double rk = __ldg(p.inv_ext[k] + idx[k]);
+    // impermeable walls on a domain side without a neighbour (test/inviscid-compressible-flow/base.hh:187-241).  The
+    // reference adds g(u, n) |I| / |E| with the outer normal n = -+e_k; along +e_k that is -g for the lower and +g for the
+    // upper face.  Wall flux: g = (0, p n, 0), i.e. (0, p e_k, 0) along +e_k on either side.  Mirror: ghost state with the
+    // normal velocity reflected, g = numerical_flux(u, v, n) = (by P(w, -n) = -P(w, n)) the flux along +e_k with the ghost
+    // on the side of the wall.
+    if (!per && (idx[k] == 0 || idx[k] == nk - 1) && ((p.wall_mask | p.mirror_mask) != 0u)) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if ((s == 0 ? idx[k] != 0 : idx[k] != nk - 1))
+          continue;
+        const unsigned bit = 1u << (2 * k + s);
+        const double sign = s ? 1. : -1.;
+        if (p.wall_mask & bit) {
+          const EulerState<D> st(p.gamma, uc);
+          acc[1 + k] += sign * st.p * rk;
+        }
+        if (p.mirror_mask & bit) {
+          double vg[M], G[M];
+#pragma unroll
+          for (int i = 0; i < M; ++i)
+            vg[i] = uc[i];
+          {
+            // conservative(rho, v - 2 (v . n) n, p): only the momentum along k changes sign, the energy is unchanged up to
+            // rounding; evaluated like the reference (primitives -> reflected velocity -> conservative)
+            const EulerState<D> st(p.gamma, uc);
+            double vel[D], v2 = 0.;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              vel[i] = st.v[i] - (i == k ? 2. * st.v[k] : 0.);
+              v2 += vel[i] * vel[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+              vg[1 + i] = st.rho * vel[i];
+            vg[M - 1] = st.p / (p.gamma - 1.) + 0.5 * st.rho * v2;
+          }
+          if (s)
+            numflux_k<D, NUMFLUX>(p, uc, vg, k, G);
+          else
+            numflux_k<D, NUMFLUX>(p, vg, uc, k, G);
+#pragma unroll
+          for (int i = 0; i < M; ++i)
+            acc[i] += sign * G[i] * rk;
+        }
+      }
+    }
     // lower face: inside = the lower neighbour, outside = this cell
     if (idx[k] > 0 || per) {
       const long long en = e + (idx[k] > 0 ? -stride[k] : (long long)(nk - 1) * stride[k]);

@@ -19,6 +19,8 @@ struct FvSysParams
   const double* inv_ext[3]; // 1 / cell extent per axis
   int euler;                // 0: out = L(u), 1: out = u - dt L(u)
   double dt;
+  // impermeable walls on non-periodic domain sides (bit 2k + s): wall flux (0, p n, 0) / mirrored ghost state
+  unsigned wall_mask, mirror_mask;
 };
 
 int launch_fvsys_apply(Launch& L, const FvSysParams& p, const double* u, double* out);

@@ -226,7 +226,7 @@ def flux(kind, numflux=NUMFLUX_UPWIND, params=()):
     return fl
 
 
-FVBND_EXTRAPOLATION, FVBND_NUMERICAL_FLUX = 0, 1
+FVBND_EXTRAPOLATION, FVBND_NUMERICAL_FLUX, FVBND_EULER_IMPERMEABLE_WALL, FVBND_EULER_INVISCID_MIRROR = 0, 1, 2, 3
 RK_EULER, RK_SSP2, RK_SSP3, RK_CLASSIC4, RK_OTHER = 0, 1, 2, 3, 4
 
 # internal::ButcherArrayProvider (tools/timestepper/explicit-rungekutta.hh:63-141): A (row-major), b, c

@@ -221,7 +221,13 @@ typedef struct gdtb_flux
 enum
 {
   GDTB_FVBND_EXTRAPOLATION = 0, /* v = a u + b, g = numerical_flux(u, v, n): a=1,b=0 absorbing; a=0 Dirichlet value b */
-  GDTB_FVBND_NUMERICAL_FLUX = 1 /* g = a (f(u) . n) + b: a=1,b=0 outflow of the physical flux; a=0 prescribed flux b  */
+  GDTB_FVBND_NUMERICAL_FLUX = 1, /* g = a (f(u) . n) + b: a=1,b=0 outflow of the physical flux; a=0 prescribed flux b */
+  /* the two impermeable-wall treatments of the Euler equations the reference's tests append to a system operator
+   * (test/inviscid-compressible-flow/base.hh:187-241; a, b unused):                                                   */
+  GDTB_FVBND_EULER_IMPERMEABLE_WALL = 2, /* numerical boundary flux g = EulerTools::flux_at_impermeable_walls(u, n)     */
+                                         /* = (0, p n, 0) (tools/euler.hh:238-251, [DF2015, (8.58)])                     */
+  GDTB_FVBND_EULER_INVISCID_MIRROR = 3   /* extrapolation v = conservative(rho, v - 2 (v . n) n, p), g = numerical_flux  */
+                                         /* (u, v, n) ([DF2015, (8.66-8.67)])                                            */
 };
 typedef struct gdtb_fv_boundary
 {

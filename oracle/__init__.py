@@ -77,6 +77,7 @@ def lib():
             "orc_lagrange_interpolate": (None, [G, C.c_int, C.c_int, C.POINTER(Function), DP]),
             "orc_fvsys_apply": (C.c_int, [G, C.POINTER(Flux), DP, DP]),
             "orc_fvsys_euler": (C.c_int, [G, C.POINTER(Flux), DP, C.c_double, C.c_int64]),
+            "orc_fvsys_apply_walls": (C.c_int, [G, C.POINTER(Flux), C.c_uint32, C.c_uint32, DP, DP]),
             "orc_fvsys_estimate_dt": (C.c_double, [G, C.POINTER(Flux), DP]),
             "orc_euler_flux": (None, [C.c_int, C.c_double, DP, DP]),
             "orc_euler_jacobian": (None, [C.c_int, C.c_double, DP, DP]),
@@ -294,6 +295,14 @@ def fvsys_apply(grid, flux, u):
     u = np.ascontiguousarray(u, dtype=np.float64)
     out = np.empty_like(u)
     assert lib().orc_fvsys_apply(C.byref(grid), C.byref(flux), _dp(u), _dp(out)) == 0
+    return out
+
+
+def fvsys_apply_walls(grid, flux, u, wall_mask=0, mirror_mask=0):
+    """impermeable walls on the domain sides of the masks (bit 2k + s): wall flux / mirrored ghost state"""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty_like(u)
+    assert lib().orc_fvsys_apply_walls(C.byref(grid), C.byref(flux), wall_mask, mirror_mask, _dp(u), _dp(out)) == 0
     return out
 
 

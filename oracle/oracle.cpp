@@ -1394,7 +1394,8 @@ void system_numerical_flux(const orc_flux& fl, const Euler& eu, const double* u,
 
 // LocalizableOperator::apply + LocalAdvectionFvCouplingOperator::apply (local/operators/advection-fv.hh:127-153) for m
 // components per cell (DoF m * element + i, spaces/mapper/finite-volume.hh:92-97); no boundary treatments
-void fvsys_apply(const Grid& g, const orc_flux& fl, const double* u, double* out)
+void fvsys_apply(const Grid& g, const orc_flux& fl, const double* u, double* out, unsigned wall_mask = 0,
+                 unsigned mirror_mask = 0)
 {
   const Euler eu{g.d, fl.p[0]};
   const int M = eu.m();
@@ -1409,8 +1410,44 @@ void fvsys_apply(const Grid& g, const orc_flux& fl, const double* u, double* out
       for (int s = 0; s < 2; ++s) {
         int64_t nb[3];
         bool boundary;
-        if (!g.neighbor(idx, k, s, nb, &boundary))
+        if (!g.neighbor(idx, k, s, nb, &boundary)) {
+          // impermeable walls (test/inviscid-compressible-flow/base.hh:187-241) on the sides selected by the masks:
+          // LocalAdvectionFvBoundaryTreatmentByCustomNumericalFluxOperator with g = flux_at_impermeable_walls(u, n)
+          // (tools/euler.hh:238-251) / ...ByCustomExtrapolationOperator with the mirrored state ([DF2015, (8.66-8.67)])
+          const unsigned bit = 1u << (2 * k + s);
+          if (!((wall_mask | mirror_mask) & bit))
+            continue;
+          const Face f = make_face(g, ext_in, k, s);
+          const double factor = f.ie / g.volume(ext_in); // local/operators/advection-fv.hh:293, 440
+          const double* uu = u + e * M;
+          if (wall_mask & bit) {
+            double rho, v[3], p;
+            eu.primitives(uu, rho, v, p);
+            for (int ii = 0; ii < g.d; ++ii)
+              out[e * M + 1 + ii] += (f.normal[ii] * p) * factor;
+          }
+          if (mirror_mask & bit) {
+            double rho, v[3] = {0., 0., 0.}, p;
+            eu.primitives(uu, rho, v, p);
+            double vn = 0.;
+            for (int ii = 0; ii < g.d; ++ii)
+              vn += v[ii] * f.normal[ii];
+            double vv[4], v2 = 0.;
+            for (int ii = 0; ii < g.d; ++ii) {
+              v[ii] -= f.normal[ii] * 2. * vn;
+              v2 += v[ii] * v[ii];
+            }
+            vv[0] = rho;
+            for (int ii = 0; ii < g.d; ++ii)
+              vv[1 + ii] = v[ii] * rho;
+            vv[M - 1] = p / (eu.gamma - 1.) + 0.5 * rho * v2; // EulerTools::conservative / energy (:127-131, 153-157)
+            double gf[4];
+            system_numerical_flux(fl, eu, uu, vv, f.normal, gf);
+            for (int ii = 0; ii < M; ++ii)
+              out[e * M + ii] += gf[ii] * factor;
+          }
           continue;
+        }
         const int64_t eo = g.index(nb);
         if (!(e < eo))
           continue;
@@ -2026,6 +2063,17 @@ int orc_fvsys_apply(const orc_grid* g, const orc_flux* flux, const double* u, do
   if (flux->kind != ORC_FLUX_EULER || gr.d > 2)
     return 1;
   fvsys_apply(gr, *flux, u, out);
+  return 0;
+}
+
+// the same with impermeable walls on the (non-periodic) domain sides of the two masks (bit 2k + s)
+int orc_fvsys_apply_walls(const orc_grid* g, const orc_flux* flux, uint32_t wall_mask, uint32_t mirror_mask, const double* u,
+                          double* out)
+{
+  Grid gr(g);
+  if (flux->kind != ORC_FLUX_EULER || gr.d > 2)
+    return 1;
+  fvsys_apply(gr, *flux, u, out, wall_mask, mirror_mask);
   return 0;
 }
 

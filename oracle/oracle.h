@@ -236,6 +236,8 @@ void orc_fv_interpolate(const orc_grid* g, const orc_function* f, double* u);
  * p[1]), m = d + 2 components per cell, DoF m * element + i; tools/euler.hh, local/operators/advection-fv.hh:127-153,
  * examples/mpi_2019_02_talk_on_hyperbolic_equations.cc:141-159, tools/hyperbolic.hh:38-86 */
 int orc_fvsys_apply(const orc_grid* g, const orc_flux* flux, const double* u, double* out);
+int orc_fvsys_apply_walls(const orc_grid* g, const orc_flux* flux, uint32_t wall_mask, uint32_t mirror_mask, const double* u,
+                          double* out);
 int orc_fvsys_euler(const orc_grid* g, const orc_flux* flux, double* u, double dt, int64_t n_steps);
 double orc_fvsys_estimate_dt(const orc_grid* g, const orc_flux* flux, const double* u);
 void orc_euler_flux(int d, double gamma, const double* w, double* f);

@@ -92,6 +92,53 @@ def test_euler_2d_driver_setup(gdt, ctx, oracle):
     assert abs(u.reshape(-1, 4)[:, 0].sum() - u0.reshape(-1, 4)[:, 0].sum()) <= 1e-12 * N * N
 
 
+@pytest.mark.parametrize("n", [[16], [5], [10, 7], [4, 9], [1, 5]])
+@pytest.mark.parametrize("kind", ["wall", "mirror", "wall-lower-mirror-upper"])
+@pytest.mark.parametrize("numflux,params", [(D.NUMFLUX_VIJAYASUNDARAM, [GAMMA]), (D.NUMFLUX_LAX_FRIEDRICHS, [GAMMA, 0.35])])
+def test_euler_impermeable_walls_parity(gdt, ctx, oracle, n, kind, numflux, params):
+    """the two impermeable-wall treatments of test/inviscid-compressible-flow/base.hh:187-241 on every domain side"""
+    d = len(n)
+    lo, up = [0.0, -1.0][:d], [3.0, 1.0][:d]
+    gdesc = D.grid_desc(lo, up, n, 0)
+    all_sides = (1 << (2 * d)) - 1
+    lower = sum(1 << (2 * k) for k in range(d))
+    wall_mask, mirror_mask = {"wall": (all_sides, 0), "mirror": (0, all_sides),
+                              "wall-lower-mirror-upper": (lower, all_sides & ~lower)}[kind]
+    space = gdt.make_finite_volume_space(gdt.Grid(ctx, gdesc), d + 2)
+    cls = gdt.NumericalVijayasundaramFlux if numflux == D.NUMFLUX_VIJAYASUNDARAM else gdt.NumericalLaxFriedrichsFlux
+    op = gdt.make_advection_fv_operator(cls(D.FLUX_EULER, params), space)
+    if wall_mask:
+        op.append(D.fv_boundary(D.FVBND_EULER_IMPERMEABLE_WALL, wall_mask, 0.0, 0.0))
+    if mirror_mask:
+        op.append(D.fv_boundary(D.FVBND_EULER_INVISCID_MIRROR, mirror_mask, 0.0, 0.0))
+    u = random_states(oracle, d, int(np.prod(n)), seed=23)
+    got = op.apply(u)
+    ref = oracle.fvsys_apply_walls(gdesc, D.flux(D.FLUX_EULER, numflux, params), u, wall_mask, mirror_mask)
+    assert rel_err(got, ref) <= TOL
+
+
+def test_euler_1d_wall_table_on_the_device(gdt, ctx, oracle):
+    """inviscid_compressible_flow__euler_1d__explicit__fv.mini:26 (direct Euler treatment, 16 elements): the momentum
+    deviation 3.50e-01 reproduced by the device time loop"""
+    from test_fv_systems_oracle import shock_tube_1d
+
+    N = 16
+    gper, u0 = shock_tube_1d(oracle, N)
+    walls = D.grid_desc([-1.0], [1.0], [N], periodic=0)
+    euler = gdt.EulerTools(1, GAMMA)
+    per_op = gdt.make_advection_fv_operator(gdt.NumericalVijayasundaramFlux(*euler.flux()),
+                                            gdt.make_finite_volume_space(gdt.Grid(ctx, gper), 3))
+    dt = 0.99 * per_op.estimate_dt(u0)
+    op = gdt.make_advection_fv_operator(gdt.NumericalVijayasundaramFlux(*euler.flux()),
+                                        gdt.make_finite_volume_space(gdt.Grid(ctx, walls), 3))
+    op.append(D.fv_boundary(D.FVBND_EULER_IMPERMEABLE_WALL, 3, 0.0, 0.0))
+    h, u, err = 2.0 / N, u0.copy(), 0.0
+    for _ in range(63):
+        u = op.explicit_euler(u, dt, 1)
+        err = max(err, abs(u.reshape(N, 3)[:, 1].sum() * h))
+    assert float(f"{err:.2e}") == 3.50e-01
+
+
 def test_system_operator_error_conventions(gdt, ctx):
     grid = gdt.Grid(ctx, D.grid_desc([0.0], [1.0], [8], periodic=1))
     scalar, system = gdt.make_finite_volume_space(grid), gdt.make_finite_volume_space(grid, 3)

@@ -1,8 +1,9 @@
 """CPU checks of the oracle's restatement of the FV path for SYSTEMS (m > 1): EulerTools (tools/euler.hh), the
 Vijayasundaram / Lax-Friedrichs numerical fluxes (local/numerical-fluxes/vijayasundaram.hh:111-133, lax-friedrichs.hh:66-88),
 LocalAdvectionFvCouplingOperator::apply for m components (local/operators/advection-fv.hh:127-153) and
-estimate_dt_for_hyperbolic_system for m > 1 (tools/hyperbolic.hh:38-86).  Pinned by the reference's own EOC table
-test/inviscid-compressible-flow/inviscid_compressible_flow__euler_1d__explicit__fv.mini:8-14 (periodic boundaries)."""
+estimate_dt_for_hyperbolic_system for m > 1 (tools/hyperbolic.hh:38-86).  Pinned by the reference's own EOC tables
+test/inviscid-compressible-flow/inviscid_compressible_flow__euler_1d__explicit__fv.mini:8-42 (periodic boundaries,
+impermeable walls by the direct Euler treatment and by the inviscid mirror treatment)."""
 import numpy as np
 import pytest
 
@@ -78,3 +79,32 @@ def test_vijayasundaram_is_consistent_and_conservative(oracle):
         for numflux, params in ((D.NUMFLUX_VIJAYASUNDARAM, [GAMMA]), (D.NUMFLUX_LAX_FRIEDRICHS, [GAMMA, 0.4])):
             L = oracle.fvsys_apply(g, D.flux(D.FLUX_EULER, numflux, params), states.ravel()).reshape(ne, d + 2)
             assert np.abs(L.sum(0)).max() <= 1e-12 * np.abs(L).max()
+
+
+@pytest.mark.parametrize("treatment,wall_mask,mirror_mask,expected", [
+    ("impermeable_walls_by_direct_euler_treatment", 3, 0, [3.50e-01, 4.20e-01, 4.57e-01]),   # .mini:26
+    ("impermeable_walls_by_inviscid_mirror_treatment", 0, 3, [3.43e-01, 4.06e-01, 4.51e-01]),  # .mini:40
+])
+def test_euler_1d_impermeable_wall_tables(oracle, treatment, wall_mask, mirror_mask, expected):
+    """quantity.rel_mass_conserv_error = max over the time points and components of |m_0 - m(t)| / (m_0 > 0 ? m_0 : 1)
+    (test/instationary-eocstudies/base.hh:325-348; the momentum is what the walls change) and quantity.num_timesteps =
+    [64 126 250], for both wall treatments of test/inviscid-compressible-flow/base.hh:187-241 -- to the table's 3 digits"""
+    for N, time_points, exp in zip((16, 32, 64), (64, 126, 250), expected):
+        g, u0 = shock_tube_1d(oracle, N)  # the dt estimate sees the same grid view as the periodic test
+        walls = D.grid_desc([-1.0], [1.0], [N], periodic=0)
+        fl = D.flux(D.FLUX_EULER, D.NUMFLUX_VIJAYASUNDARAM, [GAMMA])
+        dt = 0.99 * oracle.fvsys_estimate_dt(g, fl, u0)
+        steps, t = 0, 0.0
+        while t < 1.0 + dt:
+            t += dt
+            steps += 1
+        assert steps + 1 == time_points
+        h = 2.0 / N
+        m0 = u0.reshape(N, 3).sum(0) * h
+        u, err = u0.copy(), np.zeros(3)
+        for _ in range(steps):
+            u = u - oracle.fvsys_apply_walls(walls, fl, u, wall_mask, mirror_mask) * dt
+            m = u.reshape(N, 3).sum(0) * h
+            err = np.maximum(err, np.abs(m0 - m) / np.where(m0 > 0, m0, 1.0))
+        assert float(f"{err.max():.2e}") == exp
+        assert err[0] <= 1e-14 and err[2] <= 1e-14  # mass and energy stay conserved: only the momentum sees the walls

@@ -411,6 +411,29 @@ def test_fv_apply_parity(gdt, ctx, oracle, name, n, periodic, fl):
     assert rel_err(out, ref) <= TOL
 
 
+@pytest.mark.parametrize("n,periodic", [([512, 2], 3), ([512, 7], 0), ([512, 23], 1), ([1024, 61], 3), ([1536, 9], 2),
+                                        ([1024, 130], 3), ([512, 200], 0)])
+@pytest.mark.parametrize("kind,numflux", [(D.FLUX_LINEAR, D.NUMFLUX_UPWIND), (D.FLUX_BURGERS, D.NUMFLUX_UPWIND),
+                                          (D.FLUX_LINEAR, D.NUMFLUX_LAX_FRIEDRICHS), (D.FLUX_BURGERS, D.NUMFLUX_LAX_FRIEDRICHS)])
+@pytest.mark.parametrize("tma", ["0", "1"])
+def test_fv_apply_parity_tma_staged(gdt, ctx, oracle, monkeypatch, n, periodic, kind, numflux, tma):
+    """rows of a multiple of 512 cells can take the TMA-staged kernel (fv_tma.cu, GDTB_FV_TMA=1): one / several strips, runs
+    that end inside a row group, every periodicity, apply and the fused Euler step; anisotropic cells; the register-marching
+    kernel on the same inputs"""
+    monkeypatch.setenv("GDTB_FV_TMA", tma)
+    gdesc = D.grid_desc([0.0, -1.0], [3.0, 1.0], n, periodic)
+    space = make_space(gdt, ctx, gdesc, FV, 0)
+    fl = D.flux(kind, numflux, [1.0, -0.5] if kind == D.FLUX_LINEAR else [])
+    num = gdt.NumericalUpwindFlux(kind, list(fl.p))
+    num.desc.numflux = numflux
+    L = gdt.make_advection_fv_operator(num, space)
+    u = np.random.default_rng(SEED).uniform(-1.0, 1.0, int(np.prod(n)))
+    ref = oracle.fv_apply(gdesc, fl, u)
+    assert rel_err(L.apply(u), ref) <= TOL
+    dt = 1e-3
+    assert rel_err(L.explicit_euler(u, dt, 3), oracle.fv_euler(gdesc, fl, u, dt, 3)) <= TOL
+
+
 def test_fv_explicit_euler_reference_tables(gdt, ctx, oracle):
     """linear transport with dt = h is an exact shift and conserves mass (linear_transport__1d__explicit__fv.mini)"""
     for N in (16, 32, 64):

@@ -20,7 +20,7 @@ make -s -j4 &
 PIDS="$PIDS $!"
 for p in $PIDS; do wait $p; done
 OBJS=""
-for f in capi solve assemble_generic assemble_q1_gather assemble_q2_gather assemble_q2_qp assemble_dg_gather assemble_dg_fast pattern fv fv_system; do
+for f in capi solve assemble_generic assemble_q1_gather assemble_q2_gather assemble_q2_qp assemble_dg_gather assemble_dg_fast pattern fv fv_system fv_tma; do
   if [ -n "${REPL[$f]}" ]; then OBJS="$OBJS ${REPL[$f]}"; else OBJS="$OBJS ../build/$f.o"; fi
 done
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/ab/libgdtb_${NAME}.so $OBJS

@@ -42,7 +42,7 @@ grid = gdt.make_cube_grid(ctx, 0.0, 1.0, [n, n], periodic=3)
 space = gdt.make_finite_volume_space(grid)
 u = torch.rand(n * n, dtype=torch.float64, device="cuda")
 v = torch.empty_like(u)
-out = {"lib": os.environ.get("GDTB_LIB", "default"), "rows_env": os.environ.get("GDTB_FV_ROWS", "")}
+out = {"lib": os.environ.get("GDTB_LIB", "default"), "rows_env": os.environ.get("GDTB_FV_ROWS", ""), "tma": os.environ.get("GDTB_FV_TMA", "0")}
 out["copy_us"] = pair(lambda: v.copy_(u))
 out["fill_us"] = pair(lambda: v.fill_(1.0))
 for name, flux in (("linear", gdt.NumericalUpwindFlux(D.FLUX_LINEAR, [1.0, 0.5])), ("burgers", gdt.NumericalUpwindFlux(D.FLUX_BURGERS))):
