@@ -826,13 +826,21 @@ int gdtb_dirichlet_create(gdtb_ctx* ctx, const gdtb_space* space, uint32_t bound
   Launch& L = ctx->launch;
   if (cudaMalloc(&dc->d_flags, (size_t)std::max<long long>(n, 1)) != cudaSuccess)
     return fail(GDTB_ERR_OUT_OF_MEMORY, "dirichlet: out of device memory");
-  GDTB_CUDA(cudaMemsetAsync(dc->d_flags, 0, (size_t)std::max<long long>(n, 1), L.stream));
+  // (every exit below frees what has been allocated so far)
+  if (cudaMemsetAsync(dc->d_flags, 0, (size_t)std::max<long long>(n, 1), L.stream) != cudaSuccess) {
+    cudaFree(dc->d_flags);
+    return fail(GDTB_ERR_CUDA, "dirichlet: cudaMemsetAsync failed");
+  }
   // FV (P0) elements carry their only local key in the element interior: nothing lies on an intersection
   if (space->dev.kind != GDTB_SPACE_FV && space->dev.K > 0 && dc->grid.ne > 0) {
     k_dirichlet_flags<<<(unsigned)((dc->grid.ne + 255) / 256), 256, 0, L.stream>>>(dc->grid, dc->space, boundary_mask,
                                                                                    dc->d_flags);
     L.count++;
-    GDTB_CUDA(cudaGetLastError());
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+      cudaFree(dc->d_flags);
+      return fail(GDTB_ERR_CUDA, std::string("k_dirichlet_flags: ") + cudaGetErrorString(err));
+    }
   }
   // ascending DoF list (std::set order): stream compaction of the flags
   long long* d_count = nullptr;
