@@ -38,7 +38,11 @@
 // (ms per assembly): 2 blocks x 2 stages 1.90, 3 blocks x 1 stage 1.85, 4 blocks (64 registers, 150 B of spills) x 1 stage
 // 1.76.  The other variants are register-bound at 2 blocks and keep two stages.
 #ifndef Q2G_MIN_BLOCKS
-#define Q2G_MIN_BLOCKS 4
+#define Q2G_MIN_BLOCKS 3
+#endif
+
+#ifndef Q2G_SLOT_MAJOR
+#define Q2G_SLOT_MAJOR 1
 #endif
 
 namespace gdtb {
@@ -356,11 +360,20 @@ __global__ void __launch_bounds__(128) k_q2_axis_tables(const __grid_constant__ 
         M[first + j] = fma(ext, G.TM[il][j], M[first + j]);
       }
     }
-    double* out = tab + gi * p.sf_group_stride + p.sf_axis_off[k] + 10LL * pt;
+    if (k == 0) { // component-major along x (q2_x_index)
+      double* out = tab + gi * p.sf_group_stride + p.sf_axis_off[0];
 #pragma unroll
-    for (int a = 0; a < 5; ++a) {
-      out[a] = K[a];
-      out[5 + a] = M[a];
+      for (int a = 0; a < 5; ++a) {
+        out[q2_x_index(S, a, c, g.n[0])] = K[a];
+        out[q2_x_index(S, 5 + a, c, g.n[0])] = M[a];
+      }
+    } else {
+      double* out = tab + gi * p.sf_group_stride + p.sf_axis_off[k] + 10LL * pt;
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        out[a] = K[a];
+        out[5 + a] = M[a];
+      }
     }
   }
 }
@@ -393,6 +406,23 @@ __device__ __forceinline__ void q2_load_axis(const double* __restrict__ t, doubl
   }
 }
 
+// The x axis keeps its table component-major ("structure of arrays"): tab_x[(S * 10 + comp) * (N_x + 1) + c] for the
+// lattice point p = 2 c + S.  With the slot-major thread layout the lanes of a warp hold consecutive c, so each of the
+// 2 A loads of a warp is one contiguous run (2 shared-memory/L1 wavefronts) instead of 32 entries 80 bytes apart
+// (round-2 profile: the strided x loads were two thirds of the LSU wavefronts and the top stall, long scoreboard 6.2).
+template <int A>
+__device__ __forceinline__ void q2_load_x(const double* __restrict__ t, const int S, const int c, const long long Nx,
+                                          double (&K)[A], double (&M)[A])
+{
+  const double* q = t + q2_x_index(S, 0, c, Nx);
+  const long long stride = Nx + 1;
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    K[a] = __ldg(q + a * stride);
+    M[a] = __ldg(q + (5 + a) * stride);
+  }
+}
+
 // one group's contribution to the (a_y, a_x) plane of a row; FIRST: assign instead of accumulate
 template <int D, int AX, int AY, bool FIRST>
 __device__ __forceinline__ void q2_sf_group(const Q2GatherParams& p, const int gi, const int px, const int py, const int pl,
@@ -402,7 +432,7 @@ __device__ __forceinline__ void q2_sf_group(const Q2GatherParams& p, const int g
   const Q2Group& G = p.group[gi];
   const double* tab = p.sf_tab + gi * p.sf_group_stride;
   double KX[AX], MX[AX], KY[AY], MY[AY];
-  q2_load_axis<AX>(tab + p.sf_axis_off[0] + 10LL * px, KX, MX);
+  q2_load_x<AX>(tab + p.sf_axis_off[0], px & 1, px >> 1, p.g.n[0], KX, MX);
   if (D == 3)
     q2_load_axis<AY>(tab + p.sf_axis_off[1] + 10LL * py, KY, MY);
   const double* tl = tab + p.sf_axis_off[last] + 10LL * pl;
@@ -553,48 +583,218 @@ __device__ __forceinline__ void q2_dispatch(const Q2GatherParams& p, const int c
     q2_row_plane<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
 }
 
+// entries along x of the rows before row c of a lattice line (q2_axis_len(S, c, N).PL as an int)
+__device__ __forceinline__ int q2_xpl(const int S, const int c)
+{
+  return S ? 3 * c : 5 * c - (c > 0 ? 2 : 0);
+}
+
+// start of the lattice line (cy, cl) of a row group relative to the group's first value, and the entries w a row of the
+// line holds per entry along x: the row (cx, cy, cl) starts at line + w * q2_xpl(cx)  (q2_row_offset, regrouped)
+template <int D>
+__device__ __forceinline__ void q2_line(const GridDev& g, const Q2RowGroup& rg, const int cy, const int cl, long long& line,
+                                        int& w)
+{
+  const int s = rg.s;
+  if (D == 3) {
+    const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cy, (int)g.n[1]);
+    const Q2AxisLen Z = q2_axis_len((s >> 2) & 1, cl, (int)g.n[2]);
+    w = Y.L * Z.L;
+    line = rg.TxTy * Z.PL + (long long)((unsigned long long)(unsigned)Z.L * (rg.Tx * (unsigned)Y.PL));
+  } else {
+    const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cl, (int)g.n[1]);
+    w = Y.L;
+    line = (long long)rg.Tx * Y.PL;
+  }
+}
+
+// work-item records (Q2GatherParams::items): what the LN bookkeeping of k_q2_gather computes per item, once per grid / slab
+template <int D>
+__global__ void __launch_bounds__(128) k_q2_items(const __grid_constant__ Q2GatherParams p, int4* __restrict__ recs)
+{
+  const GridDev& g = p.g;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= p.n_items)
+    return;
+  int gi = 0;
+  for (int k = 1; k < p.n_rowgroups; ++k)
+    if (item >= p.rg[k].item_begin)
+      gi = k;
+  const Q2RowGroup& rg = p.rg[gi];
+  const int s = rg.s;
+  const bool five = !((s >> (D - 1)) & 1);
+  const int rpi = five ? Q2G_THREADS / 5 : Q2G_THREADS / 3;
+  const unsigned lrow0 = unsigned(rg.lex_begin) + unsigned(item - rg.item_begin) * rpi;
+  const int nrows = (int)min((long long)rpi, rg.lex_end - lrow0);
+  int ux, uy, ul;
+  q2_decode<D>(rg, lrow0, ux, uy, ul);
+  const int ex = (int)rg.ex;
+  const int n0 = min(nrows, ex - ux);
+  int y1 = uy + 1, l1 = ul, wrap = 0;
+  if (D == 2 || y1 == (int)rg.ey) {
+    y1 = 0;
+    l1 = ul + 1;
+    wrap = 1;
+  }
+  long long line0, line1;
+  int w0, w1;
+  q2_line<D>(g, rg, uy, ul, line0, w0);
+  q2_line<D>(g, rg, y1, l1, line1, w1);
+  const int sx = s & 1;
+  const long long off0 = line0 + w0 * q2_xpl(sx, ux);
+  const int rest = nrows - n0;
+  const long long off1 = rest > 0           ? line1 + w1 * q2_xpl(sx, rest)
+                         : ux + nrows < ex ? line0 + w0 * q2_xpl(sx, ux + nrows)
+                                           : line0 + (long long)w0 * (int)rg.Tx;
+  const long long start = rg.value_begin + off0;
+  int4 a, b;
+  a.x = (int)(unsigned)(start & 0xffffffffLL);
+  a.y = (int)(unsigned)((unsigned long long)start >> 32);
+  a.z = int(off1 - off0);
+  a.w = s | (nrows << 3) | (n0 << 10) | (w0 << 17) | ((rest > 0 ? w1 : 0) << 22) | (wrap << 27);
+  b.x = ux;
+  b.y = uy;
+  b.z = ul;
+  b.w = rest > 0 ? int(line1 - off0) : 0;
+  recs[2 * item] = a;
+  recs[2 * item + 1] = b;
+}
+
 // SF: 0 per-element coefficients, 1 sum-factorised (constant coefficients), 2 sum-factorised with a single group,
 // 3 one integrand of kind KIND with a coefficient per quadrature point (M Gauss points per direction)
-template <int D, bool ACCUMULATE, int SF, int M = 0, int KIND = 0>
+// LN: every lattice line of every row group is at least as long as a work item (checked at launch), so an item touches
+// at most two lines: row starts come from two uniform line records + one multiply-add per thread instead of a decode
+// (two divisions) and a full q2_row_offset per thread, and the end of the segment from the same records.
+// LN == 2: the uniform part (row group, first row, segment, line records) comes from the work-item records of k_q2_items.
+template <int D, bool ACCUMULATE, int SF, int M = 0, int KIND = 0, int LN = 0>
 __global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF == 3 ? 1 : 2))
     k_q2_gather(const __grid_constant__ Q2GatherParams p, double* __restrict__ values, int stage_doubles, int nbuf)
 {
   extern __shared__ __align__(16) double smem[];
   const GridDev& g = p.g;
   int buf = 0;
+  int gi = 0;
+#if Q2G_SLOT_MAJOR
+  // slot-major: the lanes of a warp hold CONSECUTIVE ROWS of one plane, so one store instruction of the warp hits rows
+  // whose starts differ by the (odd) row length -- 16 distinct 8-byte banks per half warp instead of the 5-slots-per-row
+  // pattern (2.1 x the minimal shared-memory wavefronts in the round-2 profile); surplus threads (slot >= slots) idle
+  const int slot5 = threadIdx.x / (Q2G_THREADS / 5), lr5 = threadIdx.x - slot5 * (Q2G_THREADS / 5);
+  const int slot3 = threadIdx.x / (Q2G_THREADS / 3), lr3 = threadIdx.x - slot3 * (Q2G_THREADS / 3);
+#else
+  const int lr5 = threadIdx.x / 5, slot5 = threadIdx.x - 5 * lr5;
+  const int lr3 = threadIdx.x / 3, slot3 = threadIdx.x - 3 * lr3;
+#endif
+  // LN == 2: the record of the NEXT item is requested one iteration ahead
+  const int4* const recs = reinterpret_cast<const int4*>(p.items);
+  int4 nra = make_int4(0, 0, 0, 0), nrb = nra;
+  if (LN == 2 && (long long)blockIdx.x < p.n_items) {
+    nra = __ldg(recs + 2 * blockIdx.x);
+    nrb = __ldg(recs + 2 * blockIdx.x + 1);
+  }
   for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     // ---- per item (uniform): row group, rows, CSR segment ---------------------------------------------------
-    int gi = 0;
+    int s, nrows, ux, uy, ul, n0 = 0, y1 = 0, l1 = 0;
+    int cx = 0, cy = 0, cl = 0, row_off = 0;
+    long long start;
+    int seg;
+    bool five;
+    int lr, slot;
+    bool active;
+    if (LN == 2) {
+      const int4 ra = nra, rb = nrb;
+      if (item + gridDim.x < p.n_items) {
+        nra = __ldg(recs + 2 * (item + gridDim.x));
+        nrb = __ldg(recs + 2 * (item + gridDim.x) + 1);
+      }
+      start = (long long)(((unsigned long long)(unsigned)ra.y << 32) | (unsigned long long)(unsigned)ra.x);
+      seg = ra.z;
+      const int pk = ra.w; // s | nrows << 3 | n0 << 10 | w0 << 17 | w1 << 22 | wrap << 27
+      s = pk & 7;
+      nrows = (pk >> 3) & 127;
+      n0 = (pk >> 10) & 127;
+      const int w0 = (pk >> 17) & 31, w1 = (pk >> 22) & 31, wrap = (pk >> 27) & 1;
+      ux = rb.x;
+      uy = rb.y;
+      ul = rb.z;
+      y1 = wrap ? 0 : uy + 1;
+      l1 = ul + wrap;
+      five = !((s >> (D - 1)) & 1);
+      lr = five ? lr5 : lr3;
+      slot = five ? slot5 : slot3;
+      active = lr < nrows && slot < (five ? 5 : 3);
+      const int sx = s & 1;
+      const bool second = lr >= n0;
+      cx = second ? lr - n0 : ux + lr;
+      cy = second ? y1 : uy;
+      cl = second ? l1 : ul;
+      row_off = second ? rb.w + w1 * q2_xpl(sx, cx) : w0 * (q2_xpl(sx, cx) - q2_xpl(sx, ux));
+    } else {
+    if (LN) { // items ascend: the row group only moves forward
+      while (gi + 1 < p.n_rowgroups && (int)item >= (int)p.rg[gi + 1].item_begin)
+        ++gi;
+    } else {
+      gi = 0;
 #pragma unroll
-    for (int k = 1; k < 8; ++k)
-      if (k < p.n_rowgroups && (int)item >= (int)p.rg[k].item_begin)
-        gi = k;
+      for (int k = 1; k < 8; ++k)
+        if (k < p.n_rowgroups && (int)item >= (int)p.rg[k].item_begin)
+          gi = k;
+    }
     const Q2RowGroup& rg = p.rg[gi];
-    const int s = rg.s;
-    const bool five = !((s >> (D - 1)) & 1);
-    const int slots = five ? 5 : 3;
+    s = rg.s;
+    five = !((s >> (D - 1)) & 1);
     const int rpi = five ? Q2G_THREADS / 5 : Q2G_THREADS / 3;
     const unsigned lrow0 = unsigned(rg.lex_begin) + unsigned(item - rg.item_begin) * rpi; // first row of the item
-    const int nrows = (int)min((long long)rpi, rg.lex_end - lrow0);
-    int ux, uy, ul;
+    nrows = (int)min((long long)rpi, rg.lex_end - lrow0);
     q2_decode<D>(rg, lrow0, ux, uy, ul);
-    const long long off0 = q2_row_offset<D>(g, rg, ux, uy, ul);
-    long long off1 = rg.off_end;
-    if ((long long)lrow0 + nrows < rg.lex_end) {
-      q2_decode<D>(rg, lrow0 + nrows, ux, uy, ul);
-      off1 = q2_row_offset<D>(g, rg, ux, uy, ul);
+    lr = five ? lr5 : lr3;
+    slot = five ? slot5 : slot3;
+    active = lr < nrows && slot < (five ? 5 : 3);
+    if (LN) {
+      const int ex = (int)rg.ex;
+      n0 = min(nrows, ex - ux); // rows of the item on its first line
+      y1 = uy + 1;              // the line after it
+      l1 = ul;
+      if (D == 2 || y1 == (int)rg.ey) {
+        y1 = 0;
+        l1 = ul + 1;
+      }
+      long long line0, line1;
+      int w0, w1;
+      q2_line<D>(g, rg, uy, ul, line0, w0);
+      q2_line<D>(g, rg, y1, l1, line1, w1);
+      const int sx = s & 1;
+      const long long off0 = line0 + w0 * q2_xpl(sx, ux);
+      const int rest = nrows - n0;
+      // end of the segment: inside the first line, exactly at its end (= start of the next line), or on the second line
+      const long long off1 = rest > 0           ? line1 + w1 * q2_xpl(sx, rest)
+                             : ux + nrows < ex ? line0 + w0 * q2_xpl(sx, ux + nrows)
+                                               : line0 + (long long)w0 * (int)rg.Tx;
+      start = rg.value_begin + off0;
+      seg = int(off1 - off0);
+      const bool second = lr >= n0;
+      cx = second ? lr - n0 : ux + lr;
+      cy = second ? y1 : uy;
+      cl = second ? l1 : ul;
+      row_off = (second ? int(line1 - off0) : int(line0 - off0)) + (second ? w1 : w0) * q2_xpl(sx, cx);
+    } else {
+      int vx, vy, vl;
+      const long long off0 = q2_row_offset<D>(g, rg, ux, uy, ul);
+      long long off1 = rg.off_end;
+      if ((long long)lrow0 + nrows < rg.lex_end) {
+        q2_decode<D>(rg, lrow0 + nrows, vx, vy, vl);
+        off1 = q2_row_offset<D>(g, rg, vx, vy, vl);
+      }
+      start = rg.value_begin + off0;
+      seg = int(off1 - off0);
+      if (active) {
+        q2_decode<D>(rg, lrow0 + lr, cx, cy, cl);
+        row_off = int(q2_row_offset<D>(g, rg, cx, cy, cl) - off0);
+      }
     }
-    const long long start = rg.value_begin + off0;
-    const int seg = int(off1 - off0);
+    }
     const int phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
     double* stage = smem + buf * stage_doubles + phase;
 
-    const int lr = five ? threadIdx.x / 5 : threadIdx.x / 3, slot = threadIdx.x - lr * slots;
-    int cx = 0, cy = 0, cl = 0, row_off = 0;
-    if (lr < nrows) {
-      q2_decode<D>(rg, lrow0 + lr, cx, cy, cl);
-      row_off = int(q2_row_offset<D>(g, rg, cx, cy, cl) - off0);
-    }
     // the stage about to be written must have been read out by the bulk store that used it last: waiting HERE (after
     // this item's index arithmetic) instead of right after the store lets the drain overlap the bookkeeping
     if (!ACCUMULATE && item != (long long)blockIdx.x) {
@@ -606,10 +806,10 @@ __global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF ==
       }
       __syncthreads();
     }
-    if (lr < nrows) {
+    if (active) {
       double* row = stage + row_off;
       if (D == 3) {
-        switch (rg.s) {
+        switch (s) {
           case 0: q2_dispatch<SF, 3, 0, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
           case 1: q2_dispatch<SF, 3, 1, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
           case 2: q2_dispatch<SF, 3, 0, 1, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
@@ -620,7 +820,7 @@ __global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF ==
           default: q2_dispatch<SF, 3, 1, 1, 1, M, KIND>(p, cx, cy, cl, slot, row); break;
         }
       } else {
-        switch (rg.s) {
+        switch (s) {
           case 0: q2_dispatch<SF, 2, 0, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
           case 1: q2_dispatch<SF, 2, 1, 0, 0, M, KIND>(p, cx, cy, cl, slot, row); break;
           case 2: q2_dispatch<SF, 2, 0, 0, 1, M, KIND>(p, cx, cy, cl, slot, row); break;
@@ -698,8 +898,8 @@ int q2_slab_ranges(const GridDev& g, const SpaceDev& sp, Q2SlabRange* out)
 
 long long q2_sf_table_doubles(const GridDev& g)
 {
-  long long total = 0;
-  for (int k = 0; k < g.d; ++k)
+  long long total = 20 * (g.n[0] + 1); // x: component-major, both parities padded to N_x + 1 points (q2_x_index)
+  for (int k = 1; k < g.d; ++k)
     total += 10 * (2 * g.n[k] + 1);
   return total;
 }
@@ -732,6 +932,8 @@ Q2Kernel q2_qp_kernel_d(int m, int kind, bool accumulate)
 }
 
 int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate, bool qp);
+void q2_setup_rowgroups(Q2GatherParams& p, const SpaceDev& sp);
+bool q2_lines_apply(const Q2GatherParams& p);
 
 } // namespace
 
@@ -739,6 +941,17 @@ bool q2_qp_supported(int d, int m, int kind)
 {
   (void)kind;
   return (d == 2 && m >= 2 && m <= 4) || (d == 3 && m >= 2 && m <= 3);
+}
+
+long long q2_item_count(const GridDev& g, const SpaceDev& sp)
+{
+  if ((g.d != 2 && g.d != 3) || sp.size >= (1LL << 31))
+    return 0;
+  Q2GatherParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.g = g;
+  q2_setup_rowgroups(p, sp);
+  return q2_lines_apply(p) ? p.n_items : 0;
 }
 
 int launch_q2_gather(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate)
@@ -757,24 +970,15 @@ int launch_q2_gather_qp(Launch& L, Q2GatherParams& p, const CgQpGroup& group, co
 
 namespace {
 
-int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate, bool qp)
+// row groups in ascending global index order (codim ascending, shift bitset ascending), restricted to the slab, and the
+// work items of every group
+void q2_setup_rowgroups(Q2GatherParams& p, const SpaceDev& sp)
 {
   const GridDev& g = p.g;
   const int d = g.d;
-  if (d != 2 && d != 3)
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: 2D and 3D grids only");
-  if (sp.size >= (1LL << 31))
-    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: more than 2^31 degrees of freedom");
-  for (int k = 0; k < d; ++k)
-    if (g.n[k] > 5000)
-      return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: more than 5000 elements along one axis");
-  // row groups in ascending global index order (codim ascending, shift bitset ascending), restricted to the slab
   Q2SlabRange ranges[8];
   p.n_rowgroups = q2_slab_ranges(g, sp, ranges);
   p.n_items = 0;
-  int max_row = 1;
-  for (int k = 0; k < d; ++k)
-    max_row *= 5;
   {
     int r = 0;
     for (int c = 0; c <= d; ++c)
@@ -812,6 +1016,44 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
         ++r;
       }
   }
+}
+
+// the line-based bookkeeping needs every lattice line of every (non-empty) row group to hold a work item's rows
+bool q2_lines_apply(const Q2GatherParams& p)
+{
+  for (int r = 0; r < p.n_rowgroups; ++r)
+    if (p.rg[r].lex_end > p.rg[r].lex_begin && (int)p.rg[r].ex < Q2G_THREADS / 3)
+      return false;
+  return true;
+}
+
+template <int SF>
+Q2Kernel q2_pick(int d, bool accumulate, int ln)
+{
+  if (accumulate)
+    return d == 3 ? k_q2_gather<3, true, SF> : k_q2_gather<2, true, SF>;
+  if (ln == 2)
+    return d == 3 ? k_q2_gather<3, false, SF, 0, 0, 2> : k_q2_gather<2, false, SF, 0, 0, 2>;
+  if (ln == 1)
+    return d == 3 ? k_q2_gather<3, false, SF, 0, 0, 1> : k_q2_gather<2, false, SF, 0, 0, 1>;
+  return d == 3 ? k_q2_gather<3, false, SF> : k_q2_gather<2, false, SF>;
+}
+
+int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* values, bool accumulate, bool qp)
+{
+  const GridDev& g = p.g;
+  const int d = g.d;
+  if (d != 2 && d != 3)
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: 2D and 3D grids only");
+  if (sp.size >= (1LL << 31))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: more than 2^31 degrees of freedom");
+  for (int k = 0; k < d; ++k)
+    if (g.n[k] > 5000)
+      return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather: more than 5000 elements along one axis");
+  q2_setup_rowgroups(p, sp);
+  int max_row = 1;
+  for (int k = 0; k < d; ++k)
+    max_row *= 5;
   // stage: the longest segment is rows_per_item rows of the longest row kind that uses that slot count
   // (5 slots: rows up to 5^d entries, 51 rows; 3 slots: rows up to 3 * 5^(d-1), 85 rows)
   const int seg5 = (Q2G_THREADS / 5) * max_row, seg3 = (Q2G_THREADS / 3) * (max_row / 5 * 3);
@@ -820,23 +1062,23 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
   const bool single_group = p.sf && p.n_groups == 1;
   const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : (single_group ? 1 : 2));
   const size_t smem = (size_t)nbuf * stage_doubles * sizeof(double);
-  Q2Kernel kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 0> : k_q2_gather<3, false, 0>)
-                         : (accumulate ? k_q2_gather<2, true, 0> : k_q2_gather<2, false, 0>);
+  // line-based bookkeeping (LN) needs every lattice line of every row group to hold at least one work item's rows
+  static const bool ln_off = std::getenv("GDTB_Q2_NO_LN") != nullptr;
+  static const bool items_off = std::getenv("GDTB_Q2_NO_ITEMS") != nullptr;
+  int ln = !ln_off && q2_lines_apply(p) ? 1 : 0;
+  if (ln && p.items && !items_off && !accumulate && !qp)
+    ln = 2; // work-item records
+  Q2Kernel kern = q2_pick<0>(d, accumulate, ln);
   if (qp) {
     if (!q2_qp_supported(d, p.qp.m, p.qp.kind))
       return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather_qp: unsupported number of Gauss points per direction");
     kern = d == 3 ? q2_qp_kernel_d<3>(p.qp.m, p.qp.kind, accumulate) : q2_qp_kernel_d<2>(p.qp.m, p.qp.kind, accumulate);
   } else if (p.sf) {
-    if (p.n_groups == 1)
-      kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 2> : k_q2_gather<3, false, 2>)
-                    : (accumulate ? k_q2_gather<2, true, 2> : k_q2_gather<2, false, 2>);
-    else
-      kern = d == 3 ? (accumulate ? k_q2_gather<3, true, 1> : k_q2_gather<3, false, 1>)
-                    : (accumulate ? k_q2_gather<2, true, 1> : k_q2_gather<2, false, 1>);
+    kern = p.n_groups == 1 ? q2_pick<2>(d, accumulate, ln) : q2_pick<1>(d, accumulate, ln);
     long long off = 0;
     for (int k = 0; k < d; ++k) {
       p.sf_axis_off[k] = off;
-      off += 10 * (2 * g.n[k] + 1);
+      off += k == 0 ? 20 * (g.n[0] + 1) : 10 * (2 * g.n[k] + 1);
     }
     p.sf_group_stride = off;
   }
@@ -862,6 +1104,13 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
   if (p.sf) {
     const long long work = p.sf_group_stride / 10 * p.n_groups;
     k_q2_axis_tables<<<(unsigned)((work + 127) / 128), 128, 0, L.stream>>>(p, const_cast<double*>(p.sf_tab));
+    L.count++;
+  }
+  if (ln == 2 && !p.items_ready) {
+    if (d == 3)
+      k_q2_items<3><<<(unsigned)((p.n_items + 127) / 128), 128, 0, L.stream>>>(p, reinterpret_cast<int4*>(p.items));
+    else
+      k_q2_items<2><<<(unsigned)((p.n_items + 127) / 128), 128, 0, L.stream>>>(p, reinterpret_cast<int4*>(p.items));
     L.count++;
   }
   kern<<<(unsigned)grid, Q2G_THREADS, smem, L.stream>>>(p, values, stage_doubles, nbuf);

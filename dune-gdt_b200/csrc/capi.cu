@@ -1346,6 +1346,7 @@ int gdtb_matop_destroy(gdtb_matop* op)
     cudaFree(op->d_values);
   cudaFree(op->d_forms);
   cudaFree(op->d_q2_tab);
+  cudaFree(op->d_q2_items);
   cudaFree(op->d_qp_scratch);
   cudaFree(op->d_own_rowptr);
   cudaFree(op->d_own_colidx);
@@ -2244,6 +2245,7 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       const size_t bytes = sizeof(double) * (size_t)q2_sf_table_doubles(op->grid) * (size_t)p.n_groups;
       if (op->d_q2_tab_bytes < bytes) {
         cudaFree(op->d_q2_tab);
+  cudaFree(op->d_q2_items);
         op->d_q2_tab = nullptr;
         op->d_q2_tab_bytes = 0;
         if (cudaMalloc(&op->d_q2_tab, bytes) != cudaSuccess)
@@ -2253,7 +2255,29 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       p.sf = 1;
       p.sf_tab = op->d_q2_tab;
     }
+    // work-item records of the gather kernel: computed on the device once per grid / slab, kept with the operator
+    const long long n_items = accumulate ? 0 : q2_item_count(op->grid, op->test);
+    if (n_items > 0) {
+      const size_t bytes = (size_t)n_items * 32;
+      if (op->d_q2_items_bytes < bytes) {
+        cudaFree(op->d_q2_items);
+        op->d_q2_items = nullptr;
+        op->d_q2_items_bytes = 0;
+        op->q2_items_key[2] = -1;
+        if (cudaMalloc(&op->d_q2_items, bytes) != cudaSuccess)
+          return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (Q2 work-item records)");
+        op->d_q2_items_bytes = bytes;
+      }
+      p.items = op->d_q2_items;
+      p.items_ready = op->q2_items_key[0] == op->grid.layer_lo && op->q2_items_key[1] == op->grid.layer_hi
+                      && op->q2_items_key[2] == n_items;
+    }
     GDTB_TRY(launch_q2_gather(L, p, op->test, op->d_values, accumulate));
+    if (n_items > 0) {
+      op->q2_items_key[0] = op->grid.layer_lo;
+      op->q2_items_key[1] = op->grid.layer_hi;
+      op->q2_items_key[2] = n_items;
+    }
   }
 
   // --- CG row gather with coefficients per quadrature point ----------------------------------

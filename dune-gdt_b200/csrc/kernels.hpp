@@ -288,7 +288,15 @@ struct Q2GatherParams
   const double* sf_tab;
   long long sf_axis_off[3], sf_group_stride;
   CgQpGroup qp; // launch_q2_gather_qp: the one integrand with a coefficient per quadrature point
+  // work-item records (optional, 32 bytes per item, q2_item_count() items): the uniform per-item bookkeeping (row group,
+  // first row, CSR segment, the two lattice lines the item touches) computed once by k_q2_items instead of by every warp
+  // of the gather kernel; items_ready: the buffer already holds the records of this grid / slab
+  void* items;
+  int items_ready;
 };
+// number of work items of the CG Q2 gather kernels for this grid / slab, 0 if the item records do not apply (a lattice
+// line shorter than a work item)
+long long q2_item_count(const GridDev& g, const SpaceDev& sp);
 
 long long q2_sf_table_doubles(const GridDev& g); // doubles per group
 // Row ranges a slab of element layers [g.layer_lo, g.layer_hi) owns (owner-computes-rows: a lattice layer belongs to

@@ -42,6 +42,22 @@ __device__ __forceinline__ void q2_bulk_wait0()
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+__device__ __forceinline__ void q2_cp_async16(void* sdst, const void* gsrc)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+               : "memory");
+}
+
+__device__ __forceinline__ void q2_cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void q2_cp_async_wait_all()
+{
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 __device__ __forceinline__ void q2_prefetch_l1(const void* ptr)
 {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
@@ -130,6 +146,13 @@ __host__ __device__ __forceinline__ long long q2_row_offset(const GridDev& g, co
   }
   const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cl, (int)g.n[1]);
   return (long long)rg.Tx * Y.PL + (long long)((unsigned long long)(unsigned)Y.L * (unsigned)X.PL);
+}
+
+// position of component comp (K: 0..4, M: 5..9) of the lattice point p = 2 c + S in the component-major x table of the
+// sum-factorised kernels (assemble_q2_gather.cu, q2_load_x)
+__host__ __device__ __forceinline__ long long q2_x_index(const int S, const int comp, const int c, const long long Nx)
+{
+  return (long long)(S * 10 + comp) * (Nx + 1) + c;
 }
 
 // per-axis description of a row's coupling box for parity S (compile time): the row's lattice coordinate is

@@ -190,6 +190,14 @@ def element_cases():
         ("q2-thin-grid", [1, 7, 2], 2, [laplace(1.0), mass(0.5)], "q2_gather"),
         ("q2-2d-single-row", [13, 1], 2, [laplace(1.0)], "q2_gather"),
         ("q2-bigger-3d", [17, 9, 12], 2, [laplace(D.fn_elem(rng_elem([17, 9, 12])))], "q2_gather"),
+        # lattice lines longer than a work item: the line-based row bookkeeping of k_q2_gather<..., LN = true>
+        # (single group / several groups / element-wise coefficients; items that end exactly at a line end, start at one)
+        ("q2-long-lines-3d-const", [87, 3, 4], 2, [laplace(1.0)], "q2_gather"),
+        ("q2-long-lines-3d-two-forms", [101, 2, 3], 2, [laplace(0.75), mass(0.5)], "q2_gather"),
+        ("q2-long-lines-3d-elem", [86, 3, 2], 2, [laplace(D.fn_elem(rng_elem([86, 3, 2])))], "q2_gather"),
+        ("q2-long-lines-3d-170", [170, 2, 2], 2, [laplace(1.0)], "q2_gather"),
+        ("q2-long-lines-2d-const", [255, 6], 2, [laplace(1.0)], "q2_gather"),
+        ("q2-long-lines-2d-elem", [128, 5], 2, [mass(D.fn_elem(rng_elem([128, 5], seed=3)))], "q2_gather"),
     ]
     return cases
 
@@ -570,7 +578,8 @@ def test_slab_owner_computes_rows(gdt, ctx, oracle, n, cuts, constant_kappa):
     assert rel_err(got_v, ref_v) <= TOL and rel_err(got_b, ref_b) <= TOL
 
 
-@pytest.mark.parametrize("n,cuts", [([4, 3, 6], [0, 2, 6]), ([3, 4, 7], [0, 1, 3, 7]), ([5, 6], [0, 2, 6]), ([3, 2, 4], [0, 1, 2, 3, 4])])
+@pytest.mark.parametrize("n,cuts", [([4, 3, 6], [0, 2, 6]), ([3, 4, 7], [0, 1, 3, 7]), ([5, 6], [0, 2, 6]), ([3, 2, 4], [0, 1, 2, 3, 4]),
+                                    ([90, 2, 5], [0, 2, 3, 5]), ([131, 7], [0, 3, 7])])
 def test_slab_owner_computes_rows_q2(gdt, ctx, oracle, n, cuts):
     """CG Q2 (BASELINE config 5 is sharded across the GPUs): the MCMG numbering groups DoFs by sub-entity kind, so a
     slab owns one contiguous row range per group; every owned row is complete without communication, the ranges of

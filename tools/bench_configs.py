@@ -28,6 +28,7 @@ ctx.set_stream(stream.cuda_stream)
 
 
 def timed(fn, reps):
+    reps = int(os.environ.get("GDTB_REPS", reps))
     fn()
     ctx.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
