@@ -972,10 +972,28 @@ __device__ __forceinline__ void q1qp_element(const CgQpGroup& G, const long long
       q1qp_term<D, M>(G, kq, t0, t1, t2, ix, iy, iz, G.scale * (ie * (br * bc)), out);
     }
   } else {
+    // the NQ samples of an element are contiguous; neighbouring lanes read neighbouring elements, i.e. addresses 8 NQ
+    // bytes apart: every load instruction of a warp touches 32 NQ / 16 lines whatever its width, so the widest load
+    // (256-bit, sm_100) cuts the LSU wavefronts of this stream 4 x (round-2 profile: LSU data pipe 66 % busy, 47 % of the
+    // warp-state samples waiting for these loads)
     const double* src = G.coef + e * (long long)NQ;
+    const unsigned long long base = reinterpret_cast<unsigned long long>(G.coef);
+    if (NQ % 4 == 0 && (base & 31ULL) == 0) {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q)
-      kq[q] = __ldg(src + q);
+      for (int q = 0; q < NQ / 4; ++q)
+        ldg256(src + 4 * q, kq[4 * q], kq[4 * q + 1], kq[4 * q + 2], kq[4 * q + 3]);
+    } else if (NQ % 2 == 0 && (base & 15ULL) == 0) {
+#pragma unroll
+      for (int q = 0; q < NQ / 2; ++q) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(src) + q);
+        kq[2 * q] = v.x;
+        kq[2 * q + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        kq[q] = __ldg(src + q);
+    }
     if (KIND == Q1G_MASS)
       q1qp_term<D, M>(G, kq, QPT_MM, QPT_MM, QPT_MM, ix, iy, iz, G.scale * ie, out);
     else {

@@ -19,6 +19,14 @@
 
 namespace gdtb {
 
+#ifdef __CUDACC__
+// 256-bit read-only global load (LDG.E.256.CONSTANT, sm_100): p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d)
+{
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+#endif
+
 constexpr int MAX_Q1D = 8;    // max Gauss points per direction
 constexpr int MAX_K = 3;      // max Lagrange order
 constexpr int MAX_NLOC = 64;  // (MAX_K+1)^3
