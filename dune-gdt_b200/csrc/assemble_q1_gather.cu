@@ -944,17 +944,46 @@ __device__ __forceinline__ void q1qp_term(const CgQpGroup& G, const double (&kq)
   }
 }
 
-// row i = (2^D - 1) ^ o of the local matrix of element e (offset o around the vertex): all (r, c) terms of the integrand
+// the NQ coefficient samples of element e (scalar kinds)
+template <int NQ>
+__device__ __forceinline__ void q1qp_load(const CgQpGroup& G, const long long e, double (&kq)[NQ])
+{
+  // the NQ samples of an element are contiguous; neighbouring lanes read neighbouring elements, i.e. addresses 8 NQ
+  // bytes apart: every load instruction of a warp touches 32 NQ / 16 lines whatever its width, so the widest load
+  // (256-bit, sm_100) cuts the LSU wavefronts of this stream 4 x (round-2 profile: LSU data pipe 66 % busy, 47 % of the
+  // warp-state samples waiting for these loads)
+  const double* src = G.coef + e * (long long)NQ;
+  const unsigned long long base = reinterpret_cast<unsigned long long>(G.coef);
+  if (NQ % 4 == 0 && (base & 31ULL) == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ / 4; ++q)
+      ldg256(src + 4 * q, kq[4 * q], kq[4 * q + 1], kq[4 * q + 2], kq[4 * q + 3]);
+  } else if (NQ % 2 == 0 && (base & 15ULL) == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ / 2; ++q) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(src) + q);
+      kq[2 * q] = v.x;
+      kq[2 * q + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      kq[q] = __ldg(src + q);
+  }
+}
+
+// row i = (2^D - 1) ^ o of the local matrix of element e (offset o around the vertex): all (r, c) terms of the integrand;
+// scalar kinds take the element's samples from the caller (kq_in, requested one element ahead)
 template <int D, int M, int KIND>
 __device__ __forceinline__ void q1qp_element(const CgQpGroup& G, const long long e, const int ox, const int oy,
                                              const int oz, const double (&a)[3], const double (&b)[3],
-                                             double (&out)[1 << D])
+                                             const double (&kq_in)[QpCount<D, M>::value], double (&out)[1 << D])
 {
   constexpr int NQ = QpCount<D, M>::value;
   const int ix = 1 - ox, iy = 1 - oy, iz = 1 - oz;
   const double ie = a[0] * (D > 1 ? a[1] : 1.) * (D > 2 ? a[2] : 1.); // integrals.hh:119
-  double kq[NQ];
   if (KIND == Q1G_LAPLACE_TENSOR) {
+    double kq[NQ];
     const double* src = G.coef + e * (long long)(NQ * D * D);
     // the (r, c) loop stays rolled (the point-table type becomes a run-time index into the constant bank): D * D unrolled
     // copies of the contraction per element would not fit the instruction cache
@@ -972,34 +1001,12 @@ __device__ __forceinline__ void q1qp_element(const CgQpGroup& G, const long long
       q1qp_term<D, M>(G, kq, t0, t1, t2, ix, iy, iz, G.scale * (ie * (br * bc)), out);
     }
   } else {
-    // the NQ samples of an element are contiguous; neighbouring lanes read neighbouring elements, i.e. addresses 8 NQ
-    // bytes apart: every load instruction of a warp touches 32 NQ / 16 lines whatever its width, so the widest load
-    // (256-bit, sm_100) cuts the LSU wavefronts of this stream 4 x (round-2 profile: LSU data pipe 66 % busy, 47 % of the
-    // warp-state samples waiting for these loads)
-    const double* src = G.coef + e * (long long)NQ;
-    const unsigned long long base = reinterpret_cast<unsigned long long>(G.coef);
-    if (NQ % 4 == 0 && (base & 31ULL) == 0) {
-#pragma unroll
-      for (int q = 0; q < NQ / 4; ++q)
-        ldg256(src + 4 * q, kq[4 * q], kq[4 * q + 1], kq[4 * q + 2], kq[4 * q + 3]);
-    } else if (NQ % 2 == 0 && (base & 15ULL) == 0) {
-#pragma unroll
-      for (int q = 0; q < NQ / 2; ++q) {
-        const double2 v = __ldg(reinterpret_cast<const double2*>(src) + q);
-        kq[2 * q] = v.x;
-        kq[2 * q + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        kq[q] = __ldg(src + q);
-    }
     if (KIND == Q1G_MASS)
-      q1qp_term<D, M>(G, kq, QPT_MM, QPT_MM, QPT_MM, ix, iy, iz, G.scale * ie, out);
+      q1qp_term<D, M>(G, kq_in, QPT_MM, QPT_MM, QPT_MM, ix, iy, iz, G.scale * ie, out);
     else {
 #pragma unroll
       for (int r = 0; r < D; ++r)
-        q1qp_term<D, M>(G, kq, r == 0 ? QPT_KK : QPT_MM, r == 1 ? QPT_KK : QPT_MM, r == 2 ? QPT_KK : QPT_MM, ix, iy, iz,
+        q1qp_term<D, M>(G, kq_in, r == 0 ? QPT_KK : QPT_MM, r == 1 ? QPT_KK : QPT_MM, r == 2 ? QPT_KK : QPT_MM, ix, iy, iz,
                         G.scale * (ie * (b[r] * b[r])), out);
     }
   }
@@ -1009,7 +1016,8 @@ __device__ __forceinline__ void q1qp_element(const CgQpGroup& G, const long long
 // item's CSR segment staged in shared memory and written by one TMA bulk store); the per-element arithmetic is the
 // sum-factorised quadrature loop above.
 template <int D, int M, int KIND, bool ACCUMULATE>
-__global__ void __launch_bounds__(Q1G_ROWS, 1)
+// 2 blocks per SM (128 registers) for up to 2^3 samples per element: measured 2.04 ms vs 2.21 ms with one block (C2 per-qp)
+__global__ void __launch_bounds__(Q1G_ROWS, (D == 3 && M >= 3) ? 1 : 2)
     k_q1_gather_qp(const __grid_constant__ Q1QpParams p, double* __restrict__ values, long long nrows, int nitems,
                    int stage_doubles, int nbuf)
 {
@@ -1070,18 +1078,41 @@ __global__ void __launch_bounds__(Q1G_ROWS, 1)
 #pragma unroll
         for (int k = 0; k < 9; ++k)
           P[0][k] = P[1][k] = P[2][k] = 0.;
+        // coefficient samples are requested one element ahead (cells outside the grid / slab read the thread's first
+        // valid cell instead: the request does not depend on the branch below and can be issued early)
+        constexpr int NQ = QpCount<D, M>::value;
+        constexpr bool AHEAD = KIND != Q1G_LAPLACE_TENSOR && NQ <= 8;
+        const long long e_safe = e0 + (vk[0][0] ? 0 : 1) + (long long)Nx * ((vk[1][0] ? 0 : 1) + (long long)Ny * (vk[2][0] ? 0 : 1));
+        double kq_next[NQ];
+        if (AHEAD)
+          q1qp_load<NQ>(G, vk[0][0] && vk[1][0] && vk[2][0] ? e0 : e_safe, kq_next);
 #pragma unroll
         for (int oz = 0; oz < 2; ++oz) {
 #pragma unroll
           for (int oxy = 0; oxy < 4; ++oxy) {
             const int ox = oxy & 1, oy = oxy >> 1;
+            double kq[NQ];
+            if (KIND != Q1G_LAPLACE_TENSOR && !AHEAD) {
+              if (vk[0][ox] && vk[1][oy] && vk[2][oz])
+                q1qp_load<NQ>(G, e0 + ox + (long long)Nx * (oy + (long long)Ny * oz), kq);
+            }
+            if (AHEAD) {
+#pragma unroll
+              for (int q = 0; q < NQ; ++q)
+                kq[q] = kq_next[q];
+              if (oz * 4 + oxy < 7) {
+                const int n = oz * 4 + oxy + 1, nx = n & 1, ny = (n >> 1) & 1, nz = n >> 2;
+                const long long en = e0 + nx + (long long)Nx * (ny + (long long)Ny * nz);
+                q1qp_load<NQ>(G, vk[0][nx] && vk[1][ny] && vk[2][nz] ? en : e_safe, kq_next);
+              }
+            }
             if (!(vk[0][ox] && vk[1][oy] && vk[2][oz]))
               continue;
             const double a[3] = {ha[0][ox], ha[1][oy], ha[2][oz]};
             const double b[3] = {hb[0][ox], hb[1][oy], hb[2][oz]};
             const long long e = e0 + ox + (long long)Nx * (oy + (long long)Ny * oz);
             double out[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-            q1qp_element<D, M, KIND>(G, e, ox, oy, oz, a, b, out);
+            q1qp_element<D, M, KIND>(G, e, ox, oy, oz, a, b, kq, out);
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
               const int sx = s & 1, sy = (s >> 1) & 1, sz = s >> 2;
@@ -1115,7 +1146,10 @@ __global__ void __launch_bounds__(Q1G_ROWS, 1)
 #pragma unroll
           for (int s = 0; s < NO; ++s)
             out[s] = 0.;
-          q1qp_element<D, M, KIND>(G, e, ox, oy, 0, a, b, out);
+          double kq[QpCount<D, M>::value];
+          if (KIND != Q1G_LAPLACE_TENSOR)
+            q1qp_load<QpCount<D, M>::value>(G, e, kq);
+          q1qp_element<D, M, KIND>(G, e, ox, oy, 0, a, b, kq, out);
 #pragma unroll
           for (int s = 0; s < NO; ++s)
             P[delta_index<D>(ox - 1 + (s & 1), oy - 1 + ((s >> 1) & 1), 0)] += out[s];
