@@ -713,8 +713,29 @@ int solve_csr(gdtb_ctx* ctx, const CsrView& A, const double* d_b, double* d_x, c
           status = fail(GDTB_ERR_CUDA, std::string("CG: ") + cudaGetErrorString(e2));
           break;
         }
-        it += check;
+        // the residual history of the replay: first iteration that meets the tolerance (reported; the iterate has
+        // moved on to the end of the replay and is at least as converged), stagnation = breakdown (rho or p.q became 0:
+        // the update kernels then leave x and r untouched), fail fast instead of spinning until max_iter
+        const double rr_before = rr;
+        long long first_ok = -1;
+        bool moved = false;
+        for (int k = 0; k < check; ++k) {
+          moved = moved || h_hist[(size_t)k] != rr_before;
+          if (first_ok < 0 && std::sqrt(h_hist[(size_t)k]) <= precision * std::sqrt(rr0))
+            first_ok = k;
+        }
         rr = h_hist[(size_t)check - 1];
+        if (first_ok >= 0 && rr == rr && std::sqrt(rr) <= precision * std::sqrt(rr0)) {
+          it += first_ok + 1;
+          converged = true;
+          break;
+        }
+        it += check;
+        if (rr == rr && !moved) {
+          status = fail(GDTB_ERR_OPERATOR, "apply_inverse: CG broke down (the residual stopped changing: rho or p.q "
+                                           "vanished) (XT::LA::Exceptions::linear_solver_failed)");
+          break;
+        }
         if (!(rr == rr)) {
           status = fail(GDTB_ERR_OPERATOR, "apply_inverse: CG broke down (NaN residual) -- is the matrix symmetric positive definite?");
           break;
@@ -774,8 +795,29 @@ int solve_csr(gdtb_ctx* ctx, const CsrView& A, const double* d_b, double* d_x, c
           status = fail(GDTB_ERR_CUDA, std::string("BiCGStab: ") + cudaGetErrorString(e2));
           break;
         }
-        it += check;
+        // the residual history of the replay: first iteration that meets the tolerance (reported; the iterate has
+        // moved on to the end of the replay and is at least as converged), stagnation = breakdown (rho or p.q became 0:
+        // the update kernels then leave x and r untouched), fail fast instead of spinning until max_iter
+        const double rr_before = rr;
+        long long first_ok = -1;
+        bool moved = false;
+        for (int k = 0; k < check; ++k) {
+          moved = moved || h_hist[(size_t)k] != rr_before;
+          if (first_ok < 0 && std::sqrt(h_hist[(size_t)k]) <= precision * std::sqrt(rr0))
+            first_ok = k;
+        }
         rr = h_hist[(size_t)check - 1];
+        if (first_ok >= 0 && rr == rr && std::sqrt(rr) <= precision * std::sqrt(rr0)) {
+          it += first_ok + 1;
+          converged = true;
+          break;
+        }
+        it += check;
+        if (rr == rr && !moved) {
+          status = fail(GDTB_ERR_OPERATOR, "apply_inverse: BiCGStab broke down (the residual stopped changing: rho or p.q "
+                                           "vanished) (XT::LA::Exceptions::linear_solver_failed)");
+          break;
+        }
         if (!(rr == rr)) {
           status = fail(GDTB_ERR_OPERATOR, "apply_inverse: BiCGStab broke down (NaN residual)");
           break;

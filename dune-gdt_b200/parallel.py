@@ -122,6 +122,8 @@ class DistributedAdvectionFvOperator:
             self._compute_stream = torch.cuda.Stream()
             self._comm_stream = torch.cuda.Stream()
         compute, comm = self._compute_stream, self._comm_stream
+        # the context is shared with the caller's other operators: its stream is re-pointed for this call only
+        previous = getattr(ctx, "stream_handle", None)
         ctx.set_stream(compute.cuda_stream)
         compute.wait_stream(caller)  # src is complete on the caller's stream
         comm.wait_stream(caller)
@@ -143,6 +145,7 @@ class DistributedAdvectionFvOperator:
         src.record_stream(compute)
         dst.record_stream(compute)
         src.record_stream(comm)
+        ctx.set_stream(previous)
 
     def apply(self, src, dst):
         """dst(owned) = L(src); fills src's ghost layers first"""
