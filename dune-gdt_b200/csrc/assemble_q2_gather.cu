@@ -1112,7 +1112,9 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
     else
       k_q2_items<2><<<(unsigned)((p.n_items + 127) / 128), 128, 0, L.stream>>>(p, reinterpret_cast<int4*>(p.items));
     L.count++;
-  }
+    p.items_ready = 1; // tells the caller that the buffer now holds this grid's / slab's records
+  } else if (ln != 2)
+    p.items_ready = 0;
   kern<<<(unsigned)grid, Q2G_THREADS, smem, L.stream>>>(p, values, stage_doubles, nbuf);
   time_end(L, KF_Q2_GATHER);
   L.count++;

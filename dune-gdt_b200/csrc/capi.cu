@@ -2273,7 +2273,7 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
                       && op->q2_items_key[2] == n_items;
     }
     GDTB_TRY(launch_q2_gather(L, p, op->test, op->d_values, accumulate));
-    if (n_items > 0) {
+    if (n_items > 0 && p.items_ready) {
       op->q2_items_key[0] = op->grid.layer_lo;
       op->q2_items_key[1] = op->grid.layer_hi;
       op->q2_items_key[2] = n_items;
