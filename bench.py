@@ -354,6 +354,13 @@ def assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src):
     cg_case("c2_q1_laplace_256^3_kappa_per_element", 256, 1, D.form(D.integrand(D.INT_LAPLACE, diffusion=fe)), "q1_gather", 20,
             read_bytes=8.0 * 256**3)
     del kap
+    # the same for C5 (one integrand, one kappa per element): per-element 1D factor tables in the Q2 gather
+    kap5 = torch.rand(128**3, dtype=torch.float64, device="cuda") + 0.5
+    fe5 = D.Function()
+    fe5.kind, fe5.data_on_device, fe5.data = D.FN_ELEM_SCALAR, 1, C.cast(kap5.data_ptr(), C.POINTER(C.c_double))
+    cg_case("c5_q2_laplace_128^3_kappa_per_element", 128, 2, D.form(D.integrand(D.INT_LAPLACE, diffusion=fe5)), "q2_gather", 10,
+            read_bytes=8.0 * 128**3)
+    del kap5
     # kappa per quadrature point (declared order 0: 2^3 points for Q1, 3^3 for Q2): the quadrature loop itself, sum-factorised
     f1 = qp_function(torch, 256**3, 8, 0)
     cg_case("c2_q1_laplace_256^3_kappa_per_qp", 256, 1, D.form(D.integrand(D.INT_LAPLACE, diffusion=f1)), "q1_gather", 5,

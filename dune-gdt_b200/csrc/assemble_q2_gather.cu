@@ -41,6 +41,9 @@
 #define Q2G_MIN_BLOCKS 3
 #endif
 
+#ifndef Q2G_PE_MIN_BLOCKS
+#define Q2G_PE_MIN_BLOCKS 2
+#endif
 #ifndef Q2G_SLOT_MAJOR
 #define Q2G_SLOT_MAJOR 1
 #endif
@@ -378,6 +381,61 @@ __global__ void __launch_bounds__(128) k_q2_axis_tables(const __grid_constant__ 
   }
 }
 
+// Per-ELEMENT 1D factors for a single integrand whose coefficient is one value per element (Q2GatherParams::sf == 2): for
+// the lattice point p = 2 c + S of axis k and its element candidate o (S = 1: the element c; S = 0: c - 1 and c) the row
+// vectors K_o[j] = K1[i_o][j] / h_e, M_o[j] = M1[i_o][j] h_e (j = local column index in that element, zero for an
+// element outside the grid): 12 doubles per point, [o][K0 K1 K2 M0 M1 M2]; x component-major (q2_xpe_index).
+__host__ __device__ __forceinline__ long long q2_xpe_index(const int S, const int comp, const int c, const long long Nx)
+{
+  return (long long)(S * 12 + comp) * (Nx + 1) + c;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_q2_axis_tables_pe(const __grid_constant__ Q2GatherParams p, double* __restrict__ tab)
+{
+  const GridDev& g = p.g;
+  long long total = 0;
+  for (int k = 0; k < D; ++k)
+    total += 2 * g.n[k] + 1;
+  const Q2Group& G = p.group[0];
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    int k = 0;
+    while (r >= 2 * g.n[k] + 1) {
+      r -= 2 * g.n[k] + 1;
+      ++k;
+    }
+    const int pt = (int)r, S = pt & 1, c = pt >> 1, N = (int)g.n[k];
+    double v[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+      v[i] = 0.;
+    for (int o = 0; o < (S ? 1 : 2); ++o) {
+      const int e = S ? c : c - 1 + o;
+      if (e < 0 || e >= N)
+        continue;
+      const double ext = q2_cell_extent(g.lo[k], g.h[k], e);
+      const double inv = __drcp_rn(ext);
+      const int il = S ? 1 : 2 - 2 * o;
+      for (int j = 0; j < 3; ++j) {
+        v[6 * o + j] = inv * G.TK[il][j];
+        v[6 * o + 3 + j] = ext * G.TM[il][j];
+      }
+    }
+    if (k == 0) {
+      double* out = tab + p.sf_axis_off[0];
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        out[q2_xpe_index(S, i, c, g.n[0])] = v[i];
+    } else {
+      double* out = tab + p.sf_axis_off[k] + 12LL * pt;
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        out[i] = v[i];
+    }
+  }
+}
+
 // number of box offsets a in [lo, hi] with a & 1 == par
 __device__ __forceinline__ int q2_count_par(int lo, int hi, int par)
 {
@@ -465,33 +523,18 @@ __device__ __forceinline__ void q2_sf_group(const Q2GatherParams& p, const int g
   }
 }
 
-template <int D, int SX, int SY, int SL, bool NG1>
-__device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const int cx, const int cy, const int cl,
-                                                const int slot, double* __restrict__ row)
+// writes the (a_y, a_x) plane of a row into its CSR positions (closed forms; interior rows: compile-time offsets)
+template <int D, int SX, int SY, int SL>
+__device__ __forceinline__ void q2_scatter_plane(const GridDev& g, const int px, const int py, const int pl, const int slot,
+                                                 const double (&acc)[D == 3 ? AxisBox<SY>::A : 1][AxisBox<SX>::A],
+                                                 double* __restrict__ row)
 {
   using BX = AxisBox<SX>;
   using BY = AxisBox<SY>;
   using BL = AxisBox<SL>;
-  const GridDev& g = p.g;
   constexpr int last = D - 1;
-  if (slot >= BL::A)
-    return;
   const int Nx = (int)g.n[0], Ny = D == 3 ? (int)g.n[1] : 1, Nl = (int)g.n[last];
-  const int px = 2 * cx + SX, py = 2 * cy + SY, pl = 2 * cl + SL;
   constexpr int AX = BX::A, AY = D == 3 ? BY::A : 1, AL = BL::A;
-  // the plane must lie inside the lattice
-  const int ql = pl - BL::R + slot;
-  if (ql < 0 || ql > 2 * Nl)
-    return;
-
-  double acc[AY][AX];
-  q2_sf_group<D, AX, AY, true>(p, 0, px, py, pl, slot, acc);
-  if (!NG1) { // one group (the common case) lets the compiler sink the arithmetic to the stores: fewer live registers
-#pragma unroll 1
-    for (int gi = 1; gi < p.n_groups; ++gi)
-      q2_sf_group<D, AX, AY, false>(p, gi, px, py, pl, slot, acc);
-  }
-
   // parity of the lattice point at box offset a is a & 1 (S + R = 2 for both parities); the column groups of a row
   // come in ascending global index (codim ascending, shift ascending), each lexicographic with x fastest
   const bool interior = px >= BX::R && px + BX::R <= 2 * Nx && (D == 2 || (py >= BY::R && py + BY::R <= 2 * Ny))
@@ -569,12 +612,164 @@ __device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const i
   }
 }
 
+template <int D, int SX, int SY, int SL, bool NG1>
+__device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const int cx, const int cy, const int cl,
+                                                const int slot, double* __restrict__ row)
+{
+  using BX = AxisBox<SX>;
+  using BY = AxisBox<SY>;
+  using BL = AxisBox<SL>;
+  const GridDev& g = p.g;
+  constexpr int last = D - 1;
+  if (slot >= BL::A)
+    return;
+  const int Nx = (int)g.n[0], Ny = D == 3 ? (int)g.n[1] : 1, Nl = (int)g.n[last];
+  const int px = 2 * cx + SX, py = 2 * cy + SY, pl = 2 * cl + SL;
+  constexpr int AX = BX::A, AY = D == 3 ? BY::A : 1, AL = BL::A;
+  // the plane must lie inside the lattice
+  const int ql = pl - BL::R + slot;
+  if (ql < 0 || ql > 2 * Nl)
+    return;
+
+  double acc[AY][AX];
+  q2_sf_group<D, AX, AY, true>(p, 0, px, py, pl, slot, acc);
+  if (!NG1) { // one group (the common case) lets the compiler sink the arithmetic to the stores: fewer live registers
+#pragma unroll 1
+    for (int gi = 1; gi < p.n_groups; ++gi)
+      q2_sf_group<D, AX, AY, false>(p, gi, px, py, pl, slot, acc);
+  }
+
+  q2_scatter_plane<D, SX, SY, SL>(g, px, py, pl, slot, acc, row);
+}
+
+// Single integrand with ONE coefficient value per element (sf == 2): the plane of a row is
+//   sum_{o_l, o_y} [ (ML MY[j_y]) PX + (ML KY[j_y] + KL MY[j_y]) QX ],  PX = sum_{o_x} kappa_e KX_o, QX = sum_{o_x} kappa_e MX_o
+// (mass: (ML MY[j_y]) QX) over the element candidates that contain both the row's lattice point and the plane -- the
+// per-element factors come from k_q2_axis_tables_pe, the coefficient of an element is read once per (o_x, o_y, o_l);
+// about 100-200 FMAs per thread instead of the ~1 400 instructions of the generic per-element loop (q2_row_plane)
+template <int D, int SX, int SY, int SL>
+__device__ __forceinline__ void q2_row_plane_pe(const Q2GatherParams& p, const int cx, const int cy, const int cl,
+                                                const int slot, double* __restrict__ row)
+{
+  using BX = AxisBox<SX>;
+  using BY = AxisBox<SY>;
+  using BL = AxisBox<SL>;
+  const GridDev& g = p.g;
+  constexpr int last = D - 1;
+  if (slot >= BL::A)
+    return;
+  const int Nx = (int)g.n[0], Ny = D == 3 ? (int)g.n[1] : 1, Nl = (int)g.n[last];
+  const int px = 2 * cx + SX, py = 2 * cy + SY, pl = 2 * cl + SL;
+  constexpr int AX = BX::A, AY = D == 3 ? BY::A : 1, NEX = BX::NE, NEY = D == 3 ? BY::NE : 1;
+  const int ql = pl - BL::R + slot;
+  if (ql < 0 || ql > 2 * Nl)
+    return;
+  const Q2Group& G = p.group[0];
+  const double* tab = p.sf_tab;
+  const bool mass = G.kind == Q1G_MASS;
+
+  double KX[NEX][3], MX[NEX][3], KY[NEY][3], MY[NEY][3];
+  {
+    const double* q = tab + p.sf_axis_off[0] + q2_xpe_index(SX, 0, cx, Nx);
+    const long long stride = Nx + 1;
+#pragma unroll
+    for (int o = 0; o < NEX; ++o)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        KX[o][j] = __ldg(q + (6 * o + j) * stride);
+        MX[o][j] = __ldg(q + (6 * o + 3 + j) * stride);
+      }
+  }
+  if (D == 3) {
+    const double* q = tab + p.sf_axis_off[1] + 12LL * py;
+#pragma unroll
+    for (int o = 0; o < NEY; ++o)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        KY[o][j] = __ldg(q + 6 * o + j);
+        MY[o][j] = __ldg(q + 6 * o + 3 + j);
+      }
+  }
+  // the coefficients of the <= 8 elements first: all requests are in flight before the first one is needed
+  double kap[BL::NE][NEY][NEX];
+#pragma unroll
+  for (int ol = 0; ol < BL::NE; ++ol) {
+    const int jl = slot - BL::first(ol);
+    const int el = SL ? cl : cl - 1 + ol;
+    const bool vl = jl >= 0 && jl <= 2 && el >= 0 && el < Nl;
+#pragma unroll
+    for (int oy = 0; oy < NEY; ++oy) {
+      const int ey = D == 3 ? (SY ? cy : cy - 1 + oy) : 0;
+      const bool vy = D < 3 || (ey >= 0 && ey < Ny);
+#pragma unroll
+      for (int ox = 0; ox < NEX; ++ox) {
+        const int ex = SX ? cx : cx - 1 + ox;
+        const bool valid = vl && vy && ex >= 0 && ex < Nx;
+        const long long e = (long long)ex + (long long)Nx * (D == 3 ? ey + (long long)Ny * el : el);
+        kap[ol][oy][ox] = valid ? __ldg(G.coef + e) : 0.;
+      }
+    }
+  }
+  double acc[AY][AX];
+#pragma unroll
+  for (int a = 0; a < AY; ++a)
+#pragma unroll
+    for (int b = 0; b < AX; ++b)
+      acc[a][b] = 0.;
+
+#pragma unroll
+  for (int ol = 0; ol < BL::NE; ++ol) {
+    const int jl = slot - BL::first(ol);
+    if (jl < 0 || jl > 2)
+      continue; // the element candidate does not contain the plane
+    const int el = SL ? cl : cl - 1 + ol;
+    if (el < 0 || el >= Nl)
+      continue;
+    const double* tl = tab + p.sf_axis_off[last] + 12LL * pl + 6 * ol;
+    const double KL = G.scale * __ldg(tl + jl), ML = G.scale * __ldg(tl + 3 + jl);
+#pragma unroll
+    for (int oy = 0; oy < NEY; ++oy) {
+      double PX[AX], QX[AX];
+#pragma unroll
+      for (int b = 0; b < AX; ++b)
+        PX[b] = QX[b] = 0.;
+#pragma unroll
+      for (int ox = 0; ox < NEX; ++ox) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          PX[BX::first(ox) + j] = fma(kap[ol][oy][ox], KX[ox][j], PX[BX::first(ox) + j]);
+          QX[BX::first(ox) + j] = fma(kap[ol][oy][ox], MX[ox][j], QX[BX::first(ox) + j]);
+        }
+      }
+#pragma unroll
+      for (int jy = 0; jy < (D == 3 ? 3 : 1); ++jy) {
+        const int a = D == 3 ? BY::first(oy) + jy : 0;
+        const double my = D == 3 ? MY[oy][jy] : 1., ky = D == 3 ? KY[oy][jy] : 0.;
+        if (mass) {
+          const double c = ML * my;
+#pragma unroll
+          for (int b = 0; b < AX; ++b)
+            acc[a][b] = fma(c, QX[b], acc[a][b]);
+        } else {
+          const double cA = ML * my, cB = fma(ML, ky, KL * my);
+#pragma unroll
+          for (int b = 0; b < AX; ++b)
+            acc[a][b] = fma(cA, PX[b], fma(cB, QX[b], acc[a][b]));
+        }
+      }
+    }
+  }
+  q2_scatter_plane<D, SX, SY, SL>(g, px, py, pl, slot, acc, row);
+}
+
 template <int SF, int D, int SX, int SY, int SL, int M = 0, int KIND = 0>
 __device__ __forceinline__ void q2_dispatch(const Q2GatherParams& p, const int cx, const int cy, const int cl,
                                             const int slot, double* __restrict__ row)
 {
   if constexpr (SF == 3)
     q2_row_plane<D, SX, SY, SL, M, KIND>(p, cx, cy, cl, slot, row);
+  else if (SF == 4)
+    q2_row_plane_pe<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
   else if (SF == 2)
     q2_row_plane_sf<D, SX, SY, SL, true>(p, cx, cy, cl, slot, row);
   else if (SF == 1)
@@ -661,13 +856,14 @@ __global__ void __launch_bounds__(128) k_q2_items(const __grid_constant__ Q2Gath
 }
 
 // SF: 0 per-element coefficients, 1 sum-factorised (constant coefficients), 2 sum-factorised with a single group,
-// 3 one integrand of kind KIND with a coefficient per quadrature point (M Gauss points per direction)
+// 3 one integrand of kind KIND with a coefficient per quadrature point (M Gauss points per direction), 4 one integrand
+// with one coefficient value per element (per-element 1D factor tables, q2_row_plane_pe)
 // LN: every lattice line of every row group is at least as long as a work item (checked at launch), so an item touches
 // at most two lines: row starts come from two uniform line records + one multiply-add per thread instead of a decode
 // (two divisions) and a full q2_row_offset per thread, and the end of the segment from the same records.
 // LN == 2: the uniform part (row group, first row, segment, line records) comes from the work-item records of k_q2_items.
 template <int D, bool ACCUMULATE, int SF, int M = 0, int KIND = 0, int LN = 0>
-__global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF == 3 ? 1 : 2))
+__global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF == 4 ? Q2G_PE_MIN_BLOCKS : (SF == 3 ? 1 : 2)))
     k_q2_gather(const __grid_constant__ Q2GatherParams p, double* __restrict__ values, int stage_doubles, int nbuf)
 {
   extern __shared__ __align__(16) double smem[];
@@ -688,8 +884,8 @@ __global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF ==
   const int4* const recs = reinterpret_cast<const int4*>(p.items);
   int4 nra = make_int4(0, 0, 0, 0), nrb = nra;
   if (LN == 2 && (long long)blockIdx.x < p.n_items) {
-    nra = __ldg(recs + 2 * blockIdx.x);
-    nrb = __ldg(recs + 2 * blockIdx.x + 1);
+    nra = q2_ldg_int4_here(recs + 2 * blockIdx.x);
+    nrb = q2_ldg_int4_here(recs + 2 * blockIdx.x + 1);
   }
   for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     // ---- per item (uniform): row group, rows, CSR segment ---------------------------------------------------
@@ -703,8 +899,8 @@ __global__ void __launch_bounds__(Q2G_THREADS, SF == 2 ? Q2G_MIN_BLOCKS : (SF ==
     if (LN == 2) {
       const int4 ra = nra, rb = nrb;
       if (item + gridDim.x < p.n_items) {
-        nra = __ldg(recs + 2 * (item + gridDim.x));
-        nrb = __ldg(recs + 2 * (item + gridDim.x) + 1);
+        nra = q2_ldg_int4_here(recs + 2 * (item + gridDim.x));
+        nrb = q2_ldg_int4_here(recs + 2 * (item + gridDim.x) + 1);
       }
       start = (long long)(((unsigned long long)(unsigned)ra.y << 32) | (unsigned long long)(unsigned)ra.x);
       seg = ra.z;
@@ -896,6 +1092,14 @@ int q2_slab_ranges(const GridDev& g, const SpaceDev& sp, Q2SlabRange* out)
   return r;
 }
 
+long long q2_pe_table_doubles(const GridDev& g)
+{
+  long long total = 24 * (g.n[0] + 1);
+  for (int k = 1; k < g.d; ++k)
+    total += 12 * (2 * g.n[k] + 1);
+  return total;
+}
+
 long long q2_sf_table_doubles(const GridDev& g)
 {
   long long total = 20 * (g.n[0] + 1); // x: component-major, both parities padded to N_x + 1 points (q2_x_index)
@@ -1059,7 +1263,7 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
   const int seg5 = (Q2G_THREADS / 5) * max_row, seg3 = (Q2G_THREADS / 3) * (max_row / 5 * 3);
   const int stage_doubles = ((std::max(seg5, seg3) + 2) + 1) & ~1;
   static const int nbuf_env = std::getenv("GDTB_Q2_NBUF") ? std::atoi(std::getenv("GDTB_Q2_NBUF")) : 0;
-  const bool single_group = p.sf && p.n_groups == 1;
+  const bool single_group = p.sf && p.n_groups == 1; // sf == 2 (one per-element integrand) included
   const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : (single_group ? 1 : 2));
   const size_t smem = (size_t)nbuf * stage_doubles * sizeof(double);
   // line-based bookkeeping (LN) needs every lattice line of every row group to hold at least one work item's rows
@@ -1073,6 +1277,14 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
     if (!q2_qp_supported(d, p.qp.m, p.qp.kind))
       return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_gather_qp: unsupported number of Gauss points per direction");
     kern = d == 3 ? q2_qp_kernel_d<3>(p.qp.m, p.qp.kind, accumulate) : q2_qp_kernel_d<2>(p.qp.m, p.qp.kind, accumulate);
+  } else if (p.sf == 2) {
+    kern = q2_pick<4>(d, accumulate, ln);
+    long long off = 0;
+    for (int k = 0; k < d; ++k) {
+      p.sf_axis_off[k] = off;
+      off += k == 0 ? 24 * (g.n[0] + 1) : 12 * (2 * g.n[k] + 1);
+    }
+    p.sf_group_stride = off;
   } else if (p.sf) {
     kern = p.n_groups == 1 ? q2_pick<2>(d, accumulate, ln) : q2_pick<1>(d, accumulate, ln);
     long long off = 0;
@@ -1101,7 +1313,14 @@ int launch_q2_impl(Launch& L, Q2GatherParams& p, const SpaceDev& sp, double* val
     grid = p.n_items;
   note_kernel(L, KF_Q2_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_Q2_GATHER);
-  if (p.sf) {
+  if (p.sf == 2) {
+    const long long work = p.sf_group_stride / 12;
+    if (d == 3)
+      k_q2_axis_tables_pe<3><<<(unsigned)((work + 127) / 128), 128, 0, L.stream>>>(p, const_cast<double*>(p.sf_tab));
+    else
+      k_q2_axis_tables_pe<2><<<(unsigned)((work + 127) / 128), 128, 0, L.stream>>>(p, const_cast<double*>(p.sf_tab));
+    L.count++;
+  } else if (p.sf) {
     const long long work = p.sf_group_stride / 10 * p.n_groups;
     k_q2_axis_tables<<<(unsigned)((work + 127) / 128), 128, 0, L.stream>>>(p, const_cast<double*>(p.sf_tab));
     L.count++;

@@ -2254,6 +2254,21 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       }
       p.sf = 1;
       p.sf_tab = op->d_q2_tab;
+    } else if (p.n_groups == 1 && p.group[0].coef_elem
+               && (p.group[0].kind == Q1G_MASS || p.group[0].kind == Q1G_LAPLACE_SCALAR) && !std::getenv("GDTB_Q2_NO_SF")
+               && !std::getenv("GDTB_Q2_NO_PE")) {
+      // one integrand with one coefficient value per element: per-element 1D factor tables (q2_row_plane_pe)
+      const size_t bytes = sizeof(double) * (size_t)q2_pe_table_doubles(op->grid);
+      if (op->d_q2_tab_bytes < bytes) {
+        cudaFree(op->d_q2_tab);
+        op->d_q2_tab = nullptr;
+        op->d_q2_tab_bytes = 0;
+        if (cudaMalloc(&op->d_q2_tab, bytes) != cudaSuccess)
+          return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (Q2 per-element factor tables)");
+        op->d_q2_tab_bytes = bytes;
+      }
+      p.sf = 2;
+      p.sf_tab = op->d_q2_tab;
     }
     // work-item records of the gather kernel: computed on the device once per grid / slab, kept with the operator
     const long long n_items = accumulate ? 0 : q2_item_count(op->grid, op->test);

@@ -284,7 +284,7 @@ struct Q2GatherParams
   // sum-factorised path (all coefficients constant): per group and axis, for every lattice point p in [0, 2 N_k] the
   // 1D row vectors K[0..5) = sum_e K1[i_e(p)][.] / h_e and M[0..5) = sum_e M1[i_e(p)][.] h_e over the <= 2 elements
   // that contain p, indexed by box offset; layout tab[group][sf_axis_off[k] + 10 p + {K: 0..4, M: 5..9}]
-  int sf;
+  int sf; // 0: off, 1: all coefficients constant (summed tables), 2: ONE integrand with one coefficient per element
   const double* sf_tab;
   long long sf_axis_off[3], sf_group_stride;
   CgQpGroup qp; // launch_q2_gather_qp: the one integrand with a coefficient per quadrature point
@@ -299,6 +299,7 @@ struct Q2GatherParams
 long long q2_item_count(const GridDev& g, const SpaceDev& sp);
 
 long long q2_sf_table_doubles(const GridDev& g); // doubles per group
+long long q2_pe_table_doubles(const GridDev& g); // sf == 2: per-element 1D factors of a single integrand
 // Row ranges a slab of element layers [g.layer_lo, g.layer_hi) owns (owner-computes-rows: a lattice layer belongs to
 // the slab of the element layer above it, the top layer to the last slab): one contiguous range per sub-entity group
 // of the MCMG numbering, with the global CSR offset of its first value and its position in the slab-local buffer

@@ -58,6 +58,15 @@ __device__ __forceinline__ void q2_cp_async_wait_all()
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
+// read-only 16-byte load that the compiler may not sink towards its first use (the work-item record of the NEXT item is
+// requested a whole item ahead)
+__device__ __forceinline__ int4 q2_ldg_int4_here(const int4* ptr)
+{
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+
 __device__ __forceinline__ void q2_prefetch_l1(const void* ptr)
 {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));

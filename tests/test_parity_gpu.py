@@ -589,6 +589,8 @@ def test_slab_owner_computes_rows_q2(gdt, ctx, oracle, n, cuts):
 
     gdesc = D.grid_desc(-1.0, 1.0, n)
     forms = [laplace(0.75), mass(0.5)]
+    if len(n) == 3 and n[0] in (3, 90):  # one integrand with one coefficient per element: the per-element factor tables
+        forms = [laplace(D.fn_elem(rng_elem(n, seed=5)))]
     rp, ci = oracle.pattern(gdesc, (CG, 2))
     ref_v, _ = oracle.assemble(gdesc, CG, 2, rp, ci, forms)
     space = make_space(gdt, ctx, gdesc, CG, 2)

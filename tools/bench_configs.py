@@ -119,6 +119,17 @@ def main():
         f._keep = kap
         run(f"C2 3D Q1 {n}^3, one kappa per element", D.grid_desc(-1.0, 1.0, [n, n, n]), D.SPACE_CG, 1, D.STENCIL_ELEMENT,
             element=[D.form(D.integrand(D.INT_LAPLACE, diffusion=f))], reps=10)
+    if "c5-elem" in which:
+        n = n_override or 128
+        g_ = torch.Generator(device="cuda").manual_seed(7)
+        kap = 0.5 + torch.rand(n**3, dtype=torch.float64, device="cuda", generator=g_)
+        f = D.Function()
+        f.kind = D.FN_ELEM_SCALAR
+        f.data_on_device = 1
+        f.data = C.cast(kap.data_ptr(), C.POINTER(C.c_double))
+        f._keep = kap
+        run(f"C5 3D Q2 {n}^3, one kappa per element", D.grid_desc(-1.0, 1.0, [n, n, n]), D.SPACE_CG, 2, D.STENCIL_ELEMENT,
+            element=[D.form(D.integrand(D.INT_LAPLACE, diffusion=f))], reps=5)
     if "c2" in which:
         n = n_override or 256
         run(f"C2 3D Q1 {n}^3", D.grid_desc(-1.0, 1.0, [n, n, n]), D.SPACE_CG, 1, D.STENCIL_ELEMENT, element=[lap], reps=10)
