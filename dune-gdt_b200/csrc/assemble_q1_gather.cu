@@ -146,6 +146,54 @@ __device__ __forceinline__ void q1_decode(unsigned v, const FastDiv& dx, const F
   }
 }
 
+// read-only 16-byte load that stays where it is written (the record of the NEXT item is requested an item ahead)
+__device__ __forceinline__ int4 q1_ldg_int4_here(const int4* ptr)
+{
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+
+// work-item records of k_q1_gather<..., PREF> (3D, ROWS rows per item, every lattice line at least ROWS vertices long):
+// the uniform per-item bookkeeping (first vertex, CSR segment, the two lines an item touches) once per grid / slab
+__global__ void __launch_bounds__(128) k_q1_items(const Q1GatherParams p, long long nrows, int nitems, int rows_per_item,
+                                                   int4* __restrict__ recs)
+{
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= nitems)
+    return;
+  const GridDev& g = p.g;
+  const int Nx = (int)g.n[0], Ny = (int)g.n[1], Nz = (int)g.n[2];
+  const long long l0 = (long long)item * rows_per_item;
+  const int nr = (int)min((long long)rows_per_item, nrows - l0);
+  const unsigned r0 = (unsigned)(p.row_offset + l0);
+  int bx, by, bz, cx, cy, cz;
+  q1_decode<3>(r0, p.div_vx, p.div_vy, bx, by, bz);
+  q1_decode<3>(r0 + nr, p.div_vx, p.div_vy, cx, cy, cz);
+  const long long gstart = q1_rowptr<3>(bx, by, bz, Nx, Ny, Nz);
+  const long long gend = q1_rowptr<3>(cx, cy, cz, Nx, Ny, Nz);
+  int y1 = by + 1, z1 = bz;
+  if (y1 > Ny) {
+    y1 = 0;
+    z1 = bz + 1;
+  }
+  const bool two = bx + nr > Nx + 1;
+  const int w0 = n_axis(by, Ny) * n_axis(bz, Nz);
+  const int w1 = two ? n_axis(y1, Ny) * n_axis(z1, Nz) : 0;
+  const long long start = gstart - p.value_offset;
+  int4 a, b;
+  a.x = (int)(unsigned)(start & 0xffffffffLL);
+  a.y = (int)(unsigned)((unsigned long long)start >> 32);
+  a.z = int(gend - gstart);
+  a.w = nr | (w0 << 9) | (w1 << 13);
+  b.x = bx;
+  b.y = by;
+  b.z = bz;
+  b.w = two ? int(q1_rowptr<3>(0, y1, z1, Nx, Ny, Nz) - gstart) : 0;
+  recs[2 * item] = a;
+  recs[2 * item + 1] = b;
+}
+
 constexpr int Q1G_ROWS = 256; // rows (vertices) per work item = threads per CTA
 #ifndef Q1G_ROWS_PREF
 #define Q1G_ROWS_PREF 224 // the same with the coefficient prefetch slots (k_q1_gather<..., PREF>)
@@ -305,11 +353,27 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
   // PREF: slot (o, t) = kappa of the cell with offset o around the vertex of thread t (0 for a cell outside the grid /
   // slab), behind the stage buffers
   double* const slots = smem + (size_t)nbuf * stage_doubles;
-  auto prefetch_coef = [&](int item_) {
-    const long long l0_ = (long long)item_ * ROWS;
-    if (item_ < nitems && l0_ + threadIdx.x < nrows) {
+  // (PREF) vertex of thread t of an item whose first vertex is (bx, by, bz): the item's rows are consecutive along x and
+  // a lattice line holds at least ROWS vertices (checked at launch), so at most one line break lies inside the item
+  auto item_vertex = [&](int bx, int by, int bz, int& ix, int& iy, int& iz) -> bool {
+    ix = bx + (int)threadIdx.x;
+    iy = by;
+    iz = bz;
+    const bool second = ix > Nx;
+    if (second) {
+      ix -= Nx + 1;
+      iy = by + 1;
+      if (iy > Ny) {
+        iy = 0;
+        iz = bz + 1;
+      }
+    }
+    return second;
+  };
+  auto prefetch_coef = [&](const int4& rb_, int nr_) {
+    if ((int)threadIdx.x < nr_) {
       int ix, iy, iz;
-      q1_decode<D>((unsigned)(p.row_offset + l0_) + threadIdx.x, p.div_vx, p.div_vy, ix, iy, iz);
+      item_vertex(rb_.x, rb_.y, rb_.z, ix, iy, iz);
       const long long e0 = (long long)(ix - 1) + (long long)Nx * ((iy - 1) + (long long)Ny * (iz - 1));
 #pragma unroll
       for (int o = 0; o < 8; ++o) {
@@ -347,8 +411,16 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
     const unsigned bytes = (unsigned)(((hi - lo) & ~1LL) * sizeof(double));
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
   };
+  // (PREF) work-item records (k_q1_items): {start lo, start hi, seg, nr | w0 << 9 | w1 << 13}, {bx, by, bz, rel1}; the
+  // record of the next item is requested one item ahead
+  const int4* const recs = reinterpret_cast<const int4*>(p.items);
+  int4 nra = make_int4(0, 0, 0, 0), nrb = nra;
   if (PREF) {
-    prefetch_coef(blockIdx.x);
+    if ((int)blockIdx.x < nitems) {
+      nra = q1_ldg_int4_here(recs + 2 * blockIdx.x);
+      nrb = q1_ldg_int4_here(recs + 2 * blockIdx.x + 1);
+    }
+    prefetch_coef(nrb, nra.w & 511);
     prefetch_lines_l2(blockIdx.x + (int)gridDim.x);
     prefetch_lines_l2(blockIdx.x + 2 * (int)gridDim.x);
   }
@@ -359,8 +431,17 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
     const int item = P2P ? nitems - 1 - it : it;
     // ---- per item (uniform over the CTA): the CSR segment -------------------------------------------------
     const long long l0 = (long long)item * ROWS; // first local row
-    const int nr = (int)min((long long)ROWS, nrows - l0);
+    int nr = (int)min((long long)ROWS, nrows - l0);
     const unsigned r0 = (unsigned)(p.row_offset + l0); // first global row (= vertex index)
+    int4 ra = nra, rb = nrb;
+    if (PREF) {
+      nr = ra.w & 511;
+      if (it + (int)gridDim.x < nitems) {
+        nra = q1_ldg_int4_here(recs + 2 * (it + (int)gridDim.x));
+        nrb = q1_ldg_int4_here(recs + 2 * (it + (int)gridDim.x) + 1);
+      } else
+        nra.w = 0; // no rows: the coefficient request below is empty
+    }
     const Q1HaloP2p& H = p.halo;
     const long long top_row = nrows - H.layer_rows;
     const bool recv_item = P2P && H.has_lower && l0 < H.layer_rows;
@@ -378,7 +459,12 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
     int seg = 0, phase = 0;
     unsigned start32 = 0;
     double* stage = smem;
-    if (want_values) {
+    if (PREF) {
+      start = (long long)(((unsigned long long)(unsigned)ra.y << 32) | (unsigned long long)(unsigned)ra.x);
+      seg = ra.z;
+      phase = int((reinterpret_cast<unsigned long long>(values + start) >> 3) & 1ULL);
+      stage = smem + buf * stage_doubles + phase;
+    } else if (want_values) {
       int bx, by, bz, cx, cy, cz;
       q1_decode<D>(r0, p.div_vx, p.div_vy, bx, by, bz);
       q1_decode<D>(r0 + nr, p.div_vx, p.div_vy, cx, cy, cz);
@@ -401,12 +487,16 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
 #pragma unroll
       for (int o = 0; o < 8; ++o)
         c8[o] = slots[o * ROWS + threadIdx.x];
-      prefetch_coef(it + (int)gridDim.x);
+      prefetch_coef(nrb, nra.w & 511);
       prefetch_lines_l2(it + 3 * (int)gridDim.x);
     }
     if ((int)threadIdx.x < nr) {
       int ix, iy, iz;
-      q1_decode<D>(r0 + threadIdx.x, p.div_vx, p.div_vy, ix, iy, iz);
+      bool second_line = false;
+      if (PREF)
+        second_line = item_vertex(rb.x, rb.y, rb.z, ix, iy, iz);
+      else
+        q1_decode<D>(r0 + threadIdx.x, p.div_vx, p.div_vy, ix, iy, iz);
       const int il[3] = {ix, iy, iz};
       const int Nl[3] = {Nx, Ny, Nz};
       // geometry of the two cells per axis around the vertex: ha[k][o] = h_k, hb[k][o] = 1 / h_k (J^{-T} = diag(1/h_k),
@@ -444,7 +534,11 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
       const bool full_xy = cx0 && cx1 && (D < 2 || (cy0 && cy1));
       // wrap-around 32-bit arithmetic is exact for the (small) difference of two row pointers
       double* row = stage;
-      if (want_values)
+      if (PREF) {
+        // row start from the item's line records: w = n(iy) n(iz) entries per entry along x
+        const int w0 = (ra.w >> 9) & 15, w1 = (ra.w >> 13) & 15;
+        row += second_line ? rb.w + w1 * S_axis(ix, Nx) : w0 * (S_axis(ix, Nx) - S_axis(rb.x, Nx));
+      } else if (want_values)
         row += (unsigned)q1_rowptr<D>(ix, iy, iz, Nx, Ny, Nz) - start32;
       double bsum = 0.;
 
@@ -770,7 +864,10 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
   // one kappa per element (3D Laplace): coefficients prefetched one item ahead (see the kernel)
   static const bool no_pref = std::getenv("GDTB_Q1_NO_PREFETCH") != nullptr;
   constexpr bool CAN_PREF = D == 3 && NG == 1 && KIND0 == Q1G_LAPLACE_SCALAR && CELLDATA;
-  const bool pref = CAN_PREF && with_values && p.group[0].coef_elem && !accumulate && !p.halo_p2p && !no_pref;
+  // (the PREF kernel takes its per-item bookkeeping from work-item records: needs the caller's buffer and lattice lines
+  // of at least one work item's rows)
+  const bool pref = CAN_PREF && with_values && p.group[0].coef_elem && !accumulate && !p.halo_p2p && !no_pref && p.items
+                    && g.n[0] + 1 >= Q1G_ROWS_PREF;
   const int rows_per_item = pref ? Q1G_ROWS_PREF : Q1G_ROWS;
   const long long nitems = (nrows + rows_per_item - 1) / rows_per_item;
   // two stage buffers (double-buffered bulk store), each padded for the 16-byte phase shift
@@ -804,6 +901,12 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
     grid = nitems;
   note_kernel(L, KF_Q1_GATHER, reinterpret_cast<const void*>(kern));
   time_begin(L, KF_Q1_GATHER);
+  if (pref && !p.items_ready) {
+    k_q1_items<<<(unsigned)((nitems + 127) / 128), 128, 0, L.stream>>>(p, nrows, (int)nitems, rows_per_item,
+                                                                       reinterpret_cast<int4*>(p.items));
+    L.count++;
+  }
+  const_cast<Q1GatherParams&>(p).items_ready = pref ? 1 : 0;
   kern<<<(unsigned)grid, rows_per_item, smem, L.stream>>>(p, values, rhs, nrows, (int)nitems, stage_doubles, nbuf);
   time_end(L, KF_Q1_GATHER);
   L.count++;
@@ -843,6 +946,14 @@ static int launch_q1_gather_d(Launch& L, const Q1GatherParams& p, double* values
     case 3: return launch_q1_gather_dn<D, 3, -1>(L, p, values, rhs, accumulate);
     default: return fail(GDTB_ERR_INVALID_ARGUMENT, "q1_gather: too many integrand groups");
   }
+}
+
+long long q1_pref_item_capacity(const GridDev& g, long long row_lo, long long row_hi)
+{
+  if (g.d != 3 || g.n[0] + 1 < Q1G_ROWS_PREF)
+    return 0;
+  const long long nrows = (row_hi - row_lo) * (g.n[0] + 1) * (g.n[1] + 1);
+  return nrows > 0 ? (nrows + Q1G_ROWS_PREF - 1) / Q1G_ROWS_PREF : 0;
 }
 
 int launch_q1_gather(Launch& L, const Q1GatherParams& p, double* values, double* rhs, bool accumulate)

@@ -1347,6 +1347,7 @@ int gdtb_matop_destroy(gdtb_matop* op)
   cudaFree(op->d_forms);
   cudaFree(op->d_q2_tab);
   cudaFree(op->d_q2_items);
+  cudaFree(op->d_q1_items);
   cudaFree(op->d_qp_scratch);
   cudaFree(op->d_own_rowptr);
   cudaFree(op->d_own_colidx);
@@ -2231,7 +2232,36 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       }
       op->halo_step++;
     }
+    // one kappa per element (3D, one Laplace integrand): the kernel variant with prefetched coefficients takes its
+    // per-item bookkeeping from records computed once per grid / slab and kept with the operator
+    bool q1_items = false;
+    if (op_fast && !accumulate && p.n_groups == 1 && p.group[0].coef_elem && p.group[0].kind == Q1G_LAPLACE_SCALAR
+        && !p.halo_p2p) {
+      const long long cap = q1_pref_item_capacity(p.g, p.row_lo, p.row_hi);
+      if (cap > 0) {
+        const size_t bytes = (size_t)cap * 32;
+        if (op->d_q1_items_bytes < bytes) {
+          cudaFree(op->d_q1_items);
+          op->d_q1_items = nullptr;
+          op->d_q1_items_bytes = 0;
+          op->q1_items_key[0] = -1;
+          if (cudaMalloc(&op->d_q1_items, bytes) != cudaSuccess)
+            return fail(GDTB_ERR_OUT_OF_MEMORY, "out of device memory (Q1 work-item records)");
+          op->d_q1_items_bytes = bytes;
+        }
+        p.items = op->d_q1_items;
+        p.items_ready = op->q1_items_key[0] == p.row_lo && op->q1_items_key[1] == p.row_hi
+                        && op->q1_items_key[2] == p.value_offset;
+        q1_items = true;
+      }
+    }
     GDTB_TRY(launch_q1_gather(L, p, op_fast ? op->d_values : nullptr, fun_fast ? fun->d_vec : nullptr, accumulate));
+    if (q1_items && p.items_ready) {
+      op->q1_items_key[0] = p.row_lo;
+      op->q1_items_key[1] = p.row_hi;
+      op->q1_items_key[2] = p.value_offset;
+    } else if (q1_items)
+      op->q1_items_key[0] = -1;
   }
 
   // --- CG-Q2 row-gather path ---------------------------------------------------------------
@@ -2246,6 +2276,7 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       if (op->d_q2_tab_bytes < bytes) {
         cudaFree(op->d_q2_tab);
   cudaFree(op->d_q2_items);
+  cudaFree(op->d_q1_items);
         op->d_q2_tab = nullptr;
         op->d_q2_tab_bytes = 0;
         if (cudaMalloc(&op->d_q2_tab, bytes) != cudaSuccess)
@@ -2276,6 +2307,7 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       const size_t bytes = (size_t)n_items * 32;
       if (op->d_q2_items_bytes < bytes) {
         cudaFree(op->d_q2_items);
+  cudaFree(op->d_q1_items);
         op->d_q2_items = nullptr;
         op->d_q2_items_bytes = 0;
         op->q2_items_key[2] = -1;

@@ -92,6 +92,9 @@ struct gdtb_matop
   std::vector<char> h_forms_cache; // what d_forms holds
   double* d_q2_tab = nullptr; // per-axis sum-factorisation tables of the CG Q2 gather path
   size_t d_q2_tab_bytes = 0;
+  void* d_q1_items = nullptr; // work-item records of k_q1_gather<..., PREF> (kernels.hpp, Q1GatherParams::items)
+  size_t d_q1_items_bytes = 0;
+  long long q1_items_key[3] = {-1, -1, -1}; // (row_lo, row_hi, value_offset) the records were computed for
   void* d_q2_items = nullptr; // work-item records of the CG Q2 gather kernels (kernels.hpp, Q2GatherParams::items)
   size_t d_q2_items_bytes = 0;
   long long q2_items_key[3] = {-1, -1, -1}; // (layer_lo, layer_hi, items) the records were computed for

@@ -179,6 +179,11 @@ struct Q1GatherParams
   long long elem_lo, elem_hi;
   int halo_p2p; // the interface-row halo travels inside the kernel (halo below)
   int no_sf3;   // A/B knob (GDTB_Q1_NO_SF3): constant kappa through the per-cell sum instead of the sum-factorised stencil
+  // work-item records of the kernel variant with one kappa per element (k_q1_items; 32 bytes per item of Q1G_ROWS_PREF
+  // rows, q1_pref_item_capacity() items): optional caller-owned device buffer; items_ready: it already holds the
+  // records of this grid / slab (set by the launcher when it wrote them)
+  void* items;
+  int items_ready;
   long long halo_top_value_start; // local position of the first value of the top (interface) layer
   Q1HaloP2p halo;
 };
@@ -190,6 +195,8 @@ int q1_halo_items(long long layer_rows, long long layers, bool top);
 int launch_q1_axis_tables(Launch& L, const GridDev& g, double* const* tabs, long long inv);
 
 // builds the separable right-hand-side tables B_k[i_k] for a product-separable built-in source
+// upper bound of the work items of k_q1_gather<..., PREF> for the rows [row_lo, row_hi) of the grid
+long long q1_pref_item_capacity(const GridDev& g, long long row_lo, long long row_hi);
 int launch_q1_rhs_tables(Launch& L, const GridDev& g, long long elem_lo, long long elem_hi, const FnDev& f, int m,
                          const double* qx, const double* qw, const double* phi /* [m][2] */, double* tab,
                          long long stride);

@@ -542,11 +542,23 @@ def test_slab_owner_computes_rows(gdt, ctx, oracle, n, cuts, constant_kappa):
     """every slab produces its owned rows completely and without communication; the concatenation of all slabs is
     the global matrix / vector (constant kappa: the sum-factorised row kernel of the headline configuration, which is
     what `bench.py --gpus N` runs on every rank)"""
+    kappa = rng_elem(n)
+    forms = [laplace(0.75)] if constant_kappa else [laplace(D.fn_elem(kappa)), mass(0.5)]
+    _slab_owner_computes_rows(gdt, ctx, oracle, n, cuts, forms)
+
+
+@pytest.mark.parametrize("n,cuts", [([223, 2, 3], [0, 3]), ([223, 2, 3], [0, 1, 3]), ([300, 3, 4], [0, 2, 3, 4]), ([257, 1, 2], [0, 2])])
+def test_q1_one_kappa_per_element_long_lines(gdt, ctx, oracle, n, cuts):
+    """ONE Laplace integrand with one kappa per element on lattice lines of at least 224 vertices: the kernel variant
+    with prefetched coefficients and work-item records (k_q1_items; items that end exactly at a line end, straddle a
+    line break or a layer break), whole grid and slabs, fused right-hand side"""
+    _slab_owner_computes_rows(gdt, ctx, oracle, n, cuts, [laplace(D.fn_elem(rng_elem(n, seed=3)))])
+
+
+def _slab_owner_computes_rows(gdt, ctx, oracle, n, cuts, forms):
     lib = gdt.capi.lib()
     check = gdt.capi.check
     gdesc = D.grid_desc(-1.0, 1.0, n)
-    kappa = rng_elem(n)
-    forms = [laplace(0.75)] if constant_kappa else [laplace(D.fn_elem(kappa)), mass(0.5)]
     src = D.fn_builtin(D.BUILTIN_COS_PRODUCT, 3, 2.0, 1.3)
     rp, ci = oracle.pattern(gdesc, (CG, 1))
     ref_v, ref_b = oracle.assemble(gdesc, CG, 1, rp, ci, forms, rhs_forms=[source(src), source(D.fn_const(0.25))])
