@@ -194,6 +194,15 @@ __global__ void __launch_bounds__(128) k_q1_items(const Q1GatherParams p, long l
   recs[2 * item + 1] = b;
 }
 
+// per-pair factorised arithmetic of the one-kappa-per-cell Laplace rows (see the kernel); 0: cell-by-cell sum (A/B)
+#ifndef Q1G_PF3
+#define Q1G_PF3 1
+#endif
+// the eight coefficients of a vertex through cp.async slots requested one item ahead (1) or plain loads (0, default: the
+// slot machinery costs more issue slots and registers than the latency it hides once the arithmetic is pair-factorised)
+#ifndef Q1G_PE_SLOTS
+#define Q1G_PE_SLOTS 0
+#endif
 constexpr int Q1G_ROWS = 256; // rows (vertices) per work item = threads per CTA
 #ifndef Q1G_ROWS_PREF
 #define Q1G_ROWS_PREF 224 // the same with the coefficient prefetch slots (k_q1_gather<..., PREF>)
@@ -420,7 +429,8 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
       nra = q1_ldg_int4_here(recs + 2 * blockIdx.x);
       nrb = q1_ldg_int4_here(recs + 2 * blockIdx.x + 1);
     }
-    prefetch_coef(nrb, nra.w & 511);
+    if (Q1G_PE_SLOTS)
+      prefetch_coef(nrb, nra.w & 511);
     prefetch_lines_l2(blockIdx.x + (int)gridDim.x);
     prefetch_lines_l2(blockIdx.x + 2 * (int)gridDim.x);
   }
@@ -481,15 +491,16 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
 
     // ---- per vertex --------------------------------------------------------------------------------------
     double c8[8];
-    if (PREF) {
+    if (PREF && Q1G_PE_SLOTS) {
       // this item's coefficients arrived while the previous item was computed; the next item's are requested now
       asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
       for (int o = 0; o < 8; ++o)
         c8[o] = slots[o * ROWS + threadIdx.x];
       prefetch_coef(nrb, nra.w & 511);
-      prefetch_lines_l2(it + 3 * (int)gridDim.x);
     }
+    if (PREF)
+      prefetch_lines_l2(it + 3 * (int)gridDim.x);
     if ((int)threadIdx.x < nr) {
       int ix, iy, iz;
       bool second_line = false;
@@ -570,7 +581,8 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
         // M^k[d] = sum_cells M1[.][.] h_k (1D tables of the form's rule; the vertex is node 1 of the lower and node 0 of
         // the upper cell) and the stencil is c (K^x M^y M^z + M^x K^y M^z + M^x M^y K^z): 3 FP64 instructions per entry
         // instead of 8.  Cells outside the grid / slab carry h = 1/h = 0 and drop out.
-        const bool sf3 = LAP3 && want_values && !(CELLDATA && p.group[0].coef_elem) && !p.no_sf3;
+        // (the PREF instantiation is only launched with one kappa per element: no sum-factorised stencil in it)
+        const bool sf3 = !PREF && LAP3 && want_values && !(CELLDATA && p.group[0].coef_elem) && !p.no_sf3;
         if (sf3) {
           const Q1Group& G = p.group[0];
           double Kv[3][3], Mv[3][3];
@@ -600,10 +612,62 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
             row += q1_store_plane<9>(row, Pl, full_xy, cx0, cx1, cy0, cy1);
           }
         }
+        // One Laplace integrand, kappa per cell (or constant with the sum-factorised stencil switched off): every cell's
+        // row is kappa_e sum_r prod_k T^(r,k) with the 1D factors KK[k][o][s] = K1[1 - o][s] / h_k(o), MM[k][o][s] =
+        // M1[1 - o][s] h_k(o) (s = local column, stencil offset o + s), so the two cells of an x-pair are combined first,
+        //   PX[b] = sum_ox kappa KKx[ox][b - ox],  QX[b] = sum_ox kappa MMx[ox][b - ox],
+        // and a (cell-pair, s_y, s_z) block is (MMy MMz) PX + (KKy MMz + MMy KKz) QX: 44 FP64 instructions per pair with
+        // register operands instead of 60 + 48 constant-bank loads per pair of the cell-by-cell sum (q1_add_element_lap3)
+        const bool pf3 = Q1G_PF3 && PREF && LAP3 && want_values && !sf3;
+        double KKy[2][2], MMy[2][2], KKz[2][2], MMz[2][2], KKx[2][2], MMx[2][2];
+        if (pf3) {
+          const Q1Group& G = p.group[0];
+#pragma unroll
+          for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              KKx[o][q] = fx_b[o] * G.K1[1 - o][q];
+              MMx[o][q] = fx_a[o] * G.M1[1 - o][q];
+              KKy[o][q] = hb[1][o] * G.K1[1 - o][q];
+              MMy[o][q] = ha[1][o] * G.M1[1 - o][q];
+              KKz[o][q] = hb[2][o] * G.K1[1 - o][q];
+              MMz[o][q] = ha[2][o] * G.M1[1 - o][q];
+            }
+        }
 #pragma unroll
         for (int oz = 0; oz < 2; ++oz) {
           if (sf3 && (!CELLDATA || (!p.rhs_has_const && !p.rhs_has_elem)))
             break;
+          if (pf3) {
+#pragma unroll
+            for (int oy = 0; oy < 2; ++oy) {
+              double k0 = 1., k1 = 1.;
+              if (CELLDATA && p.group[0].coef_elem) {
+                if (PREF && Q1G_PE_SLOTS) {
+                  k0 = c8[2 * oy + 4 * oz];
+                  k1 = c8[1 + 2 * oy + 4 * oz];
+                } else {
+                  const long long e = e0 + (long long)Nx * (oy + (long long)Ny * oz);
+                  const bool vyz = vk[1][oy] && vk[2][oz];
+                  k0 = vyz && vk[0][0] ? __ldg(p.group[0].coef + e) : 0.;
+                  k1 = vyz && vk[0][1] ? __ldg(p.group[0].coef + e + 1) : 0.;
+                }
+              }
+              const double PX[3] = {k0 * KKx[0][0], fma(k0, KKx[0][1], k1 * KKx[1][0]), k1 * KKx[1][1]};
+              const double QX[3] = {k0 * MMx[0][0], fma(k0, MMx[0][1], k1 * MMx[1][0]), k1 * MMx[1][1]};
+#pragma unroll
+              for (int sz = 0; sz < 2; ++sz)
+#pragma unroll
+                for (int sy = 0; sy < 2; ++sy) {
+                  const double cA = MMy[oy][sy] * MMz[oz][sz];
+                  const double cB = fma(KKy[oy][sy], MMz[oz][sz], MMy[oy][sy] * KKz[oz][sz]);
+                  double* Pp = P[oz + sz] + 3 * (oy + sy);
+#pragma unroll
+                  for (int bb = 0; bb < 3; ++bb)
+                    Pp[bb] = fma(cA, PX[bb], fma(cB, QX[bb], Pp[bb]));
+                }
+            }
+          }
 #pragma unroll
           for (int oxy = 0; oxy < 4; ++oxy) {
             const int ox = oxy & 1, oy = oxy >> 1;
@@ -611,14 +675,14 @@ __global__ void __launch_bounds__(ROWS, (D == 3 && NG == 1 && KIND0 == Q1G_LAPLA
             const double b[3] = {hb[0][ox], hb[1][oy], hb[2][oz]};
             const bool valid = vk[0][ox] && vk[1][oy] && vk[2][oz];
             const long long e = CELLDATA ? e0 + ox + (long long)Nx * (oy + (long long)Ny * oz) : 0;
-            if (want_values && !sf3) {
+            if (want_values && !sf3 && !pf3) {
               if (LAP3) {
                 // scheduling fence: keeps the weights of the 8 cells from being formed all at once (register pressure)
                 double t0 = yz_aa[oy][oz];
                 asm volatile("" : "+d"(t0));
                 double w[3] = {fx_b[ox] * t0, fx_a[ox] * yz_ba[oy][oz], fx_a[ox] * yz_ab[oy][oz]};
                 if (CELLDATA && p.group[0].coef_elem) {
-                  const double c = PREF ? c8[ox + 2 * oy + 4 * oz] : (valid ? __ldg(p.group[0].coef + e) : 0.);
+                  const double c = PREF && Q1G_PE_SLOTS ? c8[ox + 2 * oy + 4 * oz] : (valid ? __ldg(p.group[0].coef + e) : 0.);
                   w[0] *= c;
                   w[1] *= c;
                   w[2] *= c;
@@ -875,7 +939,7 @@ static int launch_q1_gather_dnc(Launch& L, const Q1GatherParams& p, double* valu
   static const int nbuf_env = std::getenv("GDTB_Q1_NBUF") ? std::atoi(std::getenv("GDTB_Q1_NBUF")) : 0;
   const int nbuf = accumulate ? 1 : (nbuf_env == 1 || nbuf_env == 2 ? nbuf_env : Q1G_DEFAULT_NBUF);
   const size_t smem =
-      with_values ? ((size_t)nbuf * stage_doubles + (pref ? 8 * Q1G_ROWS_PREF : 0)) * sizeof(double) : 16;
+      with_values ? ((size_t)nbuf * stage_doubles + (pref && Q1G_PE_SLOTS ? 8 * Q1G_ROWS_PREF : 0)) * sizeof(double) : 16;
   auto kern = accumulate ? k_q1_gather<D, NG, KIND0, true, CELLDATA, false>
                          : (p.halo_p2p ? k_q1_gather<D, NG, KIND0, false, CELLDATA, true>
                                        : k_q1_gather<D, NG, KIND0, false, CELLDATA, false>);
