@@ -390,6 +390,26 @@ def assembly_extra(gdt, ctx, torch, hbm_gbs, peak_src):
     check(lib.gdtb_matop_append_boundary(op._h, C.byref(bnd), D.FILTER_ALL_BOUNDARY))
     per = timed(op._h, "dg_gather", 20)
     entry("c3_swipdg_dg_q1_2048^2", n * n, pat.rows, pat.nnz, per, op.plan, "dg_gather")
+    # the same operator with kappa = omega = one value per element (SWIPDG's weight is the diffusion)
+    kap3 = torch.rand(n * n, dtype=torch.float64, device="cuda") + 0.5
+
+    def fe3():
+        f = D.Function()
+        f.kind, f.data_on_device, f.data = D.FN_ELEM_SCALAR, 1, C.cast(kap3.data_ptr(), C.POINTER(C.c_double))
+        return f
+
+    op2 = gdt.MatrixOperator(space, space, pat)
+    lap_e = D.form(D.integrand(D.INT_LAPLACE, diffusion=fe3()))
+    inner_e = D.form([D.integrand(D.INT_IPDG_INNER_COUPLING, prefactor=1.0, diffusion=fe3(), weight=fe3()),
+                      D.integrand(D.INT_IPDG_INNER_PENALTY, prefactor=8.0, weight=fe3(), hI_kind=D.HI_VOLUME)])
+    bnd_e = D.form([D.integrand(D.INT_IPDG_DIRICHLET_COUPLING, prefactor=1.0, diffusion=fe3()),
+                    D.integrand(D.INT_IPDG_BOUNDARY_PENALTY, prefactor=14.0, weight=fe3(), hI_kind=D.HI_VOLUME)])
+    check(lib.gdtb_matop_append_element(op2._h, C.byref(lap_e)))
+    check(lib.gdtb_matop_append_coupling(op2._h, C.byref(inner_e), D.FILTER_INNER_ONCE))
+    check(lib.gdtb_matop_append_boundary(op2._h, C.byref(bnd_e), D.FILTER_ALL_BOUNDARY))
+    per = timed(op2._h, "dg_gather", 10)
+    entry("c3_swipdg_dg_q1_2048^2_kappa_per_element", n * n, pat.rows, pat.nnz, per, op2.plan, "dg_gather", read_bytes=8.0 * n * n)
+    del op2, kap3
     del op, pat, space, grid
     torch.cuda.empty_cache()
 

@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(DGG_THREADS)
 {
   constexpr int N = 1 << D;
   const int n_elem = ONE ? 1 : p.n_elem, n_coup = ONE ? 1 : p.n_coup, n_bnd = ONE ? 1 : p.n_bnd;
+  // element-wise coefficients + the SWIPDG form structure (DgGatherParams::swip): term counts and kinds are compile time
+  constexpr bool SW = ONE && !CC;
   extern __shared__ __align__(16) double smem[];
   __shared__ DgFastTab tabs[DGG_MAX_FORMS];
   const GridDev& g = p.g;
@@ -272,11 +274,11 @@ __global__ void __launch_bounds__(DGG_THREADS)
           tK[o][1] = hinv[o] * T.K1[io][1];
         }
         // CC: the terms of a form share its tables, their constant coefficients are summed up front (two passes)
-        for (int tt = 0; tt < (CC ? 2 : F.n_terms); ++tt) {
+        for (int tt = 0; tt < (CC ? 2 : (SW ? 1 : F.n_terms)); ++tt) {
           const double c = CC ? (tt == 0 ? T.elap : T.emass) : F.scaling * dg_coef(F.terms[tt].diffusion, e);
           if (CC && c == 0.)
             continue;
-          if (CC ? tt == 0 : F.terms[tt].kind == GDTB_INT_LAPLACE) {
+          if (CC ? tt == 0 : (SW || F.terms[tt].kind == GDTB_INT_LAPLACE)) {
 #pragma unroll
             for (int j = 0; j < N; ++j) {
               double sum = 0.;
@@ -385,12 +387,15 @@ __global__ void __launch_bounds__(DGG_THREADS)
               const double vi = s ? T.pe[1][ik] : T.pe[0][ik];
               const double gi = s ? T.de[1][ik] * hinv_in : T.de[0][ik] * hinv_out;
               double ca[2] = {0., 0.}, cb[2] = {0., 0.}; // columns of the inside / outside element
-              for (int tt = 0; tt < F.n_terms; ++tt) {
+#pragma unroll
+              for (int tt = 0; tt < (SW ? 2 : F.n_terms); ++tt) {
                 const IntegrandDev& in = F.terms[tt];
                 const double delta_plus = dg_coef(in.weight, e_out), delta_minus = dg_coef(in.weight, e_in);
-                if (in.kind == GDTB_INT_IPDG_INNER_COUPLING) {
+                if (SW ? tt == 0 : in.kind == GDTB_INT_IPDG_INNER_COUPLING) {
                   const double k_in = dg_coef(in.diffusion, e_in), k_out = dg_coef(in.diffusion, e_out);
-                  const double wm = delta_plus / (delta_plus + delta_minus), wp = delta_minus / (delta_plus + delta_minus);
+                  // one reciprocal instead of two FP64 divisions (each ~30 instructions; agrees to an ulp)
+                  const double rsum = __drcp_rn(delta_plus + delta_minus);
+                  const double wm = delta_plus * rsum, wp = delta_minus * rsum;
                   const double sp_ = in.prefactor;
                   const double fi = s ? k_in * gi : k_out * gi; // (kappa grad psi_i) . n on the test function's side
 #pragma unroll
@@ -410,8 +415,8 @@ __global__ void __launch_bounds__(DGG_THREADS)
                     }
                   }
                 } else { // GDTB_INT_IPDG_INNER_PENALTY, ipdg.hh:149-170
-                  const double weight = (delta_plus * delta_minus) / (delta_plus + delta_minus);
-                  const double penalty = (in.prefactor * weight) / dg_face_h<D>(in, h, k, h_in, h_out, true);
+                  const double weight = (delta_plus * delta_minus) * __drcp_rn(delta_plus + delta_minus);
+                  const double penalty = (in.prefactor * weight) * __drcp_rn(dg_face_h<D>(in, h, k, h_in, h_out, true));
 #pragma unroll
                   for (int jk = 0; jk < 2; ++jk) {
                     const double vj_in = T.pe[1][jk], vj_out = T.pe[0][jk];
@@ -458,9 +463,10 @@ __global__ void __launch_bounds__(DGG_THREADS)
               }
               const double vi = T.pe[s][ik], gi = sg * (T.de[s][ik] * hinv[k]);
               double ca[2] = {0., 0.};
-              for (int tt = 0; tt < F.n_terms; ++tt) {
+#pragma unroll
+              for (int tt = 0; tt < (SW ? 2 : F.n_terms); ++tt) {
                 const IntegrandDev& in = F.terms[tt];
-                if (in.kind == GDTB_INT_IPDG_DIRICHLET_COUPLING) { // laplace-ipdg.hh:362-367
+                if (SW ? tt == 0 : in.kind == GDTB_INT_IPDG_DIRICHLET_COUPLING) { // laplace-ipdg.hh:362-367
                   const double kap = dg_coef(in.diffusion, e);
                   const double fi = kap * gi;
 #pragma unroll
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(DGG_THREADS)
                     ca[jk] += -1.0 * in.prefactor * vj * fi;
                   }
                 } else { // GDTB_INT_IPDG_BOUNDARY_PENALTY, ipdg.hh:276-281
-                  const double penalty = (in.prefactor * dg_coef(in.weight, e)) / dg_face_h<D>(in, h, k, h[k], h[k], false);
+                  const double penalty = (in.prefactor * dg_coef(in.weight, e)) * __drcp_rn(dg_face_h<D>(in, h, k, h[k], h[k], false));
 #pragma unroll
                   for (int jk = 0; jk < 2; ++jk)
                     ca[jk] += penalty * T.pe[s][jk] * vi;
@@ -526,7 +532,7 @@ int launch_dg_gather_fast(Launch& L, DgGatherParams& p, double* values, bool acc
   const bool one = p.n_elem == 1 && p.n_coup == 1 && p.n_bnd == 1;
   auto kern = accumulate ? (cc ? k_dg_gather_fast<D, true, true, false> : k_dg_gather_fast<D, true, false, false>)
                          : (cc ? (one ? k_dg_gather_fast<D, false, true, true> : k_dg_gather_fast<D, false, true, false>)
-                               : k_dg_gather_fast<D, false, false, false>);
+                               : (one && p.swip ? k_dg_gather_fast<D, false, false, true> : k_dg_gather_fast<D, false, false, false>));
   if (p.g.periodic)
     kern = accumulate ? (cc ? k_dg_gather_fast<D, true, true, false, true> : k_dg_gather_fast<D, true, false, false, true>)
                       : (cc ? k_dg_gather_fast<D, false, true, false, true> : k_dg_gather_fast<D, false, false, false, true>);

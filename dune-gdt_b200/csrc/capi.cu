@@ -2388,6 +2388,11 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       for (int t = 0; t < f.n_terms; ++t)
         all_const = all_const && f.terms[t].diffusion.kind == GDTB_FN_CONST_SCALAR && f.terms[t].weight.kind == GDTB_FN_CONST_SCALAR;
     p.fast = fast ? ((all_const && !std::getenv("GDTB_DG_NO_CC")) ? 2 : 1) : 0;
+    p.swip = forms.size() == 3 && p.n_elem == 1 && p.n_coup == 1 && p.n_bnd == 1 && forms[0].n_terms == 1
+             && forms[0].terms[0].kind == GDTB_INT_LAPLACE && forms[1].n_terms == 2
+             && forms[1].terms[0].kind == GDTB_INT_IPDG_INNER_COUPLING && forms[1].terms[1].kind == GDTB_INT_IPDG_INNER_PENALTY
+             && forms[2].n_terms == 2 && forms[2].terms[0].kind == GDTB_INT_IPDG_DIRICHLET_COUPLING
+             && forms[2].terms[1].kind == GDTB_INT_IPDG_BOUNDARY_PENALTY;
     if (p.fast)
       GDTB_TRY(q1_axis_tables(op->ctx, op->grid, p.axis_tab, p.axis_tab_inv));
     if (!p.fast) { // the quadrature-faithful kernel reads the row pointer (materialised for a pattern-free operator)

@@ -341,6 +341,10 @@ struct DgGatherParams
   // factorised path (order 1, every coefficient a constant or element-wise scalar): the quadrature sums of all forms
   // collapse into 1D tables; row starts are closed forms (rowptr is not read)
   int fast; // 0: quadrature-faithful kernel, 1: factorised, 2: factorised with constant coefficients tabulated
+  // the operator is exactly the reference drivers' SWIPDG one: one element form {Laplace}, one coupling form {inner
+  // coupling, inner penalty}, one boundary form {Dirichlet coupling, boundary penalty} -- lets the factorised kernel with
+  // element-wise coefficients run with compile-time term loops
+  int swip;
   unsigned long long magic[2]; // floor(2^64 / n_k) + 1 for the element-index decode (0 when n_k == 1)
   // element-owned rows: this process produces the rows of the elements [e_begin, e_end) (a slab of element layers),
   // `values` starts at the global CSR position value_offset

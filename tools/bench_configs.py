@@ -144,6 +144,26 @@ def main():
                       D.integrand(D.INT_IPDG_BOUNDARY_PENALTY, prefactor=14.0, weight=1.0, hI_kind=D.HI_VOLUME)])
         run(f"C3 2D SWIPDG DG-Q1 {n}^2", D.grid_desc(-1.0, 1.0, [n, n]), D.SPACE_DG, 1,
             D.STENCIL_ELEMENT_AND_INTERSECTION, element=[lap], coupling=[inner], boundary=[bnd], reps=5)
+    if "c3-elem" in which:
+        n = n_override or 2048
+        g_ = torch.Generator(device="cuda").manual_seed(9)
+        kap = 0.5 + torch.rand(n * n, dtype=torch.float64, device="cuda", generator=g_)
+
+        def fe():
+            f = D.Function()
+            f.kind = D.FN_ELEM_SCALAR
+            f.data_on_device = 1
+            f.data = C.cast(kap.data_ptr(), C.POINTER(C.c_double))
+            f._keep = kap
+            return f
+
+        lap_e = D.form(D.integrand(D.INT_LAPLACE, diffusion=fe()))
+        inner = D.form([D.integrand(D.INT_IPDG_INNER_COUPLING, prefactor=1.0, diffusion=fe(), weight=fe()),
+                        D.integrand(D.INT_IPDG_INNER_PENALTY, prefactor=8.0, weight=fe(), hI_kind=D.HI_VOLUME)])
+        bnd = D.form([D.integrand(D.INT_IPDG_DIRICHLET_COUPLING, prefactor=1.0, diffusion=fe()),
+                      D.integrand(D.INT_IPDG_BOUNDARY_PENALTY, prefactor=14.0, weight=fe(), hI_kind=D.HI_VOLUME)])
+        run(f"C3 2D SWIPDG DG-Q1 {n}^2, kappa = omega = one value per element", D.grid_desc(-1.0, 1.0, [n, n]), D.SPACE_DG, 1,
+            D.STENCIL_ELEMENT_AND_INTERSECTION, element=[lap_e], coupling=[inner], boundary=[bnd], reps=5)
     if "c5" in which:
         n = n_override or 128
         run(f"C5 3D Q2 {n}^3", D.grid_desc(-1.0, 1.0, [n, n, n]), D.SPACE_CG, 2, D.STENCIL_ELEMENT, element=[lap], reps=2)
