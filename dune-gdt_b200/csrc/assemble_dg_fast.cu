@@ -90,7 +90,7 @@ __device__ inline void dg_fast_tables_cc(const FormDev& F, int role, DgFastTab& 
 
 // intersection_h of local_forms.cuh for axis-aligned faces: |I|, or the face diameter (1D: element lengths)
 template <int D>
-__device__ __forceinline__ double dg_face_h(const IntegrandDev& t, const double* h, int k, double h_in, double h_out,
+__device__ __forceinline__ double dg_face_h(const int hI_kind, const double* h, int k, double h_in, double h_out,
                                             bool neighbor)
 {
   double ie = 1., d2 = 0.;
@@ -100,11 +100,17 @@ __device__ __forceinline__ double dg_face_h(const IntegrandDev& t, const double*
       ie *= h[o];
       d2 += h[o] * h[o];
     }
-  if (t.hI_kind == GDTB_HI_VOLUME)
+  if (hI_kind == GDTB_HI_VOLUME)
     return ie;
   if (D == 1)
     return neighbor ? 0.5 * (h_in + h_out) : h_in;
   return sqrt(d2);
+}
+
+// coefficient of the SWIPDG descriptor (constant bank) or of the general form array
+__device__ __forceinline__ double dg_sw(const DgGatherParams::SwFn& f, long long e)
+{
+  return f.data ? __ldg(f.data + e) : f.c;
 }
 
 // 1 / intersection_h for the CC tables: 1 / |I| (volume) or 1 / diameter (1D: element lengths) from the cell data
@@ -275,7 +281,8 @@ __global__ void __launch_bounds__(DGG_THREADS)
         }
         // CC: the terms of a form share its tables, their constant coefficients are summed up front (two passes)
         for (int tt = 0; tt < (CC ? 2 : (SW ? 1 : F.n_terms)); ++tt) {
-          const double c = CC ? (tt == 0 ? T.elap : T.emass) : F.scaling * dg_coef(F.terms[tt].diffusion, e);
+          const double c = CC ? (tt == 0 ? T.elap : T.emass)
+                              : (SW ? p.sw.s_elem * dg_sw(p.sw.elem_kappa, e) : F.scaling * dg_coef(F.terms[tt].diffusion, e));
           if (CC && c == 0.)
             continue;
           if (CC ? tt == 0 : (SW || F.terms[tt].kind == GDTB_INT_LAPLACE)) {
@@ -390,13 +397,16 @@ __global__ void __launch_bounds__(DGG_THREADS)
 #pragma unroll
               for (int tt = 0; tt < (SW ? 2 : F.n_terms); ++tt) {
                 const IntegrandDev& in = F.terms[tt];
-                const double delta_plus = dg_coef(in.weight, e_out), delta_minus = dg_coef(in.weight, e_in);
+                const DgGatherParams::SwFn& wfn = tt == 0 ? p.sw.coup_weight : p.sw.pen_weight;
+                const double delta_plus = SW ? dg_sw(wfn, e_out) : dg_coef(in.weight, e_out);
+                const double delta_minus = SW ? dg_sw(wfn, e_in) : dg_coef(in.weight, e_in);
                 if (SW ? tt == 0 : in.kind == GDTB_INT_IPDG_INNER_COUPLING) {
-                  const double k_in = dg_coef(in.diffusion, e_in), k_out = dg_coef(in.diffusion, e_out);
+                  const double k_in = SW ? dg_sw(p.sw.coup_kappa, e_in) : dg_coef(in.diffusion, e_in);
+                  const double k_out = SW ? dg_sw(p.sw.coup_kappa, e_out) : dg_coef(in.diffusion, e_out);
                   // one reciprocal instead of two FP64 divisions (each ~30 instructions; agrees to an ulp)
                   const double rsum = __drcp_rn(delta_plus + delta_minus);
                   const double wm = delta_plus * rsum, wp = delta_minus * rsum;
-                  const double sp_ = in.prefactor;
+                  const double sp_ = SW ? p.sw.coup_prefactor : in.prefactor;
                   const double fi = s ? k_in * gi : k_out * gi; // (kappa grad psi_i) . n on the test function's side
 #pragma unroll
                   for (int jk = 0; jk < 2; ++jk) {
@@ -416,7 +426,8 @@ __global__ void __launch_bounds__(DGG_THREADS)
                   }
                 } else { // GDTB_INT_IPDG_INNER_PENALTY, ipdg.hh:149-170
                   const double weight = (delta_plus * delta_minus) * __drcp_rn(delta_plus + delta_minus);
-                  const double penalty = (in.prefactor * weight) * __drcp_rn(dg_face_h<D>(in, h, k, h_in, h_out, true));
+                  const double penalty = ((SW ? p.sw.pen_prefactor : in.prefactor) * weight)
+                                         * __drcp_rn(dg_face_h<D>(SW ? p.sw.pen_hI : in.hI_kind, h, k, h_in, h_out, true));
 #pragma unroll
                   for (int jk = 0; jk < 2; ++jk) {
                     const double vj_in = T.pe[1][jk], vj_out = T.pe[0][jk];
@@ -431,8 +442,9 @@ __global__ void __launch_bounds__(DGG_THREADS)
                 }
               }
               // own columns: inside element -> ca, outside element -> cb
-              dg_add_face_block<D>(self, F.scaling, s ? ca : cb, k, tM);
-              dg_add_face_block<D>(nbb, F.scaling, s ? cb : ca, k, tM);
+              const double sc_coup = SW ? p.sw.s_coup : F.scaling;
+              dg_add_face_block<D>(self, sc_coup, s ? ca : cb, k, tM);
+              dg_add_face_block<D>(nbb, sc_coup, s ? cb : ca, k, tM);
             }
             double* blk = row + (s ? pos_hi[k] : pos_lo[k]);
             dg_store_block<N>(blk, nbb, phase == 0);
@@ -467,22 +479,23 @@ __global__ void __launch_bounds__(DGG_THREADS)
               for (int tt = 0; tt < (SW ? 2 : F.n_terms); ++tt) {
                 const IntegrandDev& in = F.terms[tt];
                 if (SW ? tt == 0 : in.kind == GDTB_INT_IPDG_DIRICHLET_COUPLING) { // laplace-ipdg.hh:362-367
-                  const double kap = dg_coef(in.diffusion, e);
+                  const double kap = SW ? dg_sw(p.sw.bnd_kappa, e) : dg_coef(in.diffusion, e);
                   const double fi = kap * gi;
 #pragma unroll
                   for (int jk = 0; jk < 2; ++jk) {
                     const double vj = T.pe[s][jk], fj = kap * (sg * (T.de[s][jk] * hinv[k]));
                     ca[jk] += -1.0 * fj * vi;
-                    ca[jk] += -1.0 * in.prefactor * vj * fi;
+                    ca[jk] += -1.0 * (SW ? p.sw.bnd_prefactor : in.prefactor) * vj * fi;
                   }
                 } else { // GDTB_INT_IPDG_BOUNDARY_PENALTY, ipdg.hh:276-281
-                  const double penalty = (in.prefactor * dg_coef(in.weight, e)) * __drcp_rn(dg_face_h<D>(in, h, k, h[k], h[k], false));
+                  const double penalty = ((SW ? p.sw.bndpen_prefactor : in.prefactor) * (SW ? dg_sw(p.sw.bnd_weight, e) : dg_coef(in.weight, e)))
+                                         * __drcp_rn(dg_face_h<D>(SW ? p.sw.bndpen_hI : in.hI_kind, h, k, h[k], h[k], false));
 #pragma unroll
                   for (int jk = 0; jk < 2; ++jk)
                     ca[jk] += penalty * T.pe[s][jk] * vi;
                 }
               }
-              dg_add_face_block<D>(self, F.scaling, ca, k, tM);
+              dg_add_face_block<D>(self, SW ? p.sw.s_bnd : F.scaling, ca, k, tM);
             }
           }
         }

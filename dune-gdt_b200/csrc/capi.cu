@@ -2393,6 +2393,29 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
              && forms[1].terms[0].kind == GDTB_INT_IPDG_INNER_COUPLING && forms[1].terms[1].kind == GDTB_INT_IPDG_INNER_PENALTY
              && forms[2].n_terms == 2 && forms[2].terms[0].kind == GDTB_INT_IPDG_DIRICHLET_COUPLING
              && forms[2].terms[1].kind == GDTB_INT_IPDG_BOUNDARY_PENALTY;
+    if (p.swip && p.fast == 1) {
+      const auto sw_fn = [](const FnDev& f) {
+        DgGatherParams::SwFn r;
+        r.data = f.kind == GDTB_FN_ELEM_SCALAR ? f.data : nullptr;
+        r.c = f.c[0];
+        return r;
+      };
+      p.sw.elem_kappa = sw_fn(forms[0].terms[0].diffusion);
+      p.sw.coup_kappa = sw_fn(forms[1].terms[0].diffusion);
+      p.sw.coup_weight = sw_fn(forms[1].terms[0].weight);
+      p.sw.pen_weight = sw_fn(forms[1].terms[1].weight);
+      p.sw.bnd_kappa = sw_fn(forms[2].terms[0].diffusion);
+      p.sw.bnd_weight = sw_fn(forms[2].terms[1].weight);
+      p.sw.coup_prefactor = forms[1].terms[0].prefactor;
+      p.sw.pen_prefactor = forms[1].terms[1].prefactor;
+      p.sw.bnd_prefactor = forms[2].terms[0].prefactor;
+      p.sw.bndpen_prefactor = forms[2].terms[1].prefactor;
+      p.sw.s_elem = forms[0].scaling;
+      p.sw.s_coup = forms[1].scaling;
+      p.sw.s_bnd = forms[2].scaling;
+      p.sw.pen_hI = forms[1].terms[1].hI_kind;
+      p.sw.bndpen_hI = forms[2].terms[1].hI_kind;
+    }
     if (p.fast)
       GDTB_TRY(q1_axis_tables(op->ctx, op->grid, p.axis_tab, p.axis_tab_inv));
     if (!p.fast) { // the quadrature-faithful kernel reads the row pointer (materialised for a pattern-free operator)

@@ -345,6 +345,20 @@ struct DgGatherParams
   // coupling, inner penalty}, one boundary form {Dirichlet coupling, boundary penalty} -- lets the factorised kernel with
   // element-wise coefficients run with compile-time term loops
   int swip;
+  // ... and then carries that operator's coefficients and scalars here (constant bank) instead of in the FormDev array in
+  // global memory, which the general kernel re-reads for every face and term
+  struct SwFn
+  {
+    const double* data; // element-wise scalar array, or nullptr: the constant c
+    double c;
+  };
+  struct SwDesc
+  {
+    SwFn elem_kappa, coup_kappa, coup_weight, pen_weight, bnd_kappa, bnd_weight;
+    double coup_prefactor, pen_prefactor, bnd_prefactor, bndpen_prefactor;
+    double s_elem, s_coup, s_bnd; // the forms' scalings
+    int pen_hI, bndpen_hI;
+  } sw;
   unsigned long long magic[2]; // floor(2^64 / n_k) + 1 for the element-index decode (0 when n_k == 1)
   // element-owned rows: this process produces the rows of the elements [e_begin, e_end) (a slab of element layers),
   // `values` starts at the global CSR position value_offset
