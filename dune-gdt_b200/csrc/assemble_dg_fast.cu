@@ -120,15 +120,19 @@ __device__ __forceinline__ double dg_inv_face(const double* h, const double* hin
 {
   if (D == 1)
     return volume ? 1. : (neighbor ? 1. / (0.5 * (h_in + h_out)) : 1. / h_in);
-  double inv = 1., d2 = 0.;
+  if (volume || D == 2) { // 2D: the face is an interval, diameter == |I|
+    double inv = 1.;
+#pragma unroll
+    for (int o = 0; o < D; ++o)
+      if (o != k)
+        inv *= hinv[o];
+    return inv;
+  }
+  double d2 = 0.;
 #pragma unroll
   for (int o = 0; o < D; ++o)
-    if (o != k) {
-      inv *= hinv[o];
+    if (o != k)
       d2 += h[o] * h[o];
-    }
-  if (volume || D == 2)
-    return inv; // 2D: the face is an interval, diameter == |I|
   return 1. / sqrt(d2);
 }
 
@@ -394,15 +398,21 @@ __global__ void __launch_bounds__(DGG_THREADS)
               const double vi = s ? T.pe[1][ik] : T.pe[0][ik];
               const double gi = s ? T.de[1][ik] * hinv_in : T.de[0][ik] * hinv_out;
               double ca[2] = {0., 0.}, cb[2] = {0., 0.}; // columns of the inside / outside element
+              // SWIPDG with kappa = omega from one array (the usual case): one load per cell of the face
+              double sw_in = 0., sw_out = 0.;
+              if (SW && p.sw.coup_same) {
+                sw_in = dg_sw(p.sw.coup_kappa, e_in);
+                sw_out = dg_sw(p.sw.coup_kappa, e_out);
+              }
 #pragma unroll
               for (int tt = 0; tt < (SW ? 2 : F.n_terms); ++tt) {
                 const IntegrandDev& in = F.terms[tt];
                 const DgGatherParams::SwFn& wfn = tt == 0 ? p.sw.coup_weight : p.sw.pen_weight;
-                const double delta_plus = SW ? dg_sw(wfn, e_out) : dg_coef(in.weight, e_out);
-                const double delta_minus = SW ? dg_sw(wfn, e_in) : dg_coef(in.weight, e_in);
+                const double delta_plus = SW ? (p.sw.coup_same ? sw_out : dg_sw(wfn, e_out)) : dg_coef(in.weight, e_out);
+                const double delta_minus = SW ? (p.sw.coup_same ? sw_in : dg_sw(wfn, e_in)) : dg_coef(in.weight, e_in);
                 if (SW ? tt == 0 : in.kind == GDTB_INT_IPDG_INNER_COUPLING) {
-                  const double k_in = SW ? dg_sw(p.sw.coup_kappa, e_in) : dg_coef(in.diffusion, e_in);
-                  const double k_out = SW ? dg_sw(p.sw.coup_kappa, e_out) : dg_coef(in.diffusion, e_out);
+                  const double k_in = SW ? (p.sw.coup_same ? sw_in : dg_sw(p.sw.coup_kappa, e_in)) : dg_coef(in.diffusion, e_in);
+                  const double k_out = SW ? (p.sw.coup_same ? sw_out : dg_sw(p.sw.coup_kappa, e_out)) : dg_coef(in.diffusion, e_out);
                   // one reciprocal instead of two FP64 divisions (each ~30 instructions; agrees to an ulp)
                   const double rsum = __drcp_rn(delta_plus + delta_minus);
                   const double wm = delta_plus * rsum, wp = delta_minus * rsum;
@@ -426,8 +436,10 @@ __global__ void __launch_bounds__(DGG_THREADS)
                   }
                 } else { // GDTB_INT_IPDG_INNER_PENALTY, ipdg.hh:149-170
                   const double weight = (delta_plus * delta_minus) * __drcp_rn(delta_plus + delta_minus);
-                  const double penalty = ((SW ? p.sw.pen_prefactor : in.prefactor) * weight)
-                                         * __drcp_rn(dg_face_h<D>(SW ? p.sw.pen_hI : in.hI_kind, h, k, h_in, h_out, true));
+                  const double penalty =
+                      SW ? (p.sw.pen_prefactor * weight)
+                               * dg_inv_face<D>(h, hinv, k, h_in, h_out, true, p.sw.pen_hI == GDTB_HI_VOLUME)
+                         : (in.prefactor * weight) * __drcp_rn(dg_face_h<D>(in.hI_kind, h, k, h_in, h_out, true));
 #pragma unroll
                   for (int jk = 0; jk < 2; ++jk) {
                     const double vj_in = T.pe[1][jk], vj_out = T.pe[0][jk];
@@ -488,8 +500,10 @@ __global__ void __launch_bounds__(DGG_THREADS)
                     ca[jk] += -1.0 * (SW ? p.sw.bnd_prefactor : in.prefactor) * vj * fi;
                   }
                 } else { // GDTB_INT_IPDG_BOUNDARY_PENALTY, ipdg.hh:276-281
-                  const double penalty = ((SW ? p.sw.bndpen_prefactor : in.prefactor) * (SW ? dg_sw(p.sw.bnd_weight, e) : dg_coef(in.weight, e)))
-                                         * __drcp_rn(dg_face_h<D>(SW ? p.sw.bndpen_hI : in.hI_kind, h, k, h[k], h[k], false));
+                  const double penalty =
+                      SW ? (p.sw.bndpen_prefactor * dg_sw(p.sw.bnd_weight, e))
+                               * dg_inv_face<D>(h, hinv, k, h[k], h[k], false, p.sw.bndpen_hI == GDTB_HI_VOLUME)
+                         : (in.prefactor * dg_coef(in.weight, e)) * __drcp_rn(dg_face_h<D>(in.hI_kind, h, k, h[k], h[k], false));
 #pragma unroll
                   for (int jk = 0; jk < 2; ++jk)
                     ca[jk] += penalty * T.pe[s][jk] * vi;

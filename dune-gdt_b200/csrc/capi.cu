@@ -2415,6 +2415,10 @@ static int assemble_impl(gdtb_matop* op, gdtb_vecfun* fun, int mode, bool synchr
       p.sw.s_bnd = forms[2].scaling;
       p.sw.pen_hI = forms[1].terms[1].hI_kind;
       p.sw.bndpen_hI = forms[2].terms[1].hI_kind;
+      const auto same = [](const DgGatherParams::SwFn& a, const DgGatherParams::SwFn& b) {
+        return a.data == b.data && (a.data || a.c == b.c);
+      };
+      p.sw.coup_same = same(p.sw.coup_kappa, p.sw.coup_weight) && same(p.sw.coup_kappa, p.sw.pen_weight) ? 1 : 0;
     }
     if (p.fast)
       GDTB_TRY(q1_axis_tables(op->ctx, op->grid, p.axis_tab, p.axis_tab_inv));

@@ -358,6 +358,7 @@ struct DgGatherParams
     double coup_prefactor, pen_prefactor, bnd_prefactor, bndpen_prefactor;
     double s_elem, s_coup, s_bnd; // the forms' scalings
     int pen_hI, bndpen_hI;
+    int coup_same; // coup_kappa, coup_weight and pen_weight are the same function (kappa = omega): one load per cell
   } sw;
   unsigned long long magic[2]; // floor(2^64 / n_k) + 1 for the element-index decode (0 when n_k == 1)
   // element-owned rows: this process produces the rows of the elements [e_begin, e_end) (a slab of element layers),

@@ -329,12 +329,34 @@ def swipdg(kappa=1.0, omega=1.0, sigma_in=8.0, sigma_d=14.0, hI=D.HI_VOLUME, s=1
     return element, coupling, boundary
 
 
+def swipdg_driver_order(kappa, omega, sigma_in=8.0, sigma_d=14.0, hI=D.HI_VOLUME, s=1.0, scaling=1.0):
+    """the SWIPDG operator exactly as the reference's drivers append it (examples/adaptive_elliptic_swipdg.cc:230-251):
+    {Laplace}, {inner coupling, inner penalty}, {Dirichlet coupling, boundary penalty} -- the structure the factorised DG
+    kernel specialises on when the coefficients are element-wise (DgGatherParams::swip)"""
+    element = D.form(D.integrand(D.INT_LAPLACE, diffusion=kappa), scaling=scaling)
+    coupling = D.form([
+        D.integrand(D.INT_IPDG_INNER_COUPLING, diffusion=kappa, weight=omega, prefactor=s),
+        D.integrand(D.INT_IPDG_INNER_PENALTY, weight=omega, prefactor=sigma_in, hI_kind=hI),
+    ], scaling=scaling)
+    boundary = D.form([
+        D.integrand(D.INT_IPDG_DIRICHLET_COUPLING, diffusion=kappa, prefactor=s),
+        D.integrand(D.INT_IPDG_BOUNDARY_PENALTY, weight=omega, prefactor=sigma_d, hI_kind=hI),
+    ], scaling=scaling)
+    return element, coupling, boundary
+
+
 def swipdg_cases():
     out = []
     for n in ([6], [8, 8], [5, 3], [4, 3, 2]):
         d = len(n)
         kt = np.diag(np.arange(1, d + 1, dtype=float)) + 0.1
+        kap = rng_elem(n, seed=21)
         out += [
+            # kappa = omega from ONE array (one load per cell), two arrays, a constant omega; both h_I conventions
+            ("driver-order-elem-kappa-is-omega", n, 1, swipdg_driver_order(D.fn_elem(kap), D.fn_elem(kap))),
+            ("driver-order-elem-kappa-omega", n, 1, swipdg_driver_order(D.fn_elem(kap), D.fn_elem(rng_elem(n, seed=22)), scaling=0.75)),
+            ("driver-order-elem-kappa-const-omega-diameter", n, 1,
+             swipdg_driver_order(D.fn_elem(kap), 2.0, sigma_in=16.0, sigma_d=16.0, hI=D.HI_DIAMETER, s=-1.0)),
             ("esv2007", n, 1, swipdg()),
             ("example-sigma16-diameter", n, 1, swipdg(sigma_in=16.0, sigma_d=16.0, hI=D.HI_DIAMETER)),
             ("nipdg", n, 1, swipdg(s=-1.0)),
