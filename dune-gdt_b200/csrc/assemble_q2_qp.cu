@@ -88,45 +88,6 @@ __device__ __forceinline__ void bulk_load_g2s(double* sdst, const double* gsrc, 
                : "memory");
 }
 
-// CSR positions of one plane of a row: column groups in ascending global index (codim ascending, shift bitset
-// ascending), each lexicographic with x fastest (see assemble_q2_gather.cu::q2_row_plane)
-template <int SX, int SY, int AYN>
-__device__ __forceinline__ void xf_scatter_plane(const AxisRuntime& ax, const AxisRuntime& ay, const AxisRuntime& al,
-                                                 const int pl_par, const int idx_l, const double (&acc)[AYN][SX ? 3 : 5],
-                                                 double* __restrict__ row)
-{
-  using BX = AxisBox<SX>;
-  using BY = AxisBox<SY>;
-  int base[4];
-  {
-    int all[8];
-    int running = 0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int s = q2_group_order(3, r);
-      all[s] = running;
-      running += ax.n[s & 1] * ay.n[(s >> 1) & 1] * al.n[(s >> 2) & 1];
-    }
-#pragma unroll
-    for (int sxy = 0; sxy < 4; ++sxy)
-      base[sxy] = pl_par ? all[sxy | 4] : all[sxy];
-  }
-#pragma unroll
-  for (int a = 0; a < BY::A; ++a) {
-    if (!ay.valid[a])
-      continue;
-    const int py = BY::parity(a);
-#pragma unroll
-    for (int b = 0; b < BX::A; ++b) {
-      if (!ax.valid[b])
-        continue;
-      const int px = BX::parity(b);
-      row[base[px | (py << 1)] + (idx_l * ay.n[py] + ay.idx[a]) * ax.n[px] + ax.idx[b]] = acc[a][b];
-    }
-  }
-}
-
-// one line kind (SY, SL): the whole per-item work of a warp (= one plane slot)
 template <int M, int KIND, int SY, int SL>
 __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const int cl, const int c0, const int slot,
                                         const double* __restrict__ coef_s, const int (&line_shift)[4],
@@ -149,14 +110,10 @@ __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const i
   axis_setup<SL>(al, cl, Nl, g.lo[2], g.h[2]);
   // the plane (uniform over the warp)
   bool valid_l = false;
-  int pl_par = 0, idx_l = 0;
 #pragma unroll
   for (int a = 0; a < BL::A; ++a)
-    if (a == slot) {
-      pl_par = BL::parity(a);
-      idx_l = al.idx[a];
+    if (a == slot)
       valid_l = al.valid[a];
-    }
   if (!valid_l)
     return;
   const bool elem_ok = c >= 0 && c < Nx;
@@ -285,17 +242,14 @@ __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const i
   if (lane == 0 || c > Nx)
     return;
   const int s0 = (SY << 1) | (SL << 2);
+  // scatter through the closed-form positions shared with the per-row kernels (interior rows: compile-time offsets)
   {
-    AxisRuntime ax;
-    axis_setup<0>(ax, c, Nx, g.lo[0], g.h[0]);
     double* row = stage0 + int(q2_row_offset<3>(g, p.rg[s0], c, cy, cl) - off0a);
-    xf_scatter_plane<0, SY, AYN>(ax, ay, al, pl_par, idx_l, accV, row);
+    q2_scatter_plane<3, 0, SY, SL>(g, 2 * c, 2 * cy + SY, 2 * cl + SL, slot, accV, row);
   }
   if (c < Nx) {
-    AxisRuntime ax;
-    axis_setup<1>(ax, c, Nx, g.lo[0], g.h[0]);
     double* row = stage1 + int(q2_row_offset<3>(g, p.rg[s0 | 1], c, cy, cl) - off1a);
-    xf_scatter_plane<1, SY, AYN>(ax, ay, al, pl_par, idx_l, accM, row);
+    q2_scatter_plane<3, 1, SY, SL>(g, 2 * c + 1, 2 * cy + SY, 2 * cl + SL, slot, accM, row);
   }
 }
 
@@ -349,26 +303,6 @@ __global__ void XF_KERNEL_ATTR
     const int cy = int(t % p.lines_y[k]);
     const int cl = int(p.cl_lo[k] + t / p.lines_y[k]);
     const int c0 = chunk * XF_ELEMS;
-    const int s0 = (sy << 1) | (sl << 2);
-    const Q2RowGroup& rg0 = p.rg[s0];
-    const Q2RowGroup& rg1 = p.rg[s0 | 1];
-    // the two CSR segments of the chunk: vertex rows c0 .. c0 + n0 - 1, mid rows c0 .. c0 + n1 - 1
-    const int n0 = min(XF_ELEMS, Nx + 1 - c0), n1 = min(XF_ELEMS, Nx - c0);
-    const long long lex0 = c0 + (long long)rg0.ex * (cy + (long long)rg0.ey * cl);
-    const long long lex1 = c0 + (long long)rg1.ex * (cy + (long long)rg1.ey * cl);
-    const long long off0a = q2_row_offset<3>(g, rg0, c0, cy, cl), off0b = xf_offset_of_lex(g, rg0, lex0 + n0);
-    long long off1a = 0, off1b = 0;
-    if (n1 > 0) {
-      off1a = q2_row_offset<3>(g, rg1, c0, cy, cl);
-      off1b = xf_offset_of_lex(g, rg1, lex1 + n1);
-    }
-    const long long start0 = rg0.value_begin + off0a, start1 = rg1.value_begin + off1a;
-    const int seg0 = int(off0b - off0a), seg1 = int(off1b - off1a);
-    const int phase0 = int((reinterpret_cast<unsigned long long>(values + start0) >> 3) & 1ULL);
-    const int phase1 = int((reinterpret_cast<unsigned long long>(values + start1) >> 3) & 1ULL);
-    double* stage0 = stage + phase0;
-    double* stage1 = stage + XF_STAGE0 + phase1;
-
     // ---- coefficient stream: the element lines (o_y, o_l) of the chunk, elements c0 - 1 .. c0 + 30 ---------------
     const int ney = sy ? 1 : 2, nel = sl ? 1 : 2;
     const int cb = max(c0 - 1, 0), ce = min(c0 + XF_ELEMS, Nx);
@@ -421,6 +355,27 @@ __global__ void XF_KERNEL_ATTR
       for (int i = threadIdx.x; i < (ce - cb) * NQ; i += blockDim.x)
         dst[i] = __ldg(src + i);
     }
+    // (the CSR segments of the chunk are worked out HERE, while the bulk loads issued above are in flight)
+    const int s0 = (sy << 1) | (sl << 2);
+    const Q2RowGroup& rg0 = p.rg[s0];
+    const Q2RowGroup& rg1 = p.rg[s0 | 1];
+    // the two CSR segments of the chunk: vertex rows c0 .. c0 + n0 - 1, mid rows c0 .. c0 + n1 - 1
+    const int n0 = min(XF_ELEMS, Nx + 1 - c0), n1 = min(XF_ELEMS, Nx - c0);
+    const long long lex0 = c0 + (long long)rg0.ex * (cy + (long long)rg0.ey * cl);
+    const long long lex1 = c0 + (long long)rg1.ex * (cy + (long long)rg1.ey * cl);
+    const long long off0a = q2_row_offset<3>(g, rg0, c0, cy, cl), off0b = xf_offset_of_lex(g, rg0, lex0 + n0);
+    long long off1a = 0, off1b = 0;
+    if (n1 > 0) {
+      off1a = q2_row_offset<3>(g, rg1, c0, cy, cl);
+      off1b = xf_offset_of_lex(g, rg1, lex1 + n1);
+    }
+    const long long start0 = rg0.value_begin + off0a, start1 = rg1.value_begin + off1a;
+    const int seg0 = int(off0b - off0a), seg1 = int(off1b - off1a);
+    const int phase0 = int((reinterpret_cast<unsigned long long>(values + start0) >> 3) & 1ULL);
+    const int phase1 = int((reinterpret_cast<unsigned long long>(values + start1) >> 3) & 1ULL);
+    double* stage0 = stage + phase0;
+    double* stage1 = stage + XF_STAGE0 + phase1;
+
     if (total_bytes > 0) {
       mbar_wait(&bar, parity);
       parity ^= 1;

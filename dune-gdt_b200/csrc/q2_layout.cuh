@@ -243,5 +243,101 @@ __device__ __forceinline__ constexpr int q2_group_order(int D, int rank)
                 : (rank == 0 ? 3 : rank == 1 ? 1 : rank == 2 ? 2 : 0);
 }
 
+// number of box offsets a in [lo, hi] with a & 1 == par
+__device__ __forceinline__ int q2_count_par(int lo, int hi, int par)
+{
+  const int first = lo + ((lo ^ par) & 1);
+  return first <= hi ? ((hi - first) >> 1) + 1 : 0;
+}
+
+// writes the (a_y, a_x) plane of a row into its CSR positions (closed forms; interior rows: compile-time offsets)
+template <int D, int SX, int SY, int SL>
+__device__ __forceinline__ void q2_scatter_plane(const GridDev& g, const int px, const int py, const int pl, const int slot,
+                                                 const double (&acc)[D == 3 ? AxisBox<SY>::A : 1][AxisBox<SX>::A],
+                                                 double* __restrict__ row)
+{
+  using BX = AxisBox<SX>;
+  using BY = AxisBox<SY>;
+  using BL = AxisBox<SL>;
+  constexpr int last = D - 1;
+  const int Nx = (int)g.n[0], Ny = D == 3 ? (int)g.n[1] : 1, Nl = (int)g.n[last];
+  constexpr int AX = BX::A, AY = D == 3 ? BY::A : 1, AL = BL::A;
+  // parity of the lattice point at box offset a is a & 1 (S + R = 2 for both parities); the column groups of a row
+  // come in ascending global index (codim ascending, shift ascending), each lexicographic with x fastest
+  const bool interior = px >= BX::R && px + BX::R <= 2 * Nx && (D == 2 || (py >= BY::R && py + BY::R <= 2 * Ny))
+                        && pl >= BL::R && pl + BL::R <= 2 * Nl;
+  const int parl = slot & 1;
+  if (interior) {
+    // unclipped box: every count and group start is a compile-time number, only the plane is a run-time choice
+    constexpr int NX[2] = {(AX + 1) / 2, AX / 2}, NY[2] = {D == 3 ? (AY + 1) / 2 : 1, D == 3 ? AY / 2 : 0};
+    constexpr int NL[2] = {(AL + 1) / 2, AL / 2};
+    int start_[2][1 << (D - 1)]; // [plane parity][sx | sy << 1]
+    {
+      int running = 0;
+#pragma unroll
+      for (int r = 0; r < (1 << D); ++r) {
+        const int s = q2_group_order(D, r);
+        const int sx = s & 1, sy = D == 3 ? (s >> 1) & 1 : 0, sl = (s >> (D - 1)) & 1;
+        start_[sl][s & ((1 << (D - 1)) - 1)] = running;
+        running += NX[sx] * (D == 3 ? NY[sy] : 1) * NL[sl];
+      }
+    }
+    const int idx_l = slot >> 1;
+    double* plane[1 << (D - 1)];
+#pragma unroll
+    for (int sxy = 0; sxy < (1 << (D - 1)); ++sxy) {
+      const int sx = sxy & 1, sy = D == 3 ? sxy >> 1 : 0;
+      plane[sxy] = row + (parl ? start_[1][sxy] : start_[0][sxy]) + idx_l * (NX[sx] * (D == 3 ? NY[sy] : 1));
+    }
+#pragma unroll
+    for (int a = 0; a < AY; ++a)
+#pragma unroll
+      for (int b = 0; b < AX; ++b)
+        plane[(b & 1) | (D == 3 ? (a & 1) << 1 : 0)][(a >> 1) * NX[b & 1] + (b >> 1)] = acc[a][b];
+    return;
+  }
+
+  // clipped box at the grid boundary: offsets [lo, hi] are inside the lattice
+  const int xlo = max(0, BX::R - px), xhi = BX::A - 1 - max(0, px + BX::R - 2 * Nx);
+  const int ylo = D == 3 ? max(0, BY::R - py) : 0, yhi = D == 3 ? BY::A - 1 - max(0, py + BY::R - 2 * Ny) : 0;
+  const int llo = max(0, BL::R - pl), lhi = BL::A - 1 - max(0, pl + BL::R - 2 * Nl);
+  const int nx0 = q2_count_par(xlo, xhi, 0), nx1 = q2_count_par(xlo, xhi, 1);
+  const int ny0 = D == 3 ? q2_count_par(ylo, yhi, 0) : 1, ny1 = D == 3 ? q2_count_par(ylo, yhi, 1) : 0;
+  const int nl0 = q2_count_par(llo, lhi, 0), nl1 = q2_count_par(llo, lhi, 1);
+  const int idx_l = (slot - llo) >> 1;
+  int base[1 << (D - 1)];
+  {
+    int running = 0;
+#pragma unroll
+    for (int r = 0; r < (1 << D); ++r) {
+      const int s = q2_group_order(D, r);
+      const int sx = s & 1, sy = D == 3 ? (s >> 1) & 1 : 0, sl = (s >> (D - 1)) & 1;
+      if (sl == parl)
+        base[s & ((1 << (D - 1)) - 1)] = running;
+      running += (sx ? nx1 : nx0) * (D == 3 ? (sy ? ny1 : ny0) : 1) * (sl ? nl1 : nl0);
+    }
+  }
+  // entries of equal parity along x are consecutive, idx_x(b) = (b >> 1) - shift_par
+  const int shx0 = (xlo + 1) >> 1, shx1 = xlo >> 1;
+#pragma unroll
+  for (int a = 0; a < AY; ++a) {
+    if (D == 3 && (a < ylo || a > yhi))
+      continue;
+    const int pary = a & 1;
+    const int line = D == 3 ? idx_l * (pary ? ny1 : ny0) + ((a - ylo) >> 1) : idx_l;
+    double* r0 = row + base[D == 3 ? (pary << 1) : 0] + line * nx0 - shx0;
+    double* r1 = row + base[D == 3 ? (1 | (pary << 1)) : 1] + line * nx1 - shx1;
+#pragma unroll
+    for (int b = 0; b < AX; ++b) {
+      if (b < xlo || b > xhi)
+        continue;
+      if (b & 1)
+        r1[b >> 1] = acc[a][b];
+      else
+        r0[b >> 1] = acc[a][b];
+    }
+  }
+}
+
 } // namespace
 } // namespace gdtb
