@@ -527,9 +527,9 @@ __device__ __forceinline__ void q2_row_plane_sf(const Q2GatherParams& p, const i
   constexpr int last = D - 1;
   if (slot >= BL::A)
     return;
-  const int Nx = (int)g.n[0], Ny = D == 3 ? (int)g.n[1] : 1, Nl = (int)g.n[last];
+  const int Nl = (int)g.n[last];
   const int px = 2 * cx + SX, py = 2 * cy + SY, pl = 2 * cl + SL;
-  constexpr int AX = BX::A, AY = D == 3 ? BY::A : 1, AL = BL::A;
+  constexpr int AX = BX::A, AY = D == 3 ? BY::A : 1;
   // the plane must lie inside the lattice
   const int ql = pl - BL::R + slot;
   if (ql < 0 || ql > 2 * Nl)
@@ -680,31 +680,6 @@ __device__ __forceinline__ void q2_dispatch(const Q2GatherParams& p, const int c
     q2_row_plane_sf<D, SX, SY, SL, false>(p, cx, cy, cl, slot, row);
   else
     q2_row_plane<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
-}
-
-// entries along x of the rows before row c of a lattice line (q2_axis_len(S, c, N).PL as an int)
-__device__ __forceinline__ int q2_xpl(const int S, const int c)
-{
-  return S ? 3 * c : 5 * c - (c > 0 ? 2 : 0);
-}
-
-// start of the lattice line (cy, cl) of a row group relative to the group's first value, and the entries w a row of the
-// line holds per entry along x: the row (cx, cy, cl) starts at line + w * q2_xpl(cx)  (q2_row_offset, regrouped)
-template <int D>
-__device__ __forceinline__ void q2_line(const GridDev& g, const Q2RowGroup& rg, const int cy, const int cl, long long& line,
-                                        int& w)
-{
-  const int s = rg.s;
-  if (D == 3) {
-    const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cy, (int)g.n[1]);
-    const Q2AxisLen Z = q2_axis_len((s >> 2) & 1, cl, (int)g.n[2]);
-    w = Y.L * Z.L;
-    line = rg.TxTy * Z.PL + (long long)((unsigned long long)(unsigned)Z.L * (rg.Tx * (unsigned)Y.PL));
-  } else {
-    const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cl, (int)g.n[1]);
-    w = Y.L;
-    line = (long long)rg.Tx * Y.PL;
-  }
 }
 
 // work-item records (Q2GatherParams::items): what the LN bookkeeping of k_q2_gather computes per item, once per grid / slab

@@ -91,8 +91,7 @@ __device__ __forceinline__ void bulk_load_g2s(double* sdst, const double* gsrc, 
 template <int M, int KIND, int SY, int SL>
 __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const int cl, const int c0, const int slot,
                                         const double* __restrict__ coef_s, const int (&line_shift)[4],
-                                        double* __restrict__ stage0, double* __restrict__ stage1, const long long off0a,
-                                        const long long off1a)
+                                        double* __restrict__ stage0, double* __restrict__ stage1, const int w_line)
 {
   using BY = AxisBox<SY>;
   using BL = AxisBox<SL>;
@@ -241,26 +240,15 @@ __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const i
   // ---- the lane's rows: vertex 2 c (c <= N_x) and mid point 2 c + 1 (c < N_x); lane 0 is the halo ----------------
   if (lane == 0 || c > Nx)
     return;
-  const int s0 = (SY << 1) | (SL << 2);
   // scatter through the closed-form positions shared with the per-row kernels (interior rows: compile-time offsets)
   {
-    double* row = stage0 + int(q2_row_offset<3>(g, p.rg[s0], c, cy, cl) - off0a);
+    double* row = stage0 + w_line * (q2_xpl(0, c) - q2_xpl(0, c0));
     q2_scatter_plane<3, 0, SY, SL>(g, 2 * c, 2 * cy + SY, 2 * cl + SL, slot, accV, row);
   }
   if (c < Nx) {
-    double* row = stage1 + int(q2_row_offset<3>(g, p.rg[s0 | 1], c, cy, cl) - off1a);
+    double* row = stage1 + w_line * (3 * (c - c0));
     q2_scatter_plane<3, 1, SY, SL>(g, 2 * c + 1, 2 * cy + SY, 2 * cl + SL, slot, accM, row);
   }
-}
-
-// CSR offset (inside its row group) of row `lex`, or the end of the owned range
-__device__ __forceinline__ long long xf_offset_of_lex(const GridDev& g, const Q2RowGroup& rg, const long long lex)
-{
-  if (lex >= rg.lex_end)
-    return rg.off_end;
-  int ux, uy, ul;
-  q2_decode<3>(rg, (unsigned)lex, ux, uy, ul);
-  return q2_row_offset<3>(g, rg, ux, uy, ul);
 }
 
 // register budget: 2 blocks x 5 warps per SM.  __launch_bounds__(160, 2) makes ptxas stop at 168 registers (it rounds
@@ -361,13 +349,19 @@ __global__ void XF_KERNEL_ATTR
     const Q2RowGroup& rg1 = p.rg[s0 | 1];
     // the two CSR segments of the chunk: vertex rows c0 .. c0 + n0 - 1, mid rows c0 .. c0 + n1 - 1
     const int n0 = min(XF_ELEMS, Nx + 1 - c0), n1 = min(XF_ELEMS, Nx - c0);
-    const long long lex0 = c0 + (long long)rg0.ex * (cy + (long long)rg0.ey * cl);
-    const long long lex1 = c0 + (long long)rg1.ex * (cy + (long long)rg1.ey * cl);
-    const long long off0a = q2_row_offset<3>(g, rg0, c0, cy, cl), off0b = xf_offset_of_lex(g, rg0, lex0 + n0);
+    // the vertex rows and the mid rows of the chunk are consecutive along x on the line (c_y, c_l) of their groups: a row
+    // starts at line + w * q2_xpl(c), w = L_y L_l entries per entry along x (q2_line); a segment that ends at the line end
+    // ends where the next line starts
+    long long line0, line1;
+    int w0, w1;
+    q2_line<3>(g, rg0, cy, cl, line0, w0);
+    q2_line<3>(g, rg1, cy, cl, line1, w1);
+    const long long off0a = line0 + w0 * q2_xpl(0, c0);
+    const long long off0b = c0 + n0 < (int)rg0.ex ? line0 + w0 * q2_xpl(0, c0 + n0) : line0 + (long long)w0 * (int)rg0.Tx;
     long long off1a = 0, off1b = 0;
     if (n1 > 0) {
-      off1a = q2_row_offset<3>(g, rg1, c0, cy, cl);
-      off1b = xf_offset_of_lex(g, rg1, lex1 + n1);
+      off1a = line1 + w1 * q2_xpl(1, c0);
+      off1b = c0 + n1 < (int)rg1.ex ? line1 + w1 * q2_xpl(1, c0 + n1) : line1 + (long long)w1 * (int)rg1.Tx;
     }
     const long long start0 = rg0.value_begin + off0a, start1 = rg1.value_begin + off1a;
     const int seg0 = int(off0b - off0a), seg1 = int(off1b - off1a);
@@ -387,10 +381,10 @@ __global__ void XF_KERNEL_ATTR
     __syncthreads();
 
     switch (k) {
-      case 0: xf_line<M, KIND, 0, 0>(p, cy, cl, c0, warp, coef_s, line_shift, stage0, stage1, off0a, off1a); break;
-      case 1: xf_line<M, KIND, 1, 0>(p, cy, cl, c0, warp, coef_s, line_shift, stage0, stage1, off0a, off1a); break;
-      case 2: xf_line<M, KIND, 0, 1>(p, cy, cl, c0, warp, coef_s, line_shift, stage0, stage1, off0a, off1a); break;
-      default: xf_line<M, KIND, 1, 1>(p, cy, cl, c0, warp, coef_s, line_shift, stage0, stage1, off0a, off1a); break;
+      case 0: xf_line<M, KIND, 0, 0>(p, cy, cl, c0, warp, coef_s, line_shift, stage0, stage1, w0); break;
+      case 1: xf_line<M, KIND, 1, 0>(p, cy, cl, c0, warp, coef_s, line_shift, stage0, stage1, w0); break;
+      case 2: xf_line<M, KIND, 0, 1>(p, cy, cl, c0, warp, coef_s, line_shift, stage0, stage1, w0); break;
+      default: xf_line<M, KIND, 1, 1>(p, cy, cl, c0, warp, coef_s, line_shift, stage0, stage1, w0); break;
     }
 
     if (ACCUMULATE) {

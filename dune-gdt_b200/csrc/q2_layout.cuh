@@ -243,6 +243,31 @@ __device__ __forceinline__ constexpr int q2_group_order(int D, int rank)
                 : (rank == 0 ? 3 : rank == 1 ? 1 : rank == 2 ? 2 : 0);
 }
 
+// entries along x of the rows before row c of a lattice line (q2_axis_len(S, c, N).PL as an int)
+__device__ __forceinline__ int q2_xpl(const int S, const int c)
+{
+  return S ? 3 * c : 5 * c - (c > 0 ? 2 : 0);
+}
+
+// start of the lattice line (cy, cl) of a row group relative to the group's first value, and the entries w a row of the
+// line holds per entry along x: the row (cx, cy, cl) starts at line + w * q2_xpl(cx)  (q2_row_offset, regrouped)
+template <int D>
+__device__ __forceinline__ void q2_line(const GridDev& g, const Q2RowGroup& rg, const int cy, const int cl, long long& line,
+                                        int& w)
+{
+  const int s = rg.s;
+  if (D == 3) {
+    const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cy, (int)g.n[1]);
+    const Q2AxisLen Z = q2_axis_len((s >> 2) & 1, cl, (int)g.n[2]);
+    w = Y.L * Z.L;
+    line = rg.TxTy * Z.PL + (long long)((unsigned long long)(unsigned)Z.L * (rg.Tx * (unsigned)Y.PL));
+  } else {
+    const Q2AxisLen Y = q2_axis_len((s >> 1) & 1, cl, (int)g.n[1]);
+    w = Y.L;
+    line = (long long)rg.Tx * Y.PL;
+  }
+}
+
 // number of box offsets a in [lo, hi] with a & 1 == par
 __device__ __forceinline__ int q2_count_par(int lo, int hi, int par)
 {
