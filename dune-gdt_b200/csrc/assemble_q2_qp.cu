@@ -51,6 +51,7 @@ struct XfParams
   int lines_y[4];
   long long cl_lo[4], cl_hi[4]; // owned lattice layers c_l along the last axis for the line kind
   int chunks;
+  unsigned long long m_chunks, m_lines[4]; // division magics floor(2^64 / d) + 1 of chunks / lines_y (q2_div)
   int line_cap;      // doubles of one staged element line
   int use_tma;       // coefficient array 16-byte aligned
   long long coef_e_end; // one past the last element index the coefficient array holds
@@ -285,11 +286,13 @@ __global__ void XF_KERNEL_ATTR
       if (item >= p.item_begin[j])
         k = j;
     const int sy = k & 1, sl = k >> 1;
-    long long t = item - p.item_begin[k];
-    const int chunk = int(t % p.chunks);
-    t /= p.chunks;
-    const int cy = int(t % p.lines_y[k]);
-    const int cl = int(p.cl_lo[k] + t / p.lines_y[k]);
+    // (32-bit divisions by run-time constants through their magics: the item count is checked at launch)
+    const unsigned t0 = (unsigned)(item - p.item_begin[k]);
+    const unsigned t1 = q2_div(t0, (unsigned)p.chunks, p.m_chunks);
+    const int chunk = int(t0 - t1 * (unsigned)p.chunks);
+    const unsigned t2 = q2_div(t1, (unsigned)p.lines_y[k], p.m_lines[k]);
+    const int cy = int(t1 - t2 * (unsigned)p.lines_y[k]);
+    const int cl = int(p.cl_lo[k] + t2);
     const int c0 = chunk * XF_ELEMS;
     // ---- coefficient stream: the element lines (o_y, o_l) of the chunk, elements c0 - 1 .. c0 + 30 ---------------
     const int ney = sy ? 1 : 2, nel = sl ? 1 : 2;
@@ -504,6 +507,11 @@ int launch_q2_qp_xfused(Launch& L, const GridDev& g, const CgQpGroup& group, con
   p.item_begin[4] = items;
   if (items <= 0)
     return GDTB_OK;
+  if (items >= (1LL << 31))
+    return fail(GDTB_ERR_NOT_IMPLEMENTED, "q2_qp_xfused: more than 2^31 work items");
+  p.m_chunks = p.chunks > 1 ? ~0ULL / (unsigned long long)p.chunks + 1 : 0;
+  for (int k = 0; k < 4; ++k)
+    p.m_lines[k] = p.lines_y[k] > 1 ? ~0ULL / (unsigned long long)p.lines_y[k] + 1 : 0;
   const int nq = group.m * group.m * group.m;
   p.line_cap = (XF_ELEMS + 3) * nq;
   p.line_cap += p.line_cap & 1;
