@@ -89,6 +89,26 @@ __device__ __forceinline__ void bulk_load_g2s(double* sdst, const double* gsrc, 
                : "memory");
 }
 
+// h and 1 / h of the element candidates of the lattice coordinate 2 c + S along one axis (axis_setup without the CSR part)
+template <int S>
+__device__ __forceinline__ void xf_axis_geometry(const int c, const int N, const double lo, const double h, double (&ha)[2],
+                                                 double (&hb)[2])
+{
+  using B = AxisBox<S>;
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    ha[o] = hb[o] = 0.;
+    if (o < B::NE) {
+      const int e = S ? c : c - 1 + o;
+      if (e >= 0 && e < N) {
+        const double ext = q2_cell_extent(lo, h, e);
+        ha[o] = ext;
+        hb[o] = __drcp_rn(ext);
+      }
+    }
+  }
+}
+
 template <int M, int KIND, int SY, int SL>
 __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const int cl, const int c0, const int slot,
                                         const double* __restrict__ coef_s, const int (&line_shift)[4],
@@ -105,15 +125,13 @@ __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const i
   const int c = c0 - 1 + lane;
   if (slot >= BL::A)
     return;
-  AxisRuntime ay, al;
-  axis_setup<SY>(ay, cy, Ny, g.lo[1], g.h[1]);
-  axis_setup<SL>(al, cl, Nl, g.lo[2], g.h[2]);
-  // the plane (uniform over the warp)
-  bool valid_l = false;
-#pragma unroll
-  for (int a = 0; a < BL::A; ++a)
-    if (a == slot)
-      valid_l = al.valid[a];
+  // geometry of the element candidates along y and the last axis (h and 1 / h, zero outside the grid); the plane must lie
+  // inside the lattice
+  double ay_ha[2], ay_hb[2], al_ha[2], al_hb[2];
+  xf_axis_geometry<SY>(cy, Ny, g.lo[1], g.h[1], ay_ha, ay_hb);
+  xf_axis_geometry<SL>(cl, Nl, g.lo[2], g.h[2], al_ha, al_hb);
+  const int ql = 2 * cl + SL - BL::R + slot;
+  const bool valid_l = ql >= 0 && ql <= 2 * Nl;
   if (!valid_l)
     return;
   const bool elem_ok = c >= 0 && c < Nx;
@@ -139,7 +157,7 @@ __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const i
     if (jl < 0 || jl > 2)
       continue; // the element candidate does not contain the plane (uniform over the warp)
     const int il = BL::local(ol);
-    const double hal = al.ha[ol], hbl = al.hb[ol];
+    const double hal = al_ha[ol], hbl = al_hb[ol];
     if (hal == 0.)
       continue; // outside the grid
     double plM[M], plK[M];
@@ -150,7 +168,7 @@ __device__ __forceinline__ void xf_line(const XfParams& p, const int cy, const i
     }
 #pragma unroll
     for (int oy = 0; oy < BY::NE; ++oy) {
-      const double hay = ay.ha[oy], hby = ay.hb[oy];
+      const double hay = ay_ha[oy], hby = ay_hb[oy];
       if (hay == 0.)
         continue;
       const int iy = BY::local(oy);
