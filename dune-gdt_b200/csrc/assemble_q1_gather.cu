@@ -211,6 +211,7 @@ constexpr int Q1G_ROWS = 256; // rows (vertices) per work item = threads per CTA
 #ifndef Q1G_ROWS_PREF
 #define Q1G_ROWS_PREF 224 // the same with the coefficient prefetch slots (k_q1_gather<..., PREF>)
 #endif
+static_assert(Q1G_ROWS_PREF < 512, "the work-item records pack the rows of an item into 9 bits");
 
 // bounded wait for a counter another GPU raises in this GPU's memory (system-scope acquire); gives up after ~1 s
 __device__ __forceinline__ void q1_wait_counter(const int* counter, int expect, int* timeout_flag)

@@ -682,6 +682,7 @@ __device__ __forceinline__ void q2_dispatch(const Q2GatherParams& p, const int c
     q2_row_plane<D, SX, SY, SL>(p, cx, cy, cl, slot, row);
 }
 
+static_assert(Q2G_THREADS / 3 < 128, "the work-item records pack the rows of an item into 7 bits");
 // work-item records (Q2GatherParams::items): what the LN bookkeeping of k_q2_gather computes per item, once per grid / slab
 template <int D>
 __global__ void __launch_bounds__(128) k_q2_items(const __grid_constant__ Q2GatherParams p, int4* __restrict__ recs)
