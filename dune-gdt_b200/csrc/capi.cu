@@ -3570,7 +3570,13 @@ int gdtb_rk_solve(gdtb_rk* ts, double* d_u, double t_end, double initial_dt, int
     const bool timing_was = L->ctx->timing.enabled;
     L->ctx->timing.enabled = false; // event records are not capturable
     const long long count_before = la.count;
-    GDTB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    {
+      const cudaError_t berr = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      if (berr != cudaSuccess) {
+        L->ctx->timing.enabled = timing_was; // (restored on this exit as well)
+        return fail(GDTB_ERR_CUDA, std::string("Runge-Kutta graph capture: ") + cudaGetErrorString(berr));
+      }
+    }
     if (ts->s == 1) {
       status = rk_enqueue_step(ts, d_u, ts->d_ui, initial_dt);
       if (status == GDTB_OK)

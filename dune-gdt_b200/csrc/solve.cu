@@ -1286,10 +1286,10 @@ int gdtb_lagrange_interpolate(gdtb_ctx* ctx, const gdtb_space* space, const gdtb
     return fail(GDTB_ERR_INVALID_ARGUMENT, "interpolate: f must be scalar");
   LoweredForm owner;
   gdtb_function ff = *f;
-  GDTB_TRY(internal_lower_function(ctx, space->grid, ff, owner));
+  // (no early return below: the device clones held by `owner` are released on every path)
+  int status = internal_lower_function(ctx, space->grid, ff, owner);
   const long long total = space->grid.ne * space->dev.nloc;
-  int status = GDTB_OK;
-  if (total > 0) {
+  if (status == GDTB_OK && total > 0) {
     k_lagrange_interpolate<<<(unsigned)((total + 255) / 256), 256, 0, ctx->launch.stream>>>(space->grid, space->dev,
                                                                                             internal_to_dev(ff), d_dofs);
     ctx->launch.count++;
