@@ -782,6 +782,19 @@ int build_q1_params(gdtb_matop* op, gdtb_vecfun* fun, Q1GatherParams& p)
 // ==================================================================================================
 // C ABI
 // ==================================================================================================
+namespace gdtb {
+// sets *flag when x holds an inf or a nan (the reference's VectorType::valid())
+__global__ void k_flag_non_finite(const double* __restrict__ x, long long n, int* __restrict__ flag)
+{
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    bad = bad || !isfinite(x[i]);
+  if (bad)
+    *flag = 1;
+}
+} // namespace gdtb
+using gdtb::k_flag_non_finite;
+
 extern "C" {
 
 const char* gdtb_last_error(void)
@@ -2949,6 +2962,26 @@ int gdtb_fvop_apply_host(gdtb_fvop* L, const double* source, double* range)
   const size_t bytes = sizeof(double) * (size_t)fv_local_size(L);
   cudaStream_t s = L->ctx->launch.stream;
   GDTB_CUDA(cudaMemcpyAsync(L->d_src, source, bytes, cudaMemcpyHostToDevice, s));
+  // apply(VectorType source, ...) of the reference refuses a source with inf / nan
+  // (operators/localizable-operator.hh:383-385); checked on the device copy.  The device-pointer entry points are the
+  // discrete-function overload, which has no such check.
+  {
+    gdtb_ctx* ctx = L->ctx;
+    const long long n = (long long)fv_local_size(L);
+    if (ctx->error_flag_pending) // an unchecked asynchronous assembly uses the same flag: report it first
+      GDTB_TRY(gdtb_ctx_synchronize(ctx));
+    GDTB_CUDA(cudaMemsetAsync(ctx->d_error_flag, 0, sizeof(int), s));
+    if (n > 0) {
+      k_flag_non_finite<<<(unsigned)std::min<long long>((n + 255) / 256, 4LL * ctx->launch.sm_count), 256, 0, s>>>(
+          L->d_src, n, ctx->d_error_flag);
+      ctx->launch.count++;
+    }
+    int flag = 0;
+    GDTB_CUDA(cudaMemcpyAsync(&flag, ctx->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GDTB_CUDA(cudaStreamSynchronize(s));
+    if (flag)
+      return fail(GDTB_ERR_OPERATOR, "source contains inf or nan! (Exceptions::operator_error, localizable-operator.hh:385)");
+  }
   GDTB_TRY(gdtb_fvop_apply(L, L->d_src, L->d_dst));
   GDTB_CUDA(cudaMemcpyAsync(range, L->d_dst, bytes, cudaMemcpyDeviceToHost, s));
   GDTB_CUDA(cudaStreamSynchronize(s));

@@ -441,6 +441,22 @@ def test_fv_apply_parity(gdt, ctx, oracle, name, n, periodic, fl):
     assert rel_err(out, ref) <= TOL
 
 
+@pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf])
+def test_fv_apply_refuses_non_finite_source(gdt, ctx, bad):
+    """apply(VectorType source, ...) throws operator_error for a source with inf / nan
+    (operators/localizable-operator.hh:383-385); afterwards the operator is still usable"""
+    gdesc = D.grid_desc(0.0, 1.0, [33, 17], 3)
+    space = make_space(gdt, ctx, gdesc, FV, 0)
+    L = gdt.make_advection_fv_operator(gdt.NumericalUpwindFlux(D.FLUX_LINEAR, [1.0, 0.5]), space)
+    u = np.random.default_rng(SEED).uniform(-1.0, 1.0, 33 * 17)
+    good = L.apply(u)
+    v = u.copy()
+    v[-1] = bad
+    with pytest.raises(gdt.capi.OperatorError):
+        L.apply(v)
+    assert np.array_equal(L.apply(u), good)
+
+
 @pytest.mark.parametrize("n,periodic", [([512, 2], 3), ([512, 7], 0), ([512, 23], 1), ([1024, 61], 3), ([1536, 9], 2),
                                         ([1024, 130], 3), ([512, 200], 0)])
 @pytest.mark.parametrize("kind,numflux", [(D.FLUX_LINEAR, D.NUMFLUX_UPWIND), (D.FLUX_BURGERS, D.NUMFLUX_UPWIND),
